@@ -1,0 +1,149 @@
+"""Flattened structure-of-arrays form of a griddy world.
+
+Every id is an item's *registration index*: the order of `add!` calls in `make-skeleton`
+(reference world.scm:21-22; Guile sees the list reversed, so index r is list position N-1-r).
+These are exactly the buffers that cross the C ABI in include/griddy_cuda.h.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+# item kinds
+K_JUNCTION, K_SEGMENT, K_SEGLANE, K_JLANE, K_OTHER = 0, 1, 2, 3, 4
+# directions / sides
+FORW, BACK = 0, 1
+# agenda item kinds
+ITEM_SLEEP, ITEM_TRAVEL = 0, 1
+# route status
+ROUTE_NONE, ROUTE_SOME, ROUTE_DONE = 0, 1, 2
+
+
+def _arr(x, dtype):
+    return np.ascontiguousarray(np.asarray(x, dtype=dtype))
+
+
+@dataclass
+class FlatNetwork:
+    """Static road network, one entry per registered item."""
+
+    kind: np.ndarray            # u8  item kind
+    lane_len: np.ndarray        # f64 lane length (spatial.scm:28-46), 0 for non-lanes
+    lane_dir: np.ndarray        # u8  segment lanes: FORW/BACK
+    lane_segment: np.ndarray    # i32 segment lanes: their segment, else -1
+    lane_out: np.ndarray        # i32 junction lanes: output segment lane (core.scm:106-111)
+    lane_junction: np.ndarray   # i32 junction lanes: their junction
+    seg_outer_forw: np.ndarray  # i32 segments: get-outer-lane for side forw (location.scm:16-24)
+    seg_outer_back: np.ndarray  # i32 segments: get-outer-lane for side back
+    # optional extras (host-side route finding / grid routing table)
+    lane_in: Optional[np.ndarray] = None       # i32 junction lanes: input segment lane
+    grid_n: int = 0                            # > 0: procedural grid with n x n junctions first
+    lane_from_j: Optional[np.ndarray] = None   # i32 segment lanes: junction they leave
+    lane_to_j: Optional[np.ndarray] = None     # i32 segment lanes: junction they reach
+    turn4: Optional[np.ndarray] = None         # i32 [n_items,4] next-hop table by heading
+    seg_reg: Optional[np.ndarray] = None       # i32 segment ordinal -> registration id
+
+    def __post_init__(self):
+        self.kind = _arr(self.kind, np.uint8)
+        self.lane_len = _arr(self.lane_len, np.float64)
+        self.lane_dir = _arr(self.lane_dir, np.uint8)
+        for name in ("lane_segment", "lane_out", "lane_junction", "seg_outer_forw", "seg_outer_back"):
+            setattr(self, name, _arr(getattr(self, name), np.int32))
+        for name in ("lane_in", "lane_from_j", "lane_to_j", "turn4", "seg_reg"):
+            v = getattr(self, name)
+            if v is not None:
+                setattr(self, name, _arr(v, np.int32))
+
+    @property
+    def n_items(self) -> int:
+        return int(self.kind.shape[0])
+
+
+@dataclass
+class FlatActors:
+    """Initial actors in `link!` order, their agendas (CSR) and, optionally, explicit routes.
+
+    route_off / route_lane: for agenda item k (global index), the (turn-onto lane) steps of the
+    route `find-route` returns for it (route.scm:48-51) — the trailing (arrive-at pos) is implied by
+    the item's destination.  None when the network's grid routing table is used instead.
+    """
+
+    loc_kind: np.ndarray    # u8  0 off-road, 1 on-road
+    container: np.ndarray   # i32 segment (off-road) or lane (on-road)
+    pos: np.ndarray         # f64 pos-param
+    side: np.ndarray        # u8  road-side-direction (off-road)
+    speed: np.ndarray       # f64 max-speed
+    speed_dt: np.ndarray    # f64 (exact->inexact (* max-speed *simulate/time-step*))
+    agenda_off: np.ndarray  # i64 [n+1]
+    item_kind: np.ndarray   # u8
+    item_sleep: np.ndarray  # i32
+    item_seg: np.ndarray    # i32
+    item_side: np.ndarray   # u8
+    item_pos: np.ndarray    # f64
+    route_off: Optional[np.ndarray] = None   # i64 [n_agenda_items+1]
+    route_lane: Optional[np.ndarray] = None  # i32
+
+    def __post_init__(self):
+        self.loc_kind = _arr(self.loc_kind, np.uint8)
+        self.container = _arr(self.container, np.int32)
+        self.pos = _arr(self.pos, np.float64)
+        self.side = _arr(self.side, np.uint8)
+        self.speed = _arr(self.speed, np.float64)
+        self.speed_dt = _arr(self.speed_dt, np.float64)
+        self.agenda_off = _arr(self.agenda_off, np.int64)
+        self.item_kind = _arr(self.item_kind, np.uint8)
+        self.item_sleep = _arr(self.item_sleep, np.int32)
+        self.item_seg = _arr(self.item_seg, np.int32)
+        self.item_side = _arr(self.item_side, np.uint8)
+        self.item_pos = _arr(self.item_pos, np.float64)
+        if self.route_off is not None:
+            self.route_off = _arr(self.route_off, np.int64)
+            self.route_lane = _arr(self.route_lane if self.route_lane is not None else [], np.int32)
+
+    @property
+    def n(self) -> int:
+        return int(self.loc_kind.shape[0])
+
+    @property
+    def n_agenda_items(self) -> int:
+        return int(self.agenda_off[-1])
+
+
+@dataclass
+class ActorState:
+    """Mutable per-actor state read back from a world (device or oracle)."""
+
+    alive: np.ndarray         # u8  0 once replaced by an equal-key insert (core.scm:173-178)
+    loc_kind: np.ndarray      # u8
+    container: np.ndarray     # i32
+    side: np.ndarray          # u8  (0 while on-road)
+    pos: np.ndarray           # f64
+    agenda_cur: np.ndarray    # i32 items popped so far
+    sleep_left: np.ndarray    # i32 head's remaining time when it is (sleep-for t), else 0
+    route_status: np.ndarray  # u8
+    route_head: np.ndarray    # i32 lane of a (turn-onto l) head, -1 for (arrive-at p), -2 no head
+    order: np.ndarray         # i32 `get-actors` order of the world (world.scm:24-30)
+
+    INT_FIELDS = ("alive", "loc_kind", "container", "side", "agenda_cur", "sleep_left",
+                  "route_status", "route_head")
+
+    def diff(self, other: "ActorState", rtol: float = 1e-9) -> list:
+        """Names of fields that differ (ints bit-exact, pos within rtol relative).
+
+        A vanished actor is in no container, so only `alive` is compared for it.
+        """
+        bad = []
+        if not np.array_equal(self.alive, other.alive):
+            return ["alive"]
+        m = self.alive.astype(bool)
+        for f in self.INT_FIELDS[1:]:
+            if not np.array_equal(getattr(self, f)[m], getattr(other, f)[m]):
+                bad.append(f)
+        if not np.array_equal(self.order, other.order):
+            bad.append("order")
+        a, b = self.pos[m], other.pos[m]
+        if not np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b))):
+            bad.append("pos")
+        return bad

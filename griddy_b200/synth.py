@@ -1,0 +1,76 @@
+"""Procedural-grid generator binding (csrc/synth.cpp): examples/procedural-grid.scm, parametrised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .flat import FlatActors, FlatNetwork
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+DEFAULT_SEED = 0x9E3779B97F4A7C15
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "csrc", "libgriddy_synth.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _LIB = C.CDLL(path)
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def grid_sizes(n: int) -> dict:
+    out = [C.c_int64() for _ in range(5)]
+    rc = _lib().synth_grid_sizes(C.c_int(n), *[C.byref(o) for o in out])
+    if rc:
+        raise ValueError(f"synth_grid_sizes({n}) -> {rc}")
+    keys = ("n_items", "n_junctions", "n_segments", "n_seg_lanes", "n_jlanes")
+    return {k: int(o.value) for k, o in zip(keys, out)}
+
+
+def grid_network(n: int, spacing: float = 150.0, origin: float = 50.0) -> FlatNetwork:
+    """n x n junction grid of procedural-grid.scm:13-67 (n = 5 there)."""
+    sz = grid_sizes(n)
+    ni = sz["n_items"]
+    kind = np.empty(ni, np.uint8); lane_len = np.empty(ni, np.float64); lane_dir = np.empty(ni, np.uint8)
+    i32 = lambda k=1: np.empty(ni * k, np.int32)
+    lane_segment, lane_out, lane_junction, so_f, so_b, lane_in, lf, lt = (i32() for _ in range(8))
+    turn4 = i32(4)
+    seg_reg = np.empty(sz["n_segments"], np.int32)
+    rc = _lib().synth_grid_network(C.c_int(n), C.c_double(spacing), C.c_double(origin), _p(kind),
+                                   _p(lane_len), _p(lane_dir), _p(lane_segment), _p(lane_out),
+                                   _p(lane_junction), _p(so_f), _p(so_b), _p(lane_in), _p(lf), _p(lt),
+                                   _p(turn4), _p(seg_reg))
+    if rc:
+        raise RuntimeError(f"synth_grid_network -> {rc}")
+    return FlatNetwork(kind, lane_len, lane_dir, lane_segment, lane_out, lane_junction, so_f, so_b,
+                       lane_in=lane_in, grid_n=n, lane_from_j=lf, lane_to_j=lt,
+                       turn4=turn4.reshape(ni, 4), seg_reg=seg_reg)
+
+
+def grid_actors(net: FlatNetwork, n_actors: int, seed: int = DEFAULT_SEED, agenda_len: int = 2) -> FlatActors:
+    """procedural-grid.scm:69-95: off-road starts, agenda alternating sleep-for / travel-to."""
+    n, L = n_actors, agenda_len
+    loc_kind = np.empty(n, np.uint8); container = np.empty(n, np.int32); pos = np.empty(n, np.float64)
+    side = np.empty(n, np.uint8); speed = np.empty(n, np.float64); speed_dt = np.empty(n, np.float64)
+    agenda_off = np.empty(n + 1, np.int64)
+    item_kind = np.empty(n * L, np.uint8); item_sleep = np.empty(n * L, np.int32)
+    item_seg = np.empty(n * L, np.int32); item_side = np.empty(n * L, np.uint8)
+    item_pos = np.empty(n * L, np.float64)
+    rc = _lib().synth_actors(C.c_int64(n), C.c_uint64(seed), C.c_int(L), C.c_int64(len(net.seg_reg)),
+                             _p(net.seg_reg), _p(loc_kind), _p(container), _p(pos), _p(side), _p(speed),
+                             _p(speed_dt), _p(agenda_off), _p(item_kind), _p(item_sleep), _p(item_seg),
+                             _p(item_side), _p(item_pos))
+    if rc:
+        raise RuntimeError(f"synth_actors -> {rc}")
+    return FlatActors(loc_kind, container, pos, side, speed, speed_dt, agenda_off, item_kind,
+                      item_sleep, item_seg, item_side, item_pos)
