@@ -1,0 +1,148 @@
+"""ctypes binding of libgriddy_cuda.so — the same symbols Guile binds with (system foreign).
+
+There is no fallback: if the CUDA library is not built, or no CUDA device is present, constructing a
+Simulation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .flat import ActorState, FlatActors, FlatNetwork
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgriddy_cuda.so")
+_LIB = None
+
+ERR_NAMES = {1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "BAD_STATE", 5: "OOM"}
+
+# every symbol include/griddy_cuda.h declares
+SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last_error",
+           "griddy_set_constants", "griddy_upload_network", "griddy_set_routing_grid",
+           "griddy_upload_actors", "griddy_step", "griddy_profile_step", "griddy_download_actors",
+           "griddy_download_occupancy", "griddy_last_step_ms", "griddy_tick", "griddy_kernel_launches")
+
+
+class GriddyCudaError(RuntimeError):
+    """Nonzero return from the C ABI; mirrors (throw 'griddy-cuda code msg) in the Guile glue."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"griddy-cuda {ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is not built (python -c 'import __graft_entry__ as g; g.build()'); "
+                               "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.griddy_last_error.restype = C.c_char_p
+        L.griddy_last_error.argtypes = [C.c_void_p]
+        L.griddy_last_step_ms.restype = C.c_double
+        L.griddy_last_step_ms.argtypes = [C.c_void_p]
+        L.griddy_tick.restype = C.c_int64
+        L.griddy_tick.argtypes = [C.c_void_p]
+        L.griddy_kernel_launches.restype = C.c_int64
+        L.griddy_kernel_launches.argtypes = [C.c_void_p]
+        L.griddy_destroy.restype = None
+        L.griddy_destroy.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Simulation:
+    """One world on one GPU: upload once, step, read back."""
+
+    def __init__(self, net: FlatNetwork, actors: FlatActors, device: int = -1,
+                 dt: float = 1.0 / 15.0, two_size: float = 10.0):
+        L = lib()
+        self.h = C.c_void_p()
+        rc = L.griddy_create(C.byref(self.h), C.c_int(device))
+        if rc:
+            self.h = None
+            raise GriddyCudaError(rc, "griddy_create failed (no CUDA device?)")
+        self.net, self.actors = net, actors
+        self._chk(L.griddy_set_constants(self.h, C.c_double(dt), C.c_double(two_size)))
+        self._chk(L.griddy_upload_network(self.h, C.c_int64(net.n_items), _p(net.kind), _p(net.lane_len),
+                                          _p(net.lane_dir), _p(net.lane_segment), _p(net.lane_out),
+                                          _p(net.lane_junction), _p(net.seg_outer_forw),
+                                          _p(net.seg_outer_back)))
+        if actors.route_off is None:
+            if not net.grid_n:
+                raise ValueError("actors carry no routes and the network has no grid routing table")
+            self._chk(L.griddy_set_routing_grid(self.h, C.c_int32(net.grid_n), _p(net.lane_from_j),
+                                                _p(net.lane_to_j), _p(net.turn4)))
+        self.upload_actors(actors)
+
+    def upload_actors(self, a: FlatActors):
+        self.actors = a
+        self._chk(lib().griddy_upload_actors(self.h, C.c_int64(a.n), _p(a.loc_kind), _p(a.container),
+                                             _p(a.pos), _p(a.side), _p(a.speed), _p(a.speed_dt),
+                                             _p(a.agenda_off), _p(a.item_kind), _p(a.item_sleep),
+                                             _p(a.item_seg), _p(a.item_side), _p(a.item_pos),
+                                             _p(a.route_off), _p(a.route_lane)))
+
+    def _chk(self, rc):
+        if rc:
+            raise GriddyCudaError(rc, lib().griddy_last_error(self.h).decode())
+
+    def step(self, n_ticks: int = 1):
+        self._chk(lib().griddy_step(self.h, C.c_int64(n_ticks)))
+
+    def profile_step(self, n_ticks: int = 1) -> dict:
+        """Per-kernel device ms summed over n_ticks (events around every launch)."""
+        ms = (C.c_double * 3)(0.0, 0.0, 0.0)
+        self._chk(lib().griddy_profile_step(self.h, C.c_int64(n_ticks), ms))
+        return {"k_advance": ms[0], "k_relink": ms[1], "k_settle": ms[2]}
+
+    @property
+    def last_step_ms(self) -> float:
+        return float(lib().griddy_last_step_ms(self.h))
+
+    @property
+    def tick(self) -> int:
+        return int(lib().griddy_tick(self.h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().griddy_kernel_launches(self.h))
+
+    def state(self, with_order: bool = True) -> ActorState:
+        n = self.actors.n
+        u8 = lambda: np.zeros(n, np.uint8)
+        i32 = lambda: np.zeros(n, np.int32)
+        alive, loc_kind, side, rs = u8(), u8(), u8(), u8()
+        container, agenda_cur, sleep_left, route_head, order = i32(), i32(), i32(), i32(), i32()
+        pos = np.zeros(n, np.float64)
+        n_order = C.c_int64(0)
+        self._chk(lib().griddy_download_actors(self.h, _p(alive), _p(loc_kind), _p(container), _p(side),
+                                               _p(pos), _p(agenda_cur), _p(sleep_left), _p(rs),
+                                               _p(route_head), _p(order) if with_order else None,
+                                               C.byref(n_order) if with_order else None))
+        return ActorState(alive, loc_kind, container, side, pos, agenda_cur, sleep_left, rs, route_head,
+                          order[: n_order.value].copy())
+
+    def occupancy(self):
+        lane_count = np.zeros(self.net.n_items, np.int32)
+        junction_count = np.zeros(self.net.n_items, np.int32)
+        self._chk(lib().griddy_download_occupancy(self.h, _p(lane_count), _p(junction_count)))
+        return lane_count, junction_count
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().griddy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

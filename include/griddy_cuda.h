@@ -1,0 +1,129 @@
+/* griddy_cuda.h — C ABI of the B200 actor-update path (libgriddy_cuda.so).
+ *
+ * The reference (eeshugerman/griddy) is pure Guile Scheme and has no FFI of its own.  The seam
+ * this library plugs into is the `update` closure of `simulate` (griddy/simulate.scm:141-153):
+ * instead of rebuilding the world and calling `advance$` per actor (simulate.scm:93-111,
+ * simulate/route.scm:53-141), the caller flattens `(make-skeleton)` + actors once, then calls
+ * griddy_step() per tick and reads state back when it wants to draw (simulate.scm:155-160).
+ * Guile binds these symbols with (system foreign) `pointer->procedure`; see INTEGRATION.md and
+ * guile/griddy/cuda.scm.  Plain pointers and sizes only: no structs by value, no C++ types.
+ *
+ * Conventions
+ *   - Every item id is its REGISTRATION INDEX: the order of `add!` calls in make-skeleton
+ *     (world.scm:21-22).  Guile's `static-items` list is consed, so list position i is id N-1-i.
+ *   - Actor ids are the order of the `link!` calls that placed them (core.scm:169-178): linking the
+ *     actors in id order must rebuild the world (later ids are nearer the head of a segment's list;
+ *     on a lane a later id replaces an earlier one with an equal pos-param).
+ *   - The caller owns every host buffer; the library copies before returning.  The library owns
+ *     all device memory.  One caller thread per context; calls block.
+ *   - Every function returns 0 on success or a GRIDDY_ERR_* code; griddy_last_error() describes it.
+ *     There is no CPU fallback: without a CUDA device griddy_create() fails with GRIDDY_ERR_CUDA.
+ */
+#ifndef GRIDDY_CUDA_H
+#define GRIDDY_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRIDDY_ABI_VERSION 1
+
+enum {
+  GRIDDY_OK = 0,
+  GRIDDY_ERR_BAD_ARG = 1,
+  GRIDDY_ERR_CUDA = 2,
+  GRIDDY_ERR_NCCL = 3,
+  GRIDDY_ERR_BAD_STATE = 4, /* the no-matching-clause / no-applicable-method cases of
+                               simulate.scm:105-111, 80-85 and location.scm:41-47 */
+  GRIDDY_ERR_OOM = 5
+};
+
+/* item kinds (road.scm:30-72) */
+enum { GRIDDY_JUNCTION = 0, GRIDDY_SEGMENT = 1, GRIDDY_SEGMENT_LANE = 2, GRIDDY_JUNCTION_LANE = 3,
+       GRIDDY_OTHER_ITEM = 4 };
+/* lane direction / road side ('forw 'back), location kind, agenda item kind, route status */
+enum { GRIDDY_FORW = 0, GRIDDY_BACK = 1 };
+enum { GRIDDY_OFF_ROAD = 0, GRIDDY_ON_ROAD = 1 };
+enum { GRIDDY_SLEEP_FOR = 0, GRIDDY_TRAVEL_TO = 1 };
+enum { GRIDDY_ROUTE_NONE = 0, GRIDDY_ROUTE_SOME = 1, GRIDDY_ROUTE_DONE = 2 };
+
+int griddy_abi_version(void);
+
+/* A context holds one world on one GPU (device = CUDA ordinal, -1 = current device). */
+int griddy_create(void** ctx, int device);
+void griddy_destroy(void* ctx);
+const char* griddy_last_error(void* ctx); /* owned by ctx, valid until the next call */
+
+/* constants.scm:34,38: dt = (exact->inexact 1/15), two_size = (* 2 *actor/size*) = 10. */
+int griddy_set_constants(void* ctx, double dt, double two_size);
+
+/* The static network of (make-skeleton), one entry per registered item.
+ *   kind           item kind
+ *   lane_len       get-length of a lane (spatial.scm:28-46), computed by the caller in fp64 — the
+ *                  device never recomputes geometry
+ *   lane_dir       segment lanes: direction
+ *   lane_segment   segment lanes: their segment                       (else -1)
+ *   lane_out       junction lanes: get-segment-lane, core.scm:106-111 (else -1)
+ *   lane_junction  junction lanes: their junction                     (else -1)
+ *   seg_outer_forw / seg_outer_back   segments: get-outer-lane for each side, location.scm:16-24 */
+int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const double* lane_len,
+                          const uint8_t* lane_dir, const int32_t* lane_segment,
+                          const int32_t* lane_out, const int32_t* lane_junction,
+                          const int32_t* seg_outer_forw, const int32_t* seg_outer_back);
+
+/* Device-side routing table for procedural grids (examples/procedural-grid.scm): the first n*n
+ * items are the junctions in row-major order; lane_from_j / lane_to_j give the junctions a segment
+ * lane leaves and reaches; turn4[4*lane + h] is the junction lane leading from `lane` onto the
+ * segment that leaves its end junction with heading h (0 +i, 1 -i, 2 +j, 3 -j), or -1.  With it,
+ * travel-to needs no uploaded routes: the next hop is dimension-ordered (i first, then j).
+ * Replaces find-route (route.scm:17-51) on synthetic grids only; a stated deviation from A*. */
+int griddy_set_routing_grid(void* ctx, int32_t n, const int32_t* lane_from_j,
+                            const int32_t* lane_to_j, const int32_t* turn4);
+
+/* The actors placed by (add-actors! world) and their agendas (actor.scm:14-37).
+ *   loc_kind/container/pos/side   location.scm:26-39 (container = segment off road, lane on road)
+ *   speed      max-speed;  speed_dt = (exact->inexact (* max-speed *simulate/time-step*))
+ *   agenda_off [n+1]  CSR offsets into the item_* arrays; item_kind sleep-for / travel-to;
+ *              item_sleep the time; item_seg/item_side/item_pos the travel-to destination
+ *   route_off  [items+1] / route_lane: for each agenda item the (turn-onto lane) steps find-route
+ *              returns for it (route.scm:48-51; the final (arrive-at pos) is implied).  Pass NULL
+ *              for both to use the grid routing table instead.
+ * Actors start with route 'none (actor.scm:19-21). */
+int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const int32_t* container,
+                         const double* pos, const uint8_t* side, const double* speed,
+                         const double* speed_dt, const int64_t* agenda_off, const uint8_t* item_kind,
+                         const int32_t* item_sleep, const int32_t* item_seg, const uint8_t* item_side,
+                         const double* item_pos, const int64_t* route_off, const int32_t* route_lane);
+
+/* Advance the world n_ticks ticks: the body of `update`, simulate.scm:144-151, n_ticks times. */
+int griddy_step(void* ctx, int64_t n_ticks);
+
+/* Read the world back (caller-allocated arrays of n entries; any pointer may be NULL).
+ *   alive        0 once an equal-key insert replaced the actor (core.scm:173-178)
+ *   agenda_cur   items popped so far;  sleep_left  the head's time if it is (sleep-for t)
+ *   route_head   lane of a (turn-onto lane) head, -1 for (arrive-at p), -2 for 'none or '()
+ *   order        the `get-actors` order of the world (world.scm:24-30); *n_order actors in it */
+int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t* container,
+                           uint8_t* side, double* pos, int32_t* agenda_cur, int32_t* sleep_left,
+                           uint8_t* route_status, int32_t* route_head, int32_t* order,
+                           int64_t* n_order);
+
+/* Actors per container (n_items entries; lanes and segments) and per junction (sum over its
+ * junction lanes — the quantity junction-full? tests, route.scm:98-104). */
+int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_count);
+
+/* Like griddy_step, but brackets every kernel launch with CUDA events on the launching stream and
+ * adds the per-kernel device time, in ms summed over the n_ticks, to kernel_ms[0..2] =
+ * {k_advance, k_relink, k_settle}.  For roofline accounting only: the events serialise launches. */
+int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms);
+
+double griddy_last_step_ms(void* ctx);       /* device time of the last griddy_step (CUDA events) */
+int64_t griddy_tick(void* ctx);              /* ticks since upload */
+int64_t griddy_kernel_launches(void* ctx);   /* kernels launched by this context so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDDY_CUDA_H */

@@ -1,0 +1,164 @@
+"""Parity of the CUDA path with the oracle, through the C ABI.  Integers bit-exact (lane id, agenda
+index, sleep counter, route status/head, actor order, occupancy counts), fp64 positions within 1e-9
+relative (ActorState.diff) — and in fact compared for exact equality as well, since every operation
+is a correctly rounded IEEE one on both sides."""
+import numpy as np
+import pytest
+
+import examples
+from griddy_b200 import core, device
+from griddy_b200.flat import FlatActors
+from helpers import compare, crowded_grid, grid_flat, simple_flat, triangle_flat, world_to_flat
+from oracle.oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def run_pair(net, actors, ticks, every=1, exact_pos=True):
+    sim, ref = device.Simulation(net, actors), Oracle(net, actors)
+    compare(sim, ref, "tick 0")
+    done = 0
+    while done < ticks:
+        k = min(every, ticks - done)
+        sim.step(k); ref.step(k)
+        done += k
+        ds = compare(sim, ref, f"tick {done}")
+        if exact_pos:
+            m = ds.alive.astype(bool)
+            assert np.array_equal(ds.pos[m], ref.state().pos[m]), f"tick {done}: pos not bit-identical"
+    return sim, ref
+
+
+def test_simple_matches_known_answer():
+    net, actors = simple_flat()
+    sim = device.Simulation(net, actors)
+    from test_oracle_kat import expected_simple
+    _, traj = expected_simple()
+    for t, (where, pos, rs, head) in enumerate(traj, start=1):
+        sim.step(1)
+        s = sim.state()
+        assert (s.loc_kind[0], s.pos[0], s.route_status[0], s.route_head[0]) == (int(where == "on"), pos, rs, head), t
+    run_pair(net, actors, 40)
+
+
+def test_triangle_10k_ticks_tick_by_tick():
+    net, actors = triangle_flat()
+    run_pair(net, actors, 10_000)
+
+
+@pytest.mark.parametrize("n,n_actors,agenda_len,seed", [(5, 80, 2, 1), (3, 200, 4, 2), (8, 3000, 4, 3)])
+def test_procedural_grid(n, n_actors, agenda_len, seed):
+    net, actors = grid_flat(n, n_actors, agenda_len=agenda_len, seed=seed)
+    run_pair(net, actors, 1500, every=25)
+
+
+@pytest.mark.parametrize("seed", [7, 8, 9])
+def test_crowded_grid_with_replacements(seed):
+    """Jammed lanes: queues, junction waits, several entrants per lane per tick, equal-key losers."""
+    net, actors = crowded_grid(4, 800, n_dest=3, seed=seed)
+    sim, ref = run_pair(net, actors, 600, every=1)
+    assert ref.vanished > 0
+    assert int(sim.state().alive.sum()) == actors.n - ref.vanished
+
+
+def test_crowded_grid_long():
+    net, actors = crowded_grid(6, 5000, n_dest=6, seed=21, agenda_len=6)
+    run_pair(net, actors, 3000, every=50)
+
+
+def test_explicit_routes_from_host_a_star():
+    """Routes uploaded as lane lists (route.scm:48-51) instead of the grid routing table."""
+    import random
+    rng = random.Random(5)
+
+    def add_actors(world):
+        segs = core.get_static_items(world, core.RoadSegment)
+        loc = lambda: core.LocationOffRoad(rng.choice(segs), rng.choice(["forw", "back"]), 0.25 + 0.5 * rng.random())
+        for _ in range(60):
+            a = core.Actor(max_speed=30 + rng.randrange(30))
+            core.link(a, loc())
+            core.agenda_push(a, ("sleep-for", rng.randrange(20)))
+            core.agenda_push(a, ("travel-to", loc()))
+            core.agenda_push(a, ("travel-to", loc()))
+    net, actors = world_to_flat(lambda: examples.grid_make_skeleton(4), add_actors)
+    assert actors.route_off is not None and len(actors.route_lane) > 0
+    run_pair(net, actors, 1200, every=10)
+
+
+def test_empty_world_and_empty_agendas():
+    net, actors = grid_flat(3, 0)
+    sim = device.Simulation(net, actors)
+    sim.step(5)
+    assert sim.state().order.size == 0
+    net, actors = grid_flat(3, 40, agenda_len=0)
+    sim, ref = run_pair(net, actors, 7)
+    assert np.array_equal(sim.state().pos, actors.pos)
+    # off-road lists reverse every tick (core.scm:169-171): after an odd count the order flips
+    o0 = device.Simulation(net, actors).state().order
+    assert not np.array_equal(o0, sim.state().order)
+
+
+def test_on_road_idle_actors_are_obstacles_and_dedupe_on_upload():
+    """Actors linked on-road with nothing to do never move but block followers (route.scm:68-74);
+    equal keys at upload keep the later link! (core.scm:173-178)."""
+    net, a = grid_flat(3, 30, agenda_len=2, seed=4)
+    lane = int(net.seg_outer_forw[a.container[0]])
+    seg = int(a.container[0])
+    n_extra = 4
+    cat = lambda x, y: np.concatenate([x, np.asarray(y, x.dtype)])
+    # everyone starts beside the same lane, behind the parked actors
+    a.container[:] = seg; a.side[:] = 0; a.pos[:] = np.linspace(0.05, 0.30, a.n)
+    acts = FlatActors(cat(a.loc_kind, [1] * n_extra), cat(a.container, [lane] * n_extra),
+                      cat(a.pos, [0.6, 0.6, 0.8, 0.95]), cat(a.side, [0] * n_extra),
+                      cat(a.speed, [80.0] * n_extra), cat(a.speed_dt, [80 / 15] * n_extra),
+                      cat(a.agenda_off, [a.agenda_off[-1]] * n_extra), a.item_kind, a.item_sleep % 5,
+                      a.item_seg, a.item_side, a.item_pos)
+    sim, ref = run_pair(net, acts, 400)
+    s = sim.state()
+    assert s.alive[a.n] == 0 and s.alive[a.n + 1] == 1
+    assert s.pos[a.n + 2] == 0.8 and s.pos[a.n + 3] == 0.95
+
+
+def test_arrive_behind_start_jumps_back():
+    """Destination on the start lane but behind the actor: the route is ((arrive-at p)) and the
+    actor lands on p in one tick, passing other residents (route.scm:81-85)."""
+    net, a = grid_flat(3, 12, agenda_len=2, seed=6)
+    seg = int(a.container[0])
+    a.container[:] = seg; a.side[:] = 1
+    a.pos[:] = np.linspace(0.30, 0.74, a.n)
+    a.item_sleep[:] = np.arange(a.n * 2)[: len(a.item_sleep)] % 3
+    a.item_seg[:] = seg; a.item_side[:] = 1
+    a.item_pos[:] = np.where(np.arange(len(a.item_pos)) % 4 == 1, 0.9, 0.28)   # half ahead, half behind
+    run_pair(net, a, 200)
+
+
+def test_begin_route_collision_same_position():
+    """Two actors beside the same lane at the same pos-param begin their routes in the same tick:
+    the later one in the segment's list replaces the other (core.scm:173-178)."""
+    net, a = grid_flat(3, 6, agenda_len=2, seed=10)
+    a.container[:] = a.container[0]; a.side[:] = 0
+    a.pos[:] = [0.4, 0.4, 0.5, 0.5, 0.5, 0.6]
+    a.item_sleep[:] = 0
+    a.item_sleep[0::2] = [3, 3, 4, 4, 4, 2]
+    sim, ref = run_pair(net, a, 100)
+    assert ref.vanished == 3
+
+
+def test_bad_state_is_reported():
+    net, a = grid_flat(3, 2, agenda_len=2)
+    lane = int(net.seg_outer_forw[a.container[0]])
+    a.loc_kind[0] = 1; a.container[0] = lane; a.item_sleep[0] = 1   # on-road actor that will travel-to
+    sim = device.Simulation(net, a)
+    with pytest.raises(device.GriddyCudaError) as e:
+        sim.step(10)
+    assert e.value.code == 4 and "begin-route$" in str(e.value)
+    with pytest.raises(RuntimeError):
+        o = Oracle(net, a); o.step(10)
+
+
+def test_bad_arguments_are_rejected():
+    net, a = grid_flat(3, 2)
+    a.container[0] = 0    # a junction
+    with pytest.raises(device.GriddyCudaError) as e:
+        device.Simulation(net, a)
+    assert e.value.code == 1
