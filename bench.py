@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — actor-updates/sec of the griddy per-tick actor update on B200.
+
+A "step" is one tick of the hot path over every actor of the world (simulate.scm:141-153).
+Workload at N = 1: BASELINE.json configs[3] — synthetic 1024x1024 procedural grid, 16M actors,
+mixed travel-to / sleep-for agendas (4 items) — the largest single-GPU configuration; its per-tick
+working set (>1.2 GB) is ten times the 126 MB L2, so every tick streams from HBM.  The world is
+first advanced `--spinup` ticks (untimed, part of set-up) so that the initial sleep-for items have
+run out and the actors are on the road, which is the expensive phase of the update.
+
+  value     device-timed throughput, state resident in HBM (CUDA events around griddy_step)
+  e2e       the same metric through the C ABI with host buffers: every step is griddy_step(1)
+            followed by griddy_download_actors into pinned host arrays (what `draw` needs,
+            simulate.scm:155-160)
+  roofline  k_advance against the measured HBM copy bandwidth, 80 algorithmic bytes per actor-update
+            (SURVEY 8(d)), timed with per-kernel CUDA events (griddy_profile_step)
+  cpu_baseline / --impl reference   the CPU oracle (C++ restatement of the reference; Guile is not in
+            this image) on one host core, on a bounded sample with the same actors per segment
+
+Launch: python bench.py --gpus N --steps K --warmup W  (N>1 under torchrun, one rank per GPU).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_UPDATE = 80   # 56 mutable R+W, 8 speed, 16 compulsory gathers
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+             0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def run(self):
+        if not self.nv:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def build_world(grid, n_actors, agenda_len, seed_offset=0):
+    from griddy_b200 import synth
+    t0 = time.time()
+    net = synth.grid_network(grid)
+    actors = synth.grid_actors(net, n_actors, seed=synth.DEFAULT_SEED + seed_offset, agenda_len=agenda_len)
+    log(f"[bench] generated {grid}x{grid} grid ({net.n_items} items), {n_actors} actors in {time.time() - t0:.1f}s")
+    return net, actors
+
+
+def cpu_sample_world(args):
+    """Bounded CPU sample: a 64x64 grid with the same actors per segment and agenda shape."""
+    from griddy_b200 import synth
+    sz_full, sz = synth.grid_sizes(args.grid), synth.grid_sizes(args.cpu_grid)
+    n = max(1, int(round(args.actors * sz["n_segments"] / sz_full["n_segments"])))
+    net, actors = build_world(args.cpu_grid, n, args.agenda_len)
+    return net, actors, n
+
+
+def time_oracle(args, ticks):
+    from oracle.oracle import Oracle
+    net, actors, n = cpu_sample_world(args)
+    o = Oracle(net, actors)
+    o.step(args.spinup)
+    t0 = time.perf_counter()
+    o.step(ticks)
+    dt = time.perf_counter() - t0
+    alive = int(o.state().alive.sum())
+    return n * ticks / dt, dt, n, alive
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  Guile + Chickadee are not installed (and cannot be:
+    no network), so this is the C++ oracle port, single-threaded like the reference (readme.md:23-26)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # size the per-step sample so the whole run stays within a couple of minutes
+    ticks_per_step = 10
+    for _ in range(args.warmup):
+        pass
+    from oracle.oracle import Oracle
+    net, actors, n = cpu_sample_world(args)
+    o = Oracle(net, actors)
+    o.step(args.spinup)
+    o.step(args.warmup * ticks_per_step)
+    steps = min(args.steps, 50)
+    t0 = time.perf_counter()
+    o.step(steps * ticks_per_step)
+    dt = time.perf_counter() - t0
+    value = n * steps * ticks_per_step / dt
+    sample = (f"{args.cpu_grid}x{args.cpu_grid} grid, {n} actors (same actors per segment as the "
+              f"{args.grid}x{args.grid}/{args.actors} workload), {ticks_per_step} ticks per step after "
+              f"{args.spinup} spin-up ticks; C++ restatement of the reference, not Guile")
+    print(json.dumps({
+        "impl": "reference", "metric": "actor-updates/sec", "value": value, "unit": "actor-updates/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "actor-updates/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "actor-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"synthetic {args.grid}x{args.grid} procedural grid, {args.actors} actors, "
+                        f"{args.agenda_len}-item sleep-for/travel-to agendas, grid routing table, "
+                        f"{args.spinup} spin-up ticks",
+            "grid": args.grid, "actors_per_gpu": args.actors, "agenda_len": args.agenda_len,
+            "spinup_ticks": args.spinup, "l2": "working set per tick >> 126 MB L2 (no flush needed)",
+            "parallelism": f"{args.gpus} x independent spatial tiles" if args.gpus > 1 else "1 gpu"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="griddy_b200", choices=["griddy_b200", "reference"])
+    ap.add_argument("--grid", type=int, default=1024)
+    ap.add_argument("--actors", type=int, default=16_000_000)
+    ap.add_argument("--agenda-len", type=int, default=4)
+    ap.add_argument("--spinup", type=int, default=300)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--profile-ticks", type=int, default=50)
+    ap.add_argument("--cpu-grid", type=int, default=64)
+    ap.add_argument("--cpu-ticks", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from griddy_b200 import device
+
+    # one spatial tile per GPU; tiles are independent worlds in this round (weak scaling)
+    net, actors = build_world(args.grid, args.actors, args.agenda_len, seed_offset=rank)
+    t0 = time.time()
+    sim = device.Simulation(net, actors, device=local_rank)
+    log(f"[bench] rank {rank}: uploaded in {time.time() - t0:.1f}s")
+    sim.step(args.spinup)
+    log(f"[bench] rank {rank}: spin-up {args.spinup} ticks in {sim.last_step_ms:.1f} ms")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sim.step(args.warmup)
+    launches0 = sim.kernel_launches
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    w0 = time.perf_counter()
+    sim.step(args.steps)            # K ticks, CUDA events on the launching stream inside
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - w0
+    clocks = sampler.stop()
+    barrier()
+    dev_ms = sim.last_step_ms
+    launches = sim.kernel_launches - launches0
+    if world > 1:
+        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    total_actors = args.actors * world
+    value = total_actors * args.steps / (dev_ms * 1e-3)
+
+    # per-kernel time of the dominant kernel (events around every launch)
+    kms = sim.profile_step(args.profile_ticks)
+    adv_ms = kms["k_advance"] / args.profile_ticks
+    peak, peak_src = measured_peaks()
+    achieved = args.actors * ALGO_BYTES_PER_UPDATE / (adv_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("k_advance_dram_bytes_per_launch")
+
+    # e2e: the call a user makes per frame — step one tick, read the world back into host buffers
+    n = actors.n
+    pin = lambda dt: torch.empty(n, dtype=dt, pin_memory=True).numpy()
+    import ctypes as C
+    bufs = [pin(torch.uint8), pin(torch.uint8), pin(torch.int32), pin(torch.uint8), pin(torch.float64),
+            pin(torch.int32), pin(torch.int32), pin(torch.uint8), pin(torch.int32)]
+    d2h = sum(b.nbytes for b in bufs)
+    L = device.lib()
+    ptrs = [b.ctypes.data_as(C.c_void_p) for b in bufs]
+
+    def e2e_step():
+        sim.step(1)
+        rc = L.griddy_download_actors(sim.h, *ptrs, None, None)
+        assert rc == 0
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e_dt = time.perf_counter() - e0
+    if world > 1:
+        t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_dt = float(t.item())
+    e2e_value = total_actors * args.e2e_steps / e_dt
+    alive = int(bufs[0].sum())
+    on_road = int((bufs[0] & bufs[1]).sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, dt, n_cpu, _ = time_oracle(args, args.cpu_ticks)
+        cpu = {"value": v, "unit": "actor-updates/s", "cores": 1, "kind": "port",
+               "sample": f"{args.cpu_grid}x{args.cpu_grid} grid, {n_cpu} actors (same actors per segment), "
+                         f"{args.cpu_ticks} ticks after {args.spinup} spin-up ticks, {dt:.1f}s; C++ restatement "
+                         f"of the reference on 1 of {os.cpu_count()} host cores (the reference is single-threaded; "
+                         f"Guile is not installed)"}
+    out = {
+        "metric": "actor-updates/sec", "value": value, "unit": "actor-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": "actor-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": d2h * world,
+                "note": "griddy_step(1) + griddy_download_actors into pinned host arrays per step; the world "
+                        "is uploaded once through the same ABI before the timed region"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_advance", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_actor_update": ALGO_BYTES_PER_UPDATE,
+                     "kernel_ms_per_tick": {k: v / args.profile_ticks for k, v in kms.items()},
+                     "whole_tick_frac": value / world * ALGO_BYTES_PER_UPDATE / 1e9 / peak},
+        "cpu_baseline": cpu,
+        "world": {"alive": alive, "on_road": on_road, "wall_s_timed_region": wall},
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -488,6 +488,43 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Read-back: format the world on the device, then one copy per output array.
+
+// Ghost rule for downloads: flag every leader that shares its follower's key.
+__global__ void __launch_bounds__(256) k_flag_ghosts(Params p, int par, uint8_t* ghost) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.n) return;
+  const uint32_t st = p.st[a];
+  if ((st & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD)) return;
+  const double* pos = p.pos[par];
+  const double cur = pos[a];
+  for (int32_t x = p.ahead[a]; x >= 0 && pos[x] == cur; x = p.ahead[x]) ghost[x] = 1;
+}
+
+struct PackOut {
+  uint8_t *alive, *loc_kind, *side, *route_status;
+  int32_t *container, *agenda_cur, *sleep_left, *route_head;
+  double* pos;
+};
+
+__global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uint8_t* ghost, PackOut o) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= p.n) return;
+  const uint32_t st = p.st[a];
+  const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
+  const int32_t aux = p.aux[a];
+  if (o.alive) o.alive[a] = ((st & ST_ALIVE) && !ghost[a]) ? 1 : 0;
+  if (o.loc_kind) o.loc_kind[a] = (st & ST_ONROAD) ? 1 : 0;
+  if (o.container) o.container[a] = p.container[a];
+  if (o.side) o.side[a] = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? 1 : 0;
+  if (o.pos) o.pos[a] = p.pos[par][a];
+  if (o.agenda_cur) o.agenda_cur[a] = (int32_t)(p.agenda_cur[a] - p.agenda_off[a]);
+  if (o.sleep_left) o.sleep_left[a] = head == HEAD_SLEEP ? aux : 0;
+  if (o.route_status) o.route_status[a] = (uint8_t)rs;
+  if (o.route_head) o.route_head[a] = rs == GRIDDY_ROUTE_SOME ? aux : -2;
+}
+
 // ================================================================================================
 // Host side
 
@@ -495,6 +532,8 @@ struct Ctx {
   int device = 0;
   std::string err;
   std::vector<void*> net_allocs, actor_allocs;
+  uint8_t* d_ghost = nullptr;   // read-back staging (actor pool)
+  uint8_t* d_pack = nullptr;
   Params p{};
   bool have_net = false, have_actors = false;
   int64_t tick = 0, launches = 0;
@@ -769,6 +808,8 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   TRY(dev_alloc(c, pool, &p.ahead_new, n));
   TRY(dev_alloc(c, pool, &p.inbox_next, n));
   TRY(dev_alloc(c, pool, &p.dead_mark, n));
+  TRY(dev_alloc(c, pool, &c->d_ghost, n));
+  TRY(dev_alloc(c, pool, &c->d_pack, 32 * n));   // 4 u8 + 4 i32 + 1 f64 per actor, 8-aligned runs
   TRY(dev_alloc(c, pool, &p.movers, n));
   TRY(dev_alloc(c, pool, &p.touched, 2 * n));
   TRY(dev_alloc(c, pool, &p.counters, 4));
@@ -915,39 +956,65 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
   const Params& p = c->p;
   const int64_t n = p.n;
   const int tick = (int)c->tick;
-  std::vector<uint32_t> st(n);
-  std::vector<int32_t> cont(n), aux(n), acur(n), land_tick(n), land_lane(n);
-  std::vector<double> ps(n), land_pos(n);
-  auto get = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess; };
-  CUDA_TRY(c, get(st.data(), p.st, n * sizeof(uint32_t)));
-  CUDA_TRY(c, get(cont.data(), p.container, n * sizeof(int32_t)));
-  CUDA_TRY(c, get(aux.data(), p.aux, n * sizeof(int32_t)));
-  CUDA_TRY(c, get(acur.data(), p.agenda_cur, n * sizeof(int32_t)));
-  CUDA_TRY(c, get(ps.data(), p.pos[tick & 1], n * sizeof(double)));
-  TRY(drop_ghosts(c, st, ps));
-  for (int64_t a = 0; a < n; ++a) {
-    const uint32_t s = st[a];
-    const int head = (s >> ST_HEAD_SHIFT) & 3, rs = (s >> ST_RS_SHIFT) & 3;
-    if (alive) alive[a] = (s & ST_ALIVE) ? 1 : 0;
-    if (loc_kind) loc_kind[a] = (s & ST_ONROAD) ? 1 : 0;
-    if (container) container[a] = cont[a];
-    if (side) side[a] = (!(s & ST_ONROAD) && (s & ST_SIDE)) ? 1 : 0;
-    if (pos) pos[a] = ps[a];
-    if (agenda_cur) agenda_cur[a] = (int32_t)(acur[a] - c->h_agenda_off[a]);
-    if (sleep_left) sleep_left[a] = head == HEAD_SLEEP ? aux[a] : 0;
-    if (route_status) route_status[a] = (uint8_t)rs;
-    if (route_head) route_head[a] = rs == GRIDDY_ROUTE_SOME ? aux[a] : -2;
+  if (n == 0) {
+    if (n_order) *n_order = 0;
+    return GRIDDY_OK;
   }
+  // device-side formatting into one staging block: [pos f64][4 x i32][4 x u8], n entries each
+  const int64_t n8 = (n + 7) / 8 * 8;
+  uint8_t* base = c->d_pack;
+  PackOut o{};
+  double* d_pos = (double*)base;
+  int32_t* d_i32 = (int32_t*)(base + 8 * n);
+  uint8_t* d_u8 = base + 8 * n + 16 * n;
+  (void)n8;
+  o.pos = pos ? d_pos : nullptr;
+  o.container = container ? d_i32 : nullptr;
+  o.agenda_cur = agenda_cur ? d_i32 + n : nullptr;
+  o.sleep_left = sleep_left ? d_i32 + 2 * n : nullptr;
+  o.route_head = route_head ? d_i32 + 3 * n : nullptr;
+  o.alive = (alive || order || n_order) ? d_u8 : nullptr;
+  o.loc_kind = loc_kind ? d_u8 + n : nullptr;
+  o.side = side ? d_u8 + 2 * n : nullptr;
+  o.route_status = route_status ? d_u8 + 3 * n : nullptr;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ghost, 0, n, c->stream));
+  k_flag_ghosts<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost);
+  k_pack_state<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost, o);
+  c->launches += 2;
+  auto get = [&](void* dst, const void* src, size_t bytes) {
+    return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
+  };
+  CUDA_TRY(c, get(pos, d_pos, n * sizeof(double)));
+  CUDA_TRY(c, get(container, d_i32, n * sizeof(int32_t)));
+  CUDA_TRY(c, get(agenda_cur, d_i32 + n, n * sizeof(int32_t)));
+  CUDA_TRY(c, get(sleep_left, d_i32 + 2 * n, n * sizeof(int32_t)));
+  CUDA_TRY(c, get(route_head, d_i32 + 3 * n, n * sizeof(int32_t)));
+  CUDA_TRY(c, get(alive, d_u8, n));
+  CUDA_TRY(c, get(loc_kind, d_u8 + n, n));
+  CUDA_TRY(c, get(side, d_u8 + 2 * n, n));
+  CUDA_TRY(c, get(route_status, d_u8 + 3 * n, n));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  CUDA_TRY(c, cudaGetLastError());
   if (order || n_order) {
     // get-actors order (world.scm:24-30): containers by descending registration index, a lane's
     // actors by descending pos-param, a segment's in list order (landing stamps, see k_relink).
-    CUDA_TRY(c, get(land_tick.data(), p.land_tick, n * sizeof(int32_t)));
-    CUDA_TRY(c, get(land_lane.data(), p.land_lane, n * sizeof(int32_t)));
-    CUDA_TRY(c, get(land_pos.data(), p.land_pos, n * sizeof(double)));
+    std::vector<uint32_t> st(n);
+    std::vector<uint8_t> live(n);
+    std::vector<int32_t> cont(n), land_tick(n), land_lane(n);
+    std::vector<double> ps(n), land_pos(n);
+    auto pull = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
+    CUDA_TRY(c, pull(st.data(), p.st, n * sizeof(uint32_t)));
+    CUDA_TRY(c, pull(live.data(), d_u8, n));
+    CUDA_TRY(c, pull(cont.data(), p.container, n * sizeof(int32_t)));
+    CUDA_TRY(c, pull(ps.data(), p.pos[tick & 1], n * sizeof(double)));
+    CUDA_TRY(c, pull(land_tick.data(), p.land_tick, n * sizeof(int32_t)));
+    CUDA_TRY(c, pull(land_lane.data(), p.land_lane, n * sizeof(int32_t)));
+    CUDA_TRY(c, pull(land_pos.data(), p.land_pos, n * sizeof(double)));
     std::vector<int32_t> ord;
     ord.reserve(n);
     for (int64_t a = 0; a < n; ++a)
-      if (st[a] & ST_ALIVE) ord.push_back((int32_t)a);
+      if (live[a]) ord.push_back((int32_t)a);
     auto landed_earlier = [&](int32_t a, int32_t b, int32_t t_land) {
       if (t_land == 0) return land_lane[a] < land_lane[b];
       if (land_lane[a] != land_lane[b]) return land_lane[a] > land_lane[b];
