@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=64)
     ap.add_argument("--cpu-ticks", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reorder-period", type=int, default=64)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -204,7 +205,7 @@ def main():
     # one spatial tile per GPU; tiles are independent worlds in this round (weak scaling)
     net, actors = build_world(args.grid, args.actors, args.agenda_len, seed_offset=rank)
     t0 = time.time()
-    sim = device.Simulation(net, actors, device=local_rank)
+    sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period)
     log(f"[bench] rank {rank}: uploaded in {time.time() - t0:.1f}s")
     sim.step(args.spinup)
     log(f"[bench] rank {rank}: spin-up {args.spinup} ticks in {sim.last_step_ms:.1f} ms")
@@ -305,6 +306,7 @@ def main():
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_actor_update": ALGO_BYTES_PER_UPDATE,
                      "kernel_ms_per_tick": {k: v / args.profile_ticks for k, v in kms.items()},
+                     "reorder_period_ticks": args.reorder_period,
                      "whole_tick_frac": value / world * ALGO_BYTES_PER_UPDATE / 1e9 / peak},
         "cpu_baseline": cpu,
         "world": {"alive": alive, "on_road": on_road, "wall_s_timed_region": wall},

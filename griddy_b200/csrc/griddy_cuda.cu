@@ -9,23 +9,35 @@
 // on a lane replaces the earlier actor (core.scm:173-178), and a segment's off-road list is consed
 // (core.scm:169-171).  Both are reproduced from local data, without a global sort (see below).
 //
-// Data layout (HBM, structure of arrays, index = actor id; items by registration index)
-//   st         u32  alive | on_road | side | route status | agenda head kind | moved | stamp class
-//   container  i32  lane (on road) or segment (off road)
-//   pos[2]     f64  pos-param, ping-pong by tick parity: followers read the old buffer
-//   ahead      i32  next actor ahead on the same lane (ascending pos-param), -1 at the front
-//   delta,buf  f64  per-tick advance and tailgate buffer on the current lane, cached at lane entry
-//                   (route.scm:62-66: fl(speed*dt)*fl(1/len) and 10/len)
-//   aux        i32  sleeping: remaining time; travelling: head route step (lane, or -1 arrive-at)
-//   lane_tail  i32  per lane: rearmost actor;  occ i32 per junction: actors on its junction lanes
-// Per-lane order is kept as linked lists that change only where an actor entered or left a lane
-// this tick; nothing is O(lanes) per tick (lanes outnumber actors 1.5:1 to 4:1 on the grids).
+// Data layout (HBM, structure of arrays).  Actors live in SLOTS; a slot's number is not the actor's
+// id.  Every REORDER_PERIOD ticks the live actors are radix-sorted by (locality key of their lane or
+// segment, coarse pos-param) and all per-slot arrays are permuted (radix_sort.cuh, k_make_keys,
+// k_permute): the actors of a lane then sit next to each other in ascending pos-param, neighbouring
+// lanes sit in neighbouring cache lines, and dead actors are dropped.  Between reorders slots are
+// stable; order within a lane is carried exactly by the `ahead` pointers, so the sort only has to be
+// good for locality, never for correctness.
+//   hot, read by every on-road actor every tick
+//     st         u32  alive | on_road | side | route status | agenda head kind | moved | stamp class
+//                     | route head is (arrive-at _)
+//     ahead      i32  slot of the next actor ahead on the same lane (ascending pos-param), -1 at the front
+//     pos[2]     f64  pos-param, ping-pong by tick parity: followers read the old buffer
+//     delta,buf  f64  per-tick advance and tailgate buffer on the current lane, cached at lane entry
+//                     (route.scm:62-66: fl(speed*dt)*fl(1/len) and 10/len)
+//   cold, touched only when an actor sleeps, changes lane, or starts / ends a route
+//     aux        i32  sleeping: remaining time; travelling: head route step (lane, or -1 arrive-at)
+//     container  i32  lane (on road) or segment (off road);  arrive f64  target of (arrive-at _)
+//     agenda_cur, route_cur, id (the actor's id), land_* (landing stamp, see below)
+//   by actor id, immutable:  speed, speed_dt, agenda CSR, explicit routes
+//   by item:  lane_tail i32 rearmost actor of a lane;  occ i32 actors on a junction's lanes
+// Per-lane order changes only where an actor entered or left a lane this tick; nothing is O(lanes)
+// per tick (lanes outnumber actors 1.5:1 to 4:1 on the grids).
 //
 // Kernels per tick
-//   k_advance  one thread per actor: agenda dispatch + motion, all handlers fused.  Coalesced SoA
-//              reads, one gather for the leader's pos-param.  Actors that change lane or
-//              road-side are appended to the movers list and pushed on their target lane's inbox
-//              (warp-aggregated atomics); their lanes are marked touched.
+//   k_advance  one thread per slot: agenda dispatch + motion, all handlers fused.  Coalesced SoA
+//              reads; the leader's pos-param is a gather that the slot order keeps inside the same
+//              or a neighbouring cache line.  Actors that change lane or road-side are appended to
+//              the movers list and pushed on their target lane's inbox (warp-aggregated atomics);
+//              their lanes are marked touched.
 //   k_relink   one thread per touched lane: merges the lane's surviving residents (already in
 //              order: residents never overtake) with its sorted entrants, drops equal-key losers
 //              exactly as bbtree-set would, rewrites the ahead pointers.
@@ -55,6 +67,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -62,6 +75,7 @@
 #include <cooperative_groups.h>
 
 #include "griddy_cuda.h"
+#include "radix_sort.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -72,31 +86,40 @@ constexpr int ST_RS_SHIFT = 3;    // 2 bits: GRIDDY_ROUTE_*
 constexpr int ST_HEAD_SHIFT = 5;  // 2 bits: 0 no head, 1 sleep-for, 2 travel-to
 constexpr uint32_t ST_MOVED = 128u;    // changed lane / road side this tick (cleared by k_settle)
 constexpr uint32_t ST_CLASS_P = 256u;  // landing stamp: came from a lane visited before the segment
+constexpr uint32_t ST_ARRIVE = 512u;   // the route head is (arrive-at _): aux == HOP_ARRIVE
 constexpr int HEAD_NONE = 0, HEAD_SLEEP = 1, HEAD_TRAVEL = 2;
 constexpr int HOP_ARRIVE = -1;
 
 constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
-              DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16;
+              DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32;
+
+// device scalars (Params::scal)
+constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_COUNT = 4;
 
 struct Params {
-  // network
+  // network, by registration index
   int64_t n_items;
   const uint8_t* kind;
   const double* lane_len;
   const uint8_t* lane_dir;
   const int32_t *lane_segment, *lane_out, *lane_junction, *outer_forw, *outer_back;
+  const uint32_t* loc_key;   // locality key for the reorder (default: the registration index)
   int32_t grid_n;
   const int32_t *lane_from_j, *lane_to_j, *turn4;
   int32_t *lane_tail, *occ, *lane_mark, *inbox_head;
-  // actors
-  int64_t n;
+  // slots
+  int32_t cap;     // allocated slots
+  int32_t* scal;   // SC_*: device error bits, slots in use, live actors counted by the reorder
   uint32_t* st;
-  int32_t* container;
-  double* pos[2];
   int32_t* ahead;
+  double* pos[2];
   double *delta, *buf;
-  int32_t *aux, *agenda_cur, *route_cur;
+  int32_t *aux, *container, *agenda_cur, *route_cur, *id;
   double* arrive;
+  int32_t *land_tick, *land_lane;
+  double* land_pos;
+  // immutable, by actor id
+  int64_t n_actors;
   const double *speed, *speed_dt;
   const int64_t* agenda_off;
   const uint8_t* item_kind;
@@ -105,14 +128,11 @@ struct Params {
   const double* item_pos;
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
-  int32_t *land_tick, *land_lane;
-  double* land_pos;
-  // per-tick scratch
+  // per-tick scratch, by slot
   int32_t *mv_old, *ahead_new, *inbox_next;
   int32_t* dead_mark;   // tick+1 when the actor was found to be a ghost during `tick`
   int32_t *movers, *touched;
   int32_t* counters;   // [2 parities][2]: movers, touched lanes
-  int32_t* err;
   double dt, two_size;
 };
 
@@ -123,6 +143,8 @@ __device__ __forceinline__ int32_t agg_append(int32_t* counter) {
   if (g.thread_rank() == 0) base = atomicAdd(counter, (int32_t)g.size());
   return g.shfl(base, 0) + (int32_t)g.thread_rank();
 }
+
+__device__ __forceinline__ void dev_error(const Params& p, int bit) { atomicOr(&p.scal[SC_ERR], bit); }
 
 // location.scm:16-24 through the uploaded per-segment table
 __device__ __forceinline__ int32_t outer_lane(const Params& p, int32_t seg, uint32_t side) {
@@ -146,7 +168,7 @@ __device__ int32_t grid_next_hop(const Params& p, int32_t lane, int32_t dest) {
 }
 
 // Head of the route after the actor has reached `lane` (route.scm:48-51 evaluated lazily).
-__device__ int32_t route_head_on(const Params& p, int a, int32_t lane, int32_t item, int32_t* rc) {
+__device__ int32_t route_head_on(const Params& p, int32_t lane, int32_t item, int32_t* rc) {
   if (p.route_off) {
     const int64_t c = *rc;
     return c < p.route_off[item + 1] ? p.route_lane[c] : HOP_ARRIVE;
@@ -155,13 +177,13 @@ __device__ int32_t route_head_on(const Params& p, int a, int32_t lane, int32_t i
   if (lane == dest) return HOP_ARRIVE;
   if (p.kind[lane] == GRIDDY_JUNCTION_LANE) return p.lane_out[lane];
   const int32_t hop = grid_next_hop(p, lane, dest);
-  if (hop < 0) atomicOr(p.err, DEV_ERR_NO_ROUTE);
+  if (hop < 0) dev_error(p, DEV_ERR_NO_ROUTE);
   return hop;
 }
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
-__device__ __forceinline__ uint32_t load_head(const Params& p, int a, int32_t ac, int32_t* aux) {
-  if (ac >= p.agenda_off[a + 1]) { *aux = 0; return HEAD_NONE; }
+__device__ __forceinline__ uint32_t load_head(const Params& p, int32_t id, int32_t ac, int32_t* aux) {
+  if (ac >= p.agenda_off[id + 1]) { *aux = 0; return HEAD_NONE; }
   if (p.item_kind[ac] == GRIDDY_SLEEP_FOR) { *aux = p.item_sleep[ac]; return HEAD_SLEEP; }
   *aux = 0;
   return HEAD_TRAVEL;
@@ -178,13 +200,14 @@ __device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane,
 
 // ------------------------------------------------------------------------------------------------
 // k_advance: advance$ for every actor (simulate.scm:93-111) with route.scm:53-141 inlined.
+// `a` is a slot.  The common case — an actor on the road, not at the end of its lane — touches only
+// the hot arrays: st, ahead, pos (old, leader, new), delta, buf.
 __global__ void __launch_bounds__(256) k_advance(Params p, int tick) {
   const int par = tick & 1;
   int32_t* counters = p.counters + 2 * par;
   if (blockIdx.x == 0 && threadIdx.x < 2) p.counters[2 * (par ^ 1) + threadIdx.x] = 0;
-  const int64_t a64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a64 >= p.n) return;
-  const int a = (int)a64;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= p.scal[SC_NSLOTS]) return;
   const uint32_t st = p.st[a];
   if (!(st & ST_ALIVE)) return;
   const double* __restrict__ pos_old = p.pos[par];
@@ -192,23 +215,25 @@ __global__ void __launch_bounds__(256) k_advance(Params p, int tick) {
   const double cur = pos_old[a];
   const int head = (st >> ST_HEAD_SHIFT) & 3;
   const int rs = (st >> ST_RS_SHIFT) & 3;
+  const bool on_route = rs == GRIDDY_ROUTE_SOME;
+
+  // issue the independent loads of the common case together
+  int32_t ah = -1;
+  double lead = 0.0, dlt = 0.0, buf = 0.0;
+  if (st & ST_ONROAD) ah = p.ahead[a];
+  if (on_route) { dlt = p.delta[a]; buf = p.buf[a]; }
 
   // nearest actor ahead on the lane (bbtree-find-min's only candidate, util.scm:152-162), skipping
   // ghosts: leaders that this actor replaced with an equal key at the end of the previous tick
-  int32_t ah = -1;
-  double lead = 0.0;
-  if (st & ST_ONROAD) {
-    ah = p.ahead[a];
-    if (ah >= 0) {
-      lead = pos_old[ah];
-      if (lead == cur) {
-        do {
-          p.dead_mark[ah] = tick + 1;
-          ah = p.ahead[ah];
-          if (ah >= 0) lead = pos_old[ah];
-        } while (ah >= 0 && lead == cur);
-        mark_touched(p, p.container[a], tick, &counters[1]);
-      }
+  if (ah >= 0) {
+    lead = pos_old[ah];
+    if (lead == cur) {
+      do {
+        p.dead_mark[ah] = tick + 1;
+        ah = p.ahead[ah];
+        if (ah >= 0) lead = pos_old[ah];
+      } while (ah >= 0 && lead == cur);
+      mark_touched(p, p.container[a], tick, &counters[1]);
     }
   }
 
@@ -221,7 +246,7 @@ __global__ void __launch_bounds__(256) k_advance(Params p, int tick) {
     if (t == 0) {
       const int32_t ac = p.agenda_cur[a] + 1;
       int32_t aux;
-      const uint32_t h = load_head(p, a, ac, &aux);
+      const uint32_t h = load_head(p, p.id[a], ac, &aux);
       p.agenda_cur[a] = ac;
       p.aux[a] = aux;
       p.st[a] = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
@@ -232,116 +257,121 @@ __global__ void __launch_bounds__(256) k_advance(Params p, int tick) {
     return;
   }
   if (head != HEAD_TRAVEL) {   // simulate.scm:105-111 has no clause for these
-    atomicOr(p.err, DEV_ERR_NO_CLAUSE);
+    dev_error(p, DEV_ERR_NO_CLAUSE);
     pos_new[a] = cur;
     return;
   }
-  const int32_t item = p.agenda_cur[a];
 
+  if (on_route) {   // advance-on-route$  route.scm:137-141
+    // get-pos-param-next on the current lane (route.scm:53-74)
+    double next = __dadd_rn(cur, dlt);
+    if (ah >= 0 && lead > cur && lead <= __dadd_rn(next, buf)) next = __dsub_rn(lead, buf);
+    if (st & ST_ARRIVE) {   // route-step/arrive-at$  route.scm:76-90
+      const double target = p.arrive[a];
+      if (next >= target) {
+        const bool back = target < cur;
+        p.st[a] = (st & ~((3u << ST_RS_SHIFT) | ST_ARRIVE)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u);
+        pos_new[a] = target;
+        if (back) {   // jumped back past other residents: re-insert by key
+          const int32_t lane = p.container[a];
+          p.mv_old[a] = lane;
+          p.movers[agg_append(&counters[0])] = a;
+          enter_lane(p, a, lane, tick, &counters[1]);
+        }
+      } else {
+        pos_new[a] = next;
+      }
+      return;
+    }
+    // route-step/turn-onto$  route.scm:92-135
+    if (!(next >= 1.0)) { pos_new[a] = next; return; }
+    const int32_t target = p.aux[a];
+    if (p.kind[target] == GRIDDY_JUNCTION_LANE && p.occ[p.lane_junction[target]] > 0) {   // waiting
+      pos_new[a] = cur;
+      return;
+    }
+    const int32_t id = p.id[a];
+    const int32_t lane = p.container[a];
+    const int32_t item = p.agenda_cur[a];
+    const double speed = p.speed[id];
+    const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), speed);
+    const double time_remaining = __dsub_rn(p.dt, time_spent);
+    const double tlen = p.lane_len[target];
+    const double tinv = __ddiv_rn(1.0, tlen);
+    const double tbuf = __ddiv_rn(p.two_size, tlen);
+    double tnext = __dmul_rn(__dmul_rn(speed, time_remaining), tinv);   // (+ 0 delta)
+    int32_t x = p.lane_tail[target];
+    while (x >= 0 && !(pos_old[x] > 0.0)) x = p.ahead[x];   // smallest key in (0, ...]
+    if (x >= 0) {
+      const double tlead = pos_old[x];
+      if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
+    }
+    int32_t rc = p.route_off ? p.route_cur[a] + 1 : 0;
+    const int32_t nhop = route_head_on(p, target, item, &rc);
+    if (p.route_off) p.route_cur[a] = rc;
+    p.aux[a] = nhop;
+    p.delta[a] = __dmul_rn(p.speed_dt[id], tinv);
+    p.buf[a] = tbuf;
+    p.container[a] = target;
+    p.mv_old[a] = lane;
+    p.st[a] = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
+    pos_new[a] = tnext;
+    p.movers[agg_append(&counters[0])] = a;
+    enter_lane(p, a, target, tick, &counters[1]);
+    mark_touched(p, lane, tick, &counters[1]);
+    return;
+  }
+
+  const int32_t item = p.agenda_cur[a];
   if (rs == GRIDDY_ROUTE_NONE) {   // begin-route$  simulate.scm:80-85
-    if (st & ST_ONROAD) { atomicOr(p.err, DEV_ERR_BEGIN_ON_ROAD); pos_new[a] = cur; return; }
+    if (st & ST_ONROAD) { dev_error(p, DEV_ERR_BEGIN_ON_ROAD); pos_new[a] = cur; return; }
     const int32_t seg = p.container[a];
     const int32_t init_lane = outer_lane(p, seg, st & ST_SIDE);
     const int32_t dest_lane = outer_lane(p, p.item_seg[item], p.item_side[item]);
-    if (init_lane < 0 || dest_lane < 0) { atomicOr(p.err, DEV_ERR_NO_LANE); pos_new[a] = cur; return; }
+    if (init_lane < 0 || dest_lane < 0) { dev_error(p, DEV_ERR_NO_LANE); pos_new[a] = cur; return; }
     // off-road->on-road  location.scm:49-57
     const double init_pos = p.lane_dir[init_lane] ? __dsub_rn(1.0, cur) : cur;
     const double ipos = p.item_pos[item];
     const double dest_pos = p.lane_dir[dest_lane] ? __dsub_rn(1.0, ipos) : ipos;
     int32_t rc = p.route_off ? (int32_t)p.route_off[item] : 0;
-    const int32_t hop = route_head_on(p, a, init_lane, item, &rc);
+    const int32_t hop = route_head_on(p, init_lane, item, &rc);
     const double len = p.lane_len[init_lane];
     p.route_cur[a] = rc;
     p.arrive[a] = dest_pos;
     p.aux[a] = hop;
-    p.delta[a] = __dmul_rn(p.speed_dt[a], __ddiv_rn(1.0, len));
+    p.delta[a] = __dmul_rn(p.speed_dt[p.id[a]], __ddiv_rn(1.0, len));
     p.buf[a] = __ddiv_rn(p.two_size, len);
     p.container[a] = init_lane;
     p.mv_old[a] = ~seg;
-    p.st[a] = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) | ST_ONROAD | ST_MOVED;
+    p.st[a] = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
+              ST_ONROAD | ST_MOVED | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);
     pos_new[a] = init_pos;
     p.movers[agg_append(&counters[0])] = a;
     enter_lane(p, a, init_lane, tick, &counters[1]);
     return;
   }
 
+  // end-route$  simulate.scm:87-91   (rs == GRIDDY_ROUTE_DONE)
   const int32_t lane = p.container[a];
-  if (rs == GRIDDY_ROUTE_DONE) {   // end-route$  simulate.scm:87-91
-    if (p.kind[lane] != GRIDDY_SEGMENT_LANE) { atomicOr(p.err, DEV_ERR_END_ON_JLANE); pos_new[a] = cur; return; }
-    const int32_t seg = p.lane_segment[lane];
-    const uint32_t dir = p.lane_dir[lane];
-    const int32_t ac = item + 1;
-    int32_t aux;
-    const uint32_t h = load_head(p, a, ac, &aux);
-    p.agenda_cur[a] = ac;
-    p.aux[a] = aux;
-    p.container[a] = seg;
-    p.mv_old[a] = lane;
-    // landing stamp: where this actor sits in the segment's consed list (core.scm:169-171)
-    p.land_tick[a] = tick + 1;
-    p.land_lane[a] = lane;
-    p.land_pos[a] = cur;
-    uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P);
-    ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
-    p.st[a] = ns;
-    pos_new[a] = dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
-    p.movers[agg_append(&counters[0])] = a;
-    mark_touched(p, lane, tick, &counters[1]);
-    return;
-  }
-
-  // advance-on-route$  route.scm:137-141.  get-pos-param-next on the current lane (route.scm:53-74)
-  const double buf = p.buf[a];
-  double next = __dadd_rn(cur, p.delta[a]);
-  if (ah >= 0 && lead > cur && lead <= __dadd_rn(next, buf)) next = __dsub_rn(lead, buf);
-  const int32_t hop = p.aux[a];
-  if (hop == HOP_ARRIVE) {   // route-step/arrive-at$  route.scm:76-90
-    const double target = p.arrive[a];
-    if (next >= target) {
-      p.st[a] = (st & ~(3u << ST_RS_SHIFT)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (target < cur ? ST_MOVED : 0u);
-      pos_new[a] = target;
-      if (target < cur) {   // jumped back past other residents: re-insert by key
-        p.mv_old[a] = lane;
-        p.movers[agg_append(&counters[0])] = a;
-        enter_lane(p, a, lane, tick, &counters[1]);
-      }
-    } else {
-      pos_new[a] = next;
-    }
-    return;
-  }
-  // route-step/turn-onto$  route.scm:92-135
-  if (!(next >= 1.0)) { pos_new[a] = next; return; }
-  const int32_t target = hop;
-  if (p.kind[target] == GRIDDY_JUNCTION_LANE && p.occ[p.lane_junction[target]] > 0) {   // waiting
-    pos_new[a] = cur;
-    return;
-  }
-  const double speed = p.speed[a];
-  const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), speed);
-  const double time_remaining = __dsub_rn(p.dt, time_spent);
-  const double tlen = p.lane_len[target];
-  const double tinv = __ddiv_rn(1.0, tlen);
-  const double tbuf = __ddiv_rn(p.two_size, tlen);
-  double tnext = __dmul_rn(__dmul_rn(speed, time_remaining), tinv);   // (+ 0 delta)
-  int32_t x = p.lane_tail[target];
-  while (x >= 0 && !(pos_old[x] > 0.0)) x = p.ahead[x];   // smallest key in (0, ...]
-  if (x >= 0) {
-    const double lead = pos_old[x];
-    if (lead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(lead, tbuf);
-  }
-  int32_t rc = p.route_cur[a] + 1;
-  const int32_t nhop = route_head_on(p, a, target, item, &rc);
-  p.route_cur[a] = rc;
-  p.aux[a] = nhop;
-  p.delta[a] = __dmul_rn(p.speed_dt[a], tinv);
-  p.buf[a] = tbuf;
-  p.container[a] = target;
+  if (p.kind[lane] != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); pos_new[a] = cur; return; }
+  const int32_t seg = p.lane_segment[lane];
+  const uint32_t dir = p.lane_dir[lane];
+  const int32_t ac = item + 1;
+  int32_t aux;
+  const uint32_t h = load_head(p, p.id[a], ac, &aux);
+  p.agenda_cur[a] = ac;
+  p.aux[a] = aux;
+  p.container[a] = seg;
   p.mv_old[a] = lane;
-  p.st[a] = st | ST_MOVED;
-  pos_new[a] = tnext;
+  // landing stamp: where this actor sits in the segment's consed list (core.scm:169-171)
+  p.land_tick[a] = tick + 1;
+  p.land_lane[a] = lane;
+  p.land_pos[a] = cur;
+  uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE);
+  ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
+  p.st[a] = ns;
+  pos_new[a] = dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
   p.movers[agg_append(&counters[0])] = a;
-  enter_lane(p, a, target, tick, &counters[1]);
   mark_touched(p, lane, tick, &counters[1]);
 }
 
@@ -489,12 +519,86 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Read-back: format the world on the device, then one copy per output array.
+// Reorder: sort the live slots by (locality key of the container, coarse pos-param), permute every
+// per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
+
+// Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
+constexpr int PERM4 = 9, PERM8 = 5;
+enum { P4_ST, P4_CONTAINER, P4_AHEAD, P4_AUX, P4_AGENDA_CUR, P4_ROUTE_CUR, P4_ID, P4_LAND_TICK, P4_LAND_LANE };
+enum { P8_POS, P8_DELTA, P8_BUF, P8_ARRIVE, P8_LAND_POS };
+
+struct Permute {
+  const uint32_t* src4[PERM4];
+  uint32_t* dst4[PERM4];
+  const uint64_t* src8[PERM8];
+  uint64_t* dst8[PERM8];
+};
+
+// grid = n_pad / 256 exactly: every lane of every warp reaches the ballot
+__global__ void __launch_bounds__(256) k_make_keys(Params p, int par, uint64_t* __restrict__ keys,
+                                                    uint32_t* __restrict__ vals, uint8_t* __restrict__ tailflag) {
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  uint64_t key = ~0ull;
+  uint32_t val = 0xffffffffu;
+  bool live = false;
+  if (s < p.scal[SC_NSLOTS]) {
+    const uint32_t st = p.st[s];
+    if (st & ST_ALIVE) {
+      live = true;
+      const int32_t c = p.container[s];
+      const double x = p.pos[par][s];
+      // 16 bits of pos-param over [-0.5, 1.5): enough to keep a lane's actors in list order
+      const double q = fmin(fmax((x + 0.5) * 32768.0, 0.0), 65535.0);
+      key = ((uint64_t)p.loc_key[c] << 16) | (uint64_t)(uint32_t)q;
+      val = (uint32_t)s;
+      tailflag[s] = ((st & ST_ONROAD) && p.lane_tail[c] == s) ? 1 : 0;
+    }
+  }
+  keys[s] = key;
+  vals[s] = val;
+  const uint32_t m = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&p.scal[SC_NALIVE], __popc(m));
+}
+
+__global__ void __launch_bounds__(256) k_inverse(const uint32_t* __restrict__ vals, int n_pad, int32_t* __restrict__ newslot) {
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= n_pad) return;
+  const uint32_t old = vals[s];
+  if (old != 0xffffffffu) newslot[old] = s;
+}
+
+__global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint32_t* __restrict__ vals,
+                                                  const int32_t* __restrict__ newslot,
+                                                  const uint8_t* __restrict__ tailflag) {
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= p.scal[SC_NALIVE]) return;
+  const uint32_t old = vals[s];
+#pragma unroll
+  for (int k = 0; k < PERM4; ++k) {
+    uint32_t v = q.src4[k][old];
+    if (k == P4_AHEAD) {   // meaningful on the road only; an off-road actor's value is stale
+      if ((q.src4[P4_ST][old] & ST_ONROAD) && (int32_t)v >= 0) {
+        const int32_t nv = newslot[v];
+        if (nv < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's leader must be live
+        v = (uint32_t)nv;
+      } else {
+        v = 0xffffffffu;
+      }
+    }
+    q.dst4[k][s] = v;
+  }
+#pragma unroll
+  for (int k = 0; k < PERM8; ++k) q.dst8[k][s] = q.src8[k][old];
+  if (tailflag[old]) p.lane_tail[q.src4[P4_CONTAINER][old]] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Read-back: format the world on the device (by actor id), then one copy per output array.
 
 // Ghost rule for downloads: flag every leader that shares its follower's key.
 __global__ void __launch_bounds__(256) k_flag_ghosts(Params p, int par, uint8_t* ghost) {
-  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= p.n) return;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= p.scal[SC_NSLOTS]) return;
   const uint32_t st = p.st[a];
   if ((st & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD)) return;
   const double* pos = p.pos[par];
@@ -509,20 +613,21 @@ struct PackOut {
 };
 
 __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uint8_t* ghost, PackOut o) {
-  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= p.n) return;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= p.scal[SC_NSLOTS]) return;
   const uint32_t st = p.st[a];
+  const int32_t id = p.id[a];
   const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
   const int32_t aux = p.aux[a];
-  if (o.alive) o.alive[a] = ((st & ST_ALIVE) && !ghost[a]) ? 1 : 0;
-  if (o.loc_kind) o.loc_kind[a] = (st & ST_ONROAD) ? 1 : 0;
-  if (o.container) o.container[a] = p.container[a];
-  if (o.side) o.side[a] = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? 1 : 0;
-  if (o.pos) o.pos[a] = p.pos[par][a];
-  if (o.agenda_cur) o.agenda_cur[a] = (int32_t)(p.agenda_cur[a] - p.agenda_off[a]);
-  if (o.sleep_left) o.sleep_left[a] = head == HEAD_SLEEP ? aux : 0;
-  if (o.route_status) o.route_status[a] = (uint8_t)rs;
-  if (o.route_head) o.route_head[a] = rs == GRIDDY_ROUTE_SOME ? aux : -2;
+  if (o.alive) o.alive[id] = ((st & ST_ALIVE) && !ghost[a]) ? 1 : 0;
+  if (o.loc_kind) o.loc_kind[id] = (st & ST_ONROAD) ? 1 : 0;
+  if (o.container) o.container[id] = p.container[a];
+  if (o.side) o.side[id] = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? 1 : 0;
+  if (o.pos) o.pos[id] = p.pos[par][a];
+  if (o.agenda_cur) o.agenda_cur[id] = (int32_t)(p.agenda_cur[a] - p.agenda_off[id]);
+  if (o.sleep_left) o.sleep_left[id] = head == HEAD_SLEEP ? aux : 0;
+  if (o.route_status) o.route_status[id] = (uint8_t)rs;
+  if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? aux : -2;
 }
 
 // ================================================================================================
@@ -532,19 +637,30 @@ struct Ctx {
   int device = 0;
   std::string err;
   std::vector<void*> net_allocs, actor_allocs;
-  uint8_t* d_ghost = nullptr;   // read-back staging (actor pool)
-  uint8_t* d_pack = nullptr;
   Params p{};
   bool have_net = false, have_actors = false;
   int64_t tick = 0, launches = 0;
   double last_ms = 0.0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // slots
+  int32_t ns_host = 0;         // upper bound of the slots in use (refreshed after every step)
+  int reorder_period = 64;
+  int64_t last_reorder_tick = -1;
+  int loc_key_bits = 1;
+  uint32_t *alt4[PERM4] = {}, *cur4[PERM4] = {};   // double buffers of the permuted arrays
+  uint64_t *alt8[PERM8] = {}, *cur8[PERM8] = {};
+  uint64_t* sort_keys = nullptr;
+  uint32_t* sort_vals = nullptr;
+  rsort::Scratch sort_scratch;
+  int32_t* newslot = nullptr;
+  uint8_t* tailflag = nullptr;
+  // read-back staging
+  uint8_t* d_ghost = nullptr;
+  uint8_t* d_pack = nullptr;
   // host copies needed to format downloads
   std::vector<uint8_t> h_kind;
   std::vector<int32_t> h_lane_junction;
-  std::vector<int64_t> h_agenda_off;
-  std::vector<uint8_t> h_item_kind;
 };
 
 int fail(Ctx* c, int code, const std::string& msg) {
@@ -590,6 +706,61 @@ void free_pool(std::vector<void*>& pool) {
     if (rc_) return rc_;     \
   } while (0)
 
+int bits_for(uint32_t max_value) {   // bits that hold 0..max_value with all-ones left unused
+  int b = 1;
+  while (b < 32 && (((uint64_t)1 << b) - 1) <= max_value) ++b;
+  return b;
+}
+
+// Point Params at the current buffers of the permuted arrays.
+void bind_slot_arrays(Ctx* c, int par) {
+  Params& p = c->p;
+  p.st = c->cur4[P4_ST];
+  p.container = (int32_t*)c->cur4[P4_CONTAINER];
+  p.ahead = (int32_t*)c->cur4[P4_AHEAD];
+  p.aux = (int32_t*)c->cur4[P4_AUX];
+  p.agenda_cur = (int32_t*)c->cur4[P4_AGENDA_CUR];
+  p.route_cur = (int32_t*)c->cur4[P4_ROUTE_CUR];
+  p.id = (int32_t*)c->cur4[P4_ID];
+  p.land_tick = (int32_t*)c->cur4[P4_LAND_TICK];
+  p.land_lane = (int32_t*)c->cur4[P4_LAND_LANE];
+  p.pos[par] = (double*)c->cur8[P8_POS];
+  p.delta = (double*)c->cur8[P8_DELTA];
+  p.buf = (double*)c->cur8[P8_BUF];
+  p.arrive = (double*)c->cur8[P8_ARRIVE];
+  p.land_pos = (double*)c->cur8[P8_LAND_POS];
+}
+
+// Enqueue a reorder of the slots on the context's stream.  Runs between ticks: no actor is marked
+// moved, every inbox is empty.  `tick` is the next tick to run (its parity names the valid pos buffer).
+int reorder_slots(Ctx* c, int64_t tick) {
+  Params& p = c->p;
+  if (c->ns_host == 0) return GRIDDY_OK;
+  const int par = (int)(tick & 1);
+  const int n_tiles = (c->ns_host + rsort::TILE - 1) / rsort::TILE;
+  const int n_pad = n_tiles * rsort::TILE;
+  cudaStream_t s = c->stream;
+  CUDA_TRY(c, cudaMemsetAsync(&p.scal[SC_NALIVE], 0, sizeof(int32_t), s));
+  CUDA_TRY(c, cudaMemsetAsync(c->newslot, 0xFF, (size_t)c->ns_host * sizeof(int32_t), s));
+  k_make_keys<<<n_pad / 256, 256, 0, s>>>(p, par, c->sort_keys, c->sort_vals, c->tailflag);
+  c->launches += 1 + rsort::sort_pairs(&c->sort_keys, &c->sort_vals, n_tiles, c->loc_key_bits + 16, &c->sort_scratch, s);
+  k_inverse<<<n_pad / 256, 256, 0, s>>>(c->sort_vals, n_pad, c->newslot);
+  // the valid pos buffer is the one of parity `par`
+  c->cur8[P8_POS] = (uint64_t*)p.pos[par];
+  Permute q;
+  for (int k = 0; k < PERM4; ++k) { q.src4[k] = c->cur4[k]; q.dst4[k] = c->alt4[k]; }
+  for (int k = 0; k < PERM8; ++k) { q.src8[k] = c->cur8[k]; q.dst8[k] = c->alt8[k]; }
+  k_permute<<<n_pad / 256, 256, 0, s>>>(p, q, c->sort_vals, c->newslot, c->tailflag);
+  c->launches += 2;
+  CUDA_TRY(c, cudaMemcpyAsync(&p.scal[SC_NSLOTS], &p.scal[SC_NALIVE], sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  for (int k = 0; k < PERM4; ++k) std::swap(c->cur4[k], c->alt4[k]);
+  for (int k = 0; k < PERM8; ++k) std::swap(c->cur8[k], c->alt8[k]);
+  bind_slot_arrays(c, par);
+  c->last_reorder_tick = tick;
+  CUDA_TRY(c, cudaGetLastError());
+  return GRIDDY_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -605,12 +776,14 @@ int griddy_create(void** ctx, int device) {
   if (device < 0) cudaGetDevice(&device);
   c->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess ||
-      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      rsort::prepare() != cudaSuccess) {
     delete c;
     return GRIDDY_ERR_CUDA;
   }
   c->p.dt = 1.0 / 15.0;
   c->p.two_size = 10.0;
+  if (const char* e = getenv("GRIDDY_REORDER_PERIOD")) c->reorder_period = atoi(e);
   *ctx = c;
   return GRIDDY_OK;
 }
@@ -638,13 +811,21 @@ int griddy_set_constants(void* ctx, double dt, double two_size) {
   return GRIDDY_OK;
 }
 
+int griddy_set_reorder_period(void* ctx, int32_t ticks) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (ticks < 0) return fail(c, GRIDDY_ERR_BAD_ARG, "reorder period must be >= 0");
+  c->reorder_period = ticks;
+  return GRIDDY_OK;
+}
+
 int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const double* lane_len,
                           const uint8_t* lane_dir, const int32_t* lane_segment,
                           const int32_t* lane_out, const int32_t* lane_junction,
                           const int32_t* seg_outer_forw, const int32_t* seg_outer_back) {
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
-  if (n_items < 0 || n_items > INT32_MAX || !kind || !lane_len || !lane_dir || !lane_segment || !lane_out ||
+  if (n_items < 0 || n_items > INT32_MAX - 1 || !kind || !lane_len || !lane_dir || !lane_segment || !lane_out ||
       !lane_junction || !seg_outer_forw || !seg_outer_back)
     return fail(c, GRIDDY_ERR_BAD_ARG, "upload_network: null array or bad n_items");
   auto in_range = [&](int32_t v, int want_kind) { return v >= 0 && v < n_items && kind[v] == want_kind; };
@@ -677,6 +858,12 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   TRY(dev_upload(c, c->net_allocs, &p.lane_junction, lane_junction, n_items));
   TRY(dev_upload(c, c->net_allocs, &p.outer_forw, seg_outer_forw, n_items));
   TRY(dev_upload(c, c->net_allocs, &p.outer_back, seg_outer_back, n_items));
+  {   // default locality key: the registration index
+    std::vector<uint32_t> key((size_t)n_items);
+    for (int64_t r = 0; r < n_items; ++r) key[r] = (uint32_t)r;
+    TRY(dev_upload(c, c->net_allocs, &p.loc_key, key.data(), n_items));
+    c->loc_key_bits = bits_for((uint32_t)std::max<int64_t>(n_items, 1));
+  }
   TRY(dev_alloc(c, c->net_allocs, &p.lane_tail, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.occ, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.lane_mark, n_items));
@@ -684,6 +871,19 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   c->h_kind.assign(kind, kind + n_items);
   c->h_lane_junction.assign(lane_junction, lane_junction + n_items);
   c->have_net = true;
+  return GRIDDY_OK;
+}
+
+int griddy_set_locality_keys(void* ctx, const uint32_t* item_key) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_net || !item_key) return fail(c, GRIDDY_ERR_BAD_ARG, "set_locality_keys: no network or null keys");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  uint32_t mx = 0;
+  for (int64_t r = 0; r < c->p.n_items; ++r) mx = std::max(mx, item_key[r]);
+  if (mx == UINT32_MAX) return fail(c, GRIDDY_ERR_BAD_ARG, "locality keys must be below 2^32-1");
+  CUDA_TRY(c, cudaMemcpy((void*)c->p.loc_key, item_key, (size_t)c->p.n_items * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  c->loc_key_bits = bits_for(mx);
   return GRIDDY_OK;
 }
 
@@ -711,7 +911,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (!c->have_net) return fail(c, GRIDDY_ERR_BAD_ARG, "upload_actors before upload_network");
-  if (n < 0 || n > INT32_MAX - 1 || !loc_kind || !container || !pos || !side || !speed || !speed_dt || !agenda_off)
+  if (n < 0 || n > INT32_MAX - 2 * rsort::TILE || !loc_kind || !container || !pos || !side || !speed || !speed_dt || !agenda_off)
     return fail(c, GRIDDY_ERR_BAD_ARG, "upload_actors: null array or bad n");
   const int64_t n_agenda = agenda_off[n];
   if (n_agenda < 0 || n_agenda > INT32_MAX - 1) return fail(c, GRIDDY_ERR_BAD_ARG, "too many agenda items");
@@ -752,12 +952,14 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   free_pool(c->actor_allocs);
   c->have_actors = false;
   Params& p = c->p;
-  p.n = n;
+  p.n_actors = n;
+  const int64_t cap = (n + rsort::TILE - 1) / rsort::TILE * rsort::TILE + rsort::TILE;   // tile-padded
+  p.cap = (int32_t)cap;
   auto& pool = c->actor_allocs;
 
-  // Initial world: link! every actor in id order (core.scm:169-178).
+  // Initial world: link! every actor in id order (core.scm:169-178).  Slot = id until the first reorder.
   std::vector<uint32_t> st(n);
-  std::vector<int32_t> aux(n, 0), acur(n), ahead(n, -1), land_lane(n);
+  std::vector<int32_t> aux(n, 0), acur(n), ahead(n, -1), ident(n);
   std::vector<int32_t> lane_tail(p.n_items, -1), occ(p.n_items, 0);
   std::vector<int32_t> on_road;
   for (int64_t a = 0; a < n; ++a) {
@@ -770,7 +972,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     if (loc_kind[a]) { s |= ST_ONROAD; on_road.push_back((int32_t)a); }
     else if (side[a]) s |= ST_SIDE;
     st[a] = s;
-    land_lane[a] = (int32_t)a;   // landing stamp of the initial placement: tick 0, link! order
+    ident[a] = (int32_t)a;   // also the landing stamp of the initial placement: tick 0, link! order
   }
   // lanes: ascending pos-param; an equal key replaces the earlier actor (bbtree-set)
   std::sort(on_road.begin(), on_road.end(), [&](int32_t x, int32_t y) {
@@ -789,37 +991,63 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     prev = a;
   }
 
-  const uint32_t* d_st; const int32_t* d_i32; const double* d_f64;
-  TRY(dev_upload(c, pool, &d_st, st.data(), n)); p.st = (uint32_t*)d_st;
-  TRY(dev_upload(c, pool, &d_i32, container, n)); p.container = (int32_t*)d_i32;
-  TRY(dev_upload(c, pool, &d_f64, pos, n)); p.pos[0] = (double*)d_f64;
-  TRY(dev_upload(c, pool, &d_f64, pos, n)); p.pos[1] = (double*)d_f64;
-  TRY(dev_upload(c, pool, &d_i32, ahead.data(), n)); p.ahead = (int32_t*)d_i32;
-  TRY(dev_upload(c, pool, &d_i32, aux.data(), n)); p.aux = (int32_t*)d_i32;
-  TRY(dev_upload(c, pool, &d_i32, acur.data(), n)); p.agenda_cur = (int32_t*)d_i32;
-  TRY(dev_upload(c, pool, &d_i32, land_lane.data(), n)); p.land_lane = (int32_t*)d_i32;
-  TRY(dev_alloc(c, pool, &p.delta, n));
-  TRY(dev_alloc(c, pool, &p.buf, n));
-  TRY(dev_alloc(c, pool, &p.arrive, n));
-  TRY(dev_alloc(c, pool, &p.land_pos, n));
-  TRY(dev_alloc(c, pool, &p.route_cur, n));
-  TRY(dev_alloc(c, pool, &p.land_tick, n));
-  TRY(dev_alloc(c, pool, &p.mv_old, n));
-  TRY(dev_alloc(c, pool, &p.ahead_new, n));
-  TRY(dev_alloc(c, pool, &p.inbox_next, n));
-  TRY(dev_alloc(c, pool, &p.dead_mark, n));
-  TRY(dev_alloc(c, pool, &c->d_ghost, n));
-  TRY(dev_alloc(c, pool, &c->d_pack, 32 * n));   // 4 u8 + 4 i32 + 1 f64 per actor, 8-aligned runs
-  TRY(dev_alloc(c, pool, &p.movers, n));
-  TRY(dev_alloc(c, pool, &p.touched, 2 * n));
+  // permuted arrays: two buffers each
+  for (int k = 0; k < PERM4; ++k) {
+    TRY(dev_alloc(c, pool, &c->cur4[k], cap));
+    TRY(dev_alloc(c, pool, &c->alt4[k], cap));
+    CUDA_TRY(c, cudaMemset(c->cur4[k], 0, (size_t)cap * sizeof(uint32_t)));
+  }
+  for (int k = 0; k < PERM8; ++k) {
+    TRY(dev_alloc(c, pool, &c->cur8[k], cap));
+    TRY(dev_alloc(c, pool, &c->alt8[k], cap));
+    CUDA_TRY(c, cudaMemset(c->cur8[k], 0, (size_t)cap * sizeof(uint64_t)));
+  }
+  auto put4 = [&](int k, const void* host) { return n ? cudaMemcpy(c->cur4[k], host, (size_t)n * 4, cudaMemcpyHostToDevice) : cudaSuccess; };
+  CUDA_TRY(c, put4(P4_ST, st.data()));
+  CUDA_TRY(c, put4(P4_CONTAINER, container));
+  CUDA_TRY(c, put4(P4_AHEAD, ahead.data()));
+  CUDA_TRY(c, put4(P4_AUX, aux.data()));
+  CUDA_TRY(c, put4(P4_AGENDA_CUR, acur.data()));
+  CUDA_TRY(c, put4(P4_ID, ident.data()));
+  CUDA_TRY(c, put4(P4_LAND_LANE, ident.data()));
+  if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_POS], pos, (size_t)n * 8, cudaMemcpyHostToDevice));
+  double* pos1 = nullptr;
+  TRY(dev_alloc(c, pool, &pos1, cap));
+  if (n) CUDA_TRY(c, cudaMemcpy(pos1, pos, (size_t)n * 8, cudaMemcpyHostToDevice));
+  p.pos[1] = pos1;
+  bind_slot_arrays(c, 0);
+
+  TRY(dev_alloc(c, pool, &p.mv_old, cap));
+  TRY(dev_alloc(c, pool, &p.ahead_new, cap));
+  TRY(dev_alloc(c, pool, &p.inbox_next, cap));
+  TRY(dev_alloc(c, pool, &p.dead_mark, cap));
+  TRY(dev_alloc(c, pool, &p.movers, cap));
+  TRY(dev_alloc(c, pool, &p.touched, 2 * cap));
   TRY(dev_alloc(c, pool, &p.counters, 4));
-  TRY(dev_alloc(c, pool, &p.err, 1));
-  for (void* z : {(void*)p.delta, (void*)p.buf, (void*)p.arrive, (void*)p.land_pos})
-    CUDA_TRY(c, cudaMemset(z, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double)));
-  for (void* z : {(void*)p.route_cur, (void*)p.land_tick, (void*)p.mv_old, (void*)p.ahead_new, (void*)p.inbox_next, (void*)p.dead_mark})
-    CUDA_TRY(c, cudaMemset(z, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(int32_t)));
+  TRY(dev_alloc(c, pool, &p.scal, SC_COUNT));
+  for (void* z : {(void*)p.mv_old, (void*)p.ahead_new, (void*)p.inbox_next, (void*)p.dead_mark})
+    CUDA_TRY(c, cudaMemset(z, 0, (size_t)cap * sizeof(int32_t)));
   CUDA_TRY(c, cudaMemset(p.counters, 0, 4 * sizeof(int32_t)));
-  CUDA_TRY(c, cudaMemset(p.err, 0, sizeof(int32_t)));
+  {
+    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, 0};
+    CUDA_TRY(c, cudaMemcpy(p.scal, scal, sizeof(scal), cudaMemcpyHostToDevice));
+  }
+  // reorder scratch
+  const int n_tiles = (int)(cap / rsort::TILE);
+  TRY(dev_alloc(c, pool, &c->sort_keys, cap));
+  TRY(dev_alloc(c, pool, &c->sort_vals, cap));
+  TRY(dev_alloc(c, pool, &c->sort_scratch.keys_alt, cap));
+  TRY(dev_alloc(c, pool, &c->sort_scratch.vals_alt, cap));
+  TRY(dev_alloc(c, pool, &c->sort_scratch.hist, (int64_t)rsort::hist_words(n_tiles)));
+  TRY(dev_alloc(c, pool, &c->sort_scratch.sums, (int64_t)rsort::scan_blocks(rsort::hist_words(n_tiles))));
+  TRY(dev_alloc(c, pool, &c->newslot, cap));
+  TRY(dev_alloc(c, pool, &c->tailflag, cap));
+  CUDA_TRY(c, cudaMemset(c->tailflag, 0, (size_t)cap));
+  // read-back staging, by actor id: [pos f64][4 x i32][4 x u8]
+  TRY(dev_alloc(c, pool, &c->d_ghost, cap));
+  TRY(dev_alloc(c, pool, &c->d_pack, 28 * std::max<int64_t>(n, 1)));
+  CUDA_TRY(c, cudaMemset(c->d_pack, 0, (size_t)(28 * std::max<int64_t>(n, 1))));
+
   TRY(dev_upload(c, pool, &p.speed, speed, n));
   TRY(dev_upload(c, pool, &p.speed_dt, speed_dt, n));
   TRY(dev_upload(c, pool, &p.agenda_off, agenda_off, n + 1));
@@ -840,18 +1068,25 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   CUDA_TRY(c, cudaMemcpy(p.occ, occ.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMemset(p.lane_mark, 0, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
   CUDA_TRY(c, cudaMemset(p.inbox_head, 0xFF, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
-  c->h_agenda_off.assign(agenda_off, agenda_off + n + 1);
-  c->h_item_kind.assign(item_kind, item_kind + n_agenda);
   c->tick = 0;
+  c->ns_host = (int32_t)n;
+  c->last_reorder_tick = -1;
   c->have_actors = true;
+  if (c->reorder_period > 0 && n > 0) {   // spatial order from the first tick on
+    TRY(reorder_slots(c, 0));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  }
   return GRIDDY_OK;
 }
 
 namespace {
 
-int check_device_error(Ctx* c) {
-  int32_t derr = 0;
-  CUDA_TRY(c, cudaMemcpy(&derr, c->p.err, sizeof(derr), cudaMemcpyDeviceToHost));
+// End of a step: device error bits and the slot count, in one copy.
+int finish_step(Ctx* c) {
+  int32_t scal[2] = {0, 0};
+  CUDA_TRY(c, cudaMemcpy(scal, c->p.scal, sizeof(scal), cudaMemcpyDeviceToHost));
+  c->ns_host = scal[SC_NSLOTS];
+  const int32_t derr = scal[SC_ERR];
   if (!derr) return GRIDDY_OK;
   std::string m = "advance$:";
   if (derr & DEV_ERR_BEGIN_ON_ROAD) m += " begin-route$ on an on-road actor (no applicable method);";
@@ -859,22 +1094,28 @@ int check_device_error(Ctx* c) {
   if (derr & DEV_ERR_END_ON_JLANE) m += " end-route$ on a junction lane;";
   if (derr & DEV_ERR_NO_LANE) m += " road-has-no-lanes;";
   if (derr & DEV_ERR_NO_ROUTE) m += " routing table has no next hop;";
+  if (derr & DEV_ERR_INTERNAL) m += " internal: a live actor pointed at a dropped slot;";
   return fail(c, GRIDDY_ERR_BAD_STATE, m);
 }
 
-// One tick = three launches.  ev (optional) receives 4 events bracketing them.
-void launch_tick(Ctx* c, int tick, cudaEvent_t* ev) {
-  const Params& p = c->p;
-  const unsigned adv_blocks = (unsigned)((p.n + 255) / 256);
-  const unsigned aux_blocks = std::min<unsigned>(adv_blocks, 148u * 8u);
+// One tick = three launches (plus a reorder every reorder_period ticks).  ev (optional) receives 5
+// events bracketing reorder, k_advance, k_relink, k_settle.
+int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   if (ev) cudaEventRecord(ev[0], c->stream);
-  k_advance<<<adv_blocks, 256, 0, c->stream>>>(p, tick);
+  if (c->reorder_period > 0 && tick % c->reorder_period == 0 && tick != c->last_reorder_tick)
+    TRY(reorder_slots(c, tick));
+  const Params& p = c->p;
+  const unsigned adv_blocks = (unsigned)((c->ns_host + 255) / 256);
+  const unsigned aux_blocks = std::min<unsigned>(std::max(adv_blocks, 1u), 148u * 8u);
   if (ev) cudaEventRecord(ev[1], c->stream);
-  k_relink<<<aux_blocks * 2, 128, 0, c->stream>>>(p, tick);
+  k_advance<<<adv_blocks, 256, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[2], c->stream);
-  k_settle<<<aux_blocks, 256, 0, c->stream>>>(p, tick);
+  k_relink<<<aux_blocks * 2, 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[3], c->stream);
+  k_settle<<<aux_blocks, 256, 0, c->stream>>>(p, (int)tick);
+  if (ev) cudaEventRecord(ev[4], c->stream);
   c->launches += 3;
+  return GRIDDY_OK;
 }
 
 }  // namespace
@@ -886,8 +1127,8 @@ int griddy_step(void* ctx, int64_t n_ticks) {
   if (n_ticks < 0 || c->tick + n_ticks > INT32_MAX - 2) return fail(c, GRIDDY_ERR_BAD_ARG, "bad n_ticks");
   CUDA_TRY(c, cudaSetDevice(c->device));
   CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
-  if (c->p.n > 0)
-    for (int64_t t = 0; t < n_ticks; ++t) launch_tick(c, (int)(c->tick + t), nullptr);
+  if (c->ns_host > 0)
+    for (int64_t t = 0; t < n_ticks; ++t) TRY(launch_tick(c, c->tick + t, nullptr));
   CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   CUDA_TRY(c, cudaGetLastError());
@@ -895,7 +1136,7 @@ int griddy_step(void* ctx, int64_t n_ticks) {
   CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->last_ms = ms;
   c->tick += n_ticks;
-  return check_device_error(c);
+  return finish_step(c);
 }
 
 int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms) {
@@ -904,16 +1145,18 @@ int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms) {
   if (!c->have_actors || !kernel_ms) return fail(c, GRIDDY_ERR_BAD_ARG, "profile_step: no actors or null output");
   if (n_ticks < 0 || c->tick + n_ticks > INT32_MAX - 2) return fail(c, GRIDDY_ERR_BAD_ARG, "bad n_ticks");
   CUDA_TRY(c, cudaSetDevice(c->device));
-  cudaEvent_t ev[4];
+  cudaEvent_t ev[5];
   for (auto& e : ev) CUDA_TRY(c, cudaEventCreate(&e));
   double total = 0.0;
-  for (int64_t t = 0; t < n_ticks && c->p.n > 0; ++t) {
-    launch_tick(c, (int)(c->tick + t), ev);
+  for (int64_t t = 0; t < n_ticks && c->ns_host > 0; ++t) {
+    TRY(launch_tick(c, c->tick + t, ev));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < 3; ++k) {
+    // kernel_ms = {k_advance, k_relink, k_settle, reorder}
+    static const int slot_of[4] = {3, 0, 1, 2};
+    for (int k = 0; k < 4; ++k) {
       float ms = 0.f;
       CUDA_TRY(c, cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
-      kernel_ms[k] += ms;
+      kernel_ms[slot_of[k]] += ms;
       total += ms;
     }
   }
@@ -921,29 +1164,8 @@ int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms) {
   CUDA_TRY(c, cudaGetLastError());
   c->last_ms = total;
   c->tick += n_ticks;
-  return check_device_error(c);
+  return finish_step(c);
 }
-
-namespace {
-
-// Ghost rule (see the header comment): an on-road actor whose list follower holds an equal key was
-// replaced at the end of the last tick and is not part of the world.  Clears its alive bit in the
-// host copy of `st`.
-int drop_ghosts(Ctx* c, std::vector<uint32_t>& st, const std::vector<double>& ps) {
-  const Params& p = c->p;
-  std::vector<int32_t> ahead(p.n);
-  if (p.n) CUDA_TRY(c, cudaMemcpy(ahead.data(), p.ahead, p.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  std::vector<uint8_t> ghost(p.n, 0);
-  for (int64_t a = 0; a < p.n; ++a) {
-    if ((st[a] & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD)) continue;
-    for (int32_t x = ahead[a]; x >= 0 && ps[x] == ps[a]; x = ahead[x]) ghost[x] = 1;
-  }
-  for (int64_t a = 0; a < p.n; ++a)
-    if (ghost[a]) st[a] &= ~ST_ALIVE;
-  return GRIDDY_OK;
-}
-
-}  // namespace
 
 int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t* container,
                            uint8_t* side, double* pos, int32_t* agenda_cur, int32_t* sleep_left,
@@ -954,34 +1176,38 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
   if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, "download before upload_actors");
   CUDA_TRY(c, cudaSetDevice(c->device));
   const Params& p = c->p;
-  const int64_t n = p.n;
+  const int64_t n = p.n_actors;
+  const int32_t ns = c->ns_host;
   const int tick = (int)c->tick;
   if (n == 0) {
     if (n_order) *n_order = 0;
     return GRIDDY_OK;
   }
-  // device-side formatting into one staging block: [pos f64][4 x i32][4 x u8], n entries each
-  const int64_t n8 = (n + 7) / 8 * 8;
+  // device-side formatting into one staging block indexed by actor id
   uint8_t* base = c->d_pack;
   PackOut o{};
   double* d_pos = (double*)base;
   int32_t* d_i32 = (int32_t*)(base + 8 * n);
   uint8_t* d_u8 = base + 8 * n + 16 * n;
-  (void)n8;
   o.pos = pos ? d_pos : nullptr;
   o.container = container ? d_i32 : nullptr;
   o.agenda_cur = agenda_cur ? d_i32 + n : nullptr;
   o.sleep_left = sleep_left ? d_i32 + 2 * n : nullptr;
   o.route_head = route_head ? d_i32 + 3 * n : nullptr;
-  o.alive = (alive || order || n_order) ? d_u8 : nullptr;
+  o.alive = alive ? d_u8 : nullptr;
   o.loc_kind = loc_kind ? d_u8 + n : nullptr;
   o.side = side ? d_u8 + 2 * n : nullptr;
   o.route_status = route_status ? d_u8 + 3 * n : nullptr;
-  const unsigned blocks = (unsigned)((n + 255) / 256);
-  CUDA_TRY(c, cudaMemsetAsync(c->d_ghost, 0, n, c->stream));
-  k_flag_ghosts<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost);
-  k_pack_state<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost, o);
-  c->launches += 2;
+  const unsigned blocks = (unsigned)((ns + 255) / 256);
+  if (ns > 0) {
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ghost, 0, (size_t)ns, c->stream));
+    if (alive) CUDA_TRY(c, cudaMemsetAsync(d_u8, 0, (size_t)n, c->stream));   // actors without a slot are gone
+    k_flag_ghosts<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost);
+    k_pack_state<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost, o);
+    c->launches += 2;
+  } else if (alive) {
+    CUDA_TRY(c, cudaMemsetAsync(d_u8, 0, (size_t)n, c->stream));
+  }
   auto get = [&](void* dst, const void* src, size_t bytes) {
     return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
   };
@@ -999,22 +1225,23 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
   if (order || n_order) {
     // get-actors order (world.scm:24-30): containers by descending registration index, a lane's
     // actors by descending pos-param, a segment's in list order (landing stamps, see k_relink).
-    std::vector<uint32_t> st(n);
-    std::vector<uint8_t> live(n);
-    std::vector<int32_t> cont(n), land_tick(n), land_lane(n);
-    std::vector<double> ps(n), land_pos(n);
-    auto pull = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
-    CUDA_TRY(c, pull(st.data(), p.st, n * sizeof(uint32_t)));
-    CUDA_TRY(c, pull(live.data(), d_u8, n));
-    CUDA_TRY(c, pull(cont.data(), p.container, n * sizeof(int32_t)));
-    CUDA_TRY(c, pull(ps.data(), p.pos[tick & 1], n * sizeof(double)));
-    CUDA_TRY(c, pull(land_tick.data(), p.land_tick, n * sizeof(int32_t)));
-    CUDA_TRY(c, pull(land_lane.data(), p.land_lane, n * sizeof(int32_t)));
-    CUDA_TRY(c, pull(land_pos.data(), p.land_pos, n * sizeof(double)));
+    std::vector<uint32_t> st(ns);
+    std::vector<uint8_t> ghost(ns);
+    std::vector<int32_t> cont(ns), land_tick(ns), land_lane(ns), ident(ns);
+    std::vector<double> ps(ns), land_pos(ns);
+    auto pull = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess; };
+    CUDA_TRY(c, pull(st.data(), p.st, ns * sizeof(uint32_t)));
+    CUDA_TRY(c, pull(ghost.data(), c->d_ghost, ns));
+    CUDA_TRY(c, pull(cont.data(), p.container, ns * sizeof(int32_t)));
+    CUDA_TRY(c, pull(ident.data(), p.id, ns * sizeof(int32_t)));
+    CUDA_TRY(c, pull(ps.data(), p.pos[tick & 1], ns * sizeof(double)));
+    CUDA_TRY(c, pull(land_tick.data(), p.land_tick, ns * sizeof(int32_t)));
+    CUDA_TRY(c, pull(land_lane.data(), p.land_lane, ns * sizeof(int32_t)));
+    CUDA_TRY(c, pull(land_pos.data(), p.land_pos, ns * sizeof(double)));
     std::vector<int32_t> ord;
-    ord.reserve(n);
-    for (int64_t a = 0; a < n; ++a)
-      if (live[a]) ord.push_back((int32_t)a);
+    ord.reserve(ns);
+    for (int32_t a = 0; a < ns; ++a)
+      if ((st[a] & ST_ALIVE) && !ghost[a]) ord.push_back(a);
     auto landed_earlier = [&](int32_t a, int32_t b, int32_t t_land) {
       if (t_land == 0) return land_lane[a] < land_lane[b];
       if (land_lane[a] != land_lane[b]) return land_lane[a] > land_lane[b];
@@ -1035,7 +1262,8 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
       if (st[a] & ST_ONROAD) return ps[a] > ps[b];
       return offroad_before(a, b);
     });
-    if (order) std::copy(ord.begin(), ord.end(), order);
+    if (order)
+      for (size_t k = 0; k < ord.size(); ++k) order[k] = ident[ord[k]];
     if (n_order) *n_order = (int64_t)ord.size();
   }
   return GRIDDY_OK;
@@ -1047,32 +1275,72 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
   if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, "download before upload_actors");
   CUDA_TRY(c, cudaSetDevice(c->device));
   const Params& p = c->p;
-  std::vector<uint32_t> st(p.n), st_raw;
-  std::vector<int32_t> cont(p.n);
-  std::vector<double> ps(p.n);
-  if (p.n) {
-    CUDA_TRY(c, cudaMemcpy(st.data(), p.st, p.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CUDA_TRY(c, cudaMemcpy(cont.data(), p.container, p.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CUDA_TRY(c, cudaMemcpy(ps.data(), p.pos[c->tick & 1], p.n * sizeof(double), cudaMemcpyDeviceToHost));
+  const int32_t ns = c->ns_host;
+  std::vector<uint32_t> st(ns);
+  std::vector<int32_t> cont(ns), ahead(ns);
+  std::vector<double> ps(ns);
+  if (ns) {
+    CUDA_TRY(c, cudaMemcpy(st.data(), p.st, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(cont.data(), p.container, ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(ahead.data(), p.ahead, ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(ps.data(), p.pos[c->tick & 1], ns * sizeof(double), cudaMemcpyDeviceToHost));
   }
-  st_raw = st;
-  TRY(drop_ghosts(c, st, ps));
+  // ghost rule: an on-road actor whose list follower holds an equal key is not part of the world
+  std::vector<uint8_t> ghost(ns, 0);
+  for (int32_t a = 0; a < ns; ++a) {
+    if ((st[a] & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD)) continue;
+    for (int32_t x = ahead[a]; x >= 0 && ps[x] == ps[a]; x = ahead[x]) ghost[x] = 1;
+  }
   if (junction_count) {   // the device's own incrementally maintained counters, less the ghosts
     CUDA_TRY(c, cudaMemcpy(junction_count, p.occ, (size_t)p.n_items * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    for (int64_t a = 0; a < p.n; ++a)
-      if ((st_raw[a] & ST_ALIVE) && !(st[a] & ST_ALIVE) && c->h_kind[cont[a]] == GRIDDY_JUNCTION_LANE)
+    for (int32_t a = 0; a < ns; ++a)
+      if ((st[a] & ST_ALIVE) && ghost[a] && c->h_kind[cont[a]] == GRIDDY_JUNCTION_LANE)
         --junction_count[c->h_lane_junction[cont[a]]];
   }
   if (lane_count) {
     std::fill(lane_count, lane_count + p.n_items, 0);
-    for (int64_t a = 0; a < p.n; ++a)
-      if (st[a] & ST_ALIVE) ++lane_count[cont[a]];
+    for (int32_t a = 0; a < ns; ++a)
+      if ((st[a] & ST_ALIVE) && !ghost[a]) ++lane_count[cont[a]];
   }
   return GRIDDY_OK;
+}
+
+// Diagnostics: the reorder's radix sort on caller data (host pointers), for tests/.
+int griddy_debug_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int32_t key_bits) {
+  if (!keys || !vals || n < 0 || key_bits < 1 || key_bits > 64) return GRIDDY_ERR_BAD_ARG;
+  if (rsort::prepare() != cudaSuccess) return GRIDDY_ERR_CUDA;
+  const int n_tiles = (int)((n + rsort::TILE - 1) / rsort::TILE);
+  if (n_tiles == 0) return GRIDDY_OK;
+  const size_t n_pad = (size_t)n_tiles * rsort::TILE;
+  void* buf[6] = {};
+  const size_t bytes[6] = {n_pad * 8, n_pad * 8, n_pad * 4, n_pad * 4, rsort::hist_words(n_tiles) * 4,
+                           rsort::scan_blocks(rsort::hist_words(n_tiles)) * 4};
+  bool ok = true;
+  for (int k = 0; k < 6 && ok; ++k) ok = cudaMalloc(&buf[k], bytes[k]) == cudaSuccess;
+  if (ok) {
+    uint64_t* kk = (uint64_t*)buf[0];
+    uint32_t* vv = (uint32_t*)buf[2];
+    rsort::Scratch sc;
+    sc.keys_alt = (uint64_t*)buf[1];
+    sc.vals_alt = (uint32_t*)buf[3];
+    sc.hist = (uint32_t*)buf[4];
+    sc.sums = (uint32_t*)buf[5];
+    cudaMemset(kk, 0xFF, n_pad * 8);   // padding sorts last
+    cudaMemset(vv, 0xFF, n_pad * 4);
+    cudaMemcpy(kk, keys, (size_t)n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(vv, vals, (size_t)n * 4, cudaMemcpyHostToDevice);
+    rsort::sort_pairs(&kk, &vv, n_tiles, key_bits, &sc, 0);
+    ok = cudaDeviceSynchronize() == cudaSuccess;
+    cudaMemcpy(keys, kk, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(vals, vv, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  }
+  for (void* ptr : buf) cudaFree(ptr);
+  return ok ? GRIDDY_OK : GRIDDY_ERR_CUDA;
 }
 
 double griddy_last_step_ms(void* ctx) { return ctx ? ((Ctx*)ctx)->last_ms : 0.0; }
 int64_t griddy_tick(void* ctx) { return ctx ? ((Ctx*)ctx)->tick : 0; }
 int64_t griddy_kernel_launches(void* ctx) { return ctx ? ((Ctx*)ctx)->launches : 0; }
+int64_t griddy_slots_in_use(void* ctx) { return ctx ? ((Ctx*)ctx)->ns_host : 0; }
 
 }  // extern "C"

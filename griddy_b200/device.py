@@ -22,7 +22,9 @@ ERR_NAMES = {1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "BAD_STATE", 5: "OOM"}
 SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last_error",
            "griddy_set_constants", "griddy_upload_network", "griddy_set_routing_grid",
            "griddy_upload_actors", "griddy_step", "griddy_profile_step", "griddy_download_actors",
-           "griddy_download_occupancy", "griddy_last_step_ms", "griddy_tick", "griddy_kernel_launches")
+           "griddy_download_occupancy", "griddy_last_step_ms", "griddy_tick", "griddy_kernel_launches",
+           "griddy_set_locality_keys", "griddy_set_reorder_period", "griddy_slots_in_use",
+           "griddy_debug_sort_pairs")
 
 
 class GriddyCudaError(RuntimeError):
@@ -48,6 +50,8 @@ def lib():
         L.griddy_tick.argtypes = [C.c_void_p]
         L.griddy_kernel_launches.restype = C.c_int64
         L.griddy_kernel_launches.argtypes = [C.c_void_p]
+        L.griddy_slots_in_use.restype = C.c_int64
+        L.griddy_slots_in_use.argtypes = [C.c_void_p]
         L.griddy_destroy.restype = None
         L.griddy_destroy.argtypes = [C.c_void_p]
         _LIB = L
@@ -62,7 +66,7 @@ class Simulation:
     """One world on one GPU: upload once, step, read back."""
 
     def __init__(self, net: FlatNetwork, actors: FlatActors, device: int = -1,
-                 dt: float = 1.0 / 15.0, two_size: float = 10.0):
+                 dt: float = 1.0 / 15.0, two_size: float = 10.0, reorder_period: int | None = None):
         L = lib()
         self.h = C.c_void_p()
         rc = L.griddy_create(C.byref(self.h), C.c_int(device))
@@ -75,6 +79,10 @@ class Simulation:
                                           _p(net.lane_dir), _p(net.lane_segment), _p(net.lane_out),
                                           _p(net.lane_junction), _p(net.seg_outer_forw),
                                           _p(net.seg_outer_back)))
+        if net.loc_key is not None:
+            self._chk(L.griddy_set_locality_keys(self.h, _p(net.loc_key)))
+        if reorder_period is not None:
+            self._chk(L.griddy_set_reorder_period(self.h, C.c_int32(reorder_period)))
         if actors.route_off is None:
             if not net.grid_n:
                 raise ValueError("actors carry no routes and the network has no grid routing table")
@@ -99,9 +107,9 @@ class Simulation:
 
     def profile_step(self, n_ticks: int = 1) -> dict:
         """Per-kernel device ms summed over n_ticks (events around every launch)."""
-        ms = (C.c_double * 3)(0.0, 0.0, 0.0)
+        ms = (C.c_double * 4)(0.0, 0.0, 0.0, 0.0)
         self._chk(lib().griddy_profile_step(self.h, C.c_int64(n_ticks), ms))
-        return {"k_advance": ms[0], "k_relink": ms[1], "k_settle": ms[2]}
+        return {"k_advance": ms[0], "k_relink": ms[1], "k_settle": ms[2], "reorder": ms[3]}
 
     @property
     def last_step_ms(self) -> float:
@@ -110,6 +118,10 @@ class Simulation:
     @property
     def tick(self) -> int:
         return int(lib().griddy_tick(self.h))
+
+    @property
+    def slots_in_use(self) -> int:
+        return int(lib().griddy_slots_in_use(self.h))
 
     @property
     def kernel_launches(self) -> int:

@@ -44,6 +44,7 @@ class FlatNetwork:
     lane_to_j: Optional[np.ndarray] = None     # i32 segment lanes: junction they reach
     turn4: Optional[np.ndarray] = None         # i32 [n_items,4] next-hop table by heading
     seg_reg: Optional[np.ndarray] = None       # i32 segment ordinal -> registration id
+    loc_key: Optional[np.ndarray] = None       # u32 locality key per item (griddy_set_locality_keys)
 
     def __post_init__(self):
         self.kind = _arr(self.kind, np.uint8)
@@ -55,6 +56,8 @@ class FlatNetwork:
             v = getattr(self, name)
             if v is not None:
                 setattr(self, name, _arr(v, np.int32))
+        if self.loc_key is not None:
+            self.loc_key = _arr(self.loc_key, np.uint32)
 
     @property
     def n_items(self) -> int:

@@ -54,7 +54,25 @@ def grid_network(n: int, spacing: float = 150.0, origin: float = 50.0) -> FlatNe
         raise RuntimeError(f"synth_grid_network -> {rc}")
     return FlatNetwork(kind, lane_len, lane_dir, lane_segment, lane_out, lane_junction, so_f, so_b,
                        lane_in=lane_in, grid_n=n, lane_from_j=lf, lane_to_j=lt,
-                       turn4=turn4.reshape(ni, 4), seg_reg=seg_reg)
+                       turn4=turn4.reshape(ni, 4), seg_reg=seg_reg,
+                       loc_key=grid_locality_keys(kind, lf, lane_junction, so_f))
+
+
+def grid_locality_keys(kind, lane_from_j, lane_junction, seg_outer_forw) -> np.ndarray:
+    """Locality key per item for griddy_set_locality_keys: items grouped by the junction they hang
+    off (row-major), so that lanes an actor passes through in succession are close in slot order.
+    A segment lane hangs off the junction it leaves, a junction lane off its junction, a segment off
+    the junction its forw lanes leave."""
+    ni = kind.shape[0]
+    j = np.arange(ni, dtype=np.int64)
+    sl, jl, sg = kind == 2, kind == 3, kind == 1
+    j[sl] = lane_from_j[sl]
+    j[jl] = lane_junction[jl]
+    j[sg] = lane_from_j[seg_outer_forw[sg]]
+    order = np.argsort(j, kind="stable")
+    key = np.empty(ni, np.uint32)
+    key[order] = np.arange(ni, dtype=np.uint32)
+    return key
 
 
 def grid_actors(net: FlatNetwork, n_actors: int, seed: int = DEFAULT_SEED, agenda_len: int = 2) -> FlatActors:

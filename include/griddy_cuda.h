@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GRIDDY_ABI_VERSION 1
+#define GRIDDY_ABI_VERSION 2
 
 enum {
   GRIDDY_OK = 0,
@@ -73,6 +73,16 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
                           const int32_t* lane_out, const int32_t* lane_junction,
                           const int32_t* seg_outer_forw, const int32_t* seg_outer_back);
 
+/* Optional.  Actors are kept in device "slots" that are re-sorted every few ticks by (locality key
+ * of their lane or segment, pos-param) so that neighbours on the road are neighbours in memory.
+ * item_key[n_items] gives each item's place in that order (items that are close on the map should
+ * get close keys; keys < 2^32-1).  Default: the registration index.  Performance only — results do
+ * not depend on it.  Call after griddy_upload_network and before griddy_upload_actors. */
+int griddy_set_locality_keys(void* ctx, const uint32_t* item_key);
+
+/* Ticks between two reorders of the actor slots (default 64; 0 = never).  Performance only. */
+int griddy_set_reorder_period(void* ctx, int32_t ticks);
+
 /* Device-side routing table for procedural grids (examples/procedural-grid.scm): the first n*n
  * items are the junctions in row-major order; lane_from_j / lane_to_j give the junctions a segment
  * lane leaves and reaches; turn4[4*lane + h] is the junction lane leading from `lane` onto the
@@ -115,13 +125,19 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
 int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_count);
 
 /* Like griddy_step, but brackets every kernel launch with CUDA events on the launching stream and
- * adds the per-kernel device time, in ms summed over the n_ticks, to kernel_ms[0..2] =
- * {k_advance, k_relink, k_settle}.  For roofline accounting only: the events serialise launches. */
+ * adds the per-kernel device time, in ms summed over the n_ticks, to kernel_ms[0..3] =
+ * {k_advance, k_relink, k_settle, reorder (all its launches)}.  For roofline accounting only: the
+ * events serialise launches. */
 int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms);
 
 double griddy_last_step_ms(void* ctx);       /* device time of the last griddy_step (CUDA events) */
 int64_t griddy_tick(void* ctx);              /* ticks since upload */
 int64_t griddy_kernel_launches(void* ctx);   /* kernels launched by this context so far */
+int64_t griddy_slots_in_use(void* ctx);      /* device slots holding actors (living, or dead and not yet dropped) */
+
+/* Diagnostics for tests/: the reorder's stable LSD radix sort (csrc/radix_sort.cuh) applied to n
+ * caller-owned (key, value) pairs in host memory, sorting by the low key_bits bits of the key. */
+int griddy_debug_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int32_t key_bits);
 
 #ifdef __cplusplus
 }

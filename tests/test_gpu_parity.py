@@ -162,3 +162,48 @@ def test_bad_arguments_are_rejected():
     with pytest.raises(device.GriddyCudaError) as e:
         device.Simulation(net, a)
     assert e.value.code == 1
+
+
+def test_radix_sort_matches_stable_argsort():
+    """The reorder's hand-written LSD radix sort against numpy's stable sort, ragged sizes included."""
+    import ctypes as C
+    L = device.lib()
+    rng = np.random.default_rng(11)
+    for n, bits in [(1, 8), (4095, 16), (4096, 24), (4097, 41), (100_000, 41), (1_000_003, 33)]:
+        keys = rng.integers(0, 1 << bits, size=n, dtype=np.uint64)
+        if n > 10:
+            keys[: n // 3] = keys[n // 2: n // 2 + n // 3]      # plenty of duplicates: stability matters
+        vals = np.arange(n, dtype=np.uint32)
+        want = np.argsort(keys, kind="stable").astype(np.uint32)
+        k, v = keys.copy(), vals.copy()
+        rc = L.griddy_debug_sort_pairs(k.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p),
+                                       C.c_int64(n), C.c_int32(bits))
+        assert rc == 0
+        assert np.array_equal(v, want), (n, bits)
+        assert np.array_equal(k, keys[want])
+
+
+@pytest.mark.parametrize("period", [0, 1, 7])
+def test_reorder_period_does_not_change_results(period):
+    """Slots are re-sorted every `period` ticks (0 = never): state, order and occupancy stay identical
+    to the oracle's, and dead actors are dropped from the slots."""
+    net, actors = crowded_grid(4, 800, n_dest=3, seed=8)
+    sim, ref = device.Simulation(net, actors, reorder_period=period), Oracle(net, actors)
+    for t in range(300):
+        sim.step(1); ref.step(1)
+        compare(sim, ref, f"period {period} tick {t + 1}")
+    assert ref.vanished > 0
+    if period:
+        sim.step(period); ref.step(period)
+        assert sim.slots_in_use <= actors.n - ref.vanished + 8   # only a few ghosts awaiting removal
+    else:
+        assert sim.slots_in_use == actors.n
+
+
+def test_default_locality_keys_without_grid():
+    """Networks without uploaded locality keys (registration index as key), explicit routes, reorder on."""
+    net, actors = triangle_flat()
+    sim, ref = device.Simulation(net, actors, reorder_period=2), Oracle(net, actors)
+    for t in range(60):
+        sim.step(1); ref.step(1)
+        compare(sim, ref, f"tick {t + 1}")
