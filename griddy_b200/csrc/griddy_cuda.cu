@@ -72,12 +72,8 @@
 #include <string>
 #include <vector>
 
-#include <cooperative_groups.h>
-
 #include "griddy_cuda.h"
 #include "radix_sort.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -93,6 +89,8 @@ constexpr int HOP_ARRIVE = -1;
 constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
               DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32;
 
+// Params::counters[parity][...]
+constexpr int CNT_TOUCHED = 1, CNT_SLOW = 2, CNT_STRIDE = 4;
 // device scalars (Params::scal)
 constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_COUNT = 4;
 
@@ -131,18 +129,10 @@ struct Params {
   // per-tick scratch, by slot
   int32_t *mv_old, *ahead_new, *inbox_next;
   int32_t* dead_mark;   // tick+1 when the actor was found to be a ghost during `tick`
-  int32_t *movers, *touched;
-  int32_t* counters;   // [2 parities][2]: movers, touched lanes
+  int32_t *touched, *slow;
+  int32_t* counters;   // [2 parities][CNT_STRIDE]: movers, touched lanes, deferred actors
   double dt, two_size;
 };
-
-// Claim-then-broadcast: one atomic per converged group instead of one per thread.
-__device__ __forceinline__ int32_t agg_append(int32_t* counter) {
-  cg::coalesced_group g = cg::coalesced_threads();
-  int32_t base = 0;
-  if (g.thread_rank() == 0) base = atomicAdd(counter, (int32_t)g.size());
-  return g.shfl(base, 0) + (int32_t)g.thread_rank();
-}
 
 __device__ __forceinline__ void dev_error(const Params& p, int bit) { atomicOr(&p.scal[SC_ERR], bit); }
 
@@ -189,107 +179,66 @@ __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t id, int32
   return HEAD_TRAVEL;
 }
 
-__device__ __forceinline__ void mark_touched(const Params& p, int32_t lane, int tick, int32_t* n_touched) {
-  if (atomicExch(&p.lane_mark[lane], tick + 1) != tick + 1) p.touched[agg_append(n_touched)] = lane;
+// Lanes whose list must be rebuilt this tick are collected per block in shared memory and flushed to
+// Params::touched with one global atomic per block (a same-address atomic per lane would serialise).
+struct TouchSink {
+  int32_t* list;   // shared, SINK_CAP entries
+  int32_t* count;  // shared
+};
+constexpr int SLOW_THREADS = 128;
+constexpr int SINK_CAP = 3 * SLOW_THREADS;   // an actor touches at most its old lane, its new lane and a ghost's lane
+
+__device__ __forceinline__ void mark_touched(const Params& p, int32_t lane, int tick, const TouchSink& sink) {
+  if (atomicExch(&p.lane_mark[lane], tick + 1) != tick + 1) sink.list[atomicAdd(sink.count, 1)] = lane;
 }
 
-__device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane, int tick, int32_t* n_touched) {
+__device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
   p.inbox_next[a] = atomicExch(&p.inbox_head[lane], a);
-  mark_touched(p, lane, tick, n_touched);
+  mark_touched(p, lane, tick, sink);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_advance: advance$ for every actor (simulate.scm:93-111) with route.scm:53-141 inlined.
-// `a` is a slot.  The common case — an actor on the road, not at the end of its lane — touches only
-// the hot arrays: st, ahead, pos (old, leader, new), delta, buf.
-__global__ void __launch_bounds__(256) k_advance(Params p, int tick) {
-  const int par = tick & 1;
-  int32_t* counters = p.counters + 2 * par;
-  if (blockIdx.x == 0 && threadIdx.x < 2) p.counters[2 * (par ^ 1) + threadIdx.x] = 0;
-  const int a = blockIdx.x * 256 + threadIdx.x;
-  if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.st[a];
-  if (!(st & ST_ALIVE)) return;
-  const double* __restrict__ pos_old = p.pos[par];
-  double* __restrict__ pos_new = p.pos[par ^ 1];
-  const double cur = pos_old[a];
+// advance$ for one actor (simulate.scm:93-111) with route.scm:53-141 inlined.  `a` is a slot; st,
+// ah, cur, dlt, buf, lead were loaded by the caller (ah = -1 and lead = 0 when there is no leader).
+// Returns the actor's new pos-param; everything else that changes is written here.
+__device__ __forceinline__ double advance_actor(const Params& p, const int a, const int tick, const uint32_t st,
+                                                int32_t ah, const double cur, const double dlt,
+                                                const double buf, double lead,
+                                                const double* __restrict__ pos_old, const TouchSink& sink) {
   const int head = (st >> ST_HEAD_SHIFT) & 3;
   const int rs = (st >> ST_RS_SHIFT) & 3;
-  const bool on_route = rs == GRIDDY_ROUTE_SOME;
-
-  // issue the independent loads of the common case together
-  int32_t ah = -1;
-  double lead = 0.0, dlt = 0.0, buf = 0.0;
-  if (st & ST_ONROAD) ah = p.ahead[a];
-  if (on_route) { dlt = p.delta[a]; buf = p.buf[a]; }
 
   // nearest actor ahead on the lane (bbtree-find-min's only candidate, util.scm:152-162), skipping
   // ghosts: leaders that this actor replaced with an equal key at the end of the previous tick
-  if (ah >= 0) {
-    lead = pos_old[ah];
-    if (lead == cur) {
-      do {
-        p.dead_mark[ah] = tick + 1;
-        ah = p.ahead[ah];
-        if (ah >= 0) lead = pos_old[ah];
-      } while (ah >= 0 && lead == cur);
-      mark_touched(p, p.container[a], tick, &counters[1]);
-    }
+  if (ah >= 0 && lead == cur) {
+    do {
+      p.dead_mark[ah] = tick + 1;
+      ah = p.ahead[ah];
+      if (ah >= 0) lead = pos_old[ah];
+    } while (ah >= 0 && lead == cur);
+    mark_touched(p, p.container[a], tick, sink);
   }
 
-  if (rs == GRIDDY_ROUTE_NONE && head == HEAD_NONE) {   // do-nothing$  simulate.scm:70-72
-    pos_new[a] = cur;
-    return;
-  }
-  if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {   // sleep$  simulate.scm:74-78
-    const int32_t t = p.aux[a];
-    if (t == 0) {
-      const int32_t ac = p.agenda_cur[a] + 1;
-      int32_t aux;
-      const uint32_t h = load_head(p, p.id[a], ac, &aux);
-      p.agenda_cur[a] = ac;
-      p.aux[a] = aux;
-      p.st[a] = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
-    } else {
-      p.aux[a] = t - 1;
-    }
-    pos_new[a] = cur;
-    return;
-  }
-  if (head != HEAD_TRAVEL) {   // simulate.scm:105-111 has no clause for these
-    dev_error(p, DEV_ERR_NO_CLAUSE);
-    pos_new[a] = cur;
-    return;
-  }
-
-  if (on_route) {   // advance-on-route$  route.scm:137-141
+  if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {   // advance-on-route$  route.scm:137-141
     // get-pos-param-next on the current lane (route.scm:53-74)
     double next = __dadd_rn(cur, dlt);
     if (ah >= 0 && lead > cur && lead <= __dadd_rn(next, buf)) next = __dsub_rn(lead, buf);
     if (st & ST_ARRIVE) {   // route-step/arrive-at$  route.scm:76-90
       const double target = p.arrive[a];
-      if (next >= target) {
-        const bool back = target < cur;
-        p.st[a] = (st & ~((3u << ST_RS_SHIFT) | ST_ARRIVE)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u);
-        pos_new[a] = target;
-        if (back) {   // jumped back past other residents: re-insert by key
-          const int32_t lane = p.container[a];
-          p.mv_old[a] = lane;
-          p.movers[agg_append(&counters[0])] = a;
-          enter_lane(p, a, lane, tick, &counters[1]);
-        }
-      } else {
-        pos_new[a] = next;
+      if (!(next >= target)) return next;
+      const bool back = target < cur;
+      p.st[a] = (st & ~((3u << ST_RS_SHIFT) | ST_ARRIVE)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u);
+      if (back) {   // jumped back past other residents: re-insert by key
+        const int32_t lane = p.container[a];
+        p.mv_old[a] = lane;
+        enter_lane(p, a, lane, tick, sink);
       }
-      return;
+      return target;
     }
     // route-step/turn-onto$  route.scm:92-135
-    if (!(next >= 1.0)) { pos_new[a] = next; return; }
+    if (!(next >= 1.0)) return next;
     const int32_t target = p.aux[a];
-    if (p.kind[target] == GRIDDY_JUNCTION_LANE && p.occ[p.lane_junction[target]] > 0) {   // waiting
-      pos_new[a] = cur;
-      return;
-    }
+    if (p.kind[target] == GRIDDY_JUNCTION_LANE && p.occ[p.lane_junction[target]] > 0) return cur;   // waiting
     const int32_t id = p.id[a];
     const int32_t lane = p.container[a];
     const int32_t item = p.agenda_cur[a];
@@ -315,20 +264,38 @@ __global__ void __launch_bounds__(256) k_advance(Params p, int tick) {
     p.container[a] = target;
     p.mv_old[a] = lane;
     p.st[a] = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
-    pos_new[a] = tnext;
-    p.movers[agg_append(&counters[0])] = a;
-    enter_lane(p, a, target, tick, &counters[1]);
-    mark_touched(p, lane, tick, &counters[1]);
-    return;
+    enter_lane(p, a, target, tick, sink);
+    mark_touched(p, lane, tick, sink);
+    return tnext;
+  }
+
+  if (rs == GRIDDY_ROUTE_NONE && head == HEAD_NONE) return cur;   // do-nothing$  simulate.scm:70-72
+  if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {            // sleep$  simulate.scm:74-78
+    const int32_t t = p.aux[a];
+    if (t == 0) {
+      const int32_t ac = p.agenda_cur[a] + 1;
+      int32_t aux;
+      const uint32_t h = load_head(p, p.id[a], ac, &aux);
+      p.agenda_cur[a] = ac;
+      p.aux[a] = aux;
+      p.st[a] = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
+    } else {
+      p.aux[a] = t - 1;
+    }
+    return cur;
+  }
+  if (head != HEAD_TRAVEL) {   // simulate.scm:105-111 has no clause for these
+    dev_error(p, DEV_ERR_NO_CLAUSE);
+    return cur;
   }
 
   const int32_t item = p.agenda_cur[a];
   if (rs == GRIDDY_ROUTE_NONE) {   // begin-route$  simulate.scm:80-85
-    if (st & ST_ONROAD) { dev_error(p, DEV_ERR_BEGIN_ON_ROAD); pos_new[a] = cur; return; }
+    if (st & ST_ONROAD) { dev_error(p, DEV_ERR_BEGIN_ON_ROAD); return cur; }
     const int32_t seg = p.container[a];
     const int32_t init_lane = outer_lane(p, seg, st & ST_SIDE);
     const int32_t dest_lane = outer_lane(p, p.item_seg[item], p.item_side[item]);
-    if (init_lane < 0 || dest_lane < 0) { dev_error(p, DEV_ERR_NO_LANE); pos_new[a] = cur; return; }
+    if (init_lane < 0 || dest_lane < 0) { dev_error(p, DEV_ERR_NO_LANE); return cur; }
     // off-road->on-road  location.scm:49-57
     const double init_pos = p.lane_dir[init_lane] ? __dsub_rn(1.0, cur) : cur;
     const double ipos = p.item_pos[item];
@@ -345,15 +312,13 @@ __global__ void __launch_bounds__(256) k_advance(Params p, int tick) {
     p.mv_old[a] = ~seg;
     p.st[a] = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
               ST_ONROAD | ST_MOVED | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);
-    pos_new[a] = init_pos;
-    p.movers[agg_append(&counters[0])] = a;
-    enter_lane(p, a, init_lane, tick, &counters[1]);
-    return;
+    enter_lane(p, a, init_lane, tick, sink);
+    return init_pos;
   }
 
   // end-route$  simulate.scm:87-91   (rs == GRIDDY_ROUTE_DONE)
   const int32_t lane = p.container[a];
-  if (p.kind[lane] != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); pos_new[a] = cur; return; }
+  if (p.kind[lane] != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); return cur; }
   const int32_t seg = p.lane_segment[lane];
   const uint32_t dir = p.lane_dir[lane];
   const int32_t ac = item + 1;
@@ -370,9 +335,126 @@ __global__ void __launch_bounds__(256) k_advance(Params p, int tick) {
   uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE);
   ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
   p.st[a] = ns;
-  pos_new[a] = dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
-  p.movers[agg_append(&counters[0])] = a;
-  mark_touched(p, lane, tick, &counters[1]);
+  mark_touched(p, lane, tick, sink);
+  return dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
+}
+
+// k_advance: the common cases of advance$ for every slot; everything else is deferred to k_slow.
+// ADV_UNROLL slots per thread, strided by the block so that every load is coalesced.  The loads of all
+// ADV_UNROLL actors are issued before the first use (one slot per thread leaves too few bytes in
+// flight to cover HBM latency): first st / ahead / pos, then the leaders' pos-params (a gather that
+// the slot order keeps inside the same or a neighbouring cache line) with delta / buf.
+// Handled here: an actor on its route that neither reaches the end of its lane nor has an
+// (arrive-at _) head; a sleeper whose time has not run out; an idle actor.  These touch only the hot
+// arrays.  Any other actor — a few percent — would drag its whole warp through chains of dependent
+// gathers, so its slot is appended to the slow list instead (block-aggregated: one global atomic per
+// block) and k_slow runs the full advance$ for it with one thread per listed actor.
+constexpr int ADV_UNROLL = 4;
+constexpr int ADV_THREADS = 256;
+
+__global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
+  __shared__ int32_t s_list[ADV_THREADS * ADV_UNROLL];
+  __shared__ int32_t s_n, s_base;
+  const int par = tick & 1;
+  int32_t* counters = p.counters + CNT_STRIDE * par;
+  if (blockIdx.x == 0 && threadIdx.x < CNT_STRIDE) p.counters[CNT_STRIDE * (par ^ 1) + threadIdx.x] = 0;
+  const int n = p.scal[SC_NSLOTS];
+  const int base = blockIdx.x * (ADV_THREADS * ADV_UNROLL) + threadIdx.x;
+  if (base - (int)threadIdx.x >= n) return;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const double* __restrict__ pos_old = p.pos[par];
+  double* __restrict__ pos_new = p.pos[par ^ 1];
+
+  uint32_t st[ADV_UNROLL];
+  int32_t ah[ADV_UNROLL], slp[ADV_UNROLL];
+  double cur[ADV_UNROLL], dlt[ADV_UNROLL], buf[ADV_UNROLL], lead[ADV_UNROLL];
+#pragma unroll
+  for (int k = 0; k < ADV_UNROLL; ++k) {
+    const int a = base + k * ADV_THREADS;
+    const bool in = a < n;
+    st[k] = in ? p.st[a] : 0u;
+    ah[k] = in ? p.ahead[a] : -1;
+    cur[k] = in ? pos_old[a] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < ADV_UNROLL; ++k) {
+    const int a = base + k * ADV_THREADS;
+    const bool alive = st[k] & ST_ALIVE;
+    const bool on_road = alive && (st[k] & ST_ONROAD);
+    if (!on_road) ah[k] = -1;   // an off-road actor's ahead is stale
+    const int rs = (st[k] >> ST_RS_SHIFT) & 3, head = (st[k] >> ST_HEAD_SHIFT) & 3;
+    const bool on_route = on_road && rs == GRIDDY_ROUTE_SOME;
+    lead[k] = ah[k] >= 0 ? pos_old[ah[k]] : 0.0;
+    dlt[k] = on_route ? p.delta[a] : 0.0;
+    buf[k] = on_route ? p.buf[a] : 0.0;
+    slp[k] = (alive && rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) ? p.aux[a] : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < ADV_UNROLL; ++k) {
+    const int a = base + k * ADV_THREADS;
+    if (!(st[k] & ST_ALIVE)) continue;
+    const int rs = (st[k] >> ST_RS_SHIFT) & 3, head = (st[k] >> ST_HEAD_SHIFT) & 3;
+    bool slow = ah[k] >= 0 && lead[k] == cur[k];   // equal key ahead: a ghost to remove
+    double np = cur[k];
+    if (!slow) {
+      if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {
+        // get-pos-param-next on the current lane (route.scm:53-74)
+        double next = __dadd_rn(cur[k], dlt[k]);
+        if (ah[k] >= 0 && lead[k] > cur[k] && lead[k] <= __dadd_rn(next, buf[k])) next = __dsub_rn(lead[k], buf[k]);
+        if ((st[k] & ST_ARRIVE) || next >= 1.0) slow = true;
+        else np = next;
+      } else if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {   // sleep$, time left  simulate.scm:77
+        if (slp[k] == 0) slow = true;
+        else p.aux[a] = slp[k] - 1;
+      } else if (!(rs == GRIDDY_ROUTE_NONE && head == HEAD_NONE)) {   // not do-nothing$ either
+        slow = true;
+      }
+    }
+    if (slow) s_list[atomicAdd(&s_n, 1)] = a;
+    else pos_new[a] = np;
+  }
+  __syncthreads();
+  const int ns = s_n;
+  if (ns == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(&counters[CNT_SLOW], ns);
+  __syncthreads();
+  for (int i = threadIdx.x; i < ns; i += ADV_THREADS) p.slow[s_base + i] = s_list[i];
+}
+
+// k_slow: the full advance$ for the actors k_advance deferred, one thread per actor, so that the
+// chains of dependent gathers of 32 such actors overlap instead of stalling 31 idle lanes.
+__global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
+  __shared__ int32_t s_touched[SINK_CAP];
+  __shared__ int32_t s_nt, s_base;
+  const int par = tick & 1;
+  int32_t* counters = p.counters + CNT_STRIDE * par;
+  const int32_t n_slow = counters[CNT_SLOW];
+  const double* __restrict__ pos_old = p.pos[par];
+  double* __restrict__ pos_new = p.pos[par ^ 1];
+  const TouchSink sink{s_touched, &s_nt};
+  for (int32_t chunk = blockIdx.x * SLOW_THREADS; chunk < n_slow; chunk += gridDim.x * SLOW_THREADS) {
+    if (threadIdx.x == 0) s_nt = 0;
+    __syncthreads();
+    const int32_t i = chunk + threadIdx.x;
+    if (i < n_slow) {
+      const int a = p.slow[i];
+      const uint32_t st = p.st[a];
+      const double cur = pos_old[a];
+      const bool on_road = st & ST_ONROAD;
+      const bool on_route = on_road && ((st >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME;
+      const int32_t ah = on_road ? p.ahead[a] : -1;
+      const double lead = ah >= 0 ? pos_old[ah] : 0.0;
+      const double dlt = on_route ? p.delta[a] : 0.0;
+      const double buf = on_route ? p.buf[a] : 0.0;
+      pos_new[a] = advance_actor(p, a, tick, st, ah, cur, dlt, buf, lead, pos_old, sink);
+    }
+    __syncthreads();
+    const int nt = s_nt;
+    if (threadIdx.x == 0 && nt) s_base = atomicAdd(&counters[CNT_TOUCHED], nt);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nt; k += SLOW_THREADS) p.touched[s_base + k] = s_touched[k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,7 +499,7 @@ __device__ int later_processed(const Params& p, int x, int y, int32_t lane, cons
 // k_relink: rebuild the ascending-pos list of every lane an actor entered or left this tick.
 __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
   const int par = tick & 1;
-  const int32_t n_touched = p.counters[2 * par + 1];
+  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
   const double* __restrict__ pos_old = p.pos[par];
   const double* __restrict__ pos_new = p.pos[par ^ 1];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
@@ -496,13 +578,14 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
   }
 }
 
-// k_settle: per mover, publish the new ahead pointer and apply junction occupancy deltas.
+// k_settle: per mover (found in the deferred list), publish the new ahead pointer and apply junction occupancy deltas.
 __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
   const int par = tick & 1;
-  const int32_t n_movers = p.counters[2 * par];
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_movers; i += gridDim.x * blockDim.x) {
-    const int a = p.movers[i];
+  const int32_t n_slow = p.counters[CNT_STRIDE * par + CNT_SLOW];   // movers are among the deferred actors
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slow; i += gridDim.x * blockDim.x) {
+    const int a = p.slow[i];
     const uint32_t st = p.st[a];
+    if (!(st & ST_MOVED)) continue;
     const int32_t old = p.mv_old[a];
     if (old >= 0 && p.kind[old] == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[p.lane_junction[old]], 1);
     if (p.dead_mark[a] == tick + 1) {   // it was a ghost when it moved: the move is void
@@ -535,7 +618,7 @@ struct Permute {
 };
 
 // grid = n_pad / 256 exactly: every lane of every warp reaches the ballot
-__global__ void __launch_bounds__(256) k_make_keys(Params p, int par, uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) k_make_keys(Params p, int par, int key_bits, uint64_t* __restrict__ keys,
                                                     uint32_t* __restrict__ vals, uint8_t* __restrict__ tailflag) {
   const int s = blockIdx.x * 256 + threadIdx.x;
   uint64_t key = ~0ull;
@@ -549,7 +632,8 @@ __global__ void __launch_bounds__(256) k_make_keys(Params p, int par, uint64_t* 
       const double x = p.pos[par][s];
       // 16 bits of pos-param over [-0.5, 1.5): enough to keep a lane's actors in list order
       const double q = fmin(fmax((x + 0.5) * 32768.0, 0.0), 65535.0);
-      key = ((uint64_t)p.loc_key[c] << 16) | (uint64_t)(uint32_t)q;
+      // off-road actors after the on-road ones: warps are then all-travelling or all-parked
+      key = ((uint64_t)((st & ST_ONROAD) ? 0u : 1u) << (key_bits - 1)) | ((uint64_t)p.loc_key[c] << 16) | (uint64_t)(uint32_t)q;
       val = (uint32_t)s;
       tailflag[s] = ((st & ST_ONROAD) && p.lane_tail[c] == s) ? 1 : 0;
     }
@@ -742,8 +826,9 @@ int reorder_slots(Ctx* c, int64_t tick) {
   cudaStream_t s = c->stream;
   CUDA_TRY(c, cudaMemsetAsync(&p.scal[SC_NALIVE], 0, sizeof(int32_t), s));
   CUDA_TRY(c, cudaMemsetAsync(c->newslot, 0xFF, (size_t)c->ns_host * sizeof(int32_t), s));
-  k_make_keys<<<n_pad / 256, 256, 0, s>>>(p, par, c->sort_keys, c->sort_vals, c->tailflag);
-  c->launches += 1 + rsort::sort_pairs(&c->sort_keys, &c->sort_vals, n_tiles, c->loc_key_bits + 16, &c->sort_scratch, s);
+  const int key_bits = c->loc_key_bits + 17;   // [off-road][locality key][pos16]
+  k_make_keys<<<n_pad / 256, 256, 0, s>>>(p, par, key_bits, c->sort_keys, c->sort_vals, c->tailflag);
+  c->launches += 1 + rsort::sort_pairs(&c->sort_keys, &c->sort_vals, n_tiles, key_bits, &c->sort_scratch, s);
   k_inverse<<<n_pad / 256, 256, 0, s>>>(c->sort_vals, n_pad, c->newslot);
   // the valid pos buffer is the one of parity `par`
   c->cur8[P8_POS] = (uint64_t*)p.pos[par];
@@ -1021,13 +1106,13 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   TRY(dev_alloc(c, pool, &p.ahead_new, cap));
   TRY(dev_alloc(c, pool, &p.inbox_next, cap));
   TRY(dev_alloc(c, pool, &p.dead_mark, cap));
-  TRY(dev_alloc(c, pool, &p.movers, cap));
   TRY(dev_alloc(c, pool, &p.touched, 2 * cap));
-  TRY(dev_alloc(c, pool, &p.counters, 4));
+  TRY(dev_alloc(c, pool, &p.slow, cap));
+  TRY(dev_alloc(c, pool, &p.counters, 2 * CNT_STRIDE));
   TRY(dev_alloc(c, pool, &p.scal, SC_COUNT));
   for (void* z : {(void*)p.mv_old, (void*)p.ahead_new, (void*)p.inbox_next, (void*)p.dead_mark})
     CUDA_TRY(c, cudaMemset(z, 0, (size_t)cap * sizeof(int32_t)));
-  CUDA_TRY(c, cudaMemset(p.counters, 0, 4 * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMemset(p.counters, 0, 2 * CNT_STRIDE * sizeof(int32_t)));
   {
     int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, 0};
     CUDA_TRY(c, cudaMemcpy(p.scal, scal, sizeof(scal), cudaMemcpyHostToDevice));
@@ -1098,23 +1183,26 @@ int finish_step(Ctx* c) {
   return fail(c, GRIDDY_ERR_BAD_STATE, m);
 }
 
-// One tick = three launches (plus a reorder every reorder_period ticks).  ev (optional) receives 5
-// events bracketing reorder, k_advance, k_relink, k_settle.
+// One tick = four launches (plus a reorder every reorder_period ticks).  ev (optional) receives 6
+// events bracketing reorder, k_advance, k_slow, k_relink, k_settle.
 int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   if (ev) cudaEventRecord(ev[0], c->stream);
   if (c->reorder_period > 0 && tick % c->reorder_period == 0 && tick != c->last_reorder_tick)
     TRY(reorder_slots(c, tick));
   const Params& p = c->p;
-  const unsigned adv_blocks = (unsigned)((c->ns_host + 255) / 256);
-  const unsigned aux_blocks = std::min<unsigned>(std::max(adv_blocks, 1u), 148u * 8u);
+  const unsigned per_block = ADV_THREADS * ADV_UNROLL;
+  const unsigned adv_blocks = (unsigned)((c->ns_host + per_block - 1) / per_block);
+  const unsigned aux_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host + 255) / 256), 1u), 148u * 8u);
   if (ev) cudaEventRecord(ev[1], c->stream);
-  k_advance<<<adv_blocks, 256, 0, c->stream>>>(p, (int)tick);
+  k_advance<<<adv_blocks, ADV_THREADS, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[2], c->stream);
-  k_relink<<<aux_blocks * 2, 128, 0, c->stream>>>(p, (int)tick);
+  k_slow<<<aux_blocks * 2, SLOW_THREADS, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[3], c->stream);
-  k_settle<<<aux_blocks, 256, 0, c->stream>>>(p, (int)tick);
+  k_relink<<<aux_blocks * 2, 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[4], c->stream);
-  c->launches += 3;
+  k_settle<<<aux_blocks, 256, 0, c->stream>>>(p, (int)tick);
+  if (ev) cudaEventRecord(ev[5], c->stream);
+  c->launches += 4;
   return GRIDDY_OK;
 }
 
@@ -1145,15 +1233,15 @@ int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms) {
   if (!c->have_actors || !kernel_ms) return fail(c, GRIDDY_ERR_BAD_ARG, "profile_step: no actors or null output");
   if (n_ticks < 0 || c->tick + n_ticks > INT32_MAX - 2) return fail(c, GRIDDY_ERR_BAD_ARG, "bad n_ticks");
   CUDA_TRY(c, cudaSetDevice(c->device));
-  cudaEvent_t ev[5];
+  cudaEvent_t ev[6];
   for (auto& e : ev) CUDA_TRY(c, cudaEventCreate(&e));
   double total = 0.0;
   for (int64_t t = 0; t < n_ticks && c->ns_host > 0; ++t) {
     TRY(launch_tick(c, c->tick + t, ev));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    // kernel_ms = {k_advance, k_relink, k_settle, reorder}
-    static const int slot_of[4] = {3, 0, 1, 2};
-    for (int k = 0; k < 4; ++k) {
+    // kernel_ms = {k_advance, k_relink, k_settle, reorder, k_slow}
+    static const int slot_of[5] = {3, 0, 4, 1, 2};
+    for (int k = 0; k < 5; ++k) {
       float ms = 0.f;
       CUDA_TRY(c, cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
       kernel_ms[slot_of[k]] += ms;

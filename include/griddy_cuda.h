@@ -125,8 +125,8 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
 int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_count);
 
 /* Like griddy_step, but brackets every kernel launch with CUDA events on the launching stream and
- * adds the per-kernel device time, in ms summed over the n_ticks, to kernel_ms[0..3] =
- * {k_advance, k_relink, k_settle, reorder (all its launches)}.  For roofline accounting only: the
+ * adds the per-kernel device time, in ms summed over the n_ticks, to kernel_ms[0..4] =
+ * {k_advance, k_relink, k_settle, reorder (all its launches), k_slow}.  For roofline accounting only: the
  * events serialise launches. */
 int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms);
 
