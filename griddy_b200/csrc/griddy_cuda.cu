@@ -94,6 +94,12 @@ constexpr int CNT_TOUCHED = 1, CNT_SLOW = 2, CNT_STRIDE = 4;
 // device scalars (Params::scal)
 constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_COUNT = 4;
 
+// st and ahead of a slot share an 8-byte word: every kernel that walks a lane needs both.
+struct __align__(8) SA {
+  uint32_t st;
+  int32_t ahead;
+};
+
 struct Params {
   // network, by registration index
   int64_t n_items;
@@ -105,14 +111,15 @@ struct Params {
   int32_t grid_n;
   const int32_t *lane_from_j, *lane_to_j, *turn4;
   int32_t *lane_tail, *occ, *lane_mark, *inbox_head;
+  int32_t* lane_ghost;   // tick+1 when a resident of the lane was found to be a ghost during `tick`
   // slots
   int32_t cap;     // allocated slots
   int32_t* scal;   // SC_*: device error bits, slots in use, live actors counted by the reorder
-  uint32_t* st;
-  int32_t* ahead;
+  SA* sa;          // {st, ahead}: one 8-byte load per actor
   double* pos[2];
   double *delta, *buf;
   int32_t *aux, *container, *agenda_cur, *route_cur, *id;
+  int32_t* tj;   // junction of the lane the route head turns onto, -1 if that is not a junction lane
   double* arrive;
   int32_t *land_tick, *land_lane;
   double* land_pos;
@@ -171,6 +178,11 @@ __device__ int32_t route_head_on(const Params& p, int32_t lane, int32_t item, in
   return hop;
 }
 
+// The junction whose occupancy gates a (turn-onto lane) head (route.scm:105-108), or -1.
+__device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop) {
+  return (hop >= 0 && p.kind[hop] == GRIDDY_JUNCTION_LANE) ? p.lane_junction[hop] : -1;
+}
+
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
 __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t id, int32_t ac, int32_t* aux) {
   if (ac >= p.agenda_off[id + 1]) { *aux = 0; return HEAD_NONE; }
@@ -213,10 +225,12 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   if (ah >= 0 && lead == cur) {
     do {
       p.dead_mark[ah] = tick + 1;
-      ah = p.ahead[ah];
+      ah = p.sa[ah].ahead;
       if (ah >= 0) lead = pos_old[ah];
     } while (ah >= 0 && lead == cur);
-    mark_touched(p, p.container[a], tick, sink);
+    const int32_t lane = p.container[a];
+    p.lane_ghost[lane] = tick + 1;
+    mark_touched(p, lane, tick, sink);
   }
 
   if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {   // advance-on-route$  route.scm:137-141
@@ -227,7 +241,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
       const double target = p.arrive[a];
       if (!(next >= target)) return next;
       const bool back = target < cur;
-      p.st[a] = (st & ~((3u << ST_RS_SHIFT) | ST_ARRIVE)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u);
+      p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_ARRIVE)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u);
       if (back) {   // jumped back past other residents: re-insert by key
         const int32_t lane = p.container[a];
         p.mv_old[a] = lane;
@@ -237,8 +251,9 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     }
     // route-step/turn-onto$  route.scm:92-135
     if (!(next >= 1.0)) return next;
+    const int32_t tj = p.tj[a];   // junction-full?  route.scm:98-108 (k_advance has usually answered this)
+    if (tj >= 0 && p.occ[tj] > 0) return cur;   // waiting
     const int32_t target = p.aux[a];
-    if (p.kind[target] == GRIDDY_JUNCTION_LANE && p.occ[p.lane_junction[target]] > 0) return cur;   // waiting
     const int32_t id = p.id[a];
     const int32_t lane = p.container[a];
     const int32_t item = p.agenda_cur[a];
@@ -250,7 +265,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const double tbuf = __ddiv_rn(p.two_size, tlen);
     double tnext = __dmul_rn(__dmul_rn(speed, time_remaining), tinv);   // (+ 0 delta)
     int32_t x = p.lane_tail[target];
-    while (x >= 0 && !(pos_old[x] > 0.0)) x = p.ahead[x];   // smallest key in (0, ...]
+    while (x >= 0 && !(pos_old[x] > 0.0)) x = p.sa[x].ahead;   // smallest key in (0, ...]
     if (x >= 0) {
       const double tlead = pos_old[x];
       if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
@@ -259,11 +274,12 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const int32_t nhop = route_head_on(p, target, item, &rc);
     if (p.route_off) p.route_cur[a] = rc;
     p.aux[a] = nhop;
+    p.tj[a] = junction_of_hop(p, nhop);
     p.delta[a] = __dmul_rn(p.speed_dt[id], tinv);
     p.buf[a] = tbuf;
     p.container[a] = target;
     p.mv_old[a] = lane;
-    p.st[a] = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
+    p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
     enter_lane(p, a, target, tick, sink);
     mark_touched(p, lane, tick, sink);
     return tnext;
@@ -278,7 +294,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
       const uint32_t h = load_head(p, p.id[a], ac, &aux);
       p.agenda_cur[a] = ac;
       p.aux[a] = aux;
-      p.st[a] = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
+      p.sa[a].st = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
     } else {
       p.aux[a] = t - 1;
     }
@@ -306,11 +322,12 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     p.route_cur[a] = rc;
     p.arrive[a] = dest_pos;
     p.aux[a] = hop;
+    p.tj[a] = junction_of_hop(p, hop);
     p.delta[a] = __dmul_rn(p.speed_dt[p.id[a]], __ddiv_rn(1.0, len));
     p.buf[a] = __ddiv_rn(p.two_size, len);
     p.container[a] = init_lane;
     p.mv_old[a] = ~seg;
-    p.st[a] = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
+    p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
               ST_ONROAD | ST_MOVED | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);
     enter_lane(p, a, init_lane, tick, sink);
     return init_pos;
@@ -334,7 +351,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   p.land_pos[a] = cur;
   uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE);
   ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
-  p.st[a] = ns;
+  p.sa[a].st = ns;
   mark_touched(p, lane, tick, sink);
   return dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
 }
@@ -344,8 +361,9 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 // ADV_UNROLL actors are issued before the first use (one slot per thread leaves too few bytes in
 // flight to cover HBM latency): first st / ahead / pos, then the leaders' pos-params (a gather that
 // the slot order keeps inside the same or a neighbouring cache line) with delta / buf.
-// Handled here: an actor on its route that neither reaches the end of its lane nor has an
-// (arrive-at _) head; a sleeper whose time has not run out; an idle actor.  These touch only the hot
+// Handled here: an actor on its route that has no (arrive-at _) head and either stays on its lane
+// or waits at its end for a full junction (the junction-occupancy table is small enough to live in
+// L2); a sleeper whose time has not run out; an idle actor.  These touch only the hot
 // arrays.  Any other actor — a few percent — would drag its whole warp through chains of dependent
 // gathers, so its slot is appended to the slow list instead (block-aggregated: one global atomic per
 // block) and k_slow runs the full advance$ for it with one thread per listed actor.
@@ -367,14 +385,15 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
   double* __restrict__ pos_new = p.pos[par ^ 1];
 
   uint32_t st[ADV_UNROLL];
-  int32_t ah[ADV_UNROLL], slp[ADV_UNROLL];
+  int32_t ah[ADV_UNROLL], slp[ADV_UNROLL], tj[ADV_UNROLL];
   double cur[ADV_UNROLL], dlt[ADV_UNROLL], buf[ADV_UNROLL], lead[ADV_UNROLL];
 #pragma unroll
   for (int k = 0; k < ADV_UNROLL; ++k) {
     const int a = base + k * ADV_THREADS;
     const bool in = a < n;
-    st[k] = in ? p.st[a] : 0u;
-    ah[k] = in ? p.ahead[a] : -1;
+    const SA sa = in ? p.sa[a] : SA{0u, -1};
+    st[k] = sa.st;
+    ah[k] = sa.ahead;
     cur[k] = in ? pos_old[a] : 0.0;
   }
 #pragma unroll
@@ -388,6 +407,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
     lead[k] = ah[k] >= 0 ? pos_old[ah[k]] : 0.0;
     dlt[k] = on_route ? p.delta[a] : 0.0;
     buf[k] = on_route ? p.buf[a] : 0.0;
+    tj[k] = (on_route && !(st[k] & ST_ARRIVE)) ? p.tj[a] : -1;
     slp[k] = (alive && rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) ? p.aux[a] : 0;
   }
 #pragma unroll
@@ -402,8 +422,10 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
         // get-pos-param-next on the current lane (route.scm:53-74)
         double next = __dadd_rn(cur[k], dlt[k]);
         if (ah[k] >= 0 && lead[k] > cur[k] && lead[k] <= __dadd_rn(next, buf[k])) next = __dsub_rn(lead[k], buf[k]);
-        if ((st[k] & ST_ARRIVE) || next >= 1.0) slow = true;
-        else np = next;
+        if (st[k] & ST_ARRIVE) slow = true;
+        else if (!(next >= 1.0)) np = next;
+        else if (tj[k] >= 0 && p.occ[tj[k]] > 0) np = cur[k];   // waiting for a full junction  route.scm:98-111
+        else slow = true;                                          // turns onto the next lane
       } else if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {   // sleep$, time left  simulate.scm:77
         if (slp[k] == 0) slow = true;
         else p.aux[a] = slp[k] - 1;
@@ -439,11 +461,12 @@ __global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
     const int32_t i = chunk + threadIdx.x;
     if (i < n_slow) {
       const int a = p.slow[i];
-      const uint32_t st = p.st[a];
+      const SA sa = p.sa[a];
+      const uint32_t st = sa.st;
       const double cur = pos_old[a];
       const bool on_road = st & ST_ONROAD;
       const bool on_route = on_road && ((st >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME;
-      const int32_t ah = on_road ? p.ahead[a] : -1;
+      const int32_t ah = on_road ? sa.ahead : -1;
       const double lead = ah >= 0 ? pos_old[ah] : 0.0;
       const double dlt = on_route ? p.delta[a] : 0.0;
       const double buf = on_route ? p.buf[a] : 0.0;
@@ -477,7 +500,7 @@ __device__ __forceinline__ bool stamp_less(const Params& p, int a, int b, uint32
 // Is a before b in their segment's list at `tick`?  The list reverses every tick (core.scm:169-171
 // conses while get-actors walks head to tail), so a stamp's sign alternates with tick parity.
 __device__ bool offroad_before(const Params& p, int a, int b, int tick) {
-  const uint32_t sta = p.st[a], stb = p.st[b];
+  const uint32_t sta = p.sa[a].st, stb = p.sa[b].st;
   const bool nega = (((tick - p.land_tick[a]) & 1) != 0) == ((sta & ST_CLASS_P) != 0);
   const bool negb = (((tick - p.land_tick[b]) & 1) != 0) == ((stb & ST_CLASS_P) != 0);
   if (nega != negb) return nega;
@@ -487,7 +510,7 @@ __device__ bool offroad_before(const Params& p, int a, int b, int tick) {
 // Of two actors landing on the same (lane, pos-param) this tick: the one visited later, which is
 // the one bbtree-set keeps (core.scm:173-178).
 __device__ int later_processed(const Params& p, int x, int y, int32_t lane, const double* pos_old, int tick) {
-  const uint32_t sx = p.st[x], sy = p.st[y];
+  const uint32_t sx = p.sa[x].st, sy = p.sa[y].st;
   const int32_t mx = (sx & ST_MOVED) ? p.mv_old[x] : lane, my = (sy & ST_MOVED) ? p.mv_old[y] : lane;
   const int32_t cx = mx < 0 ? ~mx : mx, cy = my < 0 ? ~my : my;
   if (cx != cy) return cx < cy ? x : y;
@@ -507,19 +530,21 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
     const int32_t inbox = p.inbox_head[lane];
     p.inbox_head[lane] = -1;
     const bool jl = p.kind[lane] == GRIDDY_JUNCTION_LANE;
+    const bool has_ghost = p.lane_ghost[lane] == tick + 1;   // else no resident's dead_mark needs a look
 
     // Residents that stay, in list order (they keep their relative order: route.scm:68-74).
     // Ghosts found this tick are unlinked here; one that also moved is finalised by k_settle.
     auto next_resident = [&](int32_t z) {
       while (z >= 0) {
-        const uint32_t sz = p.st[z];
-        const bool ghost = p.dead_mark[z] == tick + 1;
+        const SA sa = p.sa[z];
+        const uint32_t sz = sa.st;
+        const bool ghost = has_ghost && p.dead_mark[z] == tick + 1;
         if (!(sz & ST_MOVED) && !ghost) break;
         if (ghost && !(sz & ST_MOVED)) {
-          p.st[z] = sz & ~ST_ALIVE;
+          p.sa[z].st = sz & ~ST_ALIVE;
           if (jl) atomicSub(&p.occ[p.lane_junction[lane]], 1);
         }
-        z = p.ahead[z];
+        z = sa.ahead;
       }
       return z;
     };
@@ -544,15 +569,15 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
     int32_t prev = -1, pending = -1;
     auto commit = [&](int32_t z) {
       if (prev < 0) p.lane_tail[lane] = z;
-      else if (p.st[prev] & ST_MOVED) p.ahead_new[prev] = z;
-      else p.ahead[prev] = z;
+      else if (p.sa[prev].st & ST_MOVED) p.ahead_new[prev] = z;
+      else p.sa[prev].ahead = z;
       prev = z;
     };
     while (x >= 0 || e >= 0) {
       int32_t cand;
       if (e < 0 || (x >= 0 && pos_new[x] <= e_pos)) {
         cand = x;
-        x = next_resident(p.ahead[x]);
+        x = next_resident(p.sa[x].ahead);
       } else {
         cand = e;
         next_entrant(false);
@@ -562,8 +587,8 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
       } else if (pos_new[cand] == pos_new[pending]) {   // equal key: bbtree-set keeps the later one
         const int32_t win = later_processed(p, cand, pending, lane, pos_old, tick);
         const int32_t lose = win == cand ? pending : cand;
-        const uint32_t sl = p.st[lose];
-        p.st[lose] = sl & ~ST_ALIVE;
+        const uint32_t sl = p.sa[lose].st;
+        p.sa[lose].st = sl & ~ST_ALIVE;
         if (jl && !(sl & ST_MOVED)) atomicSub(&p.occ[p.lane_junction[lane]], 1);
         pending = win;
       } else {
@@ -573,8 +598,8 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
     }
     if (pending >= 0) commit(pending);
     if (prev < 0) p.lane_tail[lane] = -1;
-    else if (p.st[prev] & ST_MOVED) p.ahead_new[prev] = -1;
-    else p.ahead[prev] = -1;
+    else if (p.sa[prev].st & ST_MOVED) p.ahead_new[prev] = -1;
+    else p.sa[prev].ahead = -1;
   }
 }
 
@@ -584,20 +609,20 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
   const int32_t n_slow = p.counters[CNT_STRIDE * par + CNT_SLOW];   // movers are among the deferred actors
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slow; i += gridDim.x * blockDim.x) {
     const int a = p.slow[i];
-    const uint32_t st = p.st[a];
+    const uint32_t st = p.sa[a].st;
     if (!(st & ST_MOVED)) continue;
     const int32_t old = p.mv_old[a];
     if (old >= 0 && p.kind[old] == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[p.lane_junction[old]], 1);
     if (p.dead_mark[a] == tick + 1) {   // it was a ghost when it moved: the move is void
-      p.st[a] = st & ~(ST_MOVED | ST_ALIVE);
+      p.sa[a].st = st & ~(ST_MOVED | ST_ALIVE);
       continue;
     }
     if ((st & ST_ALIVE) && (st & ST_ONROAD)) {
-      p.ahead[a] = p.ahead_new[a];
+      p.sa[a].ahead = p.ahead_new[a];
       const int32_t lane = p.container[a];
       if (p.kind[lane] == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[p.lane_junction[lane]], 1);
     }
-    p.st[a] = st & ~ST_MOVED;
+    p.sa[a].st = st & ~ST_MOVED;
   }
 }
 
@@ -606,9 +631,9 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
 // per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
 
 // Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
-constexpr int PERM4 = 9, PERM8 = 5;
-enum { P4_ST, P4_CONTAINER, P4_AHEAD, P4_AUX, P4_AGENDA_CUR, P4_ROUTE_CUR, P4_ID, P4_LAND_TICK, P4_LAND_LANE };
-enum { P8_POS, P8_DELTA, P8_BUF, P8_ARRIVE, P8_LAND_POS };
+constexpr int PERM4 = 8, PERM8 = 6;
+enum { P4_CONTAINER, P4_AUX, P4_AGENDA_CUR, P4_ROUTE_CUR, P4_ID, P4_LAND_TICK, P4_LAND_LANE, P4_TJ };
+enum { P8_SA, P8_POS, P8_DELTA, P8_BUF, P8_ARRIVE, P8_LAND_POS };
 
 struct Permute {
   const uint32_t* src4[PERM4];
@@ -625,7 +650,7 @@ __global__ void __launch_bounds__(256) k_make_keys(Params p, int par, int key_bi
   uint32_t val = 0xffffffffu;
   bool live = false;
   if (s < p.scal[SC_NSLOTS]) {
-    const uint32_t st = p.st[s];
+    const uint32_t st = p.sa[s].st;
     if (st & ST_ALIVE) {
       live = true;
       const int32_t c = p.container[s];
@@ -658,21 +683,22 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
   if (s >= p.scal[SC_NALIVE]) return;
   const uint32_t old = vals[s];
 #pragma unroll
-  for (int k = 0; k < PERM4; ++k) {
-    uint32_t v = q.src4[k][old];
-    if (k == P4_AHEAD) {   // meaningful on the road only; an off-road actor's value is stale
-      if ((q.src4[P4_ST][old] & ST_ONROAD) && (int32_t)v >= 0) {
-        const int32_t nv = newslot[v];
-        if (nv < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's leader must be live
-        v = (uint32_t)nv;
-      } else {
-        v = 0xffffffffu;
-      }
-    }
-    q.dst4[k][s] = v;
-  }
+  for (int k = 0; k < PERM4; ++k) q.dst4[k][s] = q.src4[k][old];
 #pragma unroll
-  for (int k = 0; k < PERM8; ++k) q.dst8[k][s] = q.src8[k][old];
+  for (int k = 0; k < PERM8; ++k) {
+    if (k == P8_SA) {   // ahead is meaningful on the road only; an off-road actor's value is stale
+      SA sa = ((const SA*)q.src8[k])[old];
+      if ((sa.st & ST_ONROAD) && sa.ahead >= 0) {
+        sa.ahead = newslot[sa.ahead];
+        if (sa.ahead < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's leader must be live
+      } else {
+        sa.ahead = -1;
+      }
+      ((SA*)q.dst8[k])[s] = sa;
+    } else {
+      q.dst8[k][s] = q.src8[k][old];
+    }
+  }
   if (tailflag[old]) p.lane_tail[q.src4[P4_CONTAINER][old]] = s;
 }
 
@@ -683,11 +709,11 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
 __global__ void __launch_bounds__(256) k_flag_ghosts(Params p, int par, uint8_t* ghost) {
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.st[a];
+  const uint32_t st = p.sa[a].st;
   if ((st & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD)) return;
   const double* pos = p.pos[par];
   const double cur = pos[a];
-  for (int32_t x = p.ahead[a]; x >= 0 && pos[x] == cur; x = p.ahead[x]) ghost[x] = 1;
+  for (int32_t x = p.sa[a].ahead; x >= 0 && pos[x] == cur; x = p.sa[x].ahead) ghost[x] = 1;
 }
 
 struct PackOut {
@@ -699,7 +725,7 @@ struct PackOut {
 __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uint8_t* ghost, PackOut o) {
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.st[a];
+  const uint32_t st = p.sa[a].st;
   const int32_t id = p.id[a];
   const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
   const int32_t aux = p.aux[a];
@@ -799,9 +825,9 @@ int bits_for(uint32_t max_value) {   // bits that hold 0..max_value with all-one
 // Point Params at the current buffers of the permuted arrays.
 void bind_slot_arrays(Ctx* c, int par) {
   Params& p = c->p;
-  p.st = c->cur4[P4_ST];
+  p.sa = (SA*)c->cur8[P8_SA];
   p.container = (int32_t*)c->cur4[P4_CONTAINER];
-  p.ahead = (int32_t*)c->cur4[P4_AHEAD];
+  p.tj = (int32_t*)c->cur4[P4_TJ];
   p.aux = (int32_t*)c->cur4[P4_AUX];
   p.agenda_cur = (int32_t*)c->cur4[P4_AGENDA_CUR];
   p.route_cur = (int32_t*)c->cur4[P4_ROUTE_CUR];
@@ -953,6 +979,7 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   TRY(dev_alloc(c, c->net_allocs, &p.occ, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.lane_mark, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.inbox_head, n_items));
+  TRY(dev_alloc(c, c->net_allocs, &p.lane_ghost, n_items));
   c->h_kind.assign(kind, kind + n_items);
   c->h_lane_junction.assign(lane_junction, lane_junction + n_items);
   c->have_net = true;
@@ -1043,8 +1070,8 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   auto& pool = c->actor_allocs;
 
   // Initial world: link! every actor in id order (core.scm:169-178).  Slot = id until the first reorder.
-  std::vector<uint32_t> st(n);
-  std::vector<int32_t> aux(n, 0), acur(n), ahead(n, -1), ident(n);
+  std::vector<SA> sa(n);
+  std::vector<int32_t> aux(n, 0), acur(n), ident(n);
   std::vector<int32_t> lane_tail(p.n_items, -1), occ(p.n_items, 0);
   std::vector<int32_t> on_road;
   for (int64_t a = 0; a < n; ++a) {
@@ -1056,7 +1083,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     }
     if (loc_kind[a]) { s |= ST_ONROAD; on_road.push_back((int32_t)a); }
     else if (side[a]) s |= ST_SIDE;
-    st[a] = s;
+    sa[a] = SA{s, -1};
     ident[a] = (int32_t)a;   // also the landing stamp of the initial placement: tick 0, link! order
   }
   // lanes: ascending pos-param; an equal key replaces the earlier actor (bbtree-set)
@@ -1069,9 +1096,9 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   for (size_t k = 0; k < on_road.size(); ++k) {
     const int32_t a = on_road[k];
     const bool replaced = k + 1 < on_road.size() && container[on_road[k + 1]] == container[a] && pos[on_road[k + 1]] == pos[a];
-    if (replaced) { st[a] &= ~ST_ALIVE; continue; }
+    if (replaced) { sa[a].st &= ~ST_ALIVE; continue; }
     const int32_t lane = container[a];
-    if (prev >= 0 && container[prev] == lane) ahead[prev] = a; else lane_tail[lane] = a;
+    if (prev >= 0 && container[prev] == lane) sa[prev].ahead = a; else lane_tail[lane] = a;
     if (c->h_kind[lane] == GRIDDY_JUNCTION_LANE) ++occ[c->h_lane_junction[lane]];
     prev = a;
   }
@@ -1088,9 +1115,9 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     CUDA_TRY(c, cudaMemset(c->cur8[k], 0, (size_t)cap * sizeof(uint64_t)));
   }
   auto put4 = [&](int k, const void* host) { return n ? cudaMemcpy(c->cur4[k], host, (size_t)n * 4, cudaMemcpyHostToDevice) : cudaSuccess; };
-  CUDA_TRY(c, put4(P4_ST, st.data()));
+  if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SA], sa.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(c, put4(P4_CONTAINER, container));
-  CUDA_TRY(c, put4(P4_AHEAD, ahead.data()));
+  CUDA_TRY(c, cudaMemset(c->cur4[P4_TJ], 0xFF, (size_t)cap * sizeof(int32_t)));
   CUDA_TRY(c, put4(P4_AUX, aux.data()));
   CUDA_TRY(c, put4(P4_AGENDA_CUR, acur.data()));
   CUDA_TRY(c, put4(P4_ID, ident.data()));
@@ -1152,6 +1179,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   CUDA_TRY(c, cudaMemcpy(p.lane_tail, lane_tail.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMemcpy(p.occ, occ.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMemset(p.lane_mark, 0, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMemset(p.lane_ghost, 0, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
   CUDA_TRY(c, cudaMemset(p.inbox_head, 0xFF, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
   c->tick = 0;
   c->ns_host = (int32_t)n;
@@ -1193,12 +1221,14 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   const unsigned per_block = ADV_THREADS * ADV_UNROLL;
   const unsigned adv_blocks = (unsigned)((c->ns_host + per_block - 1) / per_block);
   const unsigned aux_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host + 255) / 256), 1u), 148u * 8u);
+  // one thread per touched lane where possible: a lane is walked serially, so grid-striding doubles the longest chain
+  const unsigned relink_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host / 8 + 127) / 128), 1u), 148u * 64u);
   if (ev) cudaEventRecord(ev[1], c->stream);
   k_advance<<<adv_blocks, ADV_THREADS, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[2], c->stream);
   k_slow<<<aux_blocks * 2, SLOW_THREADS, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[3], c->stream);
-  k_relink<<<aux_blocks * 2, 128, 0, c->stream>>>(p, (int)tick);
+  k_relink<<<relink_blocks, 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[4], c->stream);
   k_settle<<<aux_blocks, 256, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[5], c->stream);
@@ -1313,12 +1343,14 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
   if (order || n_order) {
     // get-actors order (world.scm:24-30): containers by descending registration index, a lane's
     // actors by descending pos-param, a segment's in list order (landing stamps, see k_relink).
+    std::vector<SA> sa(ns);
     std::vector<uint32_t> st(ns);
     std::vector<uint8_t> ghost(ns);
     std::vector<int32_t> cont(ns), land_tick(ns), land_lane(ns), ident(ns);
     std::vector<double> ps(ns), land_pos(ns);
     auto pull = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess; };
-    CUDA_TRY(c, pull(st.data(), p.st, ns * sizeof(uint32_t)));
+    CUDA_TRY(c, pull(sa.data(), p.sa, ns * sizeof(SA)));
+    for (int32_t a = 0; a < ns; ++a) st[a] = sa[a].st;
     CUDA_TRY(c, pull(ghost.data(), c->d_ghost, ns));
     CUDA_TRY(c, pull(cont.data(), p.container, ns * sizeof(int32_t)));
     CUDA_TRY(c, pull(ident.data(), p.id, ns * sizeof(int32_t)));
@@ -1364,13 +1396,14 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
   CUDA_TRY(c, cudaSetDevice(c->device));
   const Params& p = c->p;
   const int32_t ns = c->ns_host;
+  std::vector<SA> sa(ns);
   std::vector<uint32_t> st(ns);
   std::vector<int32_t> cont(ns), ahead(ns);
   std::vector<double> ps(ns);
   if (ns) {
-    CUDA_TRY(c, cudaMemcpy(st.data(), p.st, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(sa.data(), p.sa, ns * sizeof(SA), cudaMemcpyDeviceToHost));
+    for (int32_t a = 0; a < ns; ++a) { st[a] = sa[a].st; ahead[a] = sa[a].ahead; }
     CUDA_TRY(c, cudaMemcpy(cont.data(), p.container, ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CUDA_TRY(c, cudaMemcpy(ahead.data(), p.ahead, ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
     CUDA_TRY(c, cudaMemcpy(ps.data(), p.pos[c->tick & 1], ns * sizeof(double), cudaMemcpyDeviceToHost));
   }
   // ghost rule: an on-road actor whose list follower holds an equal key is not part of the world
