@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_UPDATE = 80   # 56 mutable R+W, 8 speed, 16 compulsory gathers
+# k_advance's share of those bytes (DESIGN.md "Kernels"): st+ahead 8, pos read 8 + write 8, delta 8,
+# buf 8, turn-onto junction 4; the leader's pos-param is adjacent in slot order (0 extra)
+ADVANCE_BYTES_PER_ACTOR = 44
 
 
 def log(*a):
@@ -105,15 +108,17 @@ def cpu_sample_world(args):
 
 
 def time_oracle(args, ticks):
+    """Living-actor updates per second of the oracle (vanished actors are not advanced, core.scm:173-178)."""
     from oracle.oracle import Oracle
     net, actors, n = cpu_sample_world(args)
     o = Oracle(net, actors)
     o.step(args.spinup)
+    a0 = int(o.state().alive.sum())
     t0 = time.perf_counter()
     o.step(ticks)
     dt = time.perf_counter() - t0
-    alive = int(o.state().alive.sum())
-    return n * ticks / dt, dt, n, alive
+    a1 = int(o.state().alive.sum())
+    return 0.5 * (a0 + a1) * ticks / dt, dt, n, a1
 
 
 def run_reference(args):
@@ -132,10 +137,12 @@ def run_reference(args):
     o.step(args.spinup)
     o.step(args.warmup * ticks_per_step)
     steps = min(args.steps, 50)
+    a0 = int(o.state().alive.sum())
     t0 = time.perf_counter()
     o.step(steps * ticks_per_step)
     dt = time.perf_counter() - t0
-    value = n * steps * ticks_per_step / dt
+    a1 = int(o.state().alive.sum())
+    value = 0.5 * (a0 + a1) * steps * ticks_per_step / dt   # living actors only
     sample = (f"{args.cpu_grid}x{args.cpu_grid} grid, {n} actors (same actors per segment as the "
               f"{args.grid}x{args.grid}/{args.actors} workload), {ticks_per_step} ticks per step after "
               f"{args.spinup} spin-up ticks; C++ restatement of the reference, not Guile")
@@ -171,9 +178,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--profile-ticks", type=int, default=50)
     ap.add_argument("--cpu-grid", type=int, default=64)
-    ap.add_argument("--cpu-ticks", type=int, default=100)
+    ap.add_argument("--cpu-ticks", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reorder-period", type=int, default=64)
+    ap.add_argument("--reorder-period", type=int, default=128)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -216,6 +223,7 @@ def main():
         torch.cuda.synchronize()
 
     sim.step(args.warmup)
+    alive0 = sim.count_alive()
     launches0 = sim.kernel_launches
     sampler = ClockSampler(local_rank)
     barrier()
@@ -228,37 +236,50 @@ def main():
     barrier()
     dev_ms = sim.last_step_ms
     launches = sim.kernel_launches - launches0
+    alive1 = sim.count_alive()
+    # an actor replaced by an equal-key insert is gone (core.scm:173-178) and is not advanced any
+    # more: count the living ones only (mean of before / after; the decline is slow and steady)
+    alive_mean = 0.5 * (alive0 + alive1)
     if world > 1:
         t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
-    total_actors = args.actors * world
-    value = total_actors * args.steps / (dev_ms * 1e-3)
+        t = torch.tensor([alive_mean], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        alive_total = float(t.item())
+    else:
+        alive_total = alive_mean
+    value = alive_total * args.steps / (dev_ms * 1e-3)
 
-    # per-kernel time of the dominant kernel (events around every launch)
+    # per-kernel device time (events around every launch; rank-local)
     kms = sim.profile_step(args.profile_ticks)
-    adv_ms = kms["k_advance"] / args.profile_ticks
+    alive_prof = sim.count_alive()
+    kpt = {k: v / args.profile_ticks for k, v in kms.items()}
+    tick_ms_prof = sum(kpt.values())
     peak, peak_src = measured_peaks()
-    achieved = args.actors * ALGO_BYTES_PER_UPDATE / (adv_ms * 1e-3) / 1e9
+    gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+    whole_tick = gbs(alive_mean * ALGO_BYTES_PER_UPDATE, dev_ms / args.steps)
+    adv = gbs(alive_prof * ADVANCE_BYTES_PER_ACTOR, kpt["k_advance"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("k_advance_dram_bytes_per_launch")
+            traffic = json.load(f).get("tick_dram_bytes")
 
     # e2e: the call a user makes per frame — step one tick, read the world back into host buffers
     n = actors.n
     pin = lambda dt: torch.empty(n, dtype=dt, pin_memory=True).numpy()
     import ctypes as C
-    bufs = [pin(torch.uint8), pin(torch.uint8), pin(torch.int32), pin(torch.uint8), pin(torch.float64),
-            pin(torch.int32), pin(torch.int32), pin(torch.uint8), pin(torch.int32)]
+    # what `draw` reads of every actor (simulate.scm:155-160 -> get-pos, spatial.scm:125-149):
+    # alive, location kind, container, road side, pos-param
+    bufs = [pin(torch.uint8), pin(torch.uint8), pin(torch.int32), pin(torch.uint8), pin(torch.float64)]
     d2h = sum(b.nbytes for b in bufs)
     L = device.lib()
-    ptrs = [b.ctypes.data_as(C.c_void_p) for b in bufs]
+    ptrs = [b.ctypes.data_as(C.c_void_p) for b in bufs] + [None] * 6
 
     def e2e_step():
         sim.step(1)
-        rc = L.griddy_download_actors(sim.h, *ptrs, None, None)
+        rc = L.griddy_download_actors(sim.h, *ptrs)
         assert rc == 0
 
     for _ in range(3):
@@ -273,8 +294,13 @@ def main():
         t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_dt = float(t.item())
-    e2e_value = total_actors * args.e2e_steps / e_dt
     alive = int(bufs[0].sum())
+    if world > 1:
+        t = torch.tensor([float(alive)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_value = float(t.item()) * args.e2e_steps / e_dt
+    else:
+        e2e_value = alive * args.e2e_steps / e_dt
     on_road = int((bufs[0] & bufs[1]).sum())
 
     if rank != 0:
@@ -298,18 +324,29 @@ def main():
         "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": "actor-updates/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": d2h * world,
-                "note": "griddy_step(1) + griddy_download_actors into pinned host arrays per step; the world "
-                        "is uploaded once through the same ABI before the timed region"},
+                "note": "per step: griddy_step(1) + griddy_download_actors of what draw reads (alive, location "
+                        "kind, container, side, pos-param) into pinned host arrays; no per-step input exists: "
+                        "the world is uploaded once through the same ABI before the timed region"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_advance", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        # The tick is four kernels of comparable duration, so the roofline is stated for the whole
+        # tick: 80 algorithmic bytes per living actor over the device time of one tick
+        # of the timed region.  k_advance, the kernel that streams the per-actor state, is given
+        # beside it against its own 44 bytes per actor.
+        "roofline": {"bound": "hbm", "kernel": "whole tick (k_advance + k_slow + k_relink + k_settle + amortised reorder)",
+                     "achieved": whole_tick, "peak": peak, "unit": "GB/s", "frac": whole_tick / peak,
+                     "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_actor_update": ALGO_BYTES_PER_UPDATE,
-                     "kernel_ms_per_tick": {k: v / args.profile_ticks for k, v in kms.items()},
-                     "reorder_period_ticks": args.reorder_period,
-                     "whole_tick_frac": value / world * ALGO_BYTES_PER_UPDATE / 1e9 / peak},
+                     "living_actors": alive_mean,
+                     "k_advance": {"algorithmic_bytes_per_actor": ADVANCE_BYTES_PER_ACTOR, "achieved": adv,
+                                   "frac": adv / peak if adv else None, "ms": kpt["k_advance"]},
+                     "kernel_ms_per_tick": kpt,
+                     "kernel_share_of_tick": {k: v / tick_ms_prof for k, v in kpt.items()} if tick_ms_prof else None,
+                     "reorder_period_ticks": args.reorder_period},
         "cpu_baseline": cpu,
-        "world": {"alive": alive, "on_road": on_road, "wall_s_timed_region": wall},
+        "world": {"alive_before": alive0, "alive_after": alive1, "alive_at_end": alive, "on_road": on_road,
+                  "actors_uploaded": args.actors * world, "wall_s_timed_region": wall,
+                  "note": "value counts living actors only"},
     }
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -716,6 +716,14 @@ __global__ void __launch_bounds__(256) k_flag_ghosts(Params p, int par, uint8_t*
   for (int32_t x = p.sa[a].ahead; x >= 0 && pos[x] == cur; x = p.sa[x].ahead) ghost[x] = 1;
 }
 
+// Living actors of the world: alive and not a ghost.
+__global__ void __launch_bounds__(256) k_count_alive(Params p, const uint8_t* ghost, unsigned long long* out) {
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  const bool live = a < p.scal[SC_NSLOTS] && (p.sa[a].st & ST_ALIVE) && !ghost[a];
+  const uint32_t m = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
 struct PackOut {
   uint8_t *alive, *loc_kind, *side, *route_status;
   int32_t *container, *agenda_cur, *sleep_left, *route_head;
@@ -755,7 +763,7 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // slots
   int32_t ns_host = 0;         // upper bound of the slots in use (refreshed after every step)
-  int reorder_period = 64;
+  int reorder_period = 128;
   int64_t last_reorder_tick = -1;
   int loc_key_bits = 1;
   uint32_t *alt4[PERM4] = {}, *cur4[PERM4] = {};   // double buffers of the permuted arrays
@@ -1423,6 +1431,28 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
     for (int32_t a = 0; a < ns; ++a)
       if ((st[a] & ST_ALIVE) && !ghost[a]) ++lane_count[cont[a]];
   }
+  return GRIDDY_OK;
+}
+
+int griddy_count_alive(void* ctx, int64_t* n_alive) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_actors || !n_alive) return fail(c, GRIDDY_ERR_BAD_ARG, "count_alive: no actors or null output");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  *n_alive = 0;
+  const int32_t ns = c->ns_host;
+  if (ns == 0) return GRIDDY_OK;
+  const unsigned blocks = (unsigned)((ns + 255) / 256);
+  unsigned long long* d_out = (unsigned long long*)c->sort_keys;   // reorder scratch, idle between steps
+  CUDA_TRY(c, cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ghost, 0, (size_t)ns, c->stream));
+  k_flag_ghosts<<<blocks, 256, 0, c->stream>>>(c->p, (int)(c->tick & 1), c->d_ghost);
+  k_count_alive<<<blocks, 256, 0, c->stream>>>(c->p, c->d_ghost, d_out);
+  c->launches += 2;
+  unsigned long long h = 0;
+  CUDA_TRY(c, cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  *n_alive = (int64_t)h;
   return GRIDDY_OK;
 }
 

@@ -24,7 +24,7 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_upload_actors", "griddy_step", "griddy_profile_step", "griddy_download_actors",
            "griddy_download_occupancy", "griddy_last_step_ms", "griddy_tick", "griddy_kernel_launches",
            "griddy_set_locality_keys", "griddy_set_reorder_period", "griddy_slots_in_use",
-           "griddy_debug_sort_pairs")
+           "griddy_debug_sort_pairs", "griddy_count_alive")
 
 
 class GriddyCudaError(RuntimeError):
@@ -118,6 +118,11 @@ class Simulation:
     @property
     def tick(self) -> int:
         return int(lib().griddy_tick(self.h))
+
+    def count_alive(self) -> int:
+        n = C.c_int64(0)
+        self._chk(lib().griddy_count_alive(self.h, C.byref(n)))
+        return int(n.value)
 
     @property
     def slots_in_use(self) -> int:

@@ -1,0 +1,216 @@
+;;; (griddy cuda) — Guile side of the B200 actor-update path.
+;;;
+;;; Binds libgriddy_cuda.so (include/griddy_cuda.h) with (system foreign), flattens a griddy world
+;;; into the structure-of-arrays bytevectors the C ABI takes, and rebuilds GOOPS actors from a
+;;; read-back so that `draw' (griddy/simulate.scm:155-160) keeps working.
+;;;
+;;; NOT EXECUTED IN THIS REPOSITORY'S TEST ENVIRONMENT: the build image has no Guile.  The same
+;;; symbols, argument order and array layouts are exercised through ctypes by griddy_b200/device.py
+;;; and the flattening rules by griddy_b200/flatten.py, which this file mirrors line for line.
+;;;
+;;; Conventions (include/griddy_cuda.h): item id = registration index = N-1-i for position i of
+;;; (ref world 'static-items) (world.scm:21-22 conses); actor ids such that linking the actors in id
+;;; order rebuilds every segment's list: the k-th actor of (get-actors world) gets id M-1-k.
+(define-module (griddy cuda)
+  #:use-module (system foreign)
+  #:use-module (rnrs bytevectors)
+  #:use-module (srfi srfi-1)
+  #:use-module (srfi srfi-69)
+  #:use-module (oop goops)
+  #:use-module (griddy constants)
+  #:use-module (griddy util)
+  #:use-module (griddy core)
+  #:use-module (griddy simulate route)
+  #:export (cuda-open cuda-close cuda-upload-world! cuda-step! cuda-download-world!
+            cuda-last-step-ms))
+
+(define %lib (dynamic-link (or (getenv "GRIDDY_CUDA_LIB") "libgriddy_cuda")))
+
+(define (c-fn name ret . args)
+  (pointer->procedure ret (dynamic-func name %lib) args))
+
+(define %create   (c-fn "griddy_create" int '* int))
+(define %destroy  (c-fn "griddy_destroy" void '*))
+(define %error    (c-fn "griddy_last_error" '* '*))
+(define %const    (c-fn "griddy_set_constants" int '* double double))
+(define %network  (c-fn "griddy_upload_network" int '* int64 '* '* '* '* '* '* '* '*))
+(define %actors   (c-fn "griddy_upload_actors" int '* int64 '* '* '* '* '* '* '* '* '* '* '* '* '* '*))
+(define %step     (c-fn "griddy_step" int '* int64))
+(define %download (c-fn "griddy_download_actors" int '* '* '* '* '* '* '* '* '* '* '* '*))
+(define %step-ms  (c-fn "griddy_last_step_ms" double '*))
+
+(define (check ctx rc)
+  ;; nonzero return -> (throw 'griddy-cuda code message), the reference's throw style (core.scm:83)
+  (unless (zero? rc)
+    (throw 'griddy-cuda rc (pointer->string (%error ctx)))))
+
+(define (cuda-open)
+  (let ((slot (make-bytevector (sizeof '*) 0)))
+    (let ((rc (%create (bytevector->pointer slot) -1)))
+      (unless (zero? rc) (throw 'griddy-cuda rc "griddy_create failed (no CUDA device?)")))
+    (let ((ctx (make-pointer (bytevector-uint-ref slot 0 (native-endianness) (sizeof '*)))))
+      (check ctx (%const ctx
+                         (exact->inexact *simulate/time-step*)     ; constants.scm:38
+                         (exact->inexact (* 2 *actor/size*))))     ; route.scm:62
+      ctx)))
+
+(define (cuda-close ctx) (%destroy ctx))
+(define (cuda-last-step-ms ctx) (%step-ms ctx))
+
+;;; ---- typed bytevector helpers ---------------------------------------------------------------
+(define (make-u8  n) (make-bytevector n 0))
+(define (make-i32 n fill) (let ((bv (make-bytevector (* 4 n))))
+                            (do ((i 0 (1+ i))) ((= i n) bv) (bytevector-s32-native-set! bv (* 4 i) fill))))
+(define (make-i64 n) (make-bytevector (* 8 n) 0))
+(define (make-f64 n) (make-bytevector (* 8 n) 0))
+(define (i32! bv i v) (bytevector-s32-native-set! bv (* 4 i) v))
+(define (i64! bv i v) (bytevector-s64-native-set! bv (* 8 i) v))
+(define (f64! bv i v) (bytevector-ieee-double-native-set! bv (* 8 i) (exact->inexact v)))
+(define (ptr bv) (bytevector->pointer bv))
+(define (dir->int d) (if (eq? d 'forw) 0 1))
+
+;;; ---- flatten the static network -------------------------------------------------------------
+(define (registration-index world)
+  "eq-hash: static item -> registration index (world.scm:21-22)"
+  (let* ((items (get-static-items world))
+         (n (length items))
+         (table (make-hash-table eq?)))
+    (let loop ((l items) (i 0))
+      (unless (null? l)
+        (hash-table-set! table (car l) (- n 1 i))
+        (loop (cdr l) (1+ i))))
+    table))
+
+(define (upload-network! ctx world index)
+  (let* ((n (hash-table-size index))
+         (kind (make-u8 n)) (len (make-f64 n)) (dir (make-u8 n))
+         (seg (make-i32 n -1)) (out (make-i32 n -1)) (jun (make-i32 n -1))
+         (of (make-i32 n -1)) (ob (make-i32 n -1)))
+    (define (id x) (hash-table-ref index x))
+    (define (outer segment side)
+      (catch 'road-has-no-lanes
+        (lambda () (id (ref (off-road->on-road
+                             (make <location/off-road> #:road-segment segment
+                                   #:road-side-direction side #:pos-param 0.0))
+                            'road-lane)))
+        (lambda _ -1)))
+    (hash-table-walk
+     index
+     (lambda (item r)
+       (cond
+        ((is-a? item <road-junction>) (bytevector-u8-set! kind r 0))
+        ((is-a? item <road-segment>)
+         (bytevector-u8-set! kind r 1)
+         (i32! of r (outer item 'forw))                ; location.scm:16-24
+         (i32! ob r (outer item 'back)))
+        ((is-a? item <road-lane/segment>)
+         (bytevector-u8-set! kind r 2)
+         (f64! len r (get-length item))                ; spatial.scm:28-32, host-side fp64
+         (bytevector-u8-set! dir r (dir->int (ref item 'direction)))
+         (i32! seg r (id (ref item 'segment))))
+        ((is-a? item <road-lane/junction>)
+         (bytevector-u8-set! kind r 3)
+         (f64! len r (get-length item))                ; spatial.scm:34-46
+         (i32! out r (id (get-segment-lane item)))     ; core.scm:106-111
+         (i32! jun r (id (ref item 'junction))))
+        (else (bytevector-u8-set! kind r 4)))))
+    (check ctx (%network ctx n (ptr kind) (ptr len) (ptr dir) (ptr seg) (ptr out) (ptr jun)
+                         (ptr of) (ptr ob)))))
+
+;;; ---- flatten actors, agendas and routes -----------------------------------------------------
+(define (upload-actors! ctx world index)
+  ;; id order is the reverse of get-actors order (see header)
+  (let* ((actors (reverse (get-actors world)))
+         (n (length actors))
+         (n-items (apply + (map (lambda (a) (length (ref a 'agenda))) actors)))
+         (loc-kind (make-u8 n)) (container (make-i32 n -1)) (pos (make-f64 n)) (side (make-u8 n))
+         (speed (make-f64 n)) (speed-dt (make-f64 n)) (agenda-off (make-i64 (1+ n)))
+         (item-kind (make-u8 n-items)) (item-sleep (make-i32 n-items 0))
+         (item-seg (make-i32 n-items -1)) (item-side (make-u8 n-items)) (item-pos (make-f64 n-items))
+         (route-off (make-i64 (1+ n-items)))
+         (route-lanes '()) (n-route 0) (k 0))
+    (define (id x) (hash-table-ref index x))
+    (let loop ((l actors) (a 0))
+      (unless (null? l)
+        (let* ((actor (car l)) (loc (ref actor 'location)) (cur #f))
+          (if (is-a? loc <location/on-road>)
+              (begin (bytevector-u8-set! loc-kind a 1)
+                     (i32! container a (id (ref loc 'road-lane))))
+              (begin (i32! container a (id (ref loc 'road-segment)))
+                     (bytevector-u8-set! side a (dir->int (ref loc 'road-side-direction)))
+                     (set! cur loc)))
+          (f64! pos a (ref loc 'pos-param))
+          (f64! speed a (ref actor 'max-speed))
+          ;; exact rational times exact integer stays exact, then one rounding (route.scm:64)
+          (f64! speed-dt a (* (ref actor 'max-speed) *simulate/time-step*))
+          (i64! agenda-off a k)
+          (for-each
+           (lambda (item)
+             (case (car item)
+               ((sleep-for) (i32! item-sleep k (cadr item)))
+               ((travel-to)
+                (let ((dest (cadr item)))
+                  (bytevector-u8-set! item-kind k 1)
+                  (i32! item-seg k (id (ref dest 'road-segment)))
+                  (bytevector-u8-set! item-side k (dir->int (ref dest 'road-side-direction)))
+                  (f64! item-pos k (ref dest 'pos-param))
+                  ;; the reference's own find-route (route.scm:17-51), evaluated at upload: the start
+                  ;; of travel item k is where the previous travel ended (simulate.scm:87-91)
+                  (when cur
+                    (let ((steps (find-route (off-road->on-road cur) (off-road->on-road dest))))
+                      (for-each (lambda (step)
+                                  (when (eq? (car step) 'turn-onto)
+                                    (set! route-lanes (cons (id (cadr step)) route-lanes))
+                                    (set! n-route (1+ n-route))))
+                                steps)))
+                  (set! cur (on-road->off-road (off-road->on-road dest)))))
+               (else (throw 'unknown-agenda-item item)))
+             (set! k (1+ k))
+             (i64! route-off k n-route))
+           (ref actor 'agenda)))
+        (loop (cdr l) (1+ a))))
+    (i64! agenda-off n k)
+    (let ((route-lane (make-i32 (max 1 n-route) -1)))
+      (let fill ((l (reverse route-lanes)) (i 0))
+        (unless (null? l) (i32! route-lane i (car l)) (fill (cdr l) (1+ i))))
+      (check ctx (%actors ctx n (ptr loc-kind) (ptr container) (ptr pos) (ptr side) (ptr speed)
+                          (ptr speed-dt) (ptr agenda-off) (ptr item-kind) (ptr item-sleep)
+                          (ptr item-seg) (ptr item-side) (ptr item-pos) (ptr route-off)
+                          (ptr route-lane))))
+    actors))
+
+(define (cuda-upload-world! ctx world)
+  "Flatten WORLD and upload it.  Returns (index . actors): what cuda-download-world! needs."
+  (let ((index (registration-index world)))
+    (upload-network! ctx world index)
+    (cons index (upload-actors! ctx world index))))
+
+(define (cuda-step! ctx n-ticks)
+  (check ctx (%step ctx n-ticks)))
+
+;;; ---- read the world back into a fresh skeleton ----------------------------------------------
+(define (cuda-download-world! ctx handle make-skeleton)
+  "Build a new world from (make-skeleton) holding the device's actors, for `draw'."
+  (let* ((actors (cdr handle))
+         (n (length actors))
+         (world++ (make-skeleton))
+         (items (list->vector (reverse (get-static-items world++))))   ; id -> item
+         (alive (make-u8 n)) (loc-kind (make-u8 n)) (container (make-i32 n -1)) (side (make-u8 n))
+         (pos (make-f64 n)) (order (make-i32 n -1)) (n-order (make-i64 1)))
+    (check ctx (%download ctx (ptr alive) (ptr loc-kind) (ptr container) (ptr side) (ptr pos)
+                          %null-pointer %null-pointer %null-pointer %null-pointer
+                          (ptr order) (ptr n-order)))
+    ;; link! in reverse get-actors order so that every segment's list comes out as on the device
+    (let ((actor-of (list->vector actors)))
+      (do ((k (1- (bytevector-s64-native-ref n-order 0)) (1- k))) ((< k 0))
+        (let* ((a (bytevector-s32-native-ref order (* 4 k)))
+               (old (vector-ref actor-of a))
+               (new (make <actor> #:max-speed (ref old 'max-speed)))
+               (item (vector-ref items (bytevector-s32-native-ref container (* 4 a))))
+               (p (bytevector-ieee-double-native-ref pos (* 8 a))))
+          (link! new
+                 (if (= 1 (bytevector-u8-ref loc-kind a))
+                     (make <location/on-road> #:road-lane item #:pos-param p)
+                     (make <location/off-road> #:road-segment item #:pos-param p
+                           #:road-side-direction (if (zero? (bytevector-u8-ref side a)) 'forw 'back)))))))
+    world++))

@@ -80,7 +80,7 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
  * not depend on it.  Call after griddy_upload_network and before griddy_upload_actors. */
 int griddy_set_locality_keys(void* ctx, const uint32_t* item_key);
 
-/* Ticks between two reorders of the actor slots (default 64; 0 = never).  Performance only. */
+/* Ticks between two reorders of the actor slots (default 128; 0 = never).  Performance only. */
 int griddy_set_reorder_period(void* ctx, int32_t ticks);
 
 /* Device-side routing table for procedural grids (examples/procedural-grid.scm): the first n*n
@@ -133,6 +133,8 @@ int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms);
 double griddy_last_step_ms(void* ctx);       /* device time of the last griddy_step (CUDA events) */
 int64_t griddy_tick(void* ctx);              /* ticks since upload */
 int64_t griddy_kernel_launches(void* ctx);   /* kernels launched by this context so far */
+/* Actors in the world right now (an actor replaced by an equal-key insert is gone, core.scm:173-178). */
+int griddy_count_alive(void* ctx, int64_t* n_alive);
 int64_t griddy_slots_in_use(void* ctx);      /* device slots holding actors (living, or dead and not yet dropped) */
 
 /* Diagnostics for tests/: the reorder's stable LSD radix sort (csrc/radix_sort.cuh) applied to n

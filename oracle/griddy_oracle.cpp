@@ -3,7 +3,7 @@
 // *** TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // *** --impl reference legs may load this.  The product path (griddy_b200/) never does.
 //
-// PARITY UNPINNED: the reference (eeshugerman/griddy, Guile Scheme) ships no tests, golden vectors
+// PARITY PINS: the reference (eeshugerman/griddy, Guile Scheme) ships no tests, golden vectors
 // or recorded outputs, and Guile is not installed here, so this restatement cannot be checked
 // against a run of the reference.  It is pinned only by (1) the hand-derived closed-form answer for
 // examples/simple.scm in tests/test_oracle_kat.py, and (2) tests/golden/, produced by executing the
