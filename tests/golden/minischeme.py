@@ -1,0 +1,1658 @@
+"""minischeme — a small Scheme evaluator, just large enough to execute the reference's own sources.
+
+TEST INFRASTRUCTURE.  Used only by tests/golden/generate.py, in the build container, to run
+/root/reference/griddy/*.scm and examples/*.scm headless and record what they compute.  The GPU box
+never runs it: only the recorded fixtures travel.
+
+Why: the reference (eeshugerman/griddy) is Guile Scheme with no tests or golden vectors, and Guile is
+not installed here.  Executing the reference's *source text* for the hot path — `simulate`'s `load`
+and `update` closures (simulate.scm:135-153), `advance$` and its handlers, route.scm, core.scm's
+`link!`, util.scm's `ref`/`set!`/`bbtree-find-min` — under an independent evaluator pins the C++
+restatement in oracle/ against transcription errors.  It is NOT a run of Guile: what this evaluator
+itself implements (and therefore assumes about Guile) is listed in tests/golden/README.md.
+
+Implemented: the numeric tower the path needs (exact integers and rationals via `fractions`, flonums as
+Python floats, exact->inexact on mixed operations, left-to-right n-ary folds), proper lists with
+mutation, lexical closures with tail calls, define*/lambda* keyword arguments, quasiquote,
+syntax-rules (literals, ellipsis followed by further patterns), define-macro, (ice-9 match) list
+patterns, srfi-1/26/69 subsets, a module system that respects export lists (so that a module which
+rebinds `+ * -` does not leak them), and a GOOPS subset: define-class with init options, make /
+initialize / next-method, generics merged by name across modules, multi-argument dispatch by class
+precedence.  Third-party code that is not vendored in the reference is replaced by stubs written
+here: pfds bbtrees (sorted tuple + balanced traversal), chickadee vec2 / bezier / matrix3 (fp64), a*
+(binary heap, insertion-order ties), srfi-19 time, srfi-27 random (seeded), arrays, and the SDL game
+loop (`run-game` just captures its #:load / #:update closures).
+"""
+from __future__ import annotations
+
+import heapq
+import math
+import os
+import random
+import re
+import sys
+from fractions import Fraction
+
+sys.setrecursionlimit(20000)
+
+
+# ------------------------------------------------------------------------------------------------
+# data
+class Sym:
+    __slots__ = ("name",)
+    table: dict = {}
+
+    def __new__(cls, name):
+        s = cls.table.get(name)
+        if s is None:
+            s = object.__new__(cls)
+            s.name = name
+            cls.table[name] = s
+        return s
+
+    def __repr__(self):
+        return self.name
+
+
+class Kw:
+    __slots__ = ("name",)
+    table: dict = {}
+
+    def __new__(cls, name):
+        s = cls.table.get(name)
+        if s is None:
+            s = object.__new__(cls)
+            s.name = name
+            cls.table[name] = s
+        return s
+
+    def __repr__(self):
+        return "#:" + self.name
+
+
+class Nil:
+    def __repr__(self):
+        return "()"
+
+    def __iter__(self):
+        return iter(())
+
+
+NIL = Nil()
+
+
+class Unspecified:
+    def __repr__(self):
+        return "#<unspecified>"
+
+
+UNSPEC = Unspecified()
+
+
+class Pair:
+    __slots__ = ("car", "cdr")
+
+    def __init__(self, car, cdr):
+        self.car, self.cdr = car, cdr
+
+    def __iter__(self):
+        p = self
+        while isinstance(p, Pair):
+            yield p.car
+            p = p.cdr
+
+    def __repr__(self):
+        return "(" + " ".join(map(repr, self)) + ")"
+
+
+def slist(items, tail=NIL):
+    r = tail
+    for x in reversed(list(items)):
+        r = Pair(x, r)
+    return r
+
+
+def plist(x):
+    out = []
+    while isinstance(x, Pair):
+        out.append(x.car)
+        x = x.cdr
+    return out
+
+
+S = Sym
+_ELLIPSIS, _UNDERSCORE, _DOT = S("..."), S("_"), S(".")
+
+
+class SchemeThrow(Exception):
+    def __init__(self, key, args):
+        super().__init__(f"throw {key} {args}")
+        self.key, self.args_ = key, args
+
+
+class SchemeError(Exception):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------
+# reader
+_TOKEN = re.compile(r"""\s+|;[^\n]*|#\|.*?\|#|(,@|[()\[\]'`,]|"(?:\\.|[^"\\])*"|[^\s()\[\]";]+)""", re.S)
+_INT = re.compile(r"^[+-]?\d+$")
+_RAT = re.compile(r"^[+-]?\d+/\d+$")
+_FLOAT = re.compile(r"^[+-]?(\d+\.\d*|\.\d+|\d+)([eE][+-]?\d+)?$")
+
+
+def tokenize(text):
+    pos, out = 0, []
+    while pos < len(text):
+        m = _TOKEN.match(text, pos)
+        if not m:
+            raise SchemeError(f"cannot tokenize at {text[pos:pos + 30]!r}")
+        pos = m.end()
+        if m.group(1) is not None:
+            out.append(m.group(1))
+    return out
+
+
+def atom(tok):
+    if tok[0] == '"':
+        return bytes(tok[1:-1], "utf-8").decode("unicode_escape")
+    if tok == "#t" or tok == "#true":
+        return True
+    if tok == "#f" or tok == "#false":
+        return False
+    if tok.startswith("#:"):
+        return Kw(tok[2:])
+    if _INT.match(tok):
+        return int(tok)
+    if _RAT.match(tok):
+        return norm(Fraction(tok))
+    if _FLOAT.match(tok):
+        return float(tok)
+    return Sym(tok)
+
+
+def parse_all(text):
+    toks = tokenize(text)
+    pos = 0
+
+    def read():
+        nonlocal pos
+        tok = toks[pos]
+        pos += 1
+        if tok in ("(", "["):
+            items, tail = [], NIL
+            while toks[pos] not in (")", "]"):
+                if toks[pos] == ".":
+                    pos += 1
+                    tail = read()
+                else:
+                    items.append(read())
+            pos += 1
+            return slist(items, tail)
+        if tok == "'":
+            return slist([S("quote"), read()])
+        if tok == "`":
+            return slist([S("quasiquote"), read()])
+        if tok == ",":
+            return slist([S("unquote"), read()])
+        if tok == ",@":
+            return slist([S("unquote-splicing"), read()])
+        return atom(tok)
+
+    forms = []
+    while pos < len(toks):
+        forms.append(read())
+    return forms
+
+
+# ------------------------------------------------------------------------------------------------
+# numbers
+def norm(x):
+    if isinstance(x, Fraction) and x.denominator == 1:
+        return int(x)
+    return x
+
+
+def is_number(x):
+    return isinstance(x, (int, float, Fraction)) and not isinstance(x, bool)
+
+
+def num_add(a, b):
+    return norm(a + b)
+
+
+def num_sub(a, b):
+    return norm(a - b)
+
+
+def num_mul(a, b):
+    return norm(a * b)
+
+
+def num_div(a, b):
+    if isinstance(a, float) or isinstance(b, float):
+        return float(a) / float(b)     # exact->inexact of the exact operand, then IEEE division
+    return norm(Fraction(a) / Fraction(b))
+
+
+def fold_num(op, unit, args, unary=None):
+    if not args:
+        return unit
+    if len(args) == 1 and unary:
+        return unary(args[0])
+    r = args[0]
+    for a in args[1:]:     # left to right, as Guile folds n-ary arithmetic
+        r = op(r, a)
+    return r
+
+
+# ------------------------------------------------------------------------------------------------
+# procedures, environments, modules
+class Prim:
+    def __init__(self, name, fn):
+        self.name, self.fn = name, fn
+
+    def __repr__(self):
+        return f"#<primitive {self.name}>"
+
+
+class Closure:
+    def __init__(self, req, opt, keys, rest, body, env, name="lambda"):
+        self.req, self.opt, self.keys, self.rest, self.body, self.env, self.name = req, opt, keys, rest, body, env, name
+
+    def __repr__(self):
+        return f"#<procedure {self.name}>"
+
+
+class Macro:
+    def __init__(self, expander, name):
+        self.expander, self.name = expander, name
+
+
+class Env:
+    __slots__ = ("vars", "parent", "module")
+
+    def __init__(self, parent, module=None):
+        self.vars, self.parent, self.module = {}, parent, module if module else (parent.module if parent else None)
+
+    def find(self, sym):
+        e = self
+        while e is not None:
+            if sym in e.vars:
+                return e
+            e = e.parent
+        return None
+
+    def is_toplevel(self):
+        return self.parent is None
+
+
+class Module:
+    def __init__(self, name, interp):
+        self.name, self.interp = name, interp
+        self.env = Env(None, self)
+        self.exports: set = set()
+        self.imports: list = []
+        self.cache, self.cache_version = {}, -1
+
+    def resolve(self, sym, seen=None):
+        """(found, value) for a name as seen from inside this module."""
+        I = self.interp
+        if self.cache_version != I.version:
+            self.cache, self.cache_version = {}, I.version
+        d = self.cache.get(sym)
+        if d is None:
+            d = self.cell(sym)
+            if d is None:
+                return False, None
+            self.cache[sym] = d
+        return True, d[sym]
+
+    def cell(self, sym):
+        """The dictionary that holds the binding (values may change, the holder does not)."""
+        if sym in self.env.vars:
+            return self.env.vars
+        for m in self.imports:
+            d = m.export_cell(sym, set())
+            if d is not None:
+                return d
+        if sym in self.interp.builtins:
+            return self.interp.builtins
+        # hygiene substitute: names a macro template introduces belong to the macro's module
+        for m in self.interp.modules.values():
+            if sym in m.env.vars:
+                return m.env.vars
+        return None
+
+    def export_cell(self, sym, seen):
+        if self in seen or sym not in self.exports:
+            return None
+        seen.add(self)
+        if sym in self.env.vars:
+            return self.env.vars
+        for m in self.imports:       # re-exports
+            d = m.export_cell(sym, seen)
+            if d is not None:
+                return d
+        if sym in self.interp.builtins:
+            return self.interp.builtins
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# GOOPS subset
+class Class:
+    def __init__(self, name, supers, slots):
+        self.name, self.supers, self.direct_slots = name, supers, slots
+        self.cpl = [self]
+        for s in supers:     # depth-first, left to right, duplicates keep their last position
+            for c in s.cpl:
+                if c in self.cpl:
+                    self.cpl.remove(c)
+                self.cpl.append(c)
+        self.slots = []
+        seen = set()
+        for c in self.cpl:
+            for sl in c.direct_slots:
+                if sl["name"] not in seen:
+                    seen.add(sl["name"])
+                    self.slots.append(sl)
+
+    def __repr__(self):
+        return f"#<class {self.name}>"
+
+
+class Instance:
+    def __init__(self, cls):
+        self.cls, self.slots = cls, {}
+
+    def __repr__(self):
+        return f"#<{self.cls.name} {id(self):x}>"
+
+
+class Method:
+    def __init__(self, specs, rest, proc):
+        self.specs, self.rest, self.proc = specs, rest, proc
+
+
+class Generic:
+    def __init__(self, name, default=None):
+        self.name, self.methods, self.default = name, [], default
+
+    def __repr__(self):
+        return f"#<generic {self.name}>"
+
+
+TOP = Class("<top>", [], [])
+C_NUMBER = Class("<number>", [TOP], [])
+C_LIST = Class("<list>", [TOP], [])
+C_PAIR = Class("<pair>", [C_LIST], [])
+C_NULL = Class("<null>", [C_LIST], [])
+C_SYMBOL = Class("<symbol>", [TOP], [])
+C_STRING = Class("<string>", [TOP], [])
+C_BOOLEAN = Class("<boolean>", [TOP], [])
+C_KEYWORD = Class("<keyword>", [TOP], [])
+C_PROCEDURE = Class("<procedure>", [TOP], [])
+C_GENERIC = Class("<generic>", [C_PROCEDURE], [])
+C_CLASS = Class("<class>", [TOP], [])
+C_OBJECT = Class("<object>", [TOP], [])
+C_VEC2 = Class("<vec2>", [TOP], [])
+C_HASHTABLE = Class("<hashtable>", [TOP], [])
+C_BBTREE = Class("<bbtree>", [TOP], [])
+C_TIME = Class("<time>", [TOP], [])
+C_UNKNOWN = Class("<unknown>", [TOP], [])
+
+
+class Vec2:
+    __slots__ = ("x", "y")
+
+    def __init__(self, x, y):
+        self.x, self.y = float(x), float(y)
+
+    def __repr__(self):
+        return f"#<vec2 {self.x} {self.y}>"
+
+
+class Bezier:
+    def __init__(self, p0, p1, p2, p3):
+        self.p = (p0, p1, p2, p3)
+
+
+class HashTable:
+    def __init__(self, by_identity):
+        self.by_identity, self.d = by_identity, {}
+
+    def key(self, k):
+        if self.by_identity and not isinstance(k, (Sym, int, bool)):
+            return ("id", id(k))
+        return to_hashable(k)
+
+
+def to_hashable(k):
+    if isinstance(k, Pair):
+        return ("pair",) + tuple(to_hashable(x) for x in k)
+    if isinstance(k, (Instance, Vec2, HashTable, Closure, Prim, Generic)):
+        return ("id", id(k))
+    return k
+
+
+class BBTree:
+    def __init__(self, items=()):
+        self.items = items     # sorted tuple of (key, value)
+
+
+class Array:
+    def __init__(self, dims, fill):
+        self.dims = dims
+        n = 1
+        for d in dims:
+            n *= d
+        self.data = [fill] * n
+
+
+class Time:
+    pass
+
+
+def class_of(x):
+    if isinstance(x, Instance):
+        return x.cls
+    if isinstance(x, bool):
+        return C_BOOLEAN
+    if is_number(x):
+        return C_NUMBER
+    if isinstance(x, Pair):
+        return C_PAIR
+    if x is NIL:
+        return C_NULL
+    if isinstance(x, Sym):
+        return C_SYMBOL
+    if isinstance(x, str):
+        return C_STRING
+    if isinstance(x, Kw):
+        return C_KEYWORD
+    if isinstance(x, Generic):
+        return C_GENERIC
+    if isinstance(x, (Closure, Prim)):
+        return C_PROCEDURE
+    if isinstance(x, Class):
+        return C_CLASS
+    if isinstance(x, Vec2):
+        return C_VEC2
+    if isinstance(x, HashTable):
+        return C_HASHTABLE
+    if isinstance(x, BBTree):
+        return C_BBTREE
+    if isinstance(x, Time):
+        return C_TIME
+    return C_UNKNOWN
+
+
+def is_a(x, cls):
+    return cls in class_of(x).cpl
+
+
+# ------------------------------------------------------------------------------------------------
+# pattern matching: syntax-rules and (ice-9 match)
+def sr_match(pat, form, lits, b):
+    if isinstance(pat, Sym):
+        if pat in lits:
+            return form is pat
+        if pat is not _UNDERSCORE:
+            b[pat] = form
+        return True
+    if pat is NIL:
+        return form is NIL
+    if isinstance(pat, Pair):
+        if isinstance(pat.cdr, Pair) and pat.cdr.car is _ELLIPSIS:
+            after = pat.cdr.cdr
+            n_after = len(plist(after))
+            items = []
+            f = form
+            while isinstance(f, Pair):
+                items.append(f.car)
+                f = f.cdr
+            avail = len(items) - n_after
+            if avail < 0:
+                return False
+            seqs = []
+            for it in items[:avail]:
+                bb = {}
+                if not sr_match(pat.car, it, lits, bb):
+                    return False
+                seqs.append(bb)
+            for v in pattern_vars(pat.car, lits):
+                b[v] = ("...", [bb[v] for bb in seqs])
+            rest = slist(items[avail:], f)
+            return sr_match(after, rest, lits, b)
+        if not isinstance(form, Pair):
+            return False
+        return sr_match(pat.car, form.car, lits, b) and sr_match(pat.cdr, form.cdr, lits, b)
+    return pat == form and type(pat) is type(form)
+
+
+def pattern_vars(pat, lits):
+    if isinstance(pat, Sym):
+        return [] if (pat in lits or pat is _ELLIPSIS or pat is _UNDERSCORE) else [pat]
+    if isinstance(pat, Pair):
+        return pattern_vars(pat.car, lits) + pattern_vars(pat.cdr, lits)
+    return []
+
+
+def sr_expand(tmpl, b):
+    if isinstance(tmpl, Sym):
+        if tmpl in b:
+            v = b[tmpl]
+            if isinstance(v, tuple) and v and v[0] == "...":
+                raise SchemeError(f"ellipsis variable {tmpl} used without ...")
+            return v
+        return tmpl
+    if isinstance(tmpl, Pair):
+        if isinstance(tmpl.cdr, Pair) and tmpl.cdr.car is _ELLIPSIS:
+            vars_ = [v for v in pattern_vars(tmpl.car, ()) if isinstance(b.get(v), tuple) and b[v][0] == "..."]
+            if not vars_:
+                raise SchemeError("no ellipsis variable in template")
+            n = len(b[vars_[0]][1])
+            out = []
+            for i in range(n):
+                bb = dict(b)
+                for v in vars_:
+                    bb[v] = b[v][1][i]
+                out.append(sr_expand(tmpl.car, bb))
+            return slist(out, sr_expand(tmpl.cdr.cdr, b))
+        return Pair(sr_expand(tmpl.car, b), sr_expand(tmpl.cdr, b))
+    return tmpl
+
+
+def make_syntax_rules(spec, name):
+    # (syntax-rules (literals...) (pattern template)...)
+    lits = set(plist(spec.cdr.car))
+    rules = [(r.car, r.cdr.car) for r in plist(spec.cdr.cdr)]
+
+    def expand(form, env):
+        for pat, tmpl in rules:
+            b = {}
+            if sr_match(pat.cdr, form.cdr, lits, b):
+                return sr_expand(tmpl, b)
+        raise SchemeError(f"no syntax-rules clause of {name} matches {form}")
+
+    return Macro(expand, name)
+
+
+_QUOTE, _DOTDOT1 = S("quote"), S("..1")
+
+
+def equal(a, b):
+    if isinstance(a, Pair) and isinstance(b, Pair):
+        while isinstance(a, Pair) and isinstance(b, Pair):
+            if not equal(a.car, b.car):
+                return False
+            a, b = a.cdr, b.cdr
+        return equal(a, b)
+    if is_number(a) and is_number(b):
+        return (isinstance(a, float) == isinstance(b, float)) and a == b
+    if isinstance(a, str) and isinstance(b, str):
+        return a == b
+    return a is b or (type(a) is type(b) and isinstance(a, (bool,)) and a == b)
+
+
+def m_match(pat, val, b):
+    """(ice-9 match) subset: _, variables, 'literal, atoms, lists with `...` / `..1` anywhere."""
+    if isinstance(pat, Sym):
+        if pat is not _UNDERSCORE:
+            b[pat] = val
+        return True
+    if pat is NIL:
+        return val is NIL
+    if isinstance(pat, Pair):
+        if pat.car is _QUOTE:
+            return equal(pat.cdr.car, val)
+        if isinstance(pat.cdr, Pair) and pat.cdr.car in (_ELLIPSIS, _DOTDOT1):
+            at_least = 1 if pat.cdr.car is _DOTDOT1 else 0
+            after = pat.cdr.cdr
+            n_after = len(plist(after))
+            items, f = [], val
+            while isinstance(f, Pair):
+                items.append(f.car)
+                f = f.cdr
+            avail = len(items) - n_after
+            if avail < at_least:
+                return False
+            seqs = []
+            for it in items[:avail]:
+                bb = {}
+                if not m_match(pat.car, it, bb):
+                    return False
+                seqs.append(bb)
+            for v in pattern_vars(pat.car, ()):
+                b[v] = slist([bb[v] for bb in seqs])
+            return m_match(after, slist(items[avail:], f), b)
+        if not isinstance(val, Pair):
+            return False
+        return m_match(pat.car, val.car, b) and m_match(pat.cdr, val.cdr, b)
+    return equal(pat, val)
+
+
+# ------------------------------------------------------------------------------------------------
+class Interp:
+    def __init__(self, roots, seed=1):
+        self.roots = roots           # directories searched for (a b c) -> a/b/c.scm
+        self.modules: dict = {}
+        self.builtins: dict = {}
+        self.generics: dict = {}
+        self.rng = random.Random(seed)
+        self.captured_game = None    # keyword arguments of the last (run-game ...) call
+        self.version = 0             # bumped whenever a module-level binding appears (lookup caches)
+        self.stub_modules = {("griddy", "draw"), ("griddy", "event-loop")}
+        install_builtins(self)
+        self.user = Module(("user",), self)
+        self.modules[("user",)] = self.user
+
+    # -- modules --------------------------------------------------------------------------------
+    def module(self, name):
+        name = tuple(s.name for s in plist(name)) if not isinstance(name, tuple) else name
+        if name in self.modules:
+            return self.modules[name]
+        if name[0] != "griddy" or name in self.stub_modules:
+            return None              # third-party or stubbed: served from the builtins
+        for root in self.roots:
+            path = os.path.join(root, *name) + ".scm"
+            if os.path.exists(path):
+                return self.load_file(path)
+        raise SchemeError(f"module {name} not found")
+
+    def load_file(self, path, module=None):
+        forms = parse_all(open(path).read())
+        cur = module or self.user
+        for form in forms:
+            if isinstance(form, Pair) and form.car is S("define-module"):
+                cur = self.define_module(form)
+                continue
+            self.eval(form, cur.env)
+        return cur
+
+    def define_module(self, form):
+        name = tuple(s.name for s in plist(form.cdr.car))
+        m = Module(name, self)
+        self.modules[name] = m
+        opts = plist(form.cdr.cdr)
+        i = 0
+        while i < len(opts):
+            k = opts[i]
+            if k is Kw("use-module"):
+                self.use_module(m, opts[i + 1])
+            elif k in (Kw("export"), Kw("re-export"), Kw("replace")):
+                m.exports.update(plist(opts[i + 1]))
+            i += 2
+        return m
+
+    def use_module(self, m, spec):
+        if isinstance(spec.car, Pair):     # ((srfi srfi-1) #:select (...))
+            spec = spec.car
+        dep = self.module(spec)
+        if dep is not None and dep not in m.imports:
+            m.imports.append(dep)
+            self.version += 1
+
+    # -- variables ------------------------------------------------------------------------------
+    def lookup(self, sym, env):
+        e = env.find(sym)
+        if e is not None:
+            return e.vars[sym]
+        ok, v = env.module.resolve(sym)
+        if ok:
+            return v
+        raise SchemeError(f"unbound variable {sym} in module {env.module.name}")
+
+    def binding(self, sym, env):
+        e = env.find(sym)
+        if e is not None:
+            return True, e.vars[sym]
+        return env.module.resolve(sym)
+
+    # -- application ----------------------------------------------------------------------------
+    def apply(self, f, args):
+        if isinstance(f, Prim):
+            return f.fn(*args)
+        if isinstance(f, Closure):
+            env = self.bind(f, args)
+            body = f.body
+            while isinstance(body.cdr, Pair):
+                self.eval(body.car, env)
+                body = body.cdr
+            return self.eval(body.car, env)
+        if isinstance(f, Generic):
+            return self.apply_generic(f, args)
+        if isinstance(f, Class):
+            raise SchemeError(f"cannot apply class {f}")
+        raise SchemeError(f"not a procedure: {f!r}")
+
+    def bind(self, f, args):
+        env = Env(f.env)
+        nreq = len(f.req)
+        if len(args) < nreq:
+            raise SchemeError(f"{f.name}: expected at least {nreq} arguments, got {len(args)}")
+        for p, a in zip(f.req, args):
+            env.vars[p] = a
+        rest = list(args[nreq:])
+        for p, default in f.opt:
+            if rest and not isinstance(rest[0], Kw):
+                env.vars[p] = rest.pop(0)
+            else:
+                env.vars[p] = self.eval(default, env)
+        if f.keys:
+            given = {}
+            i = 0
+            while i + 1 < len(rest) and isinstance(rest[i], Kw):
+                given[rest[i].name] = rest[i + 1]
+                i += 2
+            for p, default in f.keys:
+                env.vars[p] = given[p.name] if p.name in given else self.eval(default, env)
+            if f.rest is not None:
+                env.vars[f.rest] = slist(rest)
+        elif f.rest is not None:
+            env.vars[f.rest] = slist(rest)
+        elif rest:
+            raise SchemeError(f"{f.name}: too many arguments")
+        return env
+
+    def apply_generic(self, g, args):
+        app = []
+        for m in g.methods:
+            n = len(m.specs)
+            if len(args) < n or (len(args) > n and not m.rest):
+                continue
+            ranks = []
+            for spec, a in zip(m.specs, args):
+                cpl = class_of(a).cpl
+                if spec not in cpl:
+                    break
+                ranks.append(cpl.index(spec))
+            else:
+                # unspecialised positions (covered by a rest list) are the least specific
+                app.append((ranks + [10 ** 6] * (len(args) - n), m))
+        if not app:
+            if g.default is not None:
+                return self.apply(g.default, args)
+            raise SchemeError(f"no applicable method for {g.name} on {[class_of(a).name for a in args]}")
+        app.sort(key=lambda t: t[0])
+        chain = [m for _, m in app]
+
+        def call(i, cur_args):
+            if i >= len(chain):
+                if g.default is not None:
+                    return self.apply(g.default, cur_args)
+                raise SchemeError(f"no next method for {g.name}")
+            nm = Prim("next-method", lambda *a: call(i + 1, list(a) if a else cur_args))
+            return self.apply(chain[i].proc, [nm] + list(cur_args))
+
+        return call(0, list(args))
+
+    # -- eval -----------------------------------------------------------------------------------
+    def eval(self, x, env):
+        while True:
+            if isinstance(x, Sym):
+                return self.lookup(x, env)
+            if not isinstance(x, Pair):
+                return x
+            op = x.car
+            special = None
+            if isinstance(op, Sym):
+                found, b = self.binding(op, env)
+                if found and isinstance(b, Macro):
+                    x = b.expander(x, env)
+                    continue
+                if not found and op.name in SPECIAL:
+                    special = op.name
+            elif isinstance(op, Pair) and op.car in (S("@"), S("@@")) and op.cdr.cdr.car.name in SPECIAL \
+                    and tuple(s.name for s in plist(op.cdr.car)) == ("guile",):
+                special = op.cdr.cdr.car.name        # ((@ (guile) set!) var val)
+            if special is not None:
+                r = SPECIAL[special](self, x, env)
+                if isinstance(r, TailCall):
+                    x, env = r.x, r.env
+                    continue
+                return r
+            f = self.eval(op, env)
+            args = [self.eval(a, env) for a in x.cdr]
+            if isinstance(f, Closure):
+                env = self.bind(f, args)
+                body = f.body
+                while isinstance(body.cdr, Pair):
+                    self.eval(body.car, env)
+                    body = body.cdr
+                x = body.car
+                continue
+            return self.apply(f, args)
+
+    def eval_body(self, body, env):
+        """Evaluate all but the last form, return a TailCall for the last."""
+        if body is NIL:
+            return UNSPEC
+        while isinstance(body.cdr, Pair):
+            self.eval(body.car, env)
+            body = body.cdr
+        return TailCall(body.car, env)
+
+    def define(self, sym, val, env):
+        if env.parent is None and sym not in env.vars:
+            self.version += 1
+        env.vars[sym] = val
+        if isinstance(val, Closure) and val.name == "lambda":
+            val.name = sym.name
+
+
+class TailCall:
+    __slots__ = ("x", "env")
+
+    def __init__(self, x, env):
+        self.x, self.env = x, env
+
+
+# ------------------------------------------------------------------------------------------------
+# special forms
+def parse_params(params):
+    """(a b #:optional (c 1) #:key (d 2) e #:rest r . s) -> req, opt, keys, rest"""
+    req, opt, keys, rest = [], [], [], None
+    mode = "req"
+    p = params
+    while isinstance(p, Pair):
+        item = p.car
+        if item is Kw("optional"):
+            mode = "opt"
+        elif item is Kw("key"):
+            mode = "key"
+        elif item is Kw("rest"):
+            rest = p.cdr.car
+            break
+        elif mode == "req":
+            req.append(item)
+        else:
+            name, default = (item.car, item.cdr.car) if isinstance(item, Pair) else (item, False)
+            (opt if mode == "opt" else keys).append((name, default))
+        p = p.cdr
+    if isinstance(p, Sym):
+        rest = p
+    return req, opt, keys, rest
+
+
+def sf_quote(I, x, env):
+    return x.cdr.car
+
+
+def sf_quasiquote(I, x, env):
+    def qq(t, depth):
+        if not isinstance(t, Pair):
+            return t
+        if t.car is S("unquote"):
+            return I.eval(t.cdr.car, env) if depth == 1 else slist([t.car, qq(t.cdr.car, depth - 1)])
+        if t.car is S("quasiquote"):
+            return slist([t.car, qq(t.cdr.car, depth + 1)])
+        if isinstance(t.car, Pair) and t.car.car is S("unquote-splicing") and depth == 1:
+            spliced = plist(I.eval(t.car.cdr.car, env))
+            return slist(spliced, qq(t.cdr, depth))
+        return Pair(qq(t.car, depth), qq(t.cdr, depth))
+    return qq(x.cdr.car, 1)
+
+
+def sf_lambda(I, x, env):
+    req, opt, keys, rest = parse_params(x.cdr.car)
+    return Closure(req, opt, keys, rest, x.cdr.cdr, env)
+
+
+def sf_define(I, x, env, public=False):
+    target = x.cdr.car
+    if isinstance(target, Pair):
+        name = target.car
+        req, opt, keys, rest = parse_params(target.cdr)
+        val = Closure(req, opt, keys, rest, x.cdr.cdr, env, name.name)
+    else:
+        name = target
+        val = I.eval(x.cdr.cdr.car, env) if x.cdr.cdr is not NIL else UNSPEC
+    I.define(name, val, env)
+    if public:
+        env.module.exports.add(name)
+        I.version += 1
+    return UNSPEC
+
+
+def sf_define_public(I, x, env):
+    return sf_define(I, x, env, public=True)
+
+
+def sf_if(I, x, env):
+    if I.eval(x.cdr.car, env) is not False:
+        return TailCall(x.cdr.cdr.car, env)
+    if x.cdr.cdr.cdr is NIL:
+        return UNSPEC
+    return TailCall(x.cdr.cdr.cdr.car, env)
+
+
+def sf_cond(I, x, env):
+    for clause in x.cdr:
+        if clause.car is S("else"):
+            return I.eval_body(clause.cdr, env)
+        v = I.eval(clause.car, env)
+        if v is not False:
+            if clause.cdr is NIL:
+                return v
+            if clause.cdr.car is S("=>"):
+                return I.apply(I.eval(clause.cdr.cdr.car, env), [v])
+            return I.eval_body(clause.cdr, env)
+    return UNSPEC
+
+
+def eqv(a, b):
+    if is_number(a) and is_number(b):
+        return isinstance(a, float) == isinstance(b, float) and a == b
+    return a is b
+
+
+def sf_case(I, x, env):
+    v = I.eval(x.cdr.car, env)
+    for clause in x.cdr.cdr:
+        if clause.car is S("else") or any(eqv(v, d) for d in clause.car):
+            return I.eval_body(clause.cdr, env)
+    return UNSPEC
+
+
+def sf_when(I, x, env):
+    if I.eval(x.cdr.car, env) is not False:
+        return I.eval_body(x.cdr.cdr, env)
+    return UNSPEC
+
+
+def sf_unless(I, x, env):
+    if I.eval(x.cdr.car, env) is False:
+        return I.eval_body(x.cdr.cdr, env)
+    return UNSPEC
+
+
+def sf_and(I, x, env):
+    p = x.cdr
+    if p is NIL:
+        return True
+    while isinstance(p.cdr, Pair):
+        if I.eval(p.car, env) is False:
+            return False
+        p = p.cdr
+    return TailCall(p.car, env)
+
+
+def sf_or(I, x, env):
+    p = x.cdr
+    if p is NIL:
+        return False
+    while isinstance(p.cdr, Pair):
+        v = I.eval(p.car, env)
+        if v is not False:
+            return v
+        p = p.cdr
+    return TailCall(p.car, env)
+
+
+def sf_let(I, x, env):
+    if isinstance(x.cdr.car, Sym):     # named let
+        name, bindings, body = x.cdr.car, x.cdr.cdr.car, x.cdr.cdr.cdr
+        loop_env = Env(env)
+        params = [b.car for b in bindings]
+        f = Closure(params, [], [], None, body, loop_env, name.name)
+        loop_env.vars[name] = f
+        args = [I.eval(b.cdr.car, env) for b in bindings]
+        new = I.bind(f, args)
+        return I.eval_body(body, new)
+    new = Env(env)
+    for b in x.cdr.car:
+        new.vars[b.car] = I.eval(b.cdr.car, env)
+    return I.eval_body(x.cdr.cdr, new)
+
+
+def sf_letstar(I, x, env):
+    new = Env(env)
+    for b in x.cdr.car:
+        v = I.eval(b.cdr.car, new)
+        new = Env(new)
+        new.vars[b.car] = v
+    return I.eval_body(x.cdr.cdr, Env(new))
+
+
+def sf_letrec(I, x, env):
+    new = Env(env)
+    for b in x.cdr.car:
+        I.define(b.car, I.eval(b.cdr.car, new), new)
+    return I.eval_body(x.cdr.cdr, new)
+
+
+def sf_begin(I, x, env):
+    return I.eval_body(x.cdr, env)
+
+
+def sf_set(I, x, env):
+    sym = x.cdr.car
+    val = I.eval(x.cdr.cdr.car, env)
+    e = env.find(sym)
+    if e is not None:
+        e.vars[sym] = val
+    elif sym in env.module.env.vars:
+        env.module.env.vars[sym] = val
+    else:
+        raise SchemeError(f"set!: unbound variable {sym}")
+    return UNSPEC
+
+
+def sf_define_syntax(I, x, env):
+    name, spec = x.cdr.car, x.cdr.cdr.car
+    if not (isinstance(spec, Pair) and spec.car is S("syntax-rules")):
+        raise SchemeError("only syntax-rules transformers are supported")
+    env.vars[name] = make_syntax_rules(spec, name.name)
+    I.version += 1
+    return UNSPEC
+
+
+def sf_define_syntax_rule(I, x, env):
+    pattern, tmpl = x.cdr.car, x.cdr.cdr.car
+    spec = slist([S("syntax-rules"), NIL, slist([pattern, tmpl])])
+    env.vars[pattern.car] = make_syntax_rules(spec, pattern.car.name)
+    I.version += 1
+    return UNSPEC
+
+
+def sf_define_macro(I, x, env):
+    target = x.cdr.car
+    req, opt, keys, rest = parse_params(target.cdr)
+    proc = Closure(req, opt, keys, rest, x.cdr.cdr, env, target.car.name)
+    env.vars[target.car] = Macro(lambda form, e: I.apply(proc, plist(form.cdr)), target.car.name)
+    I.version += 1
+    return UNSPEC
+
+
+def sf_use_modules(I, x, env):
+    for spec in x.cdr:
+        I.use_module(env.module, spec)
+    return UNSPEC
+
+
+def sf_at(I, x, env):
+    name = tuple(s.name for s in plist(x.cdr.car))
+    sym = x.cdr.cdr.car
+    m = I.module(name)
+    if m is None:
+        if sym in I.builtins:
+            return I.builtins[sym]
+        raise SchemeError(f"(@ {name} {sym}): not provided by the stubs")
+    if sym in m.env.vars:
+        return m.env.vars[sym]
+    ok, v = m.resolve(sym)
+    if ok:
+        return v
+    raise SchemeError(f"(@ {name} {sym}): unbound")
+
+
+def sf_match(I, x, env):
+    val = I.eval(x.cdr.car, env)
+    for clause in x.cdr.cdr:
+        b = {}
+        if m_match(clause.car, val, b):
+            new = Env(env)
+            new.vars.update(b)
+            return I.eval_body(clause.cdr, new)
+    raise SchemeThrow(S("match-error"), [val])
+
+
+def sf_cut(I, x, env):
+    slots, items = [], []
+    for i, it in enumerate(x.cdr):
+        if it is S("<>"):
+            s = Sym(f"%cut{i}")
+            slots.append(s)
+            items.append(s)
+        else:
+            items.append(it)
+    # like srfi-26 `cut`, the non-slot operands are evaluated at every call
+    return Closure(slots, [], [], None, slist([slist(items)]), env, "cut")
+
+
+def thread(x, last):
+    acc = x.cdr.car
+    for step in x.cdr.cdr:
+        if isinstance(step, Pair):
+            acc = slist(plist(step) + [acc]) if last else Pair(step.car, Pair(acc, step.cdr))
+        else:
+            acc = slist([step, acc])
+    return acc
+
+
+def sf_thread_last(I, x, env):
+    return TailCall(thread(x, True), env)
+
+
+def sf_thread_first(I, x, env):
+    return TailCall(thread(x, False), env)
+
+
+def sf_define_class(I, x, env):
+    name = x.cdr.car
+    supers = [I.eval(s, env) for s in x.cdr.cdr.car] or [C_OBJECT]
+    slots = []
+    for spec in x.cdr.cdr.cdr:
+        if isinstance(spec, Kw):
+            break                    # class options (#:metaclass ...) are not used by the reference
+        sl = {"name": spec.car if isinstance(spec, Pair) else spec, "env": env}
+        if isinstance(spec, Pair):
+            opts = plist(spec.cdr)
+            for i in range(0, len(opts), 2):
+                k, v = opts[i].name, opts[i + 1]
+                if k == "init-keyword":
+                    sl["keyword"] = v
+                elif k == "init-value":
+                    sl["value"] = I.eval(v, env)
+                elif k == "init-form":
+                    sl["form"] = v
+                elif k == "init-thunk":
+                    sl["thunk"] = I.eval(v, env)
+        slots.append(sl)
+    I.define(name, Class(name.name, supers, slots), env)
+    return UNSPEC
+
+
+def find_generic(I, name, env, create_default=True):
+    found, b = I.binding(name, env)
+    if found and isinstance(b, Generic):
+        return b
+    if found and isinstance(b, (Prim, Closure)):
+        g = Generic(name.name, default=b)          # extending a primitive, e.g. `-` on <time>
+        env.module.env.vars[name] = g
+        I.version += 1
+        return g
+    g = I.generics.get(name)
+    if g is None:
+        g = Generic(name.name)
+        I.generics[name] = g                       # one generic per name: #:duplicates (merge-generics)
+    (env if not env.is_toplevel() and env.find(name) else env.module.env).vars[name] = g
+    I.version += 1
+    return g
+
+
+def sf_define_generic(I, x, env):
+    name = x.cdr.car
+    if env.is_toplevel():
+        find_generic(I, name, env)
+    else:
+        env.vars[name] = Generic(name.name)        # local generic (make-++, find-route)
+    return UNSPEC
+
+
+def sf_define_method(I, x, env):
+    head, body = x.cdr.car, x.cdr.cdr
+    name = head.car
+    specs, params, rest = [], [], None
+    p = head.cdr
+    while isinstance(p, Pair):
+        if isinstance(p.car, Pair):
+            params.append(p.car.car)
+            specs.append(I.eval(p.car.cdr.car, env))
+        else:
+            params.append(p.car)
+            specs.append(TOP)
+        p = p.cdr
+    if isinstance(p, Sym):
+        rest = p
+    local = env.find(name)
+    g = local.vars[name] if local is not None and isinstance(local.vars[name], Generic) else find_generic(I, name, env)
+    proc = Closure([S("next-method")] + params, [], [], rest, body, env, name.name)
+    g.methods = [m for m in g.methods if not (m.specs == specs and bool(m.rest) == bool(rest))]
+    g.methods.append(Method(specs, rest is not None, proc))
+    return UNSPEC
+
+
+SPECIAL = {
+    "quote": sf_quote, "quasiquote": sf_quasiquote, "lambda": sf_lambda, "lambda*": sf_lambda,
+    "define": sf_define, "define*": sf_define, "define-public": sf_define_public, "if": sf_if, "cond": sf_cond,
+    "case": sf_case, "when": sf_when, "unless": sf_unless, "and": sf_and, "or": sf_or, "let": sf_let,
+    "let*": sf_letstar, "letrec": sf_letrec, "letrec*": sf_letrec, "begin": sf_begin, "set!": sf_set,
+    "define-syntax": sf_define_syntax, "define-syntax-rule": sf_define_syntax_rule,
+    "define-macro": sf_define_macro, "use-modules": sf_use_modules, "@": sf_at, "@@": sf_at,
+    "match": sf_match, "cut": sf_cut, "->>": sf_thread_last, "->": sf_thread_first,
+    "define-class": sf_define_class, "define-generic": sf_define_generic, "define-method": sf_define_method,
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# builtins and third-party stubs
+def install_builtins(I):
+    B = I.builtins
+
+    def prim(name, fn):
+        B[S(name)] = Prim(name, fn)
+
+    def truth(f):
+        return lambda *a: bool(f(*a))
+
+    # numbers
+    prim("+", lambda *a: fold_num(num_add, 0, a))
+    prim("*", lambda *a: fold_num(num_mul, 1, a))
+    prim("-", lambda *a: fold_num(num_sub, 0, a, unary=lambda v: norm(-v)))
+    prim("/", lambda *a: fold_num(num_div, 1, a, unary=lambda v: num_div(1, v)))
+
+    def chain(op):
+        return lambda *a: all(op(a[i], a[i + 1]) for i in range(len(a) - 1))
+    prim("=", chain(lambda x, y: x == y))
+    prim("<", chain(lambda x, y: x < y))
+    prim(">", chain(lambda x, y: x > y))
+    prim("<=", chain(lambda x, y: x <= y))
+    prim(">=", chain(lambda x, y: x >= y))
+    prim("max", lambda *a: (float(max(a)) if any(isinstance(v, float) for v in a) else max(a)))
+    prim("min", lambda *a: (float(min(a)) if any(isinstance(v, float) for v in a) else min(a)))
+    prim("abs", lambda v: norm(abs(v)))
+    prim("quotient", lambda a, b: int(a / b) if isinstance(a, float) else (abs(a) // abs(b)) * (1 if (a >= 0) == (b >= 0) else -1))
+    prim("remainder", lambda a, b: a - b * ((abs(a) // abs(b)) * (1 if (a >= 0) == (b >= 0) else -1)))
+    prim("modulo", lambda a, b: a % b)
+    prim("even?", lambda v: v % 2 == 0)
+    prim("odd?", lambda v: v % 2 == 1)
+    prim("zero?", lambda v: v == 0)
+    prim("positive?", lambda v: v > 0)
+    prim("negative?", lambda v: v < 0)
+    prim("1+", lambda v: num_add(v, 1))
+    prim("1-", lambda v: num_sub(v, 1))
+    prim("exact->inexact", float)
+    prim("inexact->exact", lambda v: norm(Fraction(v)))
+    prim("exact?", lambda v: not isinstance(v, float))
+    prim("inexact?", lambda v: isinstance(v, float))
+    prim("number?", is_number)
+    prim("integer?", lambda v: isinstance(v, int) and not isinstance(v, bool) or (isinstance(v, float) and v.is_integer()))
+    prim("sqrt", lambda v: math.sqrt(v))
+    prim("floor", lambda v: float(math.floor(v)) if isinstance(v, float) else math.floor(v))
+    prim("round", lambda v: float(round(v)) if isinstance(v, float) else round(v))
+    prim("expt", lambda a, b: norm(a ** b))
+    prim("sin", lambda v: math.sin(v))
+    prim("cos", lambda v: math.cos(v))
+    B[S("pi")] = math.pi
+    B[S("pi/2")] = math.pi / 2
+
+    # pairs and lists
+    prim("cons", Pair)
+    prim("car", lambda p: p.car)
+    prim("cdr", lambda p: p.cdr)
+    prim("cadr", lambda p: p.cdr.car)
+    prim("cddr", lambda p: p.cdr.cdr)
+    prim("caar", lambda p: p.car.car)
+    prim("cdar", lambda p: p.car.cdr)
+    prim("caddr", lambda p: p.cdr.cdr.car)
+    prim("set-car!", lambda p, v: setattr(p, "car", v) or UNSPEC)
+    prim("set-cdr!", lambda p, v: setattr(p, "cdr", v) or UNSPEC)
+    prim("list", lambda *a: slist(a))
+    prim("length", lambda l: len(plist(l)))
+    prim("null?", lambda v: v is NIL)
+    prim("pair?", lambda v: isinstance(v, Pair))
+
+    def is_list(v):
+        while isinstance(v, Pair):
+            v = v.cdr
+        return v is NIL
+    prim("list?", is_list)
+
+    def append(*ls):
+        if not ls:
+            return NIL
+        out = ls[-1]
+        for l in reversed(ls[:-1]):
+            out = slist(plist(l), out)
+        return out
+    prim("append", append)
+    prim("reverse", lambda l: slist(reversed(plist(l))))
+    prim("first", lambda l: l.car)
+    prim("second", lambda l: l.cdr.car)
+    prim("last", lambda l: plist(l)[-1])
+    prim("list-ref", lambda l, i: plist(l)[i])
+    prim("list-tail", lambda l, i: slist(plist(l)[i:]))
+    prim("list-copy", lambda l: slist(plist(l)))
+
+    def copy_tree(t):
+        return Pair(copy_tree(t.car), copy_tree(t.cdr)) if isinstance(t, Pair) else t
+    prim("copy-tree", copy_tree)
+
+    def iota(n, start=0, step=1):
+        return slist([num_add(start, num_mul(i, step)) for i in range(n)])
+    prim("iota", iota)
+    prim("list-tabulate", lambda n, f: slist([I.apply(f, [i]) for i in range(n)]))
+
+    def smap(f, *ls):
+        cols = [plist(l) for l in ls]
+        return slist([I.apply(f, list(t)) for t in zip(*cols)])
+    prim("map", smap)
+
+    def for_each(f, *ls):
+        for t in zip(*[plist(l) for l in ls]):
+            I.apply(f, list(t))
+        return UNSPEC
+    prim("for-each", for_each)
+    prim("filter", lambda f, l: slist([v for v in plist(l) if I.apply(f, [v]) is not False]))
+    prim("find", lambda f, l: next((v for v in plist(l) if I.apply(f, [v]) is not False), False))
+    prim("any", lambda f, l: next((r for r in (I.apply(f, [v]) for v in plist(l)) if r is not False), False))
+    prim("every", lambda f, l: all(I.apply(f, [v]) is not False for v in plist(l)))
+
+    def fold(f, init, *ls):
+        acc = init
+        for t in zip(*[plist(l) for l in ls]):
+            acc = I.apply(f, list(t) + [acc])
+        return acc
+    prim("fold", fold)
+
+    def reduce_(f, default, l):
+        items = plist(l)
+        if not items:
+            return default
+        acc = items[0]
+        for v in items[1:]:
+            acc = I.apply(f, [v, acc])
+        return acc
+    prim("reduce", reduce_)
+
+    def sapply(f, *a):
+        return I.apply(f, list(a[:-1]) + plist(a[-1]))
+    prim("apply", sapply)
+    prim("memq", lambda v, l: next((p for p in iter_pairs(l) if p.car is v or eqv(p.car, v)), False))
+    prim("member", lambda v, l: next((p for p in iter_pairs(l) if equal(p.car, v)), False))
+    prim("delete", lambda v, l: slist([x for x in plist(l) if not equal(x, v)]))
+
+    def iter_pairs(l):
+        while isinstance(l, Pair):
+            yield l
+            l = l.cdr
+
+    def assq(k, al):
+        for e in plist(al):
+            if isinstance(e, Pair) and (e.car is k or eqv(e.car, k)):
+                return e
+        return False
+    prim("assq", assq)
+    prim("assoc", lambda k, al: next((e for e in plist(al) if isinstance(e, Pair) and equal(e.car, k)), False))
+    prim("assq-ref", lambda al, k: (lambda e: e.cdr if e is not False else False)(assq(k, al)))
+    prim("assoc-ref", lambda al, k: next((e.cdr for e in plist(al) if isinstance(e, Pair) and equal(e.car, k)), False))
+
+    def assoc_set(al, k, v):
+        for e in plist(al):
+            if isinstance(e, Pair) and equal(e.car, k):
+                e.cdr = v
+                return al
+        return Pair(Pair(k, v), al)
+    prim("assoc-set!", assoc_set)
+    prim("assq-set!", assoc_set)
+
+    # predicates, misc
+    prim("eq?", lambda a, b: a is b or (isinstance(a, int) and isinstance(b, int) and not isinstance(a, bool)
+                                        and not isinstance(b, bool) and a == b))
+    prim("eqv?", lambda a, b: a is b or eqv(a, b))
+    prim("equal?", equal)
+    prim("not", lambda v: v is False)
+    prim("symbol?", lambda v: isinstance(v, Sym))
+    prim("string?", lambda v: isinstance(v, str))
+    prim("procedure?", lambda v: isinstance(v, (Prim, Closure, Generic)))
+    prim("boolean?", lambda v: isinstance(v, bool))
+    prim("keyword?", lambda v: isinstance(v, Kw))
+    prim("record?", lambda v: isinstance(v, (Instance, BBTree, HashTable)))
+    prim("negate", lambda f: Prim("negated", lambda *a: I.apply(f, list(a)) is False))
+    prim("identity", lambda v: v)
+    prim("const", lambda v: Prim("const", lambda *a: v))
+    prim("symbol->string", lambda s: s.name)
+    prim("string->symbol", Sym)
+    prim("symbol-append", lambda *s: Sym("".join(x.name for x in s)))
+    prim("string-append", lambda *s: "".join(s))
+    prim("number->string", lambda v: repr(v))
+    prim("pk", lambda *a: a[-1])
+    prim("display", lambda *a: UNSPEC)
+    prim("newline", lambda *a: UNSPEC)
+    prim("format", lambda *a: UNSPEC)
+    prim("error", lambda *a: (_ for _ in ()).throw(SchemeError(" ".join(map(repr, a)))))
+
+    def throw(key, *args):
+        raise SchemeThrow(key, list(args))
+    prim("throw", throw)
+
+    def catch(key, thunk, handler):
+        try:
+            return I.apply(thunk, [])
+        except SchemeThrow as e:
+            if key is True or key is e.key:
+                return I.apply(handler, [e.key] + e.args_)
+            raise
+    prim("catch", catch)
+    B[S("*unspecified*")] = UNSPEC
+
+    def get_keyword(kw, args, default=False):
+        items = plist(args)
+        for i in range(0, len(items) - 1, 2):
+            if items[i] is kw:
+                return items[i + 1]
+        return default
+    prim("get-keyword", get_keyword)
+
+    # srfi-69 hash tables
+    def make_hash_table(*a):
+        by_id = bool(a) and a[0] is B[S("eq?")]
+        return HashTable(by_id)
+    prim("make-hash-table", make_hash_table)
+    prim("hash-table?", lambda v: isinstance(v, HashTable))
+
+    def ht_set(h, k, v):
+        h.d[h.key(k)] = (k, v)
+        return UNSPEC
+    prim("hash-table-set!", ht_set)
+
+    def ht_ref(h, k, *thunk):
+        e = h.d.get(h.key(k))
+        if e is not None:
+            return e[1]
+        if thunk:
+            return I.apply(thunk[0], [])
+        raise SchemeError(f"hash-table-ref: no such key {k!r}")
+    prim("hash-table-ref", ht_ref)
+    prim("hash-table-ref/default", lambda h, k, d: (lambda e: e[1] if e is not None else d)(h.d.get(h.key(k))))
+    prim("hash-table-keys", lambda h: slist([k for k, _ in h.d.values()]))
+    prim("hash-table-values", lambda h: slist([v for _, v in h.d.values()]))
+    prim("hash-table-size", lambda h: len(h.d))
+    prim("hash-table-walk", lambda h, f: [I.apply(f, [k, v]) for k, v in list(h.d.values())] and UNSPEC)
+
+    # pfds bbtrees (not vendored in the reference): persistent ordered map.  Only the call sites'
+    # contract is modelled: bbtree-set replaces an equal key; bbtree-fold visits keys ascending;
+    # bbtree-traverse hands the visitor its subtrees as continuations over a balanced shape.
+    prim("make-bbtree", lambda less: BBTree())
+    prim("bbtree?", lambda v: isinstance(v, BBTree))
+    prim("bbtree-size", lambda t: len(t.items))
+
+    def bbtree_set(t, k, v):
+        items = list(t.items)
+        lo, hi = 0, len(items)
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if items[mid][0] < k:
+                lo = mid + 1
+            else:
+                hi = mid
+        if lo < len(items) and items[lo][0] == k:
+            items[lo] = (k, v)
+        else:
+            items.insert(lo, (k, v))
+        return BBTree(tuple(items))
+    prim("bbtree-set", bbtree_set)
+
+    def bbtree_fold(f, base, t):
+        acc = base
+        for k, v in t.items:
+            acc = I.apply(f, [k, v, acc])
+        return acc
+    prim("bbtree-fold", bbtree_fold)
+
+    def bbtree_traverse(f, base, t):
+        items = t.items
+
+        def trav(lo, hi, b):
+            if lo >= hi:
+                return b
+            mid = (lo + hi) // 2
+            k, v = items[mid]
+            left = Prim("left", lambda bb: trav(lo, mid, bb))
+            right = Prim("right", lambda bb: trav(mid + 1, hi, bb))
+            return I.apply(f, [k, v, left, right, b])
+        return trav(0, len(items), base)
+    prim("bbtree-traverse", bbtree_traverse)
+
+    # GOOPS procedures
+    def make(cls, *initargs):
+        inst = Instance(cls)
+        I.apply(B[S("initialize")], [inst, slist(initargs)])
+        return inst
+    prim("make", make)
+
+    def default_initialize(next_method, inst, initargs):
+        args = plist(initargs)
+        for sl in inst.cls.slots:
+            kw = sl.get("keyword")
+            for i in range(0, len(args) - 1, 2):
+                if kw is not None and args[i] is kw:
+                    inst.slots[sl["name"]] = args[i + 1]
+                    break
+            else:
+                if "value" in sl:
+                    inst.slots[sl["name"]] = sl["value"]
+                elif "form" in sl:
+                    inst.slots[sl["name"]] = I.eval(sl["form"], sl["env"])
+                elif "thunk" in sl:
+                    inst.slots[sl["name"]] = I.apply(sl["thunk"], [])
+        return inst
+    g = Generic("initialize")
+    g.methods.append(Method([TOP, TOP], False, Prim("initialize", default_initialize)))
+    B[S("initialize")] = g
+    I.generics[S("initialize")] = g
+
+    def slot_ref(o, name):
+        if name not in o.slots:
+            raise SchemeThrow(S("goops-error"), [f"slot {name} of {o} is unbound"])
+        return o.slots[name]
+    prim("slot-ref", slot_ref)
+    prim("slot-set!", lambda o, n, v: o.slots.__setitem__(n, v) or UNSPEC)
+    prim("slot-bound?", lambda o, n: n in o.slots)
+    prim("is-a?", lambda o, c: is_a(o, c))
+    prim("class-of", class_of)
+    prim("class-name", lambda c: Sym(c.name))
+    for c in (TOP, C_NUMBER, C_LIST, C_PAIR, C_NULL, C_SYMBOL, C_STRING, C_BOOLEAN, C_KEYWORD, C_PROCEDURE,
+              C_GENERIC, C_CLASS, C_OBJECT):
+        B[S(c.name)] = c
+
+    # chickadee math stubs (fp64; the reference's own lane lengths go through these, which is why
+    # lengths are recorded in the fixtures as inputs rather than recomputed by the oracle)
+    prim("vec2", Vec2)
+    prim("vec2-x", lambda v: v.x)
+    prim("vec2-y", lambda v: v.y)
+    prim("vec2+", lambda a, b: Vec2(a.x + b.x, a.y + b.y))
+    prim("vec2-", lambda a, b: Vec2(a.x - b.x, a.y - b.y))
+    prim("vec2*", lambda a, b: Vec2(a.x * b.x, a.y * b.y) if isinstance(b, Vec2) else Vec2(a.x * float(b), a.y * float(b)))
+    prim("vec2-magnitude", lambda v: math.sqrt(v.x * v.x + v.y * v.y))
+
+    def normalize(v):
+        m = math.sqrt(v.x * v.x + v.y * v.y)
+        return Vec2(v.x / m, v.y / m) if m else Vec2(0.0, 0.0)
+    prim("vec2-normalize", normalize)
+    prim("matrix3-rotate", lambda a: ("rot", float(a)))
+    prim("matrix3-transform", lambda m, v: Vec2(v.x * math.cos(m[1]) - v.y * math.sin(m[1]),
+                                                 v.x * math.sin(m[1]) + v.y * math.cos(m[1])))
+    prim("make-bezier-curve", Bezier)
+    for i in range(4):
+        prim(f"bezier-curve-p{i}", (lambda k: lambda c: c.p[k])(i))
+
+    def bezier_at(c, t):
+        t = float(t)
+        u = 1.0 - t
+        w = (u * u * u, 3.0 * u * u * t, 3.0 * u * t * t, t * t * t)
+        return Vec2(sum(wi * p.x for wi, p in zip(w, c.p)), sum(wi * p.y for wi, p in zip(w, c.p)))
+    prim("bezier-curve-point-at", bezier_at)
+    for colour in ("tango-aluminium-2", "white", "tango-plum", "tango-light-chameleon"):
+        B[S(colour)] = Sym(colour)
+
+    # chickadee a* (not vendored): textbook A*, binary heap, ties broken by insertion order
+    prim("make-path-finder", lambda: "path-finder")
+
+    def a_star(pf, start, goal, neighbors, cost, distance):
+        if start is goal:
+            return slist([start])
+        counter = 0
+        frontier = [(0.0, counter, start)]
+        came, best = {id(start): None}, {id(start): 0.0}
+        nodes = {id(start): start}
+        while frontier:
+            _, _, cur = heapq.heappop(frontier)
+            if cur is goal:
+                break
+            for nb in plist(I.apply(neighbors, [cur])):
+                new = best[id(cur)] + float(I.apply(cost, [cur, nb]))
+                if id(nb) not in best or new < best[id(nb)]:
+                    best[id(nb)] = new
+                    nodes[id(nb)] = nb
+                    came[id(nb)] = cur
+                    counter += 1
+                    heapq.heappush(frontier, (new + float(I.apply(distance, [nb, goal])), counter, nb))
+        if id(goal) not in came:
+            raise SchemeThrow(S("no-path"), [start, goal])
+        path, cur = [], goal
+        while cur is not None:
+            path.append(cur)
+            cur = came[id(cur)]
+        return slist(reversed(path))
+    prim("a*", a_star)
+
+    # arrays (procedural-grid.scm)
+    def array_index(a, idx):
+        k = 0
+        for d, i in zip(a.dims, idx):
+            k = k * d + i
+        return k
+    prim("make-array", lambda fill, *dims: Array(list(dims), fill))
+    prim("array-ref", lambda a, *idx: a.data[array_index(a, idx)])
+    prim("array-set!", lambda a, v, *idx: a.data.__setitem__(array_index(a, idx), v) or UNSPEC)
+    prim("array-length", lambda a: a.dims[0])
+
+    def array_index_map(a, f):
+        def rec(prefix, dims):
+            if not dims:
+                a.data[array_index(a, prefix)] = I.apply(f, list(prefix))
+                return
+            for i in range(dims[0]):
+                rec(prefix + [i], dims[1:])
+        rec([], a.dims)
+        return UNSPEC
+    prim("array-index-map!", array_index_map)
+    prim("array-for-each", lambda f, a: [I.apply(f, [v]) for v in list(a.data)] and UNSPEC)
+
+    def list_to_array(rank, l):
+        items = plist(l)
+        a = Array([len(items)], UNSPEC)
+        a.data = items
+        return a
+    prim("list->array", list_to_array)
+
+    # srfi-27 (seeded: the reference randomises its seed, which no fixture could follow)
+    prim("random-integer", lambda n: I.rng.randrange(n))
+    prim("random-real", lambda: I.rng.random())
+    prim("random-source-randomize!", lambda s: UNSPEC)
+    B[S("default-random-source")] = "default-random-source"
+
+    # srfi-19 time (only used for the update/draw timers)
+    B[S("time-process")] = Sym("time-process")
+    prim("current-time", lambda *a: Time())
+    prim("time-difference", lambda a, b: Time())
+    prim("time-second", lambda t: 0)
+    prim("time-nanosecond", lambda t: 0)
+
+    # the SDL game loop and the painters (griddy/event-loop.scm, griddy/draw.scm): out of scope.
+    # run-game only captures the closures `simulate` hands it (simulate.scm:172-179).
+    def run_game(*args):
+        items = list(args)
+        I.captured_game = {items[i].name: items[i + 1] for i in range(0, len(items) - 1, 2)}
+        return UNSPEC
+    prim("run-game", run_game)
+    prim("abort-game", lambda: UNSPEC)
+    prim("elapsed-time", lambda: 0)
+    prim("make-skeleton-canvas", lambda w: False)
+    prim("make-actors-canvas", lambda w: False)
+    prim("draw-canvas", lambda c: UNSPEC)

@@ -1,0 +1,88 @@
+"""The oracle (and, on a GPU, the CUDA path) against golden vectors recorded by EXECUTING THE REFERENCE'S
+OWN SOURCES (tests/golden/generate.py runs griddy/*.scm and examples/*.scm under tests/golden/minischeme.py;
+see tests/golden/README.md for what that does and does not prove).
+
+Compared after every tick, for every actor in `get-actors` order (world.scm:24-30): location kind, lane or
+segment id, road side, pos-param (bit-exact), remaining agenda length, remaining sleep time, route status,
+route head, max-speed.  The fixtures also fix the world's size, so a vanished actor is noticed."""
+import glob
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from griddy_b200.flat import FlatActors, FlatNetwork
+from oracle.oracle import Oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIXTURES = sorted(os.path.basename(p)[: -len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN, "*.json.gz")))
+
+
+def load(name):
+    with gzip.open(os.path.join(GOLDEN, name + ".json.gz"), "rt") as f:
+        fx = json.load(f)
+    n, a = fx["network"], fx["actors"]
+    net = FlatNetwork(n["kind"], n["lane_len"], n["lane_dir"], n["lane_segment"], n["lane_out"], n["lane_junction"],
+                      n["seg_outer_forw"], n["seg_outer_back"])
+    actors = FlatActors(a["loc_kind"], a["container"], a["pos"], a["side"], a["speed"], a["speed_dt"], a["agenda_off"],
+                        a["item_kind"], a["item_sleep"], a["item_seg"], a["item_side"], a["item_pos"],
+                        route_off=a["route_off"], route_lane=a["route_lane"])
+    return fx, net, actors
+
+
+def expected_states(fx):
+    for s in fx["states"]:
+        for _ in range(s["repeat"]):
+            yield s
+
+
+def check(world, fx, actors, tick, s):
+    """world.state() in get-actors order against one recorded state."""
+    st = world.state()
+    o = st.order
+    where = f'{fx["scenario"]} tick {tick}'
+    assert len(o) == len(s["pos"]), f"{where}: {len(o)} actors in the world, the reference has {len(s['pos'])}"
+    assert bool(st.alive[o].all()), where
+    left = (actors.agenda_off[1:] - actors.agenda_off[:-1])[o] - st.agenda_cur[o]
+    got = {"loc_kind": st.loc_kind[o], "container": st.container[o], "side": st.side[o], "agenda_left": left,
+           "sleep_left": st.sleep_left[o], "route_status": st.route_status[o], "route_head": st.route_head[o]}
+    for k, v in got.items():
+        assert np.array_equal(np.asarray(v, np.int64), np.asarray(s[k], np.int64)), f"{where}: {k} differs"
+    assert np.array_equal(actors.speed[o], np.asarray(s["speed"])), f"{where}: actor identity (max-speed) differs"
+    want = np.array([float.fromhex(h) for h in s["pos"]])
+    assert np.array_equal(st.pos[o], want), f"{where}: pos-param not bit-identical"
+
+
+def replay(make_world, name, stride=1):
+    fx, net, actors = load(name)
+    world = make_world(net, actors, fx)
+    states = expected_states(fx)
+    check(world, fx, actors, 0, next(states))
+    pending = 0
+    for tick, s in enumerate(states, start=1):
+        pending += 1
+        if tick % stride == 0 or tick == fx["ticks"]:
+            world.step(pending)
+            pending = 0
+            check(world, fx, actors, tick, s)
+    return world
+
+
+def test_fixtures_exist():
+    assert {"simple", "triangle", "grid-5x5-80", "grid-3x3-crowded", "grid-2x2-jam"} <= set(FIXTURES)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_reproduces_the_reference_run(name):
+    replay(lambda net, actors, fx: Oracle(net, actors, dt=fx["dt"], two_size=fx["two_size"]), name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FIXTURES)
+def test_device_reproduces_the_reference_run(name):
+    from griddy_b200 import device
+    stride = 20 if name == "triangle" else 1          # triangle idles for 9,970 of its 10,000 ticks
+    replay(lambda net, actors, fx: device.Simulation(net, actors, dt=fx["dt"], two_size=fx["two_size"],
+                                                      reorder_period=16), name, stride=stride)
