@@ -63,6 +63,7 @@
 // fp64 parity: every operation of route.scm:53-135 is issued with round-to-nearest intrinsics
 // (__dadd_rn / __dmul_rn / __ddiv_rn), which the compiler never contracts into FMAs.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -86,13 +87,19 @@ constexpr uint32_t ST_ARRIVE = 512u;   // the route head is (arrive-at _): aux =
 constexpr int HEAD_NONE = 0, HEAD_SLEEP = 1, HEAD_TRAVEL = 2;
 constexpr int HOP_ARRIVE = -1;
 
+constexpr uint32_t ST_EMIG = 1024u;     // multi-GPU: moved onto a lane another rank owns (this slot dies in k_settle)
+constexpr uint32_t ST_IMMIG = 2048u;    // multi-GPU: arrived from another rank this tick (cleared in k_settle)
+
 constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
-              DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32;
+              DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32, DEV_ERR_MIG_OVERFLOW = 64,
+              DEV_ERR_MIG_AGENDA = 128;
 
 // Params::counters[parity][...]
-constexpr int CNT_TOUCHED = 1, CNT_SLOW = 2, CNT_STRIDE = 4;
+constexpr int CNT_EMIG = 0, CNT_TOUCHED = 1, CNT_SLOW = 2, CNT_STRIDE = 4;
 // device scalars (Params::scal)
-constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_COUNT = 4;
+constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NHANDLES = 3, SC_NITEMS = 4, SC_COUNT = 8;
+constexpr int MAX_RANKS = 8;     // one box
+constexpr int MIG_ITEMS = 4;     // agenda items a migrating actor can carry
 
 // st and ahead of a slot share an 8-byte word: every kernel that walks a lane needs both.
 struct __align__(8) SA {
@@ -123,22 +130,32 @@ struct Params {
   double* arrive;
   int32_t *land_tick, *land_lane;
   double* land_pos;
-  // immutable, by actor id
+  // immutable, by actor handle (= the id the actor was uploaded with; actors that arrive from another
+  // rank get fresh handles) and by agenda item
   int64_t n_actors;
-  const double *speed, *speed_dt;
-  const int64_t* agenda_off;
-  const uint8_t* item_kind;
-  const int32_t *item_sleep, *item_seg;
-  const uint8_t* item_side;
-  const double* item_pos;
+  double *speed, *speed_dt;
+  int32_t *agenda_beg, *agenda_end, *gid;
+  uint8_t* item_kind;
+  int32_t *item_sleep, *item_seg;
+  uint8_t* item_side;
+  double* item_pos;
+  int32_t hcap, icap;   // handle and item capacity
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
   // per-tick scratch, by slot
   int32_t *mv_old, *ahead_new, *inbox_next;
   int32_t* dead_mark;   // tick+1 when the actor was found to be a ghost during `tick`
   int32_t *touched, *slow;
-  int32_t* counters;   // [2 parities][CNT_STRIDE]: movers, touched lanes, deferred actors
+  int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, touched lanes, deferred actors
   double dt, two_size;
+  // multi-GPU (owner == null on a single GPU): spatial partition, see "Multi-GPU" below
+  const int32_t* owner;      // rank that owns each item
+  int32_t my_rank;
+  const double* halo_recv;   // rearmost positive pos-param of the remote lanes my actors can enter;
+                             // lane_tail[remote lane] = -2 - index into this array
+  int32_t* emig;             // slots that emigrated this tick
+  int32_t mig_cap;           // records per neighbour per tick
+  uint8_t* mig_send[MAX_RANKS];   // by destination rank: [int32 count, pad][MigRec x mig_cap]
 };
 
 __device__ __forceinline__ void dev_error(const Params& p, int bit) { atomicOr(&p.scal[SC_ERR], bit); }
@@ -185,7 +202,7 @@ __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop)
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
 __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t id, int32_t ac, int32_t* aux) {
-  if (ac >= p.agenda_off[id + 1]) { *aux = 0; return HEAD_NONE; }
+  if (ac >= p.agenda_end[id]) { *aux = 0; return HEAD_NONE; }
   if (p.item_kind[ac] == GRIDDY_SLEEP_FOR) { *aux = p.item_sleep[ac]; return HEAD_SLEEP; }
   *aux = 0;
   return HEAD_TRAVEL;
@@ -265,10 +282,16 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const double tbuf = __ddiv_rn(p.two_size, tlen);
     double tnext = __dmul_rn(__dmul_rn(speed, time_remaining), tinv);   // (+ 0 delta)
     int32_t x = p.lane_tail[target];
-    while (x >= 0 && !(pos_old[x] > 0.0)) x = p.sa[x].ahead;   // smallest key in (0, ...]
-    if (x >= 0) {
-      const double tlead = pos_old[x];
+    const bool remote = x <= -2;   // multi-GPU: another rank owns the target lane
+    if (remote) {                  // its smallest key in (0, ...] came with the halo (+inf: none)
+      const double tlead = p.halo_recv[-2 - x];
       if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
+    } else {
+      while (x >= 0 && !(pos_old[x] > 0.0)) x = p.sa[x].ahead;   // smallest key in (0, ...]
+      if (x >= 0) {
+        const double tlead = pos_old[x];
+        if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
+      }
     }
     int32_t rc = p.route_off ? p.route_cur[a] + 1 : 0;
     const int32_t nhop = route_head_on(p, target, item, &rc);
@@ -279,8 +302,9 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     p.buf[a] = tbuf;
     p.container[a] = target;
     p.mv_old[a] = lane;
-    p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
-    enter_lane(p, a, target, tick, sink);
+    p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u);
+    if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
+    else enter_lane(p, a, target, tick, sink);
     mark_touched(p, lane, tick, sink);
     return tnext;
   }
@@ -612,9 +636,11 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
     const uint32_t st = p.sa[a].st;
     if (!(st & ST_MOVED)) continue;
     const int32_t old = p.mv_old[a];
-    if (old >= 0 && p.kind[old] == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[p.lane_junction[old]], 1);
-    if (p.dead_mark[a] == tick + 1) {   // it was a ghost when it moved: the move is void
-      p.sa[a].st = st & ~(ST_MOVED | ST_ALIVE);
+    // an immigrant's old lane belongs to the rank it came from, which does this bookkeeping itself
+    if (!(st & ST_IMMIG) && old >= 0 && p.kind[old] == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[p.lane_junction[old]], 1);
+    if (p.dead_mark[a] == tick + 1 || (st & ST_EMIG)) {
+      // it was a ghost when it moved (the move is void), or it lives on another rank from now on
+      p.sa[a].st = st & ~(ST_MOVED | ST_ALIVE | ST_EMIG);
       continue;
     }
     if ((st & ST_ALIVE) && (st & ST_ONROAD)) {
@@ -622,7 +648,145 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
       const int32_t lane = p.container[a];
       if (p.kind[lane] == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[p.lane_junction[lane]], 1);
     }
-    p.sa[a].st = st & ~ST_MOVED;
+    p.sa[a].st = st & ~(ST_MOVED | ST_IMMIG);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: the world is partitioned spatially, one part per rank.  Every item has an owner; a
+// segment and its lanes share one, a junction and its lanes share one, so an actor changes rank only
+// while it turns from a segment lane onto a junction lane or back (never while it goes on or off the
+// road).  An actor lives on the rank that owns its container.  What a turning actor reads of the OLD
+// world on the other side — the target lane's rearmost positive pos-param (route.scm:118-121) and the
+// target junction's occupancy (route.scm:98-108) — is the halo, exchanged before k_advance; the actors
+// that crossed are exchanged as fixed-size records before k_relink, which then inserts them by key
+// exactly as it inserts local movers (their old lane and old pos-param travel along, because
+// processing order decides equal-key winners).  Results are identical to a single-GPU run.
+
+struct MigRec {
+  double pos_old, pos_new, delta, buf, arrive, land_pos, speed, speed_dt;
+  int32_t gid, st, container, mv_old, aux, tj, popped, n_items, land_tick, land_lane;
+  int32_t item_sleep[MIG_ITEMS], item_seg[MIG_ITEMS];
+  double item_pos[MIG_ITEMS];
+  uint8_t item_kind[MIG_ITEMS], item_side[MIG_ITEMS];
+};
+constexpr size_t MIG_HEADER = 8;
+
+// Halo out: for every lane of mine that a neighbour's actors can enter, its smallest key in (0, ...]
+// (the walk route.scm:118-121 would do), +inf if there is none; for every such junction, its occupancy.
+__global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int32_t* __restrict__ items, int n_lanes,
+                                                    int n_junctions, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lanes + n_junctions) return;
+  const int32_t item = items[i];
+  if (i >= n_lanes) { out[i] = (double)p.occ[item]; return; }
+  const double* __restrict__ pos = p.pos[par];
+  int32_t x = p.lane_tail[item];
+  while (x >= 0 && !(pos[x] > 0.0)) x = p.sa[x].ahead;
+  out[i] = x >= 0 ? pos[x] : __longlong_as_double(0x7ff0000000000000LL);
+}
+
+// Halo in: occupancy of the neighbours' junctions (the lane values are read in place from halo_recv).
+__global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __restrict__ junctions, int n,
+                                                      const double* __restrict__ in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p.occ[junctions[i]] = (int32_t)in[i];
+}
+
+__global__ void k_mig_reset(Params p) {
+  if (threadIdx.x < MAX_RANKS && p.mig_send[threadIdx.x]) *(int32_t*)p.mig_send[threadIdx.x] = 0;
+}
+
+// Emigrants -> one record each in the send buffer of the rank that owns their new lane.
+__global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
+  const int par = tick & 1;
+  const int32_t n = p.counters[CNT_STRIDE * par + CNT_EMIG];
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int a = p.emig[i];
+    if (p.dead_mark[a] == tick + 1) continue;   // a ghost's move is void
+    const int32_t lane = p.container[a];
+    uint8_t* buf = p.mig_send[p.owner[lane]];
+    const int32_t at = atomicAdd((int32_t*)buf, 1);
+    if (at >= p.mig_cap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
+    MigRec r;
+    const int32_t h = p.id[a];
+    r.pos_old = p.pos[par][a];
+    r.pos_new = p.pos[par ^ 1][a];
+    r.delta = p.delta[a];
+    r.buf = p.buf[a];
+    r.arrive = p.arrive[a];
+    r.land_pos = p.land_pos[a];
+    r.speed = p.speed[h];
+    r.speed_dt = p.speed_dt[h];
+    r.gid = p.gid[h];
+    r.st = (int32_t)((p.sa[a].st & ~ST_EMIG) | ST_IMMIG);
+    r.container = lane;
+    r.mv_old = p.mv_old[a];
+    r.aux = p.aux[a];
+    r.tj = p.tj[a];
+    const int32_t beg = p.agenda_beg[h], end = p.agenda_end[h];
+    r.popped = p.agenda_cur[a] - beg;
+    r.n_items = end - beg;
+    r.land_tick = p.land_tick[a];
+    r.land_lane = p.land_lane[a];
+    if (r.n_items > MIG_ITEMS) { dev_error(p, DEV_ERR_MIG_AGENDA); r.n_items = MIG_ITEMS; }
+    for (int k = 0; k < MIG_ITEMS; ++k) {
+      const bool in = k < r.n_items;
+      r.item_kind[k] = in ? p.item_kind[beg + k] : 0;
+      r.item_side[k] = in ? p.item_side[beg + k] : 0;
+      r.item_sleep[k] = in ? p.item_sleep[beg + k] : 0;
+      r.item_seg[k] = in ? p.item_seg[beg + k] : -1;
+      r.item_pos[k] = in ? p.item_pos[beg + k] : 0.0;
+    }
+    ((MigRec*)(buf + MIG_HEADER))[at] = r;
+  }
+}
+
+// Immigrants: a fresh slot and handle each, then onto their lane's inbox like any local mover.
+__global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const uint8_t* __restrict__ buf) {
+  const int par = tick & 1;
+  const int32_t n = min(*(const int32_t*)buf, p.mig_cap);
+  const MigRec* recs = (const MigRec*)(buf + MIG_HEADER);
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const MigRec r = recs[i];
+    const int32_t a = atomicAdd(&p.scal[SC_NSLOTS], 1);
+    const int32_t h = atomicAdd(&p.scal[SC_NHANDLES], 1);
+    const int32_t it = atomicAdd(&p.scal[SC_NITEMS], r.n_items);
+    if (a >= p.cap || h >= p.hcap || it + r.n_items > p.icap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
+    p.speed[h] = r.speed;
+    p.speed_dt[h] = r.speed_dt;
+    p.gid[h] = r.gid;
+    p.agenda_beg[h] = it;
+    p.agenda_end[h] = it + r.n_items;
+    for (int k = 0; k < r.n_items; ++k) {
+      p.item_kind[it + k] = r.item_kind[k];
+      p.item_side[it + k] = r.item_side[k];
+      p.item_sleep[it + k] = r.item_sleep[k];
+      p.item_seg[it + k] = r.item_seg[k];
+      p.item_pos[it + k] = r.item_pos[k];
+    }
+    p.sa[a] = SA{(uint32_t)r.st, -1};
+    p.pos[par][a] = r.pos_old;       // processing order among a lane's entrants looks at old lane and old key
+    p.pos[par ^ 1][a] = r.pos_new;
+    p.delta[a] = r.delta;
+    p.buf[a] = r.buf;
+    p.arrive[a] = r.arrive;
+    p.land_pos[a] = r.land_pos;
+    p.container[a] = r.container;
+    p.mv_old[a] = r.mv_old;
+    p.aux[a] = r.aux;
+    p.tj[a] = r.tj;
+    p.agenda_cur[a] = it + r.popped;
+    p.route_cur[a] = 0;
+    p.id[a] = h;
+    p.land_tick[a] = r.land_tick;
+    p.land_lane[a] = r.land_lane;
+    p.dead_mark[a] = 0;
+    // onto the lane's inbox; k_settle finds it through the deferred list
+    p.inbox_next[a] = atomicExch(&p.inbox_head[r.container], a);
+    if (atomicExch(&p.lane_mark[r.container], tick + 1) != tick + 1)
+      p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_TOUCHED], 1)] = r.container;
+    p.slow[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_SLOW], 1)] = a;
   }
 }
 
@@ -726,23 +890,26 @@ __global__ void __launch_bounds__(256) k_count_alive(Params p, const uint8_t* gh
 
 struct PackOut {
   uint8_t *alive, *loc_kind, *side, *route_status;
-  int32_t *container, *agenda_cur, *sleep_left, *route_head;
+  int32_t *container, *agenda_cur, *sleep_left, *route_head, *gid;
   double* pos;
+  int by_slot;   // index the outputs by slot (multi-GPU read-back) instead of by actor handle
 };
 
 __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uint8_t* ghost, PackOut o) {
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= p.scal[SC_NSLOTS]) return;
   const uint32_t st = p.sa[a].st;
-  const int32_t id = p.id[a];
+  const int32_t h = p.id[a];
+  const int32_t id = o.by_slot ? a : h;
   const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
   const int32_t aux = p.aux[a];
+  if (o.gid) o.gid[id] = p.gid[h];
   if (o.alive) o.alive[id] = ((st & ST_ALIVE) && !ghost[a]) ? 1 : 0;
   if (o.loc_kind) o.loc_kind[id] = (st & ST_ONROAD) ? 1 : 0;
   if (o.container) o.container[id] = p.container[a];
   if (o.side) o.side[id] = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? 1 : 0;
   if (o.pos) o.pos[id] = p.pos[par][a];
-  if (o.agenda_cur) o.agenda_cur[id] = (int32_t)(p.agenda_cur[a] - p.agenda_off[id]);
+  if (o.agenda_cur) o.agenda_cur[id] = p.agenda_cur[a] - p.agenda_beg[h];
   if (o.sleep_left) o.sleep_left[id] = head == HEAD_SLEEP ? aux : 0;
   if (o.route_status) o.route_status[id] = (uint8_t)rs;
   if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? aux : -2;
@@ -750,6 +917,34 @@ __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uin
 
 // ================================================================================================
 // Host side
+
+struct Ctx;
+
+// One neighbouring rank: what I export to it and import from it every tick.
+struct Neighbor {
+  int rank = -1;
+  int n_exp_lanes = 0, n_exp_junc = 0, n_imp_lanes = 0, n_imp_junc = 0;
+  int32_t* d_exp_items = nullptr;   // my lanes, then my junctions, that `rank` reads
+  int32_t* d_imp_junc = nullptr;    // its junctions whose occupancy my actors read
+  double *d_halo_send = nullptr, *d_halo_recv = nullptr;
+  uint8_t *d_mig_send = nullptr, *d_mig_recv = nullptr;
+};
+
+struct Multi {
+  bool on = false;
+  int rank = 0, world = 1;
+  int mig_cap = 16384;
+  int64_t extra_slots = 0;
+  std::vector<Neighbor> nb;
+  std::vector<void*> allocs;
+  std::vector<std::pair<int32_t, int32_t>> import_marks;   // (remote lane, -2 - index into halo_recv)
+  double* d_halo_recv = nullptr;
+  int32_t* d_owner = nullptr;
+  void* nccl_comm = nullptr;          // transport 1: NCCL send/recv between processes
+  std::vector<Ctx*> peers;            // transport 2: every rank is a context of this process
+  cudaEvent_t ev_ready = nullptr;     //   "my send buffers for this phase are written"
+  size_t mig_bytes() const { return MIG_HEADER + (size_t)mig_cap * sizeof(MigRec); }
+};
 
 struct Ctx {
   int device = 0;
@@ -778,7 +973,9 @@ struct Ctx {
   uint8_t* d_pack = nullptr;
   // host copies needed to format downloads
   std::vector<uint8_t> h_kind;
-  std::vector<int32_t> h_lane_junction;
+  std::vector<int32_t> h_lane_junction, h_lane_out;
+  Multi mg;
+  std::vector<int32_t> mg_owner_host;
 };
 
 int fail(Ctx* c, int code, const std::string& msg) {
@@ -879,6 +1076,96 @@ int reorder_slots(Ctx* c, int64_t tick) {
   CUDA_TRY(c, cudaGetLastError());
   return GRIDDY_OK;
 }
+
+void mg_reset(Ctx* c) {
+  Multi& m = c->mg;
+  for (void* ptr : m.allocs) cudaFree(ptr);
+  if (m.ev_ready) cudaEventDestroy(m.ev_ready);
+  // the NCCL communicator, if any, is left to process exit: destroying it is collective
+  m = Multi();
+  c->mg_owner_host.clear();
+  c->p.owner = nullptr;
+  c->p.halo_recv = nullptr;
+  c->p.my_rank = 0;
+  for (auto& b : c->p.mig_send) b = nullptr;
+}
+
+// Items of `owner_rank` that actors living on `reader_rank` read before they cross: the lanes they
+// can enter (a junction lane fed by one of the reader's segment lanes; a segment lane that one of
+// the reader's junction lanes leads onto) and the junctions whose occupancy gates the entry.  Both
+// sides derive the same ascending lists from the same global arrays, so no list is ever exchanged.
+void mg_plan(int64_t n_items, const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out,
+             const int32_t* lane_junction, const int32_t* owner, int owner_rank, int reader_rank,
+             std::vector<int32_t>& lanes, std::vector<int32_t>& junctions) {
+  std::vector<uint8_t> mark((size_t)n_items, 0);
+  for (int64_t r = 0; r < n_items; ++r) {
+    if (kind[r] != GRIDDY_JUNCTION_LANE) continue;
+    const int32_t in = lane_in[r], out = lane_out[r];
+    if (owner[r] == owner_rank && in >= 0 && owner[in] == reader_rank) { mark[r] = 1; mark[lane_junction[r]] = 2; }
+    if (owner[r] == reader_rank && out >= 0 && owner[out] == owner_rank) mark[out] = 1;
+  }
+  lanes.clear();
+  junctions.clear();
+  for (int64_t r = 0; r < n_items; ++r) {
+    if (mark[r] == 1) lanes.push_back((int32_t)r);
+    else if (mark[r] == 2) junctions.push_back((int32_t)r);
+  }
+}
+
+template <typename T>
+int mg_alloc(Ctx* c, T** out, size_t count) {
+  void* ptr = nullptr;
+  CUDA_TRY(c, cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(T)));
+  c->mg.allocs.push_back(ptr);
+  *out = (T*)ptr;
+  return GRIDDY_OK;
+}
+
+// ---- NCCL, bound lazily so that the library loads (and single-GPU worlds run) without it ---------
+struct NcclId { char internal[128]; };   // layout of ncclUniqueId (nccl.h)
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId /* ncclUniqueId by value */, int) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.lib) return &api;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return nullptr;
+  auto sym = [&](const char* n) { return dlsym(api.lib, n); };
+  api.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+  api.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+  api.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+  api.GroupStart = (int (*)())sym("ncclGroupStart");
+  api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+  api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd) {
+    api.lib = nullptr;
+    return nullptr;
+  }
+  return &api;
+}
+constexpr int NCCL_CHAR = 0;   // ncclInt8 / ncclChar in nccl.h
+
+#define NCCL_TRY(c, expr)                                                                              \
+  do {                                                                                                  \
+    int r_ = (expr);                                                                                    \
+    if (r_ != 0) {                                                                                      \
+      NcclApi* a_ = nccl_api();                                                                         \
+      return fail(c, GRIDDY_ERR_NCCL, std::string(#expr) + ": " + (a_ && a_->GetErrorString ? a_->GetErrorString(r_) : "nccl error")); \
+    }                                                                                                   \
+  } while (0)
 
 }  // namespace
 
@@ -990,6 +1277,8 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   TRY(dev_alloc(c, c->net_allocs, &p.lane_ghost, n_items));
   c->h_kind.assign(kind, kind + n_items);
   c->h_lane_junction.assign(lane_junction, lane_junction + n_items);
+  c->h_lane_out.assign(lane_out, lane_out + n_items);
+  mg_reset(c);
   c->have_net = true;
   return GRIDDY_OK;
 }
@@ -1073,8 +1362,14 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   c->have_actors = false;
   Params& p = c->p;
   p.n_actors = n;
-  const int64_t cap = (n + rsort::TILE - 1) / rsort::TILE * rsort::TILE + rsort::TILE;   // tile-padded
+  const int64_t extra = c->mg.on ? c->mg.extra_slots : 0;   // room for actors arriving from other ranks
+  if (c->mg.on && route_off) return fail(c, GRIDDY_ERR_BAD_ARG, "multi-GPU worlds need the grid routing table, not uploaded routes");
+  if (n + extra > INT32_MAX - 2 * rsort::TILE || n_agenda + extra * MIG_ITEMS > INT32_MAX - 1)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "too many slots");
+  const int64_t cap = (n + extra + rsort::TILE - 1) / rsort::TILE * rsort::TILE + rsort::TILE;   // tile-padded
   p.cap = (int32_t)cap;
+  p.hcap = (int32_t)(n + extra);
+  p.icap = (int32_t)(n_agenda + extra * MIG_ITEMS);
   auto& pool = c->actor_allocs;
 
   // Initial world: link! every actor in id order (core.scm:169-178).  Slot = id until the first reorder.
@@ -1143,13 +1438,14 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   TRY(dev_alloc(c, pool, &p.dead_mark, cap));
   TRY(dev_alloc(c, pool, &p.touched, 2 * cap));
   TRY(dev_alloc(c, pool, &p.slow, cap));
+  TRY(dev_alloc(c, pool, &p.emig, cap));
   TRY(dev_alloc(c, pool, &p.counters, 2 * CNT_STRIDE));
   TRY(dev_alloc(c, pool, &p.scal, SC_COUNT));
   for (void* z : {(void*)p.mv_old, (void*)p.ahead_new, (void*)p.inbox_next, (void*)p.dead_mark})
     CUDA_TRY(c, cudaMemset(z, 0, (size_t)cap * sizeof(int32_t)));
   CUDA_TRY(c, cudaMemset(p.counters, 0, 2 * CNT_STRIDE * sizeof(int32_t)));
   {
-    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, 0};
+    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n, (int32_t)n_agenda, 0, 0, 0};
     CUDA_TRY(c, cudaMemcpy(p.scal, scal, sizeof(scal), cudaMemcpyHostToDevice));
   }
   // reorder scratch
@@ -1165,17 +1461,28 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   CUDA_TRY(c, cudaMemset(c->tailflag, 0, (size_t)cap));
   // read-back staging, by actor id: [pos f64][4 x i32][4 x u8]
   TRY(dev_alloc(c, pool, &c->d_ghost, cap));
-  TRY(dev_alloc(c, pool, &c->d_pack, 28 * std::max<int64_t>(n, 1)));
-  CUDA_TRY(c, cudaMemset(c->d_pack, 0, (size_t)(28 * std::max<int64_t>(n, 1))));
+  TRY(dev_alloc(c, pool, &c->d_pack, 32 * cap));   // by handle, or by slot for griddy_download_local
+  CUDA_TRY(c, cudaMemset(c->d_pack, 0, (size_t)(32 * cap)));
 
-  TRY(dev_upload(c, pool, &p.speed, speed, n));
-  TRY(dev_upload(c, pool, &p.speed_dt, speed_dt, n));
-  TRY(dev_upload(c, pool, &p.agenda_off, agenda_off, n + 1));
-  TRY(dev_upload(c, pool, &p.item_kind, item_kind, n_agenda));
-  TRY(dev_upload(c, pool, &p.item_sleep, item_sleep, n_agenda));
-  TRY(dev_upload(c, pool, &p.item_seg, item_seg, n_agenda));
-  TRY(dev_upload(c, pool, &p.item_side, item_side, n_agenda));
-  TRY(dev_upload(c, pool, &p.item_pos, item_pos, n_agenda));
+  {   // immutable tables, by handle; handles n.. are for actors that arrive from other ranks
+    std::vector<int32_t> beg(n), end(n);
+    for (int64_t a = 0; a < n; ++a) { beg[a] = (int32_t)agenda_off[a]; end[a] = (int32_t)agenda_off[a + 1]; }
+    auto up = [&](auto** dst, const auto* src, int64_t count, int64_t capacity) -> int {
+      TRY(dev_alloc(c, pool, dst, capacity));
+      if (count > 0) CUDA_TRY(c, cudaMemcpy(*dst, src, (size_t)count * sizeof(**dst), cudaMemcpyHostToDevice));
+      return GRIDDY_OK;
+    };
+    TRY(up(&p.speed, speed, n, p.hcap));
+    TRY(up(&p.speed_dt, speed_dt, n, p.hcap));
+    TRY(up(&p.agenda_beg, beg.data(), n, p.hcap));
+    TRY(up(&p.agenda_end, end.data(), n, p.hcap));
+    TRY(up(&p.gid, ident.data(), n, p.hcap));     // global id = handle until griddy_mg_set_global_ids
+    TRY(up(&p.item_kind, item_kind, n_agenda, p.icap));
+    TRY(up(&p.item_sleep, item_sleep, n_agenda, p.icap));
+    TRY(up(&p.item_seg, item_seg, n_agenda, p.icap));
+    TRY(up(&p.item_side, item_side, n_agenda, p.icap));
+    TRY(up(&p.item_pos, item_pos, n_agenda, p.icap));
+  }
   if (route_off) {
     TRY(dev_upload(c, pool, &p.route_off, route_off, n_agenda + 1));
     TRY(dev_upload(c, pool, &p.route_lane, route_lane, route_off[n_agenda]));
@@ -1184,6 +1491,11 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     p.route_lane = nullptr;
   }
   // per-lane state of the network belongs to this world
+  for (const auto& m : c->mg.import_marks) lane_tail[m.first] = m.second;   // lanes other ranks own
+  if (c->mg.on)
+    for (int64_t a = 0; a < n; ++a)
+      if (c->mg_owner_host[container[a]] != c->mg.rank)
+        return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + " is not on this rank's part of the world");
   CUDA_TRY(c, cudaMemcpy(p.lane_tail, lane_tail.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMemcpy(p.occ, occ.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMemset(p.lane_mark, 0, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
@@ -1216,31 +1528,120 @@ int finish_step(Ctx* c) {
   if (derr & DEV_ERR_NO_LANE) m += " road-has-no-lanes;";
   if (derr & DEV_ERR_NO_ROUTE) m += " routing table has no next hop;";
   if (derr & DEV_ERR_INTERNAL) m += " internal: a live actor pointed at a dropped slot;";
+  if (derr & DEV_ERR_MIG_OVERFLOW) m += " multi-GPU: more boundary crossings in one tick than mig_cap, or no slots left for arrivals;";
+  if (derr & DEV_ERR_MIG_AGENDA) m += " multi-GPU: a migrating actor's agenda has more than 4 items;";
   return fail(c, GRIDDY_ERR_BAD_STATE, m);
 }
 
-// One tick = four launches (plus a reorder every reorder_period ticks).  ev (optional) receives 6
-// events bracketing reorder, k_advance, k_slow, k_relink, k_settle.
-int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+// One tick = four launches (plus a reorder every reorder_period ticks; plus, on a partitioned world,
+// the halo and migrant kernels and two exchanges).  ev (optional) receives 6 events bracketing
+// reorder (+ halo pack), k_advance, k_slow (+ emigrant pack), k_relink (+ immigrant unpack), k_settle.
+int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   if (ev) cudaEventRecord(ev[0], c->stream);
   if (c->reorder_period > 0 && tick % c->reorder_period == 0 && tick != c->last_reorder_tick)
     TRY(reorder_slots(c, tick));
+  if (c->mg.on) {
+    for (Neighbor& nb : c->mg.nb) {
+      const int n = nb.n_exp_lanes + nb.n_exp_junc;
+      if (n) k_halo_pack<<<(n + 127) / 128, 128, 0, c->stream>>>(c->p, (int)(tick & 1), nb.d_exp_items, nb.n_exp_lanes, nb.n_exp_junc, nb.d_halo_send);
+    }
+    k_mig_reset<<<1, 32, 0, c->stream>>>(c->p);
+    c->launches += 1 + (int64_t)c->mg.nb.size();
+  }
+  if (ev) cudaEventRecord(ev[1], c->stream);
+  return GRIDDY_OK;
+}
+
+int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   const Params& p = c->p;
   const unsigned per_block = ADV_THREADS * ADV_UNROLL;
   const unsigned adv_blocks = (unsigned)((c->ns_host + per_block - 1) / per_block);
   const unsigned aux_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host + 255) / 256), 1u), 148u * 8u);
-  // one thread per touched lane where possible: a lane is walked serially, so grid-striding doubles the longest chain
-  const unsigned relink_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host / 8 + 127) / 128), 1u), 148u * 64u);
-  if (ev) cudaEventRecord(ev[1], c->stream);
-  k_advance<<<adv_blocks, ADV_THREADS, 0, c->stream>>>(p, (int)tick);
+  if (c->mg.on)
+    for (Neighbor& nb : c->mg.nb)
+      if (nb.n_imp_junc) {
+        k_halo_unpack<<<(nb.n_imp_junc + 127) / 128, 128, 0, c->stream>>>(p, nb.d_imp_junc, nb.n_imp_junc, nb.d_halo_recv + nb.n_imp_lanes);
+        ++c->launches;
+      }
+  if (adv_blocks) k_advance<<<adv_blocks, ADV_THREADS, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[2], c->stream);
   k_slow<<<aux_blocks * 2, SLOW_THREADS, 0, c->stream>>>(p, (int)tick);
+  if (c->mg.on) {
+    k_emig_pack<<<64, 128, 0, c->stream>>>(p, (int)tick);
+    ++c->launches;
+  }
   if (ev) cudaEventRecord(ev[3], c->stream);
+  c->launches += 2;
+  return GRIDDY_OK;
+}
+
+int tick_finish(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+  const Params& p = c->p;
+  const unsigned aux_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host + 255) / 256), 1u), 148u * 8u);
+  // one thread per touched lane where possible: a lane is walked serially, so grid-striding doubles the longest chain
+  const unsigned relink_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host / 8 + 127) / 128), 1u), 148u * 64u);
+  if (c->mg.on) {
+    for (Neighbor& nb : c->mg.nb) {
+      k_immig_unpack<<<std::max(1, c->mg.mig_cap / 512), 128, 0, c->stream>>>(p, (int)tick, nb.d_mig_recv);
+      ++c->launches;
+    }
+    // upper bound of the slots in use: every neighbour may have filled its buffer
+    c->ns_host = (int32_t)std::min<int64_t>(p.cap, (int64_t)c->ns_host + (int64_t)c->mg.mig_cap * (int64_t)c->mg.nb.size());
+  }
   k_relink<<<relink_blocks, 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[4], c->stream);
   k_settle<<<aux_blocks, 256, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[5], c->stream);
-  c->launches += 4;
+  c->launches += 2;
+  return GRIDDY_OK;
+}
+
+// NCCL transport: one grouped send/recv with every neighbour, on the context's stream.
+int exchange_nccl(Ctx* c, bool halo) {
+  NcclApi* api = nccl_api();
+  if (!api || !c->mg.nccl_comm) return fail(c, GRIDDY_ERR_NCCL, "multi-GPU context is not connected (griddy_mg_connect_nccl)");
+  NCCL_TRY(c, api->GroupStart());
+  for (Neighbor& nb : c->mg.nb) {
+    if (halo) {
+      const size_t out = (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double);
+      const size_t in = (size_t)(nb.n_imp_lanes + nb.n_imp_junc) * sizeof(double);
+      if (out) NCCL_TRY(c, api->Send(nb.d_halo_send, out, NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
+      if (in) NCCL_TRY(c, api->Recv(nb.d_halo_recv, in, NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
+    } else {
+      NCCL_TRY(c, api->Send(nb.d_mig_send, c->mg.mig_bytes(), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
+      NCCL_TRY(c, api->Recv(nb.d_mig_recv, c->mg.mig_bytes(), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
+    }
+  }
+  NCCL_TRY(c, api->GroupEnd());
+  return GRIDDY_OK;
+}
+
+int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+  TRY(tick_begin(c, tick, ev));
+  if (c->mg.on) TRY(exchange_nccl(c, true));
+  TRY(tick_advance(c, tick, ev));
+  if (c->mg.on) TRY(exchange_nccl(c, false));
+  return tick_finish(c, tick, ev);
+}
+
+// Local transport: every rank is a context of this process; `src` has recorded ev_ready after writing
+// its send buffers, each neighbour copies what is addressed to it on its own stream.
+int exchange_local(Ctx* src, bool halo) {
+  for (Neighbor& nb : src->mg.nb) {
+    Ctx* dst = src->mg.peers[nb.rank];
+    Neighbor* back = nullptr;
+    for (Neighbor& b : dst->mg.nb)
+      if (b.rank == src->mg.rank) back = &b;
+    if (!back) return fail(src, GRIDDY_ERR_BAD_STATE, "neighbour lists are not symmetric");
+    CUDA_TRY(dst, cudaSetDevice(dst->device));
+    CUDA_TRY(dst, cudaStreamWaitEvent(dst->stream, src->mg.ev_ready, 0));
+    const void* from = halo ? (const void*)nb.d_halo_send : (const void*)nb.d_mig_send;
+    void* to = halo ? (void*)back->d_halo_recv : (void*)back->d_mig_recv;
+    const size_t bytes = halo ? (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double) : src->mg.mig_bytes();
+    if (halo && nb.n_exp_lanes + nb.n_exp_junc != back->n_imp_lanes + back->n_imp_junc)
+      return fail(src, GRIDDY_ERR_BAD_STATE, "halo lists of two neighbours disagree");
+    if (bytes) CUDA_TRY(dst, cudaMemcpyPeerAsync(to, dst->device, from, src->device, bytes, dst->stream));
+  }
   return GRIDDY_OK;
 }
 
@@ -1251,9 +1652,11 @@ int griddy_step(void* ctx, int64_t n_ticks) {
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, "step before upload_actors");
   if (n_ticks < 0 || c->tick + n_ticks > INT32_MAX - 2) return fail(c, GRIDDY_ERR_BAD_ARG, "bad n_ticks");
+  if (c->mg.on && !c->mg.nccl_comm)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "a partitioned world steps with griddy_mg_step_local, or after griddy_mg_connect_nccl");
   CUDA_TRY(c, cudaSetDevice(c->device));
   CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
-  if (c->ns_host > 0)
+  if (c->ns_host > 0 || c->mg.on)
     for (int64_t t = 0; t < n_ticks; ++t) TRY(launch_tick(c, c->tick + t, nullptr));
   CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1263,6 +1666,47 @@ int griddy_step(void* ctx, int64_t n_ticks) {
   c->last_ms = ms;
   c->tick += n_ticks;
   return finish_step(c);
+}
+
+int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks) {
+  if (!ctxs || n < 1 || n > MAX_RANKS || n_ticks < 0) return GRIDDY_ERR_BAD_ARG;
+  std::vector<Ctx*> cs((Ctx**)ctxs, (Ctx**)ctxs + n);
+  for (Ctx* c : cs)
+    if (!c || !c->have_actors || !c->mg.on || (int)c->mg.peers.size() != n)
+      return c ? fail(c, GRIDDY_ERR_BAD_ARG, "mg_step_local: context is not part of a connected local group") : GRIDDY_ERR_BAD_ARG;
+  for (Ctx* c : cs) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+  }
+  for (int64_t t = 0; t < n_ticks; ++t) {
+    for (int phase = 0; phase < 2; ++phase) {
+      for (Ctx* c : cs) {
+        CUDA_TRY(c, cudaSetDevice(c->device));
+        if (phase == 0) TRY(tick_begin(c, c->tick + t, nullptr));
+        else TRY(tick_advance(c, c->tick + t, nullptr));
+        CUDA_TRY(c, cudaEventRecord(c->mg.ev_ready, c->stream));
+      }
+      for (Ctx* c : cs) TRY(exchange_local(c, phase == 0));
+    }
+    for (Ctx* c : cs) {
+      CUDA_TRY(c, cudaSetDevice(c->device));
+      TRY(tick_finish(c, c->tick + t, nullptr));
+    }
+  }
+  int rc = GRIDDY_OK;
+  for (Ctx* c : cs) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms;
+    c->tick += n_ticks;
+    const int r = finish_step(c);
+    if (r && !rc) rc = r;
+  }
+  return rc;
 }
 
 int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms) {
@@ -1293,46 +1737,46 @@ int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms) {
   return finish_step(c);
 }
 
-int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t* container,
-                           uint8_t* side, double* pos, int32_t* agenda_cur, int32_t* sleep_left,
-                           uint8_t* route_status, int32_t* route_head, int32_t* order,
-                           int64_t* n_order) {
-  Ctx* c = (Ctx*)ctx;
-  if (!c) return GRIDDY_ERR_BAD_ARG;
-  if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, "download before upload_actors");
+namespace {
+
+// Read-back shared by griddy_download_actors (outputs indexed by actor handle = upload id, n entries)
+// and griddy_download_local (outputs indexed by slot, plus each slot's global id).
+int download_state(Ctx* c, bool by_slot, int32_t* gid, uint8_t* alive, uint8_t* loc_kind, int32_t* container,
+                   uint8_t* side, double* pos, int32_t* agenda_cur, int32_t* sleep_left, uint8_t* route_status,
+                   int32_t* route_head, int32_t* order, int64_t* n_order) {
   CUDA_TRY(c, cudaSetDevice(c->device));
   const Params& p = c->p;
-  const int64_t n = p.n_actors;
   const int32_t ns = c->ns_host;
+  const int64_t n = by_slot ? ns : p.n_actors;   // entries of every output array
   const int tick = (int)c->tick;
   if (n == 0) {
     if (n_order) *n_order = 0;
     return GRIDDY_OK;
   }
-  // device-side formatting into one staging block indexed by actor id
+  // device-side formatting into one staging block: [pos f64][5 x i32][4 x u8], n entries each
   uint8_t* base = c->d_pack;
   PackOut o{};
+  o.by_slot = by_slot ? 1 : 0;
   double* d_pos = (double*)base;
   int32_t* d_i32 = (int32_t*)(base + 8 * n);
-  uint8_t* d_u8 = base + 8 * n + 16 * n;
+  uint8_t* d_u8 = base + 8 * n + 20 * n;
   o.pos = pos ? d_pos : nullptr;
   o.container = container ? d_i32 : nullptr;
   o.agenda_cur = agenda_cur ? d_i32 + n : nullptr;
   o.sleep_left = sleep_left ? d_i32 + 2 * n : nullptr;
   o.route_head = route_head ? d_i32 + 3 * n : nullptr;
+  o.gid = gid ? d_i32 + 4 * n : nullptr;
   o.alive = alive ? d_u8 : nullptr;
   o.loc_kind = loc_kind ? d_u8 + n : nullptr;
   o.side = side ? d_u8 + 2 * n : nullptr;
   o.route_status = route_status ? d_u8 + 3 * n : nullptr;
   const unsigned blocks = (unsigned)((ns + 255) / 256);
+  if (alive) CUDA_TRY(c, cudaMemsetAsync(d_u8, 0, (size_t)n, c->stream));   // actors without a slot are gone
   if (ns > 0) {
     CUDA_TRY(c, cudaMemsetAsync(c->d_ghost, 0, (size_t)ns, c->stream));
-    if (alive) CUDA_TRY(c, cudaMemsetAsync(d_u8, 0, (size_t)n, c->stream));   // actors without a slot are gone
     k_flag_ghosts<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost);
     k_pack_state<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost, o);
     c->launches += 2;
-  } else if (alive) {
-    CUDA_TRY(c, cudaMemsetAsync(d_u8, 0, (size_t)n, c->stream));
   }
   auto get = [&](void* dst, const void* src, size_t bytes) {
     return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
@@ -1342,6 +1786,7 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
   CUDA_TRY(c, get(agenda_cur, d_i32 + n, n * sizeof(int32_t)));
   CUDA_TRY(c, get(sleep_left, d_i32 + 2 * n, n * sizeof(int32_t)));
   CUDA_TRY(c, get(route_head, d_i32 + 3 * n, n * sizeof(int32_t)));
+  CUDA_TRY(c, get(gid, d_i32 + 4 * n, n * sizeof(int32_t)));
   CUDA_TRY(c, get(alive, d_u8, n));
   CUDA_TRY(c, get(loc_kind, d_u8 + n, n));
   CUDA_TRY(c, get(side, d_u8 + 2 * n, n));
@@ -1391,10 +1836,37 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
       return offroad_before(a, b);
     });
     if (order)
-      for (size_t k = 0; k < ord.size(); ++k) order[k] = ident[ord[k]];
+      for (size_t k = 0; k < ord.size(); ++k) order[k] = by_slot ? ord[k] : ident[ord[k]];
     if (n_order) *n_order = (int64_t)ord.size();
   }
   return GRIDDY_OK;
+}
+
+}  // namespace
+
+int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t* container,
+                           uint8_t* side, double* pos, int32_t* agenda_cur, int32_t* sleep_left,
+                           uint8_t* route_status, int32_t* route_head, int32_t* order,
+                           int64_t* n_order) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, "download before upload_actors");
+  if (c->mg.on) return fail(c, GRIDDY_ERR_BAD_ARG, "a multi-GPU context is read back with griddy_download_local");
+  return download_state(c, false, nullptr, alive, loc_kind, container, side, pos, agenda_cur, sleep_left,
+                        route_status, route_head, order, n_order);
+}
+
+int griddy_download_local(void* ctx, int64_t capacity, int64_t* n_local, int32_t* gid, uint8_t* alive,
+                          uint8_t* loc_kind, int32_t* container, uint8_t* side, double* pos,
+                          int32_t* agenda_cur, int32_t* sleep_left, uint8_t* route_status,
+                          int32_t* route_head, int32_t* order, int64_t* n_order) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_actors || !n_local) return fail(c, GRIDDY_ERR_BAD_ARG, "download_local: no actors or null n_local");
+  *n_local = c->ns_host;
+  if (capacity < c->ns_host) return fail(c, GRIDDY_ERR_BAD_ARG, "download_local: arrays too small, need " + std::to_string(c->ns_host));
+  return download_state(c, true, gid, alive, loc_kind, container, side, pos, agenda_cur, sleep_left,
+                        route_status, route_head, order, n_order);
 }
 
 int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_count) {
@@ -1430,6 +1902,151 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
     std::fill(lane_count, lane_count + p.n_items, 0);
     for (int32_t a = 0; a < ns; ++a)
       if ((st[a] & ST_ALIVE) && !ghost[a]) ++lane_count[cont[a]];
+  }
+  return GRIDDY_OK;
+}
+
+// ---- multi-GPU set-up --------------------------------------------------------------------------
+int griddy_mg_plan(int64_t n_items, const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out,
+                   const int32_t* lane_junction, const int32_t* owner, int32_t owner_rank, int32_t reader_rank,
+                   int32_t* lanes, int64_t* n_lanes, int32_t* junctions, int64_t* n_junctions) {
+  if (n_items < 0 || !kind || !lane_in || !lane_out || !lane_junction || !owner || !n_lanes || !n_junctions)
+    return GRIDDY_ERR_BAD_ARG;
+  std::vector<int32_t> l, j;
+  mg_plan(n_items, kind, lane_in, lane_out, lane_junction, owner, owner_rank, reader_rank, l, j);
+  if (lanes) std::copy(l.begin(), l.end(), lanes);
+  if (junctions) std::copy(j.begin(), j.end(), junctions);
+  *n_lanes = (int64_t)l.size();
+  *n_junctions = (int64_t)j.size();
+  return GRIDDY_OK;
+}
+
+int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* owner, const int32_t* lane_in,
+                        int32_t mig_cap, int64_t extra_slots) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_net) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure before upload_network");
+  if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || !owner || !lane_in || mig_cap < 1 || extra_slots < 0)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure: bad arguments");
+  if (c->p.grid_n == 0) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure needs the grid routing table (griddy_set_routing_grid)");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const Params& q = c->p;
+  const int64_t n_items = q.n_items;
+  for (int64_t r = 0; r < n_items; ++r) {
+    if (owner[r] < 0 || owner[r] >= world) return fail(c, GRIDDY_ERR_BAD_ARG, "owner out of range");
+    const uint8_t k = c->h_kind[r];
+    // a segment and its lanes share an owner, a junction and its lanes too: actors go on and off the
+    // road, and junction occupancy is counted, without leaving the rank
+    if (k == GRIDDY_JUNCTION_LANE && owner[r] != owner[c->h_lane_junction[r]])
+      return fail(c, GRIDDY_ERR_BAD_ARG, "junction lane " + std::to_string(r) + " and its junction have different owners");
+  }
+  free_pool(c->actor_allocs);
+  c->have_actors = false;
+  mg_reset(c);
+  Multi& m = c->mg;
+  m.on = true;
+  m.rank = rank;
+  m.world = world;
+  m.mig_cap = mig_cap;
+  m.extra_slots = extra_slots;
+  c->mg_owner_host.assign(owner, owner + n_items);
+  TRY(mg_alloc(c, &m.d_owner, (size_t)n_items));
+  CUDA_TRY(c, cudaMemcpy(m.d_owner, owner, (size_t)n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
+  // what I export to / import from every other rank
+  struct Lists { std::vector<int32_t> exp_l, exp_j, imp_l, imp_j; };
+  std::vector<Lists> lists(world);
+  size_t halo_in = 0;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    Lists& L = lists[r];
+    mg_plan(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), c->h_lane_junction.data(), owner, rank, r, L.exp_l, L.exp_j);
+    mg_plan(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), c->h_lane_junction.data(), owner, r, rank, L.imp_l, L.imp_j);
+    if (L.exp_l.empty() && L.exp_j.empty() && L.imp_l.empty() && L.imp_j.empty()) continue;
+    halo_in += L.imp_l.size() + L.imp_j.size();
+  }
+  TRY(mg_alloc(c, &m.d_halo_recv, halo_in));
+  size_t off = 0;
+  for (int r = 0; r < world; ++r) {
+    Lists& L = lists[r];
+    if (r == rank || (L.exp_l.empty() && L.exp_j.empty() && L.imp_l.empty() && L.imp_j.empty())) continue;
+    Neighbor nb;
+    nb.rank = r;
+    nb.n_exp_lanes = (int)L.exp_l.size();
+    nb.n_exp_junc = (int)L.exp_j.size();
+    nb.n_imp_lanes = (int)L.imp_l.size();
+    nb.n_imp_junc = (int)L.imp_j.size();
+    std::vector<int32_t> exp(L.exp_l);
+    exp.insert(exp.end(), L.exp_j.begin(), L.exp_j.end());
+    TRY(mg_alloc(c, &nb.d_exp_items, exp.size()));
+    if (!exp.empty()) CUDA_TRY(c, cudaMemcpy(nb.d_exp_items, exp.data(), exp.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    TRY(mg_alloc(c, &nb.d_imp_junc, L.imp_j.size()));
+    if (!L.imp_j.empty()) CUDA_TRY(c, cudaMemcpy(nb.d_imp_junc, L.imp_j.data(), L.imp_j.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    TRY(mg_alloc(c, &nb.d_halo_send, exp.size()));
+    nb.d_halo_recv = m.d_halo_recv + off;
+    for (size_t k = 0; k < L.imp_l.size(); ++k) m.import_marks.emplace_back(L.imp_l[k], (int32_t)(-2 - (int64_t)(off + k)));
+    off += L.imp_l.size() + L.imp_j.size();
+    TRY(mg_alloc(c, &nb.d_mig_send, m.mig_bytes()));
+    TRY(mg_alloc(c, &nb.d_mig_recv, m.mig_bytes()));
+    CUDA_TRY(c, cudaMemset(nb.d_mig_send, 0, m.mig_bytes()));
+    CUDA_TRY(c, cudaMemset(nb.d_mig_recv, 0, m.mig_bytes()));
+    c->p.mig_send[r] = nb.d_mig_send;
+    m.nb.push_back(nb);
+  }
+  c->p.owner = m.d_owner;
+  c->p.my_rank = rank;
+  c->p.halo_recv = m.d_halo_recv;
+  c->p.mig_cap = mig_cap;
+  return GRIDDY_OK;
+}
+
+int griddy_mg_set_global_ids(void* ctx, const int32_t* gid) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_actors || !gid) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_set_global_ids: no actors or null ids");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  for (int64_t a = 1; a < c->p.n_actors; ++a)
+    if (gid[a] <= gid[a - 1]) return fail(c, GRIDDY_ERR_BAD_ARG, "global ids must ascend: they carry the order of the link! calls");
+  if (c->p.n_actors) CUDA_TRY(c, cudaMemcpy(c->p.gid, gid, (size_t)c->p.n_actors * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return GRIDDY_OK;
+}
+
+int griddy_mg_nccl_unique_id(uint8_t* out128) {
+  NcclApi* api = nccl_api();
+  if (!api || !out128) return GRIDDY_ERR_NCCL;
+  NcclId id;
+  if (api->GetUniqueId(&id) != 0) return GRIDDY_ERR_NCCL;
+  memcpy(out128, id.internal, 128);
+  return GRIDDY_OK;
+}
+
+int griddy_mg_connect_nccl(void* ctx, const uint8_t* id128) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->mg.on || !id128) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_connect_nccl before mg_configure");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(c, GRIDDY_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  NcclId id;
+  memcpy(id.internal, id128, 128);
+  NCCL_TRY(c, api->CommInitRank(&c->mg.nccl_comm, c->mg.world, id, c->mg.rank));
+  return GRIDDY_OK;
+}
+
+int griddy_mg_connect_local(void** ctxs, int32_t n) {
+  if (!ctxs || n < 1 || n > MAX_RANKS) return GRIDDY_ERR_BAD_ARG;
+  std::vector<Ctx*> cs((Ctx**)ctxs, (Ctx**)ctxs + n);
+  for (int r = 0; r < n; ++r)
+    if (!cs[r] || !cs[r]->mg.on || cs[r]->mg.rank != r || cs[r]->mg.world != n)
+      return cs[r] ? fail(cs[r], GRIDDY_ERR_BAD_ARG, "mg_connect_local: contexts must be configured as ranks 0..n-1, in order") : GRIDDY_ERR_BAD_ARG;
+  for (Ctx* c : cs) {
+    c->mg.peers = cs;
+    for (Ctx* d : cs)
+      if (d->device != c->device) {
+        cudaSetDevice(c->device);
+        cudaDeviceEnablePeerAccess(d->device, 0);   // best effort; cudaMemcpyPeerAsync stages through the host otherwise
+        cudaGetLastError();
+      }
   }
   return GRIDDY_OK;
 }

@@ -24,7 +24,9 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_upload_actors", "griddy_step", "griddy_profile_step", "griddy_download_actors",
            "griddy_download_occupancy", "griddy_last_step_ms", "griddy_tick", "griddy_kernel_launches",
            "griddy_set_locality_keys", "griddy_set_reorder_period", "griddy_slots_in_use",
-           "griddy_debug_sort_pairs", "griddy_count_alive")
+           "griddy_debug_sort_pairs", "griddy_count_alive", "griddy_mg_configure", "griddy_mg_set_global_ids",
+           "griddy_mg_nccl_unique_id", "griddy_mg_connect_nccl", "griddy_mg_connect_local", "griddy_mg_step_local",
+           "griddy_mg_plan", "griddy_download_local")
 
 
 class GriddyCudaError(RuntimeError):
@@ -63,10 +65,15 @@ def _p(a):
 
 
 class Simulation:
-    """One world on one GPU: upload once, step, read back."""
+    """One world on one GPU: upload once, step, read back.
+
+    With `partition=(rank, world, owner, mig_cap, extra_slots)` the context holds one part of a
+    spatially partitioned world (include/griddy_cuda.h, "Multi-GPU"): `actors` are then the actors on
+    this rank's items, `gids` their global ids."""
 
     def __init__(self, net: FlatNetwork, actors: FlatActors, device: int = -1,
-                 dt: float = 1.0 / 15.0, two_size: float = 10.0, reorder_period: int | None = None):
+                 dt: float = 1.0 / 15.0, two_size: float = 10.0, reorder_period: int | None = None,
+                 partition=None, gids=None):
         L = lib()
         self.h = C.c_void_p()
         rc = L.griddy_create(C.byref(self.h), C.c_int(device))
@@ -88,7 +95,15 @@ class Simulation:
                 raise ValueError("actors carry no routes and the network has no grid routing table")
             self._chk(L.griddy_set_routing_grid(self.h, C.c_int32(net.grid_n), _p(net.lane_from_j),
                                                 _p(net.lane_to_j), _p(net.turn4)))
+        self.partition = partition
+        if partition is not None:
+            rank, world, owner, mig_cap, extra_slots = partition
+            self._chk(L.griddy_mg_configure(self.h, C.c_int32(rank), C.c_int32(world), _p(owner), _p(net.lane_in),
+                                            C.c_int32(mig_cap), C.c_int64(extra_slots)))
         self.upload_actors(actors)
+        if partition is not None:
+            self.gids = np.ascontiguousarray(gids, np.int32)
+            self._chk(L.griddy_mg_set_global_ids(self.h, _p(self.gids)))
 
     def upload_actors(self, a: FlatActors):
         self.actors = a
@@ -147,6 +162,23 @@ class Simulation:
         return ActorState(alive, loc_kind, container, side, pos, agenda_cur, sleep_left, rs, route_head,
                           order[: n_order.value].copy())
 
+    def local_state(self, with_order: bool = True) -> dict:
+        """This rank's slots (griddy_download_local): arrays by slot, plus gid and the local order."""
+        cap = self.slots_in_use
+        u8 = lambda: np.zeros(cap, np.uint8)
+        i32 = lambda: np.zeros(cap, np.int32)
+        out = {"gid": i32(), "alive": u8(), "loc_kind": u8(), "container": i32(), "side": u8(),
+               "pos": np.zeros(cap, np.float64), "agenda_cur": i32(), "sleep_left": i32(), "route_status": u8(),
+               "route_head": i32(), "order": i32()}
+        n_local, n_order = C.c_int64(0), C.c_int64(0)
+        self._chk(lib().griddy_download_local(
+            self.h, C.c_int64(cap), C.byref(n_local), _p(out["gid"]), _p(out["alive"]), _p(out["loc_kind"]),
+            _p(out["container"]), _p(out["side"]), _p(out["pos"]), _p(out["agenda_cur"]), _p(out["sleep_left"]),
+            _p(out["route_status"]), _p(out["route_head"]), _p(out["order"]) if with_order else None,
+            C.byref(n_order) if with_order else None))
+        out["order"] = out["order"][: n_order.value]
+        return out
+
     def occupancy(self):
         lane_count = np.zeros(self.net.n_items, np.int32)
         junction_count = np.zeros(self.net.n_items, np.int32)
@@ -163,3 +195,89 @@ class Simulation:
             self.close()
         except Exception:
             pass
+
+
+def connect_nccl(sim: "Simulation"):
+    """One process per GPU: share rank 0's NCCL id through torch.distributed, then join the communicator."""
+    import torch
+    import torch.distributed as dist
+    rank = sim.partition[0]
+    buf = np.zeros(128, np.uint8)
+    if rank == 0:
+        rc = lib().griddy_mg_nccl_unique_id(_p(buf))
+        if rc:
+            raise GriddyCudaError(rc, "ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+    t = torch.from_numpy(buf).cuda() if dist.get_backend() == "nccl" else torch.from_numpy(buf)
+    dist.broadcast(t, src=0)
+    buf = t.cpu().numpy()
+    sim._chk(lib().griddy_mg_connect_nccl(sim.h, _p(np.ascontiguousarray(buf))))
+
+
+class PartitionedSimulation:
+    """All ranks of a partitioned world as contexts of this process (griddy_mg_connect_local): the
+    executable form of the multi-GPU path for tests — on one GPU, or spread over the visible ones."""
+
+    def __init__(self, net: FlatNetwork, actors: FlatActors, owner: np.ndarray, world: int, devices=None,
+                 mig_cap: int = 4096, extra_slots: int | None = None, reorder_period: int | None = None, **kw):
+        self.net, self.actors, self.world = net, actors, world
+        owner = np.ascontiguousarray(owner, np.int32)
+        extra = actors.n if extra_slots is None else extra_slots
+        self.ranks = []
+        for r in range(world):
+            mine = np.flatnonzero(owner[actors.container] == r)
+            self.ranks.append(Simulation(net, subset_actors(actors, mine), device=devices[r] if devices else -1,
+                                         reorder_period=reorder_period, partition=(r, world, owner, mig_cap, extra),
+                                         gids=mine, **kw))
+        self._hs = (C.c_void_p * world)(*[s.h for s in self.ranks])
+        rc = lib().griddy_mg_connect_local(self._hs, C.c_int32(world))
+        if rc:
+            raise GriddyCudaError(rc, "griddy_mg_connect_local failed")
+
+    def step(self, n_ticks: int = 1):
+        rc = lib().griddy_mg_step_local(self._hs, C.c_int32(self.world), C.c_int64(n_ticks))
+        if rc:
+            msgs = [lib().griddy_last_error(s.h).decode() for s in self.ranks]
+            raise GriddyCudaError(rc, " | ".join(m for m in msgs if m))
+
+    @property
+    def tick(self) -> int:
+        return self.ranks[0].tick
+
+    def state(self) -> ActorState:
+        """The world's state by global actor id, merged from every rank's read-back."""
+        return merge_local_states([s.local_state() for s in self.ranks], self.actors.n)
+
+    def migrants_seen(self) -> int:
+        return sum(s.slots_in_use for s in self.ranks)
+
+
+def subset_actors(a: FlatActors, idx: np.ndarray) -> FlatActors:
+    """The actors `idx` (ascending) with their agendas re-packed."""
+    beg, end = a.agenda_off[idx], a.agenda_off[idx + 1]
+    lens = end - beg
+    off = np.zeros(len(idx) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    items = np.repeat(beg - off[:-1], lens) + np.arange(off[-1]) if len(idx) else np.zeros(0, np.int64)
+    if a.route_off is not None:
+        raise ValueError("partitioned worlds use the grid routing table, not uploaded routes")
+    return FlatActors(a.loc_kind[idx], a.container[idx], a.pos[idx], a.side[idx], a.speed[idx], a.speed_dt[idx], off,
+                      a.item_kind[items], a.item_sleep[items], a.item_seg[items], a.item_side[items], a.item_pos[items])
+
+
+def merge_local_states(parts, n_total: int) -> ActorState:
+    z8, z32 = (lambda: np.zeros(n_total, np.uint8)), (lambda: np.zeros(n_total, np.int32))
+    st = ActorState(z8(), z8(), z32(), z8(), np.zeros(n_total, np.float64), z32(), z32(), z8(), z32(),
+                    np.zeros(0, np.int32))
+    order_gid, order_container = [], []
+    for p in parts:
+        live = p["alive"].astype(bool)
+        g = p["gid"][live]
+        for f in ("alive", "loc_kind", "container", "side", "pos", "agenda_cur", "sleep_left", "route_status", "route_head"):
+            getattr(st, f)[g] = p[f][live]
+        order_gid.append(p["gid"][p["order"]])
+        order_container.append(p["container"][p["order"]])
+    og, oc = np.concatenate(order_gid), np.concatenate(order_container)
+    # a container belongs to one rank: the world's get-actors order is the ranks' orders merged by
+    # descending container id (stable, so each rank's order inside a container is kept)
+    st.order = og[np.argsort(-oc.astype(np.int64), kind="stable")].astype(np.int32)
+    return st

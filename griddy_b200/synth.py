@@ -92,3 +92,17 @@ def grid_actors(net: FlatNetwork, n_actors: int, seed: int = DEFAULT_SEED, agend
         raise RuntimeError(f"synth_actors -> {rc}")
     return FlatActors(loc_kind, container, pos, side, speed, speed_dt, agenda_off, item_kind,
                       item_sleep, item_seg, item_side, item_pos)
+
+
+def grid_owner(net: FlatNetwork, world: int) -> np.ndarray:
+    """Owner rank of every item for `world` horizontal strips of junction rows.  A junction owns its
+    junction lanes; a segment and all its lanes belong to the junction the segment begins at."""
+    n, ni = net.grid_n, net.n_items
+    j = np.zeros(ni, np.int64)
+    kind = net.kind
+    jn, sg, sl, jl = kind == 0, kind == 1, kind == 2, kind == 3
+    j[jn] = np.flatnonzero(jn)
+    j[sg] = net.lane_from_j[net.seg_outer_forw[sg]]          # forw lanes leave the segment's beg junction
+    j[sl] = j[net.lane_segment[sl]]
+    j[jl] = net.lane_junction[jl]
+    return ((j // n) * world // n).astype(np.int32)

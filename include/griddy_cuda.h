@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GRIDDY_ABI_VERSION 2
+#define GRIDDY_ABI_VERSION 3
 
 enum {
   GRIDDY_OK = 0,
@@ -123,6 +123,52 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
 /* Actors per container (n_items entries; lanes and segments) and per junction (sum over its
  * junction lanes — the quantity junction-full? tests, route.scm:98-104). */
 int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_count);
+
+/* ---- Multi-GPU: one context per GPU, the world partitioned spatially -----------------------------
+ * The reference is single-threaded (readme.md:24-26); this is new.  Every item has an owner rank; a
+ * junction and its junction lanes must share one (griddy_mg_configure checks), and so should a
+ * segment and its lanes.  An actor lives on the rank that owns its container and changes rank only
+ * while it turns from one lane onto another (route.scm:92-135).  Each tick the ranks exchange (1) the
+ * halo: for every lane a neighbour's actors can enter, its rearmost positive pos-param
+ * (route.scm:118-121), and for every such junction its occupancy (route.scm:98-104), both of the OLD
+ * world; (2) the actors that crossed, as fixed-size records.  Results are identical to a single-GPU
+ * run of the same world.  Requires the grid routing table; a migrating actor carries at most 4 agenda
+ * items.
+ *
+ * Order of calls on every rank: griddy_upload_network, griddy_set_routing_grid, griddy_mg_configure,
+ * griddy_upload_actors (only the actors on this rank's items, in ascending global id),
+ * griddy_mg_set_global_ids, then one of the two transports:
+ *   griddy_mg_connect_nccl  one process per GPU (torchrun): rank 0 calls griddy_mg_nccl_unique_id and
+ *                           broadcasts the 128 bytes; afterwards every rank calls griddy_step with the
+ *                           same n_ticks, and the exchanges are grouped ncclSend/ncclRecv on the
+ *                           context's stream (NVLink / NVSwitch inside a box);
+ *   griddy_mg_connect_local all ranks are contexts of ONE process (tests; works on a single GPU too):
+ *                           griddy_mg_step_local drives them tick by tick with device-to-device copies.
+ * Read back with griddy_download_local. */
+int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* owner /* n_items */,
+                        const int32_t* lane_in /* n_items: junction lanes: their input segment lane */,
+                        int32_t mig_cap /* boundary crossings per neighbour per tick */,
+                        int64_t extra_slots /* room for actors that arrive from other ranks */);
+int griddy_mg_set_global_ids(void* ctx, const int32_t* gid /* one per uploaded actor, ascending */);
+int griddy_mg_nccl_unique_id(uint8_t* out128);
+int griddy_mg_connect_nccl(void* ctx, const uint8_t* id128);
+int griddy_mg_connect_local(void** ctxs, int32_t n);
+int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks);
+/* Host-only helper (no GPU needed): the items of owner_rank that actors on reader_rank read before
+ * crossing — lanes they can enter, junctions whose occupancy gates them — ascending.  Pass NULL
+ * arrays to get the counts.  Both sides derive identical lists, so none is ever exchanged. */
+int griddy_mg_plan(int64_t n_items, const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out,
+                   const int32_t* lane_junction, const int32_t* owner, int32_t owner_rank,
+                   int32_t reader_rank, int32_t* lanes, int64_t* n_lanes, int32_t* junctions,
+                   int64_t* n_junctions);
+/* Read back this rank's actors: arrays of `capacity` >= griddy_slots_in_use entries, indexed by slot;
+ * gid = the actor's global id; alive = 0 for slots whose actor vanished or left for another rank;
+ * order = slot numbers in get-actors order of this rank's containers (a container is owned by one
+ * rank, so the world's order is the merge of the ranks' orders by descending container id). */
+int griddy_download_local(void* ctx, int64_t capacity, int64_t* n_local, int32_t* gid, uint8_t* alive,
+                          uint8_t* loc_kind, int32_t* container, uint8_t* side, double* pos,
+                          int32_t* agenda_cur, int32_t* sleep_left, uint8_t* route_status,
+                          int32_t* route_head, int32_t* order, int64_t* n_order);
 
 /* Like griddy_step, but brackets every kernel launch with CUDA events on the launching stream and
  * adds the per-kernel device time, in ms summed over the n_ticks, to kernel_ms[0..4] =
