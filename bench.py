@@ -21,6 +21,7 @@ Launch: python bench.py --gpus N --steps K --warmup W  (N>1 under torchrun, one 
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -156,13 +157,42 @@ def run_reference(args):
     }), flush=True)
 
 
-def workload_config(args):
-    return {"workload": f"synthetic {args.grid}x{args.grid} procedural grid, {args.actors} actors, "
-                        f"{args.agenda_len}-item sleep-for/travel-to agendas, grid routing table, "
-                        f"{args.spinup} spin-up ticks",
-            "grid": args.grid, "actors_per_gpu": args.actors, "agenda_len": args.agenda_len,
-            "spinup_ticks": args.spinup, "l2": "working set per tick >> 126 MB L2 (no flush needed)",
-            "parallelism": f"{args.gpus} x independent spatial tiles" if args.gpus > 1 else "1 gpu"}
+def world_shape(args, world):
+    """Weak scaling: every GPU gets args.grid^2 junctions and args.actors actors of ONE world whose
+    junction grid is square, n = round(args.grid * sqrt(world)).  The static network is replicated
+    on every rank, so the tile is shrunk if the box's host memory could not hold `world` copies."""
+    per_gpu = args.grid
+    note = None
+    while world > 1:
+        n = int(round(per_gpu * math.sqrt(world)))
+        need = world * 30 * n * n * 100          # ~30 items per junction, ~100 host bytes per item
+        try:
+            avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+        except Exception:  # noqa: BLE001
+            avail = None
+        if avail is None or need < 0.5 * avail or per_gpu <= 128:
+            break
+        per_gpu //= 2
+        note = f"tile shrunk to {per_gpu}^2 junctions per GPU: host memory ({avail >> 30} GiB) cannot hold {world} network replicas"
+    n = int(round(per_gpu * math.sqrt(world))) if world > 1 else args.grid
+    actors = args.actors * (per_gpu * per_gpu) // (args.grid * args.grid)
+    return n, actors * world, note
+
+
+def workload_config(args, world=None):
+    world = world or args.gpus
+    n, total, note = world_shape(args, world)
+    cfg = {"workload": f"synthetic {n}x{n} procedural grid, {total} actors, "
+                       f"{args.agenda_len}-item sleep-for/travel-to agendas, grid routing table, "
+                       f"{args.spinup} spin-up ticks",
+           "grid": n, "actors": total, "actors_per_gpu": total // world, "agenda_len": args.agenda_len,
+           "spinup_ticks": args.spinup, "l2": "working set per tick >> 126 MB L2 (no flush needed)",
+           "parallelism": (f"{world} ranks = {world} horizontal strips of junction rows of one world; per tick the halo "
+                           f"(boundary lanes' rearmost pos-param, boundary junctions' occupancy) and the actors that "
+                           f"crossed are exchanged with grouped ncclSend/ncclRecv" if world > 1 else "1 gpu")}
+    if note:
+        cfg["note"] = note
+    return cfg
 
 
 def main():
@@ -181,6 +211,8 @@ def main():
     ap.add_argument("--cpu-ticks", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reorder-period", type=int, default=128)
+    ap.add_argument("--mig-cap", type=int, default=32768, help="multi-GPU: boundary crossings per neighbour per tick")
+    ap.add_argument("--extra-slots", type=int, default=4_000_000, help="multi-GPU: room for actors arriving from other ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -209,10 +241,23 @@ def main():
         dist.barrier()
     from griddy_b200 import device
 
-    # one spatial tile per GPU; tiles are independent worlds in this round (weak scaling)
-    net, actors = build_world(args.grid, args.actors, args.agenda_len, seed_offset=rank)
+    from griddy_b200 import synth
+    n_grid, total_actors, _ = world_shape(args, world)
     t0 = time.time()
-    sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period)
+    if world == 1:
+        net, actors = build_world(args.grid, args.actors, args.agenda_len)
+        sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period)
+    else:
+        # ONE world, partitioned into horizontal strips; this rank generates and uploads its own actors
+        net = synth.grid_network(n_grid)
+        owner = synth.grid_owner(net, world)
+        ids = synth.actor_ids_of_rank(net, total_actors, owner, rank)
+        actors = synth.grid_actors(net, total_actors, agenda_len=args.agenda_len, ids=ids)
+        log(f"[bench] rank {rank}: {n_grid}x{n_grid} grid ({net.n_items} items), {actors.n} of {total_actors} actors "
+            f"generated in {time.time() - t0:.1f}s")
+        sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period,
+                                partition=(rank, world, owner, args.mig_cap, args.extra_slots), gids=ids)
+        device.connect_nccl(sim)
     log(f"[bench] rank {rank}: uploaded in {time.time() - t0:.1f}s")
     sim.step(args.spinup)
     log(f"[bench] rank {rank}: spin-up {args.spinup} ticks in {sim.last_step_ms:.1f} ms")
@@ -267,7 +312,7 @@ def main():
             traffic = json.load(f).get("tick_dram_bytes")
 
     # e2e: the call a user makes per frame — step one tick, read the world back into host buffers
-    n = actors.n
+    n = actors.n if world == 1 else actors.n + args.extra_slots
     pin = lambda dt: torch.empty(n, dtype=dt, pin_memory=True).numpy()
     import ctypes as C
     # what `draw` reads of every actor (simulate.scm:155-160 -> get-pos, spatial.scm:125-149):
@@ -276,11 +321,16 @@ def main():
     d2h = sum(b.nbytes for b in bufs)
     L = device.lib()
     ptrs = [b.ctypes.data_as(C.c_void_p) for b in bufs] + [None] * 6
+    gid_buf = pin(torch.int32) if world > 1 else None
+    n_local = C.c_int64(0)
 
     def e2e_step():
         sim.step(1)
-        rc = L.griddy_download_actors(sim.h, *ptrs)
-        assert rc == 0
+        if world == 1:
+            rc = L.griddy_download_actors(sim.h, *ptrs)
+        else:
+            rc = L.griddy_download_local(sim.h, C.c_int64(n), C.byref(n_local), gid_buf.ctypes.data_as(C.c_void_p), *ptrs)
+        assert rc == 0, L.griddy_last_error(sim.h)
 
     for _ in range(3):
         e2e_step()
@@ -294,14 +344,22 @@ def main():
         t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_dt = float(t.item())
-    alive = int(bufs[0].sum())
+    if world > 1:
+        d2h = int(n_local.value) * (sum(b.itemsize for b in bufs) + 4)
+        t = torch.tensor([float(d2h)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        d2h = int(t.item()) // world
+        alive = int(bufs[0][: n_local.value].sum())
+        on_road = int((bufs[0][: n_local.value] & bufs[1][: n_local.value]).sum())
+    else:
+        alive = int(bufs[0].sum())
+        on_road = int((bufs[0] & bufs[1]).sum())
     if world > 1:
         t = torch.tensor([float(alive)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         e2e_value = float(t.item()) * args.e2e_steps / e_dt
     else:
         e2e_value = alive * args.e2e_steps / e_dt
-    on_road = int((bufs[0] & bufs[1]).sum())
 
     if rank != 0:
         if world > 1:
@@ -321,7 +379,7 @@ def main():
         "metric": "actor-updates/sec", "value": value, "unit": "actor-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args),
+        "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "actor-updates/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": d2h * world,
                 "note": "per step: griddy_step(1) + griddy_download_actors of what draw reads (alive, location "
@@ -345,7 +403,7 @@ def main():
                      "reorder_period_ticks": args.reorder_period},
         "cpu_baseline": cpu,
         "world": {"alive_before": alive0, "alive_after": alive1, "alive_at_end": alive, "on_road": on_road,
-                  "actors_uploaded": args.actors * world, "wall_s_timed_region": wall,
+                  "actors_uploaded": total_actors, "wall_s_timed_region": wall,
                   "note": "value counts living actors only"},
     }
     print(json.dumps(out), flush=True)

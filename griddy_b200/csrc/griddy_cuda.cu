@@ -97,7 +97,7 @@ constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_J
 // Params::counters[parity][...]
 constexpr int CNT_EMIG = 0, CNT_TOUCHED = 1, CNT_SLOW = 2, CNT_STRIDE = 4;
 // device scalars (Params::scal)
-constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NHANDLES = 3, SC_NITEMS = 4, SC_COUNT = 8;
+constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_COUNT = 4;
 constexpr int MAX_RANKS = 8;     // one box
 constexpr int MIG_ITEMS = 4;     // agenda items a migrating actor can carry
 
@@ -125,21 +125,21 @@ struct Params {
   SA* sa;          // {st, ahead}: one 8-byte load per actor
   double* pos[2];
   double *delta, *buf;
-  int32_t *aux, *container, *agenda_cur, *route_cur, *id;
+  int32_t *aux, *container, *agenda_cur, *route_cur;
+  int32_t* gid;                      // the actor's id (global id on a partitioned world)
+  int32_t *agenda_beg, *agenda_end;  // its agenda in the item arrays
+  double *speed, *speed_dt;          // max-speed and fl(max-speed * dt)
   int32_t* tj;   // junction of the lane the route head turns onto, -1 if that is not a junction lane
   double* arrive;
   int32_t *land_tick, *land_lane;
   double* land_pos;
-  // immutable, by actor handle (= the id the actor was uploaded with; actors that arrive from another
-  // rank get fresh handles) and by agenda item
+  // agenda items (immutable; actors that arrive from another rank append theirs)
   int64_t n_actors;
-  double *speed, *speed_dt;
-  int32_t *agenda_beg, *agenda_end, *gid;
   uint8_t* item_kind;
   int32_t *item_sleep, *item_seg;
   uint8_t* item_side;
   double* item_pos;
-  int32_t hcap, icap;   // handle and item capacity
+  int32_t icap;   // item capacity
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
   // per-tick scratch, by slot
@@ -201,8 +201,8 @@ __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop)
 }
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
-__device__ __forceinline__ uint32_t load_head(const Params& p, int32_t id, int32_t ac, int32_t* aux) {
-  if (ac >= p.agenda_end[id]) { *aux = 0; return HEAD_NONE; }
+__device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_t ac, int32_t* aux) {
+  if (ac >= p.agenda_end[a]) { *aux = 0; return HEAD_NONE; }
   if (p.item_kind[ac] == GRIDDY_SLEEP_FOR) { *aux = p.item_sleep[ac]; return HEAD_SLEEP; }
   *aux = 0;
   return HEAD_TRAVEL;
@@ -271,10 +271,9 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const int32_t tj = p.tj[a];   // junction-full?  route.scm:98-108 (k_advance has usually answered this)
     if (tj >= 0 && p.occ[tj] > 0) return cur;   // waiting
     const int32_t target = p.aux[a];
-    const int32_t id = p.id[a];
     const int32_t lane = p.container[a];
     const int32_t item = p.agenda_cur[a];
-    const double speed = p.speed[id];
+    const double speed = p.speed[a];
     const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), speed);
     const double time_remaining = __dsub_rn(p.dt, time_spent);
     const double tlen = p.lane_len[target];
@@ -298,7 +297,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     if (p.route_off) p.route_cur[a] = rc;
     p.aux[a] = nhop;
     p.tj[a] = junction_of_hop(p, nhop);
-    p.delta[a] = __dmul_rn(p.speed_dt[id], tinv);
+    p.delta[a] = __dmul_rn(p.speed_dt[a], tinv);
     p.buf[a] = tbuf;
     p.container[a] = target;
     p.mv_old[a] = lane;
@@ -315,7 +314,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     if (t == 0) {
       const int32_t ac = p.agenda_cur[a] + 1;
       int32_t aux;
-      const uint32_t h = load_head(p, p.id[a], ac, &aux);
+      const uint32_t h = load_head(p, a, ac, &aux);
       p.agenda_cur[a] = ac;
       p.aux[a] = aux;
       p.sa[a].st = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
@@ -347,7 +346,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     p.arrive[a] = dest_pos;
     p.aux[a] = hop;
     p.tj[a] = junction_of_hop(p, hop);
-    p.delta[a] = __dmul_rn(p.speed_dt[p.id[a]], __ddiv_rn(1.0, len));
+    p.delta[a] = __dmul_rn(p.speed_dt[a], __ddiv_rn(1.0, len));
     p.buf[a] = __ddiv_rn(p.two_size, len);
     p.container[a] = init_lane;
     p.mv_old[a] = ~seg;
@@ -364,7 +363,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   const uint32_t dir = p.lane_dir[lane];
   const int32_t ac = item + 1;
   int32_t aux;
-  const uint32_t h = load_head(p, p.id[a], ac, &aux);
+  const uint32_t h = load_head(p, a, ac, &aux);
   p.agenda_cur[a] = ac;
   p.aux[a] = aux;
   p.container[a] = seg;
@@ -709,22 +708,21 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     const int32_t at = atomicAdd((int32_t*)buf, 1);
     if (at >= p.mig_cap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
     MigRec r;
-    const int32_t h = p.id[a];
     r.pos_old = p.pos[par][a];
     r.pos_new = p.pos[par ^ 1][a];
     r.delta = p.delta[a];
     r.buf = p.buf[a];
     r.arrive = p.arrive[a];
     r.land_pos = p.land_pos[a];
-    r.speed = p.speed[h];
-    r.speed_dt = p.speed_dt[h];
-    r.gid = p.gid[h];
+    r.speed = p.speed[a];
+    r.speed_dt = p.speed_dt[a];
+    r.gid = p.gid[a];
     r.st = (int32_t)((p.sa[a].st & ~ST_EMIG) | ST_IMMIG);
     r.container = lane;
     r.mv_old = p.mv_old[a];
     r.aux = p.aux[a];
     r.tj = p.tj[a];
-    const int32_t beg = p.agenda_beg[h], end = p.agenda_end[h];
+    const int32_t beg = p.agenda_beg[a], end = p.agenda_end[a];
     r.popped = p.agenda_cur[a] - beg;
     r.n_items = end - beg;
     r.land_tick = p.land_tick[a];
@@ -742,7 +740,7 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
   }
 }
 
-// Immigrants: a fresh slot and handle each, then onto their lane's inbox like any local mover.
+// Immigrants: a fresh slot each, then onto their lane's inbox like any local mover.
 __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const uint8_t* __restrict__ buf) {
   const int par = tick & 1;
   const int32_t n = min(*(const int32_t*)buf, p.mig_cap);
@@ -750,14 +748,13 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const MigRec r = recs[i];
     const int32_t a = atomicAdd(&p.scal[SC_NSLOTS], 1);
-    const int32_t h = atomicAdd(&p.scal[SC_NHANDLES], 1);
     const int32_t it = atomicAdd(&p.scal[SC_NITEMS], r.n_items);
-    if (a >= p.cap || h >= p.hcap || it + r.n_items > p.icap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
-    p.speed[h] = r.speed;
-    p.speed_dt[h] = r.speed_dt;
-    p.gid[h] = r.gid;
-    p.agenda_beg[h] = it;
-    p.agenda_end[h] = it + r.n_items;
+    if (a >= p.cap || it + r.n_items > p.icap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
+    p.speed[a] = r.speed;
+    p.speed_dt[a] = r.speed_dt;
+    p.gid[a] = r.gid;
+    p.agenda_beg[a] = it;
+    p.agenda_end[a] = it + r.n_items;
     for (int k = 0; k < r.n_items; ++k) {
       p.item_kind[it + k] = r.item_kind[k];
       p.item_side[it + k] = r.item_side[k];
@@ -778,7 +775,6 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     p.tj[a] = r.tj;
     p.agenda_cur[a] = it + r.popped;
     p.route_cur[a] = 0;
-    p.id[a] = h;
     p.land_tick[a] = r.land_tick;
     p.land_lane[a] = r.land_lane;
     p.dead_mark[a] = 0;
@@ -795,9 +791,10 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
 // per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
 
 // Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
-constexpr int PERM4 = 8, PERM8 = 6;
-enum { P4_CONTAINER, P4_AUX, P4_AGENDA_CUR, P4_ROUTE_CUR, P4_ID, P4_LAND_TICK, P4_LAND_LANE, P4_TJ };
-enum { P8_SA, P8_POS, P8_DELTA, P8_BUF, P8_ARRIVE, P8_LAND_POS };
+constexpr int PERM4 = 10, PERM8 = 8;
+enum { P4_CONTAINER, P4_AUX, P4_AGENDA_CUR, P4_ROUTE_CUR, P4_GID, P4_LAND_TICK, P4_LAND_LANE, P4_TJ, P4_AGENDA_BEG,
+       P4_AGENDA_END };
+enum { P8_SA, P8_POS, P8_DELTA, P8_BUF, P8_ARRIVE, P8_LAND_POS, P8_SPEED, P8_SPEED_DT };
 
 struct Permute {
   const uint32_t* src4[PERM4];
@@ -892,24 +889,23 @@ struct PackOut {
   uint8_t *alive, *loc_kind, *side, *route_status;
   int32_t *container, *agenda_cur, *sleep_left, *route_head, *gid;
   double* pos;
-  int by_slot;   // index the outputs by slot (multi-GPU read-back) instead of by actor handle
+  int by_slot;   // index the outputs by slot (multi-GPU read-back) instead of by actor id
 };
 
 __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uint8_t* ghost, PackOut o) {
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= p.scal[SC_NSLOTS]) return;
   const uint32_t st = p.sa[a].st;
-  const int32_t h = p.id[a];
-  const int32_t id = o.by_slot ? a : h;
+  const int32_t id = o.by_slot ? a : p.gid[a];
   const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
   const int32_t aux = p.aux[a];
-  if (o.gid) o.gid[id] = p.gid[h];
+  if (o.gid) o.gid[id] = p.gid[a];
   if (o.alive) o.alive[id] = ((st & ST_ALIVE) && !ghost[a]) ? 1 : 0;
   if (o.loc_kind) o.loc_kind[id] = (st & ST_ONROAD) ? 1 : 0;
   if (o.container) o.container[id] = p.container[a];
   if (o.side) o.side[id] = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? 1 : 0;
   if (o.pos) o.pos[id] = p.pos[par][a];
-  if (o.agenda_cur) o.agenda_cur[id] = p.agenda_cur[a] - p.agenda_beg[h];
+  if (o.agenda_cur) o.agenda_cur[id] = p.agenda_cur[a] - p.agenda_beg[a];
   if (o.sleep_left) o.sleep_left[id] = head == HEAD_SLEEP ? aux : 0;
   if (o.route_status) o.route_status[id] = (uint8_t)rs;
   if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? aux : -2;
@@ -1036,7 +1032,11 @@ void bind_slot_arrays(Ctx* c, int par) {
   p.aux = (int32_t*)c->cur4[P4_AUX];
   p.agenda_cur = (int32_t*)c->cur4[P4_AGENDA_CUR];
   p.route_cur = (int32_t*)c->cur4[P4_ROUTE_CUR];
-  p.id = (int32_t*)c->cur4[P4_ID];
+  p.gid = (int32_t*)c->cur4[P4_GID];
+  p.agenda_beg = (int32_t*)c->cur4[P4_AGENDA_BEG];
+  p.agenda_end = (int32_t*)c->cur4[P4_AGENDA_END];
+  p.speed = (double*)c->cur8[P8_SPEED];
+  p.speed_dt = (double*)c->cur8[P8_SPEED_DT];
   p.land_tick = (int32_t*)c->cur4[P4_LAND_TICK];
   p.land_lane = (int32_t*)c->cur4[P4_LAND_LANE];
   p.pos[par] = (double*)c->cur8[P8_POS];
@@ -1368,7 +1368,6 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     return fail(c, GRIDDY_ERR_BAD_ARG, "too many slots");
   const int64_t cap = (n + extra + rsort::TILE - 1) / rsort::TILE * rsort::TILE + rsort::TILE;   // tile-padded
   p.cap = (int32_t)cap;
-  p.hcap = (int32_t)(n + extra);
   p.icap = (int32_t)(n_agenda + extra * MIG_ITEMS);
   auto& pool = c->actor_allocs;
 
@@ -1423,9 +1422,17 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   CUDA_TRY(c, cudaMemset(c->cur4[P4_TJ], 0xFF, (size_t)cap * sizeof(int32_t)));
   CUDA_TRY(c, put4(P4_AUX, aux.data()));
   CUDA_TRY(c, put4(P4_AGENDA_CUR, acur.data()));
-  CUDA_TRY(c, put4(P4_ID, ident.data()));
+  CUDA_TRY(c, put4(P4_GID, ident.data()));     // global id = upload index until griddy_mg_set_global_ids
   CUDA_TRY(c, put4(P4_LAND_LANE, ident.data()));
   if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_POS], pos, (size_t)n * 8, cudaMemcpyHostToDevice));
+  if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SPEED], speed, (size_t)n * 8, cudaMemcpyHostToDevice));
+  if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SPEED_DT], speed_dt, (size_t)n * 8, cudaMemcpyHostToDevice));
+  {
+    std::vector<int32_t> beg(n), end(n);
+    for (int64_t a = 0; a < n; ++a) { beg[a] = (int32_t)agenda_off[a]; end[a] = (int32_t)agenda_off[a + 1]; }
+    CUDA_TRY(c, put4(P4_AGENDA_BEG, beg.data()));
+    CUDA_TRY(c, put4(P4_AGENDA_END, end.data()));
+  }
   double* pos1 = nullptr;
   TRY(dev_alloc(c, pool, &pos1, cap));
   if (n) CUDA_TRY(c, cudaMemcpy(pos1, pos, (size_t)n * 8, cudaMemcpyHostToDevice));
@@ -1445,7 +1452,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     CUDA_TRY(c, cudaMemset(z, 0, (size_t)cap * sizeof(int32_t)));
   CUDA_TRY(c, cudaMemset(p.counters, 0, 2 * CNT_STRIDE * sizeof(int32_t)));
   {
-    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n, (int32_t)n_agenda, 0, 0, 0};
+    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n_agenda};
     CUDA_TRY(c, cudaMemcpy(p.scal, scal, sizeof(scal), cudaMemcpyHostToDevice));
   }
   // reorder scratch
@@ -1464,19 +1471,12 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   TRY(dev_alloc(c, pool, &c->d_pack, 32 * cap));   // by handle, or by slot for griddy_download_local
   CUDA_TRY(c, cudaMemset(c->d_pack, 0, (size_t)(32 * cap)));
 
-  {   // immutable tables, by handle; handles n.. are for actors that arrive from other ranks
-    std::vector<int32_t> beg(n), end(n);
-    for (int64_t a = 0; a < n; ++a) { beg[a] = (int32_t)agenda_off[a]; end[a] = (int32_t)agenda_off[a + 1]; }
+  {   // agenda items; room at the end for the items of actors that arrive from other ranks
     auto up = [&](auto** dst, const auto* src, int64_t count, int64_t capacity) -> int {
       TRY(dev_alloc(c, pool, dst, capacity));
       if (count > 0) CUDA_TRY(c, cudaMemcpy(*dst, src, (size_t)count * sizeof(**dst), cudaMemcpyHostToDevice));
       return GRIDDY_OK;
     };
-    TRY(up(&p.speed, speed, n, p.hcap));
-    TRY(up(&p.speed_dt, speed_dt, n, p.hcap));
-    TRY(up(&p.agenda_beg, beg.data(), n, p.hcap));
-    TRY(up(&p.agenda_end, end.data(), n, p.hcap));
-    TRY(up(&p.gid, ident.data(), n, p.hcap));     // global id = handle until griddy_mg_set_global_ids
     TRY(up(&p.item_kind, item_kind, n_agenda, p.icap));
     TRY(up(&p.item_sleep, item_sleep, n_agenda, p.icap));
     TRY(up(&p.item_seg, item_seg, n_agenda, p.icap));
@@ -1806,7 +1806,7 @@ int download_state(Ctx* c, bool by_slot, int32_t* gid, uint8_t* alive, uint8_t* 
     for (int32_t a = 0; a < ns; ++a) st[a] = sa[a].st;
     CUDA_TRY(c, pull(ghost.data(), c->d_ghost, ns));
     CUDA_TRY(c, pull(cont.data(), p.container, ns * sizeof(int32_t)));
-    CUDA_TRY(c, pull(ident.data(), p.id, ns * sizeof(int32_t)));
+    CUDA_TRY(c, pull(ident.data(), p.gid, ns * sizeof(int32_t)));
     CUDA_TRY(c, pull(ps.data(), p.pos[tick & 1], ns * sizeof(double)));
     CUDA_TRY(c, pull(land_tick.data(), p.land_tick, ns * sizeof(int32_t)));
     CUDA_TRY(c, pull(land_lane.data(), p.land_lane, ns * sizeof(int32_t)));
@@ -2007,7 +2007,16 @@ int griddy_mg_set_global_ids(void* ctx, const int32_t* gid) {
   CUDA_TRY(c, cudaSetDevice(c->device));
   for (int64_t a = 1; a < c->p.n_actors; ++a)
     if (gid[a] <= gid[a - 1]) return fail(c, GRIDDY_ERR_BAD_ARG, "global ids must ascend: they carry the order of the link! calls");
-  if (c->p.n_actors) CUDA_TRY(c, cudaMemcpy(c->p.gid, gid, (size_t)c->p.n_actors * sizeof(int32_t), cudaMemcpyHostToDevice));
+  // right after upload_actors the initial reorder has already permuted the slots: map through the
+  // upload indices that p.gid still holds
+  const int32_t ns = c->ns_host;
+  std::vector<int32_t> cur(ns);
+  if (ns) CUDA_TRY(c, cudaMemcpy(cur.data(), c->p.gid, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int32_t s = 0; s < ns; ++s) {
+    if (cur[s] < 0 || cur[s] >= c->p.n_actors) return fail(c, GRIDDY_ERR_BAD_STATE, "mg_set_global_ids must directly follow upload_actors");
+    cur[s] = gid[cur[s]];
+  }
+  if (ns) CUDA_TRY(c, cudaMemcpy(c->p.gid, cur.data(), (size_t)ns * sizeof(int32_t), cudaMemcpyHostToDevice));
   return GRIDDY_OK;
 }
 

@@ -313,16 +313,18 @@ int synth_grid_network(int n, double spacing, double origin, uint8_t* kind, doub
 }
 
 // procedural-grid.scm:69-95.  agenda_len items per actor alternating sleep-for / travel-to
-// (the shipped example is agenda_len = 2).  Arrays: per actor n_actors entries, agenda_off
-// n_actors+1, item arrays n_actors*agenda_len.
-int synth_actors(int64_t n_actors, uint64_t seed, int agenda_len, int64_t n_segments,
-                 const int32_t* seg_reg, uint8_t* loc_kind, int32_t* container, double* pos,
-                 uint8_t* side, double* speed, double* speed_dt, int64_t* agenda_off,
-                 uint8_t* item_kind, int32_t* item_sleep, int32_t* item_seg, uint8_t* item_side,
-                 double* item_pos) {
+// (the shipped example is agenda_len = 2).  Actor k of the output is the actor with id ids[k] (ids ==
+// null: id k), so that any rank of a partitioned world can generate exactly its own actors: every
+// field is a pure function of (seed, actor id).  Arrays: per actor n entries, agenda_off n+1, item
+// arrays n*agenda_len.
+int synth_actors_ids(int64_t n, const int64_t* ids, uint64_t seed, int agenda_len, int64_t n_segments,
+                     const int32_t* seg_reg, uint8_t* loc_kind, int32_t* container, double* pos,
+                     uint8_t* side, double* speed, double* speed_dt, int64_t* agenda_off,
+                     uint8_t* item_kind, int32_t* item_sleep, int32_t* item_seg, uint8_t* item_side,
+                     double* item_pos) {
   if (n_segments < 1 || agenda_len < 0) return 1;
-  for (int64_t a = 0; a < n_actors; ++a) {
-    const uint64_t ua = (uint64_t)a;
+  for (int64_t a = 0; a < n; ++a) {
+    const uint64_t ua = (uint64_t)(ids ? ids[a] : a);
     const double s = (double)(30 + (int)rnd_int(seed, ua, 0, 30));
     speed[a] = s;
     speed_dt[a] = s / 15.0;   // exact->inexact of the exact rational s * 1/15
@@ -347,7 +349,70 @@ int synth_actors(int64_t n_actors, uint64_t seed, int agenda_len, int64_t n_segm
       }
     }
   }
-  agenda_off[n_actors] = n_actors * agenda_len;
+  agenda_off[n] = n * agenda_len;
+  return 0;
+}
+
+int synth_actors(int64_t n_actors, uint64_t seed, int agenda_len, int64_t n_segments,
+                 const int32_t* seg_reg, uint8_t* loc_kind, int32_t* container, double* pos,
+                 uint8_t* side, double* speed, double* speed_dt, int64_t* agenda_off,
+                 uint8_t* item_kind, int32_t* item_sleep, int32_t* item_seg, uint8_t* item_side,
+                 double* item_pos) {
+  return synth_actors_ids(n_actors, nullptr, seed, agenda_len, n_segments, seg_reg, loc_kind, container, pos,
+                          side, speed, speed_dt, agenda_off, item_kind, item_sleep, item_seg, item_side, item_pos);
+}
+
+// The ids in [0, n_actors) whose start segment belongs to `rank` (owner by item): what one rank of a
+// partitioned world uploads.  ids_out has room for n_actors entries; returns the count in *n_out.
+int synth_actor_ids_of_rank(int64_t n_actors, uint64_t seed, int64_t n_segments, const int32_t* seg_reg,
+                            const int32_t* owner, int32_t rank, int64_t* ids_out, int64_t* n_out) {
+  if (n_segments < 1) return 1;
+  int64_t k = 0;
+  for (int64_t a = 0; a < n_actors; ++a)
+    if (owner[seg_reg[rnd_int(seed, (uint64_t)a, 1, (uint64_t)n_segments)]] == rank) ids_out[k++] = a;
+  *n_out = k;
+  return 0;
+}
+
+// The junction an item hangs off (row-major junction id on the grid): a junction itself, a junction
+// lane's junction, the beg junction of a segment, and for a segment lane the junction it leaves
+// (by_segment = 0, locality) or its segment's beg junction (by_segment = 1, ownership).
+static inline int64_t item_junction(int64_t r, const uint8_t* kind, const int32_t* lane_from_j,
+                                    const int32_t* lane_junction, const int32_t* seg_outer_forw,
+                                    const int32_t* lane_segment, int by_segment) {
+  switch (kind[r]) {
+    case K_JUNCTION: return r;
+    case K_SEGMENT: return lane_from_j[seg_outer_forw[r]];
+    case K_SEGLANE: return by_segment ? lane_from_j[seg_outer_forw[lane_segment[r]]] : lane_from_j[r];
+    case K_JLANE: return lane_junction[r];
+    default: return 0;
+  }
+}
+
+// Locality key per item (griddy_set_locality_keys): items grouped by the junction they hang off,
+// stable within a group.  Counting sort, O(n_items).
+int synth_locality_keys(int64_t n_items, int64_t n_junctions, const uint8_t* kind, const int32_t* lane_from_j,
+                        const int32_t* lane_junction, const int32_t* seg_outer_forw,
+                        const int32_t* lane_segment, uint32_t* key) {
+  std::vector<int64_t> start((size_t)n_junctions + 1, 0);
+  for (int64_t r = 0; r < n_items; ++r)
+    ++start[(size_t)item_junction(r, kind, lane_from_j, lane_junction, seg_outer_forw, lane_segment, 0) + 1];
+  for (int64_t j = 0; j < n_junctions; ++j) start[(size_t)j + 1] += start[(size_t)j];
+  for (int64_t r = 0; r < n_items; ++r)
+    key[r] = (uint32_t)start[(size_t)item_junction(r, kind, lane_from_j, lane_junction, seg_outer_forw, lane_segment, 0)]++;
+  return 0;
+}
+
+// Owner rank per item for `world` horizontal strips of junction rows: a junction owns its junction
+// lanes; a segment and all its lanes belong to the junction the segment begins at.
+int synth_grid_owner(int64_t n_items, int n, int world, const uint8_t* kind, const int32_t* lane_from_j,
+                     const int32_t* lane_junction, const int32_t* seg_outer_forw, const int32_t* lane_segment,
+                     int32_t* owner) {
+  if (n < 1 || world < 1) return 1;
+  for (int64_t r = 0; r < n_items; ++r) {
+    const int64_t j = item_junction(r, kind, lane_from_j, lane_junction, seg_outer_forw, lane_segment, 1);
+    owner[r] = (int32_t)((j / n) * world / n);
+  }
   return 0;
 }
 

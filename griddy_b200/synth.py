@@ -55,54 +55,62 @@ def grid_network(n: int, spacing: float = 150.0, origin: float = 50.0) -> FlatNe
     return FlatNetwork(kind, lane_len, lane_dir, lane_segment, lane_out, lane_junction, so_f, so_b,
                        lane_in=lane_in, grid_n=n, lane_from_j=lf, lane_to_j=lt,
                        turn4=turn4.reshape(ni, 4), seg_reg=seg_reg,
-                       loc_key=grid_locality_keys(kind, lf, lane_junction, so_f))
+                       loc_key=grid_locality_keys(kind, lf, lane_junction, so_f, lane_segment, n * n))
 
 
-def grid_locality_keys(kind, lane_from_j, lane_junction, seg_outer_forw) -> np.ndarray:
+def grid_locality_keys(kind, lane_from_j, lane_junction, seg_outer_forw, lane_segment, n_junctions) -> np.ndarray:
     """Locality key per item for griddy_set_locality_keys: items grouped by the junction they hang
     off (row-major), so that lanes an actor passes through in succession are close in slot order.
     A segment lane hangs off the junction it leaves, a junction lane off its junction, a segment off
     the junction its forw lanes leave."""
-    ni = kind.shape[0]
-    j = np.arange(ni, dtype=np.int64)
-    sl, jl, sg = kind == 2, kind == 3, kind == 1
-    j[sl] = lane_from_j[sl]
-    j[jl] = lane_junction[jl]
-    j[sg] = lane_from_j[seg_outer_forw[sg]]
-    order = np.argsort(j, kind="stable")
-    key = np.empty(ni, np.uint32)
-    key[order] = np.arange(ni, dtype=np.uint32)
+    key = np.empty(kind.shape[0], np.uint32)
+    rc = _lib().synth_locality_keys(C.c_int64(kind.shape[0]), C.c_int64(n_junctions), _p(kind), _p(lane_from_j),
+                                    _p(lane_junction), _p(seg_outer_forw), _p(lane_segment), _p(key))
+    if rc:
+        raise RuntimeError(f"synth_locality_keys -> {rc}")
     return key
 
 
-def grid_actors(net: FlatNetwork, n_actors: int, seed: int = DEFAULT_SEED, agenda_len: int = 2) -> FlatActors:
-    """procedural-grid.scm:69-95: off-road starts, agenda alternating sleep-for / travel-to."""
-    n, L = n_actors, agenda_len
+def grid_actors(net: FlatNetwork, n_actors: int, seed: int = DEFAULT_SEED, agenda_len: int = 2, ids=None) -> FlatActors:
+    """procedural-grid.scm:69-95: off-road starts, agenda alternating sleep-for / travel-to.
+    ids (ascending int64): generate only these actors of the n_actors-actor world (a rank's share)."""
+    if ids is not None:
+        ids = np.ascontiguousarray(ids, np.int64)
+    n, L = (n_actors if ids is None else len(ids)), agenda_len
     loc_kind = np.empty(n, np.uint8); container = np.empty(n, np.int32); pos = np.empty(n, np.float64)
     side = np.empty(n, np.uint8); speed = np.empty(n, np.float64); speed_dt = np.empty(n, np.float64)
     agenda_off = np.empty(n + 1, np.int64)
     item_kind = np.empty(n * L, np.uint8); item_sleep = np.empty(n * L, np.int32)
     item_seg = np.empty(n * L, np.int32); item_side = np.empty(n * L, np.uint8)
     item_pos = np.empty(n * L, np.float64)
-    rc = _lib().synth_actors(C.c_int64(n), C.c_uint64(seed), C.c_int(L), C.c_int64(len(net.seg_reg)),
-                             _p(net.seg_reg), _p(loc_kind), _p(container), _p(pos), _p(side), _p(speed),
-                             _p(speed_dt), _p(agenda_off), _p(item_kind), _p(item_sleep), _p(item_seg),
-                             _p(item_side), _p(item_pos))
+    rc = _lib().synth_actors_ids(C.c_int64(n), _p(ids) if ids is not None else None, C.c_uint64(seed), C.c_int(L),
+                                 C.c_int64(len(net.seg_reg)), _p(net.seg_reg), _p(loc_kind), _p(container), _p(pos),
+                                 _p(side), _p(speed), _p(speed_dt), _p(agenda_off), _p(item_kind), _p(item_sleep),
+                                 _p(item_seg), _p(item_side), _p(item_pos))
     if rc:
-        raise RuntimeError(f"synth_actors -> {rc}")
+        raise RuntimeError(f"synth_actors_ids -> {rc}")
     return FlatActors(loc_kind, container, pos, side, speed, speed_dt, agenda_off, item_kind,
                       item_sleep, item_seg, item_side, item_pos)
+
+
+def actor_ids_of_rank(net: FlatNetwork, n_actors: int, owner: np.ndarray, rank: int, seed: int = DEFAULT_SEED) -> np.ndarray:
+    """Ids (ascending) of the actors of the n_actors-actor world that start on `rank`'s items."""
+    ids = np.empty(n_actors, np.int64)
+    n = C.c_int64(0)
+    rc = _lib().synth_actor_ids_of_rank(C.c_int64(n_actors), C.c_uint64(seed), C.c_int64(len(net.seg_reg)), _p(net.seg_reg),
+                                        _p(np.ascontiguousarray(owner, np.int32)), C.c_int32(rank), _p(ids), C.byref(n))
+    if rc:
+        raise RuntimeError(f"synth_actor_ids_of_rank -> {rc}")
+    return ids[: n.value].copy()
 
 
 def grid_owner(net: FlatNetwork, world: int) -> np.ndarray:
     """Owner rank of every item for `world` horizontal strips of junction rows.  A junction owns its
     junction lanes; a segment and all its lanes belong to the junction the segment begins at."""
-    n, ni = net.grid_n, net.n_items
-    j = np.zeros(ni, np.int64)
-    kind = net.kind
-    jn, sg, sl, jl = kind == 0, kind == 1, kind == 2, kind == 3
-    j[jn] = np.flatnonzero(jn)
-    j[sg] = net.lane_from_j[net.seg_outer_forw[sg]]          # forw lanes leave the segment's beg junction
-    j[sl] = j[net.lane_segment[sl]]
-    j[jl] = net.lane_junction[jl]
-    return ((j // n) * world // n).astype(np.int32)
+    owner = np.empty(net.n_items, np.int32)
+    rc = _lib().synth_grid_owner(C.c_int64(net.n_items), C.c_int(net.grid_n), C.c_int(world), _p(net.kind),
+                                 _p(net.lane_from_j), _p(net.lane_junction), _p(net.seg_outer_forw), _p(net.lane_segment),
+                                 _p(owner))
+    if rc:
+        raise RuntimeError(f"synth_grid_owner -> {rc}")
+    return owner

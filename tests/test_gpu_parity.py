@@ -2,6 +2,8 @@
 index, sleep counter, route status/head, actor order, occupancy counts), fp64 positions within 1e-9
 relative (ActorState.diff) — and in fact compared for exact equality as well, since every operation
 is a correctly rounded IEEE one on both sides."""
+import os
+
 import numpy as np
 import pytest
 
@@ -230,3 +232,18 @@ def test_partitioned_world_matches_oracle(world, n, n_actors):
         moved += int((owner[ds.container[m]] != owner[actors.container[m]]).sum() > 0)
     assert moved > 0, "no actor ever crossed a partition boundary"
     assert ref.vanished > 0
+
+
+def test_partitioned_world_over_nccl():
+    """The NCCL transport (one process per GPU, grouped ncclSend/ncclRecv each tick) against the oracle.
+    Needs two GPUs; the single-GPU suite covers the same kernels through the in-process transport."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mg_nccl_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mg_nccl_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
