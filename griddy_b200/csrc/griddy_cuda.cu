@@ -154,7 +154,7 @@ struct Params {
   const double* halo_recv;   // rearmost positive pos-param of the remote lanes my actors can enter;
                              // lane_tail[remote lane] = -2 - index into this array
   int32_t* emig;             // slots that emigrated this tick
-  int32_t mig_cap;           // records per neighbour per tick
+  int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
   uint8_t* mig_send[MAX_RANKS];   // by destination rank: [int32 count, pad][MigRec x mig_cap]
 };
 
@@ -704,9 +704,10 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     const int a = p.emig[i];
     if (p.dead_mark[a] == tick + 1) continue;   // a ghost's move is void
     const int32_t lane = p.container[a];
-    uint8_t* buf = p.mig_send[p.owner[lane]];
+    const int32_t to = p.owner[lane];
+    uint8_t* buf = p.mig_send[to];
     const int32_t at = atomicAdd((int32_t*)buf, 1);
-    if (at >= p.mig_cap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
+    if (at >= p.mig_cap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
     MigRec r;
     r.pos_old = p.pos[par][a];
     r.pos_new = p.pos[par ^ 1][a];
@@ -741,9 +742,9 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
 }
 
 // Immigrants: a fresh slot each, then onto their lane's inbox like any local mover.
-__global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const uint8_t* __restrict__ buf) {
+__global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const uint8_t* __restrict__ buf, int cap) {
   const int par = tick & 1;
-  const int32_t n = min(*(const int32_t*)buf, p.mig_cap);
+  const int32_t n = min(*(const int32_t*)buf, cap);
   const MigRec* recs = (const MigRec*)(buf + MIG_HEADER);
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const MigRec r = recs[i];
@@ -924,6 +925,9 @@ struct Neighbor {
   int32_t* d_imp_junc = nullptr;    // its junctions whose occupancy my actors read
   double *d_halo_send = nullptr, *d_halo_recv = nullptr;
   uint8_t *d_mig_send = nullptr, *d_mig_recv = nullptr;
+  int mig_out = 0, mig_in = 0;      // records per tick at most: a lane lets one actor out per tick
+  size_t out_bytes() const { return MIG_HEADER + (size_t)mig_out * sizeof(MigRec); }
+  size_t in_bytes() const { return MIG_HEADER + (size_t)mig_in * sizeof(MigRec); }
 };
 
 struct Multi {
@@ -939,7 +943,6 @@ struct Multi {
   void* nccl_comm = nullptr;          // transport 1: NCCL send/recv between processes
   std::vector<Ctx*> peers;            // transport 2: every rank is a context of this process
   cudaEvent_t ev_ready = nullptr;     //   "my send buffers for this phase are written"
-  size_t mig_bytes() const { return MIG_HEADER + (size_t)mig_cap * sizeof(MigRec); }
 };
 
 struct Ctx {
@@ -1088,6 +1091,7 @@ void mg_reset(Ctx* c) {
   c->p.halo_recv = nullptr;
   c->p.my_rank = 0;
   for (auto& b : c->p.mig_send) b = nullptr;
+  for (auto& n : c->p.mig_cap) n = 0;
 }
 
 // Items of `owner_rank` that actors living on `reader_rank` read before they cross: the lanes they
@@ -1110,6 +1114,22 @@ void mg_plan(int64_t n_items, const uint8_t* kind, const int32_t* lane_in, const
     if (mark[r] == 1) lanes.push_back((int32_t)r);
     else if (mark[r] == 2) junctions.push_back((int32_t)r);
   }
+}
+
+// Lanes of `from` with a successor lane on `to`.  A lane lets at most one actor out per tick (the
+// follower of an actor that reaches the end is a tail-gate buffer behind, route.scm:62-74), so this
+// bounds the actors that cross from `from` to `to` in a tick — and sizes the exchange exactly.
+int64_t mg_count_feeders(int64_t n_items, const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out,
+                         const int32_t* owner, int from, int to) {
+  std::vector<uint8_t> mark((size_t)n_items, 0);
+  int64_t n = 0;
+  for (int64_t r = 0; r < n_items; ++r) {
+    if (kind[r] != GRIDDY_JUNCTION_LANE) continue;
+    const int32_t in = lane_in[r], out = lane_out[r];
+    if (owner[r] == to && in >= 0 && owner[in] == from && !mark[in]) { mark[in] = 1; ++n; }
+    if (owner[r] == from && out >= 0 && owner[out] == to && !mark[r]) { mark[r] = 1; ++n; }
+  }
+  return n;
 }
 
 template <typename T>
@@ -1582,11 +1602,11 @@ int tick_finish(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   const unsigned relink_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host / 8 + 127) / 128), 1u), 148u * 64u);
   if (c->mg.on) {
     for (Neighbor& nb : c->mg.nb) {
-      k_immig_unpack<<<std::max(1, c->mg.mig_cap / 512), 128, 0, c->stream>>>(p, (int)tick, nb.d_mig_recv);
+      k_immig_unpack<<<std::max(1, nb.mig_in / 512), 128, 0, c->stream>>>(p, (int)tick, nb.d_mig_recv, nb.mig_in);
       ++c->launches;
+      // upper bound of the slots in use: the neighbour may have filled its buffer
+      c->ns_host = (int32_t)std::min<int64_t>(p.cap, (int64_t)c->ns_host + nb.mig_in);
     }
-    // upper bound of the slots in use: every neighbour may have filled its buffer
-    c->ns_host = (int32_t)std::min<int64_t>(p.cap, (int64_t)c->ns_host + (int64_t)c->mg.mig_cap * (int64_t)c->mg.nb.size());
   }
   k_relink<<<relink_blocks, 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[4], c->stream);
@@ -1608,8 +1628,8 @@ int exchange_nccl(Ctx* c, bool halo) {
       if (out) NCCL_TRY(c, api->Send(nb.d_halo_send, out, NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
       if (in) NCCL_TRY(c, api->Recv(nb.d_halo_recv, in, NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
     } else {
-      NCCL_TRY(c, api->Send(nb.d_mig_send, c->mg.mig_bytes(), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
-      NCCL_TRY(c, api->Recv(nb.d_mig_recv, c->mg.mig_bytes(), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
+      NCCL_TRY(c, api->Send(nb.d_mig_send, nb.out_bytes(), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
+      NCCL_TRY(c, api->Recv(nb.d_mig_recv, nb.in_bytes(), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
     }
   }
   NCCL_TRY(c, api->GroupEnd());
@@ -1637,9 +1657,9 @@ int exchange_local(Ctx* src, bool halo) {
     CUDA_TRY(dst, cudaStreamWaitEvent(dst->stream, src->mg.ev_ready, 0));
     const void* from = halo ? (const void*)nb.d_halo_send : (const void*)nb.d_mig_send;
     void* to = halo ? (void*)back->d_halo_recv : (void*)back->d_mig_recv;
-    const size_t bytes = halo ? (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double) : src->mg.mig_bytes();
-    if (halo && nb.n_exp_lanes + nb.n_exp_junc != back->n_imp_lanes + back->n_imp_junc)
-      return fail(src, GRIDDY_ERR_BAD_STATE, "halo lists of two neighbours disagree");
+    const size_t bytes = halo ? (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double) : nb.out_bytes();
+    if (nb.n_exp_lanes + nb.n_exp_junc != back->n_imp_lanes + back->n_imp_junc || nb.mig_out != back->mig_in)
+      return fail(src, GRIDDY_ERR_BAD_STATE, "exchange plans of two neighbours disagree");
     if (bytes) CUDA_TRY(dst, cudaMemcpyPeerAsync(to, dst->device, from, src->device, bytes, dst->stream));
   }
   return GRIDDY_OK;
@@ -1986,17 +2006,19 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     nb.d_halo_recv = m.d_halo_recv + off;
     for (size_t k = 0; k < L.imp_l.size(); ++k) m.import_marks.emplace_back(L.imp_l[k], (int32_t)(-2 - (int64_t)(off + k)));
     off += L.imp_l.size() + L.imp_j.size();
-    TRY(mg_alloc(c, &nb.d_mig_send, m.mig_bytes()));
-    TRY(mg_alloc(c, &nb.d_mig_recv, m.mig_bytes()));
-    CUDA_TRY(c, cudaMemset(nb.d_mig_send, 0, m.mig_bytes()));
-    CUDA_TRY(c, cudaMemset(nb.d_mig_recv, 0, m.mig_bytes()));
+    nb.mig_out = (int)std::min<int64_t>(mig_cap, mg_count_feeders(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), owner, rank, r));
+    nb.mig_in = (int)std::min<int64_t>(mig_cap, mg_count_feeders(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), owner, r, rank));
+    TRY(mg_alloc(c, &nb.d_mig_send, nb.out_bytes()));
+    TRY(mg_alloc(c, &nb.d_mig_recv, nb.in_bytes()));
+    CUDA_TRY(c, cudaMemset(nb.d_mig_send, 0, nb.out_bytes()));
+    CUDA_TRY(c, cudaMemset(nb.d_mig_recv, 0, nb.in_bytes()));
     c->p.mig_send[r] = nb.d_mig_send;
+    c->p.mig_cap[r] = nb.mig_out;
     m.nb.push_back(nb);
   }
   c->p.owner = m.d_owner;
   c->p.my_rank = rank;
   c->p.halo_recv = m.d_halo_recv;
-  c->p.mig_cap = mig_cap;
   return GRIDDY_OK;
 }
 

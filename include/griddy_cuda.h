@@ -147,7 +147,8 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
  * Read back with griddy_download_local. */
 int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* owner /* n_items */,
                         const int32_t* lane_in /* n_items: junction lanes: their input segment lane */,
-                        int32_t mig_cap /* boundary crossings per neighbour per tick */,
+                        int32_t mig_cap /* ceiling on boundary crossings per neighbour per tick; the exchange is
+                                            sized by min(mig_cap, lanes that lead across), which crossings cannot exceed */,
                         int64_t extra_slots /* room for actors that arrive from other ranks */);
 int griddy_mg_set_global_ids(void* ctx, const int32_t* gid /* one per uploaded actor, ascending */);
 int griddy_mg_nccl_unique_id(uint8_t* out128);
