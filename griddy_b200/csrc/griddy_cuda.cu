@@ -38,9 +38,9 @@
 //              or a neighbouring cache line.  Actors that change lane or road-side are appended to
 //              the movers list and pushed on their target lane's inbox (warp-aggregated atomics);
 //              their lanes are marked touched.
-//   k_relink   one thread per touched lane: merges the lane's surviving residents (already in
-//              order: residents never overtake) with its sorted entrants, drops equal-key losers
-//              exactly as bbtree-set would, rewrites the ahead pointers.
+//   k_relink   one thread per touched lane.  Lanes are doubly linked lists: leavers and ghosts are
+//              unlinked in O(1), entrants are inserted by a short walk up from the rear; an entrant
+//              that lands on an occupied key is resolved exactly as bbtree-set would.
 //   k_settle   one thread per mover: publishes its new ahead pointer, applies junction occupancy
 //              deltas.
 //
@@ -52,8 +52,8 @@
 // Equal keys among residents.  Residents of a lane keep their relative order (a follower is clamped
 // to leader.old - buf, route.scm:68-74), but only weakly: in fp64 two residents an ulp apart can
 // round to the same new key, and bbtree-set then drops the one visited first — the leader, since a
-// lane is walked in descending pos-param.  Such ties are always list-adjacent.  Lanes that were
-// touched anyway resolve them in k_relink; elsewhere they are resolved one tick late at no cost: an
+// lane is walked in descending pos-param.  Such ties are always list-adjacent.  They are resolved one
+// tick late at no cost: an
 // actor whose list follower holds an equal key is a GHOST (it is not part of the world any more).
 // Every on-road actor reads its leader's key each tick, sees the tie, marks the ghost dead and has
 // the lane relinked; whatever the ghost itself did this tick is discarded by k_relink / k_settle.
@@ -117,8 +117,8 @@ struct Params {
   const uint32_t* loc_key;   // locality key for the reorder (default: the registration index)
   int32_t grid_n;
   const int32_t *lane_from_j, *lane_to_j, *turn4;
-  int32_t *lane_tail, *occ, *lane_mark, *inbox_head;
-  int32_t* lane_ghost;   // tick+1 when a resident of the lane was found to be a ghost during `tick`
+  int32_t *lane_tail, *occ, *lane_mark;
+  int32_t *inbox_head, *outbox_head, *ghost_head;   // per lane, this tick: entrants, leavers, ghosts found
   // slots
   int32_t cap;     // allocated slots
   int32_t* scal;   // SC_*: device error bits, slots in use, live actors counted by the reorder
@@ -143,7 +143,8 @@ struct Params {
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
   // per-tick scratch, by slot
-  int32_t *mv_old, *ahead_new, *inbox_next;
+  int32_t* behind;   // slot of the next actor behind on the same lane (-1 at the rear): lanes are doubly linked
+  int32_t *mv_old, *ahead_new, *behind_new, *inbox_next, *outbox_next, *ghost_next;
   int32_t* dead_mark;   // tick+1 when the actor was found to be a ghost during `tick`
   int32_t *touched, *slow;
   int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, touched lanes, deferred actors
@@ -226,6 +227,11 @@ __device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane,
   mark_touched(p, lane, tick, sink);
 }
 
+__device__ __forceinline__ void leave_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
+  p.outbox_next[a] = atomicExch(&p.outbox_head[lane], a);
+  mark_touched(p, lane, tick, sink);
+}
+
 // ------------------------------------------------------------------------------------------------
 // advance$ for one actor (simulate.scm:93-111) with route.scm:53-141 inlined.  `a` is a slot; st,
 // ah, cur, dlt, buf, lead were loaded by the caller (ah = -1 and lead = 0 when there is no leader).
@@ -240,13 +246,13 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   // nearest actor ahead on the lane (bbtree-find-min's only candidate, util.scm:152-162), skipping
   // ghosts: leaders that this actor replaced with an equal key at the end of the previous tick
   if (ah >= 0 && lead == cur) {
+    const int32_t lane = p.container[a];
     do {
-      p.dead_mark[ah] = tick + 1;
+      if (atomicExch(&p.dead_mark[ah], tick + 1) != tick + 1)   // the first to notice hands it to k_relink
+        p.ghost_next[ah] = atomicExch(&p.ghost_head[lane], ah);
       ah = p.sa[ah].ahead;
       if (ah >= 0) lead = pos_old[ah];
     } while (ah >= 0 && lead == cur);
-    const int32_t lane = p.container[a];
-    p.lane_ghost[lane] = tick + 1;
     mark_touched(p, lane, tick, sink);
   }
 
@@ -262,6 +268,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
       if (back) {   // jumped back past other residents: re-insert by key
         const int32_t lane = p.container[a];
         p.mv_old[a] = lane;
+        leave_lane(p, a, lane, tick, sink);
         enter_lane(p, a, lane, tick, sink);
       }
       return target;
@@ -304,7 +311,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u);
     if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
     else enter_lane(p, a, target, tick, sink);
-    mark_touched(p, lane, tick, sink);
+    leave_lane(p, a, lane, tick, sink);
     return tnext;
   }
 
@@ -375,7 +382,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE);
   ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
   p.sa[a].st = ns;
-  mark_touched(p, lane, tick, sink);
+  leave_lane(p, a, lane, tick, sink);
   return dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
 }
 
@@ -542,7 +549,18 @@ __device__ int later_processed(const Params& p, int x, int y, int32_t lane, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_relink: rebuild the ascending-pos list of every lane an actor entered or left this tick.
+// k_relink: one thread per lane that an actor entered or left this tick.  Lanes are doubly linked
+// lists in ascending pos-param, so nothing walks a whole lane: leavers (the lane's outbox) and ghosts
+// found this tick (its ghost list) are unlinked in O(1) each; entrants (its inbox, sorted) are
+// inserted by walking up from the rear — entrants land near pos 0, so that is a step or two.
+// Residents keep their relative order (a follower is clamped behind its leader, route.scm:68-74).
+// Equal keys: an entrant that lands on a resident's or another entrant's key is resolved here, the
+// later-processed one stays (core.scm:173-178); two residents that round to the same key are left
+// linked and resolved next tick through the ghost rule (file header) — on every lane, touched or not.
+// A mover's own pointers are staged in ahead_new / behind_new (its old ones still describe its old
+// lane, which another thread may be unlinking it from) and published by k_settle.
+constexpr int32_t UNLINKED = -3;
+
 __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
   const int par = tick & 1;
   const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
@@ -550,29 +568,33 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
   const double* __restrict__ pos_new = p.pos[par ^ 1];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = p.touched[i];
-    const int32_t inbox = p.inbox_head[lane];
-    p.inbox_head[lane] = -1;
+    const int32_t inbox = p.inbox_head[lane], outbox = p.outbox_head[lane], ghosts = p.ghost_head[lane];
+    if (inbox >= 0) p.inbox_head[lane] = -1;
+    if (outbox >= 0) p.outbox_head[lane] = -1;
+    if (ghosts >= 0) p.ghost_head[lane] = -1;
     const bool jl = p.kind[lane] == GRIDDY_JUNCTION_LANE;
-    const bool has_ghost = p.lane_ghost[lane] == tick + 1;   // else no resident's dead_mark needs a look
 
-    // Residents that stay, in list order (they keep their relative order: route.scm:68-74).
-    // Ghosts found this tick are unlinked here; one that also moved is finalised by k_settle.
-    auto next_resident = [&](int32_t z) {
-      while (z >= 0) {
-        const SA sa = p.sa[z];
-        const uint32_t sz = sa.st;
-        const bool ghost = has_ghost && p.dead_mark[z] == tick + 1;
-        if (!(sz & ST_MOVED) && !ghost) break;
-        if (ghost && !(sz & ST_MOVED)) {
-          p.sa[z].st = sz & ~ST_ALIVE;
-          if (jl) atomicSub(&p.occ[p.lane_junction[lane]], 1);
-        }
-        z = sa.ahead;
-      }
-      return z;
+    // 1. unlink.  A ghost that also moved is on both lists; the second visit finds it UNLINKED.
+    auto unlink = [&](int32_t z) {
+      const int32_t f = p.sa[z].ahead;
+      if (f == UNLINKED) return false;
+      const int32_t b = p.behind[z];
+      if (b >= 0) p.sa[b].ahead = f; else p.lane_tail[lane] = f;
+      if (f >= 0) p.behind[f] = b;
+      p.sa[z].ahead = UNLINKED;
+      return true;
     };
-    int32_t x = next_resident(p.lane_tail[lane]);
-    // entrants by ascending (pos-param, id): selection over the inbox, which is short
+    for (int32_t z = outbox; z >= 0; z = p.outbox_next[z]) unlink(z);
+    for (int32_t z = ghosts; z >= 0; z = p.ghost_next[z]) {
+      const uint32_t sz = p.sa[z].st;
+      if (unlink(z) && !(sz & ST_MOVED)) {   // one that also moved is finalised by k_settle
+        p.sa[z].st = sz & ~ST_ALIVE;
+        if (jl) atomicSub(&p.occ[p.lane_junction[lane]], 1);
+      }
+    }
+    if (inbox < 0) continue;
+
+    // 2. insert the entrants by ascending (pos-param, slot): selection over the inbox, which is short
     double e_pos = 0.0;
     int32_t e = -1;
     auto next_entrant = [&](bool first) {
@@ -587,42 +609,36 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
       e = best;
       e_pos = best_pos;
     };
-    next_entrant(true);
-
-    int32_t prev = -1, pending = -1;
-    auto commit = [&](int32_t z) {
-      if (prev < 0) p.lane_tail[lane] = z;
-      else if (p.sa[prev].st & ST_MOVED) p.ahead_new[prev] = z;
-      else p.sa[prev].ahead = z;
-      prev = z;
+    auto next_of = [&](int32_t z) {
+      const SA sz = p.sa[z];
+      return (sz.st & ST_MOVED) ? p.ahead_new[z] : sz.ahead;
     };
-    while (x >= 0 || e >= 0) {
-      int32_t cand;
-      if (e < 0 || (x >= 0 && pos_new[x] <= e_pos)) {
-        cand = x;
-        x = next_resident(p.sa[x].ahead);
-      } else {
-        cand = e;
-        next_entrant(false);
+    auto link = [&](int32_t b, int32_t z, int32_t f) {   // b -> z -> f, z an entrant
+      if (b < 0) p.lane_tail[lane] = z;
+      else if (p.sa[b].st & ST_MOVED) p.ahead_new[b] = z;
+      else p.sa[b].ahead = z;
+      p.ahead_new[z] = f;
+      p.behind_new[z] = b;
+      if (f >= 0) {
+        if (p.sa[f].st & ST_MOVED) p.behind_new[f] = z; else p.behind[f] = z;
       }
-      if (pending < 0) {
-        pending = cand;
-      } else if (pos_new[cand] == pos_new[pending]) {   // equal key: bbtree-set keeps the later one
-        const int32_t win = later_processed(p, cand, pending, lane, pos_old, tick);
-        const int32_t lose = win == cand ? pending : cand;
+    };
+    int32_t prev = -1, x = p.lane_tail[lane];
+    for (next_entrant(true); e >= 0; next_entrant(false)) {
+      while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = next_of(x); }
+      if (x >= 0 && pos_new[x] == e_pos) {   // equal key: bbtree-set keeps the one processed later
+        const bool e_wins = later_processed(p, e, x, lane, pos_old, tick) == e;
+        const int32_t lose = e_wins ? x : e;
         const uint32_t sl = p.sa[lose].st;
         p.sa[lose].st = sl & ~ST_ALIVE;
         if (jl && !(sl & ST_MOVED)) atomicSub(&p.occ[p.lane_junction[lane]], 1);
-        pending = win;
+        if (!e_wins) continue;
+        link(prev, e, next_of(x));   // e takes x's place
       } else {
-        commit(pending);
-        pending = cand;
+        link(prev, e, x);
       }
+      x = e;   // the next entrant (same or higher key) meets e first
     }
-    if (pending >= 0) commit(pending);
-    if (prev < 0) p.lane_tail[lane] = -1;
-    else if (p.sa[prev].st & ST_MOVED) p.ahead_new[prev] = -1;
-    else p.sa[prev].ahead = -1;
   }
 }
 
@@ -644,6 +660,7 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
     }
     if ((st & ST_ALIVE) && (st & ST_ONROAD)) {
       p.sa[a].ahead = p.ahead_new[a];
+      p.behind[a] = p.behind_new[a];
       const int32_t lane = p.container[a];
       if (p.kind[lane] == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[p.lane_junction[lane]], 1);
     }
@@ -764,6 +781,7 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
       p.item_pos[it + k] = r.item_pos[k];
     }
     p.sa[a] = SA{(uint32_t)r.st, -1};
+    p.behind[a] = -1;
     p.pos[par][a] = r.pos_old;       // processing order among a lane's entrants looks at old lane and old key
     p.pos[par ^ 1][a] = r.pos_new;
     p.delta[a] = r.delta;
@@ -792,9 +810,9 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
 // per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
 
 // Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
-constexpr int PERM4 = 10, PERM8 = 8;
+constexpr int PERM4 = 11, PERM8 = 8;
 enum { P4_CONTAINER, P4_AUX, P4_AGENDA_CUR, P4_ROUTE_CUR, P4_GID, P4_LAND_TICK, P4_LAND_LANE, P4_TJ, P4_AGENDA_BEG,
-       P4_AGENDA_END };
+       P4_AGENDA_END, P4_BEHIND };
 enum { P8_SA, P8_POS, P8_DELTA, P8_BUF, P8_ARRIVE, P8_LAND_POS, P8_SPEED, P8_SPEED_DT };
 
 struct Permute {
@@ -844,13 +862,26 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
   const int s = blockIdx.x * 256 + threadIdx.x;
   if (s >= p.scal[SC_NALIVE]) return;
   const uint32_t old = vals[s];
+  // ahead / behind are meaningful on the road only; an off-road actor's values are stale
+  SA sa = ((const SA*)q.src8[P8_SA])[old];
+  const bool on_road = sa.st & ST_ONROAD;
 #pragma unroll
-  for (int k = 0; k < PERM4; ++k) q.dst4[k][s] = q.src4[k][old];
+  for (int k = 0; k < PERM4; ++k) {
+    uint32_t v = q.src4[k][old];
+    if (k == P4_BEHIND) {
+      if (on_road && (int32_t)v >= 0) {
+        v = (uint32_t)newslot[v];
+        if ((int32_t)v < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's follower must be live
+      } else {
+        v = 0xffffffffu;
+      }
+    }
+    q.dst4[k][s] = v;
+  }
 #pragma unroll
   for (int k = 0; k < PERM8; ++k) {
-    if (k == P8_SA) {   // ahead is meaningful on the road only; an off-road actor's value is stale
-      SA sa = ((const SA*)q.src8[k])[old];
-      if ((sa.st & ST_ONROAD) && sa.ahead >= 0) {
+    if (k == P8_SA) {
+      if (on_road && sa.ahead >= 0) {
         sa.ahead = newslot[sa.ahead];
         if (sa.ahead < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's leader must be live
       } else {
@@ -1038,6 +1069,7 @@ void bind_slot_arrays(Ctx* c, int par) {
   p.gid = (int32_t*)c->cur4[P4_GID];
   p.agenda_beg = (int32_t*)c->cur4[P4_AGENDA_BEG];
   p.agenda_end = (int32_t*)c->cur4[P4_AGENDA_END];
+  p.behind = (int32_t*)c->cur4[P4_BEHIND];
   p.speed = (double*)c->cur8[P8_SPEED];
   p.speed_dt = (double*)c->cur8[P8_SPEED_DT];
   p.land_tick = (int32_t*)c->cur4[P4_LAND_TICK];
@@ -1294,7 +1326,8 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   TRY(dev_alloc(c, c->net_allocs, &p.occ, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.lane_mark, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.inbox_head, n_items));
-  TRY(dev_alloc(c, c->net_allocs, &p.lane_ghost, n_items));
+  TRY(dev_alloc(c, c->net_allocs, &p.outbox_head, n_items));
+  TRY(dev_alloc(c, c->net_allocs, &p.ghost_head, n_items));
   c->h_kind.assign(kind, kind + n_items);
   c->h_lane_junction.assign(lane_junction, lane_junction + n_items);
   c->h_lane_out.assign(lane_out, lane_out + n_items);
@@ -1393,7 +1426,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
 
   // Initial world: link! every actor in id order (core.scm:169-178).  Slot = id until the first reorder.
   std::vector<SA> sa(n);
-  std::vector<int32_t> aux(n, 0), acur(n), ident(n);
+  std::vector<int32_t> aux(n, 0), acur(n), ident(n), behind(n, -1);
   std::vector<int32_t> lane_tail(p.n_items, -1), occ(p.n_items, 0);
   std::vector<int32_t> on_road;
   for (int64_t a = 0; a < n; ++a) {
@@ -1420,7 +1453,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     const bool replaced = k + 1 < on_road.size() && container[on_road[k + 1]] == container[a] && pos[on_road[k + 1]] == pos[a];
     if (replaced) { sa[a].st &= ~ST_ALIVE; continue; }
     const int32_t lane = container[a];
-    if (prev >= 0 && container[prev] == lane) sa[prev].ahead = a; else lane_tail[lane] = a;
+    if (prev >= 0 && container[prev] == lane) { sa[prev].ahead = a; behind[a] = prev; } else lane_tail[lane] = a;
     if (c->h_kind[lane] == GRIDDY_JUNCTION_LANE) ++occ[c->h_lane_junction[lane]];
     prev = a;
   }
@@ -1439,6 +1472,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   auto put4 = [&](int k, const void* host) { return n ? cudaMemcpy(c->cur4[k], host, (size_t)n * 4, cudaMemcpyHostToDevice) : cudaSuccess; };
   if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SA], sa.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(c, put4(P4_CONTAINER, container));
+  CUDA_TRY(c, put4(P4_BEHIND, behind.data()));
   CUDA_TRY(c, cudaMemset(c->cur4[P4_TJ], 0xFF, (size_t)cap * sizeof(int32_t)));
   CUDA_TRY(c, put4(P4_AUX, aux.data()));
   CUDA_TRY(c, put4(P4_AGENDA_CUR, acur.data()));
@@ -1462,6 +1496,9 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   TRY(dev_alloc(c, pool, &p.mv_old, cap));
   TRY(dev_alloc(c, pool, &p.ahead_new, cap));
   TRY(dev_alloc(c, pool, &p.inbox_next, cap));
+  TRY(dev_alloc(c, pool, &p.behind_new, cap));
+  TRY(dev_alloc(c, pool, &p.outbox_next, cap));
+  TRY(dev_alloc(c, pool, &p.ghost_next, cap));
   TRY(dev_alloc(c, pool, &p.dead_mark, cap));
   TRY(dev_alloc(c, pool, &p.touched, 2 * cap));
   TRY(dev_alloc(c, pool, &p.slow, cap));
@@ -1519,7 +1556,8 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   CUDA_TRY(c, cudaMemcpy(p.lane_tail, lane_tail.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMemcpy(p.occ, occ.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaMemset(p.lane_mark, 0, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
-  CUDA_TRY(c, cudaMemset(p.lane_ghost, 0, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMemset(p.outbox_head, 0xFF, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
+  CUDA_TRY(c, cudaMemset(p.ghost_head, 0xFF, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
   CUDA_TRY(c, cudaMemset(p.inbox_head, 0xFF, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
   c->tick = 0;
   c->ns_host = (int32_t)n;
