@@ -107,6 +107,29 @@ struct __align__(8) SA {
   int32_t ahead;
 };
 
+// Everything about a slot that only matters when its actor does something rare (changes lane, wakes,
+// starts or ends a route), in one 64-byte record — one DRAM burst instead of a dozen sectors.
+struct __align__(16) Cold {
+  // travels with the actor
+  int32_t container;                  // lane (on road) or segment (off road)
+  int32_t agenda_cur, route_cur;      // agenda head (index into the item arrays), route head (explicit routes)
+  int32_t gid;                        // the actor's id (global id on a partitioned world)
+  int32_t agenda_beg, agenda_end;     // its agenda in the item arrays
+  int32_t land_tick, land_lane;       // landing stamp (with ColdF::land_pos), see "processing order"
+  int32_t behind;                     // slot of the next actor behind on the lane (-1 at the rear)
+  // list surgery of the current tick
+  int32_t mv_old;                     // where a mover came from: lane, or ~segment
+  int32_t ahead_new, behind_new;      // a mover's pointers on its new lane, published by k_settle
+  int32_t inbox_next, outbox_next, ghost_next;
+  int32_t dead_mark;                  // tick+1 when the actor was found to be a ghost during `tick`
+};
+struct __align__(16) ColdF {
+  double arrive;            // target of the (arrive-at _) that ends the current route
+  double land_pos;          // landing stamp
+  double speed, speed_dt;   // max-speed and fl(max-speed * dt)
+};
+static_assert(sizeof(Cold) == 64 && sizeof(ColdF) == 32, "cold records are one / half a DRAM burst");
+
 struct Params {
   // network, by registration index
   int64_t n_items;
@@ -125,14 +148,10 @@ struct Params {
   SA* sa;          // {st, ahead}: one 8-byte load per actor
   double* pos[2];
   double *delta, *buf;
-  int32_t *aux, *container, *agenda_cur, *route_cur;
-  int32_t* gid;                      // the actor's id (global id on a partitioned world)
-  int32_t *agenda_beg, *agenda_end;  // its agenda in the item arrays
-  double *speed, *speed_dt;          // max-speed and fl(max-speed * dt)
-  int32_t* tj;   // junction of the lane the route head turns onto, -1 if that is not a junction lane
-  double* arrive;
-  int32_t *land_tick, *land_lane;
-  double* land_pos;
+  int32_t* aux;   // sleeping: remaining time; travelling: head route step (lane, or -1 arrive-at)
+  int32_t* tj;    // junction of the lane the route head turns onto, -1 if that is not a junction lane
+  Cold* cold;
+  ColdF* coldf;
   // agenda items (immutable; actors that arrive from another rank append theirs)
   int64_t n_actors;
   uint8_t* item_kind;
@@ -143,9 +162,6 @@ struct Params {
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
   // per-tick scratch, by slot
-  int32_t* behind;   // slot of the next actor behind on the same lane (-1 at the rear): lanes are doubly linked
-  int32_t *mv_old, *ahead_new, *behind_new, *inbox_next, *outbox_next, *ghost_next;
-  int32_t* dead_mark;   // tick+1 when the actor was found to be a ghost during `tick`
   int32_t *touched, *slow;
   int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, touched lanes, deferred actors
   double dt, two_size;
@@ -203,7 +219,7 @@ __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop)
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
 __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_t ac, int32_t* aux) {
-  if (ac >= p.agenda_end[a]) { *aux = 0; return HEAD_NONE; }
+  if (ac >= p.cold[a].agenda_end) { *aux = 0; return HEAD_NONE; }
   if (p.item_kind[ac] == GRIDDY_SLEEP_FOR) { *aux = p.item_sleep[ac]; return HEAD_SLEEP; }
   *aux = 0;
   return HEAD_TRAVEL;
@@ -223,12 +239,12 @@ __device__ __forceinline__ void mark_touched(const Params& p, int32_t lane, int 
 }
 
 __device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
-  p.inbox_next[a] = atomicExch(&p.inbox_head[lane], a);
+  p.cold[a].inbox_next = atomicExch(&p.inbox_head[lane], a);
   mark_touched(p, lane, tick, sink);
 }
 
 __device__ __forceinline__ void leave_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
-  p.outbox_next[a] = atomicExch(&p.outbox_head[lane], a);
+  p.cold[a].outbox_next = atomicExch(&p.outbox_head[lane], a);
   mark_touched(p, lane, tick, sink);
 }
 
@@ -246,10 +262,10 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   // nearest actor ahead on the lane (bbtree-find-min's only candidate, util.scm:152-162), skipping
   // ghosts: leaders that this actor replaced with an equal key at the end of the previous tick
   if (ah >= 0 && lead == cur) {
-    const int32_t lane = p.container[a];
+    const int32_t lane = p.cold[a].container;
     do {
-      if (atomicExch(&p.dead_mark[ah], tick + 1) != tick + 1)   // the first to notice hands it to k_relink
-        p.ghost_next[ah] = atomicExch(&p.ghost_head[lane], ah);
+      if (atomicExch(&p.cold[ah].dead_mark, tick + 1) != tick + 1)   // the first to notice hands it to k_relink
+        p.cold[ah].ghost_next = atomicExch(&p.ghost_head[lane], ah);
       ah = p.sa[ah].ahead;
       if (ah >= 0) lead = pos_old[ah];
     } while (ah >= 0 && lead == cur);
@@ -261,13 +277,13 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     double next = __dadd_rn(cur, dlt);
     if (ah >= 0 && lead > cur && lead <= __dadd_rn(next, buf)) next = __dsub_rn(lead, buf);
     if (st & ST_ARRIVE) {   // route-step/arrive-at$  route.scm:76-90
-      const double target = p.arrive[a];
+      const double target = p.coldf[a].arrive;
       if (!(next >= target)) return next;
       const bool back = target < cur;
       p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_ARRIVE)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u);
       if (back) {   // jumped back past other residents: re-insert by key
-        const int32_t lane = p.container[a];
-        p.mv_old[a] = lane;
+        const int32_t lane = p.cold[a].container;
+        p.cold[a].mv_old = lane;
         leave_lane(p, a, lane, tick, sink);
         enter_lane(p, a, lane, tick, sink);
       }
@@ -278,9 +294,9 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const int32_t tj = p.tj[a];   // junction-full?  route.scm:98-108 (k_advance has usually answered this)
     if (tj >= 0 && p.occ[tj] > 0) return cur;   // waiting
     const int32_t target = p.aux[a];
-    const int32_t lane = p.container[a];
-    const int32_t item = p.agenda_cur[a];
-    const double speed = p.speed[a];
+    const int32_t lane = p.cold[a].container;
+    const int32_t item = p.cold[a].agenda_cur;
+    const double speed = p.coldf[a].speed;
     const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), speed);
     const double time_remaining = __dsub_rn(p.dt, time_spent);
     const double tlen = p.lane_len[target];
@@ -299,15 +315,15 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
         if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
       }
     }
-    int32_t rc = p.route_off ? p.route_cur[a] + 1 : 0;
+    int32_t rc = p.route_off ? p.cold[a].route_cur + 1 : 0;
     const int32_t nhop = route_head_on(p, target, item, &rc);
-    if (p.route_off) p.route_cur[a] = rc;
+    if (p.route_off) p.cold[a].route_cur = rc;
     p.aux[a] = nhop;
     p.tj[a] = junction_of_hop(p, nhop);
-    p.delta[a] = __dmul_rn(p.speed_dt[a], tinv);
+    p.delta[a] = __dmul_rn(p.coldf[a].speed_dt, tinv);
     p.buf[a] = tbuf;
-    p.container[a] = target;
-    p.mv_old[a] = lane;
+    p.cold[a].container = target;
+    p.cold[a].mv_old = lane;
     p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u);
     if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
     else enter_lane(p, a, target, tick, sink);
@@ -319,10 +335,10 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {            // sleep$  simulate.scm:74-78
     const int32_t t = p.aux[a];
     if (t == 0) {
-      const int32_t ac = p.agenda_cur[a] + 1;
+      const int32_t ac = p.cold[a].agenda_cur + 1;
       int32_t aux;
       const uint32_t h = load_head(p, a, ac, &aux);
-      p.agenda_cur[a] = ac;
+      p.cold[a].agenda_cur = ac;
       p.aux[a] = aux;
       p.sa[a].st = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
     } else {
@@ -335,10 +351,10 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     return cur;
   }
 
-  const int32_t item = p.agenda_cur[a];
+  const int32_t item = p.cold[a].agenda_cur;
   if (rs == GRIDDY_ROUTE_NONE) {   // begin-route$  simulate.scm:80-85
     if (st & ST_ONROAD) { dev_error(p, DEV_ERR_BEGIN_ON_ROAD); return cur; }
-    const int32_t seg = p.container[a];
+    const int32_t seg = p.cold[a].container;
     const int32_t init_lane = outer_lane(p, seg, st & ST_SIDE);
     const int32_t dest_lane = outer_lane(p, p.item_seg[item], p.item_side[item]);
     if (init_lane < 0 || dest_lane < 0) { dev_error(p, DEV_ERR_NO_LANE); return cur; }
@@ -349,14 +365,14 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     int32_t rc = p.route_off ? (int32_t)p.route_off[item] : 0;
     const int32_t hop = route_head_on(p, init_lane, item, &rc);
     const double len = p.lane_len[init_lane];
-    p.route_cur[a] = rc;
-    p.arrive[a] = dest_pos;
+    p.cold[a].route_cur = rc;
+    p.coldf[a].arrive = dest_pos;
     p.aux[a] = hop;
     p.tj[a] = junction_of_hop(p, hop);
-    p.delta[a] = __dmul_rn(p.speed_dt[a], __ddiv_rn(1.0, len));
+    p.delta[a] = __dmul_rn(p.coldf[a].speed_dt, __ddiv_rn(1.0, len));
     p.buf[a] = __ddiv_rn(p.two_size, len);
-    p.container[a] = init_lane;
-    p.mv_old[a] = ~seg;
+    p.cold[a].container = init_lane;
+    p.cold[a].mv_old = ~seg;
     p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
               ST_ONROAD | ST_MOVED | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);
     enter_lane(p, a, init_lane, tick, sink);
@@ -364,21 +380,21 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   }
 
   // end-route$  simulate.scm:87-91   (rs == GRIDDY_ROUTE_DONE)
-  const int32_t lane = p.container[a];
+  const int32_t lane = p.cold[a].container;
   if (p.kind[lane] != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); return cur; }
   const int32_t seg = p.lane_segment[lane];
   const uint32_t dir = p.lane_dir[lane];
   const int32_t ac = item + 1;
   int32_t aux;
   const uint32_t h = load_head(p, a, ac, &aux);
-  p.agenda_cur[a] = ac;
+  p.cold[a].agenda_cur = ac;
   p.aux[a] = aux;
-  p.container[a] = seg;
-  p.mv_old[a] = lane;
+  p.cold[a].container = seg;
+  p.cold[a].mv_old = lane;
   // landing stamp: where this actor sits in the segment's consed list (core.scm:169-171)
-  p.land_tick[a] = tick + 1;
-  p.land_lane[a] = lane;
-  p.land_pos[a] = cur;
+  p.cold[a].land_tick = tick + 1;
+  p.cold[a].land_lane = lane;
+  p.coldf[a].land_pos = cur;
   uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE);
   ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
   p.sa[a].st = ns;
@@ -515,14 +531,14 @@ __global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
 
 // earlier(a,b) among actors that landed on the same segment in the same tick
 __device__ __forceinline__ bool landed_earlier(const Params& p, int a, int b, int32_t t_land) {
-  const int32_t la = p.land_lane[a], lb = p.land_lane[b];
+  const int32_t la = p.cold[a].land_lane, lb = p.cold[b].land_lane;
   if (t_land == 0) return la < lb;   // initial placement: land_lane holds the link! order
   if (la != lb) return la > lb;      // higher registration index comes first in static-items
-  return p.land_pos[a] > p.land_pos[b];   // a lane yields its actors in descending pos-param
+  return p.coldf[a].land_pos > p.coldf[b].land_pos;   // a lane yields its actors in descending pos-param
 }
 
 __device__ __forceinline__ bool stamp_less(const Params& p, int a, int b, uint32_t sta) {
-  const int32_t ta = p.land_tick[a], tb = p.land_tick[b];
+  const int32_t ta = p.cold[a].land_tick, tb = p.cold[b].land_tick;
   if (ta != tb) return ta < tb;
   return (sta & ST_CLASS_P) ? landed_earlier(p, b, a, ta) : landed_earlier(p, a, b, ta);
 }
@@ -531,8 +547,8 @@ __device__ __forceinline__ bool stamp_less(const Params& p, int a, int b, uint32
 // conses while get-actors walks head to tail), so a stamp's sign alternates with tick parity.
 __device__ bool offroad_before(const Params& p, int a, int b, int tick) {
   const uint32_t sta = p.sa[a].st, stb = p.sa[b].st;
-  const bool nega = (((tick - p.land_tick[a]) & 1) != 0) == ((sta & ST_CLASS_P) != 0);
-  const bool negb = (((tick - p.land_tick[b]) & 1) != 0) == ((stb & ST_CLASS_P) != 0);
+  const bool nega = (((tick - p.cold[a].land_tick) & 1) != 0) == ((sta & ST_CLASS_P) != 0);
+  const bool negb = (((tick - p.cold[b].land_tick) & 1) != 0) == ((stb & ST_CLASS_P) != 0);
   if (nega != negb) return nega;
   return nega ? stamp_less(p, b, a, stb) : stamp_less(p, a, b, sta);
 }
@@ -541,7 +557,7 @@ __device__ bool offroad_before(const Params& p, int a, int b, int tick) {
 // the one bbtree-set keeps (core.scm:173-178).
 __device__ int later_processed(const Params& p, int x, int y, int32_t lane, const double* pos_old, int tick) {
   const uint32_t sx = p.sa[x].st, sy = p.sa[y].st;
-  const int32_t mx = (sx & ST_MOVED) ? p.mv_old[x] : lane, my = (sy & ST_MOVED) ? p.mv_old[y] : lane;
+  const int32_t mx = (sx & ST_MOVED) ? p.cold[x].mv_old : lane, my = (sy & ST_MOVED) ? p.cold[y].mv_old : lane;
   const int32_t cx = mx < 0 ? ~mx : mx, cy = my < 0 ? ~my : my;
   if (cx != cy) return cx < cy ? x : y;
   if (mx < 0) return offroad_before(p, x, y, tick) ? y : x;
@@ -578,14 +594,14 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
     auto unlink = [&](int32_t z) {
       const int32_t f = p.sa[z].ahead;
       if (f == UNLINKED) return false;
-      const int32_t b = p.behind[z];
+      const int32_t b = p.cold[z].behind;
       if (b >= 0) p.sa[b].ahead = f; else p.lane_tail[lane] = f;
-      if (f >= 0) p.behind[f] = b;
+      if (f >= 0) p.cold[f].behind = b;
       p.sa[z].ahead = UNLINKED;
       return true;
     };
-    for (int32_t z = outbox; z >= 0; z = p.outbox_next[z]) unlink(z);
-    for (int32_t z = ghosts; z >= 0; z = p.ghost_next[z]) {
+    for (int32_t z = outbox; z >= 0; z = p.cold[z].outbox_next) unlink(z);
+    for (int32_t z = ghosts; z >= 0; z = p.cold[z].ghost_next) {
       const uint32_t sz = p.sa[z].st;
       if (unlink(z) && !(sz & ST_MOVED)) {   // one that also moved is finalised by k_settle
         p.sa[z].st = sz & ~ST_ALIVE;
@@ -600,8 +616,8 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
     auto next_entrant = [&](bool first) {
       int32_t best = -1;
       double best_pos = 0.0;
-      for (int32_t y = inbox; y >= 0; y = p.inbox_next[y]) {
-        if (p.dead_mark[y] == tick + 1) continue;   // a ghost's move is void
+      for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
+        if (p.cold[y].dead_mark == tick + 1) continue;   // a ghost's move is void
         const double py = pos_new[y];
         if (!first && !(py > e_pos || (py == e_pos && y > e))) continue;
         if (best < 0 || py < best_pos || (py == best_pos && y < best)) { best = y; best_pos = py; }
@@ -611,16 +627,16 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
     };
     auto next_of = [&](int32_t z) {
       const SA sz = p.sa[z];
-      return (sz.st & ST_MOVED) ? p.ahead_new[z] : sz.ahead;
+      return (sz.st & ST_MOVED) ? p.cold[z].ahead_new : sz.ahead;
     };
     auto link = [&](int32_t b, int32_t z, int32_t f) {   // b -> z -> f, z an entrant
       if (b < 0) p.lane_tail[lane] = z;
-      else if (p.sa[b].st & ST_MOVED) p.ahead_new[b] = z;
+      else if (p.sa[b].st & ST_MOVED) p.cold[b].ahead_new = z;
       else p.sa[b].ahead = z;
-      p.ahead_new[z] = f;
-      p.behind_new[z] = b;
+      p.cold[z].ahead_new = f;
+      p.cold[z].behind_new = b;
       if (f >= 0) {
-        if (p.sa[f].st & ST_MOVED) p.behind_new[f] = z; else p.behind[f] = z;
+        if (p.sa[f].st & ST_MOVED) p.cold[f].behind_new = z; else p.cold[f].behind = z;
       }
     };
     int32_t prev = -1, x = p.lane_tail[lane];
@@ -650,18 +666,18 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
     const int a = p.slow[i];
     const uint32_t st = p.sa[a].st;
     if (!(st & ST_MOVED)) continue;
-    const int32_t old = p.mv_old[a];
+    const int32_t old = p.cold[a].mv_old;
     // an immigrant's old lane belongs to the rank it came from, which does this bookkeeping itself
     if (!(st & ST_IMMIG) && old >= 0 && p.kind[old] == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[p.lane_junction[old]], 1);
-    if (p.dead_mark[a] == tick + 1 || (st & ST_EMIG)) {
+    if (p.cold[a].dead_mark == tick + 1 || (st & ST_EMIG)) {
       // it was a ghost when it moved (the move is void), or it lives on another rank from now on
       p.sa[a].st = st & ~(ST_MOVED | ST_ALIVE | ST_EMIG);
       continue;
     }
     if ((st & ST_ALIVE) && (st & ST_ONROAD)) {
-      p.sa[a].ahead = p.ahead_new[a];
-      p.behind[a] = p.behind_new[a];
-      const int32_t lane = p.container[a];
+      p.sa[a].ahead = p.cold[a].ahead_new;
+      p.cold[a].behind = p.cold[a].behind_new;
+      const int32_t lane = p.cold[a].container;
       if (p.kind[lane] == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[p.lane_junction[lane]], 1);
     }
     p.sa[a].st = st & ~(ST_MOVED | ST_IMMIG);
@@ -719,8 +735,8 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
   const int32_t n = p.counters[CNT_STRIDE * par + CNT_EMIG];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int a = p.emig[i];
-    if (p.dead_mark[a] == tick + 1) continue;   // a ghost's move is void
-    const int32_t lane = p.container[a];
+    if (p.cold[a].dead_mark == tick + 1) continue;   // a ghost's move is void
+    const int32_t lane = p.cold[a].container;
     const int32_t to = p.owner[lane];
     uint8_t* buf = p.mig_send[to];
     const int32_t at = atomicAdd((int32_t*)buf, 1);
@@ -730,21 +746,21 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     r.pos_new = p.pos[par ^ 1][a];
     r.delta = p.delta[a];
     r.buf = p.buf[a];
-    r.arrive = p.arrive[a];
-    r.land_pos = p.land_pos[a];
-    r.speed = p.speed[a];
-    r.speed_dt = p.speed_dt[a];
-    r.gid = p.gid[a];
+    r.arrive = p.coldf[a].arrive;
+    r.land_pos = p.coldf[a].land_pos;
+    r.speed = p.coldf[a].speed;
+    r.speed_dt = p.coldf[a].speed_dt;
+    r.gid = p.cold[a].gid;
     r.st = (int32_t)((p.sa[a].st & ~ST_EMIG) | ST_IMMIG);
     r.container = lane;
-    r.mv_old = p.mv_old[a];
+    r.mv_old = p.cold[a].mv_old;
     r.aux = p.aux[a];
     r.tj = p.tj[a];
-    const int32_t beg = p.agenda_beg[a], end = p.agenda_end[a];
-    r.popped = p.agenda_cur[a] - beg;
+    const int32_t beg = p.cold[a].agenda_beg, end = p.cold[a].agenda_end;
+    r.popped = p.cold[a].agenda_cur - beg;
     r.n_items = end - beg;
-    r.land_tick = p.land_tick[a];
-    r.land_lane = p.land_lane[a];
+    r.land_tick = p.cold[a].land_tick;
+    r.land_lane = p.cold[a].land_lane;
     if (r.n_items > MIG_ITEMS) { dev_error(p, DEV_ERR_MIG_AGENDA); r.n_items = MIG_ITEMS; }
     for (int k = 0; k < MIG_ITEMS; ++k) {
       const bool in = k < r.n_items;
@@ -768,11 +784,11 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     const int32_t a = atomicAdd(&p.scal[SC_NSLOTS], 1);
     const int32_t it = atomicAdd(&p.scal[SC_NITEMS], r.n_items);
     if (a >= p.cap || it + r.n_items > p.icap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
-    p.speed[a] = r.speed;
-    p.speed_dt[a] = r.speed_dt;
-    p.gid[a] = r.gid;
-    p.agenda_beg[a] = it;
-    p.agenda_end[a] = it + r.n_items;
+    p.coldf[a].speed = r.speed;
+    p.coldf[a].speed_dt = r.speed_dt;
+    p.cold[a].gid = r.gid;
+    p.cold[a].agenda_beg = it;
+    p.cold[a].agenda_end = it + r.n_items;
     for (int k = 0; k < r.n_items; ++k) {
       p.item_kind[it + k] = r.item_kind[k];
       p.item_side[it + k] = r.item_side[k];
@@ -781,24 +797,24 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
       p.item_pos[it + k] = r.item_pos[k];
     }
     p.sa[a] = SA{(uint32_t)r.st, -1};
-    p.behind[a] = -1;
+    p.cold[a].behind = -1;
     p.pos[par][a] = r.pos_old;       // processing order among a lane's entrants looks at old lane and old key
     p.pos[par ^ 1][a] = r.pos_new;
     p.delta[a] = r.delta;
     p.buf[a] = r.buf;
-    p.arrive[a] = r.arrive;
-    p.land_pos[a] = r.land_pos;
-    p.container[a] = r.container;
-    p.mv_old[a] = r.mv_old;
+    p.coldf[a].arrive = r.arrive;
+    p.coldf[a].land_pos = r.land_pos;
+    p.cold[a].container = r.container;
+    p.cold[a].mv_old = r.mv_old;
     p.aux[a] = r.aux;
     p.tj[a] = r.tj;
-    p.agenda_cur[a] = it + r.popped;
-    p.route_cur[a] = 0;
-    p.land_tick[a] = r.land_tick;
-    p.land_lane[a] = r.land_lane;
-    p.dead_mark[a] = 0;
+    p.cold[a].agenda_cur = it + r.popped;
+    p.cold[a].route_cur = 0;
+    p.cold[a].land_tick = r.land_tick;
+    p.cold[a].land_lane = r.land_lane;
+    p.cold[a].dead_mark = 0;
     // onto the lane's inbox; k_settle finds it through the deferred list
-    p.inbox_next[a] = atomicExch(&p.inbox_head[r.container], a);
+    p.cold[a].inbox_next = atomicExch(&p.inbox_head[r.container], a);
     if (atomicExch(&p.lane_mark[r.container], tick + 1) != tick + 1)
       p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_TOUCHED], 1)] = r.container;
     p.slow[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_SLOW], 1)] = a;
@@ -810,16 +826,19 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
 // per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
 
 // Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
-constexpr int PERM4 = 11, PERM8 = 8;
-enum { P4_CONTAINER, P4_AUX, P4_AGENDA_CUR, P4_ROUTE_CUR, P4_GID, P4_LAND_TICK, P4_LAND_LANE, P4_TJ, P4_AGENDA_BEG,
-       P4_AGENDA_END, P4_BEHIND };
-enum { P8_SA, P8_POS, P8_DELTA, P8_BUF, P8_ARRIVE, P8_LAND_POS, P8_SPEED, P8_SPEED_DT };
+constexpr int PERM4 = 2, PERM8 = 4;
+enum { P4_AUX, P4_TJ };
+enum { P8_SA, P8_POS, P8_DELTA, P8_BUF };
 
 struct Permute {
   const uint32_t* src4[PERM4];
   uint32_t* dst4[PERM4];
   const uint64_t* src8[PERM8];
   uint64_t* dst8[PERM8];
+  const Cold* src_cold;
+  Cold* dst_cold;
+  const ColdF* src_coldf;
+  ColdF* dst_coldf;
 };
 
 // grid = n_pad / 256 exactly: every lane of every warp reaches the ballot
@@ -833,7 +852,7 @@ __global__ void __launch_bounds__(256) k_make_keys(Params p, int par, int key_bi
     const uint32_t st = p.sa[s].st;
     if (st & ST_ALIVE) {
       live = true;
-      const int32_t c = p.container[s];
+      const int32_t c = p.cold[s].container;
       const double x = p.pos[par][s];
       // 16 bits of pos-param over [-0.5, 1.5): enough to keep a lane's actors in list order
       const double q = fmin(fmax((x + 0.5) * 32768.0, 0.0), 65535.0);
@@ -866,18 +885,16 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
   SA sa = ((const SA*)q.src8[P8_SA])[old];
   const bool on_road = sa.st & ST_ONROAD;
 #pragma unroll
-  for (int k = 0; k < PERM4; ++k) {
-    uint32_t v = q.src4[k][old];
-    if (k == P4_BEHIND) {
-      if (on_road && (int32_t)v >= 0) {
-        v = (uint32_t)newslot[v];
-        if ((int32_t)v < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's follower must be live
-      } else {
-        v = 0xffffffffu;
-      }
-    }
-    q.dst4[k][s] = v;
+  for (int k = 0; k < PERM4; ++k) q.dst4[k][s] = q.src4[k][old];
+  Cold cold = q.src_cold[old];
+  if (on_road && cold.behind >= 0) {
+    cold.behind = newslot[cold.behind];
+    if (cold.behind < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's follower must be live
+  } else {
+    cold.behind = -1;
   }
+  q.dst_cold[s] = cold;
+  q.dst_coldf[s] = q.src_coldf[old];
 #pragma unroll
   for (int k = 0; k < PERM8; ++k) {
     if (k == P8_SA) {
@@ -892,7 +909,7 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
       q.dst8[k][s] = q.src8[k][old];
     }
   }
-  if (tailflag[old]) p.lane_tail[q.src4[P4_CONTAINER][old]] = s;
+  if (tailflag[old]) p.lane_tail[cold.container] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -928,16 +945,16 @@ __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uin
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= p.scal[SC_NSLOTS]) return;
   const uint32_t st = p.sa[a].st;
-  const int32_t id = o.by_slot ? a : p.gid[a];
+  const int32_t id = o.by_slot ? a : p.cold[a].gid;
   const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
   const int32_t aux = p.aux[a];
-  if (o.gid) o.gid[id] = p.gid[a];
+  if (o.gid) o.gid[id] = p.cold[a].gid;
   if (o.alive) o.alive[id] = ((st & ST_ALIVE) && !ghost[a]) ? 1 : 0;
   if (o.loc_kind) o.loc_kind[id] = (st & ST_ONROAD) ? 1 : 0;
-  if (o.container) o.container[id] = p.container[a];
+  if (o.container) o.container[id] = p.cold[a].container;
   if (o.side) o.side[id] = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? 1 : 0;
   if (o.pos) o.pos[id] = p.pos[par][a];
-  if (o.agenda_cur) o.agenda_cur[id] = p.agenda_cur[a] - p.agenda_beg[a];
+  if (o.agenda_cur) o.agenda_cur[id] = p.cold[a].agenda_cur - p.cold[a].agenda_beg;
   if (o.sleep_left) o.sleep_left[id] = head == HEAD_SLEEP ? aux : 0;
   if (o.route_status) o.route_status[id] = (uint8_t)rs;
   if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? aux : -2;
@@ -993,6 +1010,8 @@ struct Ctx {
   int loc_key_bits = 1;
   uint32_t *alt4[PERM4] = {}, *cur4[PERM4] = {};   // double buffers of the permuted arrays
   uint64_t *alt8[PERM8] = {}, *cur8[PERM8] = {};
+  Cold *cold_cur = nullptr, *cold_alt = nullptr;
+  ColdF *coldf_cur = nullptr, *coldf_alt = nullptr;
   uint64_t* sort_keys = nullptr;
   uint32_t* sort_vals = nullptr;
   rsort::Scratch sort_scratch;
@@ -1061,24 +1080,13 @@ int bits_for(uint32_t max_value) {   // bits that hold 0..max_value with all-one
 void bind_slot_arrays(Ctx* c, int par) {
   Params& p = c->p;
   p.sa = (SA*)c->cur8[P8_SA];
-  p.container = (int32_t*)c->cur4[P4_CONTAINER];
-  p.tj = (int32_t*)c->cur4[P4_TJ];
   p.aux = (int32_t*)c->cur4[P4_AUX];
-  p.agenda_cur = (int32_t*)c->cur4[P4_AGENDA_CUR];
-  p.route_cur = (int32_t*)c->cur4[P4_ROUTE_CUR];
-  p.gid = (int32_t*)c->cur4[P4_GID];
-  p.agenda_beg = (int32_t*)c->cur4[P4_AGENDA_BEG];
-  p.agenda_end = (int32_t*)c->cur4[P4_AGENDA_END];
-  p.behind = (int32_t*)c->cur4[P4_BEHIND];
-  p.speed = (double*)c->cur8[P8_SPEED];
-  p.speed_dt = (double*)c->cur8[P8_SPEED_DT];
-  p.land_tick = (int32_t*)c->cur4[P4_LAND_TICK];
-  p.land_lane = (int32_t*)c->cur4[P4_LAND_LANE];
+  p.tj = (int32_t*)c->cur4[P4_TJ];
   p.pos[par] = (double*)c->cur8[P8_POS];
   p.delta = (double*)c->cur8[P8_DELTA];
   p.buf = (double*)c->cur8[P8_BUF];
-  p.arrive = (double*)c->cur8[P8_ARRIVE];
-  p.land_pos = (double*)c->cur8[P8_LAND_POS];
+  p.cold = c->cold_cur;
+  p.coldf = c->coldf_cur;
 }
 
 // Enqueue a reorder of the slots on the context's stream.  Runs between ticks: no actor is marked
@@ -1101,11 +1109,15 @@ int reorder_slots(Ctx* c, int64_t tick) {
   Permute q;
   for (int k = 0; k < PERM4; ++k) { q.src4[k] = c->cur4[k]; q.dst4[k] = c->alt4[k]; }
   for (int k = 0; k < PERM8; ++k) { q.src8[k] = c->cur8[k]; q.dst8[k] = c->alt8[k]; }
+  q.src_cold = c->cold_cur; q.dst_cold = c->cold_alt;
+  q.src_coldf = c->coldf_cur; q.dst_coldf = c->coldf_alt;
   k_permute<<<n_pad / 256, 256, 0, s>>>(p, q, c->sort_vals, c->newslot, c->tailflag);
   c->launches += 2;
   CUDA_TRY(c, cudaMemcpyAsync(&p.scal[SC_NSLOTS], &p.scal[SC_NALIVE], sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
   for (int k = 0; k < PERM4; ++k) std::swap(c->cur4[k], c->alt4[k]);
   for (int k = 0; k < PERM8; ++k) std::swap(c->cur8[k], c->alt8[k]);
+  std::swap(c->cold_cur, c->cold_alt);
+  std::swap(c->coldf_cur, c->coldf_alt);
   bind_slot_arrays(c, par);
   c->last_reorder_tick = tick;
   CUDA_TRY(c, cudaGetLastError());
@@ -1426,12 +1438,22 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
 
   // Initial world: link! every actor in id order (core.scm:169-178).  Slot = id until the first reorder.
   std::vector<SA> sa(n);
-  std::vector<int32_t> aux(n, 0), acur(n), ident(n), behind(n, -1);
+  std::vector<int32_t> aux(n, 0);
+  std::vector<Cold> cold(n);
+  std::vector<ColdF> coldf(n);
   std::vector<int32_t> lane_tail(p.n_items, -1), occ(p.n_items, 0);
   std::vector<int32_t> on_road;
   for (int64_t a = 0; a < n; ++a) {
     uint32_t s = ST_ALIVE;
-    acur[a] = (int32_t)agenda_off[a];
+    Cold& k = cold[a];
+    memset(&k, 0, sizeof(k));
+    k.container = container[a];
+    k.agenda_cur = k.agenda_beg = (int32_t)agenda_off[a];
+    k.agenda_end = (int32_t)agenda_off[a + 1];
+    k.gid = (int32_t)a;         // global id = upload index until griddy_mg_set_global_ids
+    k.land_lane = (int32_t)a;   // landing stamp of the initial placement: tick 0, link! order
+    k.behind = -1;
+    coldf[a] = ColdF{0.0, 0.0, speed[a], speed_dt[a]};
     if (agenda_off[a] < agenda_off[a + 1]) {
       if (item_kind[agenda_off[a]] == GRIDDY_SLEEP_FOR) { s |= HEAD_SLEEP << ST_HEAD_SHIFT; aux[a] = item_sleep[agenda_off[a]]; }
       else s |= HEAD_TRAVEL << ST_HEAD_SHIFT;
@@ -1439,7 +1461,6 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     if (loc_kind[a]) { s |= ST_ONROAD; on_road.push_back((int32_t)a); }
     else if (side[a]) s |= ST_SIDE;
     sa[a] = SA{s, -1};
-    ident[a] = (int32_t)a;   // also the landing stamp of the initial placement: tick 0, link! order
   }
   // lanes: ascending pos-param; an equal key replaces the earlier actor (bbtree-set)
   std::sort(on_road.begin(), on_road.end(), [&](int32_t x, int32_t y) {
@@ -1453,7 +1474,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     const bool replaced = k + 1 < on_road.size() && container[on_road[k + 1]] == container[a] && pos[on_road[k + 1]] == pos[a];
     if (replaced) { sa[a].st &= ~ST_ALIVE; continue; }
     const int32_t lane = container[a];
-    if (prev >= 0 && container[prev] == lane) { sa[prev].ahead = a; behind[a] = prev; } else lane_tail[lane] = a;
+    if (prev >= 0 && container[prev] == lane) { sa[prev].ahead = a; cold[a].behind = prev; } else lane_tail[lane] = a;
     if (c->h_kind[lane] == GRIDDY_JUNCTION_LANE) ++occ[c->h_lane_junction[lane]];
     prev = a;
   }
@@ -1469,44 +1490,31 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     TRY(dev_alloc(c, pool, &c->alt8[k], cap));
     CUDA_TRY(c, cudaMemset(c->cur8[k], 0, (size_t)cap * sizeof(uint64_t)));
   }
-  auto put4 = [&](int k, const void* host) { return n ? cudaMemcpy(c->cur4[k], host, (size_t)n * 4, cudaMemcpyHostToDevice) : cudaSuccess; };
-  if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SA], sa.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
-  CUDA_TRY(c, put4(P4_CONTAINER, container));
-  CUDA_TRY(c, put4(P4_BEHIND, behind.data()));
-  CUDA_TRY(c, cudaMemset(c->cur4[P4_TJ], 0xFF, (size_t)cap * sizeof(int32_t)));
-  CUDA_TRY(c, put4(P4_AUX, aux.data()));
-  CUDA_TRY(c, put4(P4_AGENDA_CUR, acur.data()));
-  CUDA_TRY(c, put4(P4_GID, ident.data()));     // global id = upload index until griddy_mg_set_global_ids
-  CUDA_TRY(c, put4(P4_LAND_LANE, ident.data()));
-  if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_POS], pos, (size_t)n * 8, cudaMemcpyHostToDevice));
-  if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SPEED], speed, (size_t)n * 8, cudaMemcpyHostToDevice));
-  if (n) CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SPEED_DT], speed_dt, (size_t)n * 8, cudaMemcpyHostToDevice));
-  {
-    std::vector<int32_t> beg(n), end(n);
-    for (int64_t a = 0; a < n; ++a) { beg[a] = (int32_t)agenda_off[a]; end[a] = (int32_t)agenda_off[a + 1]; }
-    CUDA_TRY(c, put4(P4_AGENDA_BEG, beg.data()));
-    CUDA_TRY(c, put4(P4_AGENDA_END, end.data()));
+  TRY(dev_alloc(c, pool, &c->cold_cur, cap));
+  TRY(dev_alloc(c, pool, &c->cold_alt, cap));
+  TRY(dev_alloc(c, pool, &c->coldf_cur, cap));
+  TRY(dev_alloc(c, pool, &c->coldf_alt, cap));
+  CUDA_TRY(c, cudaMemset(c->cold_cur, 0, (size_t)cap * sizeof(Cold)));
+  CUDA_TRY(c, cudaMemset(c->coldf_cur, 0, (size_t)cap * sizeof(ColdF)));
+  if (n) {
+    CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SA], sa.data(), (size_t)n * sizeof(SA), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->cur8[P8_POS], pos, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->cur4[P4_AUX], aux.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->cold_cur, cold.data(), (size_t)n * sizeof(Cold), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->coldf_cur, coldf.data(), (size_t)n * sizeof(ColdF), cudaMemcpyHostToDevice));
   }
+  CUDA_TRY(c, cudaMemset(c->cur4[P4_TJ], 0xFF, (size_t)cap * sizeof(int32_t)));
   double* pos1 = nullptr;
   TRY(dev_alloc(c, pool, &pos1, cap));
   if (n) CUDA_TRY(c, cudaMemcpy(pos1, pos, (size_t)n * 8, cudaMemcpyHostToDevice));
   p.pos[1] = pos1;
   bind_slot_arrays(c, 0);
 
-  TRY(dev_alloc(c, pool, &p.mv_old, cap));
-  TRY(dev_alloc(c, pool, &p.ahead_new, cap));
-  TRY(dev_alloc(c, pool, &p.inbox_next, cap));
-  TRY(dev_alloc(c, pool, &p.behind_new, cap));
-  TRY(dev_alloc(c, pool, &p.outbox_next, cap));
-  TRY(dev_alloc(c, pool, &p.ghost_next, cap));
-  TRY(dev_alloc(c, pool, &p.dead_mark, cap));
   TRY(dev_alloc(c, pool, &p.touched, 2 * cap));
   TRY(dev_alloc(c, pool, &p.slow, cap));
   TRY(dev_alloc(c, pool, &p.emig, cap));
   TRY(dev_alloc(c, pool, &p.counters, 2 * CNT_STRIDE));
   TRY(dev_alloc(c, pool, &p.scal, SC_COUNT));
-  for (void* z : {(void*)p.mv_old, (void*)p.ahead_new, (void*)p.inbox_next, (void*)p.dead_mark})
-    CUDA_TRY(c, cudaMemset(z, 0, (size_t)cap * sizeof(int32_t)));
   CUDA_TRY(c, cudaMemset(p.counters, 0, 2 * CNT_STRIDE * sizeof(int32_t)));
   {
     int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n_agenda};
@@ -1863,12 +1871,15 @@ int download_state(Ctx* c, bool by_slot, int32_t* gid, uint8_t* alive, uint8_t* 
     CUDA_TRY(c, pull(sa.data(), p.sa, ns * sizeof(SA)));
     for (int32_t a = 0; a < ns; ++a) st[a] = sa[a].st;
     CUDA_TRY(c, pull(ghost.data(), c->d_ghost, ns));
-    CUDA_TRY(c, pull(cont.data(), p.container, ns * sizeof(int32_t)));
-    CUDA_TRY(c, pull(ident.data(), p.gid, ns * sizeof(int32_t)));
+    std::vector<Cold> cold(ns);
+    std::vector<ColdF> coldf(ns);
+    CUDA_TRY(c, pull(cold.data(), p.cold, ns * sizeof(Cold)));
+    CUDA_TRY(c, pull(coldf.data(), p.coldf, ns * sizeof(ColdF)));
+    for (int32_t a = 0; a < ns; ++a) {
+      cont[a] = cold[a].container; ident[a] = cold[a].gid;
+      land_tick[a] = cold[a].land_tick; land_lane[a] = cold[a].land_lane; land_pos[a] = coldf[a].land_pos;
+    }
     CUDA_TRY(c, pull(ps.data(), p.pos[tick & 1], ns * sizeof(double)));
-    CUDA_TRY(c, pull(land_tick.data(), p.land_tick, ns * sizeof(int32_t)));
-    CUDA_TRY(c, pull(land_lane.data(), p.land_lane, ns * sizeof(int32_t)));
-    CUDA_TRY(c, pull(land_pos.data(), p.land_pos, ns * sizeof(double)));
     std::vector<int32_t> ord;
     ord.reserve(ns);
     for (int32_t a = 0; a < ns; ++a)
@@ -1941,7 +1952,9 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
   if (ns) {
     CUDA_TRY(c, cudaMemcpy(sa.data(), p.sa, ns * sizeof(SA), cudaMemcpyDeviceToHost));
     for (int32_t a = 0; a < ns; ++a) { st[a] = sa[a].st; ahead[a] = sa[a].ahead; }
-    CUDA_TRY(c, cudaMemcpy(cont.data(), p.container, ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<Cold> cold(ns);
+    CUDA_TRY(c, cudaMemcpy(cold.data(), p.cold, ns * sizeof(Cold), cudaMemcpyDeviceToHost));
+    for (int32_t a = 0; a < ns; ++a) cont[a] = cold[a].container;
     CUDA_TRY(c, cudaMemcpy(ps.data(), p.pos[c->tick & 1], ns * sizeof(double), cudaMemcpyDeviceToHost));
   }
   // ghost rule: an on-road actor whose list follower holds an equal key is not part of the world
@@ -2068,15 +2081,15 @@ int griddy_mg_set_global_ids(void* ctx, const int32_t* gid) {
   for (int64_t a = 1; a < c->p.n_actors; ++a)
     if (gid[a] <= gid[a - 1]) return fail(c, GRIDDY_ERR_BAD_ARG, "global ids must ascend: they carry the order of the link! calls");
   // right after upload_actors the initial reorder has already permuted the slots: map through the
-  // upload indices that p.gid still holds
+  // upload indices that Cold::gid still holds
   const int32_t ns = c->ns_host;
-  std::vector<int32_t> cur(ns);
-  if (ns) CUDA_TRY(c, cudaMemcpy(cur.data(), c->p.gid, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  std::vector<Cold> cur(ns);
+  if (ns) CUDA_TRY(c, cudaMemcpy(cur.data(), c->p.cold, (size_t)ns * sizeof(Cold), cudaMemcpyDeviceToHost));
   for (int32_t s = 0; s < ns; ++s) {
-    if (cur[s] < 0 || cur[s] >= c->p.n_actors) return fail(c, GRIDDY_ERR_BAD_STATE, "mg_set_global_ids must directly follow upload_actors");
-    cur[s] = gid[cur[s]];
+    if (cur[s].gid < 0 || cur[s].gid >= c->p.n_actors) return fail(c, GRIDDY_ERR_BAD_STATE, "mg_set_global_ids must directly follow upload_actors");
+    cur[s].gid = gid[cur[s].gid];
   }
-  if (ns) CUDA_TRY(c, cudaMemcpy(c->p.gid, cur.data(), (size_t)ns * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (ns) CUDA_TRY(c, cudaMemcpy(c->p.cold, cur.data(), (size_t)ns * sizeof(Cold), cudaMemcpyHostToDevice));
   return GRIDDY_OK;
 }
 
