@@ -130,18 +130,34 @@ struct __align__(16) ColdF {
 };
 static_assert(sizeof(Cold) == 64 && sizeof(ColdF) == 32, "cold records are one / half a DRAM burst");
 
+// The static network, one 32-byte record per registered item: a lane change reads its target lane's
+// kind, length, successor and junctions from one sector.
+struct __align__(16) Item {
+  double len;             // lanes: length (host-computed, spatial.scm:28-46)
+  int32_t link;           // segment lane: its segment; junction lane: the lane it leads onto; segment: outer forw-side lane
+  int32_t link2;          // junction lane: its junction; segment: outer back-side lane
+  int32_t from_j, to_j;   // grid routing: junction a segment lane leaves / reaches
+  uint32_t loc_key;       // locality key for the reorder (default: the registration index)
+  uint8_t kind, dir;
+  uint16_t pad;
+};
+// Per-lane list heads: rearmost actor, and this tick's entrants, leavers and ghosts.
+struct __align__(16) LaneDyn {
+  int32_t tail;      // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
+  int32_t inbox, outbox, ghosts;
+  int32_t mark;      // tick+1 once the lane is on this tick's touched list
+  int32_t pad[3];
+};
+static_assert(sizeof(Item) == 32 && sizeof(LaneDyn) == 32, "one sector per record");
+
 struct Params {
   // network, by registration index
   int64_t n_items;
-  const uint8_t* kind;
-  const double* lane_len;
-  const uint8_t* lane_dir;
-  const int32_t *lane_segment, *lane_out, *lane_junction, *outer_forw, *outer_back;
-  const uint32_t* loc_key;   // locality key for the reorder (default: the registration index)
+  Item* item;
+  LaneDyn* lane;
+  int32_t* occ;       // actors on a junction's lanes (route.scm:98-104); compact, so that it lives in L2
   int32_t grid_n;
-  const int32_t *lane_from_j, *lane_to_j, *turn4;
-  int32_t *lane_tail, *occ, *lane_mark;
-  int32_t *inbox_head, *outbox_head, *ghost_head;   // per lane, this tick: entrants, leavers, ghosts found
+  const int32_t* turn4;
   // slots
   int32_t cap;     // allocated slots
   int32_t* scal;   // SC_*: device error bits, slots in use, live actors counted by the reorder
@@ -179,16 +195,16 @@ __device__ __forceinline__ void dev_error(const Params& p, int bit) { atomicOr(&
 
 // location.scm:16-24 through the uploaded per-segment table
 __device__ __forceinline__ int32_t outer_lane(const Params& p, int32_t seg, uint32_t side) {
-  return side ? p.outer_back[seg] : p.outer_forw[seg];
+  return side ? p.item[seg].link2 : p.item[seg].link;
 }
 
 // Dimension-ordered next hop on procedural grids (include/griddy_cuda.h, griddy_set_routing_grid).
 __device__ int32_t grid_next_hop(const Params& p, int32_t lane, int32_t dest) {
   const int n = p.grid_n;
-  const int32_t J = p.lane_to_j[lane], E = p.lane_from_j[dest];
+  const int32_t J = p.item[lane].to_j, E = p.item[dest].from_j;
   int h;
   if (J == E) {
-    const int32_t T = p.lane_to_j[dest];
+    const int32_t T = p.item[dest].to_j;
     h = (T / n != E / n) ? (T / n > E / n ? 0 : 1) : (T % n > E % n ? 2 : 3);
   } else if (J / n != E / n) {
     h = E / n > J / n ? 0 : 1;
@@ -206,7 +222,7 @@ __device__ int32_t route_head_on(const Params& p, int32_t lane, int32_t item, in
   }
   const int32_t dest = outer_lane(p, p.item_seg[item], p.item_side[item]);
   if (lane == dest) return HOP_ARRIVE;
-  if (p.kind[lane] == GRIDDY_JUNCTION_LANE) return p.lane_out[lane];
+  if (p.item[lane].kind == GRIDDY_JUNCTION_LANE) return p.item[lane].link;
   const int32_t hop = grid_next_hop(p, lane, dest);
   if (hop < 0) dev_error(p, DEV_ERR_NO_ROUTE);
   return hop;
@@ -214,7 +230,7 @@ __device__ int32_t route_head_on(const Params& p, int32_t lane, int32_t item, in
 
 // The junction whose occupancy gates a (turn-onto lane) head (route.scm:105-108), or -1.
 __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop) {
-  return (hop >= 0 && p.kind[hop] == GRIDDY_JUNCTION_LANE) ? p.lane_junction[hop] : -1;
+  return (hop >= 0 && p.item[hop].kind == GRIDDY_JUNCTION_LANE) ? p.item[hop].link2 : -1;
 }
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
@@ -235,16 +251,16 @@ constexpr int SLOW_THREADS = 128;
 constexpr int SINK_CAP = 3 * SLOW_THREADS;   // an actor touches at most its old lane, its new lane and a ghost's lane
 
 __device__ __forceinline__ void mark_touched(const Params& p, int32_t lane, int tick, const TouchSink& sink) {
-  if (atomicExch(&p.lane_mark[lane], tick + 1) != tick + 1) sink.list[atomicAdd(sink.count, 1)] = lane;
+  if (atomicExch(&p.lane[lane].mark, tick + 1) != tick + 1) sink.list[atomicAdd(sink.count, 1)] = lane;
 }
 
 __device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
-  p.cold[a].inbox_next = atomicExch(&p.inbox_head[lane], a);
+  p.cold[a].inbox_next = atomicExch(&p.lane[lane].inbox, a);
   mark_touched(p, lane, tick, sink);
 }
 
 __device__ __forceinline__ void leave_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
-  p.cold[a].outbox_next = atomicExch(&p.outbox_head[lane], a);
+  p.cold[a].outbox_next = atomicExch(&p.lane[lane].outbox, a);
   mark_touched(p, lane, tick, sink);
 }
 
@@ -265,7 +281,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const int32_t lane = p.cold[a].container;
     do {
       if (atomicExch(&p.cold[ah].dead_mark, tick + 1) != tick + 1)   // the first to notice hands it to k_relink
-        p.cold[ah].ghost_next = atomicExch(&p.ghost_head[lane], ah);
+        p.cold[ah].ghost_next = atomicExch(&p.lane[lane].ghosts, ah);
       ah = p.sa[ah].ahead;
       if (ah >= 0) lead = pos_old[ah];
     } while (ah >= 0 && lead == cur);
@@ -299,11 +315,11 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const double speed = p.coldf[a].speed;
     const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), speed);
     const double time_remaining = __dsub_rn(p.dt, time_spent);
-    const double tlen = p.lane_len[target];
+    const double tlen = p.item[target].len;
     const double tinv = __ddiv_rn(1.0, tlen);
     const double tbuf = __ddiv_rn(p.two_size, tlen);
     double tnext = __dmul_rn(__dmul_rn(speed, time_remaining), tinv);   // (+ 0 delta)
-    int32_t x = p.lane_tail[target];
+    int32_t x = p.lane[target].tail;
     const bool remote = x <= -2;   // multi-GPU: another rank owns the target lane
     if (remote) {                  // its smallest key in (0, ...] came with the halo (+inf: none)
       const double tlead = p.halo_recv[-2 - x];
@@ -359,12 +375,12 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const int32_t dest_lane = outer_lane(p, p.item_seg[item], p.item_side[item]);
     if (init_lane < 0 || dest_lane < 0) { dev_error(p, DEV_ERR_NO_LANE); return cur; }
     // off-road->on-road  location.scm:49-57
-    const double init_pos = p.lane_dir[init_lane] ? __dsub_rn(1.0, cur) : cur;
+    const double init_pos = p.item[init_lane].dir ? __dsub_rn(1.0, cur) : cur;
     const double ipos = p.item_pos[item];
-    const double dest_pos = p.lane_dir[dest_lane] ? __dsub_rn(1.0, ipos) : ipos;
+    const double dest_pos = p.item[dest_lane].dir ? __dsub_rn(1.0, ipos) : ipos;
     int32_t rc = p.route_off ? (int32_t)p.route_off[item] : 0;
     const int32_t hop = route_head_on(p, init_lane, item, &rc);
-    const double len = p.lane_len[init_lane];
+    const double len = p.item[init_lane].len;
     p.cold[a].route_cur = rc;
     p.coldf[a].arrive = dest_pos;
     p.aux[a] = hop;
@@ -381,9 +397,9 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 
   // end-route$  simulate.scm:87-91   (rs == GRIDDY_ROUTE_DONE)
   const int32_t lane = p.cold[a].container;
-  if (p.kind[lane] != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); return cur; }
-  const int32_t seg = p.lane_segment[lane];
-  const uint32_t dir = p.lane_dir[lane];
+  if (p.item[lane].kind != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); return cur; }
+  const int32_t seg = p.item[lane].link;
+  const uint32_t dir = p.item[lane].dir;
   const int32_t ac = item + 1;
   int32_t aux;
   const uint32_t h = load_head(p, a, ac, &aux);
@@ -584,18 +600,18 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
   const double* __restrict__ pos_new = p.pos[par ^ 1];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = p.touched[i];
-    const int32_t inbox = p.inbox_head[lane], outbox = p.outbox_head[lane], ghosts = p.ghost_head[lane];
-    if (inbox >= 0) p.inbox_head[lane] = -1;
-    if (outbox >= 0) p.outbox_head[lane] = -1;
-    if (ghosts >= 0) p.ghost_head[lane] = -1;
-    const bool jl = p.kind[lane] == GRIDDY_JUNCTION_LANE;
+    const int32_t inbox = p.lane[lane].inbox, outbox = p.lane[lane].outbox, ghosts = p.lane[lane].ghosts;
+    if (inbox >= 0) p.lane[lane].inbox = -1;
+    if (outbox >= 0) p.lane[lane].outbox = -1;
+    if (ghosts >= 0) p.lane[lane].ghosts = -1;
+    const bool jl = p.item[lane].kind == GRIDDY_JUNCTION_LANE;
 
     // 1. unlink.  A ghost that also moved is on both lists; the second visit finds it UNLINKED.
     auto unlink = [&](int32_t z) {
       const int32_t f = p.sa[z].ahead;
       if (f == UNLINKED) return false;
       const int32_t b = p.cold[z].behind;
-      if (b >= 0) p.sa[b].ahead = f; else p.lane_tail[lane] = f;
+      if (b >= 0) p.sa[b].ahead = f; else p.lane[lane].tail = f;
       if (f >= 0) p.cold[f].behind = b;
       p.sa[z].ahead = UNLINKED;
       return true;
@@ -605,7 +621,7 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
       const uint32_t sz = p.sa[z].st;
       if (unlink(z) && !(sz & ST_MOVED)) {   // one that also moved is finalised by k_settle
         p.sa[z].st = sz & ~ST_ALIVE;
-        if (jl) atomicSub(&p.occ[p.lane_junction[lane]], 1);
+        if (jl) atomicSub(&p.occ[p.item[lane].link2], 1);
       }
     }
     if (inbox < 0) continue;
@@ -630,7 +646,7 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
       return (sz.st & ST_MOVED) ? p.cold[z].ahead_new : sz.ahead;
     };
     auto link = [&](int32_t b, int32_t z, int32_t f) {   // b -> z -> f, z an entrant
-      if (b < 0) p.lane_tail[lane] = z;
+      if (b < 0) p.lane[lane].tail = z;
       else if (p.sa[b].st & ST_MOVED) p.cold[b].ahead_new = z;
       else p.sa[b].ahead = z;
       p.cold[z].ahead_new = f;
@@ -639,7 +655,7 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
         if (p.sa[f].st & ST_MOVED) p.cold[f].behind_new = z; else p.cold[f].behind = z;
       }
     };
-    int32_t prev = -1, x = p.lane_tail[lane];
+    int32_t prev = -1, x = p.lane[lane].tail;
     for (next_entrant(true); e >= 0; next_entrant(false)) {
       while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = next_of(x); }
       if (x >= 0 && pos_new[x] == e_pos) {   // equal key: bbtree-set keeps the one processed later
@@ -647,7 +663,7 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
         const int32_t lose = e_wins ? x : e;
         const uint32_t sl = p.sa[lose].st;
         p.sa[lose].st = sl & ~ST_ALIVE;
-        if (jl && !(sl & ST_MOVED)) atomicSub(&p.occ[p.lane_junction[lane]], 1);
+        if (jl && !(sl & ST_MOVED)) atomicSub(&p.occ[p.item[lane].link2], 1);
         if (!e_wins) continue;
         link(prev, e, next_of(x));   // e takes x's place
       } else {
@@ -668,7 +684,7 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
     if (!(st & ST_MOVED)) continue;
     const int32_t old = p.cold[a].mv_old;
     // an immigrant's old lane belongs to the rank it came from, which does this bookkeeping itself
-    if (!(st & ST_IMMIG) && old >= 0 && p.kind[old] == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[p.lane_junction[old]], 1);
+    if (!(st & ST_IMMIG) && old >= 0 && p.item[old].kind == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[p.item[old].link2], 1);
     if (p.cold[a].dead_mark == tick + 1 || (st & ST_EMIG)) {
       // it was a ghost when it moved (the move is void), or it lives on another rank from now on
       p.sa[a].st = st & ~(ST_MOVED | ST_ALIVE | ST_EMIG);
@@ -678,10 +694,54 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
       p.sa[a].ahead = p.cold[a].ahead_new;
       p.cold[a].behind = p.cold[a].behind_new;
       const int32_t lane = p.cold[a].container;
-      if (p.kind[lane] == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[p.lane_junction[lane]], 1);
+      if (p.item[lane].kind == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[p.item[lane].link2], 1);
     }
     p.sa[a].st = st & ~(ST_MOVED | ST_IMMIG);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Set-up: the network is assembled on the device from the arrays that cross the ABI (staged through
+// a reusable device buffer), so that no host copy of the 32-byte records is ever made.
+__global__ void __launch_bounds__(256) k_item_build(Item* __restrict__ item, int64_t n, const uint8_t* __restrict__ kind,
+                                                     const double* __restrict__ len, const uint8_t* __restrict__ dir,
+                                                     const int32_t* __restrict__ seg, const int32_t* __restrict__ out,
+                                                     const int32_t* __restrict__ junction, const int32_t* __restrict__ of,
+                                                     const int32_t* __restrict__ ob) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= n) return;
+  Item it;
+  it.kind = kind[r];
+  it.dir = dir[r];
+  it.pad = 0;
+  it.len = len[r];
+  it.link = it.kind == GRIDDY_SEGMENT_LANE ? seg[r] : it.kind == GRIDDY_JUNCTION_LANE ? out[r] : it.kind == GRIDDY_SEGMENT ? of[r] : -1;
+  it.link2 = it.kind == GRIDDY_JUNCTION_LANE ? junction[r] : it.kind == GRIDDY_SEGMENT ? ob[r] : -1;
+  it.from_j = it.to_j = -1;
+  it.loc_key = (uint32_t)r;   // default locality key: the registration index
+  item[r] = it;
+}
+
+__global__ void __launch_bounds__(256) k_item_set_grid(Item* __restrict__ item, int64_t n, const int32_t* __restrict__ from_j,
+                                                        const int32_t* __restrict__ to_j) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r < n) { item[r].from_j = from_j[r]; item[r].to_j = to_j[r]; }
+}
+
+__global__ void __launch_bounds__(256) k_item_set_key(Item* __restrict__ item, int64_t n, const uint32_t* __restrict__ key) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r < n) item[r].loc_key = key[r];
+}
+
+__global__ void __launch_bounds__(256) k_lane_init(LaneDyn* __restrict__ lane, int64_t n) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r < n) lane[r] = LaneDyn{-1, -1, -1, -1, 0, {0, 0, 0}};
+}
+
+__global__ void __launch_bounds__(256) k_lane_set_tail(LaneDyn* __restrict__ lane, const int32_t* __restrict__ which,
+                                                        const int32_t* __restrict__ tail, int64_t m) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < m) lane[which[i]].tail = tail[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -713,7 +773,7 @@ __global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int3
   const int32_t item = items[i];
   if (i >= n_lanes) { out[i] = (double)p.occ[item]; return; }
   const double* __restrict__ pos = p.pos[par];
-  int32_t x = p.lane_tail[item];
+  int32_t x = p.lane[item].tail;
   while (x >= 0 && !(pos[x] > 0.0)) x = p.sa[x].ahead;
   out[i] = x >= 0 ? pos[x] : __longlong_as_double(0x7ff0000000000000LL);
 }
@@ -814,8 +874,8 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     p.cold[a].land_lane = r.land_lane;
     p.cold[a].dead_mark = 0;
     // onto the lane's inbox; k_settle finds it through the deferred list
-    p.cold[a].inbox_next = atomicExch(&p.inbox_head[r.container], a);
-    if (atomicExch(&p.lane_mark[r.container], tick + 1) != tick + 1)
+    p.cold[a].inbox_next = atomicExch(&p.lane[r.container].inbox, a);
+    if (atomicExch(&p.lane[r.container].mark, tick + 1) != tick + 1)
       p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_TOUCHED], 1)] = r.container;
     p.slow[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_SLOW], 1)] = a;
   }
@@ -857,9 +917,9 @@ __global__ void __launch_bounds__(256) k_make_keys(Params p, int par, int key_bi
       // 16 bits of pos-param over [-0.5, 1.5): enough to keep a lane's actors in list order
       const double q = fmin(fmax((x + 0.5) * 32768.0, 0.0), 65535.0);
       // off-road actors after the on-road ones: warps are then all-travelling or all-parked
-      key = ((uint64_t)((st & ST_ONROAD) ? 0u : 1u) << (key_bits - 1)) | ((uint64_t)p.loc_key[c] << 16) | (uint64_t)(uint32_t)q;
+      key = ((uint64_t)((st & ST_ONROAD) ? 0u : 1u) << (key_bits - 1)) | ((uint64_t)p.item[c].loc_key << 16) | (uint64_t)(uint32_t)q;
       val = (uint32_t)s;
-      tailflag[s] = ((st & ST_ONROAD) && p.lane_tail[c] == s) ? 1 : 0;
+      tailflag[s] = ((st & ST_ONROAD) && p.lane[c].tail == s) ? 1 : 0;
     }
   }
   keys[s] = key;
@@ -909,7 +969,7 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
       q.dst8[k][s] = q.src8[k][old];
     }
   }
-  if (tailflag[old]) p.lane_tail[cold.container] = s;
+  if (tailflag[old]) p.lane[cold.container].tail = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1319,27 +1379,31 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   Params& p = c->p;
   p.n_items = n_items;
   p.grid_n = 0;
-  p.lane_from_j = p.lane_to_j = p.turn4 = nullptr;
-  TRY(dev_upload(c, c->net_allocs, &p.kind, kind, n_items));
-  TRY(dev_upload(c, c->net_allocs, &p.lane_len, lane_len, n_items));
-  TRY(dev_upload(c, c->net_allocs, &p.lane_dir, lane_dir, n_items));
-  TRY(dev_upload(c, c->net_allocs, &p.lane_segment, lane_segment, n_items));
-  TRY(dev_upload(c, c->net_allocs, &p.lane_out, lane_out, n_items));
-  TRY(dev_upload(c, c->net_allocs, &p.lane_junction, lane_junction, n_items));
-  TRY(dev_upload(c, c->net_allocs, &p.outer_forw, seg_outer_forw, n_items));
-  TRY(dev_upload(c, c->net_allocs, &p.outer_back, seg_outer_back, n_items));
-  {   // default locality key: the registration index
-    std::vector<uint32_t> key((size_t)n_items);
-    for (int64_t r = 0; r < n_items; ++r) key[r] = (uint32_t)r;
-    TRY(dev_upload(c, c->net_allocs, &p.loc_key, key.data(), n_items));
-    c->loc_key_bits = bits_for((uint32_t)std::max<int64_t>(n_items, 1));
-  }
-  TRY(dev_alloc(c, c->net_allocs, &p.lane_tail, n_items));
+  p.turn4 = nullptr;
+  TRY(dev_alloc(c, c->net_allocs, &p.item, n_items));
+  TRY(dev_alloc(c, c->net_allocs, &p.lane, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.occ, n_items));
-  TRY(dev_alloc(c, c->net_allocs, &p.lane_mark, n_items));
-  TRY(dev_alloc(c, c->net_allocs, &p.inbox_head, n_items));
-  TRY(dev_alloc(c, c->net_allocs, &p.outbox_head, n_items));
-  TRY(dev_alloc(c, c->net_allocs, &p.ghost_head, n_items));
+  if (n_items > 0) {   // stage the ABI arrays on the device, assemble the records there
+    std::vector<void*> tmp;
+    const uint8_t *d_kind, *d_dir;
+    const double* d_len;
+    const int32_t *d_seg, *d_out, *d_jun, *d_of, *d_ob;
+    int rc = dev_upload(c, tmp, &d_kind, kind, n_items);
+    if (!rc) rc = dev_upload(c, tmp, &d_len, lane_len, n_items);
+    if (!rc) rc = dev_upload(c, tmp, &d_dir, lane_dir, n_items);
+    if (!rc) rc = dev_upload(c, tmp, &d_seg, lane_segment, n_items);
+    if (!rc) rc = dev_upload(c, tmp, &d_out, lane_out, n_items);
+    if (!rc) rc = dev_upload(c, tmp, &d_jun, lane_junction, n_items);
+    if (!rc) rc = dev_upload(c, tmp, &d_of, seg_outer_forw, n_items);
+    if (!rc) rc = dev_upload(c, tmp, &d_ob, seg_outer_back, n_items);
+    if (!rc) {
+      k_item_build<<<(unsigned)((n_items + 255) / 256), 256>>>(p.item, n_items, d_kind, d_len, d_dir, d_seg, d_out, d_jun, d_of, d_ob);
+      if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_build failed");
+    }
+    free_pool(tmp);
+    if (rc) return rc;
+  }
+  c->loc_key_bits = bits_for((uint32_t)std::max<int64_t>(n_items, 1));
   c->h_kind.assign(kind, kind + n_items);
   c->h_lane_junction.assign(lane_junction, lane_junction + n_items);
   c->h_lane_out.assign(lane_out, lane_out + n_items);
@@ -1356,7 +1420,17 @@ int griddy_set_locality_keys(void* ctx, const uint32_t* item_key) {
   uint32_t mx = 0;
   for (int64_t r = 0; r < c->p.n_items; ++r) mx = std::max(mx, item_key[r]);
   if (mx == UINT32_MAX) return fail(c, GRIDDY_ERR_BAD_ARG, "locality keys must be below 2^32-1");
-  CUDA_TRY(c, cudaMemcpy((void*)c->p.loc_key, item_key, (size_t)c->p.n_items * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  {
+    std::vector<void*> tmp;
+    const uint32_t* d_key;
+    int rc = dev_upload(c, tmp, &d_key, item_key, c->p.n_items);
+    if (!rc && c->p.n_items > 0) {
+      k_item_set_key<<<(unsigned)((c->p.n_items + 255) / 256), 256>>>(c->p.item, c->p.n_items, d_key);
+      if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_set_key failed");
+    }
+    free_pool(tmp);
+    if (rc) return rc;
+  }
   c->loc_key_bits = bits_for(mx);
   return GRIDDY_OK;
 }
@@ -1370,8 +1444,18 @@ int griddy_set_routing_grid(void* ctx, int32_t n, const int32_t* lane_from_j, co
     return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid: bad arguments");
   CUDA_TRY(c, cudaSetDevice(c->device));
   Params& p = c->p;
-  TRY(dev_upload(c, c->net_allocs, &p.lane_from_j, lane_from_j, p.n_items));
-  TRY(dev_upload(c, c->net_allocs, &p.lane_to_j, lane_to_j, p.n_items));
+  {
+    std::vector<void*> tmp;
+    const int32_t *d_from, *d_to;
+    int rc = dev_upload(c, tmp, &d_from, lane_from_j, p.n_items);
+    if (!rc) rc = dev_upload(c, tmp, &d_to, lane_to_j, p.n_items);
+    if (!rc && p.n_items > 0) {
+      k_item_set_grid<<<(unsigned)((p.n_items + 255) / 256), 256>>>(p.item, p.n_items, d_from, d_to);
+      if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_set_grid failed");
+    }
+    free_pool(tmp);
+    if (rc) return rc;
+  }
   TRY(dev_upload(c, c->net_allocs, &p.turn4, turn4, 4 * p.n_items));
   p.grid_n = n;
   return GRIDDY_OK;
@@ -1441,7 +1525,8 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   std::vector<int32_t> aux(n, 0);
   std::vector<Cold> cold(n);
   std::vector<ColdF> coldf(n);
-  std::vector<int32_t> lane_tail(p.n_items, -1), occ(p.n_items, 0);
+  std::vector<int32_t> occ(p.n_items, 0);
+  std::vector<int32_t> tail_lane, tail_slot;   // the few lanes that start with actors on them, and remote-lane marks
   std::vector<int32_t> on_road;
   for (int64_t a = 0; a < n; ++a) {
     uint32_t s = ST_ALIVE;
@@ -1474,7 +1559,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     const bool replaced = k + 1 < on_road.size() && container[on_road[k + 1]] == container[a] && pos[on_road[k + 1]] == pos[a];
     if (replaced) { sa[a].st &= ~ST_ALIVE; continue; }
     const int32_t lane = container[a];
-    if (prev >= 0 && container[prev] == lane) { sa[prev].ahead = a; cold[a].behind = prev; } else lane_tail[lane] = a;
+    if (prev >= 0 && container[prev] == lane) { sa[prev].ahead = a; cold[a].behind = prev; } else { tail_lane.push_back(lane); tail_slot.push_back(a); }
     if (c->h_kind[lane] == GRIDDY_JUNCTION_LANE) ++occ[c->h_lane_junction[lane]];
     prev = a;
   }
@@ -1556,17 +1641,23 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     p.route_lane = nullptr;
   }
   // per-lane state of the network belongs to this world
-  for (const auto& m : c->mg.import_marks) lane_tail[m.first] = m.second;   // lanes other ranks own
+  for (const auto& m : c->mg.import_marks) { tail_lane.push_back(m.first); tail_slot.push_back(m.second); }   // lanes other ranks own
   if (c->mg.on)
     for (int64_t a = 0; a < n; ++a)
       if (c->mg_owner_host[container[a]] != c->mg.rank)
         return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + " is not on this rank's part of the world");
-  CUDA_TRY(c, cudaMemcpy(p.lane_tail, lane_tail.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (p.n_items > 0) k_lane_init<<<(unsigned)((p.n_items + 255) / 256), 256>>>(p.lane, p.n_items);
+  if (!tail_lane.empty()) {
+    std::vector<void*> tmp;
+    const int32_t *d_which, *d_tail;
+    int rc = dev_upload(c, tmp, &d_which, tail_lane.data(), (int64_t)tail_lane.size());
+    if (!rc) rc = dev_upload(c, tmp, &d_tail, tail_slot.data(), (int64_t)tail_slot.size());
+    if (!rc) k_lane_set_tail<<<(unsigned)((tail_lane.size() + 255) / 256), 256>>>(p.lane, d_which, d_tail, (int64_t)tail_lane.size());
+    if (cudaDeviceSynchronize() != cudaSuccess && !rc) rc = fail(c, GRIDDY_ERR_CUDA, "k_lane_set_tail failed");
+    free_pool(tmp);
+    if (rc) return rc;
+  }
   CUDA_TRY(c, cudaMemcpy(p.occ, occ.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CUDA_TRY(c, cudaMemset(p.lane_mark, 0, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
-  CUDA_TRY(c, cudaMemset(p.outbox_head, 0xFF, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
-  CUDA_TRY(c, cudaMemset(p.ghost_head, 0xFF, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
-  CUDA_TRY(c, cudaMemset(p.inbox_head, 0xFF, (size_t)std::max<int64_t>(p.n_items, 1) * sizeof(int32_t)));
   c->tick = 0;
   c->ns_host = (int32_t)n;
   c->last_reorder_tick = -1;
