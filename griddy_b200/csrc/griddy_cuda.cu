@@ -114,21 +114,25 @@ struct __align__(16) Cold {
   int32_t container;                  // lane (on road) or segment (off road)
   int32_t agenda_cur, route_cur;      // agenda head (index into the item arrays), route head (explicit routes)
   int32_t gid;                        // the actor's id (global id on a partitioned world)
-  int32_t agenda_beg, agenda_end;     // its agenda in the item arrays
-  int32_t land_tick, land_lane;       // landing stamp (with ColdF::land_pos), see "processing order"
   int32_t behind;                     // slot of the next actor behind on the lane (-1 at the rear)
+  int32_t hop;                        // head of the route: lane of (turn-onto lane), or -1 for (arrive-at _)
+  int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions
   // list surgery of the current tick
   int32_t mv_old;                     // where a mover came from: lane, or ~segment
   int32_t ahead_new, behind_new;      // a mover's pointers on its new lane, published by k_settle
   int32_t inbox_next, outbox_next, ghost_next;
   int32_t dead_mark;                  // tick+1 when the actor was found to be a ghost during `tick`
 };
+// The rest of an actor's rarely read state, also one burst.
 struct __align__(16) ColdF {
   double arrive;            // target of the (arrive-at _) that ends the current route
-  double land_pos;          // landing stamp
+  double land_pos;          // landing stamp (with land_tick, land_lane), see "processing order"
   double speed, speed_dt;   // max-speed and fl(max-speed * dt)
+  int32_t agenda_beg, agenda_end;     // the actor's agenda in the item arrays
+  int32_t land_tick, land_lane;
+  int32_t pad[4];
 };
-static_assert(sizeof(Cold) == 64 && sizeof(ColdF) == 32, "cold records are one / half a DRAM burst");
+static_assert(sizeof(Cold) == 64 && sizeof(ColdF) == 64, "cold records are one DRAM burst each");
 
 // The static network, one 32-byte record per registered item: a lane change reads its target lane's
 // kind, length, successor and junctions from one sector.
@@ -198,13 +202,14 @@ __device__ __forceinline__ int32_t outer_lane(const Params& p, int32_t seg, uint
   return side ? p.item[seg].link2 : p.item[seg].link;
 }
 
-// Dimension-ordered next hop on procedural grids (include/griddy_cuda.h, griddy_set_routing_grid).
-__device__ int32_t grid_next_hop(const Params& p, int32_t lane, int32_t dest) {
+// Dimension-ordered next hop on procedural grids (include/griddy_cuda.h, griddy_set_routing_grid):
+// from segment lane `lane` towards the lane that leaves junction dest_from_j for junction dest_to_j.
+__device__ int32_t grid_next_hop(const Params& p, int32_t lane, int32_t lane_to_j, int32_t dest_from_j, int32_t dest_to_j) {
   const int n = p.grid_n;
-  const int32_t J = p.item[lane].to_j, E = p.item[dest].from_j;
+  const int32_t J = lane_to_j, E = dest_from_j;
   int h;
   if (J == E) {
-    const int32_t T = p.item[dest].to_j;
+    const int32_t T = dest_to_j;
     h = (T / n != E / n) ? (T / n > E / n ? 0 : 1) : (T % n > E % n ? 2 : 3);
   } else if (J / n != E / n) {
     h = E / n > J / n ? 0 : 1;
@@ -214,16 +219,16 @@ __device__ int32_t grid_next_hop(const Params& p, int32_t lane, int32_t dest) {
   return p.turn4[4 * (int64_t)lane + h];
 }
 
-// Head of the route after the actor has reached `lane` (route.scm:48-51 evaluated lazily).
-__device__ int32_t route_head_on(const Params& p, int32_t lane, int32_t item, int32_t* rc) {
+// Head of the route after the actor has reached `lane` (route.scm:48-51 evaluated lazily); `it` is
+// lane's record, k holds the route's destination.
+__device__ int32_t route_head_on(const Params& p, int32_t lane, const Item& it, const Cold& k, int32_t item, int32_t* rc) {
   if (p.route_off) {
     const int64_t c = *rc;
     return c < p.route_off[item + 1] ? p.route_lane[c] : HOP_ARRIVE;
   }
-  const int32_t dest = outer_lane(p, p.item_seg[item], p.item_side[item]);
-  if (lane == dest) return HOP_ARRIVE;
-  if (p.item[lane].kind == GRIDDY_JUNCTION_LANE) return p.item[lane].link;
-  const int32_t hop = grid_next_hop(p, lane, dest);
+  if (lane == k.dest_lane) return HOP_ARRIVE;
+  if (it.kind == GRIDDY_JUNCTION_LANE) return it.link;
+  const int32_t hop = grid_next_hop(p, lane, it.to_j, k.dest_from_j, k.dest_to_j);
   if (hop < 0) dev_error(p, DEV_ERR_NO_ROUTE);
   return hop;
 }
@@ -235,7 +240,7 @@ __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop)
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
 __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_t ac, int32_t* aux) {
-  if (ac >= p.cold[a].agenda_end) { *aux = 0; return HEAD_NONE; }
+  if (ac >= p.coldf[a].agenda_end) { *aux = 0; return HEAD_NONE; }
   if (p.item_kind[ac] == GRIDDY_SLEEP_FOR) { *aux = p.item_sleep[ac]; return HEAD_SLEEP; }
   *aux = 0;
   return HEAD_TRAVEL;
@@ -262,6 +267,49 @@ __device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane,
 __device__ __forceinline__ void leave_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
   p.cold[a].outbox_next = atomicExch(&p.lane[lane].outbox, a);
   mark_touched(p, lane, tick, sink);
+}
+
+// ------------------------------------------------------------------------------------------------
+// route-step/turn-onto$ (route.scm:92-135) for an actor that reaches the end of its lane and is not
+// held by a full junction: carry the rest of the tick over into the target lane, pop the route.
+// Reads one cold record of the actor and one record of the target lane; returns the new pos-param.
+__device__ __forceinline__ double turn_onto(const Params& p, const int a, const int tick, const uint32_t st,
+                                            const double cur, const double* __restrict__ pos_old, const TouchSink& sink) {
+  Cold k = p.cold[a];
+  const ColdF f = p.coldf[a];
+  const int32_t target = k.hop, lane = k.container;
+  const Item it = p.item[target];
+  const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), f.speed);
+  const double time_remaining = __dsub_rn(p.dt, time_spent);
+  const double tinv = __ddiv_rn(1.0, it.len);
+  const double tbuf = __ddiv_rn(p.two_size, it.len);
+  double tnext = __dmul_rn(__dmul_rn(f.speed, time_remaining), tinv);   // (+ 0 delta)
+  int32_t x = p.lane[target].tail;
+  const bool remote = x <= -2;   // multi-GPU: another rank owns the target lane
+  if (remote) {                  // its smallest key in (0, ...] came with the halo (+inf: none)
+    const double tlead = p.halo_recv[-2 - x];
+    if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
+  } else {
+    while (x >= 0 && !(pos_old[x] > 0.0)) x = p.sa[x].ahead;   // smallest key in (0, ...]
+    if (x >= 0) {
+      const double tlead = pos_old[x];
+      if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
+    }
+  }
+  int32_t rc = p.route_off ? k.route_cur + 1 : 0;
+  const int32_t nhop = route_head_on(p, target, it, k, k.agenda_cur, &rc);
+  p.cold[a].route_cur = rc;
+  p.cold[a].hop = nhop;
+  p.cold[a].container = target;
+  p.cold[a].mv_old = lane;
+  p.tj[a] = junction_of_hop(p, nhop);
+  p.delta[a] = __dmul_rn(f.speed_dt, tinv);
+  p.buf[a] = tbuf;
+  p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u);
+  if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
+  else enter_lane(p, a, target, tick, sink);
+  leave_lane(p, a, lane, tick, sink);
+  return tnext;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -309,42 +357,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     if (!(next >= 1.0)) return next;
     const int32_t tj = p.tj[a];   // junction-full?  route.scm:98-108 (k_advance has usually answered this)
     if (tj >= 0 && p.occ[tj] > 0) return cur;   // waiting
-    const int32_t target = p.aux[a];
-    const int32_t lane = p.cold[a].container;
-    const int32_t item = p.cold[a].agenda_cur;
-    const double speed = p.coldf[a].speed;
-    const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), speed);
-    const double time_remaining = __dsub_rn(p.dt, time_spent);
-    const double tlen = p.item[target].len;
-    const double tinv = __ddiv_rn(1.0, tlen);
-    const double tbuf = __ddiv_rn(p.two_size, tlen);
-    double tnext = __dmul_rn(__dmul_rn(speed, time_remaining), tinv);   // (+ 0 delta)
-    int32_t x = p.lane[target].tail;
-    const bool remote = x <= -2;   // multi-GPU: another rank owns the target lane
-    if (remote) {                  // its smallest key in (0, ...] came with the halo (+inf: none)
-      const double tlead = p.halo_recv[-2 - x];
-      if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
-    } else {
-      while (x >= 0 && !(pos_old[x] > 0.0)) x = p.sa[x].ahead;   // smallest key in (0, ...]
-      if (x >= 0) {
-        const double tlead = pos_old[x];
-        if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
-      }
-    }
-    int32_t rc = p.route_off ? p.cold[a].route_cur + 1 : 0;
-    const int32_t nhop = route_head_on(p, target, item, &rc);
-    if (p.route_off) p.cold[a].route_cur = rc;
-    p.aux[a] = nhop;
-    p.tj[a] = junction_of_hop(p, nhop);
-    p.delta[a] = __dmul_rn(p.coldf[a].speed_dt, tinv);
-    p.buf[a] = tbuf;
-    p.cold[a].container = target;
-    p.cold[a].mv_old = lane;
-    p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u);
-    if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
-    else enter_lane(p, a, target, tick, sink);
-    leave_lane(p, a, lane, tick, sink);
-    return tnext;
+    return turn_onto(p, a, tick, st, cur, pos_old, sink);
   }
 
   if (rs == GRIDDY_ROUTE_NONE && head == HEAD_NONE) return cur;   // do-nothing$  simulate.scm:70-72
@@ -379,11 +392,19 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const double ipos = p.item_pos[item];
     const double dest_pos = p.item[dest_lane].dir ? __dsub_rn(1.0, ipos) : ipos;
     int32_t rc = p.route_off ? (int32_t)p.route_off[item] : 0;
-    const int32_t hop = route_head_on(p, init_lane, item, &rc);
-    const double len = p.item[init_lane].len;
+    const Item init_it = p.item[init_lane], dest_it = p.item[dest_lane];
+    Cold k;
+    k.dest_lane = dest_lane;
+    k.dest_from_j = dest_it.from_j;
+    k.dest_to_j = dest_it.to_j;
+    const int32_t hop = route_head_on(p, init_lane, init_it, k, item, &rc);
+    const double len = init_it.len;
     p.cold[a].route_cur = rc;
+    p.cold[a].dest_lane = dest_lane;
+    p.cold[a].dest_from_j = k.dest_from_j;
+    p.cold[a].dest_to_j = k.dest_to_j;
     p.coldf[a].arrive = dest_pos;
-    p.aux[a] = hop;
+    p.cold[a].hop = hop;
     p.tj[a] = junction_of_hop(p, hop);
     p.delta[a] = __dmul_rn(p.coldf[a].speed_dt, __ddiv_rn(1.0, len));
     p.buf[a] = __ddiv_rn(p.two_size, len);
@@ -408,8 +429,8 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   p.cold[a].container = seg;
   p.cold[a].mv_old = lane;
   // landing stamp: where this actor sits in the segment's consed list (core.scm:169-171)
-  p.cold[a].land_tick = tick + 1;
-  p.cold[a].land_lane = lane;
+  p.coldf[a].land_tick = tick + 1;
+  p.coldf[a].land_lane = lane;
   p.coldf[a].land_pos = cur;
   uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE);
   ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
@@ -478,6 +499,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
     if (!(st[k] & ST_ALIVE)) continue;
     const int rs = (st[k] >> ST_RS_SHIFT) & 3, head = (st[k] >> ST_HEAD_SHIFT) & 3;
     bool slow = ah[k] >= 0 && lead[k] == cur[k];   // equal key ahead: a ghost to remove
+    bool turn = false;                              // the only thing left to do is route-step/turn-onto$
     double np = cur[k];
     if (!slow) {
       if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {
@@ -487,7 +509,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
         if (st[k] & ST_ARRIVE) slow = true;
         else if (!(next >= 1.0)) np = next;
         else if (tj[k] >= 0 && p.occ[tj[k]] > 0) np = cur[k];   // waiting for a full junction  route.scm:98-111
-        else slow = true;                                          // turns onto the next lane
+        else slow = turn = true;                                   // turns onto the next lane
       } else if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {   // sleep$, time left  simulate.scm:77
         if (slp[k] == 0) slow = true;
         else p.aux[a] = slp[k] - 1;
@@ -495,7 +517,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
         slow = true;
       }
     }
-    if (slow) s_list[atomicAdd(&s_n, 1)] = a;
+    if (slow) s_list[atomicAdd(&s_n, 1)] = turn ? ~a : a;   // ~slot: k_slow goes straight to turn_onto
     else pos_new[a] = np;
   }
   __syncthreads();
@@ -522,10 +544,14 @@ __global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
     __syncthreads();
     const int32_t i = chunk + threadIdx.x;
     if (i < n_slow) {
-      const int a = p.slow[i];
+      const int32_t e = p.slow[i];
+      const int a = e < 0 ? ~e : e;
       const SA sa = p.sa[a];
       const uint32_t st = sa.st;
       const double cur = pos_old[a];
+      if (e < 0) {
+        pos_new[a] = turn_onto(p, a, tick, st, cur, pos_old, sink);
+      } else {
       const bool on_road = st & ST_ONROAD;
       const bool on_route = on_road && ((st >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME;
       const int32_t ah = on_road ? sa.ahead : -1;
@@ -533,6 +559,7 @@ __global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
       const double dlt = on_route ? p.delta[a] : 0.0;
       const double buf = on_route ? p.buf[a] : 0.0;
       pos_new[a] = advance_actor(p, a, tick, st, ah, cur, dlt, buf, lead, pos_old, sink);
+      }
     }
     __syncthreads();
     const int nt = s_nt;
@@ -547,14 +574,14 @@ __global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
 
 // earlier(a,b) among actors that landed on the same segment in the same tick
 __device__ __forceinline__ bool landed_earlier(const Params& p, int a, int b, int32_t t_land) {
-  const int32_t la = p.cold[a].land_lane, lb = p.cold[b].land_lane;
+  const int32_t la = p.coldf[a].land_lane, lb = p.coldf[b].land_lane;
   if (t_land == 0) return la < lb;   // initial placement: land_lane holds the link! order
   if (la != lb) return la > lb;      // higher registration index comes first in static-items
   return p.coldf[a].land_pos > p.coldf[b].land_pos;   // a lane yields its actors in descending pos-param
 }
 
 __device__ __forceinline__ bool stamp_less(const Params& p, int a, int b, uint32_t sta) {
-  const int32_t ta = p.cold[a].land_tick, tb = p.cold[b].land_tick;
+  const int32_t ta = p.coldf[a].land_tick, tb = p.coldf[b].land_tick;
   if (ta != tb) return ta < tb;
   return (sta & ST_CLASS_P) ? landed_earlier(p, b, a, ta) : landed_earlier(p, a, b, ta);
 }
@@ -563,8 +590,8 @@ __device__ __forceinline__ bool stamp_less(const Params& p, int a, int b, uint32
 // conses while get-actors walks head to tail), so a stamp's sign alternates with tick parity.
 __device__ bool offroad_before(const Params& p, int a, int b, int tick) {
   const uint32_t sta = p.sa[a].st, stb = p.sa[b].st;
-  const bool nega = (((tick - p.cold[a].land_tick) & 1) != 0) == ((sta & ST_CLASS_P) != 0);
-  const bool negb = (((tick - p.cold[b].land_tick) & 1) != 0) == ((stb & ST_CLASS_P) != 0);
+  const bool nega = (((tick - p.coldf[a].land_tick) & 1) != 0) == ((sta & ST_CLASS_P) != 0);
+  const bool negb = (((tick - p.coldf[b].land_tick) & 1) != 0) == ((stb & ST_CLASS_P) != 0);
   if (nega != negb) return nega;
   return nega ? stamp_less(p, b, a, stb) : stamp_less(p, a, b, sta);
 }
@@ -679,7 +706,8 @@ __global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
   const int par = tick & 1;
   const int32_t n_slow = p.counters[CNT_STRIDE * par + CNT_SLOW];   // movers are among the deferred actors
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slow; i += gridDim.x * blockDim.x) {
-    const int a = p.slow[i];
+    const int32_t e = p.slow[i];
+    const int a = e < 0 ? ~e : e;
     const uint32_t st = p.sa[a].st;
     if (!(st & ST_MOVED)) continue;
     const int32_t old = p.cold[a].mv_old;
@@ -757,7 +785,8 @@ __global__ void __launch_bounds__(256) k_lane_set_tail(LaneDyn* __restrict__ lan
 
 struct MigRec {
   double pos_old, pos_new, delta, buf, arrive, land_pos, speed, speed_dt;
-  int32_t gid, st, container, mv_old, aux, tj, popped, n_items, land_tick, land_lane;
+  int32_t gid, st, container, mv_old, hop, tj, popped, n_items, land_tick, land_lane, dest_lane, dest_from_j,
+      dest_to_j, pad;
   int32_t item_sleep[MIG_ITEMS], item_seg[MIG_ITEMS];
   double item_pos[MIG_ITEMS];
   uint8_t item_kind[MIG_ITEMS], item_side[MIG_ITEMS];
@@ -814,13 +843,17 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     r.st = (int32_t)((p.sa[a].st & ~ST_EMIG) | ST_IMMIG);
     r.container = lane;
     r.mv_old = p.cold[a].mv_old;
-    r.aux = p.aux[a];
+    r.hop = p.cold[a].hop;
     r.tj = p.tj[a];
-    const int32_t beg = p.cold[a].agenda_beg, end = p.cold[a].agenda_end;
+    r.dest_lane = p.cold[a].dest_lane;
+    r.dest_from_j = p.cold[a].dest_from_j;
+    r.dest_to_j = p.cold[a].dest_to_j;
+    r.pad = 0;
+    const int32_t beg = p.coldf[a].agenda_beg, end = p.coldf[a].agenda_end;
     r.popped = p.cold[a].agenda_cur - beg;
     r.n_items = end - beg;
-    r.land_tick = p.cold[a].land_tick;
-    r.land_lane = p.cold[a].land_lane;
+    r.land_tick = p.coldf[a].land_tick;
+    r.land_lane = p.coldf[a].land_lane;
     if (r.n_items > MIG_ITEMS) { dev_error(p, DEV_ERR_MIG_AGENDA); r.n_items = MIG_ITEMS; }
     for (int k = 0; k < MIG_ITEMS; ++k) {
       const bool in = k < r.n_items;
@@ -847,8 +880,8 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     p.coldf[a].speed = r.speed;
     p.coldf[a].speed_dt = r.speed_dt;
     p.cold[a].gid = r.gid;
-    p.cold[a].agenda_beg = it;
-    p.cold[a].agenda_end = it + r.n_items;
+    p.coldf[a].agenda_beg = it;
+    p.coldf[a].agenda_end = it + r.n_items;
     for (int k = 0; k < r.n_items; ++k) {
       p.item_kind[it + k] = r.item_kind[k];
       p.item_side[it + k] = r.item_side[k];
@@ -866,12 +899,16 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     p.coldf[a].land_pos = r.land_pos;
     p.cold[a].container = r.container;
     p.cold[a].mv_old = r.mv_old;
-    p.aux[a] = r.aux;
+    p.aux[a] = 0;
+    p.cold[a].hop = r.hop;
+    p.cold[a].dest_lane = r.dest_lane;
+    p.cold[a].dest_from_j = r.dest_from_j;
+    p.cold[a].dest_to_j = r.dest_to_j;
     p.tj[a] = r.tj;
     p.cold[a].agenda_cur = it + r.popped;
     p.cold[a].route_cur = 0;
-    p.cold[a].land_tick = r.land_tick;
-    p.cold[a].land_lane = r.land_lane;
+    p.coldf[a].land_tick = r.land_tick;
+    p.coldf[a].land_lane = r.land_lane;
     p.cold[a].dead_mark = 0;
     // onto the lane's inbox; k_settle finds it through the deferred list
     p.cold[a].inbox_next = atomicExch(&p.lane[r.container].inbox, a);
@@ -1014,10 +1051,10 @@ __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uin
   if (o.container) o.container[id] = p.cold[a].container;
   if (o.side) o.side[id] = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? 1 : 0;
   if (o.pos) o.pos[id] = p.pos[par][a];
-  if (o.agenda_cur) o.agenda_cur[id] = p.cold[a].agenda_cur - p.cold[a].agenda_beg;
+  if (o.agenda_cur) o.agenda_cur[id] = p.cold[a].agenda_cur - p.coldf[a].agenda_beg;
   if (o.sleep_left) o.sleep_left[id] = head == HEAD_SLEEP ? aux : 0;
   if (o.route_status) o.route_status[id] = (uint8_t)rs;
-  if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? aux : -2;
+  if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? p.cold[a].hop : -2;
 }
 
 // ================================================================================================
@@ -1533,12 +1570,18 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     Cold& k = cold[a];
     memset(&k, 0, sizeof(k));
     k.container = container[a];
-    k.agenda_cur = k.agenda_beg = (int32_t)agenda_off[a];
-    k.agenda_end = (int32_t)agenda_off[a + 1];
+    k.agenda_cur = (int32_t)agenda_off[a];
     k.gid = (int32_t)a;         // global id = upload index until griddy_mg_set_global_ids
-    k.land_lane = (int32_t)a;   // landing stamp of the initial placement: tick 0, link! order
     k.behind = -1;
-    coldf[a] = ColdF{0.0, 0.0, speed[a], speed_dt[a]};
+    k.hop = HOP_ARRIVE;
+    k.dest_lane = k.dest_from_j = k.dest_to_j = -1;
+    ColdF& f = coldf[a];
+    memset(&f, 0, sizeof(f));
+    f.speed = speed[a];
+    f.speed_dt = speed_dt[a];
+    f.agenda_beg = (int32_t)agenda_off[a];
+    f.agenda_end = (int32_t)agenda_off[a + 1];
+    f.land_lane = (int32_t)a;   // landing stamp of the initial placement: tick 0, link! order
     if (agenda_off[a] < agenda_off[a + 1]) {
       if (item_kind[agenda_off[a]] == GRIDDY_SLEEP_FOR) { s |= HEAD_SLEEP << ST_HEAD_SHIFT; aux[a] = item_sleep[agenda_off[a]]; }
       else s |= HEAD_TRAVEL << ST_HEAD_SHIFT;
@@ -1968,7 +2011,7 @@ int download_state(Ctx* c, bool by_slot, int32_t* gid, uint8_t* alive, uint8_t* 
     CUDA_TRY(c, pull(coldf.data(), p.coldf, ns * sizeof(ColdF)));
     for (int32_t a = 0; a < ns; ++a) {
       cont[a] = cold[a].container; ident[a] = cold[a].gid;
-      land_tick[a] = cold[a].land_tick; land_lane[a] = cold[a].land_lane; land_pos[a] = coldf[a].land_pos;
+      land_tick[a] = coldf[a].land_tick; land_lane[a] = coldf[a].land_lane; land_pos[a] = coldf[a].land_pos;
     }
     CUDA_TRY(c, pull(ps.data(), p.pos[tick & 1], ns * sizeof(double)));
     std::vector<int32_t> ord;
