@@ -391,7 +391,7 @@ def main():
         # tick: 80 algorithmic bytes per living actor over the device time of one tick
         # of the timed region.  k_advance, the kernel that streams the per-actor state, is given
         # beside it against its own 44 bytes per actor.
-        "roofline": {"bound": "hbm", "kernel": "whole tick (k_advance + k_slow + k_relink + k_settle + amortised reorder)",
+        "roofline": {"bound": "hbm", "kernel": "whole tick (k_advance + k_slow + k_unlink + k_link + amortised reorder)",
                      "achieved": whole_tick, "peak": peak, "unit": "GB/s", "frac": whole_tick / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_actor_update": ALGO_BYTES_PER_UPDATE,

@@ -38,11 +38,10 @@
 //              or a neighbouring cache line.  Actors that change lane or road-side are appended to
 //              the movers list and pushed on their target lane's inbox (warp-aggregated atomics);
 //              their lanes are marked touched.
-//   k_relink   one thread per touched lane.  Lanes are doubly linked lists: leavers and ghosts are
-//              unlinked in O(1), entrants are inserted by a short walk up from the rear; an entrant
-//              that lands on an occupied key is resolved exactly as bbtree-set would.
-//   k_settle   one thread per mover: publishes its new ahead pointer, applies junction occupancy
-//              deltas.
+//   k_unlink   one thread per touched lane.  Lanes are doubly linked lists: leavers and ghosts are
+//              taken out in O(1) each; actors that are done for the tick are settled.
+//   k_link     one thread per touched lane: entrants are inserted by a short walk up from the rear; an
+//              entrant that lands on an occupied key is resolved exactly as bbtree-set would.
 //
 // Processing order without a global sort.  "a is processed before b" (world.scm:24-30) is decided
 // from their OLD locations: different containers -> higher registration index first; same lane ->
@@ -56,7 +55,7 @@
 // tick late at no cost: an
 // actor whose list follower holds an equal key is a GHOST (it is not part of the world any more).
 // Every on-road actor reads its leader's key each tick, sees the tie, marks the ghost dead and has
-// the lane relinked; whatever the ghost itself did this tick is discarded by k_relink / k_settle.
+// the lane relinked; whatever the ghost itself did this tick is discarded by k_unlink.
 // Nothing else can observe a ghost: queries reach the follower first and see the same key, and the
 // junction it may stand on is occupied by the follower as well.  Downloads apply the same rule.
 //
@@ -81,14 +80,14 @@ namespace {
 constexpr uint32_t ST_ALIVE = 1u, ST_ONROAD = 2u, ST_SIDE = 4u;
 constexpr int ST_RS_SHIFT = 3;    // 2 bits: GRIDDY_ROUTE_*
 constexpr int ST_HEAD_SHIFT = 5;  // 2 bits: 0 no head, 1 sleep-for, 2 travel-to
-constexpr uint32_t ST_MOVED = 128u;    // changed lane / road side this tick (cleared by k_settle)
+constexpr uint32_t ST_MOVED = 128u;    // changed lane / road side this tick (cleared by k_unlink / k_link)
 constexpr uint32_t ST_CLASS_P = 256u;  // landing stamp: came from a lane visited before the segment
 constexpr uint32_t ST_ARRIVE = 512u;   // the route head is (arrive-at _): aux == HOP_ARRIVE
 constexpr int HEAD_NONE = 0, HEAD_SLEEP = 1, HEAD_TRAVEL = 2;
 constexpr int HOP_ARRIVE = -1;
 
-constexpr uint32_t ST_EMIG = 1024u;     // multi-GPU: moved onto a lane another rank owns (this slot dies in k_settle)
-constexpr uint32_t ST_IMMIG = 2048u;    // multi-GPU: arrived from another rank this tick (cleared in k_settle)
+constexpr uint32_t ST_EMIG = 1024u;     // multi-GPU: moved onto a lane another rank owns (this slot dies in k_unlink)
+constexpr uint32_t ST_IMMIG = 2048u;    // multi-GPU: arrived from another rank this tick (cleared in k_link)
 
 constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
               DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32, DEV_ERR_MIG_OVERFLOW = 64,
@@ -119,7 +118,7 @@ struct __align__(16) Cold {
   int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions
   // list surgery of the current tick
   int32_t mv_old;                     // where a mover came from: lane, or ~segment
-  int32_t ahead_new, behind_new;      // a mover's pointers on its new lane, published by k_settle
+  int32_t spare[2];
   int32_t inbox_next, outbox_next, ghost_next;
   int32_t dead_mark;                  // tick+1 when the actor was found to be a ghost during `tick`
 };
@@ -150,7 +149,8 @@ struct __align__(16) LaneDyn {
   int32_t tail;      // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
   int32_t inbox, outbox, ghosts;
   int32_t mark;      // tick+1 once the lane is on this tick's touched list
-  int32_t pad[3];
+  int32_t junction;  // junction lanes: their junction (whose occupancy they count towards), else -1
+  int32_t pad[2];
 };
 static_assert(sizeof(Item) == 32 && sizeof(LaneDyn) == 32, "one sector per record");
 
@@ -608,59 +608,83 @@ __device__ int later_processed(const Params& p, int x, int y, int32_t lane, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_relink: one thread per lane that an actor entered or left this tick.  Lanes are doubly linked
-// lists in ascending pos-param, so nothing walks a whole lane: leavers (the lane's outbox) and ghosts
-// found this tick (its ghost list) are unlinked in O(1) each; entrants (its inbox, sorted) are
-// inserted by walking up from the rear — entrants land near pos 0, so that is a step or two.
+// k_unlink / k_link: one thread per lane that an actor entered or left this tick.  Lanes are doubly
+// linked lists in ascending pos-param, so nothing walks a whole lane.
+//   k_unlink  takes the lane's leavers (its outbox) and the ghosts found on it this tick out of the
+//             list in O(1) each, and settles the actors that are done for this tick: a ghost's move is
+//             void, an emigrant lives on another rank from now on, an actor that left the road has no
+//             lane to enter.
+//   k_link    (after every lane has been unlinked, so a mover's pointers are free to overwrite)
+//             inserts the lane's entrants (its inbox, sorted) by walking up from the rear — entrants
+//             land near pos 0, so that is a step or two — and writes their final pointers.
 // Residents keep their relative order (a follower is clamped behind its leader, route.scm:68-74).
-// Equal keys: an entrant that lands on a resident's or another entrant's key is resolved here, the
-// later-processed one stays (core.scm:173-178); two residents that round to the same key are left
+// Equal keys: an entrant that lands on a resident's or another entrant's key is resolved in k_link,
+// the later-processed one stays (core.scm:173-178); two residents that round to the same key are left
 // linked and resolved next tick through the ghost rule (file header) — on every lane, touched or not.
-// A mover's own pointers are staged in ahead_new / behind_new (its old ones still describe its old
-// lane, which another thread may be unlinking it from) and published by k_settle.
+// Junction occupancy (route.scm:98-104) changes by whole lanes: one atomic per lane and kernel.
 constexpr int32_t UNLINKED = -3;
 
-__global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
+__global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
+  const int par = tick & 1;
+  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
+    const int32_t lane = p.touched[i];
+    const LaneDyn ld = p.lane[lane];
+    if (ld.outbox < 0 && ld.ghosts < 0) continue;
+    if (ld.outbox >= 0) p.lane[lane].outbox = -1;
+    if (ld.ghosts >= 0) p.lane[lane].ghosts = -1;
+    int32_t tail = ld.tail, gone = 0;
+    // A ghost that also moved is on both lists; the second visit finds it UNLINKED.
+    auto unlink = [&](int32_t z, int32_t b) {
+      const int32_t f = p.sa[z].ahead;
+      if (f == UNLINKED) return false;
+      if (b >= 0) p.sa[b].ahead = f; else tail = f;
+      if (f >= 0) p.cold[f].behind = b;
+      p.sa[z].ahead = UNLINKED;
+      return true;
+    };
+    for (int32_t z = ld.outbox; z >= 0;) {
+      const Cold k = p.cold[z];
+      unlink(z, k.behind);
+      ++gone;   // every mover leaves its old lane, whatever becomes of it
+      const uint32_t sz = p.sa[z].st;
+      if (k.dead_mark == tick + 1 || (sz & ST_EMIG)) p.sa[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG);
+      else if (!(sz & ST_ONROAD)) p.sa[z].st = sz & ~ST_MOVED;   // went off the road: nothing to link
+      z = k.outbox_next;
+    }
+    for (int32_t z = ld.ghosts; z >= 0;) {
+      const Cold k = p.cold[z];
+      const uint32_t sz = p.sa[z].st;
+      if (unlink(z, k.behind) && !(sz & ST_MOVED)) {   // (one that also moved was settled above)
+        p.sa[z].st = sz & ~ST_ALIVE;
+        ++gone;
+      }
+      z = k.ghost_next;
+    }
+    if (tail != ld.tail) p.lane[lane].tail = tail;
+    if (ld.junction >= 0 && gone) atomicSub(&p.occ[ld.junction], gone);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_link(Params p, int tick) {
   const int par = tick & 1;
   const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
   const double* __restrict__ pos_old = p.pos[par];
   const double* __restrict__ pos_new = p.pos[par ^ 1];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = p.touched[i];
-    const int32_t inbox = p.lane[lane].inbox, outbox = p.lane[lane].outbox, ghosts = p.lane[lane].ghosts;
-    if (inbox >= 0) p.lane[lane].inbox = -1;
-    if (outbox >= 0) p.lane[lane].outbox = -1;
-    if (ghosts >= 0) p.lane[lane].ghosts = -1;
-    const bool jl = p.item[lane].kind == GRIDDY_JUNCTION_LANE;
-
-    // 1. unlink.  A ghost that also moved is on both lists; the second visit finds it UNLINKED.
-    auto unlink = [&](int32_t z) {
-      const int32_t f = p.sa[z].ahead;
-      if (f == UNLINKED) return false;
-      const int32_t b = p.cold[z].behind;
-      if (b >= 0) p.sa[b].ahead = f; else p.lane[lane].tail = f;
-      if (f >= 0) p.cold[f].behind = b;
-      p.sa[z].ahead = UNLINKED;
-      return true;
-    };
-    for (int32_t z = outbox; z >= 0; z = p.cold[z].outbox_next) unlink(z);
-    for (int32_t z = ghosts; z >= 0; z = p.cold[z].ghost_next) {
-      const uint32_t sz = p.sa[z].st;
-      if (unlink(z) && !(sz & ST_MOVED)) {   // one that also moved is finalised by k_settle
-        p.sa[z].st = sz & ~ST_ALIVE;
-        if (jl) atomicSub(&p.occ[p.item[lane].link2], 1);
-      }
-    }
+    const LaneDyn ld = p.lane[lane];
+    const int32_t inbox = ld.inbox;
     if (inbox < 0) continue;
-
-    // 2. insert the entrants by ascending (pos-param, slot): selection over the inbox, which is short
+    p.lane[lane].inbox = -1;
+    // entrants by ascending (pos-param, slot): selection over the inbox, which is short
     double e_pos = 0.0;
     int32_t e = -1;
     auto next_entrant = [&](bool first) {
       int32_t best = -1;
       double best_pos = 0.0;
       for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
-        if (p.cold[y].dead_mark == tick + 1) continue;   // a ghost's move is void
+        if (!(p.sa[y].st & ST_MOVED)) continue;   // a ghost's move is void: k_unlink settled it
         const double py = pos_new[y];
         if (!first && !(py > e_pos || (py == e_pos && y > e))) continue;
         if (best < 0 || py < best_pos || (py == best_pos && y < best)) { best = y; best_pos = py; }
@@ -668,63 +692,35 @@ __global__ void __launch_bounds__(128) k_relink(Params p, int tick) {
       e = best;
       e_pos = best_pos;
     };
-    auto next_of = [&](int32_t z) {
-      const SA sz = p.sa[z];
-      return (sz.st & ST_MOVED) ? p.cold[z].ahead_new : sz.ahead;
+    auto link = [&](int32_t b, int32_t z, int32_t f) {   // b -> z -> f
+      if (b < 0) p.lane[lane].tail = z; else p.sa[b].ahead = z;
+      p.sa[z].ahead = f;
+      p.cold[z].behind = b;
+      if (f >= 0) p.cold[f].behind = z;
     };
-    auto link = [&](int32_t b, int32_t z, int32_t f) {   // b -> z -> f, z an entrant
-      if (b < 0) p.lane[lane].tail = z;
-      else if (p.sa[b].st & ST_MOVED) p.cold[b].ahead_new = z;
-      else p.sa[b].ahead = z;
-      p.cold[z].ahead_new = f;
-      p.cold[z].behind_new = b;
-      if (f >= 0) {
-        if (p.sa[f].st & ST_MOVED) p.cold[f].behind_new = z; else p.cold[f].behind = z;
-      }
-    };
-    int32_t prev = -1, x = p.lane[lane].tail;
+    int32_t prev = -1, x = ld.tail, delta = 0;
     for (next_entrant(true); e >= 0; next_entrant(false)) {
-      while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = next_of(x); }
+      while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = p.sa[x].ahead; }
       if (x >= 0 && pos_new[x] == e_pos) {   // equal key: bbtree-set keeps the one processed later
         const bool e_wins = later_processed(p, e, x, lane, pos_old, tick) == e;
         const int32_t lose = e_wins ? x : e;
         const uint32_t sl = p.sa[lose].st;
-        p.sa[lose].st = sl & ~ST_ALIVE;
-        if (jl && !(sl & ST_MOVED)) atomicSub(&p.occ[p.item[lane].link2], 1);
+        p.sa[lose].st = sl & ~ST_ALIVE;        // (still marked moved if it is an entrant: see below)
+        if (!(sl & ST_MOVED) || lose == x) --delta;   // a resident, or an entrant that had been counted in
         if (!e_wins) continue;
-        link(prev, e, next_of(x));   // e takes x's place
+        link(prev, e, p.sa[x].ahead);   // e takes x's place
       } else {
         link(prev, e, x);
       }
+      ++delta;
       x = e;   // the next entrant (same or higher key) meets e first
     }
-  }
-}
-
-// k_settle: per mover (found in the deferred list), publish the new ahead pointer and apply junction occupancy deltas.
-__global__ void __launch_bounds__(256) k_settle(Params p, int tick) {
-  const int par = tick & 1;
-  const int32_t n_slow = p.counters[CNT_STRIDE * par + CNT_SLOW];   // movers are among the deferred actors
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slow; i += gridDim.x * blockDim.x) {
-    const int32_t e = p.slow[i];
-    const int a = e < 0 ? ~e : e;
-    const uint32_t st = p.sa[a].st;
-    if (!(st & ST_MOVED)) continue;
-    const int32_t old = p.cold[a].mv_old;
-    // an immigrant's old lane belongs to the rank it came from, which does this bookkeeping itself
-    if (!(st & ST_IMMIG) && old >= 0 && p.item[old].kind == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[p.item[old].link2], 1);
-    if (p.cold[a].dead_mark == tick + 1 || (st & ST_EMIG)) {
-      // it was a ghost when it moved (the move is void), or it lives on another rank from now on
-      p.sa[a].st = st & ~(ST_MOVED | ST_ALIVE | ST_EMIG);
-      continue;
+    // the entrants stayed marked as movers so that ties among them could look at where they came from
+    for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
+      const uint32_t sy = p.sa[y].st;
+      if (sy & ST_MOVED) p.sa[y].st = sy & ~(ST_MOVED | ST_IMMIG);
     }
-    if ((st & ST_ALIVE) && (st & ST_ONROAD)) {
-      p.sa[a].ahead = p.cold[a].ahead_new;
-      p.cold[a].behind = p.cold[a].behind_new;
-      const int32_t lane = p.cold[a].container;
-      if (p.item[lane].kind == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[p.item[lane].link2], 1);
-    }
-    p.sa[a].st = st & ~(ST_MOVED | ST_IMMIG);
+    if (ld.junction >= 0 && delta) atomicAdd(&p.occ[ld.junction], delta);
   }
 }
 
@@ -761,9 +757,11 @@ __global__ void __launch_bounds__(256) k_item_set_key(Item* __restrict__ item, i
   if (r < n) item[r].loc_key = key[r];
 }
 
-__global__ void __launch_bounds__(256) k_lane_init(LaneDyn* __restrict__ lane, int64_t n) {
+__global__ void __launch_bounds__(256) k_lane_init(LaneDyn* __restrict__ lane, const Item* __restrict__ item, int64_t n) {
   const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (r < n) lane[r] = LaneDyn{-1, -1, -1, -1, 0, {0, 0, 0}};
+  if (r >= n) return;
+  const Item it = item[r];
+  lane[r] = LaneDyn{-1, -1, -1, -1, 0, it.kind == GRIDDY_JUNCTION_LANE ? it.link2 : -1, {0, 0}};
 }
 
 __global__ void __launch_bounds__(256) k_lane_set_tail(LaneDyn* __restrict__ lane, const int32_t* __restrict__ which,
@@ -910,11 +908,10 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     p.coldf[a].land_tick = r.land_tick;
     p.coldf[a].land_lane = r.land_lane;
     p.cold[a].dead_mark = 0;
-    // onto the lane's inbox; k_settle finds it through the deferred list
+    // onto the lane's inbox
     p.cold[a].inbox_next = atomicExch(&p.lane[r.container].inbox, a);
     if (atomicExch(&p.lane[r.container].mark, tick + 1) != tick + 1)
       p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_TOUCHED], 1)] = r.container;
-    p.slow[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_SLOW], 1)] = a;
   }
 }
 
@@ -1689,7 +1686,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     for (int64_t a = 0; a < n; ++a)
       if (c->mg_owner_host[container[a]] != c->mg.rank)
         return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + " is not on this rank's part of the world");
-  if (p.n_items > 0) k_lane_init<<<(unsigned)((p.n_items + 255) / 256), 256>>>(p.lane, p.n_items);
+  if (p.n_items > 0) k_lane_init<<<(unsigned)((p.n_items + 255) / 256), 256>>>(p.lane, p.item, p.n_items);
   if (!tail_lane.empty()) {
     std::vector<void*> tmp;
     const int32_t *d_which, *d_tail;
@@ -1735,7 +1732,7 @@ int finish_step(Ctx* c) {
 
 // One tick = four launches (plus a reorder every reorder_period ticks; plus, on a partitioned world,
 // the halo and migrant kernels and two exchanges).  ev (optional) receives 6 events bracketing
-// reorder (+ halo pack), k_advance, k_slow (+ emigrant pack), k_relink (+ immigrant unpack), k_settle.
+// reorder (+ halo pack), k_advance, k_slow (+ emigrant pack), k_unlink (+ immigrant unpack), k_link.
 int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   if (ev) cudaEventRecord(ev[0], c->stream);
   if (c->reorder_period > 0 && tick % c->reorder_period == 0 && tick != c->last_reorder_tick)
@@ -1777,7 +1774,6 @@ int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
 
 int tick_finish(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   const Params& p = c->p;
-  const unsigned aux_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host + 255) / 256), 1u), 148u * 8u);
   // one thread per touched lane where possible: a lane is walked serially, so grid-striding doubles the longest chain
   const unsigned relink_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host / 8 + 127) / 128), 1u), 148u * 64u);
   if (c->mg.on) {
@@ -1788,9 +1784,9 @@ int tick_finish(Ctx* c, int64_t tick, cudaEvent_t* ev) {
       c->ns_host = (int32_t)std::min<int64_t>(p.cap, (int64_t)c->ns_host + nb.mig_in);
     }
   }
-  k_relink<<<relink_blocks, 128, 0, c->stream>>>(p, (int)tick);
+  k_unlink<<<relink_blocks, 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[4], c->stream);
-  k_settle<<<aux_blocks, 256, 0, c->stream>>>(p, (int)tick);
+  k_link<<<relink_blocks, 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[5], c->stream);
   c->launches += 2;
   return GRIDDY_OK;
@@ -1921,7 +1917,7 @@ int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms) {
   for (int64_t t = 0; t < n_ticks && c->ns_host > 0; ++t) {
     TRY(launch_tick(c, c->tick + t, ev));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    // kernel_ms = {k_advance, k_relink, k_settle, reorder, k_slow}
+    // kernel_ms = {k_advance, k_unlink, k_link, reorder, k_slow}
     static const int slot_of[5] = {3, 0, 4, 1, 2};
     for (int k = 0; k < 5; ++k) {
       float ms = 0.f;

@@ -124,7 +124,7 @@ class Simulation:
         """Per-kernel device ms summed over n_ticks (events around every launch)."""
         ms = (C.c_double * 5)(0.0, 0.0, 0.0, 0.0, 0.0)
         self._chk(lib().griddy_profile_step(self.h, C.c_int64(n_ticks), ms))
-        return {"k_advance": ms[0], "k_slow": ms[4], "k_relink": ms[1], "k_settle": ms[2], "reorder": ms[3]}
+        return {"k_advance": ms[0], "k_slow": ms[4], "k_unlink": ms[1], "k_link": ms[2], "reorder": ms[3]}
 
     @property
     def last_step_ms(self) -> float:

@@ -173,7 +173,7 @@ int griddy_download_local(void* ctx, int64_t capacity, int64_t* n_local, int32_t
 
 /* Like griddy_step, but brackets every kernel launch with CUDA events on the launching stream and
  * adds the per-kernel device time, in ms summed over the n_ticks, to kernel_ms[0..4] =
- * {k_advance, k_relink, k_settle, reorder (all its launches), k_slow}.  For roofline accounting only: the
+ * {k_advance, k_unlink, k_link, reorder (all its launches), k_slow}.  For roofline accounting only: the
  * events serialise launches. */
 int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms);
 
