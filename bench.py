@@ -210,11 +210,12 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=64)
     ap.add_argument("--cpu-ticks", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reorder-period", type=int, default=128)
+    ap.add_argument("--reorder-period", type=int, default=384)
     ap.add_argument("--mig-cap", type=int, default=1 << 24, help="multi-GPU: boundary crossings per neighbour per tick")
     ap.add_argument("--extra-slots", type=int, default=4_000_000, help="multi-GPU: room for actors arriving from other ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout, which carries the one JSON line
 
     if args.impl == "reference":
         run_reference(args)

@@ -233,9 +233,15 @@ __device__ int32_t route_head_on(const Params& p, int32_t lane, const Item& it, 
   return hop;
 }
 
-// The junction whose occupancy gates a (turn-onto lane) head (route.scm:105-108), or -1.
+// The junction whose occupancy gates a (turn-onto lane) head (route.scm:105-108), or -1.  On a
+// partitioned world a junction another rank owns carries TJ_REMOTE: its occupancy arrives with the
+// halo, which k_advance does not wait for, so such actors are left to k_slow.
+constexpr int32_t TJ_REMOTE = 1 << 30;
+__device__ __forceinline__ int32_t tag_junction(const Params& p, int32_t j) {
+  return (j >= 0 && p.owner && p.owner[j] != p.my_rank) ? (j | TJ_REMOTE) : j;
+}
 __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop) {
-  return (hop >= 0 && p.item[hop].kind == GRIDDY_JUNCTION_LANE) ? p.item[hop].link2 : -1;
+  return tag_junction(p, (hop >= 0 && p.item[hop].kind == GRIDDY_JUNCTION_LANE) ? p.item[hop].link2 : -1);
 }
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
@@ -356,7 +362,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     // route-step/turn-onto$  route.scm:92-135
     if (!(next >= 1.0)) return next;
     const int32_t tj = p.tj[a];   // junction-full?  route.scm:98-108 (k_advance has usually answered this)
-    if (tj >= 0 && p.occ[tj] > 0) return cur;   // waiting
+    if (tj >= 0 && p.occ[tj & ~TJ_REMOTE] > 0) return cur;   // waiting
     return turn_onto(p, a, tick, st, cur, pos_old, sink);
   }
 
@@ -508,6 +514,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
         if (ah[k] >= 0 && lead[k] > cur[k] && lead[k] <= __dadd_rn(next, buf[k])) next = __dsub_rn(lead[k], buf[k]);
         if (st[k] & ST_ARRIVE) slow = true;
         else if (!(next >= 1.0)) np = next;
+        else if (tj[k] >= TJ_REMOTE) slow = true;                  // the junction's occupancy is still on its way (halo)
         else if (tj[k] >= 0 && p.occ[tj[k]] > 0) np = cur[k];   // waiting for a full junction  route.scm:98-111
         else slow = turn = true;                                   // turns onto the next lane
       } else if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {   // sleep$, time left  simulate.scm:77
@@ -842,7 +849,7 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     r.container = lane;
     r.mv_old = p.cold[a].mv_old;
     r.hop = p.cold[a].hop;
-    r.tj = p.tj[a];
+    r.tj = p.tj[a] >= 0 ? (p.tj[a] & ~TJ_REMOTE) : -1;
     r.dest_lane = p.cold[a].dest_lane;
     r.dest_from_j = p.cold[a].dest_from_j;
     r.dest_to_j = p.cold[a].dest_to_j;
@@ -902,7 +909,7 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     p.cold[a].dest_lane = r.dest_lane;
     p.cold[a].dest_from_j = r.dest_from_j;
     p.cold[a].dest_to_j = r.dest_to_j;
-    p.tj[a] = r.tj;
+    p.tj[a] = tag_junction(p, r.tj);
     p.cold[a].agenda_cur = it + r.popped;
     p.cold[a].route_cur = 0;
     p.coldf[a].land_tick = r.land_tick;
@@ -1082,7 +1089,9 @@ struct Multi {
   std::vector<std::pair<int32_t, int32_t>> import_marks;   // (remote lane, -2 - index into halo_recv)
   double* d_halo_recv = nullptr;
   int32_t* d_owner = nullptr;
-  void* nccl_comm = nullptr;          // transport 1: NCCL send/recv between processes
+  void* nccl_comm = nullptr;          // transport 1: NCCL send/recv between processes, on their own stream
+  cudaStream_t comm_stream = nullptr; //   so that k_advance hides the halo exchange and k_unlink the migrants'
+  cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
   std::vector<Ctx*> peers;            // transport 2: every rank is a context of this process
   cudaEvent_t ev_ready = nullptr;     //   "my send buffers for this phase are written"
 };
@@ -1099,7 +1108,7 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // slots
   int32_t ns_host = 0;         // upper bound of the slots in use (refreshed after every step)
-  int reorder_period = 128;
+  int reorder_period = 384;
   int64_t last_reorder_tick = -1;
   int loc_key_bits = 1;
   uint32_t *alt4[PERM4] = {}, *cur4[PERM4] = {};   // double buffers of the permuted arrays
@@ -1222,6 +1231,9 @@ void mg_reset(Ctx* c) {
   Multi& m = c->mg;
   for (void* ptr : m.allocs) cudaFree(ptr);
   if (m.ev_ready) cudaEventDestroy(m.ev_ready);
+  if (m.ev_packed) cudaEventDestroy(m.ev_packed);
+  if (m.ev_arrived) cudaEventDestroy(m.ev_arrived);
+  if (m.comm_stream) cudaStreamDestroy(m.comm_stream);
   // the NCCL communicator, if any, is left to process exit: destroying it is collective
   m = Multi();
   c->mg_owner_host.clear();
@@ -1749,10 +1761,19 @@ int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   return GRIDDY_OK;
 }
 
+// k_advance does not read the halo (actors gated by a remote junction are deferred to k_slow), so it
+// can run while the halo is in flight.
 int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
-  const Params& p = c->p;
   const unsigned per_block = ADV_THREADS * ADV_UNROLL;
   const unsigned adv_blocks = (unsigned)((c->ns_host + per_block - 1) / per_block);
+  if (adv_blocks) k_advance<<<adv_blocks, ADV_THREADS, 0, c->stream>>>(c->p, (int)tick);
+  if (ev) cudaEventRecord(ev[2], c->stream);
+  ++c->launches;
+  return GRIDDY_OK;
+}
+
+int tick_slow(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // needs the halo
+  const Params& p = c->p;
   const unsigned aux_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host + 255) / 256), 1u), 148u * 8u);
   if (c->mg.on)
     for (Neighbor& nb : c->mg.nb)
@@ -1760,42 +1781,57 @@ int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
         k_halo_unpack<<<(nb.n_imp_junc + 127) / 128, 128, 0, c->stream>>>(p, nb.d_imp_junc, nb.n_imp_junc, nb.d_halo_recv + nb.n_imp_lanes);
         ++c->launches;
       }
-  if (adv_blocks) k_advance<<<adv_blocks, ADV_THREADS, 0, c->stream>>>(p, (int)tick);
-  if (ev) cudaEventRecord(ev[2], c->stream);
   k_slow<<<aux_blocks * 2, SLOW_THREADS, 0, c->stream>>>(p, (int)tick);
   if (c->mg.on) {
     k_emig_pack<<<64, 128, 0, c->stream>>>(p, (int)tick);
     ++c->launches;
   }
   if (ev) cudaEventRecord(ev[3], c->stream);
-  c->launches += 2;
+  ++c->launches;
   return GRIDDY_OK;
 }
 
-int tick_finish(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+// one thread per touched lane where possible: grid-striding doubles the longest chain
+unsigned relink_blocks(const Ctx* c) {
+  return std::min<unsigned>(std::max((unsigned)((c->ns_host / 8 + 127) / 128), 1u), 148u * 64u);
+}
+
+int tick_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // local lists only: does not need the migrants
+  k_unlink<<<relink_blocks(c), 128, 0, c->stream>>>(c->p, (int)tick);
+  if (ev) cudaEventRecord(ev[4], c->stream);
+  ++c->launches;
+  return GRIDDY_OK;
+}
+
+int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // needs the migrants
   const Params& p = c->p;
-  // one thread per touched lane where possible: a lane is walked serially, so grid-striding doubles the longest chain
-  const unsigned relink_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host / 8 + 127) / 128), 1u), 148u * 64u);
-  if (c->mg.on) {
+  if (c->mg.on)
     for (Neighbor& nb : c->mg.nb) {
       k_immig_unpack<<<std::max(1, nb.mig_in / 512), 128, 0, c->stream>>>(p, (int)tick, nb.d_mig_recv, nb.mig_in);
       ++c->launches;
       // upper bound of the slots in use: the neighbour may have filled its buffer
       c->ns_host = (int32_t)std::min<int64_t>(p.cap, (int64_t)c->ns_host + nb.mig_in);
     }
-  }
-  k_unlink<<<relink_blocks, 128, 0, c->stream>>>(p, (int)tick);
-  if (ev) cudaEventRecord(ev[4], c->stream);
-  k_link<<<relink_blocks, 128, 0, c->stream>>>(p, (int)tick);
+  k_link<<<relink_blocks(c), 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[5], c->stream);
-  c->launches += 2;
+  ++c->launches;
   return GRIDDY_OK;
 }
 
 // NCCL transport: one grouped send/recv with every neighbour, on the context's stream.
+// What was packed on the compute stream so far is sent; whoever needs what arrives waits for
+// exchange_arrived().  In between the compute stream is free to run kernels that need neither.
 int exchange_nccl(Ctx* c, bool halo) {
   NcclApi* api = nccl_api();
   if (!api || !c->mg.nccl_comm) return fail(c, GRIDDY_ERR_NCCL, "multi-GPU context is not connected (griddy_mg_connect_nccl)");
+  cudaStream_t compute = c->stream;
+  CUDA_TRY(c, cudaEventRecord(c->mg.ev_packed, compute));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->mg.comm_stream, c->mg.ev_packed, 0));
+  struct OnComm {   // the sends and receives below go to the communication stream
+    Ctx* c; cudaStream_t saved;
+    OnComm(Ctx* c_) : c(c_), saved(c_->stream) { c->stream = c->mg.comm_stream; }
+    ~OnComm() { c->stream = saved; }
+  } on_comm(c);
   NCCL_TRY(c, api->GroupStart());
   for (Neighbor& nb : c->mg.nb) {
     if (halo) {
@@ -1809,15 +1845,25 @@ int exchange_nccl(Ctx* c, bool halo) {
     }
   }
   NCCL_TRY(c, api->GroupEnd());
+  CUDA_TRY(c, cudaEventRecord(c->mg.ev_arrived, c->mg.comm_stream));
+  return GRIDDY_OK;
+}
+
+int exchange_arrived(Ctx* c) {
+  CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->mg.ev_arrived, 0));
   return GRIDDY_OK;
 }
 
 int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   TRY(tick_begin(c, tick, ev));
-  if (c->mg.on) TRY(exchange_nccl(c, true));
-  TRY(tick_advance(c, tick, ev));
-  if (c->mg.on) TRY(exchange_nccl(c, false));
-  return tick_finish(c, tick, ev);
+  if (c->mg.on) TRY(exchange_nccl(c, true));      // halo in flight ...
+  TRY(tick_advance(c, tick, ev));                  // ... behind k_advance
+  if (c->mg.on) TRY(exchange_arrived(c));
+  TRY(tick_slow(c, tick, ev));
+  if (c->mg.on) TRY(exchange_nccl(c, false));     // migrants in flight ...
+  TRY(tick_unlink(c, tick, ev));                   // ... behind k_unlink
+  if (c->mg.on) TRY(exchange_arrived(c));
+  return tick_link(c, tick, ev);
 }
 
 // Local transport: every rank is a context of this process; `src` has recorded ev_ready after writing
@@ -1874,20 +1920,22 @@ int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks) {
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
   }
-  for (int64_t t = 0; t < n_ticks; ++t) {
-    for (int phase = 0; phase < 2; ++phase) {
-      for (Ctx* c : cs) {
-        CUDA_TRY(c, cudaSetDevice(c->device));
-        if (phase == 0) TRY(tick_begin(c, c->tick + t, nullptr));
-        else TRY(tick_advance(c, c->tick + t, nullptr));
-        CUDA_TRY(c, cudaEventRecord(c->mg.ev_ready, c->stream));
-      }
-      for (Ctx* c : cs) TRY(exchange_local(c, phase == 0));
-    }
+  auto each = [&](int (*phase)(Ctx*, int64_t, cudaEvent_t*), int64_t t, bool ready) -> int {
     for (Ctx* c : cs) {
       CUDA_TRY(c, cudaSetDevice(c->device));
-      TRY(tick_finish(c, c->tick + t, nullptr));
+      TRY(phase(c, c->tick + t, nullptr));
+      if (ready) CUDA_TRY(c, cudaEventRecord(c->mg.ev_ready, c->stream));
     }
+    return GRIDDY_OK;
+  };
+  for (int64_t t = 0; t < n_ticks; ++t) {
+    TRY(each(tick_begin, t, true));
+    for (Ctx* c : cs) TRY(exchange_local(c, true));
+    TRY(each(tick_advance, t, false));
+    TRY(each(tick_slow, t, true));
+    for (Ctx* c : cs) TRY(exchange_local(c, false));
+    TRY(each(tick_unlink, t, false));
+    TRY(each(tick_link, t, false));
   }
   int rc = GRIDDY_OK;
   for (Ctx* c : cs) {
@@ -2154,6 +2202,9 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
   TRY(mg_alloc(c, &m.d_owner, (size_t)n_items));
   CUDA_TRY(c, cudaMemcpy(m.d_owner, owner, (size_t)n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_packed, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_arrived, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&m.comm_stream, cudaStreamNonBlocking));
   // what I export to / import from every other rank
   struct Lists { std::vector<int32_t> exp_l, exp_j, imp_l, imp_j; };
   std::vector<Lists> lists(world);

@@ -80,7 +80,7 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
  * not depend on it.  Call after griddy_upload_network and before griddy_upload_actors. */
 int griddy_set_locality_keys(void* ctx, const uint32_t* item_key);
 
-/* Ticks between two reorders of the actor slots (default 128; 0 = never).  Performance only. */
+/* Ticks between two reorders of the actor slots (default 384; 0 = never).  Performance only. */
 int griddy_set_reorder_period(void* ctx, int32_t ticks);
 
 /* Device-side routing table for procedural grids (examples/procedural-grid.scm): the first n*n
