@@ -286,13 +286,16 @@ def main():
     # an actor replaced by an equal-key insert is gone (core.scm:173-178) and is not advanced any
     # more: count the living ones only (mean of before / after; the decline is slow and steady)
     alive_mean = 0.5 * (alive0 + alive1)
+    per_rank = None
     if world > 1:
         t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
-        t = torch.tensor([alive_mean], device="cuda", dtype=torch.float64)
+        t = torch.zeros(world, 2, device="cuda", dtype=torch.float64)
+        t[rank, 0], t[rank, 1] = alive0, alive1
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        alive_total = float(t.item())
+        per_rank = {"alive_before": [int(v) for v in t[:, 0].tolist()], "alive_after": [int(v) for v in t[:, 1].tolist()]}
+        alive_total = float(t.mean(dim=1).sum().item())
     else:
         alive_total = alive_mean
     value = alive_total * args.steps / (dev_ms * 1e-3)
@@ -405,7 +408,10 @@ def main():
         "cpu_baseline": cpu,
         "world": {"alive_before": alive0, "alive_after": alive1, "alive_at_end": alive, "on_road": on_road,
                   "actors_uploaded": total_actors, "wall_s_timed_region": wall,
-                  "note": "value counts living actors only"},
+                  "note": "value counts living actors only" + ("; alive_* are rank 0's, per_rank has every rank's: strips "
+                          "at the edge of the grid drain towards the middle, and the tick is as long as the fullest rank's"
+                          if world > 1 else ""),
+                  "per_rank": per_rank},
     }
     print(json.dumps(out), flush=True)
     if world > 1:
