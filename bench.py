@@ -187,7 +187,8 @@ def workload_config(args, world=None):
                        f"{args.spinup} spin-up ticks",
            "grid": n, "actors": total, "actors_per_gpu": total // world, "agenda_len": args.agenda_len,
            "spinup_ticks": args.spinup, "l2": "working set per tick >> 126 MB L2 (no flush needed)",
-           "parallelism": (f"{world} ranks = {world} horizontal strips of junction rows of one world; per tick the halo "
+           "parallelism": (f"{world} ranks, {world * args.strips_per_rank} horizontal strips of junction rows of one world dealt "
+                           f"to the ranks in turn; per tick the halo "
                            f"(boundary lanes' rearmost pos-param, boundary junctions' occupancy) and the actors that "
                            f"crossed are exchanged with grouped ncclSend/ncclRecv" if world > 1 else "1 gpu")}
     if note:
@@ -211,6 +212,8 @@ def main():
     ap.add_argument("--cpu-ticks", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reorder-period", type=int, default=384)
+    ap.add_argument("--strips-per-rank", type=int, default=1,
+                    help="multi-GPU: strips of junction rows per rank, dealt in turn (load balance)")
     ap.add_argument("--mig-cap", type=int, default=1 << 24, help="multi-GPU: boundary crossings per neighbour per tick")
     ap.add_argument("--extra-slots", type=int, default=4_000_000, help="multi-GPU: room for actors arriving from other ranks")
     args = ap.parse_args()
@@ -251,7 +254,7 @@ def main():
     else:
         # ONE world, partitioned into horizontal strips; this rank generates and uploads its own actors
         net = synth.grid_network(n_grid)
-        owner = synth.grid_owner(net, world)
+        owner = synth.grid_owner(net, world, args.strips_per_rank)
         ids = synth.actor_ids_of_rank(net, total_actors, owner, rank)
         actors = synth.grid_actors(net, total_actors, agenda_len=args.agenda_len, ids=ids)
         log(f"[bench] rank {rank}: {n_grid}x{n_grid} grid ({net.n_items} items), {actors.n} of {total_actors} actors "

@@ -403,15 +403,18 @@ int synth_locality_keys(int64_t n_items, int64_t n_junctions, const uint8_t* kin
   return 0;
 }
 
-// Owner rank per item for `world` horizontal strips of junction rows: a junction owns its junction
-// lanes; a segment and all its lanes belong to the junction the segment begins at.
-int synth_grid_owner(int64_t n_items, int n, int world, const uint8_t* kind, const int32_t* lane_from_j,
-                     const int32_t* lane_junction, const int32_t* seg_outer_forw, const int32_t* lane_segment,
-                     int32_t* owner) {
-  if (n < 1 || world < 1) return 1;
+// Owner rank per item: world * strips_per_rank horizontal strips of junction rows, dealt to the ranks
+// in turn (with more than one strip per rank every rank gets its share of the busy middle of the grid
+// and of its quiet edges).  A junction owns its junction lanes; a segment and all its lanes belong to
+// the junction the segment begins at.
+int synth_grid_owner(int64_t n_items, int n, int world, int strips_per_rank, const uint8_t* kind,
+                     const int32_t* lane_from_j, const int32_t* lane_junction, const int32_t* seg_outer_forw,
+                     const int32_t* lane_segment, int32_t* owner) {
+  if (n < 1 || world < 1 || strips_per_rank < 1) return 1;
+  const int64_t strips = (int64_t)world * strips_per_rank;
   for (int64_t r = 0; r < n_items; ++r) {
     const int64_t j = item_junction(r, kind, lane_from_j, lane_junction, seg_outer_forw, lane_segment, 1);
-    owner[r] = (int32_t)((j / n) * world / n);
+    owner[r] = (int32_t)(((j / n) * strips / n) % world);   // strips are dealt to the ranks in turn
   }
   return 0;
 }

@@ -104,13 +104,14 @@ def actor_ids_of_rank(net: FlatNetwork, n_actors: int, owner: np.ndarray, rank: 
     return ids[: n.value].copy()
 
 
-def grid_owner(net: FlatNetwork, world: int) -> np.ndarray:
-    """Owner rank of every item for `world` horizontal strips of junction rows.  A junction owns its
-    junction lanes; a segment and all its lanes belong to the junction the segment begins at."""
+def grid_owner(net: FlatNetwork, world: int, strips_per_rank: int = 1) -> np.ndarray:
+    """Owner rank of every item: world * strips_per_rank horizontal strips of junction rows, dealt to the
+    ranks in turn.  A junction owns its junction lanes; a segment and all its lanes belong to the
+    junction the segment begins at."""
     owner = np.empty(net.n_items, np.int32)
-    rc = _lib().synth_grid_owner(C.c_int64(net.n_items), C.c_int(net.grid_n), C.c_int(world), _p(net.kind),
-                                 _p(net.lane_from_j), _p(net.lane_junction), _p(net.seg_outer_forw), _p(net.lane_segment),
-                                 _p(owner))
+    rc = _lib().synth_grid_owner(C.c_int64(net.n_items), C.c_int(net.grid_n), C.c_int(world), C.c_int(strips_per_rank),
+                                 _p(net.kind), _p(net.lane_from_j), _p(net.lane_junction), _p(net.seg_outer_forw),
+                                 _p(net.lane_segment), _p(owner))
     if rc:
         raise RuntimeError(f"synth_grid_owner -> {rc}")
     return owner

@@ -211,13 +211,14 @@ def test_default_locality_keys_without_grid():
         compare(sim, ref, f"tick {t + 1}")
 
 
-@pytest.mark.parametrize("world,n,n_actors", [(2, 6, 2500), (4, 8, 4000), (3, 5, 600)])
-def test_partitioned_world_matches_oracle(world, n, n_actors):
+@pytest.mark.parametrize("world,n,n_actors,strips", [(2, 6, 2500, 1), (4, 8, 4000, 1), (3, 5, 600, 1), (3, 9, 3000, 2),
+                                                     (2, 8, 3000, 4)])
+def test_partitioned_world_matches_oracle(world, n, n_actors, strips):
     """The multi-GPU path (spatial partition, halo + migrant exchange every tick) with all ranks as
     contexts of this process: state, order and population identical to the oracle's single world."""
     from griddy_b200 import synth
     net, actors = crowded_grid(n, n_actors, n_dest=max(4, n), seed=31 + world, agenda_len=4)
-    owner = synth.grid_owner(net, world)
+    owner = synth.grid_owner(net, world, strips)   # strips > 1: interleaved strips, every rank borders every other
     assert len(set(owner.tolist())) == world
     sim = device.PartitionedSimulation(net, actors, owner, world, reorder_period=5)
     ref = Oracle(net, actors)
