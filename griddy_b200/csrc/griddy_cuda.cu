@@ -192,7 +192,10 @@ struct Params {
                              // lane_tail[remote lane] = -2 - index into this array
   int32_t* emig;             // slots that emigrated this tick
   int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
-  uint8_t* mig_send[MAX_RANKS];   // by destination rank: [int32 count, pad][MigRec x mig_cap]
+  // by destination rank and tick parity: that rank's receive buffer for my emigrants, in ITS memory
+  // (peer access over NVLink): [int32 count, pad][MigRec x mig_cap].  k_emig_pack writes there directly.
+  uint8_t* mig_peer[MAX_RANKS][2];
+  int32_t* mig_mine[MAX_RANKS][2];   // headers of my own receive buffers, to reset after unpacking
 };
 
 __device__ __forceinline__ void dev_error(const Params& p, int bit) { atomicOr(&p.scal[SC_ERR], bit); }
@@ -819,11 +822,15 @@ __global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __
   if (i < n) p.occ[junctions[i]] = (int32_t)in[i];
 }
 
-__global__ void k_mig_reset(Params p) {
-  if (threadIdx.x < MAX_RANKS && p.mig_send[threadIdx.x]) *(int32_t*)p.mig_send[threadIdx.x] = 0;
+// After this tick's immigrants are unpacked: empty my receive buffers of this parity.  The sender writes
+// them again two ticks from now, after it has seen the token I send next tick.
+__global__ void k_mig_reset(Params p, int par) {
+  if (threadIdx.x < MAX_RANKS && p.mig_mine[threadIdx.x][par]) *p.mig_mine[threadIdx.x][par] = 0;
 }
 
-// Emigrants -> one record each in the send buffer of the rank that owns their new lane.
+// Emigrants -> one record each, written straight into the receive buffer of the rank that owns their
+// new lane (peer memory over NVLink: remote atomic for the slot, remote stores for the record), so only
+// the actors that actually crossed travel, not a bound-sized message.
 __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
   const int par = tick & 1;
   const int32_t n = p.counters[CNT_STRIDE * par + CNT_EMIG];
@@ -832,8 +839,8 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     if (p.cold[a].dead_mark == tick + 1) continue;   // a ghost's move is void
     const int32_t lane = p.cold[a].container;
     const int32_t to = p.owner[lane];
-    uint8_t* buf = p.mig_send[to];
-    const int32_t at = atomicAdd((int32_t*)buf, 1);
+    uint8_t* buf = p.mig_peer[to][par];
+    const int32_t at = atomicAdd_system((int32_t*)buf, 1);
     if (at >= p.mig_cap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
     MigRec r;
     r.pos_old = p.pos[par][a];
@@ -1073,9 +1080,10 @@ struct Neighbor {
   int32_t* d_exp_items = nullptr;   // my lanes, then my junctions, that `rank` reads
   int32_t* d_imp_junc = nullptr;    // its junctions whose occupancy my actors read
   double *d_halo_send = nullptr, *d_halo_recv = nullptr;
-  uint8_t *d_mig_send = nullptr, *d_mig_recv = nullptr;
+  uint8_t* d_mig_recv[2] = {nullptr, nullptr};   // by tick parity; the neighbour's k_emig_pack writes here
+  uint8_t* peer_mig[2] = {nullptr, nullptr};     // the neighbour's receive buffers for me, mapped into this process
+  int64_t *d_token_out = nullptr, *d_token_in = nullptr;   // NCCL transport: "my emigrants of this tick are written"
   int mig_out = 0, mig_in = 0;      // records per tick at most: a lane lets one actor out per tick
-  size_t out_bytes() const { return MIG_HEADER + (size_t)mig_out * sizeof(MigRec); }
   size_t in_bytes() const { return MIG_HEADER + (size_t)mig_in * sizeof(MigRec); }
 };
 
@@ -1240,7 +1248,8 @@ void mg_reset(Ctx* c) {
   c->p.owner = nullptr;
   c->p.halo_recv = nullptr;
   c->p.my_rank = 0;
-  for (auto& b : c->p.mig_send) b = nullptr;
+  for (auto& b : c->p.mig_peer) b[0] = b[1] = nullptr;
+  for (auto& b : c->p.mig_mine) b[0] = b[1] = nullptr;
   for (auto& n : c->p.mig_cap) n = 0;
 }
 
@@ -1754,8 +1763,7 @@ int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
       const int n = nb.n_exp_lanes + nb.n_exp_junc;
       if (n) k_halo_pack<<<(n + 127) / 128, 128, 0, c->stream>>>(c->p, (int)(tick & 1), nb.d_exp_items, nb.n_exp_lanes, nb.n_exp_junc, nb.d_halo_send);
     }
-    k_mig_reset<<<1, 32, 0, c->stream>>>(c->p);
-    c->launches += 1 + (int64_t)c->mg.nb.size();
+    c->launches += (int64_t)c->mg.nb.size();
   }
   if (ev) cudaEventRecord(ev[1], c->stream);
   return GRIDDY_OK;
@@ -1807,11 +1815,15 @@ int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // needs the migrants
   const Params& p = c->p;
   if (c->mg.on)
     for (Neighbor& nb : c->mg.nb) {
-      k_immig_unpack<<<std::max(1, nb.mig_in / 512), 128, 0, c->stream>>>(p, (int)tick, nb.d_mig_recv, nb.mig_in);
+      k_immig_unpack<<<std::max(1, nb.mig_in / 512), 128, 0, c->stream>>>(p, (int)tick, nb.d_mig_recv[tick & 1], nb.mig_in);
       ++c->launches;
       // upper bound of the slots in use: the neighbour may have filled its buffer
       c->ns_host = (int32_t)std::min<int64_t>(p.cap, (int64_t)c->ns_host + nb.mig_in);
     }
+  if (c->mg.on) {
+    k_mig_reset<<<1, 32, 0, c->stream>>>(p, (int)(tick & 1));
+    ++c->launches;
+  }
   k_link<<<relink_blocks(c), 128, 0, c->stream>>>(p, (int)tick);
   if (ev) cudaEventRecord(ev[5], c->stream);
   ++c->launches;
@@ -1840,8 +1852,11 @@ int exchange_nccl(Ctx* c, bool halo) {
       if (out) NCCL_TRY(c, api->Send(nb.d_halo_send, out, NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
       if (in) NCCL_TRY(c, api->Recv(nb.d_halo_recv, in, NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
     } else {
-      NCCL_TRY(c, api->Send(nb.d_mig_send, nb.out_bytes(), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
-      NCCL_TRY(c, api->Recv(nb.d_mig_recv, nb.in_bytes(), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
+      // the records themselves were written into the neighbour's memory by k_emig_pack; this token
+      // orders them: it leaves after my kernel has completed, and what arrives tells me the same
+      if (!nb.peer_mig[0]) return fail(c, GRIDDY_ERR_BAD_STATE, "migrant buffers of rank " + std::to_string(nb.rank) + " are not mapped (griddy_mg_ipc_import)");
+      NCCL_TRY(c, api->Send(nb.d_token_out, sizeof(int64_t), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
+      NCCL_TRY(c, api->Recv(nb.d_token_in, sizeof(int64_t), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
     }
   }
   NCCL_TRY(c, api->GroupEnd());
@@ -1875,14 +1890,12 @@ int exchange_local(Ctx* src, bool halo) {
     for (Neighbor& b : dst->mg.nb)
       if (b.rank == src->mg.rank) back = &b;
     if (!back) return fail(src, GRIDDY_ERR_BAD_STATE, "neighbour lists are not symmetric");
-    CUDA_TRY(dst, cudaSetDevice(dst->device));
-    CUDA_TRY(dst, cudaStreamWaitEvent(dst->stream, src->mg.ev_ready, 0));
-    const void* from = halo ? (const void*)nb.d_halo_send : (const void*)nb.d_mig_send;
-    void* to = halo ? (void*)back->d_halo_recv : (void*)back->d_mig_recv;
-    const size_t bytes = halo ? (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double) : nb.out_bytes();
     if (nb.n_exp_lanes + nb.n_exp_junc != back->n_imp_lanes + back->n_imp_junc || nb.mig_out != back->mig_in)
       return fail(src, GRIDDY_ERR_BAD_STATE, "exchange plans of two neighbours disagree");
-    if (bytes) CUDA_TRY(dst, cudaMemcpyPeerAsync(to, dst->device, from, src->device, bytes, dst->stream));
+    CUDA_TRY(dst, cudaSetDevice(dst->device));
+    CUDA_TRY(dst, cudaStreamWaitEvent(dst->stream, src->mg.ev_ready, 0));   // migrants: src's kernel wrote them in place
+    const size_t bytes = (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double);
+    if (halo && bytes) CUDA_TRY(dst, cudaMemcpyPeerAsync(back->d_halo_recv, dst->device, nb.d_halo_send, src->device, bytes, dst->stream));
   }
   return GRIDDY_OK;
 }
@@ -2240,11 +2253,14 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     off += L.imp_l.size() + L.imp_j.size();
     nb.mig_out = (int)std::min<int64_t>(mig_cap, mg_count_feeders(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), owner, rank, r));
     nb.mig_in = (int)std::min<int64_t>(mig_cap, mg_count_feeders(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), owner, r, rank));
-    TRY(mg_alloc(c, &nb.d_mig_send, nb.out_bytes()));
-    TRY(mg_alloc(c, &nb.d_mig_recv, nb.in_bytes()));
-    CUDA_TRY(c, cudaMemset(nb.d_mig_send, 0, nb.out_bytes()));
-    CUDA_TRY(c, cudaMemset(nb.d_mig_recv, 0, nb.in_bytes()));
-    c->p.mig_send[r] = nb.d_mig_send;
+    for (int par = 0; par < 2; ++par) {   // plain cudaMalloc: these are shared with the neighbour through cudaIpc
+      TRY(mg_alloc(c, &nb.d_mig_recv[par], nb.in_bytes()));
+      CUDA_TRY(c, cudaMemset(nb.d_mig_recv[par], 0, nb.in_bytes()));
+      c->p.mig_mine[r][par] = (int32_t*)nb.d_mig_recv[par];
+    }
+    TRY(mg_alloc(c, &nb.d_token_out, 1));
+    TRY(mg_alloc(c, &nb.d_token_in, 1));
+    CUDA_TRY(c, cudaMemset(nb.d_token_out, 0, sizeof(int64_t)));
     c->p.mig_cap[r] = nb.mig_out;
     m.nb.push_back(nb);
   }
@@ -2296,6 +2312,56 @@ int griddy_mg_connect_nccl(void* ctx, const uint8_t* id128) {
   return GRIDDY_OK;
 }
 
+int griddy_mg_neighbors(void* ctx, int32_t* ranks, int32_t* n) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->mg.on || !n) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_neighbors before mg_configure");
+  *n = (int32_t)c->mg.nb.size();
+  if (ranks)
+    for (size_t k = 0; k < c->mg.nb.size(); ++k) ranks[k] = c->mg.nb[k].rank;
+  return GRIDDY_OK;
+}
+
+// One process per GPU: the receive buffers for `from_rank`'s emigrants are handed to that rank as
+// cudaIpc handles (2 x 64 bytes, one per tick parity), which it maps with griddy_mg_ipc_import.
+int griddy_mg_ipc_export(void* ctx, int32_t from_rank, uint8_t* handles128) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->mg.on || !handles128) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_ipc_export before mg_configure");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  for (Neighbor& nb : c->mg.nb)
+    if (nb.rank == from_rank) {
+      for (int par = 0; par < 2; ++par) {
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(c, cudaIpcGetMemHandle(&h, nb.d_mig_recv[par]));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handles128 + 64 * par, &h, 64);
+      }
+      return GRIDDY_OK;
+    }
+  return fail(c, GRIDDY_ERR_BAD_ARG, "rank " + std::to_string(from_rank) + " is not a neighbour");
+}
+
+int griddy_mg_ipc_import(void* ctx, int32_t to_rank, const uint8_t* handles128) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->mg.on || !handles128) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_ipc_import before mg_configure");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  for (Neighbor& nb : c->mg.nb)
+    if (nb.rank == to_rank) {
+      for (int par = 0; par < 2; ++par) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles128 + 64 * par, 64);
+        void* ptr = nullptr;
+        CUDA_TRY(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        nb.peer_mig[par] = (uint8_t*)ptr;
+        c->p.mig_peer[to_rank][par] = (uint8_t*)ptr;
+      }
+      return GRIDDY_OK;
+    }
+  return fail(c, GRIDDY_ERR_BAD_ARG, "rank " + std::to_string(to_rank) + " is not a neighbour");
+}
+
 int griddy_mg_connect_local(void** ctxs, int32_t n) {
   if (!ctxs || n < 1 || n > MAX_RANKS) return GRIDDY_ERR_BAD_ARG;
   std::vector<Ctx*> cs((Ctx**)ctxs, (Ctx**)ctxs + n);
@@ -2307,9 +2373,16 @@ int griddy_mg_connect_local(void** ctxs, int32_t n) {
     for (Ctx* d : cs)
       if (d->device != c->device) {
         cudaSetDevice(c->device);
-        cudaDeviceEnablePeerAccess(d->device, 0);   // best effort; cudaMemcpyPeerAsync stages through the host otherwise
+        const cudaError_t e = cudaDeviceEnablePeerAccess(d->device, 0);
         cudaGetLastError();
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(c, GRIDDY_ERR_CUDA, "no peer access between devices " + std::to_string(c->device) + " and " + std::to_string(d->device));
       }
+    // same process: the neighbours' receive buffers are directly addressable
+    for (Neighbor& nb : c->mg.nb)
+      for (Neighbor& back : cs[nb.rank]->mg.nb)
+        if (back.rank == c->mg.rank)
+          for (int par = 0; par < 2; ++par) c->p.mig_peer[nb.rank][par] = nb.peer_mig[par] = back.d_mig_recv[par];
   }
   return GRIDDY_OK;
 }

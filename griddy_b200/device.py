@@ -26,7 +26,8 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_set_locality_keys", "griddy_set_reorder_period", "griddy_slots_in_use",
            "griddy_debug_sort_pairs", "griddy_count_alive", "griddy_mg_configure", "griddy_mg_set_global_ids",
            "griddy_mg_nccl_unique_id", "griddy_mg_connect_nccl", "griddy_mg_connect_local", "griddy_mg_step_local",
-           "griddy_mg_plan", "griddy_download_local")
+           "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
+           "griddy_mg_ipc_import")
 
 
 class GriddyCudaError(RuntimeError):
@@ -211,6 +212,22 @@ def connect_nccl(sim: "Simulation"):
     dist.broadcast(t, src=0)
     buf = t.cpu().numpy()
     sim._chk(lib().griddy_mg_connect_nccl(sim.h, _p(np.ascontiguousarray(buf))))
+    # the buffers each neighbour writes its emigrants into: cudaIpc handles, rank -> rank
+    nbs = np.zeros(8, np.int32)
+    n = C.c_int32(0)
+    sim._chk(lib().griddy_mg_neighbors(sim.h, _p(nbs), C.byref(n)))
+    mine = {}
+    for q in nbs[: n.value].tolist():
+        h = np.zeros(128, np.uint8)
+        sim._chk(lib().griddy_mg_ipc_export(sim.h, C.c_int32(q), _p(h)))
+        mine[q] = h.tobytes()
+    everyone = [None] * dist.get_world_size()
+    dist.all_gather_object(everyone, mine)
+    for q in nbs[: n.value].tolist():
+        h = np.frombuffer(everyone[q][rank], np.uint8).copy()      # q's buffers for what comes from me
+        sim._chk(lib().griddy_mg_ipc_import(sim.h, C.c_int32(q), _p(h)))
+    dist.barrier()
+
 
 
 class PartitionedSimulation:
