@@ -212,12 +212,14 @@ def main():
     ap.add_argument("--cpu-ticks", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reorder-period", type=int, default=384)
-    ap.add_argument("--strips-per-rank", type=int, default=1,
-                    help="multi-GPU: strips of junction rows per rank, dealt in turn (load balance)")
+    ap.add_argument("--strips-per-rank", type=int, default=0,
+                    help="multi-GPU: strips of junction rows per rank, dealt in turn (load balance); 0 = 2 beyond two GPUs")
     ap.add_argument("--mig-cap", type=int, default=1 << 24, help="multi-GPU: boundary crossings per neighbour per tick")
     ap.add_argument("--extra-slots", type=int, default=4_000_000, help="multi-GPU: room for actors arriving from other ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.strips_per_rank <= 0:   # edge strips drain towards the middle of the grid: give every rank some of both
+        args.strips_per_rank = 2 if args.gpus > 2 else 1
     os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout, which carries the one JSON line
 
     if args.impl == "reference":
