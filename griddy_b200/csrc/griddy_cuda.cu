@@ -459,7 +459,9 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 // arrays.  Any other actor — a few percent — would drag its whole warp through chains of dependent
 // gathers, so its slot is appended to the slow list instead (block-aggregated: one global atomic per
 // block) and k_slow runs the full advance$ for it with one thread per listed actor.
-constexpr int ADV_UNROLL = 4;
+#ifndef ADV_UNROLL
+#define ADV_UNROLL 3
+#endif
 constexpr int ADV_THREADS = 256;
 
 __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
