@@ -75,1000 +75,18 @@
 #include "griddy_cuda.h"
 #include "radix_sort.cuh"
 
+// The device code lives in the .cuh files next to this one, included in dependency order:
+#include "records.cuh"
+#include "advance.cuh"
+#include "lanes.cuh"
+#include "setup.cuh"
+#include "multi_gpu.cuh"
+#include "reorder.cuh"
+#include "readback.cuh"
+
+using namespace griddy;
+
 namespace {
-
-constexpr uint32_t ST_ALIVE = 1u, ST_ONROAD = 2u, ST_SIDE = 4u;
-constexpr int ST_RS_SHIFT = 3;    // 2 bits: GRIDDY_ROUTE_*
-constexpr int ST_HEAD_SHIFT = 5;  // 2 bits: 0 no head, 1 sleep-for, 2 travel-to
-constexpr uint32_t ST_MOVED = 128u;    // changed lane / road side this tick (cleared by k_unlink / k_link)
-constexpr uint32_t ST_CLASS_P = 256u;  // landing stamp: came from a lane visited before the segment
-constexpr uint32_t ST_ARRIVE = 512u;   // the route head is (arrive-at _): aux == HOP_ARRIVE
-constexpr int HEAD_NONE = 0, HEAD_SLEEP = 1, HEAD_TRAVEL = 2;
-constexpr int HOP_ARRIVE = -1;
-
-constexpr uint32_t ST_EMIG = 1024u;     // multi-GPU: moved onto a lane another rank owns (this slot dies in k_unlink)
-constexpr uint32_t ST_IMMIG = 2048u;    // multi-GPU: arrived from another rank this tick (cleared in k_link)
-
-constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
-              DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32, DEV_ERR_MIG_OVERFLOW = 64,
-              DEV_ERR_MIG_AGENDA = 128;
-
-// Params::counters[parity][...]
-constexpr int CNT_EMIG = 0, CNT_TOUCHED = 1, CNT_SLOW = 2, CNT_STRIDE = 4;
-// device scalars (Params::scal)
-constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_COUNT = 4;
-constexpr int MAX_RANKS = 8;     // one box
-constexpr int MIG_ITEMS = 4;     // agenda items a migrating actor can carry
-
-// st and ahead of a slot share an 8-byte word: every kernel that walks a lane needs both.
-struct __align__(8) SA {
-  uint32_t st;
-  int32_t ahead;
-};
-
-// Everything about a slot that only matters when its actor does something rare (changes lane, wakes,
-// starts or ends a route), in one 64-byte record — one DRAM burst instead of a dozen sectors.
-struct __align__(16) Cold {
-  // travels with the actor
-  int32_t container;                  // lane (on road) or segment (off road)
-  int32_t agenda_cur, route_cur;      // agenda head (index into the item arrays), route head (explicit routes)
-  int32_t gid;                        // the actor's id (global id on a partitioned world)
-  int32_t behind;                     // slot of the next actor behind on the lane (-1 at the rear)
-  int32_t hop;                        // head of the route: lane of (turn-onto lane), or -1 for (arrive-at _)
-  int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions
-  // list surgery of the current tick
-  int32_t mv_old;                     // where a mover came from: lane, or ~segment
-  int32_t spare[2];
-  int32_t inbox_next, outbox_next, ghost_next;
-  int32_t dead_mark;                  // tick+1 when the actor was found to be a ghost during `tick`
-};
-// The rest of an actor's rarely read state, also one burst.
-struct __align__(16) ColdF {
-  double arrive;            // target of the (arrive-at _) that ends the current route
-  double land_pos;          // landing stamp (with land_tick, land_lane), see "processing order"
-  double speed, speed_dt;   // max-speed and fl(max-speed * dt)
-  int32_t agenda_beg, agenda_end;     // the actor's agenda in the item arrays
-  int32_t land_tick, land_lane;
-  int32_t pad[4];
-};
-static_assert(sizeof(Cold) == 64 && sizeof(ColdF) == 64, "cold records are one DRAM burst each");
-
-// The static network, one 32-byte record per registered item: a lane change reads its target lane's
-// kind, length, successor and junctions from one sector.
-struct __align__(16) Item {
-  double len;             // lanes: length (host-computed, spatial.scm:28-46)
-  int32_t link;           // segment lane: its segment; junction lane: the lane it leads onto; segment: outer forw-side lane
-  int32_t link2;          // junction lane: its junction; segment: outer back-side lane
-  int32_t from_j, to_j;   // grid routing: junction a segment lane leaves / reaches
-  uint32_t loc_key;       // locality key for the reorder (default: the registration index)
-  uint8_t kind, dir;
-  uint16_t pad;
-};
-// Per-lane list heads: rearmost actor, and this tick's entrants, leavers and ghosts.
-struct __align__(16) LaneDyn {
-  int32_t tail;      // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
-  int32_t inbox, outbox, ghosts;
-  int32_t mark;      // tick+1 once the lane is on this tick's touched list
-  int32_t junction;  // junction lanes: their junction (whose occupancy they count towards), else -1
-  int32_t pad[2];
-};
-static_assert(sizeof(Item) == 32 && sizeof(LaneDyn) == 32, "one sector per record");
-
-struct Params {
-  // network, by registration index
-  int64_t n_items;
-  Item* item;
-  LaneDyn* lane;
-  int32_t* occ;       // actors on a junction's lanes (route.scm:98-104); compact, so that it lives in L2
-  int32_t grid_n;
-  const int32_t* turn4;
-  // slots
-  int32_t cap;     // allocated slots
-  int32_t* scal;   // SC_*: device error bits, slots in use, live actors counted by the reorder
-  SA* sa;          // {st, ahead}: one 8-byte load per actor
-  double* pos[2];
-  double *delta, *buf;
-  int32_t* aux;   // sleeping: remaining time; travelling: head route step (lane, or -1 arrive-at)
-  int32_t* tj;    // junction of the lane the route head turns onto, -1 if that is not a junction lane
-  Cold* cold;
-  ColdF* coldf;
-  // agenda items (immutable; actors that arrive from another rank append theirs)
-  int64_t n_actors;
-  uint8_t* item_kind;
-  int32_t *item_sleep, *item_seg;
-  uint8_t* item_side;
-  double* item_pos;
-  int32_t icap;   // item capacity
-  const int64_t* route_off;   // null: grid routing table
-  const int32_t* route_lane;
-  // per-tick scratch, by slot
-  int32_t *touched, *slow;
-  int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, touched lanes, deferred actors
-  double dt, two_size;
-  // multi-GPU (owner == null on a single GPU): spatial partition, see "Multi-GPU" below
-  const int32_t* owner;      // rank that owns each item
-  int32_t my_rank;
-  const double* halo_recv;   // rearmost positive pos-param of the remote lanes my actors can enter;
-                             // lane_tail[remote lane] = -2 - index into this array
-  int32_t* emig;             // slots that emigrated this tick
-  int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
-  // by destination rank and tick parity: that rank's receive buffer for my emigrants, in ITS memory
-  // (peer access over NVLink): [int32 count, pad][MigRec x mig_cap].  k_emig_pack writes there directly.
-  uint8_t* mig_peer[MAX_RANKS][2];
-  int32_t* mig_mine[MAX_RANKS][2];   // headers of my own receive buffers, to reset after unpacking
-};
-
-__device__ __forceinline__ void dev_error(const Params& p, int bit) { atomicOr(&p.scal[SC_ERR], bit); }
-
-// location.scm:16-24 through the uploaded per-segment table
-__device__ __forceinline__ int32_t outer_lane(const Params& p, int32_t seg, uint32_t side) {
-  return side ? p.item[seg].link2 : p.item[seg].link;
-}
-
-// Dimension-ordered next hop on procedural grids (include/griddy_cuda.h, griddy_set_routing_grid):
-// from segment lane `lane` towards the lane that leaves junction dest_from_j for junction dest_to_j.
-__device__ int32_t grid_next_hop(const Params& p, int32_t lane, int32_t lane_to_j, int32_t dest_from_j, int32_t dest_to_j) {
-  const int n = p.grid_n;
-  const int32_t J = lane_to_j, E = dest_from_j;
-  int h;
-  if (J == E) {
-    const int32_t T = dest_to_j;
-    h = (T / n != E / n) ? (T / n > E / n ? 0 : 1) : (T % n > E % n ? 2 : 3);
-  } else if (J / n != E / n) {
-    h = E / n > J / n ? 0 : 1;
-  } else {
-    h = E % n > J % n ? 2 : 3;
-  }
-  return p.turn4[4 * (int64_t)lane + h];
-}
-
-// Head of the route after the actor has reached `lane` (route.scm:48-51 evaluated lazily); `it` is
-// lane's record, k holds the route's destination.
-__device__ int32_t route_head_on(const Params& p, int32_t lane, const Item& it, const Cold& k, int32_t item, int32_t* rc) {
-  if (p.route_off) {
-    const int64_t c = *rc;
-    return c < p.route_off[item + 1] ? p.route_lane[c] : HOP_ARRIVE;
-  }
-  if (lane == k.dest_lane) return HOP_ARRIVE;
-  if (it.kind == GRIDDY_JUNCTION_LANE) return it.link;
-  const int32_t hop = grid_next_hop(p, lane, it.to_j, k.dest_from_j, k.dest_to_j);
-  if (hop < 0) dev_error(p, DEV_ERR_NO_ROUTE);
-  return hop;
-}
-
-// The junction whose occupancy gates a (turn-onto lane) head (route.scm:105-108), or -1.  On a
-// partitioned world a junction another rank owns carries TJ_REMOTE: its occupancy arrives with the
-// halo, which k_advance does not wait for, so such actors are left to k_slow.
-constexpr int32_t TJ_REMOTE = 1 << 30;
-__device__ __forceinline__ int32_t tag_junction(const Params& p, int32_t j) {
-  return (j >= 0 && p.owner && p.owner[j] != p.my_rank) ? (j | TJ_REMOTE) : j;
-}
-__device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop) {
-  return tag_junction(p, (hop >= 0 && p.item[hop].kind == GRIDDY_JUNCTION_LANE) ? p.item[hop].link2 : -1);
-}
-
-// New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
-__device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_t ac, int32_t* aux) {
-  if (ac >= p.coldf[a].agenda_end) { *aux = 0; return HEAD_NONE; }
-  if (p.item_kind[ac] == GRIDDY_SLEEP_FOR) { *aux = p.item_sleep[ac]; return HEAD_SLEEP; }
-  *aux = 0;
-  return HEAD_TRAVEL;
-}
-
-// Lanes whose list must be rebuilt this tick are collected per block in shared memory and flushed to
-// Params::touched with one global atomic per block (a same-address atomic per lane would serialise).
-struct TouchSink {
-  int32_t* list;   // shared, SINK_CAP entries
-  int32_t* count;  // shared
-};
-constexpr int SLOW_THREADS = 128;
-constexpr int SINK_CAP = 3 * SLOW_THREADS;   // an actor touches at most its old lane, its new lane and a ghost's lane
-
-__device__ __forceinline__ void mark_touched(const Params& p, int32_t lane, int tick, const TouchSink& sink) {
-  if (atomicExch(&p.lane[lane].mark, tick + 1) != tick + 1) sink.list[atomicAdd(sink.count, 1)] = lane;
-}
-
-__device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
-  p.cold[a].inbox_next = atomicExch(&p.lane[lane].inbox, a);
-  mark_touched(p, lane, tick, sink);
-}
-
-__device__ __forceinline__ void leave_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
-  p.cold[a].outbox_next = atomicExch(&p.lane[lane].outbox, a);
-  mark_touched(p, lane, tick, sink);
-}
-
-// ------------------------------------------------------------------------------------------------
-// route-step/turn-onto$ (route.scm:92-135) for an actor that reaches the end of its lane and is not
-// held by a full junction: carry the rest of the tick over into the target lane, pop the route.
-// Reads one cold record of the actor and one record of the target lane; returns the new pos-param.
-__device__ __forceinline__ double turn_onto(const Params& p, const int a, const int tick, const uint32_t st,
-                                            const double cur, const double* __restrict__ pos_old, const TouchSink& sink) {
-  Cold k = p.cold[a];
-  const ColdF f = p.coldf[a];
-  const int32_t target = k.hop, lane = k.container;
-  const Item it = p.item[target];
-  const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), f.speed);
-  const double time_remaining = __dsub_rn(p.dt, time_spent);
-  const double tinv = __ddiv_rn(1.0, it.len);
-  const double tbuf = __ddiv_rn(p.two_size, it.len);
-  double tnext = __dmul_rn(__dmul_rn(f.speed, time_remaining), tinv);   // (+ 0 delta)
-  int32_t x = p.lane[target].tail;
-  const bool remote = x <= -2;   // multi-GPU: another rank owns the target lane
-  if (remote) {                  // its smallest key in (0, ...] came with the halo (+inf: none)
-    const double tlead = p.halo_recv[-2 - x];
-    if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
-  } else {
-    while (x >= 0 && !(pos_old[x] > 0.0)) x = p.sa[x].ahead;   // smallest key in (0, ...]
-    if (x >= 0) {
-      const double tlead = pos_old[x];
-      if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
-    }
-  }
-  int32_t rc = p.route_off ? k.route_cur + 1 : 0;
-  const int32_t nhop = route_head_on(p, target, it, k, k.agenda_cur, &rc);
-  p.cold[a].route_cur = rc;
-  p.cold[a].hop = nhop;
-  p.cold[a].container = target;
-  p.cold[a].mv_old = lane;
-  p.tj[a] = junction_of_hop(p, nhop);
-  p.delta[a] = __dmul_rn(f.speed_dt, tinv);
-  p.buf[a] = tbuf;
-  p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u);
-  if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
-  else enter_lane(p, a, target, tick, sink);
-  leave_lane(p, a, lane, tick, sink);
-  return tnext;
-}
-
-// ------------------------------------------------------------------------------------------------
-// advance$ for one actor (simulate.scm:93-111) with route.scm:53-141 inlined.  `a` is a slot; st,
-// ah, cur, dlt, buf, lead were loaded by the caller (ah = -1 and lead = 0 when there is no leader).
-// Returns the actor's new pos-param; everything else that changes is written here.
-__device__ __forceinline__ double advance_actor(const Params& p, const int a, const int tick, const uint32_t st,
-                                                int32_t ah, const double cur, const double dlt,
-                                                const double buf, double lead,
-                                                const double* __restrict__ pos_old, const TouchSink& sink) {
-  const int head = (st >> ST_HEAD_SHIFT) & 3;
-  const int rs = (st >> ST_RS_SHIFT) & 3;
-
-  // nearest actor ahead on the lane (bbtree-find-min's only candidate, util.scm:152-162), skipping
-  // ghosts: leaders that this actor replaced with an equal key at the end of the previous tick
-  if (ah >= 0 && lead == cur) {
-    const int32_t lane = p.cold[a].container;
-    do {
-      if (atomicExch(&p.cold[ah].dead_mark, tick + 1) != tick + 1)   // the first to notice hands it to k_relink
-        p.cold[ah].ghost_next = atomicExch(&p.lane[lane].ghosts, ah);
-      ah = p.sa[ah].ahead;
-      if (ah >= 0) lead = pos_old[ah];
-    } while (ah >= 0 && lead == cur);
-    mark_touched(p, lane, tick, sink);
-  }
-
-  if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {   // advance-on-route$  route.scm:137-141
-    // get-pos-param-next on the current lane (route.scm:53-74)
-    double next = __dadd_rn(cur, dlt);
-    if (ah >= 0 && lead > cur && lead <= __dadd_rn(next, buf)) next = __dsub_rn(lead, buf);
-    if (st & ST_ARRIVE) {   // route-step/arrive-at$  route.scm:76-90
-      const double target = p.coldf[a].arrive;
-      if (!(next >= target)) return next;
-      const bool back = target < cur;
-      p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_ARRIVE)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u);
-      if (back) {   // jumped back past other residents: re-insert by key
-        const int32_t lane = p.cold[a].container;
-        p.cold[a].mv_old = lane;
-        leave_lane(p, a, lane, tick, sink);
-        enter_lane(p, a, lane, tick, sink);
-      }
-      return target;
-    }
-    // route-step/turn-onto$  route.scm:92-135
-    if (!(next >= 1.0)) return next;
-    const int32_t tj = p.tj[a];   // junction-full?  route.scm:98-108 (k_advance has usually answered this)
-    if (tj >= 0 && p.occ[tj & ~TJ_REMOTE] > 0) return cur;   // waiting
-    return turn_onto(p, a, tick, st, cur, pos_old, sink);
-  }
-
-  if (rs == GRIDDY_ROUTE_NONE && head == HEAD_NONE) return cur;   // do-nothing$  simulate.scm:70-72
-  if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {            // sleep$  simulate.scm:74-78
-    const int32_t t = p.aux[a];
-    if (t == 0) {
-      const int32_t ac = p.cold[a].agenda_cur + 1;
-      int32_t aux;
-      const uint32_t h = load_head(p, a, ac, &aux);
-      p.cold[a].agenda_cur = ac;
-      p.aux[a] = aux;
-      p.sa[a].st = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
-    } else {
-      p.aux[a] = t - 1;
-    }
-    return cur;
-  }
-  if (head != HEAD_TRAVEL) {   // simulate.scm:105-111 has no clause for these
-    dev_error(p, DEV_ERR_NO_CLAUSE);
-    return cur;
-  }
-
-  const int32_t item = p.cold[a].agenda_cur;
-  if (rs == GRIDDY_ROUTE_NONE) {   // begin-route$  simulate.scm:80-85
-    if (st & ST_ONROAD) { dev_error(p, DEV_ERR_BEGIN_ON_ROAD); return cur; }
-    const int32_t seg = p.cold[a].container;
-    const int32_t init_lane = outer_lane(p, seg, st & ST_SIDE);
-    const int32_t dest_lane = outer_lane(p, p.item_seg[item], p.item_side[item]);
-    if (init_lane < 0 || dest_lane < 0) { dev_error(p, DEV_ERR_NO_LANE); return cur; }
-    // off-road->on-road  location.scm:49-57
-    const double init_pos = p.item[init_lane].dir ? __dsub_rn(1.0, cur) : cur;
-    const double ipos = p.item_pos[item];
-    const double dest_pos = p.item[dest_lane].dir ? __dsub_rn(1.0, ipos) : ipos;
-    int32_t rc = p.route_off ? (int32_t)p.route_off[item] : 0;
-    const Item init_it = p.item[init_lane], dest_it = p.item[dest_lane];
-    Cold k;
-    k.dest_lane = dest_lane;
-    k.dest_from_j = dest_it.from_j;
-    k.dest_to_j = dest_it.to_j;
-    const int32_t hop = route_head_on(p, init_lane, init_it, k, item, &rc);
-    const double len = init_it.len;
-    p.cold[a].route_cur = rc;
-    p.cold[a].dest_lane = dest_lane;
-    p.cold[a].dest_from_j = k.dest_from_j;
-    p.cold[a].dest_to_j = k.dest_to_j;
-    p.coldf[a].arrive = dest_pos;
-    p.cold[a].hop = hop;
-    p.tj[a] = junction_of_hop(p, hop);
-    p.delta[a] = __dmul_rn(p.coldf[a].speed_dt, __ddiv_rn(1.0, len));
-    p.buf[a] = __ddiv_rn(p.two_size, len);
-    p.cold[a].container = init_lane;
-    p.cold[a].mv_old = ~seg;
-    p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
-              ST_ONROAD | ST_MOVED | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);
-    enter_lane(p, a, init_lane, tick, sink);
-    return init_pos;
-  }
-
-  // end-route$  simulate.scm:87-91   (rs == GRIDDY_ROUTE_DONE)
-  const int32_t lane = p.cold[a].container;
-  if (p.item[lane].kind != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); return cur; }
-  const int32_t seg = p.item[lane].link;
-  const uint32_t dir = p.item[lane].dir;
-  const int32_t ac = item + 1;
-  int32_t aux;
-  const uint32_t h = load_head(p, a, ac, &aux);
-  p.cold[a].agenda_cur = ac;
-  p.aux[a] = aux;
-  p.cold[a].container = seg;
-  p.cold[a].mv_old = lane;
-  // landing stamp: where this actor sits in the segment's consed list (core.scm:169-171)
-  p.coldf[a].land_tick = tick + 1;
-  p.coldf[a].land_lane = lane;
-  p.coldf[a].land_pos = cur;
-  uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE);
-  ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
-  p.sa[a].st = ns;
-  leave_lane(p, a, lane, tick, sink);
-  return dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
-}
-
-// k_advance: the common cases of advance$ for every slot; everything else is deferred to k_slow.
-// ADV_UNROLL slots per thread, strided by the block so that every load is coalesced.  The loads of all
-// ADV_UNROLL actors are issued before the first use (one slot per thread leaves too few bytes in
-// flight to cover HBM latency): first st / ahead / pos, then the leaders' pos-params (a gather that
-// the slot order keeps inside the same or a neighbouring cache line) with delta / buf.
-// Handled here: an actor on its route that has no (arrive-at _) head and either stays on its lane
-// or waits at its end for a full junction (the junction-occupancy table is small enough to live in
-// L2); a sleeper whose time has not run out; an idle actor.  These touch only the hot
-// arrays.  Any other actor — a few percent — would drag its whole warp through chains of dependent
-// gathers, so its slot is appended to the slow list instead (block-aggregated: one global atomic per
-// block) and k_slow runs the full advance$ for it with one thread per listed actor.
-#ifndef ADV_UNROLL
-#define ADV_UNROLL 3
-#endif
-constexpr int ADV_THREADS = 256;
-
-__global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
-  __shared__ int32_t s_list[ADV_THREADS * ADV_UNROLL];
-  __shared__ int32_t s_n, s_base;
-  const int par = tick & 1;
-  int32_t* counters = p.counters + CNT_STRIDE * par;
-  if (blockIdx.x == 0 && threadIdx.x < CNT_STRIDE) p.counters[CNT_STRIDE * (par ^ 1) + threadIdx.x] = 0;
-  const int n = p.scal[SC_NSLOTS];
-  const int base = blockIdx.x * (ADV_THREADS * ADV_UNROLL) + threadIdx.x;
-  if (base - (int)threadIdx.x >= n) return;
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  const double* __restrict__ pos_old = p.pos[par];
-  double* __restrict__ pos_new = p.pos[par ^ 1];
-
-  uint32_t st[ADV_UNROLL];
-  int32_t ah[ADV_UNROLL], slp[ADV_UNROLL], tj[ADV_UNROLL];
-  double cur[ADV_UNROLL], dlt[ADV_UNROLL], buf[ADV_UNROLL], lead[ADV_UNROLL];
-#pragma unroll
-  for (int k = 0; k < ADV_UNROLL; ++k) {
-    const int a = base + k * ADV_THREADS;
-    const bool in = a < n;
-    const SA sa = in ? p.sa[a] : SA{0u, -1};
-    st[k] = sa.st;
-    ah[k] = sa.ahead;
-    cur[k] = in ? pos_old[a] : 0.0;
-  }
-#pragma unroll
-  for (int k = 0; k < ADV_UNROLL; ++k) {
-    const int a = base + k * ADV_THREADS;
-    const bool alive = st[k] & ST_ALIVE;
-    const bool on_road = alive && (st[k] & ST_ONROAD);
-    if (!on_road) ah[k] = -1;   // an off-road actor's ahead is stale
-    const int rs = (st[k] >> ST_RS_SHIFT) & 3, head = (st[k] >> ST_HEAD_SHIFT) & 3;
-    const bool on_route = on_road && rs == GRIDDY_ROUTE_SOME;
-    lead[k] = ah[k] >= 0 ? pos_old[ah[k]] : 0.0;
-    dlt[k] = on_route ? p.delta[a] : 0.0;
-    buf[k] = on_route ? p.buf[a] : 0.0;
-    tj[k] = (on_route && !(st[k] & ST_ARRIVE)) ? p.tj[a] : -1;
-    slp[k] = (alive && rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) ? p.aux[a] : 0;
-  }
-#pragma unroll
-  for (int k = 0; k < ADV_UNROLL; ++k) {
-    const int a = base + k * ADV_THREADS;
-    if (!(st[k] & ST_ALIVE)) continue;
-    const int rs = (st[k] >> ST_RS_SHIFT) & 3, head = (st[k] >> ST_HEAD_SHIFT) & 3;
-    bool slow = ah[k] >= 0 && lead[k] == cur[k];   // equal key ahead: a ghost to remove
-    bool turn = false;                              // the only thing left to do is route-step/turn-onto$
-    double np = cur[k];
-    if (!slow) {
-      if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {
-        // get-pos-param-next on the current lane (route.scm:53-74)
-        double next = __dadd_rn(cur[k], dlt[k]);
-        if (ah[k] >= 0 && lead[k] > cur[k] && lead[k] <= __dadd_rn(next, buf[k])) next = __dsub_rn(lead[k], buf[k]);
-        if (st[k] & ST_ARRIVE) slow = true;
-        else if (!(next >= 1.0)) np = next;
-        else if (tj[k] >= TJ_REMOTE) slow = true;                  // the junction's occupancy is still on its way (halo)
-        else if (tj[k] >= 0 && p.occ[tj[k]] > 0) np = cur[k];   // waiting for a full junction  route.scm:98-111
-        else slow = turn = true;                                   // turns onto the next lane
-      } else if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {   // sleep$, time left  simulate.scm:77
-        if (slp[k] == 0) slow = true;
-        else p.aux[a] = slp[k] - 1;
-      } else if (!(rs == GRIDDY_ROUTE_NONE && head == HEAD_NONE)) {   // not do-nothing$ either
-        slow = true;
-      }
-    }
-    if (slow) s_list[atomicAdd(&s_n, 1)] = turn ? ~a : a;   // ~slot: k_slow goes straight to turn_onto
-    else pos_new[a] = np;
-  }
-  __syncthreads();
-  const int ns = s_n;
-  if (ns == 0) return;
-  if (threadIdx.x == 0) s_base = atomicAdd(&counters[CNT_SLOW], ns);
-  __syncthreads();
-  for (int i = threadIdx.x; i < ns; i += ADV_THREADS) p.slow[s_base + i] = s_list[i];
-}
-
-// k_slow: the full advance$ for the actors k_advance deferred, one thread per actor, so that the
-// chains of dependent gathers of 32 such actors overlap instead of stalling 31 idle lanes.
-__global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
-  __shared__ int32_t s_touched[SINK_CAP];
-  __shared__ int32_t s_nt, s_base;
-  const int par = tick & 1;
-  int32_t* counters = p.counters + CNT_STRIDE * par;
-  const int32_t n_slow = counters[CNT_SLOW];
-  const double* __restrict__ pos_old = p.pos[par];
-  double* __restrict__ pos_new = p.pos[par ^ 1];
-  const TouchSink sink{s_touched, &s_nt};
-  for (int32_t chunk = blockIdx.x * SLOW_THREADS; chunk < n_slow; chunk += gridDim.x * SLOW_THREADS) {
-    if (threadIdx.x == 0) s_nt = 0;
-    __syncthreads();
-    const int32_t i = chunk + threadIdx.x;
-    if (i < n_slow) {
-      const int32_t e = p.slow[i];
-      const int a = e < 0 ? ~e : e;
-      const SA sa = p.sa[a];
-      const uint32_t st = sa.st;
-      const double cur = pos_old[a];
-      if (e < 0) {
-        pos_new[a] = turn_onto(p, a, tick, st, cur, pos_old, sink);
-      } else {
-      const bool on_road = st & ST_ONROAD;
-      const bool on_route = on_road && ((st >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME;
-      const int32_t ah = on_road ? sa.ahead : -1;
-      const double lead = ah >= 0 ? pos_old[ah] : 0.0;
-      const double dlt = on_route ? p.delta[a] : 0.0;
-      const double buf = on_route ? p.buf[a] : 0.0;
-      pos_new[a] = advance_actor(p, a, tick, st, ah, cur, dlt, buf, lead, pos_old, sink);
-      }
-    }
-    __syncthreads();
-    const int nt = s_nt;
-    if (threadIdx.x == 0 && nt) s_base = atomicAdd(&counters[CNT_TOUCHED], nt);
-    __syncthreads();
-    for (int k = threadIdx.x; k < nt; k += SLOW_THREADS) p.touched[s_base + k] = s_touched[k];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Processing order (world.scm:24-30) from old locations.
-
-// earlier(a,b) among actors that landed on the same segment in the same tick
-__device__ __forceinline__ bool landed_earlier(const Params& p, int a, int b, int32_t t_land) {
-  const int32_t la = p.coldf[a].land_lane, lb = p.coldf[b].land_lane;
-  if (t_land == 0) return la < lb;   // initial placement: land_lane holds the link! order
-  if (la != lb) return la > lb;      // higher registration index comes first in static-items
-  return p.coldf[a].land_pos > p.coldf[b].land_pos;   // a lane yields its actors in descending pos-param
-}
-
-__device__ __forceinline__ bool stamp_less(const Params& p, int a, int b, uint32_t sta) {
-  const int32_t ta = p.coldf[a].land_tick, tb = p.coldf[b].land_tick;
-  if (ta != tb) return ta < tb;
-  return (sta & ST_CLASS_P) ? landed_earlier(p, b, a, ta) : landed_earlier(p, a, b, ta);
-}
-
-// Is a before b in their segment's list at `tick`?  The list reverses every tick (core.scm:169-171
-// conses while get-actors walks head to tail), so a stamp's sign alternates with tick parity.
-__device__ bool offroad_before(const Params& p, int a, int b, int tick) {
-  const uint32_t sta = p.sa[a].st, stb = p.sa[b].st;
-  const bool nega = (((tick - p.coldf[a].land_tick) & 1) != 0) == ((sta & ST_CLASS_P) != 0);
-  const bool negb = (((tick - p.coldf[b].land_tick) & 1) != 0) == ((stb & ST_CLASS_P) != 0);
-  if (nega != negb) return nega;
-  return nega ? stamp_less(p, b, a, stb) : stamp_less(p, a, b, sta);
-}
-
-// Of two actors landing on the same (lane, pos-param) this tick: the one visited later, which is
-// the one bbtree-set keeps (core.scm:173-178).
-__device__ int later_processed(const Params& p, int x, int y, int32_t lane, const double* pos_old, int tick) {
-  const uint32_t sx = p.sa[x].st, sy = p.sa[y].st;
-  const int32_t mx = (sx & ST_MOVED) ? p.cold[x].mv_old : lane, my = (sy & ST_MOVED) ? p.cold[y].mv_old : lane;
-  const int32_t cx = mx < 0 ? ~mx : mx, cy = my < 0 ? ~my : my;
-  if (cx != cy) return cx < cy ? x : y;
-  if (mx < 0) return offroad_before(p, x, y, tick) ? y : x;
-  return pos_old[x] < pos_old[y] ? x : y;
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_unlink / k_link: one thread per lane that an actor entered or left this tick.  Lanes are doubly
-// linked lists in ascending pos-param, so nothing walks a whole lane.
-//   k_unlink  takes the lane's leavers (its outbox) and the ghosts found on it this tick out of the
-//             list in O(1) each, and settles the actors that are done for this tick: a ghost's move is
-//             void, an emigrant lives on another rank from now on, an actor that left the road has no
-//             lane to enter.
-//   k_link    (after every lane has been unlinked, so a mover's pointers are free to overwrite)
-//             inserts the lane's entrants (its inbox, sorted) by walking up from the rear — entrants
-//             land near pos 0, so that is a step or two — and writes their final pointers.
-// Residents keep their relative order (a follower is clamped behind its leader, route.scm:68-74).
-// Equal keys: an entrant that lands on a resident's or another entrant's key is resolved in k_link,
-// the later-processed one stays (core.scm:173-178); two residents that round to the same key are left
-// linked and resolved next tick through the ghost rule (file header) — on every lane, touched or not.
-// Junction occupancy (route.scm:98-104) changes by whole lanes: one atomic per lane and kernel.
-constexpr int32_t UNLINKED = -3;
-
-__global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
-  const int par = tick & 1;
-  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
-    const int32_t lane = p.touched[i];
-    const LaneDyn ld = p.lane[lane];
-    if (ld.outbox < 0 && ld.ghosts < 0) continue;
-    if (ld.outbox >= 0) p.lane[lane].outbox = -1;
-    if (ld.ghosts >= 0) p.lane[lane].ghosts = -1;
-    int32_t tail = ld.tail, gone = 0;
-    // A ghost that also moved is on both lists; the second visit finds it UNLINKED.
-    auto unlink = [&](int32_t z, int32_t b) {
-      const int32_t f = p.sa[z].ahead;
-      if (f == UNLINKED) return false;
-      if (b >= 0) p.sa[b].ahead = f; else tail = f;
-      if (f >= 0) p.cold[f].behind = b;
-      p.sa[z].ahead = UNLINKED;
-      return true;
-    };
-    for (int32_t z = ld.outbox; z >= 0;) {
-      const Cold k = p.cold[z];
-      unlink(z, k.behind);
-      ++gone;   // every mover leaves its old lane, whatever becomes of it
-      const uint32_t sz = p.sa[z].st;
-      if (k.dead_mark == tick + 1 || (sz & ST_EMIG)) p.sa[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG);
-      else if (!(sz & ST_ONROAD)) p.sa[z].st = sz & ~ST_MOVED;   // went off the road: nothing to link
-      z = k.outbox_next;
-    }
-    for (int32_t z = ld.ghosts; z >= 0;) {
-      const Cold k = p.cold[z];
-      const uint32_t sz = p.sa[z].st;
-      if (unlink(z, k.behind) && !(sz & ST_MOVED)) {   // (one that also moved was settled above)
-        p.sa[z].st = sz & ~ST_ALIVE;
-        ++gone;
-      }
-      z = k.ghost_next;
-    }
-    if (tail != ld.tail) p.lane[lane].tail = tail;
-    if (ld.junction >= 0 && gone) atomicSub(&p.occ[ld.junction], gone);
-  }
-}
-
-__global__ void __launch_bounds__(128) k_link(Params p, int tick) {
-  const int par = tick & 1;
-  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
-  const double* __restrict__ pos_old = p.pos[par];
-  const double* __restrict__ pos_new = p.pos[par ^ 1];
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
-    const int32_t lane = p.touched[i];
-    const LaneDyn ld = p.lane[lane];
-    const int32_t inbox = ld.inbox;
-    if (inbox < 0) continue;
-    p.lane[lane].inbox = -1;
-    // entrants by ascending (pos-param, slot): selection over the inbox, which is short
-    double e_pos = 0.0;
-    int32_t e = -1;
-    auto next_entrant = [&](bool first) {
-      int32_t best = -1;
-      double best_pos = 0.0;
-      for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
-        if (!(p.sa[y].st & ST_MOVED)) continue;   // a ghost's move is void: k_unlink settled it
-        const double py = pos_new[y];
-        if (!first && !(py > e_pos || (py == e_pos && y > e))) continue;
-        if (best < 0 || py < best_pos || (py == best_pos && y < best)) { best = y; best_pos = py; }
-      }
-      e = best;
-      e_pos = best_pos;
-    };
-    auto link = [&](int32_t b, int32_t z, int32_t f) {   // b -> z -> f
-      if (b < 0) p.lane[lane].tail = z; else p.sa[b].ahead = z;
-      p.sa[z].ahead = f;
-      p.cold[z].behind = b;
-      if (f >= 0) p.cold[f].behind = z;
-    };
-    int32_t prev = -1, x = ld.tail, delta = 0;
-    for (next_entrant(true); e >= 0; next_entrant(false)) {
-      while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = p.sa[x].ahead; }
-      if (x >= 0 && pos_new[x] == e_pos) {   // equal key: bbtree-set keeps the one processed later
-        const bool e_wins = later_processed(p, e, x, lane, pos_old, tick) == e;
-        const int32_t lose = e_wins ? x : e;
-        const uint32_t sl = p.sa[lose].st;
-        p.sa[lose].st = sl & ~ST_ALIVE;        // (still marked moved if it is an entrant: see below)
-        if (!(sl & ST_MOVED) || lose == x) --delta;   // a resident, or an entrant that had been counted in
-        if (!e_wins) continue;
-        link(prev, e, p.sa[x].ahead);   // e takes x's place
-      } else {
-        link(prev, e, x);
-      }
-      ++delta;
-      x = e;   // the next entrant (same or higher key) meets e first
-    }
-    // the entrants stayed marked as movers so that ties among them could look at where they came from
-    for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
-      const uint32_t sy = p.sa[y].st;
-      if (sy & ST_MOVED) p.sa[y].st = sy & ~(ST_MOVED | ST_IMMIG);
-    }
-    if (ld.junction >= 0 && delta) atomicAdd(&p.occ[ld.junction], delta);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Set-up: the network is assembled on the device from the arrays that cross the ABI (staged through
-// a reusable device buffer), so that no host copy of the 32-byte records is ever made.
-__global__ void __launch_bounds__(256) k_item_build(Item* __restrict__ item, int64_t n, const uint8_t* __restrict__ kind,
-                                                     const double* __restrict__ len, const uint8_t* __restrict__ dir,
-                                                     const int32_t* __restrict__ seg, const int32_t* __restrict__ out,
-                                                     const int32_t* __restrict__ junction, const int32_t* __restrict__ of,
-                                                     const int32_t* __restrict__ ob) {
-  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (r >= n) return;
-  Item it;
-  it.kind = kind[r];
-  it.dir = dir[r];
-  it.pad = 0;
-  it.len = len[r];
-  it.link = it.kind == GRIDDY_SEGMENT_LANE ? seg[r] : it.kind == GRIDDY_JUNCTION_LANE ? out[r] : it.kind == GRIDDY_SEGMENT ? of[r] : -1;
-  it.link2 = it.kind == GRIDDY_JUNCTION_LANE ? junction[r] : it.kind == GRIDDY_SEGMENT ? ob[r] : -1;
-  it.from_j = it.to_j = -1;
-  it.loc_key = (uint32_t)r;   // default locality key: the registration index
-  item[r] = it;
-}
-
-__global__ void __launch_bounds__(256) k_item_set_grid(Item* __restrict__ item, int64_t n, const int32_t* __restrict__ from_j,
-                                                        const int32_t* __restrict__ to_j) {
-  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (r < n) { item[r].from_j = from_j[r]; item[r].to_j = to_j[r]; }
-}
-
-__global__ void __launch_bounds__(256) k_item_set_key(Item* __restrict__ item, int64_t n, const uint32_t* __restrict__ key) {
-  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (r < n) item[r].loc_key = key[r];
-}
-
-__global__ void __launch_bounds__(256) k_lane_init(LaneDyn* __restrict__ lane, const Item* __restrict__ item, int64_t n) {
-  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (r >= n) return;
-  const Item it = item[r];
-  lane[r] = LaneDyn{-1, -1, -1, -1, 0, it.kind == GRIDDY_JUNCTION_LANE ? it.link2 : -1, {0, 0}};
-}
-
-__global__ void __launch_bounds__(256) k_lane_set_tail(LaneDyn* __restrict__ lane, const int32_t* __restrict__ which,
-                                                        const int32_t* __restrict__ tail, int64_t m) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i < m) lane[which[i]].tail = tail[i];
-}
-
-// ------------------------------------------------------------------------------------------------
-// Multi-GPU: the world is partitioned spatially, one part per rank.  Every item has an owner; a
-// segment and its lanes share one, a junction and its lanes share one, so an actor changes rank only
-// while it turns from a segment lane onto a junction lane or back (never while it goes on or off the
-// road).  An actor lives on the rank that owns its container.  What a turning actor reads of the OLD
-// world on the other side — the target lane's rearmost positive pos-param (route.scm:118-121) and the
-// target junction's occupancy (route.scm:98-108) — is the halo, exchanged before k_advance; the actors
-// that crossed are exchanged as fixed-size records before k_relink, which then inserts them by key
-// exactly as it inserts local movers (their old lane and old pos-param travel along, because
-// processing order decides equal-key winners).  Results are identical to a single-GPU run.
-
-struct MigRec {
-  double pos_old, pos_new, delta, buf, arrive, land_pos, speed, speed_dt;
-  int32_t gid, st, container, mv_old, hop, tj, popped, n_items, land_tick, land_lane, dest_lane, dest_from_j,
-      dest_to_j, pad;
-  int32_t item_sleep[MIG_ITEMS], item_seg[MIG_ITEMS];
-  double item_pos[MIG_ITEMS];
-  uint8_t item_kind[MIG_ITEMS], item_side[MIG_ITEMS];
-};
-constexpr size_t MIG_HEADER = 8;
-
-// Halo out: for every lane of mine that a neighbour's actors can enter, its smallest key in (0, ...]
-// (the walk route.scm:118-121 would do), +inf if there is none; for every such junction, its occupancy.
-__global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int32_t* __restrict__ items, int n_lanes,
-                                                    int n_junctions, double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_lanes + n_junctions) return;
-  const int32_t item = items[i];
-  if (i >= n_lanes) { out[i] = (double)p.occ[item]; return; }
-  const double* __restrict__ pos = p.pos[par];
-  int32_t x = p.lane[item].tail;
-  while (x >= 0 && !(pos[x] > 0.0)) x = p.sa[x].ahead;
-  out[i] = x >= 0 ? pos[x] : __longlong_as_double(0x7ff0000000000000LL);
-}
-
-// Halo in: occupancy of the neighbours' junctions (the lane values are read in place from halo_recv).
-__global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __restrict__ junctions, int n,
-                                                      const double* __restrict__ in) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p.occ[junctions[i]] = (int32_t)in[i];
-}
-
-// After this tick's immigrants are unpacked: empty my receive buffers of this parity.  The sender writes
-// them again two ticks from now, after it has seen the token I send next tick.
-__global__ void k_mig_reset(Params p, int par) {
-  if (threadIdx.x < MAX_RANKS && p.mig_mine[threadIdx.x][par]) *p.mig_mine[threadIdx.x][par] = 0;
-}
-
-// Emigrants -> one record each, written straight into the receive buffer of the rank that owns their
-// new lane (peer memory over NVLink: remote atomic for the slot, remote stores for the record), so only
-// the actors that actually crossed travel, not a bound-sized message.
-__global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
-  const int par = tick & 1;
-  const int32_t n = p.counters[CNT_STRIDE * par + CNT_EMIG];
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int a = p.emig[i];
-    if (p.cold[a].dead_mark == tick + 1) continue;   // a ghost's move is void
-    const int32_t lane = p.cold[a].container;
-    const int32_t to = p.owner[lane];
-    uint8_t* buf = p.mig_peer[to][par];
-    const int32_t at = atomicAdd_system((int32_t*)buf, 1);
-    if (at >= p.mig_cap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
-    MigRec r;
-    r.pos_old = p.pos[par][a];
-    r.pos_new = p.pos[par ^ 1][a];
-    r.delta = p.delta[a];
-    r.buf = p.buf[a];
-    r.arrive = p.coldf[a].arrive;
-    r.land_pos = p.coldf[a].land_pos;
-    r.speed = p.coldf[a].speed;
-    r.speed_dt = p.coldf[a].speed_dt;
-    r.gid = p.cold[a].gid;
-    r.st = (int32_t)((p.sa[a].st & ~ST_EMIG) | ST_IMMIG);
-    r.container = lane;
-    r.mv_old = p.cold[a].mv_old;
-    r.hop = p.cold[a].hop;
-    r.tj = p.tj[a] >= 0 ? (p.tj[a] & ~TJ_REMOTE) : -1;
-    r.dest_lane = p.cold[a].dest_lane;
-    r.dest_from_j = p.cold[a].dest_from_j;
-    r.dest_to_j = p.cold[a].dest_to_j;
-    r.pad = 0;
-    const int32_t beg = p.coldf[a].agenda_beg, end = p.coldf[a].agenda_end;
-    r.popped = p.cold[a].agenda_cur - beg;
-    r.n_items = end - beg;
-    r.land_tick = p.coldf[a].land_tick;
-    r.land_lane = p.coldf[a].land_lane;
-    if (r.n_items > MIG_ITEMS) { dev_error(p, DEV_ERR_MIG_AGENDA); r.n_items = MIG_ITEMS; }
-    for (int k = 0; k < MIG_ITEMS; ++k) {
-      const bool in = k < r.n_items;
-      r.item_kind[k] = in ? p.item_kind[beg + k] : 0;
-      r.item_side[k] = in ? p.item_side[beg + k] : 0;
-      r.item_sleep[k] = in ? p.item_sleep[beg + k] : 0;
-      r.item_seg[k] = in ? p.item_seg[beg + k] : -1;
-      r.item_pos[k] = in ? p.item_pos[beg + k] : 0.0;
-    }
-    ((MigRec*)(buf + MIG_HEADER))[at] = r;
-  }
-}
-
-// Immigrants: a fresh slot each, then onto their lane's inbox like any local mover.
-__global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const uint8_t* __restrict__ buf, int cap) {
-  const int par = tick & 1;
-  const int32_t n = min(*(const int32_t*)buf, cap);
-  const MigRec* recs = (const MigRec*)(buf + MIG_HEADER);
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const MigRec r = recs[i];
-    const int32_t a = atomicAdd(&p.scal[SC_NSLOTS], 1);
-    const int32_t it = atomicAdd(&p.scal[SC_NITEMS], r.n_items);
-    if (a >= p.cap || it + r.n_items > p.icap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
-    p.coldf[a].speed = r.speed;
-    p.coldf[a].speed_dt = r.speed_dt;
-    p.cold[a].gid = r.gid;
-    p.coldf[a].agenda_beg = it;
-    p.coldf[a].agenda_end = it + r.n_items;
-    for (int k = 0; k < r.n_items; ++k) {
-      p.item_kind[it + k] = r.item_kind[k];
-      p.item_side[it + k] = r.item_side[k];
-      p.item_sleep[it + k] = r.item_sleep[k];
-      p.item_seg[it + k] = r.item_seg[k];
-      p.item_pos[it + k] = r.item_pos[k];
-    }
-    p.sa[a] = SA{(uint32_t)r.st, -1};
-    p.cold[a].behind = -1;
-    p.pos[par][a] = r.pos_old;       // processing order among a lane's entrants looks at old lane and old key
-    p.pos[par ^ 1][a] = r.pos_new;
-    p.delta[a] = r.delta;
-    p.buf[a] = r.buf;
-    p.coldf[a].arrive = r.arrive;
-    p.coldf[a].land_pos = r.land_pos;
-    p.cold[a].container = r.container;
-    p.cold[a].mv_old = r.mv_old;
-    p.aux[a] = 0;
-    p.cold[a].hop = r.hop;
-    p.cold[a].dest_lane = r.dest_lane;
-    p.cold[a].dest_from_j = r.dest_from_j;
-    p.cold[a].dest_to_j = r.dest_to_j;
-    p.tj[a] = tag_junction(p, r.tj);
-    p.cold[a].agenda_cur = it + r.popped;
-    p.cold[a].route_cur = 0;
-    p.coldf[a].land_tick = r.land_tick;
-    p.coldf[a].land_lane = r.land_lane;
-    p.cold[a].dead_mark = 0;
-    // onto the lane's inbox
-    p.cold[a].inbox_next = atomicExch(&p.lane[r.container].inbox, a);
-    if (atomicExch(&p.lane[r.container].mark, tick + 1) != tick + 1)
-      p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_TOUCHED], 1)] = r.container;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Reorder: sort the live slots by (locality key of the container, coarse pos-param), permute every
-// per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
-
-// Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
-constexpr int PERM4 = 2, PERM8 = 4;
-enum { P4_AUX, P4_TJ };
-enum { P8_SA, P8_POS, P8_DELTA, P8_BUF };
-
-struct Permute {
-  const uint32_t* src4[PERM4];
-  uint32_t* dst4[PERM4];
-  const uint64_t* src8[PERM8];
-  uint64_t* dst8[PERM8];
-  const Cold* src_cold;
-  Cold* dst_cold;
-  const ColdF* src_coldf;
-  ColdF* dst_coldf;
-};
-
-// grid = n_pad / 256 exactly: every lane of every warp reaches the ballot
-__global__ void __launch_bounds__(256) k_make_keys(Params p, int par, int key_bits, uint64_t* __restrict__ keys,
-                                                    uint32_t* __restrict__ vals, uint8_t* __restrict__ tailflag) {
-  const int s = blockIdx.x * 256 + threadIdx.x;
-  uint64_t key = ~0ull;
-  uint32_t val = 0xffffffffu;
-  bool live = false;
-  if (s < p.scal[SC_NSLOTS]) {
-    const uint32_t st = p.sa[s].st;
-    if (st & ST_ALIVE) {
-      live = true;
-      const int32_t c = p.cold[s].container;
-      const double x = p.pos[par][s];
-      // 16 bits of pos-param over [-0.5, 1.5): enough to keep a lane's actors in list order
-      const double q = fmin(fmax((x + 0.5) * 32768.0, 0.0), 65535.0);
-      // off-road actors after the on-road ones: warps are then all-travelling or all-parked
-      key = ((uint64_t)((st & ST_ONROAD) ? 0u : 1u) << (key_bits - 1)) | ((uint64_t)p.item[c].loc_key << 16) | (uint64_t)(uint32_t)q;
-      val = (uint32_t)s;
-      tailflag[s] = ((st & ST_ONROAD) && p.lane[c].tail == s) ? 1 : 0;
-    }
-  }
-  keys[s] = key;
-  vals[s] = val;
-  const uint32_t m = __ballot_sync(0xffffffffu, live);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&p.scal[SC_NALIVE], __popc(m));
-}
-
-__global__ void __launch_bounds__(256) k_inverse(const uint32_t* __restrict__ vals, int n_pad, int32_t* __restrict__ newslot) {
-  const int s = blockIdx.x * 256 + threadIdx.x;
-  if (s >= n_pad) return;
-  const uint32_t old = vals[s];
-  if (old != 0xffffffffu) newslot[old] = s;
-}
-
-__global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint32_t* __restrict__ vals,
-                                                  const int32_t* __restrict__ newslot,
-                                                  const uint8_t* __restrict__ tailflag) {
-  const int s = blockIdx.x * 256 + threadIdx.x;
-  if (s >= p.scal[SC_NALIVE]) return;
-  const uint32_t old = vals[s];
-  // ahead / behind are meaningful on the road only; an off-road actor's values are stale
-  SA sa = ((const SA*)q.src8[P8_SA])[old];
-  const bool on_road = sa.st & ST_ONROAD;
-#pragma unroll
-  for (int k = 0; k < PERM4; ++k) q.dst4[k][s] = q.src4[k][old];
-  Cold cold = q.src_cold[old];
-  if (on_road && cold.behind >= 0) {
-    cold.behind = newslot[cold.behind];
-    if (cold.behind < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's follower must be live
-  } else {
-    cold.behind = -1;
-  }
-  q.dst_cold[s] = cold;
-  q.dst_coldf[s] = q.src_coldf[old];
-#pragma unroll
-  for (int k = 0; k < PERM8; ++k) {
-    if (k == P8_SA) {
-      if (on_road && sa.ahead >= 0) {
-        sa.ahead = newslot[sa.ahead];
-        if (sa.ahead < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's leader must be live
-      } else {
-        sa.ahead = -1;
-      }
-      ((SA*)q.dst8[k])[s] = sa;
-    } else {
-      q.dst8[k][s] = q.src8[k][old];
-    }
-  }
-  if (tailflag[old]) p.lane[cold.container].tail = s;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Read-back: format the world on the device (by actor id), then one copy per output array.
-
-// Ghost rule for downloads: flag every leader that shares its follower's key.
-__global__ void __launch_bounds__(256) k_flag_ghosts(Params p, int par, uint8_t* ghost) {
-  const int a = blockIdx.x * 256 + threadIdx.x;
-  if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.sa[a].st;
-  if ((st & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD)) return;
-  const double* pos = p.pos[par];
-  const double cur = pos[a];
-  for (int32_t x = p.sa[a].ahead; x >= 0 && pos[x] == cur; x = p.sa[x].ahead) ghost[x] = 1;
-}
-
-// Living actors of the world: alive and not a ghost.
-__global__ void __launch_bounds__(256) k_count_alive(Params p, const uint8_t* ghost, unsigned long long* out) {
-  const int a = blockIdx.x * 256 + threadIdx.x;
-  const bool live = a < p.scal[SC_NSLOTS] && (p.sa[a].st & ST_ALIVE) && !ghost[a];
-  const uint32_t m = __ballot_sync(0xffffffffu, live);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
-}
-
-struct PackOut {
-  uint8_t *alive, *loc_kind, *side, *route_status;
-  int32_t *container, *agenda_cur, *sleep_left, *route_head, *gid;
-  double* pos;
-  int by_slot;   // index the outputs by slot (multi-GPU read-back) instead of by actor id
-};
-
-__global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uint8_t* ghost, PackOut o) {
-  const int a = blockIdx.x * 256 + threadIdx.x;
-  if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.sa[a].st;
-  const int32_t id = o.by_slot ? a : p.cold[a].gid;
-  const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
-  const int32_t aux = p.aux[a];
-  if (o.gid) o.gid[id] = p.cold[a].gid;
-  if (o.alive) o.alive[id] = ((st & ST_ALIVE) && !ghost[a]) ? 1 : 0;
-  if (o.loc_kind) o.loc_kind[id] = (st & ST_ONROAD) ? 1 : 0;
-  if (o.container) o.container[id] = p.cold[a].container;
-  if (o.side) o.side[id] = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? 1 : 0;
-  if (o.pos) o.pos[id] = p.pos[par][a];
-  if (o.agenda_cur) o.agenda_cur[id] = p.cold[a].agenda_cur - p.coldf[a].agenda_beg;
-  if (o.sleep_left) o.sleep_left[id] = head == HEAD_SLEEP ? aux : 0;
-  if (o.route_status) o.route_status[id] = (uint8_t)rs;
-  if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? p.cold[a].hop : -2;
-}
 
 // ================================================================================================
 // Host side

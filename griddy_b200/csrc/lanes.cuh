@@ -1,0 +1,161 @@
+// lanes.cuh — part of griddy_cuda.cu (one translation unit).  Per-lane order maintenance: processing order, k_unlink, k_link.
+#pragma once
+
+namespace griddy {
+
+// ------------------------------------------------------------------------------------------------
+// Processing order (world.scm:24-30) from old locations.
+
+// earlier(a,b) among actors that landed on the same segment in the same tick
+__device__ __forceinline__ bool landed_earlier(const Params& p, int a, int b, int32_t t_land) {
+  const int32_t la = p.coldf[a].land_lane, lb = p.coldf[b].land_lane;
+  if (t_land == 0) return la < lb;   // initial placement: land_lane holds the link! order
+  if (la != lb) return la > lb;      // higher registration index comes first in static-items
+  return p.coldf[a].land_pos > p.coldf[b].land_pos;   // a lane yields its actors in descending pos-param
+}
+
+__device__ __forceinline__ bool stamp_less(const Params& p, int a, int b, uint32_t sta) {
+  const int32_t ta = p.coldf[a].land_tick, tb = p.coldf[b].land_tick;
+  if (ta != tb) return ta < tb;
+  return (sta & ST_CLASS_P) ? landed_earlier(p, b, a, ta) : landed_earlier(p, a, b, ta);
+}
+
+// Is a before b in their segment's list at `tick`?  The list reverses every tick (core.scm:169-171
+// conses while get-actors walks head to tail), so a stamp's sign alternates with tick parity.
+__device__ bool offroad_before(const Params& p, int a, int b, int tick) {
+  const uint32_t sta = p.sa[a].st, stb = p.sa[b].st;
+  const bool nega = (((tick - p.coldf[a].land_tick) & 1) != 0) == ((sta & ST_CLASS_P) != 0);
+  const bool negb = (((tick - p.coldf[b].land_tick) & 1) != 0) == ((stb & ST_CLASS_P) != 0);
+  if (nega != negb) return nega;
+  return nega ? stamp_less(p, b, a, stb) : stamp_less(p, a, b, sta);
+}
+
+// Of two actors landing on the same (lane, pos-param) this tick: the one visited later, which is
+// the one bbtree-set keeps (core.scm:173-178).
+__device__ int later_processed(const Params& p, int x, int y, int32_t lane, const double* pos_old, int tick) {
+  const uint32_t sx = p.sa[x].st, sy = p.sa[y].st;
+  const int32_t mx = (sx & ST_MOVED) ? p.cold[x].mv_old : lane, my = (sy & ST_MOVED) ? p.cold[y].mv_old : lane;
+  const int32_t cx = mx < 0 ? ~mx : mx, cy = my < 0 ? ~my : my;
+  if (cx != cy) return cx < cy ? x : y;
+  if (mx < 0) return offroad_before(p, x, y, tick) ? y : x;
+  return pos_old[x] < pos_old[y] ? x : y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_unlink / k_link: one thread per lane that an actor entered or left this tick.  Lanes are doubly
+// linked lists in ascending pos-param, so nothing walks a whole lane.
+//   k_unlink  takes the lane's leavers (its outbox) and the ghosts found on it this tick out of the
+//             list in O(1) each, and settles the actors that are done for this tick: a ghost's move is
+//             void, an emigrant lives on another rank from now on, an actor that left the road has no
+//             lane to enter.
+//   k_link    (after every lane has been unlinked, so a mover's pointers are free to overwrite)
+//             inserts the lane's entrants (its inbox, sorted) by walking up from the rear — entrants
+//             land near pos 0, so that is a step or two — and writes their final pointers.
+// Residents keep their relative order (a follower is clamped behind its leader, route.scm:68-74).
+// Equal keys: an entrant that lands on a resident's or another entrant's key is resolved in k_link,
+// the later-processed one stays (core.scm:173-178); two residents that round to the same key are left
+// linked and resolved next tick through the ghost rule (file header) — on every lane, touched or not.
+// Junction occupancy (route.scm:98-104) changes by whole lanes: one atomic per lane and kernel.
+constexpr int32_t UNLINKED = -3;
+
+__global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
+  const int par = tick & 1;
+  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
+    const int32_t lane = p.touched[i];
+    const LaneDyn ld = p.lane[lane];
+    if (ld.outbox < 0 && ld.ghosts < 0) continue;
+    if (ld.outbox >= 0) p.lane[lane].outbox = -1;
+    if (ld.ghosts >= 0) p.lane[lane].ghosts = -1;
+    int32_t tail = ld.tail, gone = 0;
+    // A ghost that also moved is on both lists; the second visit finds it UNLINKED.
+    auto unlink = [&](int32_t z, int32_t b) {
+      const int32_t f = p.sa[z].ahead;
+      if (f == UNLINKED) return false;
+      if (b >= 0) p.sa[b].ahead = f; else tail = f;
+      if (f >= 0) p.cold[f].behind = b;
+      p.sa[z].ahead = UNLINKED;
+      return true;
+    };
+    for (int32_t z = ld.outbox; z >= 0;) {
+      const Cold k = p.cold[z];
+      unlink(z, k.behind);
+      ++gone;   // every mover leaves its old lane, whatever becomes of it
+      const uint32_t sz = p.sa[z].st;
+      if (k.dead_mark == tick + 1 || (sz & ST_EMIG)) p.sa[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG);
+      else if (!(sz & ST_ONROAD)) p.sa[z].st = sz & ~ST_MOVED;   // went off the road: nothing to link
+      z = k.outbox_next;
+    }
+    for (int32_t z = ld.ghosts; z >= 0;) {
+      const Cold k = p.cold[z];
+      const uint32_t sz = p.sa[z].st;
+      if (unlink(z, k.behind) && !(sz & ST_MOVED)) {   // (one that also moved was settled above)
+        p.sa[z].st = sz & ~ST_ALIVE;
+        ++gone;
+      }
+      z = k.ghost_next;
+    }
+    if (tail != ld.tail) p.lane[lane].tail = tail;
+    if (ld.junction >= 0 && gone) atomicSub(&p.occ[ld.junction], gone);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_link(Params p, int tick) {
+  const int par = tick & 1;
+  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
+  const double* __restrict__ pos_old = p.pos[par];
+  const double* __restrict__ pos_new = p.pos[par ^ 1];
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
+    const int32_t lane = p.touched[i];
+    const LaneDyn ld = p.lane[lane];
+    const int32_t inbox = ld.inbox;
+    if (inbox < 0) continue;
+    p.lane[lane].inbox = -1;
+    // entrants by ascending (pos-param, slot): selection over the inbox, which is short
+    double e_pos = 0.0;
+    int32_t e = -1;
+    auto next_entrant = [&](bool first) {
+      int32_t best = -1;
+      double best_pos = 0.0;
+      for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
+        if (!(p.sa[y].st & ST_MOVED)) continue;   // a ghost's move is void: k_unlink settled it
+        const double py = pos_new[y];
+        if (!first && !(py > e_pos || (py == e_pos && y > e))) continue;
+        if (best < 0 || py < best_pos || (py == best_pos && y < best)) { best = y; best_pos = py; }
+      }
+      e = best;
+      e_pos = best_pos;
+    };
+    auto link = [&](int32_t b, int32_t z, int32_t f) {   // b -> z -> f
+      if (b < 0) p.lane[lane].tail = z; else p.sa[b].ahead = z;
+      p.sa[z].ahead = f;
+      p.cold[z].behind = b;
+      if (f >= 0) p.cold[f].behind = z;
+    };
+    int32_t prev = -1, x = ld.tail, delta = 0;
+    for (next_entrant(true); e >= 0; next_entrant(false)) {
+      while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = p.sa[x].ahead; }
+      if (x >= 0 && pos_new[x] == e_pos) {   // equal key: bbtree-set keeps the one processed later
+        const bool e_wins = later_processed(p, e, x, lane, pos_old, tick) == e;
+        const int32_t lose = e_wins ? x : e;
+        const uint32_t sl = p.sa[lose].st;
+        p.sa[lose].st = sl & ~ST_ALIVE;        // (still marked moved if it is an entrant: see below)
+        if (!(sl & ST_MOVED) || lose == x) --delta;   // a resident, or an entrant that had been counted in
+        if (!e_wins) continue;
+        link(prev, e, p.sa[x].ahead);   // e takes x's place
+      } else {
+        link(prev, e, x);
+      }
+      ++delta;
+      x = e;   // the next entrant (same or higher key) meets e first
+    }
+    // the entrants stayed marked as movers so that ties among them could look at where they came from
+    for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
+      const uint32_t sy = p.sa[y].st;
+      if (sy & ST_MOVED) p.sa[y].st = sy & ~(ST_MOVED | ST_IMMIG);
+    }
+    if (ld.junction >= 0 && delta) atomicAdd(&p.occ[ld.junction], delta);
+  }
+}
+
+}  // namespace griddy

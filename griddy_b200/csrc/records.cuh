@@ -1,0 +1,127 @@
+// records.cuh — part of griddy_cuda.cu (one translation unit).  Constants, per-slot / per-item records and the kernel parameter block.
+#pragma once
+
+namespace griddy {
+
+constexpr uint32_t ST_ALIVE = 1u, ST_ONROAD = 2u, ST_SIDE = 4u;
+constexpr int ST_RS_SHIFT = 3;    // 2 bits: GRIDDY_ROUTE_*
+constexpr int ST_HEAD_SHIFT = 5;  // 2 bits: 0 no head, 1 sleep-for, 2 travel-to
+constexpr uint32_t ST_MOVED = 128u;    // changed lane / road side this tick (cleared by k_unlink / k_link)
+constexpr uint32_t ST_CLASS_P = 256u;  // landing stamp: came from a lane visited before the segment
+constexpr uint32_t ST_ARRIVE = 512u;   // the route head is (arrive-at _): aux == HOP_ARRIVE
+constexpr int HEAD_NONE = 0, HEAD_SLEEP = 1, HEAD_TRAVEL = 2;
+constexpr int HOP_ARRIVE = -1;
+
+constexpr uint32_t ST_EMIG = 1024u;     // multi-GPU: moved onto a lane another rank owns (this slot dies in k_unlink)
+constexpr uint32_t ST_IMMIG = 2048u;    // multi-GPU: arrived from another rank this tick (cleared in k_link)
+
+constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
+              DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32, DEV_ERR_MIG_OVERFLOW = 64,
+              DEV_ERR_MIG_AGENDA = 128;
+
+// Params::counters[parity][...]
+constexpr int CNT_EMIG = 0, CNT_TOUCHED = 1, CNT_SLOW = 2, CNT_STRIDE = 4;
+// device scalars (Params::scal)
+constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_COUNT = 4;
+constexpr int MAX_RANKS = 8;     // one box
+constexpr int MIG_ITEMS = 4;     // agenda items a migrating actor can carry
+
+// st and ahead of a slot share an 8-byte word: every kernel that walks a lane needs both.
+struct __align__(8) SA {
+  uint32_t st;
+  int32_t ahead;
+};
+
+// Everything about a slot that only matters when its actor does something rare (changes lane, wakes,
+// starts or ends a route), in one 64-byte record — one DRAM burst instead of a dozen sectors.
+struct __align__(16) Cold {
+  // travels with the actor
+  int32_t container;                  // lane (on road) or segment (off road)
+  int32_t agenda_cur, route_cur;      // agenda head (index into the item arrays), route head (explicit routes)
+  int32_t gid;                        // the actor's id (global id on a partitioned world)
+  int32_t behind;                     // slot of the next actor behind on the lane (-1 at the rear)
+  int32_t hop;                        // head of the route: lane of (turn-onto lane), or -1 for (arrive-at _)
+  int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions
+  // list surgery of the current tick
+  int32_t mv_old;                     // where a mover came from: lane, or ~segment
+  int32_t spare[2];
+  int32_t inbox_next, outbox_next, ghost_next;
+  int32_t dead_mark;                  // tick+1 when the actor was found to be a ghost during `tick`
+};
+// The rest of an actor's rarely read state, also one burst.
+struct __align__(16) ColdF {
+  double arrive;            // target of the (arrive-at _) that ends the current route
+  double land_pos;          // landing stamp (with land_tick, land_lane), see "processing order"
+  double speed, speed_dt;   // max-speed and fl(max-speed * dt)
+  int32_t agenda_beg, agenda_end;     // the actor's agenda in the item arrays
+  int32_t land_tick, land_lane;
+  int32_t pad[4];
+};
+static_assert(sizeof(Cold) == 64 && sizeof(ColdF) == 64, "cold records are one DRAM burst each");
+
+// The static network, one 32-byte record per registered item: a lane change reads its target lane's
+// kind, length, successor and junctions from one sector.
+struct __align__(16) Item {
+  double len;             // lanes: length (host-computed, spatial.scm:28-46)
+  int32_t link;           // segment lane: its segment; junction lane: the lane it leads onto; segment: outer forw-side lane
+  int32_t link2;          // junction lane: its junction; segment: outer back-side lane
+  int32_t from_j, to_j;   // grid routing: junction a segment lane leaves / reaches
+  uint32_t loc_key;       // locality key for the reorder (default: the registration index)
+  uint8_t kind, dir;
+  uint16_t pad;
+};
+// Per-lane list heads: rearmost actor, and this tick's entrants, leavers and ghosts.
+struct __align__(16) LaneDyn {
+  int32_t tail;      // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
+  int32_t inbox, outbox, ghosts;
+  int32_t mark;      // tick+1 once the lane is on this tick's touched list
+  int32_t junction;  // junction lanes: their junction (whose occupancy they count towards), else -1
+  int32_t pad[2];
+};
+static_assert(sizeof(Item) == 32 && sizeof(LaneDyn) == 32, "one sector per record");
+
+struct Params {
+  // network, by registration index
+  int64_t n_items;
+  Item* item;
+  LaneDyn* lane;
+  int32_t* occ;       // actors on a junction's lanes (route.scm:98-104); compact, so that it lives in L2
+  int32_t grid_n;
+  const int32_t* turn4;
+  // slots
+  int32_t cap;     // allocated slots
+  int32_t* scal;   // SC_*: device error bits, slots in use, live actors counted by the reorder
+  SA* sa;          // {st, ahead}: one 8-byte load per actor
+  double* pos[2];
+  double *delta, *buf;
+  int32_t* aux;   // sleeping: remaining time; travelling: head route step (lane, or -1 arrive-at)
+  int32_t* tj;    // junction of the lane the route head turns onto, -1 if that is not a junction lane
+  Cold* cold;
+  ColdF* coldf;
+  // agenda items (immutable; actors that arrive from another rank append theirs)
+  int64_t n_actors;
+  uint8_t* item_kind;
+  int32_t *item_sleep, *item_seg;
+  uint8_t* item_side;
+  double* item_pos;
+  int32_t icap;   // item capacity
+  const int64_t* route_off;   // null: grid routing table
+  const int32_t* route_lane;
+  // per-tick scratch, by slot
+  int32_t *touched, *slow;
+  int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, touched lanes, deferred actors
+  double dt, two_size;
+  // multi-GPU (owner == null on a single GPU): spatial partition, see "Multi-GPU" below
+  const int32_t* owner;      // rank that owns each item
+  int32_t my_rank;
+  const double* halo_recv;   // rearmost positive pos-param of the remote lanes my actors can enter;
+                             // lane_tail[remote lane] = -2 - index into this array
+  int32_t* emig;             // slots that emigrated this tick
+  int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
+  // by destination rank and tick parity: that rank's receive buffer for my emigrants, in ITS memory
+  // (peer access over NVLink): [int32 count, pad][MigRec x mig_cap].  k_emig_pack writes there directly.
+  uint8_t* mig_peer[MAX_RANKS][2];
+  int32_t* mig_mine[MAX_RANKS][2];   // headers of my own receive buffers, to reset after unpacking
+};
+
+}  // namespace griddy

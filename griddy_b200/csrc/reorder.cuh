@@ -1,0 +1,97 @@
+// reorder.cuh — part of griddy_cuda.cu (one translation unit).  Periodic spatial reorder of the slots (with radix_sort.cuh).
+#pragma once
+
+namespace griddy {
+
+// ------------------------------------------------------------------------------------------------
+// Reorder: sort the live slots by (locality key of the container, coarse pos-param), permute every
+// per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
+
+// Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
+constexpr int PERM4 = 2, PERM8 = 4;
+enum { P4_AUX, P4_TJ };
+enum { P8_SA, P8_POS, P8_DELTA, P8_BUF };
+
+struct Permute {
+  const uint32_t* src4[PERM4];
+  uint32_t* dst4[PERM4];
+  const uint64_t* src8[PERM8];
+  uint64_t* dst8[PERM8];
+  const Cold* src_cold;
+  Cold* dst_cold;
+  const ColdF* src_coldf;
+  ColdF* dst_coldf;
+};
+
+// grid = n_pad / 256 exactly: every lane of every warp reaches the ballot
+__global__ void __launch_bounds__(256) k_make_keys(Params p, int par, int key_bits, uint64_t* __restrict__ keys,
+                                                    uint32_t* __restrict__ vals, uint8_t* __restrict__ tailflag) {
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  uint64_t key = ~0ull;
+  uint32_t val = 0xffffffffu;
+  bool live = false;
+  if (s < p.scal[SC_NSLOTS]) {
+    const uint32_t st = p.sa[s].st;
+    if (st & ST_ALIVE) {
+      live = true;
+      const int32_t c = p.cold[s].container;
+      const double x = p.pos[par][s];
+      // 16 bits of pos-param over [-0.5, 1.5): enough to keep a lane's actors in list order
+      const double q = fmin(fmax((x + 0.5) * 32768.0, 0.0), 65535.0);
+      // off-road actors after the on-road ones: warps are then all-travelling or all-parked
+      key = ((uint64_t)((st & ST_ONROAD) ? 0u : 1u) << (key_bits - 1)) | ((uint64_t)p.item[c].loc_key << 16) | (uint64_t)(uint32_t)q;
+      val = (uint32_t)s;
+      tailflag[s] = ((st & ST_ONROAD) && p.lane[c].tail == s) ? 1 : 0;
+    }
+  }
+  keys[s] = key;
+  vals[s] = val;
+  const uint32_t m = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&p.scal[SC_NALIVE], __popc(m));
+}
+
+__global__ void __launch_bounds__(256) k_inverse(const uint32_t* __restrict__ vals, int n_pad, int32_t* __restrict__ newslot) {
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= n_pad) return;
+  const uint32_t old = vals[s];
+  if (old != 0xffffffffu) newslot[old] = s;
+}
+
+__global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint32_t* __restrict__ vals,
+                                                  const int32_t* __restrict__ newslot,
+                                                  const uint8_t* __restrict__ tailflag) {
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= p.scal[SC_NALIVE]) return;
+  const uint32_t old = vals[s];
+  // ahead / behind are meaningful on the road only; an off-road actor's values are stale
+  SA sa = ((const SA*)q.src8[P8_SA])[old];
+  const bool on_road = sa.st & ST_ONROAD;
+#pragma unroll
+  for (int k = 0; k < PERM4; ++k) q.dst4[k][s] = q.src4[k][old];
+  Cold cold = q.src_cold[old];
+  if (on_road && cold.behind >= 0) {
+    cold.behind = newslot[cold.behind];
+    if (cold.behind < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's follower must be live
+  } else {
+    cold.behind = -1;
+  }
+  q.dst_cold[s] = cold;
+  q.dst_coldf[s] = q.src_coldf[old];
+#pragma unroll
+  for (int k = 0; k < PERM8; ++k) {
+    if (k == P8_SA) {
+      if (on_road && sa.ahead >= 0) {
+        sa.ahead = newslot[sa.ahead];
+        if (sa.ahead < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's leader must be live
+      } else {
+        sa.ahead = -1;
+      }
+      ((SA*)q.dst8[k])[s] = sa;
+    } else {
+      q.dst8[k][s] = q.src8[k][old];
+    }
+  }
+  if (tailflag[old]) p.lane[cold.container].tail = s;
+}
+
+}  // namespace griddy
