@@ -52,6 +52,15 @@ __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop)
   return tag_junction(p, (hop >= 0 && p.item[hop].kind == GRIDDY_JUNCTION_LANE) ? p.item[hop].link2 : -1);
 }
 
+// The same for the head `nhop` of a route that has just reached lane `it`.  With the grid routing table a
+// segment lane's next hop is a junction lane of the junction the lane reaches (Item::to_j; checked by
+// griddy_set_routing_grid) and a junction lane's next hop is a segment lane, so the hop's own record
+// is not needed.
+__device__ __forceinline__ int32_t junction_after(const Params& p, const Item& it, int32_t nhop) {
+  if (p.route_off) return junction_of_hop(p, nhop);
+  return tag_junction(p, (nhop >= 0 && it.kind == GRIDDY_SEGMENT_LANE) ? it.to_j : -1);
+}
+
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
 __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_t ac, int32_t* aux) {
   if (ac >= p.coldf[a].agenda_end) { *aux = 0; return HEAD_NONE; }
@@ -116,9 +125,8 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
   p.cold[a].hop = nhop;
   p.cold[a].container = target;
   p.cold[a].mv_old = lane;
-  p.tj[a] = junction_of_hop(p, nhop);
-  p.delta[a] = __dmul_rn(f.speed_dt, tinv);
-  p.buf[a] = tbuf;
+  p.tj[a] = junction_after(p, it, nhop);
+  p.db[a] = make_double2(__dmul_rn(f.speed_dt, tinv), tbuf);
   p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u);
   if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
   else enter_lane(p, a, target, tick, sink);
@@ -219,9 +227,8 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     p.cold[a].dest_to_j = k.dest_to_j;
     p.coldf[a].arrive = dest_pos;
     p.cold[a].hop = hop;
-    p.tj[a] = junction_of_hop(p, hop);
-    p.delta[a] = __dmul_rn(p.coldf[a].speed_dt, __ddiv_rn(1.0, len));
-    p.buf[a] = __ddiv_rn(p.two_size, len);
+    p.tj[a] = junction_after(p, init_it, hop);
+    p.db[a] = make_double2(__dmul_rn(p.coldf[a].speed_dt, __ddiv_rn(1.0, len)), __ddiv_rn(p.two_size, len));
     p.cold[a].container = init_lane;
     p.cold[a].mv_old = ~seg;
     p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
@@ -264,13 +271,23 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 // arrays.  Any other actor — a few percent — would drag its whole warp through chains of dependent
 // gathers, so its slot is appended to the slow list instead (block-aggregated: one global atomic per
 // block) and k_slow runs the full advance$ for it with one thread per listed actor.
+// Measured on B200 (profiles/r2_variants.md): 2 slots per thread = 40 registers = 6 blocks per SM beats
+// 3 slots (58 registers with the slow list's payload, 4 blocks) and 3 slots capped at 48 registers.
 #ifndef ADV_UNROLL
-#define ADV_UNROLL 3
+#define ADV_UNROLL 2
 #endif
 constexpr int ADV_THREADS = 256;
+#ifndef SLOW_PAYLOAD
+#define SLOW_PAYLOAD 1
+#endif
+#ifdef ADV_MIN_BLOCKS
+#define ADV_BOUNDS __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
+#else
+#define ADV_BOUNDS __launch_bounds__(ADV_THREADS)
+#endif
 
-__global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
-  __shared__ int32_t s_list[ADV_THREADS * ADV_UNROLL];
+__global__ void ADV_BOUNDS k_advance(Params p, int tick) {
+  __shared__ int4 s_list[ADV_THREADS * ADV_UNROLL];
   __shared__ int32_t s_n, s_base;
   const int par = tick & 1;
   int32_t* counters = p.counters + CNT_STRIDE * par;
@@ -304,8 +321,11 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
     const int rs = (st[k] >> ST_RS_SHIFT) & 3, head = (st[k] >> ST_HEAD_SHIFT) & 3;
     const bool on_route = on_road && rs == GRIDDY_ROUTE_SOME;
     lead[k] = ah[k] >= 0 ? pos_old[ah[k]] : 0.0;
-    dlt[k] = on_route ? p.delta[a] : 0.0;
-    buf[k] = on_route ? p.buf[a] : 0.0;
+    const double2 db = on_route ? p.db[a] : make_double2(0.0, 0.0);
+    dlt[k] = db.x;
+    buf[k] = db.y;
+    // (loading tj only at the lane's end was measured slower: on a congested grid every queue head
+    // gets there every tick, so most sectors are fetched anyway, now behind a dependent load)
     tj[k] = (on_route && !(st[k] & ST_ARRIVE)) ? p.tj[a] : -1;
     slp[k] = (alive && rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) ? p.aux[a] : 0;
   }
@@ -334,7 +354,12 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(Params p, int tick) {
         slow = true;
       }
     }
-    if (slow) s_list[atomicAdd(&s_n, 1)] = turn ? ~a : a;   // ~slot: k_slow goes straight to turn_onto
+    if (slow)   // ~slot: k_slow goes straight to turn_onto; st and pos-param ride along (two gathers less there)
+#if SLOW_PAYLOAD
+      s_list[atomicAdd(&s_n, 1)] = make_int4(turn ? ~a : a, (int)st[k], __double2loint(cur[k]), __double2hiint(cur[k]));
+#else
+      s_list[atomicAdd(&s_n, 1)] = make_int4(turn ? ~a : a, 0, 0, 0);
+#endif
     else pos_new[a] = np;
   }
   __syncthreads();
@@ -361,21 +386,25 @@ __global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
     __syncthreads();
     const int32_t i = chunk + threadIdx.x;
     if (i < n_slow) {
-      const int32_t e = p.slow[i];
+      const int4 ent = p.slow[i];
+      const int32_t e = ent.x;
       const int a = e < 0 ? ~e : e;
-      const SA sa = p.sa[a];
-      const uint32_t st = sa.st;
+#if SLOW_PAYLOAD
+      const uint32_t st = (uint32_t)ent.y;
+      const double cur = __hiloint2double(ent.w, ent.z);
+#else
+      const uint32_t st = p.sa[a].st;
       const double cur = pos_old[a];
+#endif
       if (e < 0) {
         pos_new[a] = turn_onto(p, a, tick, st, cur, pos_old, sink);
       } else {
       const bool on_road = st & ST_ONROAD;
       const bool on_route = on_road && ((st >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME;
-      const int32_t ah = on_road ? sa.ahead : -1;
+      const int32_t ah = on_road ? p.sa[a].ahead : -1;
       const double lead = ah >= 0 ? pos_old[ah] : 0.0;
-      const double dlt = on_route ? p.delta[a] : 0.0;
-      const double buf = on_route ? p.buf[a] : 0.0;
-      pos_new[a] = advance_actor(p, a, tick, st, ah, cur, dlt, buf, lead, pos_old, sink);
+      const double2 db = on_route ? p.db[a] : make_double2(0.0, 0.0);
+      pos_new[a] = advance_actor(p, a, tick, st, ah, cur, db.x, db.y, lead, pos_old, sink);
       }
     }
     __syncthreads();

@@ -141,6 +141,7 @@ struct Ctx {
   int loc_key_bits = 1;
   uint32_t *alt4[PERM4] = {}, *cur4[PERM4] = {};   // double buffers of the permuted arrays
   uint64_t *alt8[PERM8] = {}, *cur8[PERM8] = {};
+  double2 *db_cur = nullptr, *db_alt = nullptr;
   Cold *cold_cur = nullptr, *cold_alt = nullptr;
   ColdF *coldf_cur = nullptr, *coldf_alt = nullptr;
   uint64_t* sort_keys = nullptr;
@@ -214,8 +215,7 @@ void bind_slot_arrays(Ctx* c, int par) {
   p.aux = (int32_t*)c->cur4[P4_AUX];
   p.tj = (int32_t*)c->cur4[P4_TJ];
   p.pos[par] = (double*)c->cur8[P8_POS];
-  p.delta = (double*)c->cur8[P8_DELTA];
-  p.buf = (double*)c->cur8[P8_BUF];
+  p.db = c->db_cur;
   p.cold = c->cold_cur;
   p.coldf = c->coldf_cur;
 }
@@ -240,6 +240,7 @@ int reorder_slots(Ctx* c, int64_t tick) {
   Permute q;
   for (int k = 0; k < PERM4; ++k) { q.src4[k] = c->cur4[k]; q.dst4[k] = c->alt4[k]; }
   for (int k = 0; k < PERM8; ++k) { q.src8[k] = c->cur8[k]; q.dst8[k] = c->alt8[k]; }
+  q.src_db = c->db_cur; q.dst_db = c->db_alt;
   q.src_cold = c->cold_cur; q.dst_cold = c->cold_alt;
   q.src_coldf = c->coldf_cur; q.dst_coldf = c->coldf_alt;
   k_permute<<<n_pad / 256, 256, 0, s>>>(p, q, c->sort_vals, c->newslot, c->tailflag);
@@ -247,6 +248,7 @@ int reorder_slots(Ctx* c, int64_t tick) {
   CUDA_TRY(c, cudaMemcpyAsync(&p.scal[SC_NSLOTS], &p.scal[SC_NALIVE], sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
   for (int k = 0; k < PERM4; ++k) std::swap(c->cur4[k], c->alt4[k]);
   for (int k = 0; k < PERM8; ++k) std::swap(c->cur8[k], c->alt8[k]);
+  std::swap(c->db_cur, c->db_alt);
   std::swap(c->cold_cur, c->cold_alt);
   std::swap(c->coldf_cur, c->coldf_alt);
   bind_slot_arrays(c, par);
@@ -517,6 +519,18 @@ int griddy_set_routing_grid(void* ctx, int32_t n, const int32_t* lane_from_j, co
   if (!c->have_net) return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid before upload_network");
   if (n < 1 || (int64_t)n * n > c->p.n_items || !lane_from_j || !lane_to_j || !turn4)
     return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid: bad arguments");
+  // Every turn of a segment lane must be a junction lane of the junction the lane reaches: the device
+  // takes a route head's gating junction from lane_to_j instead of reading the junction lane's record.
+  for (int64_t r = 0; r < c->p.n_items; ++r) {
+    if (c->h_kind[r] != GRIDDY_SEGMENT_LANE) continue;
+    for (int h = 0; h < 4; ++h) {
+      const int32_t t = turn4[4 * r + h];
+      if (t < 0) continue;
+      if (t >= c->p.n_items || c->h_kind[t] != GRIDDY_JUNCTION_LANE || c->h_lane_junction[t] != lane_to_j[r])
+        return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid: turn " + std::to_string(h) + " of lane " + std::to_string(r) +
+                                               " is not a junction lane of the junction the lane reaches");
+    }
+  }
   CUDA_TRY(c, cudaSetDevice(c->device));
   Params& p = c->p;
   {
@@ -656,6 +670,9 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     TRY(dev_alloc(c, pool, &c->alt8[k], cap));
     CUDA_TRY(c, cudaMemset(c->cur8[k], 0, (size_t)cap * sizeof(uint64_t)));
   }
+  TRY(dev_alloc(c, pool, &c->db_cur, cap));
+  TRY(dev_alloc(c, pool, &c->db_alt, cap));
+  CUDA_TRY(c, cudaMemset(c->db_cur, 0, (size_t)cap * sizeof(double2)));
   TRY(dev_alloc(c, pool, &c->cold_cur, cap));
   TRY(dev_alloc(c, pool, &c->cold_alt, cap));
   TRY(dev_alloc(c, pool, &c->coldf_cur, cap));

@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     MigRec r;
     r.pos_old = p.pos[par][a];
     r.pos_new = p.pos[par ^ 1][a];
-    r.delta = p.delta[a];
-    r.buf = p.buf[a];
+    r.delta = p.db[a].x;
+    r.buf = p.db[a].y;
     r.arrive = p.coldf[a].arrive;
     r.land_pos = p.coldf[a].land_pos;
     r.speed = p.coldf[a].speed;
@@ -128,8 +128,7 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     p.cold[a].behind = -1;
     p.pos[par][a] = r.pos_old;       // processing order among a lane's entrants looks at old lane and old key
     p.pos[par ^ 1][a] = r.pos_new;
-    p.delta[a] = r.delta;
-    p.buf[a] = r.buf;
+    p.db[a] = make_double2(r.delta, r.buf);
     p.coldf[a].arrive = r.arrive;
     p.coldf[a].land_pos = r.land_pos;
     p.cold[a].container = r.container;

@@ -35,18 +35,18 @@ struct __align__(8) SA {
 // Everything about a slot that only matters when its actor does something rare (changes lane, wakes,
 // starts or ends a route), in one 64-byte record — one DRAM burst instead of a dozen sectors.
 struct __align__(16) Cold {
-  // travels with the actor
+  // first sector: where the actor is and where it is going (read by a lane change, k_make_keys, read-back)
   int32_t container;                  // lane (on road) or segment (off road)
   int32_t agenda_cur, route_cur;      // agenda head (index into the item arrays), route head (explicit routes)
   int32_t gid;                        // the actor's id (global id on a partitioned world)
-  int32_t behind;                     // slot of the next actor behind on the lane (-1 at the rear)
   int32_t hop;                        // head of the route: lane of (turn-onto lane), or -1 for (arrive-at _)
   int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions
-  // list surgery of the current tick
+  // second sector: everything k_unlink / k_link read and write — list surgery touches this sector only
+  int32_t behind;                     // slot of the next actor behind on the lane (-1 at the rear)
   int32_t mv_old;                     // where a mover came from: lane, or ~segment
-  int32_t spare[2];
   int32_t inbox_next, outbox_next, ghost_next;
   int32_t dead_mark;                  // tick+1 when the actor was found to be a ghost during `tick`
+  int32_t spare[2];
 };
 // The rest of an actor's rarely read state, also one burst.
 struct __align__(16) ColdF {
@@ -93,7 +93,7 @@ struct Params {
   int32_t* scal;   // SC_*: device error bits, slots in use, live actors counted by the reorder
   SA* sa;          // {st, ahead}: one 8-byte load per actor
   double* pos[2];
-  double *delta, *buf;
+  double2* db;    // {delta, buf}: fl(speed*dt)*fl(1/len) and 10/len on the current lane (route.scm:62-66), one 16-byte load
   int32_t* aux;   // sleeping: remaining time; travelling: head route step (lane, or -1 arrive-at)
   int32_t* tj;    // junction of the lane the route head turns onto, -1 if that is not a junction lane
   Cold* cold;
@@ -108,7 +108,8 @@ struct Params {
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
   // per-tick scratch, by slot
-  int32_t *touched, *slow;
+  int32_t* touched;
+  int4* slow;   // deferred actors: {slot (~slot: turn-onto), st, pos-param lo, hi} as k_advance read them
   int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, touched lanes, deferred actors
   double dt, two_size;
   // multi-GPU (owner == null on a single GPU): spatial partition, see "Multi-GPU" below

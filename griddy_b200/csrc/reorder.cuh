@@ -8,15 +8,17 @@ namespace griddy {
 // per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
 
 // Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
-constexpr int PERM4 = 2, PERM8 = 4;
+constexpr int PERM4 = 2, PERM8 = 2;
 enum { P4_AUX, P4_TJ };
-enum { P8_SA, P8_POS, P8_DELTA, P8_BUF };
+enum { P8_SA, P8_POS };
 
 struct Permute {
   const uint32_t* src4[PERM4];
   uint32_t* dst4[PERM4];
   const uint64_t* src8[PERM8];
   uint64_t* dst8[PERM8];
+  const double2* src_db;
+  double2* dst_db;
   const Cold* src_cold;
   Cold* dst_cold;
   const ColdF* src_coldf;
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
   }
   q.dst_cold[s] = cold;
   q.dst_coldf[s] = q.src_coldf[old];
+  q.dst_db[s] = q.src_db[old];
 #pragma unroll
   for (int k = 0; k < PERM8; ++k) {
     if (k == P8_SA) {

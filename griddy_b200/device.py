@@ -13,7 +13,8 @@ import numpy as np
 from .flat import ActorState, FlatActors, FlatNetwork
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgriddy_cuda.so")
+# GRIDDY_CUDA_LIB names another build of the same library (kernel experiments, profiles/variants.md)
+LIB_PATH = os.environ.get("GRIDDY_CUDA_LIB") or os.path.join(_HERE, "csrc", "libgriddy_cuda.so")
 _LIB = None
 
 ERR_NAMES = {1: "BAD_ARG", 2: "CUDA", 3: "NCCL", 4: "BAD_STATE", 5: "OOM"}
