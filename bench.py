@@ -9,9 +9,12 @@ first advanced `--spinup` ticks (untimed, part of set-up) so that the initial sl
 run out and the actors are on the road, which is the expensive phase of the update.
 
   value     device-timed throughput, state resident in HBM (CUDA events around griddy_step)
-  e2e       the same metric through the C ABI with host buffers: every step is griddy_step(1)
-            followed by griddy_download_actors into pinned host arrays (what `draw` needs,
-            simulate.scm:155-160)
+  e2e       the same metric through the C ABI with host buffers, as the reference's game loop runs it:
+            every step is one `update` (griddy_step(1)) and one `draw` read-back — (get-pos actor) of every
+            actor (simulate.scm:155-160 -> draw.scm:74-88 -> spatial.scm:125-149) computed on the device
+            and copied into pinned host memory, 8 bytes per slot, the copy of frame t in flight while tick
+            t+1 runs (griddy_positions_begin / _end).  e2e_full_state: the round-1 definition, the whole
+            per-actor state (15 bytes per actor) fetched synchronously after every tick
   roofline  k_advance against the measured HBM copy bandwidth, 80 algorithmic bytes per actor-update
             (SURVEY 8(d)), timed with per-kernel CUDA events (griddy_profile_step)
   cpu_baseline / --impl reference   the CPU oracle (C++ restatement of the reference; Guile is not in
@@ -90,10 +93,10 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def build_world(grid, n_actors, agenda_len, seed_offset=0):
+def build_world(grid, n_actors, agenda_len, seed_offset=0, geometry=False):
     from griddy_b200 import synth
     t0 = time.time()
-    net = synth.grid_network(grid)
+    net = synth.grid_network(grid, geometry=geometry)
     actors = synth.grid_actors(net, n_actors, seed=synth.DEFAULT_SEED + seed_offset, agenda_len=agenda_len)
     log(f"[bench] generated {grid}x{grid} grid ({net.n_items} items), {n_actors} actors in {time.time() - t0:.1f}s")
     return net, actors
@@ -165,7 +168,7 @@ def world_shape(args, world):
     note = None
     while world > 1:
         n = int(round(per_gpu * math.sqrt(world)))
-        need = world * 30 * n * n * 100          # ~30 items per junction, ~100 host bytes per item
+        need = world * 30 * n * n * 170          # ~30 items per junction, ~100 host bytes per item + 64 of geometry
         try:
             avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
         except Exception:  # noqa: BLE001
@@ -206,7 +209,7 @@ def main():
     ap.add_argument("--actors", type=int, default=16_000_000)
     ap.add_argument("--agenda-len", type=int, default=4)
     ap.add_argument("--spinup", type=int, default=300)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--profile-ticks", type=int, default=50)
     ap.add_argument("--cpu-grid", type=int, default=64)
     ap.add_argument("--cpu-ticks", type=int, default=1500)
@@ -251,11 +254,11 @@ def main():
     n_grid, total_actors, _ = world_shape(args, world)
     t0 = time.time()
     if world == 1:
-        net, actors = build_world(args.grid, args.actors, args.agenda_len)
+        net, actors = build_world(args.grid, args.actors, args.agenda_len, geometry=True)
         sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period)
     else:
         # ONE world, partitioned into horizontal strips; this rank generates and uploads its own actors
-        net = synth.grid_network(n_grid)
+        net = synth.grid_network(n_grid, geometry=True)
         owner = synth.grid_owner(net, world, args.strips_per_rank)
         ids = synth.actor_ids_of_rank(net, total_actors, owner, rank)
         actors = synth.grid_actors(net, total_actors, agenda_len=args.agenda_len, ids=ids)
@@ -264,6 +267,7 @@ def main():
         sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period,
                                 partition=(rank, world, owner, args.mig_cap, args.extra_slots), gids=ids)
         device.connect_nccl(sim)
+    net.geom = None   # on the device now
     log(f"[bench] rank {rank}: uploaded in {time.time() - t0:.1f}s")
     sim.step(args.spinup)
     log(f"[bench] rank {rank}: spin-up {args.spinup} ticks in {sim.last_step_ms:.1f} ms")
@@ -320,20 +324,52 @@ def main():
         with open(tpath) as f:
             traffic = json.load(f).get("tick_dram_bytes")
 
-    # e2e: the call a user makes per frame — step one tick, read the world back into host buffers
-    n = actors.n if world == 1 else actors.n + args.extra_slots
-    pin = lambda dt: torch.empty(n, dtype=dt, pin_memory=True).numpy()
+    # e2e: what the reference's game loop does per tick — `update`, then `draw` reads (get-pos actor) of
+    # every actor.  Frame t is formatted on the device and copied into pinned host memory while tick t+1
+    # runs; every frame is complete on the host inside the timed region.
     import ctypes as C
-    # what `draw` reads of every actor (simulate.scm:155-160 -> get-pos, spatial.scm:125-149):
-    # alive, location kind, container, road side, pos-param
-    bufs = [pin(torch.uint8), pin(torch.uint8), pin(torch.int32), pin(torch.uint8), pin(torch.float64)]
-    d2h = sum(b.nbytes for b in bufs)
     L = device.lib()
+    cap = actors.n if world == 1 else actors.n + args.extra_slots
+    frames = [device.PinnedFrame(cap), device.PinnedFrame(cap)]
+
+    def e2e_loop(steps):
+        slots = 0
+        sim.step(1)
+        sim.frame_begin(frames[0])
+        for k in range(1, steps):
+            sim.step(1)
+            sim.frame_begin(frames[k & 1])
+            slots += len(sim.frame_end())        # frame k-1 is on the host
+        last = sim.frame_end()
+        return slots + len(last), last
+
+    e2e_loop(3)
+    barrier()
+    e0 = time.perf_counter()
+    slots_read, last_frame = e2e_loop(args.e2e_steps)
+    e_dt = time.perf_counter() - e0
+    living_in_frame = int((~np.isnan(last_frame[:, 0])).sum())
+    d2h = 8.0 * slots_read / args.e2e_steps
+    alive_e2e = sim.count_alive()
+    t = torch.tensor([e_dt, float(alive_e2e), d2h, float(living_in_frame)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e_dt = float(tmax[0].item())
+    alive_e2e_total, d2h_total, living_in_frame = float(t[1].item()), float(t[2].item()), int(t[3].item())
+    e2e_value = alive_e2e_total * args.e2e_steps / e_dt
+
+    # the round-1 definition, kept for continuity: the whole per-actor state `draw` could want (alive,
+    # location kind, container, road side, pos-param), fetched synchronously after every tick
+    n = cap
+    pin = lambda dt: torch.empty(n, dtype=dt, pin_memory=True).numpy()
+    bufs = [pin(torch.uint8), pin(torch.uint8), pin(torch.int32), pin(torch.uint8), pin(torch.float64)]
     ptrs = [b.ctypes.data_as(C.c_void_p) for b in bufs] + [None] * 6
     gid_buf = pin(torch.int32) if world > 1 else None
     n_local = C.c_int64(0)
 
-    def e2e_step():
+    def full_state_step():
         sim.step(1)
         if world == 1:
             rc = L.griddy_download_actors(sim.h, *ptrs)
@@ -341,34 +377,28 @@ def main():
             rc = L.griddy_download_local(sim.h, C.c_int64(n), C.byref(n_local), gid_buf.ctypes.data_as(C.c_void_p), *ptrs)
         assert rc == 0, L.griddy_last_error(sim.h)
 
-    for _ in range(3):
-        e2e_step()
+    full_steps = max(1, min(args.e2e_steps, 5))
+    full_state_step()
     barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
+    f0 = time.perf_counter()
+    for _ in range(full_steps):
+        full_state_step()
     torch.cuda.synchronize()
-    e_dt = time.perf_counter() - e0
+    f_dt = time.perf_counter() - f0
     if world > 1:
-        t = torch.tensor([e_dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_dt = float(t.item())
-    if world > 1:
-        d2h = int(n_local.value) * (sum(b.itemsize for b in bufs) + 4)
-        t = torch.tensor([float(d2h)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        d2h = int(t.item()) // world
+        full_bytes = int(n_local.value) * (sum(b.itemsize for b in bufs) + 4)
         alive = int(bufs[0][: n_local.value].sum())
         on_road = int((bufs[0][: n_local.value] & bufs[1][: n_local.value]).sum())
+        t = torch.tensor([float(alive), float(full_bytes)], device="cuda", dtype=torch.float64)
+        tm = torch.tensor([f_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        full_value, full_bytes = float(t[0].item()) * full_steps / float(tm.item()), int(t[1].item())
     else:
+        full_bytes = sum(b.nbytes for b in bufs)
         alive = int(bufs[0].sum())
         on_road = int((bufs[0] & bufs[1]).sum())
-    if world > 1:
-        t = torch.tensor([float(alive)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e_value = float(t.item()) * args.e2e_steps / e_dt
-    else:
-        e2e_value = alive * args.e2e_steps / e_dt
+        full_value = alive * full_steps / f_dt
 
     if rank != 0:
         if world > 1:
@@ -390,10 +420,17 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "actor-updates/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": d2h * world,
-                "note": "per step: griddy_step(1) + griddy_download_actors of what draw reads (alive, location "
-                        "kind, container, side, pos-param) into pinned host arrays; no per-step input exists: "
-                        "the world is uploaded once through the same ABI before the timed region"},
+                "d2h_bytes_per_step": int(d2h_total), "steps": args.e2e_steps,
+                "living_actors_in_last_frame": living_in_frame,
+                "note": "per step: one `update` (griddy_step(1)) + one `draw` read-back: (get-pos actor) of every "
+                        "slot computed on the device (spatial.scm:125-149), float x,y, copied into pinned host memory "
+                        "with griddy_positions_begin/_end — the copy of frame t overlaps tick t+1, every frame is on "
+                        "the host inside the timed region; no per-step input exists: the world is uploaded once "
+                        "through the same ABI before the timed region"},
+        "e2e_full_state": {"value": full_value, "unit": "actor-updates/s", "d2h_bytes_per_step": full_bytes,
+                           "steps": full_steps,
+                           "note": "round-1 definition: griddy_step(1) + synchronous griddy_download_actors of alive, "
+                                   "location kind, container, side, pos-param (15 bytes per actor)"},
         "gpu_launches": launches,
         "clocks": clocks,
         # The tick is four kernels of comparable duration, so the roofline is stated for the whole

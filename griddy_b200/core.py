@@ -275,6 +275,24 @@ def get_pos(obj, beg_or_end=None):   # spatial.scm:104-122
     raise GriddyError("not-implemented", obj)
 
 
+def get_width(segment: RoadSegment):   # spatial.scm:47-50
+    return (1 + Fraction(ROAD_SEGMENT_WIGGLE_ROOM_PCT, 100)) * ROAD_LANE_WIDTH * get_lane_count(segment)
+
+
+def get_pos_of_location(loc):   # spatial.scm:125-146
+    """(get-pos location): where `draw` puts the actor's circle (draw.scm:74-76)."""
+    if isinstance(loc, LocationOffRoad):
+        seg = loc.road_segment
+        sign = 1 if loc.road_side_direction == "forw" else -1
+        scale = sign * Fraction(1, 2) * get_width(seg) * (1 + 2 * Fraction(ROAD_SEGMENT_WIGGLE_ROOM_PCT, 100))
+        v_offset = _vmul(get_ortho_vec(seg), scale)
+        return _vadd(_vadd(get_pos(seg, "beg"), v_offset), _vmul(get_vec(seg), loc.pos_param))
+    lane = loc.road_lane
+    if isinstance(lane, RoadLaneSegment):
+        return _vadd(get_pos(lane, "beg"), _vmul(get_vec(lane), loc.pos_param))
+    return _bezier_at(lane.curve, loc.pos_param)
+
+
 def get_vec(obj):   # spatial.scm:152-158
     return _vsub(get_pos(obj, "end"), get_pos(obj, "beg"))
 

@@ -72,24 +72,23 @@ __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_
 // Lanes whose list must be rebuilt this tick are collected per block in shared memory and flushed to
 // Params::touched with one global atomic per block (a same-address atomic per lane would serialise).
 struct TouchSink {
-  int32_t* list;   // shared, SINK_CAP entries
-  int32_t* count;  // shared
+  int32_t *left, *n_left;         // shared: lanes that lost an actor or hold a ghost (k_unlink), SLOW_THREADS entries
+  int32_t *entered, *n_entered;   // shared: lanes that gained an actor (k_link), SLOW_THREADS entries
 };
-constexpr int SLOW_THREADS = 128;
-constexpr int SINK_CAP = 3 * SLOW_THREADS;   // an actor touches at most its old lane, its new lane and a ghost's lane
+constexpr int SLOW_THREADS = 128;   // an actor leaves at most one lane (its own, ghost or not) and enters at most one
 
-__device__ __forceinline__ void mark_touched(const Params& p, int32_t lane, int tick, const TouchSink& sink) {
-  if (atomicExch(&p.lane[lane].mark, tick + 1) != tick + 1) sink.list[atomicAdd(sink.count, 1)] = lane;
+__device__ __forceinline__ void mark_left(const Params& p, int32_t lane, int tick, const TouchSink& sink) {
+  if (atomicExch(&p.lane[lane].mark_out, tick + 1) != tick + 1) sink.left[atomicAdd(sink.n_left, 1)] = lane;
 }
 
 __device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
   p.cold[a].inbox_next = atomicExch(&p.lane[lane].inbox, a);
-  mark_touched(p, lane, tick, sink);
+  if (atomicExch(&p.lane[lane].mark_in, tick + 1) != tick + 1) sink.entered[atomicAdd(sink.n_entered, 1)] = lane;
 }
 
 __device__ __forceinline__ void leave_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
   p.cold[a].outbox_next = atomicExch(&p.lane[lane].outbox, a);
-  mark_touched(p, lane, tick, sink);
+  mark_left(p, lane, tick, sink);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -155,7 +154,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
       ah = p.sa[ah].ahead;
       if (ah >= 0) lead = pos_old[ah];
     } while (ah >= 0 && lead == cur);
-    mark_touched(p, lane, tick, sink);
+    mark_left(p, lane, tick, sink);
   }
 
   if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {   // advance-on-route$  route.scm:137-141
@@ -271,7 +270,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 // arrays.  Any other actor — a few percent — would drag its whole warp through chains of dependent
 // gathers, so its slot is appended to the slow list instead (block-aggregated: one global atomic per
 // block) and k_slow runs the full advance$ for it with one thread per listed actor.
-// Measured on B200 (profiles/r2_variants.md): 2 slots per thread = 40 registers = 6 blocks per SM beats
+// Measured on B200 (profiles/r1_variants.md): 2 slots per thread = 40 registers = 6 blocks per SM beats
 // 3 slots (58 registers with the slow list's payload, 4 blocks) and 3 slots capped at 48 registers.
 #ifndef ADV_UNROLL
 #define ADV_UNROLL 2
@@ -373,16 +372,16 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick) {
 // k_slow: the full advance$ for the actors k_advance deferred, one thread per actor, so that the
 // chains of dependent gathers of 32 such actors overlap instead of stalling 31 idle lanes.
 __global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
-  __shared__ int32_t s_touched[SINK_CAP];
-  __shared__ int32_t s_nt, s_base;
+  __shared__ int32_t s_left[SLOW_THREADS], s_entered[SLOW_THREADS];
+  __shared__ int32_t s_nl, s_ne, s_base_l, s_base_e;
   const int par = tick & 1;
   int32_t* counters = p.counters + CNT_STRIDE * par;
   const int32_t n_slow = counters[CNT_SLOW];
   const double* __restrict__ pos_old = p.pos[par];
   double* __restrict__ pos_new = p.pos[par ^ 1];
-  const TouchSink sink{s_touched, &s_nt};
+  const TouchSink sink{s_left, &s_nl, s_entered, &s_ne};
   for (int32_t chunk = blockIdx.x * SLOW_THREADS; chunk < n_slow; chunk += gridDim.x * SLOW_THREADS) {
-    if (threadIdx.x == 0) s_nt = 0;
+    if (threadIdx.x == 0) s_nl = s_ne = 0;
     __syncthreads();
     const int32_t i = chunk + threadIdx.x;
     if (i < n_slow) {
@@ -408,10 +407,12 @@ __global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
       }
     }
     __syncthreads();
-    const int nt = s_nt;
-    if (threadIdx.x == 0 && nt) s_base = atomicAdd(&counters[CNT_TOUCHED], nt);
+    const int nl = s_nl, ne = s_ne;
+    if (threadIdx.x == 0 && nl) s_base_l = atomicAdd(&counters[CNT_LEFT], nl);
+    if (threadIdx.x == 1 && ne) s_base_e = atomicAdd(&counters[CNT_ENTERED], ne);
     __syncthreads();
-    for (int k = threadIdx.x; k < nt; k += SLOW_THREADS) p.touched[s_base + k] = s_touched[k];
+    if (threadIdx.x < nl) p.touched[s_base_l + threadIdx.x] = s_left[threadIdx.x];
+    if (threadIdx.x < ne) p.touched[p.cap + s_base_e + threadIdx.x] = s_entered[threadIdx.x];
   }
 }
 

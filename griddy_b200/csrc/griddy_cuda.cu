@@ -152,6 +152,14 @@ struct Ctx {
   // read-back staging
   uint8_t* d_ghost = nullptr;
   uint8_t* d_pack = nullptr;
+  // drawing read-back (griddy_download_positions, griddy_positions_begin / _end)
+  const double2* d_geom = nullptr;          // 4 x double2 per item (griddy_upload_geometry)
+  cudaStream_t draw_stream = nullptr;        // carries the copies of finished frames while the next ticks run
+  float2* d_xy32[2] = {nullptr, nullptr};    // two frames in flight at most
+  uint8_t* d_xy_sync = nullptr;              // staging of griddy_download_positions: [xy64 16][xy32 8][gid 4] per slot
+  cudaEvent_t ev_drawn[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  int64_t frame_n[2] = {0, 0};
+  uint64_t frames_begun = 0, frames_ended = 0;
   // host copies needed to format downloads
   std::vector<uint8_t> h_kind;
   std::vector<int32_t> h_lane_junction, h_lane_out;
@@ -403,6 +411,11 @@ void griddy_destroy(void* ctx) {
   free_pool(c->actor_allocs);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int f = 0; f < 2; ++f) {
+    if (c->ev_drawn[f]) cudaEventDestroy(c->ev_drawn[f]);
+    if (c->ev_copied[f]) cudaEventDestroy(c->ev_copied[f]);
+  }
+  if (c->draw_stream) cudaStreamDestroy(c->draw_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -457,6 +470,7 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   p.n_items = n_items;
   p.grid_n = 0;
   p.turn4 = nullptr;
+  c->d_geom = nullptr;
   TRY(dev_alloc(c, c->net_allocs, &p.item, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.lane, n_items));
   TRY(dev_alloc(c, c->net_allocs, &p.occ, n_items));
@@ -598,6 +612,9 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   CUDA_TRY(c, cudaSetDevice(c->device));
   free_pool(c->actor_allocs);
   c->have_actors = false;
+  c->d_xy32[0] = c->d_xy32[1] = nullptr;
+  c->d_xy_sync = nullptr;
+  c->frames_begun = c->frames_ended = 0;
   Params& p = c->p;
   p.n_actors = n;
   const int64_t extra = c->mg.on ? c->mg.extra_slots : 0;   // room for actors arriving from other ranks
@@ -1422,6 +1439,115 @@ int griddy_mg_connect_local(void** ctxs, int32_t n) {
           for (int par = 0; par < 2; ++par) c->p.mig_peer[nb.rank][par] = nb.peer_mig[par] = back.d_mig_recv[par];
   }
   return GRIDDY_OK;
+}
+
+// ---- drawing read-back ---------------------------------------------------------------------------
+int griddy_upload_geometry(void* ctx, const double* geom) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_net || !geom) return fail(c, GRIDDY_ERR_BAD_ARG, "upload_geometry: no network or null array");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const double2* d = nullptr;
+  TRY(dev_upload(c, c->net_allocs, &d, (const double2*)geom, 4 * c->p.n_items));
+  c->d_geom = d;
+  return GRIDDY_OK;
+}
+
+namespace {
+
+// Enqueue (get-pos actor) of every slot on the compute stream, behind the ticks run so far.
+int launch_positions(Ctx* c, double2* xy64, float2* xy32, int32_t* gid) {
+  const int32_t ns = c->ns_host;
+  if (ns <= 0) return GRIDDY_OK;
+  const unsigned blocks = (unsigned)((ns + 255) / 256);
+  const int par = (int)(c->tick & 1);
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ghost, 0, (size_t)ns, c->stream));
+  k_flag_ghosts<<<blocks, 256, 0, c->stream>>>(c->p, par, c->d_ghost);
+  k_positions<<<blocks, 256, 0, c->stream>>>(c->p, par, c->d_geom, c->d_ghost, xy64, xy32, gid);
+  c->launches += 2;
+  CUDA_TRY(c, cudaGetLastError());
+  return GRIDDY_OK;
+}
+
+int positions_ready(Ctx* c, const char* who) {
+  if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, std::string(who) + " before upload_actors");
+  if (!c->d_geom) return fail(c, GRIDDY_ERR_BAD_ARG, std::string(who) + " before upload_geometry");
+  return GRIDDY_OK;
+}
+
+}  // namespace
+
+int griddy_download_positions(void* ctx, int64_t capacity, int64_t* n, double* xy64, float* xy32, int32_t* gid) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  TRY(positions_ready(c, "download_positions"));
+  if (!n) return fail(c, GRIDDY_ERR_BAD_ARG, "download_positions: null n");
+  const int64_t ns = c->ns_host;
+  *n = ns;
+  if (capacity < ns) return fail(c, GRIDDY_ERR_BAD_ARG, "download_positions: arrays too small, need " + std::to_string(ns));
+  if (ns == 0) return GRIDDY_OK;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!c->d_xy_sync) TRY(dev_alloc(c, c->actor_allocs, &c->d_xy_sync, 28 * (int64_t)c->p.cap));
+  double2* d64 = (double2*)c->d_xy_sync;
+  float2* d32 = (float2*)(c->d_xy_sync + 16 * (size_t)c->p.cap);
+  int32_t* dg = (int32_t*)(c->d_xy_sync + 24 * (size_t)c->p.cap);
+  TRY(launch_positions(c, xy64 ? d64 : nullptr, xy32 ? d32 : nullptr, gid ? dg : nullptr));
+  if (xy64) CUDA_TRY(c, cudaMemcpyAsync(xy64, d64, (size_t)ns * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+  if (xy32) CUDA_TRY(c, cudaMemcpyAsync(xy32, d32, (size_t)ns * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  if (gid) CUDA_TRY(c, cudaMemcpyAsync(gid, dg, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return GRIDDY_OK;
+}
+
+int griddy_positions_begin(void* ctx, float* xy32, int64_t capacity) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  TRY(positions_ready(c, "positions_begin"));
+  if (!xy32) return fail(c, GRIDDY_ERR_BAD_ARG, "positions_begin: null buffer");
+  if (c->frames_begun - c->frames_ended >= 2) return fail(c, GRIDDY_ERR_BAD_STATE, "positions_begin: two frames are in flight already (call griddy_positions_end)");
+  const int64_t ns = c->ns_host;
+  if (capacity < ns) return fail(c, GRIDDY_ERR_BAD_ARG, "positions_begin: buffer too small, need " + std::to_string(ns));
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!c->draw_stream) {
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->draw_stream, cudaStreamNonBlocking));
+    for (int f = 0; f < 2; ++f) {
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_drawn[f], cudaEventDisableTiming));
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[f], cudaEventDisableTiming));
+    }
+  }
+  if (!c->d_xy32[0])
+    for (int f = 0; f < 2; ++f) TRY(dev_alloc(c, c->actor_allocs, &c->d_xy32[f], c->p.cap));
+  const int f = (int)(c->frames_begun & 1);   // its previous user has been waited for by griddy_positions_end
+  TRY(launch_positions(c, nullptr, c->d_xy32[f], nullptr));
+  CUDA_TRY(c, cudaEventRecord(c->ev_drawn[f], c->stream));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->draw_stream, c->ev_drawn[f], 0));
+  if (ns > 0) CUDA_TRY(c, cudaMemcpyAsync(xy32, c->d_xy32[f], (size_t)ns * sizeof(float2), cudaMemcpyDeviceToHost, c->draw_stream));
+  CUDA_TRY(c, cudaEventRecord(c->ev_copied[f], c->draw_stream));
+  c->frame_n[f] = ns;
+  ++c->frames_begun;
+  return GRIDDY_OK;
+}
+
+int griddy_positions_end(void* ctx, int64_t* n) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (c->frames_begun == c->frames_ended) return fail(c, GRIDDY_ERR_BAD_STATE, "positions_end without positions_begin");
+  const int f = (int)(c->frames_ended & 1);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaEventSynchronize(c->ev_copied[f]));
+  if (n) *n = c->frame_n[f];
+  ++c->frames_ended;
+  return GRIDDY_OK;
+}
+
+void* griddy_host_alloc(int64_t bytes) {
+  void* ptr = nullptr;
+  if (bytes <= 0 || cudaHostAlloc(&ptr, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return ptr;
+}
+
+void griddy_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
 }
 
 int griddy_count_alive(void* ctx, int64_t* n_alive) {

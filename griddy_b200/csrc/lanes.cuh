@@ -42,7 +42,7 @@ __device__ int later_processed(const Params& p, int x, int y, int32_t lane, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_unlink / k_link: one thread per lane that an actor entered or left this tick.  Lanes are doubly
+// k_unlink: one thread per lane that an actor left this tick; k_link: one per lane that an actor entered.  Lanes are doubly
 // linked lists in ascending pos-param, so nothing walks a whole lane.
 //   k_unlink  takes the lane's leavers (its outbox) and the ghosts found on it this tick out of the
 //             list in O(1) each, and settles the actors that are done for this tick: a ghost's move is
@@ -60,7 +60,7 @@ constexpr int32_t UNLINKED = -3;
 
 __global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
   const int par = tick & 1;
-  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
+  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_LEFT];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = p.touched[i];
     const LaneDyn ld = p.lane[lane];
@@ -102,11 +102,12 @@ __global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
 
 __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
   const int par = tick & 1;
-  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_TOUCHED];
+  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_ENTERED];
   const double* __restrict__ pos_old = p.pos[par];
   const double* __restrict__ pos_new = p.pos[par ^ 1];
+  const int32_t* __restrict__ entered = p.touched + p.cap;
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
-    const int32_t lane = p.touched[i];
+    const int32_t lane = entered[i];
     const LaneDyn ld = p.lane[lane];
     const int32_t inbox = ld.inbox;
     if (inbox < 0) continue;

@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const 
     p.cold[a].dead_mark = 0;
     // onto the lane's inbox
     p.cold[a].inbox_next = atomicExch(&p.lane[r.container].inbox, a);
-    if (atomicExch(&p.lane[r.container].mark, tick + 1) != tick + 1)
-      p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_TOUCHED], 1)] = r.container;
+    if (atomicExch(&p.lane[r.container].mark_in, tick + 1) != tick + 1)
+      p.touched[p.cap + atomicAdd(&p.counters[CNT_STRIDE * par + CNT_ENTERED], 1)] = r.container;
   }
 }
 

@@ -51,4 +51,52 @@ __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uin
   if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? p.cold[a].hop : -2;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Drawing read-back: (get-pos actor) for every slot (spatial.scm:125-149), which is all that `draw`
+// reads of an actor (simulate.scm:155-160 -> draw.scm:74-88).  geom holds 8 doubles per item,
+// computed by the host with the reference's own get-pos / get-vec / curve (include/griddy_cuda.h,
+// griddy_upload_geometry) — like the lane lengths, because they go through Chickadee's vec2:
+//   off road      (v-beg + v-offset) + pos-param * (get-vec segment)      spatial.scm:125-136
+//   segment lane  (get-pos lane 'beg) + pos-param * (get-vec lane)         spatial.scm:142-144
+//   junction lane bezier-curve-point-at curve pos-param                    spatial.scm:145-146
+// one rounding per vec2 operation and component.  A slot without a living actor gets NaN, NaN.
+__device__ __forceinline__ double bezier_1d(double w0, double w1, double w2, double w3, double a, double b, double c, double d) {
+  return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w0, a), __dmul_rn(w1, b)), __dmul_rn(w2, c)), __dmul_rn(w3, d));
+}
+
+__global__ void __launch_bounds__(256) k_positions(Params p, int par, const double2* __restrict__ geom,
+                                                    const uint8_t* __restrict__ ghost, double2* __restrict__ xy64,
+                                                    float2* __restrict__ xy32, int32_t* __restrict__ gid) {
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= p.scal[SC_NSLOTS]) return;
+  const uint32_t st = p.sa[a].st;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double x = nan, y = nan;
+  int32_t id = -1;
+  if ((st & ST_ALIVE) && !ghost[a]) {
+    const int32_t c = p.cold[a].container;
+    id = p.cold[a].gid;
+    const double t = p.pos[par][a];
+    const double2* g = geom + 4 * (int64_t)c;
+    if (!(st & ST_ONROAD) || p.item[c].kind == GRIDDY_SEGMENT_LANE) {
+      const double2 o = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? g[2] : g[0];
+      const double2 v = g[1];
+      x = __dadd_rn(o.x, __dmul_rn(t, v.x));
+      y = __dadd_rn(o.y, __dmul_rn(t, v.y));
+    } else {   // chickadee bezier-curve-point-at (not vendored; the form tests/golden/minischeme.py assumes)
+      const double2 p0 = g[0], p1 = g[1], p2 = g[2], p3 = g[3];
+      const double u = __dsub_rn(1.0, t);
+      const double w0 = __dmul_rn(__dmul_rn(u, u), u);
+      const double w1 = __dmul_rn(__dmul_rn(__dmul_rn(3.0, u), u), t);
+      const double w2 = __dmul_rn(__dmul_rn(__dmul_rn(3.0, u), t), t);
+      const double w3 = __dmul_rn(__dmul_rn(t, t), t);
+      x = bezier_1d(w0, w1, w2, w3, p0.x, p1.x, p2.x, p3.x);
+      y = bezier_1d(w0, w1, w2, w3, p0.y, p1.y, p2.y, p3.y);
+    }
+  }
+  if (xy64) xy64[a] = make_double2(x, y);
+  if (xy32) xy32[a] = make_float2((float)x, (float)y);
+  if (gid) gid[a] = id;
+}
+
 }  // namespace griddy

@@ -20,7 +20,7 @@ constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_J
               DEV_ERR_MIG_AGENDA = 128;
 
 // Params::counters[parity][...]
-constexpr int CNT_EMIG = 0, CNT_TOUCHED = 1, CNT_SLOW = 2, CNT_STRIDE = 4;
+constexpr int CNT_EMIG = 0, CNT_LEFT = 1, CNT_SLOW = 2, CNT_ENTERED = 3, CNT_STRIDE = 4;
 // device scalars (Params::scal)
 constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_COUNT = 4;
 constexpr int MAX_RANKS = 8;     // one box
@@ -74,9 +74,10 @@ struct __align__(16) Item {
 struct __align__(16) LaneDyn {
   int32_t tail;      // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
   int32_t inbox, outbox, ghosts;
-  int32_t mark;      // tick+1 once the lane is on this tick's touched list
+  int32_t mark_out;  // tick+1 once the lane is on this tick's list of lanes that lost an actor (k_unlink's work)
   int32_t junction;  // junction lanes: their junction (whose occupancy they count towards), else -1
-  int32_t pad[2];
+  int32_t mark_in;   // tick+1 once the lane is on this tick's list of lanes that gained an actor (k_link's work)
+  int32_t pad;
 };
 static_assert(sizeof(Item) == 32 && sizeof(LaneDyn) == 32, "one sector per record");
 
@@ -108,9 +109,11 @@ struct Params {
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
   // per-tick scratch, by slot
+  // lanes an actor left (or a ghost was found on) / entered this tick: [0, cap) and [cap, 2 cap).  Two
+  // lists, so that k_unlink and k_link each fetch only the lane records they have work on.
   int32_t* touched;
   int4* slow;   // deferred actors: {slot (~slot: turn-onto), st, pos-param lo, hi} as k_advance read them
-  int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, touched lanes, deferred actors
+  int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, lanes left, deferred actors, lanes entered
   double dt, two_size;
   // multi-GPU (owner == null on a single GPU): spatial partition, see "Multi-GPU" below
   const int32_t* owner;      // rank that owns each item

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_lane_init(LaneDyn* __restrict__ lane, c
   const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (r >= n) return;
   const Item it = item[r];
-  lane[r] = LaneDyn{-1, -1, -1, -1, 0, it.kind == GRIDDY_JUNCTION_LANE ? it.link2 : -1, {0, 0}};
+  lane[r] = LaneDyn{-1, -1, -1, -1, 0, it.kind == GRIDDY_JUNCTION_LANE ? it.link2 : -1, 0, 0};
 }
 
 __global__ void __launch_bounds__(256) k_lane_set_tail(LaneDyn* __restrict__ lane, const int32_t* __restrict__ which,

@@ -166,14 +166,21 @@ V2 bezier_at(V2 p0, V2 p1, V2 p2, V2 p3, double t) {
 }
 
 // spatial.scm:34-46 with the curve of core.scm:196-206.
-double jlane_length(const Geo& geo, int jreg, const Seg& in, int in_dir, int in_rank, const Seg& out,
-                    int out_dir, int out_rank) {
+void jlane_curve(const Geo& geo, int jreg, const Seg& in, int in_dir, int in_rank, const Seg& out,
+                 int out_dir, int out_rank, V2 p[4]) {
   // (* 2 radius (/ 20 100)) is an exact rational in the reference; convert once, correctly rounded
   const double offset = (2.0 * geo.jrad(jreg) * 20.0) / 100.0;
-  V2 p0 = geo.lane_pos(in, in_dir, in_rank, true);
-  V2 p3 = geo.lane_pos(out, out_dir, out_rank, false);
-  V2 p1 = vadd(p0, vmul(geo.lane_tangent(in, in_dir), offset));
-  V2 p2 = vsub(p3, vmul(geo.lane_tangent(out, out_dir), offset));
+  p[0] = geo.lane_pos(in, in_dir, in_rank, true);
+  p[3] = geo.lane_pos(out, out_dir, out_rank, false);
+  p[1] = vadd(p[0], vmul(geo.lane_tangent(in, in_dir), offset));
+  p[2] = vsub(p[3], vmul(geo.lane_tangent(out, out_dir), offset));
+}
+
+double jlane_length(const Geo& geo, int jreg, const Seg& in, int in_dir, int in_rank, const Seg& out,
+                    int out_dir, int out_rank) {
+  V2 cp[4];
+  jlane_curve(geo, jreg, in, in_dir, in_rank, out, out_dir, out_rank, cp);
+  const V2 p0 = cp[0], p1 = cp[1], p2 = cp[2], p3 = cp[3];
   double acc = 0.0;
   V2 lo = bezier_at(p0, p1, p2, p3, 0.0);
   for (int k = 1; k <= 5; ++k) {
@@ -306,6 +313,60 @@ int synth_grid_network(int n, double spacing, double origin, uint8_t* kind, doub
             lane_in[jl] = lin;
             lane_junction[jl] = jreg;
             turn4[4 * (int64_t)lin + lane_heading(out, dout)] = jl;
+          }
+        }
+    }
+  return reg == n_items ? 0 : 2;
+}
+
+// Geometry for the drawing read-back (include/griddy_cuda.h, griddy_upload_geometry): 8 doubles per
+// item, the fp64 restatement of spatial.scm:104-158 used for the lane lengths above (self-consistent
+// only, like them).  Items are visited in the order synth_grid_network registers them.
+int synth_grid_geometry(int n, double spacing, double origin, double* geom) {
+  if (n < 1) return 1;
+  Grid g; g.n = n;
+  build_segments(g);
+  Geo geo(spacing, origin, &g);
+  int64_t n_items, nj, ns, nsl, njl;
+  synth_grid_sizes(n, &n_items, &nj, &ns, &nsl, &njl);
+  for (int64_t k = 0; k < 8 * n_items; ++k) geom[k] = 0.0;
+  auto put = [&](int64_t item, int at, V2 v) { geom[8 * item + at] = v.x; geom[8 * item + at + 1] = v.y; };
+  for (const Seg& s : g.segs) {
+    const V2 beg = geo.seg_pos(s, false);
+    const V2 vec = vsub(geo.seg_pos(s, true), beg);
+    // spatial.scm:125-136 with get-width spatial.scm:47-50: v-offset = ortho * (sign * 1/2 * (6/5 * 15 * lanes)
+    // * 7/5) — the scalar is the exact rational 63 * lanes / 5, converted once
+    const int lc = s.cnt[FORW] + s.cnt[BACK];
+    const double w = (63.0 * (double)lc) / 5.0;
+    const V2 o = geo.seg_ortho(s);
+    put(s.reg, 0, vadd(beg, vmul(o, w)));
+    put(s.reg, 2, vec);
+    put(s.reg, 4, vadd(beg, vmul(o, -w)));
+    for (int d = 0; d < 2; ++d)
+      for (int r = 0; r < s.cnt[d]; ++r) {
+        const V2 lb = geo.lane_pos(s, d, r, false);
+        put(s.lane[d][r], 0, lb);
+        put(s.lane[d][r], 2, vsub(geo.lane_pos(s, d, r, true), lb));
+      }
+  }
+  int64_t reg = g.n_items_before_jlanes;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      int segs[4];
+      const int c = junction_segments(g, i, j, segs);
+      const int jreg = i * n + j;
+      for (int a = 0; a < c; ++a)
+        for (int b = 0; b < c; ++b) {
+          const Seg& in = g.segs[segs[a]];
+          const Seg& out = g.segs[segs[b]];
+          const int din = in.jend == jreg ? FORW : BACK;
+          const int dout = out.jend == jreg ? BACK : FORW;
+          const int m = in.cnt[din] < out.cnt[dout] ? in.cnt[din] : out.cnt[dout];
+          for (int k = 0; k < m; ++k) {
+            V2 cp[4];
+            jlane_curve(geo, jreg, in, din, in.cnt[din] - 1 - k, out, dout, out.cnt[dout] - 1 - k, cp);
+            for (int q = 0; q < 4; ++q) put(reg, 2 * q, cp[q]);
+            ++reg;
           }
         }
     }

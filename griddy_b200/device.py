@@ -28,7 +28,8 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_debug_sort_pairs", "griddy_count_alive", "griddy_mg_configure", "griddy_mg_set_global_ids",
            "griddy_mg_nccl_unique_id", "griddy_mg_connect_nccl", "griddy_mg_connect_local", "griddy_mg_step_local",
            "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
-           "griddy_mg_ipc_import")
+           "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
+           "griddy_positions_end", "griddy_host_alloc", "griddy_host_free")
 
 
 class GriddyCudaError(RuntimeError):
@@ -58,6 +59,10 @@ def lib():
         L.griddy_slots_in_use.argtypes = [C.c_void_p]
         L.griddy_destroy.restype = None
         L.griddy_destroy.argtypes = [C.c_void_p]
+        L.griddy_host_alloc.restype = C.c_void_p
+        L.griddy_host_alloc.argtypes = [C.c_int64]
+        L.griddy_host_free.restype = None
+        L.griddy_host_free.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -90,6 +95,9 @@ class Simulation:
                                           _p(net.seg_outer_back)))
         if net.loc_key is not None:
             self._chk(L.griddy_set_locality_keys(self.h, _p(net.loc_key)))
+        if net.geom is not None:
+            self._chk(L.griddy_upload_geometry(self.h, _p(net.geom)))
+        self._frames = []
         if reorder_period is not None:
             self._chk(L.griddy_set_reorder_period(self.h, C.c_int32(reorder_period)))
         if actors.route_off is None:
@@ -181,6 +189,29 @@ class Simulation:
         out["order"] = out["order"][: n_order.value]
         return out
 
+    def positions(self, f32: bool = False):
+        """(get-pos actor) of every slot (spatial.scm:125-149): xy [n, 2] (NaN where the slot holds no living
+        actor) and the actor id per slot (-1: none).  Needs a network with `geom`."""
+        cap = max(self.slots_in_use, 1)
+        xy = np.zeros((cap, 2), np.float32 if f32 else np.float64)
+        gid = np.zeros(cap, np.int32)
+        n = C.c_int64(0)
+        self._chk(lib().griddy_download_positions(self.h, C.c_int64(cap), C.byref(n), None if f32 else _p(xy),
+                                                  _p(xy) if f32 else None, _p(gid)))
+        return xy[: n.value], gid[: n.value]
+
+    def frame_begin(self, buf: "PinnedFrame"):
+        """Start the asynchronous read-back of a frame (float x, y per slot) into pinned host memory."""
+        self._chk(lib().griddy_positions_begin(self.h, C.c_void_p(buf.ptr), C.c_int64(buf.capacity)))
+        self._frames.append(buf)
+
+    def frame_end(self) -> np.ndarray:
+        """Wait for the oldest frame begun; returns its [n, 2] float32 view of the pinned buffer."""
+        n = C.c_int64(0)
+        self._chk(lib().griddy_positions_end(self.h, C.byref(n)))
+        buf = self._frames.pop(0)
+        return buf.array[: n.value]
+
     def occupancy(self):
         lane_count = np.zeros(self.net.n_items, np.int32)
         junction_count = np.zeros(self.net.n_items, np.int32)
@@ -197,6 +228,23 @@ class Simulation:
             self.close()
         except Exception:
             pass
+
+
+class PinnedFrame:
+    """Page-locked host memory for one frame of `capacity` float pairs (griddy_host_alloc)."""
+
+    def __init__(self, capacity: int):
+        self.capacity = int(capacity)
+        self.ptr = lib().griddy_host_alloc(C.c_int64(8 * max(self.capacity, 1)))
+        if not self.ptr:
+            raise GriddyCudaError(5, "griddy_host_alloc failed")
+        self.array = np.ctypeslib.as_array((C.c_float * (2 * self.capacity)).from_address(self.ptr)).reshape(-1, 2)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().griddy_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
 
 
 def connect_nccl(sim: "Simulation"):

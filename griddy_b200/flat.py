@@ -45,6 +45,7 @@ class FlatNetwork:
     turn4: Optional[np.ndarray] = None         # i32 [n_items,4] next-hop table by heading
     seg_reg: Optional[np.ndarray] = None       # i32 segment ordinal -> registration id
     loc_key: Optional[np.ndarray] = None       # u32 locality key per item (griddy_set_locality_keys)
+    geom: Optional[np.ndarray] = None          # f64 [n_items,8] drawing geometry (griddy_upload_geometry)
 
     def __post_init__(self):
         self.kind = _arr(self.kind, np.uint8)
@@ -58,6 +59,9 @@ class FlatNetwork:
                 setattr(self, name, _arr(v, np.int32))
         if self.loc_key is not None:
             self.loc_key = _arr(self.loc_key, np.uint32)
+        if self.geom is not None:
+            self.geom = _arr(self.geom, np.float64).reshape(-1, 8)
+            assert self.geom.shape[0] == self.kind.shape[0], "geom needs 8 doubles per item"
 
     @property
     def n_items(self) -> int:

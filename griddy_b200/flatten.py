@@ -60,6 +60,23 @@ def flatten_network(world: core.World):
                        lane_in=lane_in), idx
 
 
+def flatten_geometry(world: core.World, idx: dict) -> np.ndarray:
+    """Drawing geometry, 8 doubles per item (include/griddy_cuda.h, griddy_upload_geometry): what the
+    Guile glue computes with the reference's own get-pos / get-vec / curve (guile/griddy/cuda.scm)."""
+    geom = np.zeros((len(idx), 8), np.float64)
+    for item, r in idx.items():
+        if isinstance(item, core.RoadLaneSegment):
+            geom[r, 0:2] = core.get_pos(item, "beg")
+            geom[r, 2:4] = core.get_vec(item)
+        elif isinstance(item, core.RoadLaneJunction):
+            geom[r] = [c for pt in item.curve for c in pt]
+        elif isinstance(item, core.RoadSegment):
+            geom[r, 0:2] = core.get_pos_of_location(core.LocationOffRoad(item, "forw", 0))
+            geom[r, 2:4] = core.get_vec(item)
+            geom[r, 4:6] = core.get_pos_of_location(core.LocationOffRoad(item, "back", 0))
+    return geom
+
+
 def speed_dt_of(max_speed) -> float:
     """(exact->inexact (* max-speed *simulate/time-step*)) under Guile's numeric tower."""
     if isinstance(max_speed, float):

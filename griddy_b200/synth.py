@@ -37,7 +37,7 @@ def grid_sizes(n: int) -> dict:
     return {k: int(o.value) for k, o in zip(keys, out)}
 
 
-def grid_network(n: int, spacing: float = 150.0, origin: float = 50.0) -> FlatNetwork:
+def grid_network(n: int, spacing: float = 150.0, origin: float = 50.0, geometry: bool = False) -> FlatNetwork:
     """n x n junction grid of procedural-grid.scm:13-67 (n = 5 there)."""
     sz = grid_sizes(n)
     ni = sz["n_items"]
@@ -55,7 +55,17 @@ def grid_network(n: int, spacing: float = 150.0, origin: float = 50.0) -> FlatNe
     return FlatNetwork(kind, lane_len, lane_dir, lane_segment, lane_out, lane_junction, so_f, so_b,
                        lane_in=lane_in, grid_n=n, lane_from_j=lf, lane_to_j=lt,
                        turn4=turn4.reshape(ni, 4), seg_reg=seg_reg,
-                       loc_key=grid_locality_keys(kind, lf, lane_junction, so_f, lane_segment, n * n))
+                       loc_key=grid_locality_keys(kind, lf, lane_junction, so_f, lane_segment, n * n),
+                       geom=grid_geometry(n, spacing, origin) if geometry else None)
+
+
+def grid_geometry(n: int, spacing: float = 150.0, origin: float = 50.0) -> np.ndarray:
+    """Drawing geometry of the n x n grid, [n_items, 8] float64 (griddy_upload_geometry)."""
+    geom = np.empty((grid_sizes(n)["n_items"], 8), np.float64)
+    rc = _lib().synth_grid_geometry(C.c_int(n), C.c_double(spacing), C.c_double(origin), _p(geom))
+    if rc:
+        raise RuntimeError(f"synth_grid_geometry -> {rc}")
+    return geom
 
 
 def grid_locality_keys(kind, lane_from_j, lane_junction, seg_outer_forw, lane_segment, n_junctions) -> np.ndarray:

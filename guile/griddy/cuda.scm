@@ -21,8 +21,10 @@
   #:use-module (griddy util)
   #:use-module (griddy core)
   #:use-module (griddy simulate route)
+  #:use-module (chickadee math vector)
+  #:use-module (chickadee math bezier)
   #:export (cuda-open cuda-close cuda-upload-world! cuda-step! cuda-download-world!
-            cuda-last-step-ms))
+            cuda-last-step-ms cuda-positions make-frame-buffer cuda-frame-begin! cuda-frame-end!))
 
 (define %lib (dynamic-link (or (getenv "GRIDDY_CUDA_LIB") "libgriddy_cuda")))
 
@@ -38,6 +40,12 @@
 (define %step     (c-fn "griddy_step" int '* int64))
 (define %download (c-fn "griddy_download_actors" int '* '* '* '* '* '* '* '* '* '* '* '*))
 (define %step-ms  (c-fn "griddy_last_step_ms" double '*))
+(define %geometry (c-fn "griddy_upload_geometry" int '* '*))
+(define %positions (c-fn "griddy_download_positions" int '* int64 '* '* '* '*))
+(define %frame-begin (c-fn "griddy_positions_begin" int '* '* int64))
+(define %frame-end (c-fn "griddy_positions_end" int '* '*))
+(define %host-alloc (c-fn "griddy_host_alloc" '* int64))
+(define %slots    (c-fn "griddy_slots_in_use" int64 '*))
 
 (define (check ctx rc)
   ;; nonzero return -> (throw 'griddy-cuda code message), the reference's throw style (core.scm:83)
@@ -117,6 +125,38 @@
     (check ctx (%network ctx n (ptr kind) (ptr len) (ptr dir) (ptr seg) (ptr out) (ptr jun)
                          (ptr of) (ptr ob)))))
 
+;;; ---- geometry for the drawing read-back -----------------------------------------------------
+;;; 8 doubles per item (include/griddy_cuda.h, griddy_upload_geometry), every number produced by the
+;;; reference's own procedures, so that the device only evaluates origin + pos-param * vec (and
+;;; bezier-curve-point-at on junction lanes) — spatial.scm:125-146.
+(define (upload-geometry! ctx world index)
+  (let* ((n (hash-table-size index))
+         (geom (make-f64 (* 8 n))))
+    (define (vec! r at v)
+      (f64! geom (+ (* 8 r) at) (vec2-x v))
+      (f64! geom (+ (* 8 r) at 1) (vec2-y v)))
+    (define (off-road-origin segment side)
+      (get-pos (make <location/off-road> #:road-segment segment
+                     #:road-side-direction side #:pos-param 0)))
+    (hash-table-walk
+     index
+     (lambda (item r)
+       (cond
+        ((is-a? item <road-lane/segment>)
+         (vec! r 0 (get-pos item 'beg))                 ; spatial.scm:104-107
+         (vec! r 2 (get-vec item)))                     ; spatial.scm:156-158
+        ((is-a? item <road-lane/junction>)
+         (let ((curve (ref item 'curve)))               ; core.scm:196-206
+           (vec! r 0 (bezier-curve-p0 curve))
+           (vec! r 2 (bezier-curve-p1 curve))
+           (vec! r 4 (bezier-curve-p2 curve))
+           (vec! r 6 (bezier-curve-p3 curve))))
+        ((is-a? item <road-segment>)
+         (vec! r 0 (off-road-origin item 'forw))        ; v-beg + v-offset, spatial.scm:125-136
+         (vec! r 2 (get-vec item))
+         (vec! r 4 (off-road-origin item 'back))))))
+    (check ctx (%geometry ctx (ptr geom)))))
+
 ;;; ---- flatten actors, agendas and routes -----------------------------------------------------
 (define (upload-actors! ctx world index)
   ;; id order is the reverse of get-actors order (see header)
@@ -183,6 +223,7 @@
   "Flatten WORLD and upload it.  Returns (index . actors): what cuda-download-world! needs."
   (let ((index (registration-index world)))
     (upload-network! ctx world index)
+    (upload-geometry! ctx world index)
     (cons index (upload-actors! ctx world index))))
 
 (define (cuda-step! ctx n-ticks)
@@ -214,3 +255,29 @@
                      (make <location/off-road> #:road-segment item #:pos-param p
                            #:road-side-direction (if (zero? (bytevector-u8-ref side a)) 'forw 'back)))))))
     world++))
+
+;;; ---- the drawing read-back: (get-pos actor) of every actor, computed on the device -----------
+;;; `draw' needs nothing else of an actor (draw.scm:74-76).  One f32vector of x, y pairs per frame,
+;;; in slot order; a pair of NaNs marks a slot without a living actor.
+(define (cuda-positions ctx)
+  "Synchronous: returns (values n xy) with XY a bytevector of N float pairs."
+  (let* ((cap (max 1 (%slots ctx)))
+         (xy (make-bytevector (* 8 cap)))
+         (n (make-i64 1)))
+    (check ctx (%positions ctx cap (ptr n) %null-pointer (ptr xy) %null-pointer))
+    (values (bytevector-s64-native-ref n 0) xy)))
+
+(define (make-frame-buffer capacity)
+  "Page-locked host memory for CAPACITY float pairs, as a bytevector (asynchronous copies need it)."
+  (pointer->bytevector (%host-alloc (* 8 capacity)) (* 8 capacity)))
+
+(define (cuda-frame-begin! ctx buffer)
+  "Start reading the current frame back into BUFFER (from make-frame-buffer); returns at once.  The
+caller may run cuda-step! meanwhile; at most two frames are in flight."
+  (check ctx (%frame-begin ctx (ptr buffer) (quotient (bytevector-length buffer) 8))))
+
+(define (cuda-frame-end! ctx)
+  "Wait for the oldest frame begun; returns the number of float pairs it holds."
+  (let ((n (make-i64 1)))
+    (check ctx (%frame-end ctx (ptr n)))
+    (bytevector-s64-native-ref n 0)))

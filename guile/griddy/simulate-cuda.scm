@@ -17,6 +17,8 @@
   #:use-module (griddy event-loop)
   #:use-module (griddy cuda)
   #:use-module (chickadee graphics path)
+  #:use-module (chickadee math vector)
+  #:use-module (rnrs bytevectors)
   #:export (simulate simulate/headless))
 
 (define* (simulate make-skeleton add-actors! #:key (width 500) (height 500) (duration #f))
@@ -38,9 +40,24 @@
       (quit))
     (cuda-step! ctx 1))                                   ; was: rebuild world, for-each advance$
 
+  ;; was: (draw-canvas (make-actors-canvas world)) — one (get-pos actor) per actor on the host
+  ;; (draw.scm:74-88).  The device computes the positions; the painter is draw.scm:74-76's.
   (define (draw alpha)
     (draw-canvas skeleton-canvas)
-    (draw-canvas (make-actors-canvas (cuda-download-world! ctx handle make-skeleton))))
+    (call-with-values (lambda () (cuda-positions ctx))
+      (lambda (n xy)
+        (draw-canvas
+         (make-canvas
+          (with-style ((fill-color *actor/color*))
+            (apply superimpose
+                   (let loop ((k 0) (acc '()))
+                     (if (= k n)
+                         acc
+                         (let ((x (bytevector-ieee-single-native-ref xy (* 8 k)))
+                               (y (bytevector-ieee-single-native-ref xy (+ 4 (* 8 k)))))
+                           (loop (1+ k)
+                                 (if (nan? x) acc
+                                     (cons (fill (circle (vec2 x y) *actor/size*)) acc)))))))))))))
 
   (define (quit)
     (pk 'last-update-ms (cuda-last-step-ms ctx))

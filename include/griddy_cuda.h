@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GRIDDY_ABI_VERSION 3
+#define GRIDDY_ABI_VERSION 4
 
 enum {
   GRIDDY_OK = 0,
@@ -123,6 +123,37 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
 /* Actors per container (n_items entries; lanes and segments) and per junction (sum over its
  * junction lanes — the quantity junction-full? tests, route.scm:98-104). */
 int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_count);
+
+/* ---- Drawing read-back: (get-pos actor) of every actor, computed on the device --------------------
+ * All that `draw` reads of an actor is its position (simulate.scm:155-160 -> draw.scm:74-88 ->
+ * spatial.scm:125-149), so a frame needs 8 bytes per actor instead of the whole state.
+ *
+ * geom: 8 doubles per registered item, computed by the host with the reference's own procedures
+ * (they go through Chickadee's vec2, like the lane lengths):
+ *   segment lane   beg.x beg.y vec.x vec.y 0 0 0 0            (get-pos lane 'beg), (get-vec lane)      spatial.scm:104-107,156-158
+ *   junction lane  p0.x p0.y p1.x p1.y p2.x p2.y p3.x p3.y    (ref lane 'curve)                        core.scm:196-206
+ *   segment        of.x of.y vec.x vec.y ob.x ob.y 0 0        (get-pos <off-road at pos-param 0>) for the forw and the
+ *                                                             back side, (get-vec segment)             spatial.scm:125-136
+ *   anything else  ignored
+ * The device evaluates  origin + pos-param * vec  (one rounding per operation and component, the
+ * reference's order) and, on junction lanes, bezier-curve-point-at. */
+int griddy_upload_geometry(void* ctx, const double* geom /* 8 x n_items */);
+
+/* Positions of all slots, in slot order: *n = griddy_slots_in_use entries of 2 values (x, y); a slot
+ * without a living actor holds NaN, NaN.  xy64: as the reference's arithmetic gives them; xy32: the
+ * same rounded to float, ready for a vertex buffer; gid: the actor's id per slot (-1: none).  Any of
+ * the three may be NULL.  `capacity` entries must fit. */
+int griddy_download_positions(void* ctx, int64_t capacity, int64_t* n, double* xy64, float* xy32, int32_t* gid);
+
+/* The same for a frame loop, as a pipeline: _begin formats the frame on the device behind the ticks run
+ * so far, starts an asynchronous copy of the float pairs into xy32 (pinned host memory, e.g. from
+ * griddy_host_alloc; it must stay valid until the matching _end) and returns at once.  The caller may
+ * run griddy_step for the next ticks while the copy is in flight.  _end waits for the oldest frame
+ * begun and returns its entry count.  At most two frames are in flight. */
+int griddy_positions_begin(void* ctx, float* xy32, int64_t capacity);
+int griddy_positions_end(void* ctx, int64_t* n);
+void* griddy_host_alloc(int64_t bytes);   /* page-locked host memory; NULL on failure */
+void griddy_host_free(void* ptr);
 
 /* ---- Multi-GPU: one context per GPU, the world partitioned spatially -----------------------------
  * The reference is single-threaded (readme.md:24-26); this is new.  Every item has an owner rank; a

@@ -451,6 +451,44 @@ int go_get_occupancy(void* h, int32_t* lane_count, int32_t* junction_count) {
   return ERR_OK;
 }
 
+// get-pos of an actor (spatial.scm:125-149), stateless: what `draw` computes for every actor
+// (draw.scm:74-76, simulate.scm:155-160).  geom holds 8 doubles per item, host-computed by the
+// reference's own get-pos / get-vec / curve (include/griddy_cuda.h, griddy_upload_geometry):
+//   off road      (+ v-beg v-offset (* pos-param (get-vec segment)))   spatial.scm:125-136; griddy:+ folds
+//                 (math.scm:59-62), so this is (v-beg + v-offset) + pos-param * vec, and v-beg + v-offset
+//                 is the recorded get-pos at pos-param 0
+//   segment lane  (+ (get-pos lane 'beg) (* pos-param (get-vec lane)))   spatial.scm:142-144
+//   junction lane (bezier-curve-point-at curve pos-param)   spatial.scm:145-146.  Chickadee is not vendored:
+//                 PARITY UNPINNED for this clause beyond the evaluator's stub, whose form is restated —
+//                 weights u*u*u, 3*u*u*t, 3*u*t*t, t*t*t (left to right), terms summed from p0 to p3.
+// Every vec2 operation is one rounding per component, as in a vec2 of doubles.
+int go_get_pos(int64_t n_items, int64_t n, const uint8_t* kind, const double* geom, const uint8_t* loc_kind,
+               const int32_t* container, const uint8_t* side, const double* pos, double* xy) {
+  for (int64_t a = 0; a < n; ++a) {
+    const int32_t c = container[a];
+    if (c < 0 || c >= n_items) return ERR_BAD_ARG;
+    const double* g = geom + 8 * (int64_t)c;
+    const double t = pos[a];
+    if (!loc_kind[a]) {
+      if (kind[c] != K_SEGMENT) return ERR_BAD_ARG;
+      const double* o = side[a] == BACK ? g + 4 : g;
+      xy[2 * a] = o[0] + t * g[2];
+      xy[2 * a + 1] = o[1] + t * g[3];
+    } else if (kind[c] == K_SEGLANE) {
+      xy[2 * a] = g[0] + t * g[2];
+      xy[2 * a + 1] = g[1] + t * g[3];
+    } else if (kind[c] == K_JLANE) {
+      const double u = 1.0 - t;
+      const double w0 = u * u * u, w1 = 3.0 * u * u * t, w2 = 3.0 * u * t * t, w3 = t * t * t;
+      xy[2 * a] = w0 * g[0] + w1 * g[2] + w2 * g[4] + w3 * g[6];
+      xy[2 * a + 1] = w0 * g[1] + w1 * g[3] + w2 * g[5] + w3 * g[7];
+    } else {
+      return ERR_BAD_ARG;
+    }
+  }
+  return ERR_OK;
+}
+
 int64_t go_vanished(void* h) { return ((Oracle*)h)->vanished; }
 int64_t go_ticks(void* h) { return ((Oracle*)h)->ticks; }
 

@@ -31,6 +31,20 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def get_pos(net, geom, loc_kind, container, side, pos):
+    """(get-pos actor) for every actor (spatial.scm:125-149) -> float64 [n, 2]."""
+    n = len(pos)
+    as_ = lambda a, dt: np.ascontiguousarray(np.asarray(a, dt))
+    geom = as_(geom, np.float64)
+    assert geom.size == 8 * net.n_items
+    lk, ct, sd, ps = as_(loc_kind, np.uint8), as_(container, np.int32), as_(side, np.uint8), as_(pos, np.float64)
+    xy = np.zeros((n, 2), np.float64)
+    rc = lib().go_get_pos(C.c_int64(net.n_items), C.c_int64(n), _p(net.kind), _p(geom), _p(lk), _p(ct), _p(sd), _p(ps), _p(xy))
+    if rc:
+        raise RuntimeError(f"oracle get_pos error {rc}")
+    return xy
+
+
 class Oracle:
     """Same call shape as griddy_b200.device.Simulation, so parity tests feed both identically."""
 

@@ -11,6 +11,10 @@ The fixture also holds the INPUTS the oracle / device need to replay the run: th
 registration index (with the lane lengths the reference's own `get-length` returned), and the actors
 with their agendas and the routes the reference's own `find-route` returned.
 
+For the drawing read-back (`get-pos` of every actor, spatial.scm:125-149) it records, per item, the
+geometry the reference's own `get-pos` / `get-vec` / `curve` return (8 doubles, layout of
+include/griddy_cuda.h griddy_upload_geometry), and every XY_EVERY ticks `(get-pos actor)` of every actor.
+
     python tests/golden/generate.py            # all scenarios
     python tests/golden/generate.py simple     # one
 
@@ -42,6 +46,9 @@ SCENARIOS = {
                      [("(n 5)", "(n 2)"), ("(list-tabulate 80 make-actor)", "(list-tabulate 60 make-actor)"),
                       ("(random-integer 300)", "(random-integer 4)")], 400, 13),
 }
+
+
+XY_EVERY = 10   # scenarios with more than one actor record (get-pos actor) every 10th tick
 
 
 class Run:
@@ -111,6 +118,32 @@ class Run:
                 net["lane_junction"][r] = idx[id(it.slots[S("junction")])]
         return net, idx
 
+    def flatten_geometry(self, world, idx):
+        """Per item, 8 doubles (include/griddy_cuda.h griddy_upload_geometry), all from the reference's code:
+        segment lane   beg.x beg.y vec.x vec.y 0 0 0 0        (get-pos lane 'beg), (get-vec lane)
+        junction lane  p0.x p0.y p1.x p1.y p2.x p2.y p3.x p3.y   (ref lane 'curve)
+        segment        of.x of.y vec.x vec.y ob.x ob.y 0 0    (get-pos <off-road forw|back at pos-param 0>), (get-vec segment)"""
+        _, items = self.index(world)
+        geom = [[0.0] * 8 for _ in items]
+        LocOff = self.cls("<location/off-road>")
+        xy = lambda v: [float(v.x), float(v.y)]
+        for it in items:
+            r = idx[id(it)]
+            cname = it.cls.name
+            if cname == "<road-lane/segment>":
+                geom[r] = xy(self.call("get-pos", it, S("beg"))) + xy(self.call("get-vec", it)) + [0.0] * 4
+            elif cname == "<road-lane/junction>":
+                c = it.slots[S("curve")]
+                geom[r] = [v for k in range(4) for v in xy(c.p[k])]
+            elif cname == "<road-segment>":
+                o = []
+                for side in ("forw", "back"):
+                    loc = self.call("make", LocOff, ms.Kw("road-segment"), it, ms.Kw("road-side-direction"), S(side),
+                                    ms.Kw("pos-param"), 0)
+                    o.append(xy(self.call("get-pos", loc)))
+                geom[r] = o[0] + xy(self.call("get-vec", it)) + o[1] + [0.0] * 2
+        return [v for g in geom for v in g]
+
     def flatten_actors(self, world, idx):
         order = plist(self.call("get-actors", world))
         actors = order[::-1]            # id k-th of get-actors -> M-1-k: linking in id order rebuilds the lists
@@ -152,7 +185,7 @@ class Run:
         return A
 
     # ---- state after a tick -----------------------------------------------------------------------
-    def state(self, world):
+    def state(self, world, with_xy=False):
         idx, _ = self.index(world)
         st = {k: [] for k in ("loc_kind", "container", "side", "pos", "agenda_left", "sleep_left", "route_status",
                               "route_head", "speed")}
@@ -176,6 +209,9 @@ class Run:
                 head = route.car
                 st["route_head"].append(idx[id(head.cdr.car)] if head.car is S("turn-onto") else -1)
             st["speed"].append(float(a.slots[S("max-speed")]))
+            if with_xy:
+                v = self.call("get-pos", a)
+                st.setdefault("xy", []).extend([float(v.x), float(v.y)])
         return st
 
     def run(self):
@@ -184,10 +220,12 @@ class Run:
         world = self.world()
         net, idx = self.flatten_network(world)
         actors = self.flatten_actors(world, idx)
-        states = [self.state(world)]                 # tick 0: the world `load` built
+        net["geom"] = self.flatten_geometry(world, idx)
+        every = 1 if len(actors["loc_kind"]) == 1 else XY_EVERY
+        states = [self.state(world, True)]           # tick 0: the world `load` built
         for t in range(self.ticks):
             self.I.apply(self.game["update"], [0])
-            states.append(self.state(self.world()))
+            states.append(self.state(self.world(), (t + 1) % every == 0))
             if (t + 1) % 100 == 0:
                 print(f"  {self.name}: tick {t + 1}/{self.ticks}, {len(states[-1]['pos'])} actors, {time.time() - t0:.0f}s",
                       flush=True)

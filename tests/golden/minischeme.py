@@ -1565,7 +1565,10 @@ def install_builtins(I):
         t = float(t)
         u = 1.0 - t
         w = (u * u * u, 3.0 * u * u * t, 3.0 * u * t * t, t * t * t)
-        return Vec2(sum(wi * p.x for wi, p in zip(w, c.p)), sum(wi * p.y for wi, p in zip(w, c.p)))
+        # plain left-to-right additions, as Guile's n-ary + folds (Python's sum() compensates since 3.12)
+        p0, p1, p2, p3 = c.p
+        return Vec2(w[0] * p0.x + w[1] * p1.x + w[2] * p2.x + w[3] * p3.x,
+                    w[0] * p0.y + w[1] * p1.y + w[2] * p2.y + w[3] * p3.y)
     prim("bezier-curve-point-at", bezier_at)
     for colour in ("tango-aluminium-2", "white", "tango-plum", "tango-light-chameleon"):
         B[S(colour)] = Sym(colour)

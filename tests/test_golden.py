@@ -86,3 +86,30 @@ def test_device_reproduces_the_reference_run(name):
     stride = 20 if name == "triangle" else 1          # triangle idles for 9,970 of its 10,000 ticks
     replay(lambda net, actors, fx: device.Simulation(net, actors, dt=fx["dt"], two_size=fx["two_size"],
                                                       reorder_period=16), name, stride=stride)
+
+
+def test_guile_dump_checker(tmp_path):
+    """tests/golden/check_guile_dump.py (the comparison a maintainer with a real Guile runs on the output of
+    guile/tools/headless-reference.scm) accepts a dump that agrees with the fixture and flags one that does not."""
+    import subprocess
+    import sys
+    fx, _, _ = load("simple")
+    lines = []
+    for tick, s in enumerate(expected_states(fx)):
+        lines.append(f"tick {tick} {len(s['pos'])}")
+        for k in range(len(s["pos"])):
+            route = {0: "none", 2: "done"}.get(s["route_status"][k], "arrive" if s["route_head"][k] == -1 else s["route_head"][k])
+            lines.append(" ".join(str(v) for v in (
+                s["loc_kind"][k], s["container"][k], s["side"][k], repr(float.fromhex(s["pos"][k])), s["agenda_left"][k],
+                s["sleep_left"][k], route, s["speed"][k], s["xy"][2 * k], s["xy"][2 * k + 1])))
+    good = tmp_path / "good.dump"
+    good.write_text("\n".join(lines) + "\n")
+    script = os.path.join(GOLDEN, "check_guile_dump.py")
+    fixture = os.path.join(GOLDEN, "simple.json.gz")
+    ok = subprocess.run([sys.executable, script, str(good), fixture, "--xy"], capture_output=True, text=True)
+    assert ok.returncode == 0, ok.stdout
+    bad = tmp_path / "bad.dump"
+    lines[5] = lines[5].replace(lines[5].split()[3], "0.5", 1)
+    bad.write_text("\n".join(lines) + "\n")
+    ko = subprocess.run([sys.executable, script, str(bad), fixture], capture_output=True, text=True)
+    assert ko.returncode == 1 and "pos-param" in ko.stdout
