@@ -75,6 +75,11 @@ struct TouchSink {
   int32_t *left, *n_left;         // shared: lanes that lost an actor or hold a ghost (k_unlink), SLOW_THREADS entries
   int32_t *entered, *n_entered;   // shared: lanes that gained an actor (k_link), SLOW_THREADS entries
 };
+#ifdef SLOW_MIN_BLOCKS
+#define SLOW_BOUNDS __launch_bounds__(SLOW_THREADS, SLOW_MIN_BLOCKS)
+#else
+#define SLOW_BOUNDS __launch_bounds__(SLOW_THREADS)
+#endif
 constexpr int SLOW_THREADS = 128;   // an actor leaves at most one lane (its own, ghost or not) and enters at most one
 
 __device__ __forceinline__ void mark_left(const Params& p, int32_t lane, int tick, const TouchSink& sink) {
@@ -288,6 +293,7 @@ constexpr int ADV_THREADS = 256;
 __global__ void ADV_BOUNDS k_advance(Params p, int tick) {
   __shared__ int4 s_list[ADV_THREADS * ADV_UNROLL];
   __shared__ int32_t s_n, s_base;
+  grid_dependency_wait();
   const int par = tick & 1;
   int32_t* counters = p.counters + CNT_STRIDE * par;
   if (blockIdx.x == 0 && threadIdx.x < CNT_STRIDE) p.counters[CNT_STRIDE * (par ^ 1) + threadIdx.x] = 0;
@@ -371,15 +377,17 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick) {
 
 // k_slow: the full advance$ for the actors k_advance deferred, one thread per actor, so that the
 // chains of dependent gathers of 32 such actors overlap instead of stalling 31 idle lanes.
-__global__ void __launch_bounds__(SLOW_THREADS) k_slow(Params p, int tick) {
+__global__ void SLOW_BOUNDS k_slow(Params p, int tick) {
   __shared__ int32_t s_left[SLOW_THREADS], s_entered[SLOW_THREADS];
   __shared__ int32_t s_nl, s_ne, s_base_l, s_base_e;
+  grid_dependency_wait();
   const int par = tick & 1;
   int32_t* counters = p.counters + CNT_STRIDE * par;
   const int32_t n_slow = counters[CNT_SLOW];
   const double* __restrict__ pos_old = p.pos[par];
   double* __restrict__ pos_new = p.pos[par ^ 1];
   const TouchSink sink{s_left, &s_nl, s_entered, &s_ne};
+  // (handing the chunks out through a counter instead of this static split was measured 8 % slower)
   for (int32_t chunk = blockIdx.x * SLOW_THREADS; chunk < n_slow; chunk += gridDim.x * SLOW_THREADS) {
     if (threadIdx.x == 0) s_nl = s_ne = 0;
     __syncthreads();

@@ -97,9 +97,7 @@ struct Ctx;
 struct Neighbor {
   int rank = -1;
   int n_exp_lanes = 0, n_exp_junc = 0, n_imp_lanes = 0, n_imp_junc = 0;
-  int32_t* d_exp_items = nullptr;   // my lanes, then my junctions, that `rank` reads
-  int32_t* d_imp_junc = nullptr;    // its junctions whose occupancy my actors read
-  double *d_halo_send = nullptr, *d_halo_recv = nullptr;
+  double *d_halo_send = nullptr, *d_halo_recv = nullptr;   // parts of Multi::d_halo_send / d_halo_recv
   uint8_t* d_mig_recv[2] = {nullptr, nullptr};   // by tick parity; the neighbour's k_emig_pack writes here
   uint8_t* peer_mig[2] = {nullptr, nullptr};     // the neighbour's receive buffers for me, mapped into this process
   int64_t *d_token_out = nullptr, *d_token_in = nullptr;   // NCCL transport: "my emigrants of this tick are written"
@@ -115,7 +113,12 @@ struct Multi {
   std::vector<Neighbor> nb;
   std::vector<void*> allocs;
   std::vector<std::pair<int32_t, int32_t>> import_marks;   // (remote lane, -2 - index into halo_recv)
-  double* d_halo_recv = nullptr;
+  double* d_halo_recv = nullptr;      // all neighbours' halos back to back: [lanes, junctions] each
+  double* d_halo_send = nullptr;      // what I send, likewise
+  int32_t* d_exp_items = nullptr;     // per entry of d_halo_send: my lane, or ~(my junction)
+  int n_exp = 0;
+  int32_t *d_imp_junc = nullptr, *d_imp_where = nullptr;   // the neighbours' junctions my actors read, and where in d_halo_recv
+  int n_imp_junc = 0;
   int32_t* d_owner = nullptr;
   void* nccl_comm = nullptr;          // transport 1: NCCL send/recv between processes, on their own stream
   cudaStream_t comm_stream = nullptr; //   so that k_advance hides the halo exchange and k_unlink the migrants'
@@ -281,6 +284,7 @@ void mg_reset(Ctx* c) {
   for (auto& b : c->p.mig_peer) b[0] = b[1] = nullptr;
   for (auto& b : c->p.mig_mine) b[0] = b[1] = nullptr;
   for (auto& n : c->p.mig_cap) n = 0;
+  for (auto& n : c->p.mig_in) n = 0;
 }
 
 // Items of `owner_rank` that actors living on `reader_rank` read before they cross: the lanes they
@@ -375,6 +379,22 @@ constexpr int NCCL_CHAR = 0;   // ncclInt8 / ncclChar in nccl.h
       return fail(c, GRIDDY_ERR_NCCL, std::string(#expr) + ": " + (a_ && a_->GetErrorString ? a_->GetErrorString(r_) : "nccl error")); \
     }                                                                                                   \
   } while (0)
+
+// Launch one of the tick's kernels behind its predecessor on the stream with programmatic dependent
+// launch (records.cuh, grid_dependency_wait).
+template <typename... Args>
+cudaError_t launch_dependent(void (*kernel)(Args...), unsigned blocks, unsigned threads, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = GRIDDY_PDL;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 }  // namespace
 
@@ -812,12 +832,10 @@ int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   if (ev) cudaEventRecord(ev[0], c->stream);
   if (c->reorder_period > 0 && tick % c->reorder_period == 0 && tick != c->last_reorder_tick)
     TRY(reorder_slots(c, tick));
-  if (c->mg.on) {
-    for (Neighbor& nb : c->mg.nb) {
-      const int n = nb.n_exp_lanes + nb.n_exp_junc;
-      if (n) k_halo_pack<<<(n + 127) / 128, 128, 0, c->stream>>>(c->p, (int)(tick & 1), nb.d_exp_items, nb.n_exp_lanes, nb.n_exp_junc, nb.d_halo_send);
-    }
-    c->launches += (int64_t)c->mg.nb.size();
+  if (c->mg.on && c->mg.n_exp) {
+    CUDA_TRY(c, launch_dependent(k_halo_pack, (unsigned)((c->mg.n_exp + 127) / 128), 128u, c->stream, c->p, (int)(tick & 1),
+                                 (const int32_t*)c->mg.d_exp_items, c->mg.n_exp, c->mg.d_halo_send));
+    ++c->launches;
   }
   if (ev) cudaEventRecord(ev[1], c->stream);
   return GRIDDY_OK;
@@ -828,7 +846,7 @@ int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
 int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   const unsigned per_block = ADV_THREADS * ADV_UNROLL;
   const unsigned adv_blocks = (unsigned)((c->ns_host + per_block - 1) / per_block);
-  if (adv_blocks) k_advance<<<adv_blocks, ADV_THREADS, 0, c->stream>>>(c->p, (int)tick);
+  if (adv_blocks) CUDA_TRY(c, launch_dependent(k_advance, adv_blocks, ADV_THREADS, c->stream, c->p, (int)tick));
   if (ev) cudaEventRecord(ev[2], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -837,15 +855,14 @@ int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
 int tick_slow(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // needs the halo
   const Params& p = c->p;
   const unsigned aux_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host + 255) / 256), 1u), 148u * 8u);
-  if (c->mg.on)
-    for (Neighbor& nb : c->mg.nb)
-      if (nb.n_imp_junc) {
-        k_halo_unpack<<<(nb.n_imp_junc + 127) / 128, 128, 0, c->stream>>>(p, nb.d_imp_junc, nb.n_imp_junc, nb.d_halo_recv + nb.n_imp_lanes);
-        ++c->launches;
-      }
-  k_slow<<<aux_blocks * 2, SLOW_THREADS, 0, c->stream>>>(p, (int)tick);
+  if (c->mg.on && c->mg.n_imp_junc) {
+    CUDA_TRY(c, launch_dependent(k_halo_unpack, (unsigned)((c->mg.n_imp_junc + 127) / 128), 128u, c->stream, p,
+                                 (const int32_t*)c->mg.d_imp_junc, (const int32_t*)c->mg.d_imp_where, c->mg.n_imp_junc));
+    ++c->launches;
+  }
+  CUDA_TRY(c, launch_dependent(k_slow, aux_blocks * 2, SLOW_THREADS, c->stream, p, (int)tick));
   if (c->mg.on) {
-    k_emig_pack<<<64, 128, 0, c->stream>>>(p, (int)tick);
+    CUDA_TRY(c, launch_dependent(k_emig_pack, 64u, 128u, c->stream, p, (int)tick));
     ++c->launches;
   }
   if (ev) cudaEventRecord(ev[3], c->stream);
@@ -859,7 +876,7 @@ unsigned relink_blocks(const Ctx* c) {
 }
 
 int tick_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // local lists only: does not need the migrants
-  k_unlink<<<relink_blocks(c), 128, 0, c->stream>>>(c->p, (int)tick);
+  CUDA_TRY(c, launch_dependent(k_unlink, relink_blocks(c), 128u, c->stream, c->p, (int)tick));
   if (ev) cudaEventRecord(ev[4], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -867,18 +884,26 @@ int tick_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // local lists only: 
 
 int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // needs the migrants
   const Params& p = c->p;
-  if (c->mg.on)
+  if (c->mg.on && !c->mg.nb.empty()) {
+    int most = 1;
     for (Neighbor& nb : c->mg.nb) {
-      k_immig_unpack<<<std::max(1, nb.mig_in / 512), 128, 0, c->stream>>>(p, (int)tick, nb.d_mig_recv[tick & 1], nb.mig_in);
-      ++c->launches;
+      most = std::max(most, nb.mig_in);
       // upper bound of the slots in use: the neighbour may have filled its buffer
       c->ns_host = (int32_t)std::min<int64_t>(p.cap, (int64_t)c->ns_host + nb.mig_in);
     }
-  if (c->mg.on) {
-    k_mig_reset<<<1, 32, 0, c->stream>>>(p, (int)(tick & 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::max(1, most / 512), (unsigned)c->mg.world);   // blockIdx.y: the rank they came from
+    cfg.blockDim = dim3(128);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = GRIDDY_PDL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, k_immig_unpack, p, (int)tick));
     ++c->launches;
   }
-  k_link<<<relink_blocks(c), 128, 0, c->stream>>>(p, (int)tick);
+  CUDA_TRY(c, launch_dependent(k_link, relink_blocks(c), 128u, c->stream, p, (int)tick));
   if (ev) cudaEventRecord(ev[5], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -1285,6 +1310,11 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     halo_in += L.imp_l.size() + L.imp_j.size();
   }
   TRY(mg_alloc(c, &m.d_halo_recv, halo_in));
+  size_t halo_out = 0;
+  for (int r = 0; r < world; ++r)
+    if (r != rank) halo_out += lists[r].exp_l.size() + lists[r].exp_j.size();
+  TRY(mg_alloc(c, &m.d_halo_send, halo_out));
+  std::vector<int32_t> exp_all, imp_junc_all, imp_where_all;
   size_t off = 0;
   for (int r = 0; r < world; ++r) {
     Lists& L = lists[r];
@@ -1295,15 +1325,15 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     nb.n_exp_junc = (int)L.exp_j.size();
     nb.n_imp_lanes = (int)L.imp_l.size();
     nb.n_imp_junc = (int)L.imp_j.size();
-    std::vector<int32_t> exp(L.exp_l);
-    exp.insert(exp.end(), L.exp_j.begin(), L.exp_j.end());
-    TRY(mg_alloc(c, &nb.d_exp_items, exp.size()));
-    if (!exp.empty()) CUDA_TRY(c, cudaMemcpy(nb.d_exp_items, exp.data(), exp.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    TRY(mg_alloc(c, &nb.d_imp_junc, L.imp_j.size()));
-    if (!L.imp_j.empty()) CUDA_TRY(c, cudaMemcpy(nb.d_imp_junc, L.imp_j.data(), L.imp_j.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    TRY(mg_alloc(c, &nb.d_halo_send, exp.size()));
+    nb.d_halo_send = m.d_halo_send + exp_all.size();
+    exp_all.insert(exp_all.end(), L.exp_l.begin(), L.exp_l.end());
+    for (int32_t j : L.exp_j) exp_all.push_back(~j);
     nb.d_halo_recv = m.d_halo_recv + off;
     for (size_t k = 0; k < L.imp_l.size(); ++k) m.import_marks.emplace_back(L.imp_l[k], (int32_t)(-2 - (int64_t)(off + k)));
+    for (size_t k = 0; k < L.imp_j.size(); ++k) {
+      imp_junc_all.push_back(L.imp_j[k]);
+      imp_where_all.push_back((int32_t)(off + L.imp_l.size() + k));
+    }
     off += L.imp_l.size() + L.imp_j.size();
     nb.mig_out = (int)std::min<int64_t>(mig_cap, mg_count_feeders(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), owner, rank, r));
     nb.mig_in = (int)std::min<int64_t>(mig_cap, mg_count_feeders(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), owner, r, rank));
@@ -1316,7 +1346,18 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     TRY(mg_alloc(c, &nb.d_token_in, 1));
     CUDA_TRY(c, cudaMemset(nb.d_token_out, 0, sizeof(int64_t)));
     c->p.mig_cap[r] = nb.mig_out;
+    c->p.mig_in[r] = nb.mig_in;
     m.nb.push_back(nb);
+  }
+  m.n_exp = (int)exp_all.size();
+  m.n_imp_junc = (int)imp_junc_all.size();
+  TRY(mg_alloc(c, &m.d_exp_items, exp_all.size()));
+  TRY(mg_alloc(c, &m.d_imp_junc, imp_junc_all.size()));
+  TRY(mg_alloc(c, &m.d_imp_where, imp_where_all.size()));
+  if (m.n_exp) CUDA_TRY(c, cudaMemcpy(m.d_exp_items, exp_all.data(), exp_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (m.n_imp_junc) {
+    CUDA_TRY(c, cudaMemcpy(m.d_imp_junc, imp_junc_all.data(), imp_junc_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(m.d_imp_where, imp_where_all.data(), imp_where_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   c->p.owner = m.d_owner;
   c->p.my_rank = rank;

@@ -59,6 +59,7 @@ __device__ int later_processed(const Params& p, int x, int y, int32_t lane, cons
 constexpr int32_t UNLINKED = -3;
 
 __global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
+  grid_dependency_wait();
   const int par = tick & 1;
   const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_LEFT];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
@@ -100,9 +101,18 @@ __global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
   }
 }
 
+// After this tick's immigrants are unpacked (k_link runs behind k_immig_unpack): empty my
+// receive buffers of this parity.  The sender writes them again two ticks from now, after it has seen
+// the token I send next tick.
+__device__ __forceinline__ void mig_reset(const Params& p, int par) {
+  if (blockIdx.x == 0 && threadIdx.x < MAX_RANKS && p.mig_mine[threadIdx.x][par]) *p.mig_mine[threadIdx.x][par] = 0;
+}
+
 __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
+  grid_dependency_wait();
   const int par = tick & 1;
   const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_ENTERED];
+  mig_reset(p, par);
   const double* __restrict__ pos_old = p.pos[par];
   const double* __restrict__ pos_new = p.pos[par ^ 1];
   const int32_t* __restrict__ entered = p.touched + p.cap;

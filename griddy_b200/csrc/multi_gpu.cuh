@@ -26,12 +26,15 @@ constexpr size_t MIG_HEADER = 8;
 
 // Halo out: for every lane of mine that a neighbour's actors can enter, its smallest key in (0, ...]
 // (the walk route.scm:118-121 would do), +inf if there is none; for every such junction, its occupancy.
-__global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int32_t* __restrict__ items, int n_lanes,
-                                                    int n_junctions, double* __restrict__ out) {
+// One launch for all neighbours: `items` and `out` are the neighbours' lists back to back (each
+// neighbour's part of `out` is what is sent to it); a junction is listed as ~id.
+__global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int32_t* __restrict__ items, int n,
+                                                    double* __restrict__ out) {
+  grid_dependency_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_lanes + n_junctions) return;
+  if (i >= n) return;
   const int32_t item = items[i];
-  if (i >= n_lanes) { out[i] = (double)p.occ[item]; return; }
+  if (item < 0) { out[i] = (double)p.occ[~item]; return; }
   const double* __restrict__ pos = p.pos[par];
   int32_t x = p.lane[item].tail;
   while (x >= 0 && !(pos[x] > 0.0)) x = p.sa[x].ahead;
@@ -39,22 +42,20 @@ __global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int3
 }
 
 // Halo in: occupancy of the neighbours' junctions (the lane values are read in place from halo_recv).
-__global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __restrict__ junctions, int n,
-                                                      const double* __restrict__ in) {
+// One launch for all neighbours: junctions[i] is a junction another rank owns, where[i] its place in
+// halo_recv.
+__global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __restrict__ junctions,
+                                                      const int32_t* __restrict__ where, int n) {
+  grid_dependency_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p.occ[junctions[i]] = (int32_t)in[i];
-}
-
-// After this tick's immigrants are unpacked: empty my receive buffers of this parity.  The sender writes
-// them again two ticks from now, after it has seen the token I send next tick.
-__global__ void k_mig_reset(Params p, int par) {
-  if (threadIdx.x < MAX_RANKS && p.mig_mine[threadIdx.x][par]) *p.mig_mine[threadIdx.x][par] = 0;
+  if (i < n) p.occ[junctions[i]] = (int32_t)p.halo_recv[where[i]];
 }
 
 // Emigrants -> one record each, written straight into the receive buffer of the rank that owns their
 // new lane (peer memory over NVLink: remote atomic for the slot, remote stores for the record), so only
 // the actors that actually crossed travel, not a bound-sized message.
 __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
+  grid_dependency_wait();
   const int par = tick & 1;
   const int32_t n = p.counters[CNT_STRIDE * par + CNT_EMIG];
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -102,10 +103,14 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
   }
 }
 
-// Immigrants: a fresh slot each, then onto their lane's inbox like any local mover.
-__global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick, const uint8_t* __restrict__ buf, int cap) {
+// Immigrants: a fresh slot each, then onto their lane's inbox like any local mover.  One launch for all
+// neighbours: blockIdx.y is the rank the records came from.
+__global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
+  grid_dependency_wait();
   const int par = tick & 1;
-  const int32_t n = min(*(const int32_t*)buf, cap);
+  const uint8_t* buf = (const uint8_t*)p.mig_mine[blockIdx.y][par];
+  if (!buf) return;
+  const int32_t n = min(*(const int32_t*)buf, p.mig_in[blockIdx.y]);
   const MigRec* recs = (const MigRec*)(buf + MIG_HEADER);
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const MigRec r = recs[i];

@@ -21,6 +21,19 @@ constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_J
 
 // Params::counters[parity][...]
 constexpr int CNT_EMIG = 0, CNT_LEFT = 1, CNT_SLOW = 2, CNT_ENTERED = 3, CNT_STRIDE = 4;
+
+// Programmatic dependent launch (sm_90+): the four kernels of a tick are launched with
+// programmaticStreamSerializationAllowed, so the blocks of the next one become resident while the last
+// blocks of the previous one drain; nothing is read or written before grid_dependency_wait() returns,
+// which is when the previous kernel has completed and its writes are visible.
+#ifndef GRIDDY_PDL
+#define GRIDDY_PDL 1
+#endif
+__device__ __forceinline__ void grid_dependency_wait() {
+#if GRIDDY_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 // device scalars (Params::scal)
 constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_COUNT = 4;
 constexpr int MAX_RANKS = 8;     // one box
@@ -125,7 +138,8 @@ struct Params {
   // by destination rank and tick parity: that rank's receive buffer for my emigrants, in ITS memory
   // (peer access over NVLink): [int32 count, pad][MigRec x mig_cap].  k_emig_pack writes there directly.
   uint8_t* mig_peer[MAX_RANKS][2];
-  int32_t* mig_mine[MAX_RANKS][2];   // headers of my own receive buffers, to reset after unpacking
+  int32_t* mig_mine[MAX_RANKS][2];   // my own receive buffers, by source rank: [int32 count, pad][MigRec x mig_in[rank]]
+  int32_t mig_in[MAX_RANKS];         // by source rank: records per tick at most
 };
 
 }  // namespace griddy
