@@ -100,7 +100,6 @@ struct Neighbor {
   double *d_halo_send = nullptr, *d_halo_recv = nullptr;   // parts of Multi::d_halo_send / d_halo_recv
   uint8_t* d_mig_recv[2] = {nullptr, nullptr};   // by tick parity; the neighbour's k_emig_pack writes here
   uint8_t* peer_mig[2] = {nullptr, nullptr};     // the neighbour's receive buffers for me, mapped into this process
-  int64_t *d_token_out = nullptr, *d_token_in = nullptr;   // NCCL transport: "my emigrants of this tick are written"
   int mig_out = 0, mig_in = 0;      // records per tick at most: a lane lets one actor out per tick
   size_t in_bytes() const { return MIG_HEADER + (size_t)mig_in * sizeof(MigRec); }
 };
@@ -285,6 +284,7 @@ void mg_reset(Ctx* c) {
   for (auto& b : c->p.mig_mine) b[0] = b[1] = nullptr;
   for (auto& n : c->p.mig_cap) n = 0;
   for (auto& n : c->p.mig_in) n = 0;
+  c->p.mig_done = nullptr;
 }
 
 // Items of `owner_rank` that actors living on `reader_rank` read before they cross: the lanes they
@@ -793,6 +793,10 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     if (rc) return rc;
   }
   CUDA_TRY(c, cudaMemcpy(p.occ, occ.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
+  // a partitioned world starts over: no records, no flags (they count ticks) in my receive buffers
+  for (Neighbor& nb : c->mg.nb)
+    for (int par = 0; par < 2; ++par) CUDA_TRY(c, cudaMemset(nb.d_mig_recv[par], 0, MIG_HEADER));
+  if (c->mg.on) CUDA_TRY(c, cudaMemset(c->p.mig_done, 0, sizeof(int32_t)));
   c->tick = 0;
   c->ns_host = (int32_t)n;
   c->last_reorder_tick = -1;
@@ -822,27 +826,21 @@ int finish_step(Ctx* c) {
   if (derr & DEV_ERR_INTERNAL) m += " internal: a live actor pointed at a dropped slot;";
   if (derr & DEV_ERR_MIG_OVERFLOW) m += " multi-GPU: more boundary crossings in one tick than mig_cap, or no slots left for arrivals;";
   if (derr & DEV_ERR_MIG_AGENDA) m += " multi-GPU: a migrating actor's agenda has more than 4 items;";
+  if (derr & DEV_ERR_MIG_TIMEOUT) m += " multi-GPU: a neighbour never signalled that its migrants of a tick were written;";
   return fail(c, GRIDDY_ERR_BAD_STATE, m);
 }
 
-// One tick = four launches (plus a reorder every reorder_period ticks; plus, on a partitioned world,
-// the halo and migrant kernels and two exchanges).  ev (optional) receives 6 events bracketing
-// reorder (+ halo pack), k_advance, k_slow (+ emigrant pack), k_unlink (+ immigrant unpack), k_link.
+// One tick = four launches on the compute stream (plus a reorder every reorder_period ticks; on a
+// partitioned world the halo and migrant kernels and the two exchanges run beside them, see launch_tick).
+// ev (optional) receives 6 events bracketing reorder, k_advance, k_slow, k_unlink, k_link.
 int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   if (ev) cudaEventRecord(ev[0], c->stream);
   if (c->reorder_period > 0 && tick % c->reorder_period == 0 && tick != c->last_reorder_tick)
     TRY(reorder_slots(c, tick));
-  if (c->mg.on && c->mg.n_exp) {
-    CUDA_TRY(c, launch_dependent(k_halo_pack, (unsigned)((c->mg.n_exp + 127) / 128), 128u, c->stream, c->p, (int)(tick & 1),
-                                 (const int32_t*)c->mg.d_exp_items, c->mg.n_exp, c->mg.d_halo_send));
-    ++c->launches;
-  }
   if (ev) cudaEventRecord(ev[1], c->stream);
   return GRIDDY_OK;
 }
 
-// k_advance does not read the halo (actors gated by a remote junction are deferred to k_slow), so it
-// can run while the halo is in flight.
 int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   const unsigned per_block = ADV_THREADS * ADV_UNROLL;
   const unsigned adv_blocks = (unsigned)((c->ns_host + per_block - 1) / per_block);
@@ -852,19 +850,9 @@ int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   return GRIDDY_OK;
 }
 
-int tick_slow(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // needs the halo
-  const Params& p = c->p;
+int tick_slow(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // on a partitioned world: needs the halo
   const unsigned aux_blocks = std::min<unsigned>(std::max((unsigned)((c->ns_host + 255) / 256), 1u), 148u * 8u);
-  if (c->mg.on && c->mg.n_imp_junc) {
-    CUDA_TRY(c, launch_dependent(k_halo_unpack, (unsigned)((c->mg.n_imp_junc + 127) / 128), 128u, c->stream, p,
-                                 (const int32_t*)c->mg.d_imp_junc, (const int32_t*)c->mg.d_imp_where, c->mg.n_imp_junc));
-    ++c->launches;
-  }
-  CUDA_TRY(c, launch_dependent(k_slow, aux_blocks * 2, SLOW_THREADS, c->stream, p, (int)tick));
-  if (c->mg.on) {
-    CUDA_TRY(c, launch_dependent(k_emig_pack, 64u, 128u, c->stream, p, (int)tick));
-    ++c->launches;
-  }
+  CUDA_TRY(c, launch_dependent(k_slow, aux_blocks * 2, SLOW_THREADS, c->stream, c->p, (int)tick));
   if (ev) cudaEventRecord(ev[3], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -882,86 +870,145 @@ int tick_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // local lists only: 
   return GRIDDY_OK;
 }
 
-int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // needs the migrants
-  const Params& p = c->p;
-  if (c->mg.on && !c->mg.nb.empty()) {
-    int most = 1;
-    for (Neighbor& nb : c->mg.nb) {
-      most = std::max(most, nb.mig_in);
-      // upper bound of the slots in use: the neighbour may have filled its buffer
-      c->ns_host = (int32_t)std::min<int64_t>(p.cap, (int64_t)c->ns_host + nb.mig_in);
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)std::max(1, most / 512), (unsigned)c->mg.world);   // blockIdx.y: the rank they came from
-    cfg.blockDim = dim3(128);
-    cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = GRIDDY_PDL;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CUDA_TRY(c, cudaLaunchKernelEx(&cfg, k_immig_unpack, p, (int)tick));
-    ++c->launches;
-  }
-  CUDA_TRY(c, launch_dependent(k_link, relink_blocks(c), 128u, c->stream, p, (int)tick));
+int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // on a partitioned world: needs the migrants
+  CUDA_TRY(c, launch_dependent(k_link, relink_blocks(c), 128u, c->stream, c->p, (int)tick));
   if (ev) cudaEventRecord(ev[5], c->stream);
   ++c->launches;
   return GRIDDY_OK;
 }
 
-// NCCL transport: one grouped send/recv with every neighbour, on the context's stream.
-// What was packed on the compute stream so far is sent; whoever needs what arrives waits for
-// exchange_arrived().  In between the compute stream is free to run kernels that need neither.
-int exchange_nccl(Ctx* c, bool halo) {
-  NcclApi* api = nccl_api();
-  if (!api || !c->mg.nccl_comm) return fail(c, GRIDDY_ERR_NCCL, "multi-GPU context is not connected (griddy_mg_connect_nccl)");
-  cudaStream_t compute = c->stream;
-  CUDA_TRY(c, cudaEventRecord(c->mg.ev_packed, compute));
-  CUDA_TRY(c, cudaStreamWaitEvent(c->mg.comm_stream, c->mg.ev_packed, 0));
-  struct OnComm {   // the sends and receives below go to the communication stream
-    Ctx* c; cudaStream_t saved;
-    OnComm(Ctx* c_) : c(c_), saved(c_->stream) { c->stream = c->mg.comm_stream; }
-    ~OnComm() { c->stream = saved; }
-  } on_comm(c);
-  NCCL_TRY(c, api->GroupStart());
-  for (Neighbor& nb : c->mg.nb) {
-    if (halo) {
-      const size_t out = (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double);
-      const size_t in = (size_t)(nb.n_imp_lanes + nb.n_imp_junc) * sizeof(double);
-      if (out) NCCL_TRY(c, api->Send(nb.d_halo_send, out, NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
-      if (in) NCCL_TRY(c, api->Recv(nb.d_halo_recv, in, NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
-    } else {
-      // the records themselves were written into the neighbour's memory by k_emig_pack; this token
-      // orders them: it leaves after my kernel has completed, and what arrives tells me the same
-      if (!nb.peer_mig[0]) return fail(c, GRIDDY_ERR_BAD_STATE, "migrant buffers of rank " + std::to_string(nb.rank) + " are not mapped (griddy_mg_ipc_import)");
-      NCCL_TRY(c, api->Send(nb.d_token_out, sizeof(int64_t), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
-      NCCL_TRY(c, api->Recv(nb.d_token_in, sizeof(int64_t), NCCL_CHAR, nb.rank, c->mg.nccl_comm, c->stream));
-    }
-  }
-  NCCL_TRY(c, api->GroupEnd());
-  CUDA_TRY(c, cudaEventRecord(c->mg.ev_arrived, c->mg.comm_stream));
+// ---- the four small kernels of a partitioned world, on stream s -------------------------------------
+// None of them touches what the compute kernel running beside it writes (see launch_tick), so the NCCL
+// transport keeps them off the compute stream altogether.
+int mg_halo_pack(Ctx* c, int64_t tick, cudaStream_t s) {
+  if (!c->mg.n_exp) return GRIDDY_OK;
+  CUDA_TRY(c, launch_dependent(k_halo_pack, (unsigned)((c->mg.n_exp + 127) / 128), 128u, s, c->p, (int)(tick & 1),
+                               (const int32_t*)c->mg.d_exp_items, c->mg.n_exp, c->mg.d_halo_send));
+  ++c->launches;
   return GRIDDY_OK;
 }
 
-int exchange_arrived(Ctx* c) {
+int mg_halo_unpack(Ctx* c, cudaStream_t s) {
+  if (!c->mg.n_imp_junc) return GRIDDY_OK;
+  CUDA_TRY(c, launch_dependent(k_halo_unpack, (unsigned)((c->mg.n_imp_junc + 127) / 128), 128u, s, c->p,
+                               (const int32_t*)c->mg.d_imp_junc, (const int32_t*)c->mg.d_imp_where, c->mg.n_imp_junc));
+  ++c->launches;
+  return GRIDDY_OK;
+}
+
+int mg_emig_pack(Ctx* c, int64_t tick, cudaStream_t s) {
+  CUDA_TRY(c, launch_dependent(k_emig_pack, 64u, 128u, s, c->p, (int)tick));
+  ++c->launches;
+  return GRIDDY_OK;
+}
+
+int mg_immig_unpack(Ctx* c, int64_t tick, cudaStream_t s) {
+  if (c->mg.nb.empty()) return GRIDDY_OK;
+  int most = 1;
+  for (Neighbor& nb : c->mg.nb) {
+    most = std::max(most, nb.mig_in);
+    // upper bound of the slots in use: the neighbour may have filled its buffer
+    c->ns_host = (int32_t)std::min<int64_t>(c->p.cap, (int64_t)c->ns_host + nb.mig_in);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::max(1, most / 512), (unsigned)c->mg.world);   // blockIdx.y: the rank they came from
+  cfg.blockDim = dim3(128);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = GRIDDY_PDL;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(c, cudaLaunchKernelEx(&cfg, k_immig_unpack, c->p, (int)tick));
+  ++c->launches;
+  return GRIDDY_OK;
+}
+
+// ---- NCCL transport ------------------------------------------------------------------------------------
+// Everything an exchange needs runs on the communication stream (high priority), beside one kernel of the
+// compute stream:
+//   k_halo_pack -> halo send/recv -> k_halo_unpack      beside k_advance, which writes pos[new], aux and the
+//       slow list, reads occupancy only of junctions this rank owns, and defers actors gated by a remote
+//       junction to k_slow;
+//   k_emig_pack -> k_immig_unpack     beside k_unlink, which edits the lists of lanes that lost an actor and
+//       the st word of the slots it settles (k_emig_pack rebuilds the three bits it may clear); immigrants
+//       get fresh slots and go on their lane's inbox, which k_unlink does not read.  No message: the sender's
+//       kernel writes the records into the receiver's memory and raises a flag there, the receiver's kernel
+//       waits for the flag.  A receive buffer is written again two ticks later; the halo exchange of the tick
+//       in between (the sender receives it after the receiver's k_link has emptied the buffer) orders that.
+// The compute stream carries the same four kernels as on a single GPU plus two waits.
+int comm_fork(Ctx* c) {   // the communication stream continues from what the compute stream has enqueued so far
+  CUDA_TRY(c, cudaEventRecord(c->mg.ev_packed, c->stream));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->mg.comm_stream, c->mg.ev_packed, 0));
+  return GRIDDY_OK;
+}
+
+int comm_join(Ctx* c) {   // the compute stream continues once the communication stream is done
+  CUDA_TRY(c, cudaEventRecord(c->mg.ev_arrived, c->mg.comm_stream));
   CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->mg.ev_arrived, 0));
+  return GRIDDY_OK;
+}
+
+// The halo: one grouped send/recv with every neighbour on the communication stream.
+int exchange_nccl(Ctx* c) {
+  NcclApi* api = nccl_api();
+  if (!api || !c->mg.nccl_comm) return fail(c, GRIDDY_ERR_NCCL, "multi-GPU context is not connected (griddy_mg_connect_nccl)");
+  cudaStream_t s = c->mg.comm_stream;
+  NCCL_TRY(c, api->GroupStart());
+  for (Neighbor& nb : c->mg.nb) {
+    if (!nb.peer_mig[0]) return fail(c, GRIDDY_ERR_BAD_STATE, "migrant buffers of rank " + std::to_string(nb.rank) + " are not mapped (griddy_mg_ipc_import)");
+    const size_t out = (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double);
+    const size_t in = (size_t)(nb.n_imp_lanes + nb.n_imp_junc) * sizeof(double);
+    if (out) NCCL_TRY(c, api->Send(nb.d_halo_send, out, NCCL_CHAR, nb.rank, c->mg.nccl_comm, s));
+    if (in) NCCL_TRY(c, api->Recv(nb.d_halo_recv, in, NCCL_CHAR, nb.rank, c->mg.nccl_comm, s));
+  }
+  NCCL_TRY(c, api->GroupEnd());
   return GRIDDY_OK;
 }
 
 int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   TRY(tick_begin(c, tick, ev));
-  if (c->mg.on) TRY(exchange_nccl(c, true));      // halo in flight ...
-  TRY(tick_advance(c, tick, ev));                  // ... behind k_advance
-  if (c->mg.on) TRY(exchange_arrived(c));
+  if (!c->mg.on) {
+    TRY(tick_advance(c, tick, ev));
+    TRY(tick_slow(c, tick, ev));
+    TRY(tick_unlink(c, tick, ev));
+    return tick_link(c, tick, ev);
+  }
+  cudaStream_t comm = c->mg.comm_stream;
+  TRY(comm_fork(c));
+  TRY(mg_halo_pack(c, tick, comm));
+  TRY(exchange_nccl(c));
+  TRY(mg_halo_unpack(c, comm));
+  TRY(tick_advance(c, tick, ev));       // while the halo travels
+  TRY(comm_join(c));
   TRY(tick_slow(c, tick, ev));
-  if (c->mg.on) TRY(exchange_nccl(c, false));     // migrants in flight ...
-  TRY(tick_unlink(c, tick, ev));                   // ... behind k_unlink
-  if (c->mg.on) TRY(exchange_arrived(c));
+  TRY(comm_fork(c));
+  TRY(mg_emig_pack(c, tick, comm));
+  TRY(mg_immig_unpack(c, tick, comm));   // waits for the neighbours' flags
+  TRY(tick_unlink(c, tick, ev));        // while the migrants travel
+  TRY(comm_join(c));
   return tick_link(c, tick, ev);
 }
 
-// Local transport: every rank is a context of this process; `src` has recorded ev_ready after writing
-// its send buffers, each neighbour copies what is addressed to it on its own stream.
+// ---- local transport: every rank is a context of this process (tests) -------------------------------
+// Everything runs on each context's own stream; `src` has recorded ev_ready after writing its send
+// buffers, each neighbour copies what is addressed to it on its own stream.
+int local_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+  TRY(tick_begin(c, tick, ev));
+  return mg_halo_pack(c, tick, c->stream);
+}
+
+int local_slow(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+  TRY(mg_halo_unpack(c, c->stream));
+  TRY(tick_slow(c, tick, ev));
+  return mg_emig_pack(c, tick, c->stream);
+}
+
+int local_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+  TRY(mg_immig_unpack(c, tick, c->stream));
+  return tick_link(c, tick, ev);
+}
+
 int exchange_local(Ctx* src, bool halo) {
   for (Neighbor& nb : src->mg.nb) {
     Ctx* dst = src->mg.peers[nb.rank];
@@ -1021,13 +1068,13 @@ int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks) {
     return GRIDDY_OK;
   };
   for (int64_t t = 0; t < n_ticks; ++t) {
-    TRY(each(tick_begin, t, true));
+    TRY(each(local_begin, t, true));
     for (Ctx* c : cs) TRY(exchange_local(c, true));
     TRY(each(tick_advance, t, false));
-    TRY(each(tick_slow, t, true));
+    TRY(each(local_slow, t, true));
     for (Ctx* c : cs) TRY(exchange_local(c, false));
     TRY(each(tick_unlink, t, false));
-    TRY(each(tick_link, t, false));
+    TRY(each(local_link, t, false));
   }
   int rc = GRIDDY_OK;
   for (Ctx* c : cs) {
@@ -1296,7 +1343,11 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
   CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_packed, cudaEventDisableTiming));
   CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_arrived, cudaEventDisableTiming));
-  CUDA_TRY(c, cudaStreamCreateWithFlags(&m.comm_stream, cudaStreamNonBlocking));
+  {   // the small kernels and the exchanges must not queue behind the compute stream's blocks
+    int least = 0, greatest = 0;
+    CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CUDA_TRY(c, cudaStreamCreateWithPriority(&m.comm_stream, cudaStreamNonBlocking, greatest));
+  }
   // what I export to / import from every other rank
   struct Lists { std::vector<int32_t> exp_l, exp_j, imp_l, imp_j; };
   std::vector<Lists> lists(world);
@@ -1342,13 +1393,12 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
       CUDA_TRY(c, cudaMemset(nb.d_mig_recv[par], 0, nb.in_bytes()));
       c->p.mig_mine[r][par] = (int32_t*)nb.d_mig_recv[par];
     }
-    TRY(mg_alloc(c, &nb.d_token_out, 1));
-    TRY(mg_alloc(c, &nb.d_token_in, 1));
-    CUDA_TRY(c, cudaMemset(nb.d_token_out, 0, sizeof(int64_t)));
     c->p.mig_cap[r] = nb.mig_out;
     c->p.mig_in[r] = nb.mig_in;
     m.nb.push_back(nb);
   }
+  TRY(mg_alloc(c, &c->p.mig_done, 1));
+  CUDA_TRY(c, cudaMemset(c->p.mig_done, 0, sizeof(int32_t)));
   m.n_exp = (int)exp_all.size();
   m.n_imp_junc = (int)imp_junc_all.size();
   TRY(mg_alloc(c, &m.d_exp_items, exp_all.size()));

@@ -22,7 +22,16 @@ struct MigRec {
   double item_pos[MIG_ITEMS];
   uint8_t item_kind[MIG_ITEMS], item_side[MIG_ITEMS];
 };
-constexpr size_t MIG_HEADER = 8;
+constexpr size_t MIG_HEADER = 8;   // int32 count (reserved by remote atomics), int32 flag (tick + 1 once the sender is done)
+
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* ptr) {
+  int32_t v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* ptr, int32_t v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
 
 // Halo out: for every lane of mine that a neighbour's actors can enter, its smallest key in (0, ...]
 // (the walk route.scm:118-121 would do), +inf if there is none; for every such junction, its occupancy.
@@ -53,8 +62,10 @@ __global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __
 
 // Emigrants -> one record each, written straight into the receive buffer of the rank that owns their
 // new lane (peer memory over NVLink: remote atomic for the slot, remote stores for the record), so only
-// the actors that actually crossed travel, not a bound-sized message.
+// the actors that actually crossed travel, not a bound-sized message.  The block that finishes last
+// raises the flag in every neighbour's buffer: no message follows the records.
 __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
+  __shared__ bool s_last;
   grid_dependency_wait();
   const int par = tick & 1;
   const int32_t n = p.counters[CNT_STRIDE * par + CNT_EMIG];
@@ -76,7 +87,9 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     r.speed = p.coldf[a].speed;
     r.speed_dt = p.coldf[a].speed_dt;
     r.gid = p.cold[a].gid;
-    r.st = (int32_t)((p.sa[a].st & ~ST_EMIG) | ST_IMMIG);
+    // (k_unlink, which may be running beside this kernel, clears ALIVE | MOVED | EMIG of an emigrant's
+    // slot; an emigrant had all three set)
+    r.st = (int32_t)(((p.sa[a].st | ST_ALIVE | ST_MOVED) & ~ST_EMIG) | ST_IMMIG);
     r.container = lane;
     r.mv_old = p.cold[a].mv_old;
     r.hop = p.cold[a].hop;
@@ -101,6 +114,14 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
     }
     ((MigRec*)(buf + MIG_HEADER))[at] = r;
   }
+  __threadfence_system();   // my records before my block's count
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(p.mig_done, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();   // every block's records before the flags
+  if (threadIdx.x < MAX_RANKS && p.mig_peer[threadIdx.x][par]) st_release_sys((int32_t*)p.mig_peer[threadIdx.x][par] + 1, tick + 1);
+  if (threadIdx.x == 0) *p.mig_done = 0;
 }
 
 // Immigrants: a fresh slot each, then onto their lane's inbox like any local mover.  One launch for all
@@ -110,7 +131,13 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
   const int par = tick & 1;
   const uint8_t* buf = (const uint8_t*)p.mig_mine[blockIdx.y][par];
   if (!buf) return;
-  const int32_t n = min(*(const int32_t*)buf, p.mig_in[blockIdx.y]);
+  if (threadIdx.x == 0) {   // the sender's flag: all its records of this tick are in my memory
+    const long long t0 = clock64();
+    while (ld_acquire_sys((const int32_t*)buf + 1) < tick + 1)
+      if (clock64() - t0 > (20LL << 30)) { dev_error(p, DEV_ERR_MIG_TIMEOUT); break; }   // ~10 s: the neighbour is gone
+  }
+  __syncthreads();
+  const int32_t n = min(ld_acquire_sys((const int32_t*)buf), p.mig_in[blockIdx.y]);
   const MigRec* recs = (const MigRec*)(buf + MIG_HEADER);
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const MigRec r = recs[i];

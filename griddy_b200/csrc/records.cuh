@@ -17,7 +17,7 @@ constexpr uint32_t ST_IMMIG = 2048u;    // multi-GPU: arrived from another rank 
 
 constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
               DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32, DEV_ERR_MIG_OVERFLOW = 64,
-              DEV_ERR_MIG_AGENDA = 128;
+              DEV_ERR_MIG_AGENDA = 128, DEV_ERR_MIG_TIMEOUT = 256;
 
 // Params::counters[parity][...]
 constexpr int CNT_EMIG = 0, CNT_LEFT = 1, CNT_SLOW = 2, CNT_ENTERED = 3, CNT_STRIDE = 4;
@@ -136,10 +136,12 @@ struct Params {
   int32_t* emig;             // slots that emigrated this tick
   int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
   // by destination rank and tick parity: that rank's receive buffer for my emigrants, in ITS memory
-  // (peer access over NVLink): [int32 count, pad][MigRec x mig_cap].  k_emig_pack writes there directly.
+  // (peer access over NVLink): [int32 count, int32 flag][MigRec x mig_cap].  k_emig_pack writes the records there
+  // directly and then raises the flag to tick + 1, which is what the receiver's k_immig_unpack waits for.
   uint8_t* mig_peer[MAX_RANKS][2];
   int32_t* mig_mine[MAX_RANKS][2];   // my own receive buffers, by source rank: [int32 count, pad][MigRec x mig_in[rank]]
   int32_t mig_in[MAX_RANKS];         // by source rank: records per tick at most
+  int32_t* mig_done;                 // blocks of k_emig_pack that have finished (the last one raises the flags)
 };
 
 }  // namespace griddy

@@ -186,7 +186,7 @@ int griddy_mg_nccl_unique_id(uint8_t* out128);
 int griddy_mg_connect_nccl(void* ctx, const uint8_t* id128);
 /* NCCL transport only: the actors that cross are written by the sender's kernel straight into the
  * receiver's memory (peer access over NVLink), so every rank hands each neighbour the cudaIpc handles
- * of the buffers it receives in (2 x 64 bytes), after griddy_mg_configure and before the first step. */
+ * of the buffers it receives in (2 x 64 bytes), after griddy_mg_configure and before the first step.  Nothing else follows the records: the sender raises a flag in the receiver's buffer. */
 int griddy_mg_neighbors(void* ctx, int32_t* ranks /* MAX 8, may be NULL */, int32_t* n);
 int griddy_mg_ipc_export(void* ctx, int32_t from_rank, uint8_t* handles128);
 int griddy_mg_ipc_import(void* ctx, int32_t to_rank, const uint8_t* handles128);
