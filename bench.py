@@ -291,6 +291,12 @@ def main():
     barrier()
     dev_ms = sim.last_step_ms
     launches = sim.kernel_launches - launches0
+    if os.environ.get("GRIDDY_DUMP_TRACE"):   # -DGRIDDY_TRACE builds: the last 64 ticks' kernel start stamps
+        stamps = np.zeros((64, 16), np.uint64)
+        rc = device.lib().griddy_debug_trace(sim.h, stamps.ctypes.data)
+        if rc == 0:
+            np.save(os.path.join(os.environ["GRIDDY_DUMP_TRACE"], f"trace_n{world}_rank{rank}.npy"), stamps)
+            log(f"[bench] rank {rank}: trace written")
     alive1 = sim.count_alive()
     # an actor replaced by an equal-key insert is gone (core.scm:173-178) and is not advanced any
     # more: count the living ones only (mean of before / after; the decline is slow and steady)

@@ -294,6 +294,7 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick) {
   __shared__ int4 s_list[ADV_THREADS * ADV_UNROLL];
   __shared__ int32_t s_n, s_base;
   grid_dependency_wait();
+  TRACE(p, tick, TR_ADVANCE);
   const int par = tick & 1;
   int32_t* counters = p.counters + CNT_STRIDE * par;
   if (blockIdx.x == 0 && threadIdx.x < CNT_STRIDE) p.counters[CNT_STRIDE * (par ^ 1) + threadIdx.x] = 0;
@@ -381,6 +382,7 @@ __global__ void SLOW_BOUNDS k_slow(Params p, int tick) {
   __shared__ int32_t s_left[SLOW_THREADS], s_entered[SLOW_THREADS];
   __shared__ int32_t s_nl, s_ne, s_base_l, s_base_e;
   grid_dependency_wait();
+  TRACE(p, tick, TR_SLOW);
   const int par = tick & 1;
   int32_t* counters = p.counters + CNT_STRIDE * par;
   const int32_t n_slow = counters[CNT_SLOW];

@@ -78,9 +78,9 @@
 // The device code lives in the .cuh files next to this one, included in dependency order:
 #include "records.cuh"
 #include "advance.cuh"
+#include "multi_gpu.cuh"
 #include "lanes.cuh"
 #include "setup.cuh"
-#include "multi_gpu.cuh"
 #include "reorder.cuh"
 #include "readback.cuh"
 
@@ -735,6 +735,12 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   TRY(dev_alloc(c, pool, &p.emig, cap));
   TRY(dev_alloc(c, pool, &p.counters, 2 * CNT_STRIDE));
   TRY(dev_alloc(c, pool, &p.scal, SC_COUNT));
+#ifdef GRIDDY_TRACE
+  TRY(dev_alloc(c, pool, &p.trace, 64 * TR_COUNT));
+  CUDA_TRY(c, cudaMemset(p.trace, 0, 64 * TR_COUNT * sizeof(unsigned long long)));
+#else
+  p.trace = nullptr;
+#endif
   CUDA_TRY(c, cudaMemset(p.counters, 0, 2 * CNT_STRIDE * sizeof(int32_t)));
   {
     int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n_agenda};
@@ -864,7 +870,10 @@ unsigned relink_blocks(const Ctx* c) {
 }
 
 int tick_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // local lists only: does not need the migrants
-  CUDA_TRY(c, launch_dependent(k_unlink, relink_blocks(c), 128u, c->stream, c->p, (int)tick));
+  if (c->mg.on)   // its first blocks send this tick's emigrants
+    CUDA_TRY(c, launch_dependent(k_unlink<true>, relink_blocks(c) + EMIG_BLOCKS, 128u, c->stream, c->p, (int)tick));
+  else
+    CUDA_TRY(c, launch_dependent(k_unlink<false>, relink_blocks(c), 128u, c->stream, c->p, (int)tick));
   if (ev) cudaEventRecord(ev[4], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -883,21 +892,15 @@ int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // on a partitioned wor
 int mg_halo_pack(Ctx* c, int64_t tick, cudaStream_t s) {
   if (!c->mg.n_exp) return GRIDDY_OK;
   CUDA_TRY(c, launch_dependent(k_halo_pack, (unsigned)((c->mg.n_exp + 127) / 128), 128u, s, c->p, (int)(tick & 1),
-                               (const int32_t*)c->mg.d_exp_items, c->mg.n_exp, c->mg.d_halo_send));
+                               (const int32_t*)c->mg.d_exp_items, c->mg.n_exp, c->mg.d_halo_send, (int)tick));
   ++c->launches;
   return GRIDDY_OK;
 }
 
-int mg_halo_unpack(Ctx* c, cudaStream_t s) {
+int mg_halo_unpack(Ctx* c, int64_t tick, cudaStream_t s) {
   if (!c->mg.n_imp_junc) return GRIDDY_OK;
   CUDA_TRY(c, launch_dependent(k_halo_unpack, (unsigned)((c->mg.n_imp_junc + 127) / 128), 128u, s, c->p,
-                               (const int32_t*)c->mg.d_imp_junc, (const int32_t*)c->mg.d_imp_where, c->mg.n_imp_junc));
-  ++c->launches;
-  return GRIDDY_OK;
-}
-
-int mg_emig_pack(Ctx* c, int64_t tick, cudaStream_t s) {
-  CUDA_TRY(c, launch_dependent(k_emig_pack, 64u, 128u, s, c->p, (int)tick));
+                               (const int32_t*)c->mg.d_imp_junc, (const int32_t*)c->mg.d_imp_where, c->mg.n_imp_junc, (int)tick));
   ++c->launches;
   return GRIDDY_OK;
 }
@@ -925,17 +928,15 @@ int mg_immig_unpack(Ctx* c, int64_t tick, cudaStream_t s) {
 }
 
 // ---- NCCL transport ------------------------------------------------------------------------------------
-// Everything an exchange needs runs on the communication stream (high priority), beside one kernel of the
-// compute stream:
-//   k_halo_pack -> halo send/recv -> k_halo_unpack      beside k_advance, which writes pos[new], aux and the
-//       slow list, reads occupancy only of junctions this rank owns, and defers actors gated by a remote
-//       junction to k_slow;
-//   k_emig_pack -> k_immig_unpack     beside k_unlink, which edits the lists of lanes that lost an actor and
-//       the st word of the slots it settles (k_emig_pack rebuilds the three bits it may clear); immigrants
-//       get fresh slots and go on their lane's inbox, which k_unlink does not read.  No message: the sender's
-//       kernel writes the records into the receiver's memory and raises a flag there, the receiver's kernel
-//       waits for the flag.  A receive buffer is written again two ticks later; the halo exchange of the tick
-//       in between (the sender receives it after the receiver's k_link has emptied the buffer) orders that.
+// The halo travels on the communication stream (high priority) beside k_advance:
+//   k_halo_pack -> halo send/recv -> k_halo_unpack.  k_advance writes pos[new], aux and the slow list, reads
+//       occupancy only of junctions this rank owns, and defers actors gated by a remote junction to k_slow.
+// The migrants need no message and no second stream: the first blocks of k_unlink write the records into the
+// receivers' memory and raise a flag there (the other blocks edit the lists of lanes that lost an actor and
+// the st word of the slots they settle; the packing blocks rebuild the three bits that may clear);
+// k_immig_unpack, next on the compute stream, waits for the neighbours' flags.  A receive buffer is written
+// again two ticks later; the halo exchange of the tick in between (the sender receives it after the
+// receiver's k_link has emptied the buffer) orders that.
 // The compute stream carries the same four kernels as on a single GPU plus two waits.
 int comm_fork(Ctx* c) {   // the communication stream continues from what the compute stream has enqueued so far
   CUDA_TRY(c, cudaEventRecord(c->mg.ev_packed, c->stream));
@@ -978,15 +979,12 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   TRY(comm_fork(c));
   TRY(mg_halo_pack(c, tick, comm));
   TRY(exchange_nccl(c));
-  TRY(mg_halo_unpack(c, comm));
+  TRY(mg_halo_unpack(c, tick, comm));
   TRY(tick_advance(c, tick, ev));       // while the halo travels
   TRY(comm_join(c));
   TRY(tick_slow(c, tick, ev));
-  TRY(comm_fork(c));
-  TRY(mg_emig_pack(c, tick, comm));
-  TRY(mg_immig_unpack(c, tick, comm));   // waits for the neighbours' flags
-  TRY(tick_unlink(c, tick, ev));        // while the migrants travel
-  TRY(comm_join(c));
+  TRY(tick_unlink(c, tick, ev));                  // its first blocks send the emigrants
+  TRY(mg_immig_unpack(c, tick, c->stream));       // waits for the neighbours' flags
   return tick_link(c, tick, ev);
 }
 
@@ -999,9 +997,8 @@ int local_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
 }
 
 int local_slow(Ctx* c, int64_t tick, cudaEvent_t* ev) {
-  TRY(mg_halo_unpack(c, c->stream));
-  TRY(tick_slow(c, tick, ev));
-  return mg_emig_pack(c, tick, c->stream);
+  TRY(mg_halo_unpack(c, tick, c->stream));
+  return tick_slow(c, tick, ev);
 }
 
 int local_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {
@@ -1071,9 +1068,9 @@ int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks) {
     TRY(each(local_begin, t, true));
     for (Ctx* c : cs) TRY(exchange_local(c, true));
     TRY(each(tick_advance, t, false));
-    TRY(each(local_slow, t, true));
+    TRY(each(local_slow, t, false));
+    TRY(each(tick_unlink, t, true));                       // (its first blocks write the emigrants)
     for (Ctx* c : cs) TRY(exchange_local(c, false));
-    TRY(each(tick_unlink, t, false));
     TRY(each(local_link, t, false));
   }
   int rc = GRIDDY_OK;
@@ -1639,6 +1636,19 @@ void* griddy_host_alloc(int64_t bytes) {
 
 void griddy_host_free(void* ptr) {
   if (ptr) cudaFreeHost(ptr);
+}
+
+int griddy_debug_trace(void* ctx, uint64_t* stamps) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c || !stamps) return GRIDDY_ERR_BAD_ARG;
+#ifdef GRIDDY_TRACE
+  if (!c->p.trace) return fail(c, GRIDDY_ERR_BAD_STATE, "debug_trace: no actors uploaded");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaMemcpy(stamps, c->p.trace, 64 * TR_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return GRIDDY_OK;
+#else
+  return fail(c, GRIDDY_ERR_BAD_STATE, "debug_trace: the library was not built with -DGRIDDY_TRACE");
+#endif
 }
 
 int griddy_count_alive(void* ctx, int64_t* n_alive) {

@@ -38,8 +38,9 @@ __device__ __forceinline__ void st_release_sys(int32_t* ptr, int32_t v) {
 // One launch for all neighbours: `items` and `out` are the neighbours' lists back to back (each
 // neighbour's part of `out` is what is sent to it); a junction is listed as ~id.
 __global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int32_t* __restrict__ items, int n,
-                                                    double* __restrict__ out) {
+                                                    double* __restrict__ out, int tick) {
   grid_dependency_wait();
+  TRACE(p, tick, TR_HALO_PACK);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int32_t item = items[i];
@@ -54,74 +55,104 @@ __global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int3
 // One launch for all neighbours: junctions[i] is a junction another rank owns, where[i] its place in
 // halo_recv.
 __global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __restrict__ junctions,
-                                                      const int32_t* __restrict__ where, int n) {
+                                                      const int32_t* __restrict__ where, int n, int tick) {
   grid_dependency_wait();
+  TRACE(p, tick, TR_HALO_UNPACK);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p.occ[junctions[i]] = (int32_t)p.halo_recv[where[i]];
 }
 
 // Emigrants -> one record each, written straight into the receive buffer of the rank that owns their
-// new lane (peer memory over NVLink: remote atomic for the slot, remote stores for the record), so only
-// the actors that actually crossed travel, not a bound-sized message.  The block that finishes last
-// raises the flag in every neighbour's buffer: no message follows the records.
-__global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
+// new lane (peer memory over NVLink: remote stores for the records, one remote atomic per block and
+// destination for the slots), so only the actors that actually crossed travel, not a bound-sized message.
+// The block that finishes last raises the flag in every neighbour's buffer: no message follows the records.
+// Runs as the first EMIG_BLOCKS blocks of k_unlink (lanes.cuh): both need k_slow only, and what k_unlink
+// changes of an emigrant's slot — it clears ALIVE | MOVED | EMIG in st — is rebuilt here.
+constexpr int EMIG_BLOCKS = 64;
+
+__device__ __forceinline__ void emig_pack_block(const Params& p, const int tick, const int block, const int n_blocks) {
   __shared__ bool s_last;
-  grid_dependency_wait();
+  __shared__ int32_t s_count[MAX_RANKS], s_base[MAX_RANKS];
+  TRACE(p, tick, TR_EMIG_PACK);
   const int par = tick & 1;
   const int32_t n = p.counters[CNT_STRIDE * par + CNT_EMIG];
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int a = p.emig[i];
-    if (p.cold[a].dead_mark == tick + 1) continue;   // a ghost's move is void
-    const int32_t lane = p.cold[a].container;
-    const int32_t to = p.owner[lane];
-    uint8_t* buf = p.mig_peer[to][par];
-    const int32_t at = atomicAdd_system((int32_t*)buf, 1);
-    if (at >= p.mig_cap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
+  for (int32_t chunk = block * blockDim.x; chunk < n; chunk += n_blocks * blockDim.x) {
+    if (threadIdx.x < MAX_RANKS) s_count[threadIdx.x] = 0;
+    __syncthreads();
+    const int32_t i = chunk + threadIdx.x;
+    int a = -1, to = -1, mine = 0;
     MigRec r;
-    r.pos_old = p.pos[par][a];
-    r.pos_new = p.pos[par ^ 1][a];
-    r.delta = p.db[a].x;
-    r.buf = p.db[a].y;
-    r.arrive = p.coldf[a].arrive;
-    r.land_pos = p.coldf[a].land_pos;
-    r.speed = p.coldf[a].speed;
-    r.speed_dt = p.coldf[a].speed_dt;
-    r.gid = p.cold[a].gid;
-    // (k_unlink, which may be running beside this kernel, clears ALIVE | MOVED | EMIG of an emigrant's
-    // slot; an emigrant had all three set)
-    r.st = (int32_t)(((p.sa[a].st | ST_ALIVE | ST_MOVED) & ~ST_EMIG) | ST_IMMIG);
-    r.container = lane;
-    r.mv_old = p.cold[a].mv_old;
-    r.hop = p.cold[a].hop;
-    r.tj = p.tj[a] >= 0 ? (p.tj[a] & ~TJ_REMOTE) : -1;
-    r.dest_lane = p.cold[a].dest_lane;
-    r.dest_from_j = p.cold[a].dest_from_j;
-    r.dest_to_j = p.cold[a].dest_to_j;
-    r.pad = 0;
-    const int32_t beg = p.coldf[a].agenda_beg, end = p.coldf[a].agenda_end;
-    r.popped = p.cold[a].agenda_cur - beg;
-    r.n_items = end - beg;
-    r.land_tick = p.coldf[a].land_tick;
-    r.land_lane = p.coldf[a].land_lane;
-    if (r.n_items > MIG_ITEMS) { dev_error(p, DEV_ERR_MIG_AGENDA); r.n_items = MIG_ITEMS; }
-    for (int k = 0; k < MIG_ITEMS; ++k) {
-      const bool in = k < r.n_items;
-      r.item_kind[k] = in ? p.item_kind[beg + k] : 0;
-      r.item_side[k] = in ? p.item_side[beg + k] : 0;
-      r.item_sleep[k] = in ? p.item_sleep[beg + k] : 0;
-      r.item_seg[k] = in ? p.item_seg[beg + k] : -1;
-      r.item_pos[k] = in ? p.item_pos[beg + k] : 0.0;
+    if (i < n) {
+      a = p.emig[i];
+      const Cold k = p.cold[a];
+      if (k.dead_mark == tick + 1) {
+        a = -1;   // a ghost's move is void
+      } else {
+        // the whole record is gathered before the slot is reserved: one round trip less on the way
+        const ColdF f = p.coldf[a];
+        const double2 db = p.db[a];
+        const int32_t tj = p.tj[a];
+        to = p.owner[k.container];
+        mine = atomicAdd(&s_count[to], 1);
+        r.pos_old = p.pos[par][a];
+        r.pos_new = p.pos[par ^ 1][a];
+        r.delta = db.x;
+        r.buf = db.y;
+        r.arrive = f.arrive;
+        r.land_pos = f.land_pos;
+        r.speed = f.speed;
+        r.speed_dt = f.speed_dt;
+        r.gid = k.gid;
+        r.st = (int32_t)(((p.sa[a].st | ST_ALIVE | ST_MOVED) & ~ST_EMIG) | ST_IMMIG);
+        r.container = k.container;
+        r.mv_old = k.mv_old;
+        r.hop = k.hop;
+        r.tj = tj >= 0 ? (tj & ~TJ_REMOTE) : -1;
+        r.dest_lane = k.dest_lane;
+        r.dest_from_j = k.dest_from_j;
+        r.dest_to_j = k.dest_to_j;
+        r.pad = 0;
+        const int32_t beg = f.agenda_beg;
+        r.popped = k.agenda_cur - beg;
+        r.n_items = f.agenda_end - beg;
+        r.land_tick = f.land_tick;
+        r.land_lane = f.land_lane;
+        if (r.n_items > MIG_ITEMS) { dev_error(p, DEV_ERR_MIG_AGENDA); r.n_items = MIG_ITEMS; }
+#pragma unroll
+        for (int q = 0; q < MIG_ITEMS; ++q) {
+          const bool in = q < r.n_items;
+          r.item_kind[q] = in ? p.item_kind[beg + q] : 0;
+          r.item_side[q] = in ? p.item_side[beg + q] : 0;
+          r.item_sleep[q] = in ? p.item_sleep[beg + q] : 0;
+          r.item_seg[q] = in ? p.item_seg[beg + q] : -1;
+          r.item_pos[q] = in ? p.item_pos[beg + q] : 0.0;
+        }
+      }
     }
-    ((MigRec*)(buf + MIG_HEADER))[at] = r;
+    __syncthreads();
+    if (threadIdx.x < MAX_RANKS && s_count[threadIdx.x] > 0)
+      s_base[threadIdx.x] = atomicAdd_system((int32_t*)p.mig_peer[threadIdx.x][par], s_count[threadIdx.x]);
+    __syncthreads();
+    if (a < 0) continue;
+    const int32_t at = s_base[to] + mine;
+    if (at >= p.mig_cap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
+    ((MigRec*)(p.mig_peer[to][par] + MIG_HEADER))[at] = r;
   }
   __threadfence_system();   // my records before my block's count
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(p.mig_done, 1) == (int)gridDim.x - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(p.mig_done, 1) == n_blocks - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();   // every block's records before the flags
   if (threadIdx.x < MAX_RANKS && p.mig_peer[threadIdx.x][par]) st_release_sys((int32_t*)p.mig_peer[threadIdx.x][par] + 1, tick + 1);
   if (threadIdx.x == 0) *p.mig_done = 0;
+#ifdef GRIDDY_TRACE
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    p.trace[(tick & 63) * TR_COUNT + TR_EMIG_FLAG] = t_;
+  }
+#endif
 }
 
 // Immigrants: a fresh slot each, then onto their lane's inbox like any local mover.  One launch for all
@@ -129,6 +160,7 @@ __global__ void __launch_bounds__(128) k_emig_pack(Params p, int tick) {
 __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
   grid_dependency_wait();
   const int par = tick & 1;
+  TRACE(p, tick, TR_IMMIG_UNPACK);
   const uint8_t* buf = (const uint8_t*)p.mig_mine[blockIdx.y][par];
   if (!buf) return;
   if (threadIdx.x == 0) {   // the sender's flag: all its records of this tick are in my memory
@@ -137,6 +169,13 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
       if (clock64() - t0 > (20LL << 30)) { dev_error(p, DEV_ERR_MIG_TIMEOUT); break; }   // ~10 s: the neighbour is gone
   }
   __syncthreads();
+#ifdef GRIDDY_TRACE
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {   // the later of the neighbours' flags
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    atomicMax(&p.trace[(tick & 63) * TR_COUNT + TR_IMMIG_GO], t_);
+  }
+#endif
   const int32_t n = min(ld_acquire_sys((const int32_t*)buf), p.mig_in[blockIdx.y]);
   const MigRec* recs = (const MigRec*)(buf + MIG_HEADER);
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

@@ -29,6 +29,22 @@ constexpr int CNT_EMIG = 0, CNT_LEFT = 1, CNT_SLOW = 2, CNT_ENTERED = 3, CNT_STR
 #ifndef GRIDDY_PDL
 #define GRIDDY_PDL 1
 #endif
+// Timeline diagnostics (profiles/r1_mg_timeline.md): compiled in with -DGRIDDY_TRACE only.
+enum { TR_ADVANCE, TR_SLOW, TR_UNLINK, TR_LINK, TR_HALO_PACK, TR_HALO_UNPACK, TR_EMIG_PACK, TR_EMIG_FLAG,
+       TR_IMMIG_UNPACK, TR_IMMIG_GO, TR_LINK_END, TR_COUNT = 16 };
+#ifdef GRIDDY_TRACE
+#define TRACE(p, tick, slot)                                                                 \
+  do {                                                                                       \
+    if ((p).trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {               \
+      unsigned long long t_;                                                                 \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
+      (p).trace[((tick) & 63) * TR_COUNT + (slot)] = t_;                                     \
+    }                                                                                        \
+  } while (0)
+#else
+#define TRACE(p, tick, slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ void grid_dependency_wait() {
 #if GRIDDY_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -142,6 +158,7 @@ struct Params {
   int32_t* mig_mine[MAX_RANKS][2];   // my own receive buffers, by source rank: [int32 count, pad][MigRec x mig_in[rank]]
   int32_t mig_in[MAX_RANKS];         // by source rank: records per tick at most
   int32_t* mig_done;                 // blocks of k_emig_pack that have finished (the last one raises the flags)
+  unsigned long long* trace;         // -DGRIDDY_TRACE builds: [64 ticks][16] %globaltimer stamps (griddy_debug_trace)
 };
 
 }  // namespace griddy

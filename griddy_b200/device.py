@@ -29,7 +29,7 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_mg_nccl_unique_id", "griddy_mg_connect_nccl", "griddy_mg_connect_local", "griddy_mg_step_local",
            "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
            "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
-           "griddy_positions_end", "griddy_host_alloc", "griddy_host_free")
+           "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace")
 
 
 class GriddyCudaError(RuntimeError):
