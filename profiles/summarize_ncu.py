@@ -30,7 +30,7 @@ def main(raw, out):
     hdr, units = rows[0], rows[1]
     kernels = []
     for r in rows[2:]:
-        k = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].replace("<unnamed>::", "")}
+        k = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].replace("<unnamed>::", "").replace("void ", "").split("<")[0]}
         for metric, name in WANT.items():
             if metric in hdr:
                 i = hdr.index(metric)
