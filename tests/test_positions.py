@@ -155,3 +155,20 @@ def test_positions_need_geometry():
     with pytest.raises(device.GriddyCudaError) as e:
         sim.positions()
     assert e.value.code == 1
+
+
+@pytest.mark.parametrize("name,make", [("simple", examples.simple_make_skeleton),
+                                       ("triangle", examples.triangle_make_skeleton),
+                                       ("grid-5x5-80", lambda: examples.grid_make_skeleton(5)),
+                                       ("grid-3x3-crowded", lambda: examples.grid_make_skeleton(3)),
+                                       ("grid-2x2-jam", lambda: examples.grid_make_skeleton(2))])
+def test_api_mirror_geometry_matches_the_reference(name, make):
+    """The Python mirror of spatial.scm (griddy_b200/core.py) — and through test_generator_geometry_matches_api_mirror
+    the C++ generator — yields, bit for bit, the lane lengths and the drawing geometry that the reference's own
+    spatial.scm produced when the fixture was recorded (fp64 vec2 stub, tests/golden/README.md)."""
+    fx, net, _ = load(name)
+    world = make()
+    mirror, idx = flatten.flatten_network(world)
+    assert np.array_equal(mirror.kind, net.kind)
+    assert np.array_equal(mirror.lane_len, net.lane_len)
+    assert np.array_equal(flatten.flatten_geometry(world, idx), np.asarray(fx["network"]["geom"]).reshape(-1, 8))
