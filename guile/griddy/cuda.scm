@@ -4,9 +4,12 @@
 ;;; into the structure-of-arrays bytevectors the C ABI takes, and rebuilds GOOPS actors from a
 ;;; read-back so that `draw' (griddy/simulate.scm:155-160) keeps working.
 ;;;
-;;; NOT EXECUTED IN THIS REPOSITORY'S TEST ENVIRONMENT: the build image has no Guile.  The same
-;;; symbols, argument order and array layouts are exercised through ctypes by griddy_b200/device.py
-;;; and the flattening rules by griddy_b200/flatten.py, which this file mirrors line for line.
+;;; NOT EXECUTED UNDER GUILE IN THIS REPOSITORY (the build image has none).  It IS executed by
+;;; tests/test_guile_glue.py under the Scheme evaluator that records the golden fixtures, with (system
+;;; foreign) replaced by a stand-in for the library: the arrays this file hands to griddy_upload_network /
+;;; _geometry / _actors for the reference's own examples equal the fixtures' (which the device tests
+;;; upload), and cuda-download-world! rebuilds the reference's world from a read-back.  The same symbols,
+;;; argument order and array layouts are exercised through ctypes by griddy_b200/device.py.
 ;;;
 ;;; Conventions (include/griddy_cuda.h): item id = registration index = N-1-i for position i of
 ;;; (ref world 'static-items) (world.scm:21-22 conses); actor ids such that linking the actors in id

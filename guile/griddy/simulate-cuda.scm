@@ -8,7 +8,9 @@
 ;;; `simulate/headless' is the fixed-tick-count driver BASELINE.json's configs ask for; the stock loop
 ;;; cannot run without a window (event-loop.scm:192-211).
 ;;;
-;;; NOT EXECUTED IN THIS REPOSITORY'S TEST ENVIRONMENT (no Guile in the build image).
+;;; Not executed under Guile here (no Guile in the build image); executed under the fixtures' Scheme
+;;; evaluator by tests/test_guile_glue.py: the reference's example scripts, with (griddy simulate) replaced by
+;;; this module in their use-modules, load / update / draw through it.
 (define-module (griddy simulate-cuda)
   #:use-module (griddy constants)
   #:use-module (griddy math)

@@ -19,7 +19,8 @@
 ;;; check_guile_dump.py compares such a dump with a fixture of tests/golden/ tick by tick, bit for bit.
 ;;; The last line on stderr is the baseline: living-actor updates per second of the Guile loop.
 ;;;
-;;; NOT EXECUTED IN THIS REPOSITORY'S TEST ENVIRONMENT (no Guile, Chickadee, pfds in the build image).
+;;; Not executed under Guile here (no Guile, Chickadee, pfds in the build image).  tests/test_guile_glue.py runs
+;;; this very file under the fixtures' Scheme evaluator and feeds its output to check_guile_dump.py.
 (use-modules (oop goops)
              (srfi srfi-1)
              (srfi srfi-26)
