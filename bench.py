@@ -239,6 +239,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    try:   # run next to this GPU: the pinned frame buffers of the e2e leg are then allocated on its NUMA node
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        log(f"[bench] rank {rank}: bound to the CPUs next to GPU {local_rank} ({len(os.sched_getaffinity(0))} of {os.cpu_count()})")
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] rank {rank}: CPU affinity left alone ({e!r})")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
