@@ -280,7 +280,10 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 #ifndef ADV_UNROLL
 #define ADV_UNROLL 2
 #endif
-constexpr int ADV_THREADS = 256;
+#ifndef ADV_THREADS_N
+#define ADV_THREADS_N 256
+#endif
+constexpr int ADV_THREADS = ADV_THREADS_N;
 #ifndef SLOW_PAYLOAD
 #define SLOW_PAYLOAD 1
 #endif
