@@ -102,19 +102,19 @@ def build_world(grid, n_actors, agenda_len, seed_offset=0, geometry=False):
     return net, actors
 
 
-def cpu_sample_world(args):
+def cpu_sample_world(args, seed_offset=0):
     """Bounded CPU sample: a 64x64 grid with the same actors per segment and agenda shape."""
     from griddy_b200 import synth
     sz_full, sz = synth.grid_sizes(args.grid), synth.grid_sizes(args.cpu_grid)
     n = max(1, int(round(args.actors * sz["n_segments"] / sz_full["n_segments"])))
-    net, actors = build_world(args.cpu_grid, n, args.agenda_len)
+    net, actors = build_world(args.cpu_grid, n, args.agenda_len, seed_offset=seed_offset)
     return net, actors, n
 
 
-def time_oracle(args, ticks):
+def time_oracle(args, ticks, seed_offset=0):
     """Living-actor updates per second of the oracle (vanished actors are not advanced, core.scm:173-178)."""
     from oracle.oracle import Oracle
-    net, actors, n = cpu_sample_world(args)
+    net, actors, n = cpu_sample_world(args, seed_offset)
     o = Oracle(net, actors)
     o.step(args.spinup)
     a0 = int(o.state().alive.sum())
@@ -123,6 +123,26 @@ def time_oracle(args, ticks):
     dt = time.perf_counter() - t0
     a1 = int(o.state().alive.sum())
     return 0.5 * (a0 + a1) * ticks / dt, dt, n, a1
+
+
+def time_oracle_all_cores(args, ticks):
+    """The same sample on every host core at once: independent replicas of the single-threaded loop (different
+    actors each), one process per core.  The reference cannot use more than one core for one world
+    (readme.md:23-26); this is what the box's CPUs deliver in total, for scale."""
+    import subprocess
+    cores = len(os.sched_getaffinity(0))
+    cmd = [sys.executable, os.path.abspath(__file__), "--grid", str(args.grid), "--actors", str(args.actors),
+           "--agenda-len", str(args.agenda_len), "--spinup", str(args.spinup), "--cpu-grid", str(args.cpu_grid),
+           "--cpu-ticks", str(ticks)]
+    procs = [subprocess.Popen(cmd + ["--oracle-worker", str(k + 1)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+             for k in range(cores)]
+    updates, slowest = 0.0, 0.0
+    for pr in procs:
+        out, _ = pr.communicate(timeout=600)
+        r = json.loads(out.strip().splitlines()[-1])
+        updates += r["updates"]
+        slowest = max(slowest, r["seconds"])
+    return updates / slowest, slowest, cores
 
 
 def run_reference(args):
@@ -214,6 +234,7 @@ def main():
     ap.add_argument("--cpu-grid", type=int, default=64)
     ap.add_argument("--cpu-ticks", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--oracle-worker", type=int, default=0, help=argparse.SUPPRESS)   # one replica of time_oracle_all_cores
     ap.add_argument("--reorder-period", type=int, default=384)
     ap.add_argument("--strips-per-rank", type=int, default=0,
                     help="multi-GPU: strips of junction rows per rank, dealt in turn (load balance); 0 = 2 beyond two GPUs")
@@ -225,6 +246,10 @@ def main():
         args.strips_per_rank = 2 if args.gpus > 2 else 1
     os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout, which carries the one JSON line
 
+    if args.oracle_worker:
+        v, dt, _, _ = time_oracle(args, args.cpu_ticks, seed_offset=args.oracle_worker)
+        print(json.dumps({"updates": v * dt, "seconds": dt}), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
@@ -419,7 +444,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    cpu = None
+    cpu = cpu_all = None
     if not args.no_cpu_baseline and world == 1:
         v, dt, n_cpu, _ = time_oracle(args, args.cpu_ticks)
         cpu = {"value": v, "unit": "actor-updates/s", "cores": 1, "kind": "port",
@@ -427,6 +452,15 @@ def main():
                          f"{args.cpu_ticks} ticks after {args.spinup} spin-up ticks, {dt:.1f}s; C++ restatement "
                          f"of the reference on 1 of {os.cpu_count()} host cores (the reference is single-threaded; "
                          f"Guile is not installed)"}
+        try:
+            va, dta, cores = time_oracle_all_cores(args, max(args.cpu_ticks // 2, 1))
+            cpu_all = {"value": va, "unit": "actor-updates/s", "cores": cores, "kind": "port",
+                       "sample": f"{cores} independent replicas of the same sample (different actors each), one process "
+                                 f"per core, {max(args.cpu_ticks // 2, 1)} ticks after {args.spinup} spin-up ticks, "
+                                 f"{dta:.1f}s; the reference itself is single-threaded, so this is the box's total, not "
+                                 f"one world's speed"}
+        except Exception as e:  # noqa: BLE001  (an extra, never worth losing the line for)
+            log(f"[bench] all-cores CPU leg failed: {e!r}")
     out = {
         "metric": "actor-updates/sec", "value": value, "unit": "actor-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -461,6 +495,7 @@ def main():
                      "kernel_share_of_tick": {k: v / tick_ms_prof for k, v in kpt.items()} if tick_ms_prof else None,
                      "reorder_period_ticks": args.reorder_period},
         "cpu_baseline": cpu,
+        "cpu_baseline_all_cores": cpu_all,
         "world": {"alive_before": alive0, "alive_after": alive1, "alive_at_end": alive, "on_road": on_road,
                   "actors_uploaded": total_actors, "wall_s_timed_region": wall,
                   "note": "value counts living actors only" + ("; alive_* are rank 0's, per_rank has every rank's: strips "
