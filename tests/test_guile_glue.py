@@ -331,3 +331,29 @@ def test_headless_reference_runner_and_dump_checker(name, example, ticks, tmp_pa
                         os.path.join(ROOT, "tests", "golden", f"{name}.json.gz"), "--xy"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert f"{ticks + 1} ticks compared, 0 differences" in r.stdout
+
+
+def test_glue_bindings_match_the_header():
+    """Every (c-fn "griddy_…" ret args…) in guile/griddy/cuda.scm has the return type, the number and the types of
+    arguments that include/griddy_cuda.h declares (pointers '*, int64_t int64, int/int32_t int, double double)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "griddy_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = {}
+    for ret, name, params in re.findall(r"\b(int|void|double|int64_t|const char\*|void\*)\s+(griddy_[a-z_]+)\s*\(([^;{]*?)\)\s*;", hdr):
+        def kind(t):
+            t = t.strip()
+            if "*" in t:
+                return "'*"
+            base = t.split()[0] if t.split()[0] != "const" else t.split()[1]
+            return {"int64_t": "int64", "int32_t": "int", "int": "int", "double": "double", "void": "void"}[base]
+        args = [] if params.strip() in ("", "void") else [kind(p) for p in params.split(",")]
+        protos[name] = (kind(ret), args)
+    scm = open(os.path.join(ROOT, "guile", "griddy", "cuda.scm")).read()
+    bound = re.findall(r'\(c-fn "(griddy_[a-z_]+)"\s+([^\s()]+)((?:\s+[^\s()]+)*)\)', scm)
+    assert len(bound) >= 15
+    for name, ret, args in bound:
+        assert name in protos, f"{name} is not declared in the header"
+        want_ret, want_args = protos[name]
+        assert ret == want_ret, (name, ret, want_ret)
+        assert args.split() == want_args, (name, args.split(), want_args)
