@@ -133,3 +133,17 @@ def test_product_code_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "libgriddy_oracle" not in src, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/griddy_cuda.h compiles as C99 with no C++ or CUDA in sight."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = tmp_path / "h.c"
+    src.write_text('#include "griddy_cuda.h"\nint main(void) { return griddy_abi_version() == GRIDDY_ABI_VERSION ? 0 : 1; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
