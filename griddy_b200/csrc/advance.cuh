@@ -154,7 +154,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   if (ah >= 0 && lead == cur) {
     const int32_t lane = p.cold[a].container;
     do {
-      if (atomicExch(&p.cold[ah].dead_mark, tick + 1) != tick + 1)   // the first to notice hands it to k_relink
+      if (atomicExch(&p.cold[ah].dead_mark, tick + 1) != tick + 1)   // the first to notice hands it to k_unlink
         p.cold[ah].ghost_next = atomicExch(&p.lane[lane].ghosts, ah);
       ah = p.sa[ah].ahead;
       if (ah >= 0) lead = pos_old[ah];

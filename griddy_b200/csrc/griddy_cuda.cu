@@ -98,7 +98,7 @@ struct Neighbor {
   int rank = -1;
   int n_exp_lanes = 0, n_exp_junc = 0, n_imp_lanes = 0, n_imp_junc = 0;
   double *d_halo_send = nullptr, *d_halo_recv = nullptr;   // parts of Multi::d_halo_send / d_halo_recv
-  uint8_t* d_mig_recv[2] = {nullptr, nullptr};   // by tick parity; the neighbour's k_emig_pack writes here
+  uint8_t* d_mig_recv[2] = {nullptr, nullptr};   // by tick parity; the neighbour's k_unlink (its packing blocks) writes here
   uint8_t* peer_mig[2] = {nullptr, nullptr};     // the neighbour's receive buffers for me, mapped into this process
   int mig_out = 0, mig_in = 0;      // records per tick at most: a lane lets one actor out per tick
   size_t in_bytes() const { return MIG_HEADER + (size_t)mig_in * sizeof(MigRec); }
@@ -1175,7 +1175,7 @@ int download_state(Ctx* c, bool by_slot, int32_t* gid, uint8_t* alive, uint8_t* 
   CUDA_TRY(c, cudaGetLastError());
   if (order || n_order) {
     // get-actors order (world.scm:24-30): containers by descending registration index, a lane's
-    // actors by descending pos-param, a segment's in list order (landing stamps, see k_relink).
+    // actors by descending pos-param, a segment's in list order (landing stamps, see lanes.cuh).
     std::vector<SA> sa(ns);
     std::vector<uint32_t> st(ns);
     std::vector<uint8_t> ghost(ns);

@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(128, MG ? 12 : 1) k_unlink(Params p, int tick)
 }
 
 // After this tick's immigrants are unpacked (k_link runs behind k_immig_unpack): empty my
-// receive buffers of this parity.  The sender writes them again two ticks from now, after it has seen
-// the token I send next tick.
+// receive buffers of this parity.  The sender writes them again two ticks from now, after it has
+// received the halo I send next tick.
 __device__ __forceinline__ void mig_reset(const Params& p, int par) {
   if (blockIdx.x == 0 && threadIdx.x < MAX_RANKS && p.mig_mine[threadIdx.x][par]) *p.mig_mine[threadIdx.x][par] = 0;
 }

@@ -9,8 +9,8 @@ namespace griddy {
 // while it turns from a segment lane onto a junction lane or back (never while it goes on or off the
 // road).  An actor lives on the rank that owns its container.  What a turning actor reads of the OLD
 // world on the other side — the target lane's rearmost positive pos-param (route.scm:118-121) and the
-// target junction's occupancy (route.scm:98-108) — is the halo, exchanged before k_advance; the actors
-// that crossed are exchanged as fixed-size records before k_relink, which then inserts them by key
+// target junction's occupancy (route.scm:98-108) — is the halo, exchanged while k_advance runs; the actors
+// that crossed are exchanged as fixed-size records before k_link, which then inserts them by key
 // exactly as it inserts local movers (their old lane and old pos-param travel along, because
 // processing order decides equal-key winners).  Results are identical to a single-GPU run.
 

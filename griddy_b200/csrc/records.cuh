@@ -152,12 +152,12 @@ struct Params {
   int32_t* emig;             // slots that emigrated this tick
   int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
   // by destination rank and tick parity: that rank's receive buffer for my emigrants, in ITS memory
-  // (peer access over NVLink): [int32 count, int32 flag][MigRec x mig_cap].  k_emig_pack writes the records there
+  // (peer access over NVLink): [int32 count, int32 flag][MigRec x mig_cap].  emig_pack_block writes the records there
   // directly and then raises the flag to tick + 1, which is what the receiver's k_immig_unpack waits for.
   uint8_t* mig_peer[MAX_RANKS][2];
   int32_t* mig_mine[MAX_RANKS][2];   // my own receive buffers, by source rank: [int32 count, pad][MigRec x mig_in[rank]]
   int32_t mig_in[MAX_RANKS];         // by source rank: records per tick at most
-  int32_t* mig_done;                 // blocks of k_emig_pack that have finished (the last one raises the flags)
+  int32_t* mig_done;                 // packing blocks of k_unlink that have finished (the last one raises the flags)
   unsigned long long* trace;         // -DGRIDDY_TRACE builds: [64 ticks][16] %globaltimer stamps (griddy_debug_trace)
 };
 
