@@ -1259,36 +1259,33 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
   CUDA_TRY(c, cudaSetDevice(c->device));
   const Params& p = c->p;
   const int32_t ns = c->ns_host;
-  std::vector<SA> sa(ns);
-  std::vector<uint32_t> st(ns);
-  std::vector<int32_t> cont(ns), ahead(ns);
-  std::vector<double> ps(ns);
-  if (ns) {
-    CUDA_TRY(c, cudaMemcpy(sa.data(), p.sa, ns * sizeof(SA), cudaMemcpyDeviceToHost));
-    for (int32_t a = 0; a < ns; ++a) { st[a] = sa[a].st; ahead[a] = sa[a].ahead; }
-    std::vector<Cold> cold(ns);
-    CUDA_TRY(c, cudaMemcpy(cold.data(), p.cold, ns * sizeof(Cold), cudaMemcpyDeviceToHost));
-    for (int32_t a = 0; a < ns; ++a) cont[a] = cold[a].container;
-    CUDA_TRY(c, cudaMemcpy(ps.data(), p.pos[c->tick & 1], ns * sizeof(double), cudaMemcpyDeviceToHost));
+  const int64_t n_items = p.n_items;
+  if (n_items == 0 || (!lane_count && !junction_count)) return GRIDDY_OK;
+  // counted on the device: one atomic per living actor; the junction counters are the device's own
+  // incrementally maintained ones (route.scm:98-104), less the ghosts (file header)
+  std::vector<void*> tmp;
+  int32_t *d_lane = nullptr, *d_junc = nullptr;
+  int rc = GRIDDY_OK;
+  if (lane_count) rc = dev_alloc(c, tmp, &d_lane, n_items);
+  if (!rc && junction_count) rc = dev_alloc(c, tmp, &d_junc, n_items);
+  auto done = [&](int r) { free_pool(tmp); return r; };
+  if (rc) return done(rc);
+  cudaStream_t s = c->stream;
+  if (d_lane && cudaMemsetAsync(d_lane, 0, (size_t)n_items * sizeof(int32_t), s) != cudaSuccess) return done(fail(c, GRIDDY_ERR_CUDA, "memset failed"));
+  if (d_junc && cudaMemcpyAsync(d_junc, p.occ, (size_t)n_items * sizeof(int32_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    return done(fail(c, GRIDDY_ERR_CUDA, "copy of the junction counters failed"));
+  if (ns > 0) {
+    const unsigned blocks = (unsigned)((ns + 255) / 256);
+    cudaMemsetAsync(c->d_ghost, 0, (size_t)ns, s);
+    k_flag_ghosts<<<blocks, 256, 0, s>>>(p, (int)(c->tick & 1), c->d_ghost);
+    k_occupancy<<<blocks, 256, 0, s>>>(p, c->d_ghost, d_lane, d_junc);
+    c->launches += 2;
   }
-  // ghost rule: an on-road actor whose list follower holds an equal key is not part of the world
-  std::vector<uint8_t> ghost(ns, 0);
-  for (int32_t a = 0; a < ns; ++a) {
-    if ((st[a] & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD)) continue;
-    for (int32_t x = ahead[a]; x >= 0 && ps[x] == ps[a]; x = ahead[x]) ghost[x] = 1;
-  }
-  if (junction_count) {   // the device's own incrementally maintained counters, less the ghosts
-    CUDA_TRY(c, cudaMemcpy(junction_count, p.occ, (size_t)p.n_items * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    for (int32_t a = 0; a < ns; ++a)
-      if ((st[a] & ST_ALIVE) && ghost[a] && c->h_kind[cont[a]] == GRIDDY_JUNCTION_LANE)
-        --junction_count[c->h_lane_junction[cont[a]]];
-  }
-  if (lane_count) {
-    std::fill(lane_count, lane_count + p.n_items, 0);
-    for (int32_t a = 0; a < ns; ++a)
-      if ((st[a] & ST_ALIVE) && !ghost[a]) ++lane_count[cont[a]];
-  }
-  return GRIDDY_OK;
+  if (d_lane) cudaMemcpyAsync(lane_count, d_lane, (size_t)n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+  if (d_junc) cudaMemcpyAsync(junction_count, d_junc, (size_t)n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+  const cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return done(fail(c, GRIDDY_ERR_CUDA, std::string("download_occupancy: ") + cudaGetErrorString(e)));
+  return done(GRIDDY_OK);
 }
 
 // ---- multi-GPU set-up --------------------------------------------------------------------------
@@ -1670,6 +1667,28 @@ int griddy_count_alive(void* ctx, int64_t* n_alive) {
   CUDA_TRY(c, cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   *n_alive = (int64_t)h;
+  return GRIDDY_OK;
+}
+
+int griddy_state_digest(void* ctx, uint64_t* out3) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_actors || !out3) return fail(c, GRIDDY_ERR_BAD_ARG, "state_digest: no actors or null output");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  out3[0] = out3[1] = out3[2] = 0;
+  const int32_t ns = c->ns_host;
+  if (ns == 0) return GRIDDY_OK;
+  const unsigned blocks = (unsigned)((ns + 255) / 256);
+  unsigned long long* d_out = (unsigned long long*)c->sort_keys;   // reorder scratch, idle between steps
+  CUDA_TRY(c, cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), c->stream));
+  CUDA_TRY(c, cudaMemsetAsync(c->d_ghost, 0, (size_t)ns, c->stream));
+  k_flag_ghosts<<<blocks, 256, 0, c->stream>>>(c->p, (int)(c->tick & 1), c->d_ghost);
+  k_digest<<<blocks, 256, 0, c->stream>>>(c->p, (int)(c->tick & 1), c->d_ghost, d_out);
+  c->launches += 2;
+  unsigned long long h[3] = {0, 0, 0};
+  CUDA_TRY(c, cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 3; ++k) out3[k] = (uint64_t)h[k];
   return GRIDDY_OK;
 }
 

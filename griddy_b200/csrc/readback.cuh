@@ -52,6 +52,70 @@ __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
+// State digest (griddy_state_digest): a 64-bit hash per living actor of its id and of everything
+// griddy_download_actors reports about it, summed and xor-ed over the world.  Both reductions commute, so
+// the digest does not depend on slot order or on how the world is partitioned over ranks: the ranks'
+// digests add / xor up to the single world's.  griddy_b200/digest.py restates it in numpy for read-backs.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {   // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_digest(Params p, int par, const uint8_t* __restrict__ ghost,
+                                                 unsigned long long* __restrict__ out /* sum, xor, living */) {
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  uint64_t h = 0;
+  bool live = false;
+  if (a < p.scal[SC_NSLOTS]) {
+    const uint32_t st = p.sa[a].st;
+    if ((st & ST_ALIVE) && !ghost[a]) {
+      live = true;
+      const Cold k = p.cold[a];
+      const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
+      const uint64_t on_road = (st & ST_ONROAD) ? 1 : 0, side = (!on_road && (st & ST_SIDE)) ? 1 : 0;
+      const uint32_t popped = (uint32_t)(k.agenda_cur - p.coldf[a].agenda_beg);
+      const uint32_t sleep_left = head == HEAD_SLEEP ? (uint32_t)p.aux[a] : 0u;
+      const uint32_t route_head = (uint32_t)(rs == GRIDDY_ROUTE_SOME ? k.hop : -2);
+      h = mix64((uint64_t)(int64_t)k.gid + 1);
+      h = mix64(h ^ ((uint64_t)(uint32_t)k.container | (on_road << 32) | (side << 33) | ((uint64_t)rs << 34)));
+      h = mix64(h ^ (uint64_t)__double_as_longlong(p.pos[par][a]));
+      h = mix64(h ^ ((uint64_t)popped | ((uint64_t)sleep_left << 32)));
+      h = mix64(h ^ (uint64_t)route_head);
+    }
+  }
+  uint64_t sum = h, x = h;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    x ^= __shfl_xor_sync(0xffffffffu, x, d);
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && m) {
+    atomicAdd(&out[0], (unsigned long long)sum);
+    atomicXor(&out[1], (unsigned long long)x);
+    atomicAdd(&out[2], (unsigned long long)__popc(m));
+  }
+}
+
+// Occupancy read-back (griddy_download_occupancy): actors per container, and per junction the device's own
+// incrementally maintained counter less the ghosts standing on its lanes.
+__global__ void __launch_bounds__(256) k_occupancy(Params p, const uint8_t* __restrict__ ghost, int32_t* __restrict__ lane_count,
+                                                    int32_t* __restrict__ junction_count) {
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= p.scal[SC_NSLOTS]) return;
+  const uint32_t st = p.sa[a].st;
+  if (!(st & ST_ALIVE)) return;
+  const int32_t c = p.cold[a].container;
+  if (!ghost[a]) {
+    if (lane_count) atomicAdd(&lane_count[c], 1);
+  } else if (junction_count && p.item[c].kind == GRIDDY_JUNCTION_LANE) {
+    atomicSub(&junction_count[p.item[c].link2], 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Drawing read-back: (get-pos actor) for every slot (spatial.scm:125-149), which is all that `draw`
 // reads of an actor (simulate.scm:155-160 -> draw.scm:74-88).  geom holds 8 doubles per item,
 // computed by the host with the reference's own get-pos / get-vec / curve (include/griddy_cuda.h,

@@ -29,7 +29,7 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_mg_nccl_unique_id", "griddy_mg_connect_nccl", "griddy_mg_connect_local", "griddy_mg_step_local",
            "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
            "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
-           "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace")
+           "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace", "griddy_state_digest")
 
 
 class GriddyCudaError(RuntimeError):
@@ -148,6 +148,12 @@ class Simulation:
         n = C.c_int64(0)
         self._chk(lib().griddy_count_alive(self.h, C.byref(n)))
         return int(n.value)
+
+    def digest(self) -> dict:
+        """Partition-independent digest of this context's living actors (griddy_state_digest; digest.py)."""
+        out = (C.c_uint64 * 3)(0, 0, 0)
+        self._chk(lib().griddy_state_digest(self.h, out))
+        return {"sum": f"{out[0]:016x}", "xor": f"{out[1]:016x}", "alive": int(out[2])}
 
     @property
     def slots_in_use(self) -> int:

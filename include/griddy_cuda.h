@@ -220,6 +220,12 @@ int64_t griddy_kernel_launches(void* ctx);   /* kernels launched by this context
 /* Actors in the world right now (an actor replaced by an equal-key insert is gone, core.scm:173-178). */
 int griddy_count_alive(void* ctx, int64_t* n_alive);
 int64_t griddy_slots_in_use(void* ctx);      /* device slots holding actors (living, or dead and not yet dropped) */
+/* Digest of the world's state: out3 = {sum, xor, count} over the living actors of a 64-bit hash of the actor's id
+ * and of everything griddy_download_actors reports about it (location kind, container, side, pos-param bits, items
+ * popped, sleep time left, route status, route head).  Sum and xor commute: the digests of the ranks of a partitioned
+ * world add / xor up to the digest of the same world on one GPU.  griddy_b200/digest.py computes the same from a
+ * read-back (device or oracle). */
+int griddy_state_digest(void* ctx, uint64_t* out3);
 
 /* Diagnostics for tests/: the reorder's stable LSD radix sort (csrc/radix_sort.cuh) applied to n
  * caller-owned (key, value) pairs in host memory, sorting by the low key_bits bits of the key. */

@@ -1,12 +1,51 @@
 """BASELINE.json configs at (or scaled towards) full size, through the C ABI."""
+import json
+import os
+
 import numpy as np
 import pytest
 
-from griddy_b200 import device
+from griddy_b200 import device, digest
 from helpers import compare, grid_flat
 from oracle.oracle import Oracle
 
 pytestmark = pytest.mark.gpu
+
+SCALE_DIGESTS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_digests.json")
+
+
+def check_against_scale_digests(name):
+    """Step the device through a full-size world and compare, at every checkpoint, one SHA-256 per field of the
+    whole state (actor-id order, pos-param bits, get-actors order, occupancy) and the device's own commutative
+    digest with what the oracle produced for the same world (tests/golden/make_scale_digests.py)."""
+    with open(SCALE_DIGESTS) as f:
+        want = json.load(f)[name]
+    net, actors = grid_flat(want["grid"], want["actors"], agenda_len=want["agenda_len"])
+    sim = device.Simulation(net, actors)
+    tick = 0
+    for cp in sorted(int(k) for k in want["checkpoints"]):
+        sim.step(cp - tick)
+        tick = cp
+        w = want["checkpoints"][str(cp)]
+        assert sim.digest() == w["commutative"], f"{name} tick {cp}: device digest differs from the oracle's"
+        st = sim.state()
+        lane_count, junction_count = sim.occupancy()
+        got = digest.sha_fields(st, lane_count, junction_count)
+        bad = [k for k in w["sha"] if got[k] != w["sha"][k]]
+        assert not bad, f"{name} tick {cp}: device differs from the oracle in {bad}"
+        assert digest.commutative(st) == w["commutative"]
+    return sim
+
+
+def test_c3_full_size_against_oracle_digests():
+    """configs[2] (256x256, 1M actors): every field bit for bit at ticks 100, 200, 300."""
+    check_against_scale_digests("c3")
+
+
+def test_c4_full_size_against_oracle_digests():
+    """configs[3] (1024x1024, 16M actors, 4-item agendas — the bench workload): every field bit for bit at ticks
+    100, 200, 300 and at tick 325, the end of the driver's timed window."""
+    check_against_scale_digests("c4")
 
 
 def test_c3_256_grid_1m_actors_against_oracle():
@@ -52,6 +91,8 @@ def test_c4_one_rank_vs_two_ranks_identical_state():
         assert not a.diff(b), f"tick {150 * (k + 1)}"
         m = a.alive.astype(bool)
         assert np.array_equal(a.pos[m], b.pos[m])
+        # the device-side digests: the two ranks' add / xor up to the single world's
+        assert digest.combine([r.digest() for r in two.ranks]) == one.digest() == digest.commutative(a)
     assert int(a.alive.sum()) < actors.n          # actors vanished, identically on both
     assert int((a.loc_kind[m] == 1).sum()) > 400_000
 
