@@ -298,7 +298,7 @@ def main():
             f"generated in {time.time() - t0:.1f}s")
         sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period,
                                 partition=(rank, world, owner, args.mig_cap, args.extra_slots), gids=ids)
-        device.connect_nccl(sim)
+        device.connect_ipc(sim)
     net.geom = None   # on the device now
     log(f"[bench] rank {rank}: uploaded in {time.time() - t0:.1f}s")
     sim.step(args.spinup)

@@ -64,7 +64,8 @@ __device__ __forceinline__ int32_t junction_after(const Params& p, const Item& i
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
 __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_t ac, int32_t* aux) {
   if (ac >= p.coldf[a].agenda_end) { *aux = 0; return HEAD_NONE; }
-  if (p.item_kind[ac] == GRIDDY_SLEEP_FOR) { *aux = p.item_sleep[ac]; return HEAD_SLEEP; }
+  const AgendaItem ai = p.agenda[ac];
+  if (ai.kind == GRIDDY_SLEEP_FOR) { *aux = ai.sleep; return HEAD_SLEEP; }
   *aux = 0;
   return HEAD_TRAVEL;
 }
@@ -114,7 +115,7 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
   int32_t x = p.lane[target].tail;
   const bool remote = x <= -2;   // multi-GPU: another rank owns the target lane
   if (remote) {                  // its smallest key in (0, ...] came with the halo (+inf: none)
-    const double tlead = p.halo_recv[-2 - x];
+    const double tlead = __ldcg(&p.halo_recv[tick & 1][-2 - x]);
     if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
   } else {
     while (x >= 0 && !(pos_old[x] > 0.0)) x = p.sa[x].ahead;   // smallest key in (0, ...]
@@ -211,18 +212,19 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     if (st & ST_ONROAD) { dev_error(p, DEV_ERR_BEGIN_ON_ROAD); return cur; }
     const int32_t seg = p.cold[a].container;
     const int32_t init_lane = outer_lane(p, seg, st & ST_SIDE);
-    const int32_t dest_lane = outer_lane(p, p.item_seg[item], p.item_side[item]);
+    // the destination was resolved at upload time (off-road->on-road of the travel-to item, location.scm:49-57)
+    const AgendaItem ai = p.agenda[item];
+    const int32_t dest_lane = ai.dlane;
     if (init_lane < 0 || dest_lane < 0) { dev_error(p, DEV_ERR_NO_LANE); return cur; }
+    const Item init_it = p.item[init_lane];
     // off-road->on-road  location.scm:49-57
-    const double init_pos = p.item[init_lane].dir ? __dsub_rn(1.0, cur) : cur;
-    const double ipos = p.item_pos[item];
-    const double dest_pos = p.item[dest_lane].dir ? __dsub_rn(1.0, ipos) : ipos;
+    const double init_pos = init_it.dir ? __dsub_rn(1.0, cur) : cur;
+    const double dest_pos = ai.dpos;
     int32_t rc = p.route_off ? (int32_t)p.route_off[item] : 0;
-    const Item init_it = p.item[init_lane], dest_it = p.item[dest_lane];
     Cold k;
     k.dest_lane = dest_lane;
-    k.dest_from_j = dest_it.from_j;
-    k.dest_to_j = dest_it.to_j;
+    k.dest_from_j = ai.dfrom;
+    k.dest_to_j = ai.dto;
     const int32_t hop = route_head_on(p, init_lane, init_it, k, item, &rc);
     const double len = init_it.len;
     p.cold[a].route_cur = rc;

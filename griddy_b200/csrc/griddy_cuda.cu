@@ -61,8 +61,8 @@
 //
 // fp64 parity: every operation of route.scm:53-135 is issued with round-to-nearest intrinsics
 // (__dadd_rn / __dmul_rn / __ddiv_rn), which the compiler never contracts into FMAs.
+#include <cuda.h>
 #include <cuda_runtime.h>
-#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -93,43 +93,80 @@ namespace {
 
 struct Ctx;
 
-// One neighbouring rank: what I export to it and import from it every tick.
+// One neighbouring rank: what I export to it and import from it every tick, and where in the two windows it goes.
 struct Neighbor {
   int rank = -1;
   int n_exp_lanes = 0, n_exp_junc = 0, n_imp_lanes = 0, n_imp_junc = 0;
-  double *d_halo_send = nullptr, *d_halo_recv = nullptr;   // parts of Multi::d_halo_send / d_halo_recv
-  uint8_t* d_mig_recv[2] = {nullptr, nullptr};   // by tick parity; the neighbour's k_unlink (its packing blocks) writes here
-  uint8_t* peer_mig[2] = {nullptr, nullptr};     // the neighbour's receive buffers for me, mapped into this process
+  int exp_first = 0;                // my export list: entries [exp_first, exp_first + n_exp_lanes + n_exp_junc)
   int mig_out = 0, mig_in = 0;      // records per tick at most: a lane lets one actor out per tick
-  size_t in_bytes() const { return MIG_HEADER + (size_t)mig_in * sizeof(MigRec); }
+  int64_t item_out = 0, item_in = 0;   // agenda items per tick at most
+  // what this neighbour writes into MY window, by tick parity (byte offsets)
+  size_t halo_off[2] = {0, 0}, hflag_off[2] = {0, 0}, mig_off[2] = {0, 0};
+  // its window as mapped here, and where I write in it
+  uint8_t* peer_base = nullptr;
+  size_t peer_halo_off[2] = {0, 0}, peer_hflag_off[2] = {0, 0}, peer_mig_off[2] = {0, 0};
+  bool mapped = false;
+  size_t mig_bytes_in() const { return sizeof(MigHeader) + (size_t)mig_in * sizeof(MigRec) + (size_t)item_in * sizeof(AgendaItem); }
 };
 
 struct Multi {
   bool on = false;
   int rank = 0, world = 1;
   int mig_cap = 16384;
+  int max_agenda_items = 4;
   int64_t extra_slots = 0;
   std::vector<Neighbor> nb;
   std::vector<void*> allocs;
   std::vector<std::pair<int32_t, int32_t>> import_marks;   // (remote lane, -2 - index into halo_recv)
-  double* d_halo_recv = nullptr;      // all neighbours' halos back to back: [lanes, junctions] each
-  double* d_halo_send = nullptr;      // what I send, likewise
-  int32_t* d_exp_items = nullptr;     // per entry of d_halo_send: my lane, or ~(my junction)
+  uint8_t* window = nullptr;          // what my neighbours write into (one allocation, shared through cudaIpc)
+  size_t window_bytes = 0;
+  size_t halo_base[2] = {0, 0};       // byte offset of the halo values of either parity (all neighbours back to back)
+  int32_t* d_exp_items = nullptr;     // my export list: my lane, or ~(my junction), by neighbour
   int n_exp = 0;
-  int32_t *d_imp_junc = nullptr, *d_imp_where = nullptr;   // the neighbours' junctions my actors read, and where in d_halo_recv
+  int32_t *d_imp_junc = nullptr, *d_imp_where = nullptr;   // the neighbours' junctions my actors read, and where in halo_recv
   int n_imp_junc = 0;
   int32_t* d_owner = nullptr;
-  void* nccl_comm = nullptr;          // transport 1: NCCL send/recv between processes, on their own stream
-  cudaStream_t comm_stream = nullptr; //   so that k_advance hides the halo exchange and k_unlink the migrants'
-  cudaEvent_t ev_packed = nullptr, ev_arrived = nullptr;
-  std::vector<Ctx*> peers;            // transport 2: every rank is a context of this process
-  cudaEvent_t ev_ready = nullptr;     //   "my send buffers for this phase are written"
+  bool connected = false;             // every neighbour's window is mapped
+  std::vector<Ctx*> peers;            // local transport: every rank is a context of this process
+  cudaEvent_t ev_ready = nullptr;     //   "what I write into my neighbours' windows in this phase is enqueued"
+};
+
+// Which items this context holds (griddy_set_item_ranges).  Ids are global registration indices everywhere;
+// the per-item device arrays are sparse (virtual address space for every id, memory behind the held ranges
+// only) and the host-side copies are compact, in range order.
+struct Tiling {
+  int64_t n_global = 0, n_local = 0;
+  std::vector<int64_t> beg, end, off;   // ascending, disjoint; off = compact index of each range's first item
+  bool tiled() const { return !(beg.size() == 1 && beg[0] == 0 && end[0] == n_global) && n_global > 0; }
+  void whole(int64_t n) { n_global = n_local = n; beg.assign(1, 0); end.assign(1, n); off.assign(1, 0); }
+  int64_t local(int64_t g) const {   // compact index of a held item, -1 if it is not held
+    size_t lo = 0, hi = beg.size();
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (g < beg[mid]) hi = mid; else if (g >= end[mid]) lo = mid + 1; else return off[mid] + (g - beg[mid]);
+    }
+    return -1;
+  }
+};
+
+// A per-item device array over the GLOBAL id space.  Untiled: one cudaMalloc.  Tiled: a virtual address
+// range for all ids with physical memory mapped behind the held ranges only (CUDA virtual memory management,
+// bound through cudaGetDriverEntryPoint so that the library does not link libcuda).
+struct SparseArray {
+  void* base = nullptr;
+  size_t va_bytes = 0;
+  bool vmm = false;
+  std::vector<std::pair<size_t, size_t>> spans;   // mapped (offset, bytes)
+  std::vector<unsigned long long> handles;
 };
 
 struct Ctx {
   int device = 0;
   std::string err;
   std::vector<void*> net_allocs, actor_allocs;
+  std::vector<SparseArray> net_sparse;
+  Tiling tl, tl_next;      // tl_next: set by griddy_set_item_ranges for the next griddy_upload_network
+  bool have_ranges = false;
   Params p{};
   bool have_net = false, have_actors = false;
   int64_t tick = 0, launches = 0;
@@ -162,11 +199,19 @@ struct Ctx {
   cudaEvent_t ev_drawn[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   int64_t frame_n[2] = {0, 0};
   uint64_t frames_begun = 0, frames_ended = 0;
-  // host copies needed to format downloads
-  std::vector<uint8_t> h_kind;
-  std::vector<int32_t> h_lane_junction, h_lane_out;
+  // host copies of the held items (compact, range order) that uploads validate against
+  std::vector<uint8_t> h_kind, h_dir;
+  std::vector<int32_t> h_lane_junction, h_lane_out, h_of, h_ob, h_from, h_to;
+  // travel-to destinations resolved by the caller (griddy_set_agenda_destinations), for the next upload_actors
+  std::vector<int32_t> dst_lane, dst_from, dst_to;
+  std::vector<uint8_t> dst_dir;
+  bool have_dst = false;
+  AgendaItem* agenda_alt = nullptr;   // second item pool: a reorder of a partitioned world compacts into it
+  int32_t* d_nitems_new = nullptr;
   Multi mg;
-  std::vector<int32_t> mg_owner_host;
+  std::vector<int32_t> mg_owner_host;   // compact
+  uint8_t kind_of(int64_t g) const { const int64_t l = tl.local(g); return l < 0 ? (uint8_t)255 : h_kind[(size_t)l]; }
+  int32_t owner_of(int64_t g) const { const int64_t l = tl.local(g); return l < 0 ? -1 : mg_owner_host[(size_t)l]; }
 };
 
 int fail(Ctx* c, int code, const std::string& msg) {
@@ -253,9 +298,18 @@ int reorder_slots(Ctx* c, int64_t tick) {
   q.src_db = c->db_cur; q.dst_db = c->db_alt;
   q.src_cold = c->cold_cur; q.dst_cold = c->cold_alt;
   q.src_coldf = c->coldf_cur; q.dst_coldf = c->coldf_alt;
+  // a partitioned world: the surviving actors' remaining agenda items move to the second pool, so that the
+  // room taken by the items of actors that have left (or popped them) is reclaimed
+  q.agenda_dst = c->agenda_alt;
+  q.n_items_new = c->d_nitems_new;
+  if (c->agenda_alt) CUDA_TRY(c, cudaMemsetAsync(c->d_nitems_new, 0, sizeof(int32_t), s));
   k_permute<<<n_pad / 256, 256, 0, s>>>(p, q, c->sort_vals, c->newslot, c->tailflag);
   c->launches += 2;
   CUDA_TRY(c, cudaMemcpyAsync(&p.scal[SC_NSLOTS], &p.scal[SC_NALIVE], sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  if (c->agenda_alt) {
+    CUDA_TRY(c, cudaMemcpyAsync(&p.scal[SC_NITEMS], c->d_nitems_new, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    std::swap(p.agenda, c->agenda_alt);
+  }
   for (int k = 0; k < PERM4; ++k) std::swap(c->cur4[k], c->alt4[k]);
   for (int k = 0; k < PERM8; ++k) std::swap(c->cur8[k], c->alt8[k]);
   std::swap(c->db_cur, c->db_alt);
@@ -269,59 +323,84 @@ int reorder_slots(Ctx* c, int64_t tick) {
 
 void mg_reset(Ctx* c) {
   Multi& m = c->mg;
+  for (Neighbor& nb : m.nb)
+    if (nb.mapped && nb.peer_base && m.peers.empty()) cudaIpcCloseMemHandle(nb.peer_base);
   for (void* ptr : m.allocs) cudaFree(ptr);
   if (m.ev_ready) cudaEventDestroy(m.ev_ready);
-  if (m.ev_packed) cudaEventDestroy(m.ev_packed);
-  if (m.ev_arrived) cudaEventDestroy(m.ev_arrived);
-  if (m.comm_stream) cudaStreamDestroy(m.comm_stream);
-  // the NCCL communicator, if any, is left to process exit: destroying it is collective
   m = Multi();
   c->mg_owner_host.clear();
-  c->p.owner = nullptr;
-  c->p.halo_recv = nullptr;
-  c->p.my_rank = 0;
-  for (auto& b : c->p.mig_peer) b[0] = b[1] = nullptr;
-  for (auto& b : c->p.mig_mine) b[0] = b[1] = nullptr;
-  for (auto& n : c->p.mig_cap) n = 0;
-  for (auto& n : c->p.mig_in) n = 0;
-  c->p.mig_done = nullptr;
+  Params& p = c->p;
+  p.owner = nullptr;
+  p.halo_recv[0] = p.halo_recv[1] = nullptr;
+  p.my_rank = 0;
+  for (int r = 0; r < MAX_RANKS; ++r) {
+    for (int q = 0; q < 2; ++q) {
+      p.halo_peer[r][q] = nullptr;
+      p.hflag_peer[r][q] = nullptr;
+      p.hflag_mine[r][q] = nullptr;
+      p.mig_peer[r][q] = nullptr;
+      p.mig_mine[r][q] = nullptr;
+    }
+    p.halo_first[r] = p.halo_n[r] = 0;
+    p.mig_cap[r] = p.mig_icap[r] = p.mig_in[r] = 0;
+  }
+  p.halo_done = p.mig_done = p.mig_count = nullptr;
 }
+
+// What a rank (or the host-only helper griddy_mg_plan) sees of the network: compact arrays over the held
+// items, ids inside them global.  An item that is not held has no known owner (-1), which matches no rank.
+struct NetView {
+  const Tiling* tl;
+  const uint8_t* kind;
+  const int32_t *lane_in, *lane_out, *lane_junction, *owner;
+  int32_t own(int64_t g) const { const int64_t l = g < 0 ? -1 : tl->local(g); return l < 0 ? -1 : owner[l]; }
+  template <typename F>
+  void each(F f) const {   // f(compact index, global id), ascending
+    for (size_t k = 0; k < tl->beg.size(); ++k)
+      for (int64_t g = tl->beg[k]; g < tl->end[k]; ++g) f(tl->off[k] + (g - tl->beg[k]), g);
+  }
+};
 
 // Items of `owner_rank` that actors living on `reader_rank` read before they cross: the lanes they
 // can enter (a junction lane fed by one of the reader's segment lanes; a segment lane that one of
 // the reader's junction lanes leads onto) and the junctions whose occupancy gates the entry.  Both
-// sides derive the same ascending lists from the same global arrays, so no list is ever exchanged.
-void mg_plan(int64_t n_items, const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out,
-             const int32_t* lane_junction, const int32_t* owner, int owner_rank, int reader_rank,
-             std::vector<int32_t>& lanes, std::vector<int32_t>& junctions) {
-  std::vector<uint8_t> mark((size_t)n_items, 0);
-  for (int64_t r = 0; r < n_items; ++r) {
-    if (kind[r] != GRIDDY_JUNCTION_LANE) continue;
-    const int32_t in = lane_in[r], out = lane_out[r];
-    if (owner[r] == owner_rank && in >= 0 && owner[in] == reader_rank) { mark[r] = 1; mark[lane_junction[r]] = 2; }
-    if (owner[r] == reader_rank && out >= 0 && owner[out] == owner_rank) mark[out] = 1;
-  }
+// sides derive the same ascending lists — each from the items it holds, which include everything next to
+// its own part — so no list is ever exchanged.
+void mg_plan(const NetView& v, int owner_rank, int reader_rank, std::vector<int32_t>& lanes, std::vector<int32_t>& junctions) {
+  std::vector<uint8_t> mark((size_t)v.tl->n_local, 0);
+  v.each([&](int64_t l, int64_t) {
+    if (v.kind[l] != GRIDDY_JUNCTION_LANE) return;
+    const int32_t in = v.lane_in[l], out = v.lane_out[l];
+    if (v.owner[l] == owner_rank && v.own(in) == reader_rank) {
+      mark[(size_t)l] = 1;
+      const int64_t j = v.tl->local(v.lane_junction[l]);
+      if (j >= 0) mark[(size_t)j] = 2;
+    }
+    if (v.owner[l] == reader_rank && v.own(out) == owner_rank) mark[(size_t)v.tl->local(out)] = 1;
+  });
   lanes.clear();
   junctions.clear();
-  for (int64_t r = 0; r < n_items; ++r) {
-    if (mark[r] == 1) lanes.push_back((int32_t)r);
-    else if (mark[r] == 2) junctions.push_back((int32_t)r);
-  }
+  v.each([&](int64_t l, int64_t g) {
+    if (mark[(size_t)l] == 1) lanes.push_back((int32_t)g);
+    else if (mark[(size_t)l] == 2) junctions.push_back((int32_t)g);
+  });
 }
 
 // Lanes of `from` with a successor lane on `to`.  A lane lets at most one actor out per tick (the
 // follower of an actor that reaches the end is a tail-gate buffer behind, route.scm:62-74), so this
 // bounds the actors that cross from `from` to `to` in a tick — and sizes the exchange exactly.
-int64_t mg_count_feeders(int64_t n_items, const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out,
-                         const int32_t* owner, int from, int to) {
-  std::vector<uint8_t> mark((size_t)n_items, 0);
+int64_t mg_count_feeders(const NetView& v, int from, int to) {
+  std::vector<uint8_t> mark((size_t)v.tl->n_local, 0);
   int64_t n = 0;
-  for (int64_t r = 0; r < n_items; ++r) {
-    if (kind[r] != GRIDDY_JUNCTION_LANE) continue;
-    const int32_t in = lane_in[r], out = lane_out[r];
-    if (owner[r] == to && in >= 0 && owner[in] == from && !mark[in]) { mark[in] = 1; ++n; }
-    if (owner[r] == from && out >= 0 && owner[out] == to && !mark[r]) { mark[r] = 1; ++n; }
-  }
+  v.each([&](int64_t l, int64_t) {
+    if (v.kind[l] != GRIDDY_JUNCTION_LANE) return;
+    const int32_t in = v.lane_in[l], out = v.lane_out[l];
+    if (v.owner[l] == to && v.own(in) == from) {
+      const int64_t li = v.tl->local(in);
+      if (!mark[(size_t)li]) { mark[(size_t)li] = 1; ++n; }
+    }
+    if (v.owner[l] == from && v.own(out) == to && !mark[(size_t)l]) { mark[(size_t)l] = 1; ++n; }
+  });
   return n;
 }
 
@@ -334,51 +413,142 @@ int mg_alloc(Ctx* c, T** out, size_t count) {
   return GRIDDY_OK;
 }
 
-// ---- NCCL, bound lazily so that the library loads (and single-GPU worlds run) without it ---------
-struct NcclId { char internal[128]; };   // layout of ncclUniqueId (nccl.h)
-struct NcclApi {
-  void* lib = nullptr;
-  int (*GetUniqueId)(void*) = nullptr;
-  int (*CommInitRank)(void**, int, NcclId /* ncclUniqueId by value */, int) = nullptr;
-  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
-  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
-  int (*GroupStart)() = nullptr;
-  int (*GroupEnd)() = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
+// ---- sparse per-item arrays (tiled networks) --------------------------------------------------------
+// CUDA virtual memory management, bound at run time: the library keeps no link-time dependency on libcuda.
+struct VmmApi {
+  CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
 };
 
-NcclApi* nccl_api() {
-  static NcclApi api;
-  if (api.lib) return &api;
-  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-    api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-    if (api.lib) break;
-  }
-  if (!api.lib) return nullptr;
-  auto sym = [&](const char* n) { return dlsym(api.lib, n); };
-  api.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
-  api.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
-  api.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
-  api.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
-  api.GroupStart = (int (*)())sym("ncclGroupStart");
-  api.GroupEnd = (int (*)())sym("ncclGroupEnd");
-  api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
-  if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd) {
-    api.lib = nullptr;
-    return nullptr;
-  }
-  return &api;
+VmmApi* vmm_api() {
+  static VmmApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  auto get = [](const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult q;
+    return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+  };
+  api.ok = get("cuMemAddressReserve", (void**)&api.AddressReserve) && get("cuMemAddressFree", (void**)&api.AddressFree) &&
+           get("cuMemCreate", (void**)&api.Create) && get("cuMemRelease", (void**)&api.Release) &&
+           get("cuMemMap", (void**)&api.Map) && get("cuMemUnmap", (void**)&api.Unmap) &&
+           get("cuMemSetAccess", (void**)&api.SetAccess) && get("cuMemGetAllocationGranularity", (void**)&api.GetGranularity);
+  cudaGetLastError();
+  return api.ok ? &api : nullptr;
 }
-constexpr int NCCL_CHAR = 0;   // ncclInt8 / ncclChar in nccl.h
 
-#define NCCL_TRY(c, expr)                                                                              \
-  do {                                                                                                  \
-    int r_ = (expr);                                                                                    \
-    if (r_ != 0) {                                                                                      \
-      NcclApi* a_ = nccl_api();                                                                         \
-      return fail(c, GRIDDY_ERR_NCCL, std::string(#expr) + ": " + (a_ && a_->GetErrorString ? a_->GetErrorString(r_) : "nccl error")); \
-    }                                                                                                   \
-  } while (0)
+void sparse_free(SparseArray& a) {
+  if (!a.base) return;
+  if (!a.vmm) {
+    cudaFree(a.base);
+  } else if (VmmApi* v = vmm_api()) {
+    for (size_t k = 0; k < a.spans.size(); ++k) {
+      v->Unmap((CUdeviceptr)a.base + a.spans[k].first, a.spans[k].second);
+      v->Release((CUmemGenericAllocationHandle)a.handles[k]);
+    }
+    v->AddressFree((CUdeviceptr)a.base, a.va_bytes);
+  }
+  a = SparseArray();
+}
+
+// Allocate a zero-filled array of `elem`-byte entries indexed by global item id, backed where the context holds items.
+int sparse_alloc(Ctx* c, size_t elem, void** out) {
+  const Tiling& tl = c->tl;
+  SparseArray a;
+  if (!tl.tiled()) {
+    const size_t bytes = std::max<size_t>((size_t)tl.n_global * elem, 16);
+    CUDA_TRY(c, cudaMalloc(&a.base, bytes));
+    CUDA_TRY(c, cudaMemset(a.base, 0, bytes));
+    c->net_sparse.push_back(a);
+    *out = a.base;
+    return GRIDDY_OK;
+  }
+  VmmApi* v = vmm_api();
+  if (!v) return fail(c, GRIDDY_ERR_CUDA, "a tiled network needs CUDA virtual memory management (cuMemCreate / cuMemMap), which this driver does not offer");
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = c->device;
+  size_t gran = 0;
+  if (v->GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
+    return fail(c, GRIDDY_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+  auto up = [&](size_t x) { return (x + gran - 1) / gran * gran; };
+  a.vmm = true;
+  a.va_bytes = up(std::max<size_t>((size_t)tl.n_global * elem, 1));
+  CUdeviceptr base = 0;
+  if (v->AddressReserve(&base, a.va_bytes, gran, 0, 0) != CUDA_SUCCESS)
+    return fail(c, GRIDDY_ERR_OOM, "cuMemAddressReserve failed for " + std::to_string(a.va_bytes) + " bytes of address space");
+  a.base = (void*)base;
+  for (size_t k = 0; k < tl.beg.size(); ++k) {   // granule-aligned spans behind the ranges, merged where they touch
+    if (tl.end[k] == tl.beg[k]) continue;
+    const size_t lo = (size_t)tl.beg[k] * elem / gran * gran, hi = up((size_t)tl.end[k] * elem);
+    if (!a.spans.empty() && lo <= a.spans.back().first + a.spans.back().second)
+      a.spans.back().second = std::max(a.spans.back().second, hi - a.spans.back().first);
+    else
+      a.spans.emplace_back(lo, hi - lo);
+  }
+  CUmemAccessDesc acc = {};
+  acc.location = prop.location;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  for (size_t k = 0; k < a.spans.size(); ++k) {
+    CUmemGenericAllocationHandle h = 0;
+    const CUresult r1 = v->Create(&h, a.spans[k].second, &prop, 0);
+    if (r1 != CUDA_SUCCESS) {
+      a.spans.resize(k);
+      sparse_free(a);
+      return fail(c, GRIDDY_ERR_OOM, "cuMemCreate failed for " + std::to_string(a.spans[k].second) + " bytes");
+    }
+    a.handles.push_back((unsigned long long)h);
+    if (v->Map(base + a.spans[k].first, a.spans[k].second, 0, h, 0) != CUDA_SUCCESS ||
+        v->SetAccess(base + a.spans[k].first, a.spans[k].second, &acc, 1) != CUDA_SUCCESS) {
+      v->Release(h);
+      a.handles.pop_back();
+      a.spans.resize(k);
+      sparse_free(a);
+      return fail(c, GRIDDY_ERR_CUDA, "cuMemMap / cuMemSetAccess failed");
+    }
+    if (cudaMemset((uint8_t*)a.base + a.spans[k].first, 0, a.spans[k].second) != cudaSuccess) {
+      sparse_free(a);
+      return fail(c, GRIDDY_ERR_CUDA, "clearing a mapped span failed");
+    }
+  }
+  c->net_sparse.push_back(a);
+  *out = a.base;
+  return GRIDDY_OK;
+}
+
+void free_sparse(Ctx* c) {
+  for (SparseArray& a : c->net_sparse) sparse_free(a);
+  c->net_sparse.clear();
+}
+
+// Compact host array (held items in range order) -> sparse device array, range by range.
+template <typename T>
+int sparse_upload(Ctx* c, T* dst, const T* host, int per_item = 1) {
+  for (size_t k = 0; k < c->tl.beg.size(); ++k) {
+    const int64_t n = c->tl.end[k] - c->tl.beg[k];
+    if (n > 0)
+      CUDA_TRY(c, cudaMemcpy(dst + c->tl.beg[k] * per_item, host + c->tl.off[k] * per_item, (size_t)n * per_item * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  return GRIDDY_OK;
+}
+
+// Sparse device array -> compact host array.
+template <typename T>
+int sparse_download(Ctx* c, T* host, const T* src, cudaStream_t s) {
+  for (size_t k = 0; k < c->tl.beg.size(); ++k) {
+    const int64_t n = c->tl.end[k] - c->tl.beg[k];
+    if (n > 0) CUDA_TRY(c, cudaMemcpyAsync(host + c->tl.off[k], src + c->tl.beg[k], (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  return GRIDDY_OK;
+}
 
 // Launch one of the tick's kernels behind its predecessor on the stream with programmatic dependent
 // launch (records.cuh, grid_dependency_wait).
@@ -427,8 +597,10 @@ void griddy_destroy(void* ctx) {
   Ctx* c = (Ctx*)ctx;
   if (!c) return;
   cudaSetDevice(c->device);
+  mg_reset(c);
   free_pool(c->net_allocs);
   free_pool(c->actor_allocs);
+  free_sparse(c);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   for (int f = 0; f < 2; ++f) {
@@ -459,6 +631,32 @@ int griddy_set_reorder_period(void* ctx, int32_t ticks) {
   return GRIDDY_OK;
 }
 
+int griddy_set_item_ranges(void* ctx, int64_t n_items_global, int32_t n_ranges, const int64_t* range_beg, const int64_t* range_end) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (n_ranges == 0) {   // back to an untiled network
+    c->have_ranges = false;
+    return GRIDDY_OK;
+  }
+  if (n_items_global < 0 || n_items_global > INT32_MAX - 1 || n_ranges < 0 || n_ranges > MAX_RANGES || !range_beg || !range_end)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "set_item_ranges: bad arguments (at most " + std::to_string(MAX_RANGES) + " ranges)");
+  Tiling t;
+  t.n_global = n_items_global;
+  int64_t prev = 0;
+  for (int k = 0; k < n_ranges; ++k) {
+    if (range_beg[k] < prev || range_end[k] < range_beg[k] || range_end[k] > n_items_global)
+      return fail(c, GRIDDY_ERR_BAD_ARG, "set_item_ranges: ranges must ascend, be disjoint and lie inside [0, n_items_global)");
+    t.beg.push_back(range_beg[k]);
+    t.end.push_back(range_end[k]);
+    t.off.push_back(t.n_local);
+    t.n_local += range_end[k] - range_beg[k];
+    prev = range_end[k];
+  }
+  c->tl_next = t;
+  c->have_ranges = true;
+  return GRIDDY_OK;
+}
+
 int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const double* lane_len,
                           const uint8_t* lane_dir, const int32_t* lane_segment,
                           const int32_t* lane_out, const int32_t* lane_junction,
@@ -468,32 +666,47 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   if (n_items < 0 || n_items > INT32_MAX - 1 || !kind || !lane_len || !lane_dir || !lane_segment || !lane_out ||
       !lane_junction || !seg_outer_forw || !seg_outer_back)
     return fail(c, GRIDDY_ERR_BAD_ARG, "upload_network: null array or bad n_items");
-  auto in_range = [&](int32_t v, int want_kind) { return v >= 0 && v < n_items && kind[v] == want_kind; };
+  Tiling tl;
+  if (c->have_ranges) {
+    tl = c->tl_next;
+    if (tl.n_local != n_items)
+      return fail(c, GRIDDY_ERR_BAD_ARG, "upload_network: n_items must equal the " + std::to_string(tl.n_local) + " items of the ranges set with griddy_set_item_ranges");
+  } else {
+    tl.whole(n_items);
+  }
+  // ids inside the arrays are global; a referenced item that this context does not hold cannot be checked
+  auto ok_ref = [&](int32_t v, int want_kind) {
+    if (v < 0 || v >= tl.n_global) return false;
+    const int64_t l = tl.local(v);
+    return l < 0 || kind[l] == want_kind;
+  };
   for (int64_t r = 0; r < n_items; ++r) {
     const bool lane = kind[r] == GRIDDY_SEGMENT_LANE || kind[r] == GRIDDY_JUNCTION_LANE;
-    if (lane && !(lane_len[r] > 0.0)) return fail(c, GRIDDY_ERR_BAD_ARG, "lane " + std::to_string(r) + " has no positive length");
-    if (kind[r] == GRIDDY_SEGMENT_LANE && !in_range(lane_segment[r], GRIDDY_SEGMENT))
-      return fail(c, GRIDDY_ERR_BAD_ARG, "segment lane " + std::to_string(r) + " has no segment");
+    if (lane && !(lane_len[r] > 0.0)) return fail(c, GRIDDY_ERR_BAD_ARG, "lane (entry " + std::to_string(r) + ") has no positive length");
+    if (kind[r] == GRIDDY_SEGMENT_LANE && !ok_ref(lane_segment[r], GRIDDY_SEGMENT))
+      return fail(c, GRIDDY_ERR_BAD_ARG, "segment lane (entry " + std::to_string(r) + ") has no segment");
     if (kind[r] == GRIDDY_JUNCTION_LANE &&
-        (!in_range(lane_out[r], GRIDDY_SEGMENT_LANE) || !in_range(lane_junction[r], GRIDDY_JUNCTION)))
-      return fail(c, GRIDDY_ERR_BAD_ARG, "junction lane " + std::to_string(r) + " is not linked");
+        (!ok_ref(lane_out[r], GRIDDY_SEGMENT_LANE) || !ok_ref(lane_junction[r], GRIDDY_JUNCTION)))
+      return fail(c, GRIDDY_ERR_BAD_ARG, "junction lane (entry " + std::to_string(r) + ") is not linked");
     if (kind[r] == GRIDDY_SEGMENT)
       for (int32_t o : {seg_outer_forw[r], seg_outer_back[r]})
-        if (o != -1 && !in_range(o, GRIDDY_SEGMENT_LANE))
-          return fail(c, GRIDDY_ERR_BAD_ARG, "segment " + std::to_string(r) + " has a bad outer lane");
+        if (o != -1 && !ok_ref(o, GRIDDY_SEGMENT_LANE))
+          return fail(c, GRIDDY_ERR_BAD_ARG, "segment (entry " + std::to_string(r) + ") has a bad outer lane");
   }
   CUDA_TRY(c, cudaSetDevice(c->device));
   free_pool(c->net_allocs);
   free_pool(c->actor_allocs);
+  free_sparse(c);
   c->have_net = c->have_actors = false;
+  c->tl = tl;
   Params& p = c->p;
-  p.n_items = n_items;
+  p.n_items = tl.n_global;
   p.grid_n = 0;
   p.turn4 = nullptr;
   c->d_geom = nullptr;
-  TRY(dev_alloc(c, c->net_allocs, &p.item, n_items));
-  TRY(dev_alloc(c, c->net_allocs, &p.lane, n_items));
-  TRY(dev_alloc(c, c->net_allocs, &p.occ, n_items));
+  TRY(sparse_alloc(c, sizeof(Item), (void**)&p.item));
+  TRY(sparse_alloc(c, sizeof(LaneDyn), (void**)&p.lane));
+  TRY(sparse_alloc(c, sizeof(int32_t), (void**)&p.occ));
   if (n_items > 0) {   // stage the ABI arrays on the device, assemble the records there
     std::vector<void*> tmp;
     const uint8_t *d_kind, *d_dir;
@@ -508,16 +721,27 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
     if (!rc) rc = dev_upload(c, tmp, &d_of, seg_outer_forw, n_items);
     if (!rc) rc = dev_upload(c, tmp, &d_ob, seg_outer_back, n_items);
     if (!rc) {
-      k_item_build<<<(unsigned)((n_items + 255) / 256), 256>>>(p.item, n_items, d_kind, d_len, d_dir, d_seg, d_out, d_jun, d_of, d_ob);
+      for (size_t k = 0; k < tl.beg.size(); ++k) {
+        const int64_t m = tl.end[k] - tl.beg[k], o = tl.off[k];
+        if (m > 0)
+          k_item_build<<<(unsigned)((m + 255) / 256), 256>>>(p.item + tl.beg[k], m, d_kind + o, d_len + o, d_dir + o, d_seg + o,
+                                                              d_out + o, d_jun + o, d_of + o, d_ob + o, tl.beg[k]);
+      }
       if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_build failed");
     }
     free_pool(tmp);
     if (rc) return rc;
   }
-  c->loc_key_bits = bits_for((uint32_t)std::max<int64_t>(n_items, 1));
+  c->loc_key_bits = bits_for((uint32_t)std::max<int64_t>(tl.n_global, 1));
   c->h_kind.assign(kind, kind + n_items);
+  c->h_dir.assign(lane_dir, lane_dir + n_items);
   c->h_lane_junction.assign(lane_junction, lane_junction + n_items);
   c->h_lane_out.assign(lane_out, lane_out + n_items);
+  c->h_of.assign(seg_outer_forw, seg_outer_forw + n_items);
+  c->h_ob.assign(seg_outer_back, seg_outer_back + n_items);
+  c->h_from.clear();
+  c->h_to.clear();
+  c->have_dst = false;
   mg_reset(c);
   c->have_net = true;
   return GRIDDY_OK;
@@ -528,15 +752,19 @@ int griddy_set_locality_keys(void* ctx, const uint32_t* item_key) {
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (!c->have_net || !item_key) return fail(c, GRIDDY_ERR_BAD_ARG, "set_locality_keys: no network or null keys");
   CUDA_TRY(c, cudaSetDevice(c->device));
+  const Tiling& tl = c->tl;
   uint32_t mx = 0;
-  for (int64_t r = 0; r < c->p.n_items; ++r) mx = std::max(mx, item_key[r]);
+  for (int64_t r = 0; r < tl.n_local; ++r) mx = std::max(mx, item_key[r]);
   if (mx == UINT32_MAX) return fail(c, GRIDDY_ERR_BAD_ARG, "locality keys must be below 2^32-1");
   {
     std::vector<void*> tmp;
     const uint32_t* d_key;
-    int rc = dev_upload(c, tmp, &d_key, item_key, c->p.n_items);
-    if (!rc && c->p.n_items > 0) {
-      k_item_set_key<<<(unsigned)((c->p.n_items + 255) / 256), 256>>>(c->p.item, c->p.n_items, d_key);
+    int rc = dev_upload(c, tmp, &d_key, item_key, tl.n_local);
+    if (!rc) {
+      for (size_t k = 0; k < tl.beg.size(); ++k) {
+        const int64_t m = tl.end[k] - tl.beg[k];
+        if (m > 0) k_item_set_key<<<(unsigned)((m + 255) / 256), 256>>>(c->p.item + tl.beg[k], m, d_key + tl.off[k]);
+      }
       if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_set_key failed");
     }
     free_pool(tmp);
@@ -551,17 +779,19 @@ int griddy_set_routing_grid(void* ctx, int32_t n, const int32_t* lane_from_j, co
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (!c->have_net) return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid before upload_network");
-  if (n < 1 || (int64_t)n * n > c->p.n_items || !lane_from_j || !lane_to_j || !turn4)
+  const Tiling& tl = c->tl;
+  if (n < 1 || (int64_t)n * n > tl.n_global || !lane_from_j || !lane_to_j || !turn4)
     return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid: bad arguments");
   // Every turn of a segment lane must be a junction lane of the junction the lane reaches: the device
   // takes a route head's gating junction from lane_to_j instead of reading the junction lane's record.
-  for (int64_t r = 0; r < c->p.n_items; ++r) {
+  for (int64_t r = 0; r < tl.n_local; ++r) {
     if (c->h_kind[r] != GRIDDY_SEGMENT_LANE) continue;
     for (int h = 0; h < 4; ++h) {
       const int32_t t = turn4[4 * r + h];
       if (t < 0) continue;
-      if (t >= c->p.n_items || c->h_kind[t] != GRIDDY_JUNCTION_LANE || c->h_lane_junction[t] != lane_to_j[r])
-        return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid: turn " + std::to_string(h) + " of lane " + std::to_string(r) +
+      const int64_t lt = t < tl.n_global ? tl.local(t) : -1;
+      if (t >= tl.n_global || (lt >= 0 && (c->h_kind[lt] != GRIDDY_JUNCTION_LANE || c->h_lane_junction[lt] != lane_to_j[r])))
+        return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid: turn " + std::to_string(h) + " of the lane at entry " + std::to_string(r) +
                                                " is not a junction lane of the junction the lane reaches");
     }
   }
@@ -570,17 +800,44 @@ int griddy_set_routing_grid(void* ctx, int32_t n, const int32_t* lane_from_j, co
   {
     std::vector<void*> tmp;
     const int32_t *d_from, *d_to;
-    int rc = dev_upload(c, tmp, &d_from, lane_from_j, p.n_items);
-    if (!rc) rc = dev_upload(c, tmp, &d_to, lane_to_j, p.n_items);
-    if (!rc && p.n_items > 0) {
-      k_item_set_grid<<<(unsigned)((p.n_items + 255) / 256), 256>>>(p.item, p.n_items, d_from, d_to);
+    int rc = dev_upload(c, tmp, &d_from, lane_from_j, tl.n_local);
+    if (!rc) rc = dev_upload(c, tmp, &d_to, lane_to_j, tl.n_local);
+    if (!rc) {
+      for (size_t k = 0; k < tl.beg.size(); ++k) {
+        const int64_t m = tl.end[k] - tl.beg[k];
+        if (m > 0) k_item_set_grid<<<(unsigned)((m + 255) / 256), 256>>>(p.item + tl.beg[k], m, d_from + tl.off[k], d_to + tl.off[k]);
+      }
       if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_set_grid failed");
     }
     free_pool(tmp);
     if (rc) return rc;
   }
-  TRY(dev_upload(c, c->net_allocs, &p.turn4, turn4, 4 * p.n_items));
+  int32_t* d_turn4 = nullptr;
+  TRY(sparse_alloc(c, 4 * sizeof(int32_t), (void**)&d_turn4));
+  TRY(sparse_upload(c, d_turn4, turn4, 4));
+  p.turn4 = d_turn4;
   p.grid_n = n;
+  c->h_from.assign(lane_from_j, lane_from_j + tl.n_local);
+  c->h_to.assign(lane_to_j, lane_to_j + tl.n_local);
+  return GRIDDY_OK;
+}
+
+int griddy_set_agenda_destinations(void* ctx, int64_t n_agenda_items, const int32_t* dest_lane, const uint8_t* dest_dir,
+                                   const int32_t* dest_from_j, const int32_t* dest_to_j) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (n_agenda_items < 0 || (n_agenda_items > 0 && (!dest_lane || !dest_dir)))
+    return fail(c, GRIDDY_ERR_BAD_ARG, "set_agenda_destinations: null array or bad count");
+  c->dst_lane.assign(dest_lane, dest_lane + n_agenda_items);
+  c->dst_dir.assign(dest_dir, dest_dir + n_agenda_items);
+  if (dest_from_j && dest_to_j) {
+    c->dst_from.assign(dest_from_j, dest_from_j + n_agenda_items);
+    c->dst_to.assign(dest_to_j, dest_to_j + n_agenda_items);
+  } else {
+    c->dst_from.assign((size_t)n_agenda_items, -1);
+    c->dst_to.assign((size_t)n_agenda_items, -1);
+  }
+  c->have_dst = true;
   return GRIDDY_OK;
 }
 
@@ -601,21 +858,60 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   if (!route_off && c->p.grid_n == 0)
     return fail(c, GRIDDY_ERR_BAD_ARG, "no routes uploaded and no grid routing table set");
   const Params& q = c->p;
+  const Tiling& tl = c->tl;
   for (int64_t a = 0; a < n; ++a) {
     const int32_t ct = container[a];
-    if (ct < 0 || ct >= q.n_items) return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + ": container out of range");
-    const uint8_t k = c->h_kind[ct];
+    if (ct < 0 || ct >= q.n_items || tl.local(ct) < 0)
+      return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + ": container out of range (or not held by this context)");
+    const uint8_t k = c->kind_of(ct);
     if (loc_kind[a] ? (k != GRIDDY_SEGMENT_LANE && k != GRIDDY_JUNCTION_LANE) : (k != GRIDDY_SEGMENT))
       return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + ": location kind does not match its container");
     if (!(speed[a] > 0.0)) return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + ": max-speed must be positive");
     if (agenda_off[a + 1] < agenda_off[a]) return fail(c, GRIDDY_ERR_BAD_ARG, "agenda_off not monotone");
   }
+  if (c->have_dst && (int64_t)c->dst_lane.size() != n_agenda)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "griddy_set_agenda_destinations was given " + std::to_string(c->dst_lane.size()) +
+                                           " items, the agendas hold " + std::to_string(n_agenda));
+  // Agenda items as the device keeps them: a travel-to carries its destination resolved now —
+  // off-road->on-road (location.scm:49-57): the outer lane of (segment, side) (location.scm:16-24), the
+  // pos-param flipped on a 'back lane, the lane's junctions for the grid routing table.
+  std::vector<AgendaItem> agenda((size_t)n_agenda);
   for (int64_t k = 0; k < n_agenda; ++k) {
-    if (item_kind[k] == GRIDDY_TRAVEL_TO) {
-      const int32_t s = item_seg[k];
-      if (s < 0 || s >= q.n_items || c->h_kind[s] != GRIDDY_SEGMENT)
+    AgendaItem& ai = agenda[(size_t)k];
+    memset(&ai, 0, sizeof(ai));
+    ai.dlane = ai.dfrom = ai.dto = -1;
+    ai.kind = item_kind[k];
+    if (item_kind[k] == GRIDDY_SLEEP_FOR) {
+      ai.sleep = item_sleep[k];
+    } else if (item_kind[k] == GRIDDY_TRAVEL_TO) {
+      const int32_t sg = item_seg[k];
+      if (sg < 0 || sg >= q.n_items) return fail(c, GRIDDY_ERR_BAD_ARG, "agenda item " + std::to_string(k) + ": destination out of range");
+      const int64_t ls = tl.local(sg);
+      if (ls >= 0 && c->h_kind[ls] != GRIDDY_SEGMENT)
         return fail(c, GRIDDY_ERR_BAD_ARG, "agenda item " + std::to_string(k) + ": destination is not a segment");
-    } else if (item_kind[k] != GRIDDY_SLEEP_FOR) {
+      uint8_t dir = 0;
+      if (c->have_dst) {
+        ai.dlane = c->dst_lane[(size_t)k];
+        dir = c->dst_dir[(size_t)k];
+        ai.dfrom = c->dst_from[(size_t)k];
+        ai.dto = c->dst_to[(size_t)k];
+        if (ai.dlane >= q.n_items) return fail(c, GRIDDY_ERR_BAD_ARG, "agenda item " + std::to_string(k) + ": destination lane out of range");
+      } else {
+        if (ls < 0)
+          return fail(c, GRIDDY_ERR_BAD_ARG, "agenda item " + std::to_string(k) + ": its destination segment is not held by this context; "
+                                                 "a tiled network needs griddy_set_agenda_destinations");
+        ai.dlane = item_side[k] ? c->h_ob[ls] : c->h_of[ls];
+        const int64_t ll = ai.dlane >= 0 ? tl.local(ai.dlane) : -1;
+        if (ai.dlane >= 0 && ll < 0)
+          return fail(c, GRIDDY_ERR_BAD_ARG, "agenda item " + std::to_string(k) + ": its destination lane is not held by this context; "
+                                                 "a tiled network needs griddy_set_agenda_destinations");
+        if (ll >= 0) {
+          dir = c->h_dir[ll];
+          if (!c->h_from.empty()) { ai.dfrom = c->h_from[ll]; ai.dto = c->h_to[ll]; }
+        }
+      }
+      ai.dpos = dir ? 1.0 - item_pos[k] : item_pos[k];
+    } else {
       return fail(c, GRIDDY_ERR_BAD_ARG, "agenda item " + std::to_string(k) + ": unknown kind");
     }
   }
@@ -624,7 +920,8 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     if (route_off[n_agenda] > INT32_MAX - 1) return fail(c, GRIDDY_ERR_BAD_ARG, "too many route steps");
     for (int64_t k = 0; k < route_off[n_agenda]; ++k) {
       const int32_t l = route_lane[k];
-      if (l < 0 || l >= q.n_items || (c->h_kind[l] != GRIDDY_SEGMENT_LANE && c->h_kind[l] != GRIDDY_JUNCTION_LANE))
+      const uint8_t kd = (l >= 0 && l < q.n_items) ? c->kind_of(l) : (uint8_t)254;
+      if (kd != 255 && kd != GRIDDY_SEGMENT_LANE && kd != GRIDDY_JUNCTION_LANE)
         return fail(c, GRIDDY_ERR_BAD_ARG, "route step " + std::to_string(k) + " is not a lane");
     }
   }
@@ -639,11 +936,12 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   p.n_actors = n;
   const int64_t extra = c->mg.on ? c->mg.extra_slots : 0;   // room for actors arriving from other ranks
   if (c->mg.on && route_off) return fail(c, GRIDDY_ERR_BAD_ARG, "multi-GPU worlds need the grid routing table, not uploaded routes");
-  if (n + extra > INT32_MAX - 2 * rsort::TILE || n_agenda + extra * MIG_ITEMS > INT32_MAX - 1)
+  const int64_t extra_items = extra * std::max(c->mg.max_agenda_items, 1);
+  if (n + extra > INT32_MAX - 2 * rsort::TILE || n_agenda + extra_items > INT32_MAX - 1)
     return fail(c, GRIDDY_ERR_BAD_ARG, "too many slots");
   const int64_t cap = (n + extra + rsort::TILE - 1) / rsort::TILE * rsort::TILE + rsort::TILE;   // tile-padded
   p.cap = (int32_t)cap;
-  p.icap = (int32_t)(n_agenda + extra * MIG_ITEMS);
+  p.icap = (int32_t)(n_agenda + extra_items);
   auto& pool = c->actor_allocs;
 
   // Initial world: link! every actor in id order (core.scm:169-178).  Slot = id until the first reorder.
@@ -651,7 +949,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   std::vector<int32_t> aux(n, 0);
   std::vector<Cold> cold(n);
   std::vector<ColdF> coldf(n);
-  std::vector<int32_t> occ(p.n_items, 0);
+  std::vector<int32_t> occ((size_t)tl.n_local, 0);   // compact, like every host copy of a per-item array
   std::vector<int32_t> tail_lane, tail_slot;   // the few lanes that start with actors on them, and remote-lane marks
   std::vector<int32_t> on_road;
   for (int64_t a = 0; a < n; ++a) {
@@ -692,7 +990,12 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     if (replaced) { sa[a].st &= ~ST_ALIVE; continue; }
     const int32_t lane = container[a];
     if (prev >= 0 && container[prev] == lane) { sa[prev].ahead = a; cold[a].behind = prev; } else { tail_lane.push_back(lane); tail_slot.push_back(a); }
-    if (c->h_kind[lane] == GRIDDY_JUNCTION_LANE) ++occ[c->h_lane_junction[lane]];
+    const int64_t ll = tl.local(lane);
+    if (c->h_kind[ll] == GRIDDY_JUNCTION_LANE) {
+      const int64_t lj = tl.local(c->h_lane_junction[ll]);
+      if (lj < 0) return fail(c, GRIDDY_ERR_BAD_ARG, "an actor stands on a junction lane whose junction this context does not hold");
+      ++occ[(size_t)lj];
+    }
     prev = a;
   }
 
@@ -762,17 +1065,14 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   TRY(dev_alloc(c, pool, &c->d_pack, 32 * cap));   // by handle, or by slot for griddy_download_local
   CUDA_TRY(c, cudaMemset(c->d_pack, 0, (size_t)(32 * cap)));
 
-  {   // agenda items; room at the end for the items of actors that arrive from other ranks
-    auto up = [&](auto** dst, const auto* src, int64_t count, int64_t capacity) -> int {
-      TRY(dev_alloc(c, pool, dst, capacity));
-      if (count > 0) CUDA_TRY(c, cudaMemcpy(*dst, src, (size_t)count * sizeof(**dst), cudaMemcpyHostToDevice));
-      return GRIDDY_OK;
-    };
-    TRY(up(&p.item_kind, item_kind, n_agenda, p.icap));
-    TRY(up(&p.item_sleep, item_sleep, n_agenda, p.icap));
-    TRY(up(&p.item_seg, item_seg, n_agenda, p.icap));
-    TRY(up(&p.item_side, item_side, n_agenda, p.icap));
-    TRY(up(&p.item_pos, item_pos, n_agenda, p.icap));
+  // agenda items; room at the end for the items of actors that arrive from other ranks
+  TRY(dev_alloc(c, pool, &p.agenda, p.icap));
+  if (n_agenda > 0) CUDA_TRY(c, cudaMemcpy(p.agenda, agenda.data(), (size_t)n_agenda * sizeof(AgendaItem), cudaMemcpyHostToDevice));
+  c->agenda_alt = nullptr;
+  c->d_nitems_new = nullptr;
+  if (c->mg.on) {   // a reorder compacts the pool into a second one (arrivals keep appending their items)
+    TRY(dev_alloc(c, pool, &c->agenda_alt, p.icap));
+    TRY(dev_alloc(c, pool, &c->d_nitems_new, 1));
   }
   if (route_off) {
     TRY(dev_upload(c, pool, &p.route_off, route_off, n_agenda + 1));
@@ -785,9 +1085,12 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   for (const auto& m : c->mg.import_marks) { tail_lane.push_back(m.first); tail_slot.push_back(m.second); }   // lanes other ranks own
   if (c->mg.on)
     for (int64_t a = 0; a < n; ++a)
-      if (c->mg_owner_host[container[a]] != c->mg.rank)
+      if (c->owner_of(container[a]) != c->mg.rank)
         return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + " is not on this rank's part of the world");
-  if (p.n_items > 0) k_lane_init<<<(unsigned)((p.n_items + 255) / 256), 256>>>(p.lane, p.item, p.n_items);
+  for (size_t k = 0; k < tl.beg.size(); ++k) {
+    const int64_t m = tl.end[k] - tl.beg[k];
+    if (m > 0) k_lane_init<<<(unsigned)((m + 255) / 256), 256>>>(p.lane + tl.beg[k], p.item + tl.beg[k], m);
+  }
   if (!tail_lane.empty()) {
     std::vector<void*> tmp;
     const int32_t *d_which, *d_tail;
@@ -798,11 +1101,14 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     free_pool(tmp);
     if (rc) return rc;
   }
-  CUDA_TRY(c, cudaMemcpy(p.occ, occ.data(), (size_t)p.n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
-  // a partitioned world starts over: no records, no flags (they count ticks) in my receive buffers
-  for (Neighbor& nb : c->mg.nb)
-    for (int par = 0; par < 2; ++par) CUDA_TRY(c, cudaMemset(nb.d_mig_recv[par], 0, MIG_HEADER));
-  if (c->mg.on) CUDA_TRY(c, cudaMemset(c->p.mig_done, 0, sizeof(int32_t)));
+  TRY(sparse_upload(c, p.occ, occ.data()));
+  // a partitioned world starts over: no records, no flags (they count ticks) in my window
+  if (c->mg.on) {
+    CUDA_TRY(c, cudaMemset(c->mg.window, 0, c->mg.window_bytes));
+    CUDA_TRY(c, cudaMemset(c->p.mig_done, 0, sizeof(int32_t)));
+    CUDA_TRY(c, cudaMemset(c->p.halo_done, 0, sizeof(int32_t)));
+    CUDA_TRY(c, cudaMemset(c->p.mig_count, 0, 2 * MAX_RANKS * sizeof(int32_t)));
+  }
   c->tick = 0;
   c->ns_host = (int32_t)n;
   c->last_reorder_tick = -1;
@@ -886,21 +1192,29 @@ int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // on a partitioned wor
   return GRIDDY_OK;
 }
 
-// ---- the four small kernels of a partitioned world, on stream s -------------------------------------
-// None of them touches what the compute kernel running beside it writes (see launch_tick), so the NCCL
-// transport keeps them off the compute stream altogether.
+// ---- the small kernels of a partitioned world ----------------------------------------------------------
+// All of them run on the compute stream, in this order per tick:
+//   k_halo_pack      (before k_advance: the halo travels over NVLink while k_advance streams the actors; it
+//                     reads the OLD world only, which k_advance does not write)
+//   k_advance
+//   k_halo_unpack    waits for the neighbours' halo flags; k_slow behind it may read the halo
+//   k_slow
+//   k_unlink         its first blocks write the emigrants into the neighbours' windows and raise the flags
+//   k_immig_unpack   waits for the neighbours' migrant flags
+//   k_link
 int mg_halo_pack(Ctx* c, int64_t tick, cudaStream_t s) {
-  if (!c->mg.n_exp) return GRIDDY_OK;
-  CUDA_TRY(c, launch_dependent(k_halo_pack, (unsigned)((c->mg.n_exp + 127) / 128), 128u, s, c->p, (int)(tick & 1),
-                               (const int32_t*)c->mg.d_exp_items, c->mg.n_exp, c->mg.d_halo_send, (int)tick));
+  if (c->mg.nb.empty()) return GRIDDY_OK;
+  const unsigned blocks = (unsigned)std::max(1, (c->mg.n_exp + 127) / 128);   // at least one: it raises the flags
+  CUDA_TRY(c, launch_dependent(k_halo_pack, blocks, 128u, s, c->p, (const int32_t*)c->mg.d_exp_items, c->mg.n_exp, (int)tick));
   ++c->launches;
   return GRIDDY_OK;
 }
 
 int mg_halo_unpack(Ctx* c, int64_t tick, cudaStream_t s) {
-  if (!c->mg.n_imp_junc) return GRIDDY_OK;
-  CUDA_TRY(c, launch_dependent(k_halo_unpack, (unsigned)((c->mg.n_imp_junc + 127) / 128), 128u, s, c->p,
-                               (const int32_t*)c->mg.d_imp_junc, (const int32_t*)c->mg.d_imp_where, c->mg.n_imp_junc, (int)tick));
+  if (c->mg.nb.empty()) return GRIDDY_OK;
+  const unsigned blocks = (unsigned)std::max(1, (c->mg.n_imp_junc + 127) / 128);   // at least one: it waits for the flags
+  CUDA_TRY(c, launch_dependent(k_halo_unpack, blocks, 128u, s, c->p, (const int32_t*)c->mg.d_imp_junc,
+                               (const int32_t*)c->mg.d_imp_where, c->mg.n_imp_junc, (int)tick));
   ++c->launches;
   return GRIDDY_OK;
 }
@@ -927,46 +1241,6 @@ int mg_immig_unpack(Ctx* c, int64_t tick, cudaStream_t s) {
   return GRIDDY_OK;
 }
 
-// ---- NCCL transport ------------------------------------------------------------------------------------
-// The halo travels on the communication stream (high priority) beside k_advance:
-//   k_halo_pack -> halo send/recv -> k_halo_unpack.  k_advance writes pos[new], aux and the slow list, reads
-//       occupancy only of junctions this rank owns, and defers actors gated by a remote junction to k_slow.
-// The migrants need no message and no second stream: the first blocks of k_unlink write the records into the
-// receivers' memory and raise a flag there (the other blocks edit the lists of lanes that lost an actor and
-// the st word of the slots they settle; the packing blocks rebuild the three bits that may clear);
-// k_immig_unpack, next on the compute stream, waits for the neighbours' flags.  A receive buffer is written
-// again two ticks later; the halo exchange of the tick in between (the sender receives it after the
-// receiver's k_link has emptied the buffer) orders that.
-// The compute stream carries the same four kernels as on a single GPU plus two waits.
-int comm_fork(Ctx* c) {   // the communication stream continues from what the compute stream has enqueued so far
-  CUDA_TRY(c, cudaEventRecord(c->mg.ev_packed, c->stream));
-  CUDA_TRY(c, cudaStreamWaitEvent(c->mg.comm_stream, c->mg.ev_packed, 0));
-  return GRIDDY_OK;
-}
-
-int comm_join(Ctx* c) {   // the compute stream continues once the communication stream is done
-  CUDA_TRY(c, cudaEventRecord(c->mg.ev_arrived, c->mg.comm_stream));
-  CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->mg.ev_arrived, 0));
-  return GRIDDY_OK;
-}
-
-// The halo: one grouped send/recv with every neighbour on the communication stream.
-int exchange_nccl(Ctx* c) {
-  NcclApi* api = nccl_api();
-  if (!api || !c->mg.nccl_comm) return fail(c, GRIDDY_ERR_NCCL, "multi-GPU context is not connected (griddy_mg_connect_nccl)");
-  cudaStream_t s = c->mg.comm_stream;
-  NCCL_TRY(c, api->GroupStart());
-  for (Neighbor& nb : c->mg.nb) {
-    if (!nb.peer_mig[0]) return fail(c, GRIDDY_ERR_BAD_STATE, "migrant buffers of rank " + std::to_string(nb.rank) + " are not mapped (griddy_mg_ipc_import)");
-    const size_t out = (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double);
-    const size_t in = (size_t)(nb.n_imp_lanes + nb.n_imp_junc) * sizeof(double);
-    if (out) NCCL_TRY(c, api->Send(nb.d_halo_send, out, NCCL_CHAR, nb.rank, c->mg.nccl_comm, s));
-    if (in) NCCL_TRY(c, api->Recv(nb.d_halo_recv, in, NCCL_CHAR, nb.rank, c->mg.nccl_comm, s));
-  }
-  NCCL_TRY(c, api->GroupEnd());
-  return GRIDDY_OK;
-}
-
 int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   TRY(tick_begin(c, tick, ev));
   if (!c->mg.on) {
@@ -975,22 +1249,20 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
     TRY(tick_unlink(c, tick, ev));
     return tick_link(c, tick, ev);
   }
-  cudaStream_t comm = c->mg.comm_stream;
-  TRY(comm_fork(c));
-  TRY(mg_halo_pack(c, tick, comm));
-  TRY(exchange_nccl(c));
-  TRY(mg_halo_unpack(c, tick, comm));
-  TRY(tick_advance(c, tick, ev));       // while the halo travels
-  TRY(comm_join(c));
+  TRY(mg_halo_pack(c, tick, c->stream));
+  TRY(tick_advance(c, tick, ev));                 // while the halo travels
+  TRY(mg_halo_unpack(c, tick, c->stream));        // waits for the neighbours' halo flags
   TRY(tick_slow(c, tick, ev));
   TRY(tick_unlink(c, tick, ev));                  // its first blocks send the emigrants
-  TRY(mg_immig_unpack(c, tick, c->stream));       // waits for the neighbours' flags
+  TRY(mg_immig_unpack(c, tick, c->stream));       // waits for the neighbours' migrant flags
   return tick_link(c, tick, ev);
 }
 
 // ---- local transport: every rank is a context of this process (tests) -------------------------------
-// Everything runs on each context's own stream; `src` has recorded ev_ready after writing its send
-// buffers, each neighbour copies what is addressed to it on its own stream.
+// The same kernels and the same windows; what differs is only that the ranks' streams are ordered with
+// events (a rank's waiting kernel is enqueued behind the event its neighbour recorded after the writing
+// kernel), so that the flags are always up when a waiting kernel starts — several ranks may share one GPU,
+// where a spinning kernel could otherwise keep the writer from running.
 int local_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   TRY(tick_begin(c, tick, ev));
   return mg_halo_pack(c, tick, c->stream);
@@ -1006,19 +1278,11 @@ int local_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   return tick_link(c, tick, ev);
 }
 
-int exchange_local(Ctx* src, bool halo) {
+int wait_for_neighbours(Ctx* src) {   // every neighbour's stream waits for what src has enqueued so far
   for (Neighbor& nb : src->mg.nb) {
     Ctx* dst = src->mg.peers[nb.rank];
-    Neighbor* back = nullptr;
-    for (Neighbor& b : dst->mg.nb)
-      if (b.rank == src->mg.rank) back = &b;
-    if (!back) return fail(src, GRIDDY_ERR_BAD_STATE, "neighbour lists are not symmetric");
-    if (nb.n_exp_lanes + nb.n_exp_junc != back->n_imp_lanes + back->n_imp_junc || nb.mig_out != back->mig_in)
-      return fail(src, GRIDDY_ERR_BAD_STATE, "exchange plans of two neighbours disagree");
     CUDA_TRY(dst, cudaSetDevice(dst->device));
-    CUDA_TRY(dst, cudaStreamWaitEvent(dst->stream, src->mg.ev_ready, 0));   // migrants: src's kernel wrote them in place
-    const size_t bytes = (size_t)(nb.n_exp_lanes + nb.n_exp_junc) * sizeof(double);
-    if (halo && bytes) CUDA_TRY(dst, cudaMemcpyPeerAsync(back->d_halo_recv, dst->device, nb.d_halo_send, src->device, bytes, dst->stream));
+    CUDA_TRY(dst, cudaStreamWaitEvent(dst->stream, src->mg.ev_ready, 0));
   }
   return GRIDDY_OK;
 }
@@ -1030,8 +1294,9 @@ int griddy_step(void* ctx, int64_t n_ticks) {
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, "step before upload_actors");
   if (n_ticks < 0 || c->tick + n_ticks > INT32_MAX - 2) return fail(c, GRIDDY_ERR_BAD_ARG, "bad n_ticks");
-  if (c->mg.on && !c->mg.nccl_comm)
-    return fail(c, GRIDDY_ERR_BAD_ARG, "a partitioned world steps with griddy_mg_step_local, or after griddy_mg_connect_nccl");
+  if (c->mg.on && (!c->mg.connected || !c->mg.peers.empty()))
+    return fail(c, GRIDDY_ERR_BAD_ARG, "a partitioned world steps with griddy_mg_step_local, or — one process per GPU — with griddy_step "
+                                       "once every neighbour's window is mapped (griddy_mg_ipc_import)");
   CUDA_TRY(c, cudaSetDevice(c->device));
   CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
   if (c->ns_host > 0 || c->mg.on)
@@ -1065,12 +1330,12 @@ int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks) {
     return GRIDDY_OK;
   };
   for (int64_t t = 0; t < n_ticks; ++t) {
-    TRY(each(local_begin, t, true));
-    for (Ctx* c : cs) TRY(exchange_local(c, true));
+    TRY(each(local_begin, t, true));                       // (k_halo_pack writes the neighbours' windows)
     TRY(each(tick_advance, t, false));
+    for (Ctx* c : cs) TRY(wait_for_neighbours(c));
     TRY(each(local_slow, t, false));
     TRY(each(tick_unlink, t, true));                       // (its first blocks write the emigrants)
-    for (Ctx* c : cs) TRY(exchange_local(c, false));
+    for (Ctx* c : cs) TRY(wait_for_neighbours(c));
     TRY(each(local_link, t, false));
   }
   int rc = GRIDDY_OK;
@@ -1259,21 +1524,25 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
   CUDA_TRY(c, cudaSetDevice(c->device));
   const Params& p = c->p;
   const int32_t ns = c->ns_host;
-  const int64_t n_items = p.n_items;
-  if (n_items == 0 || (!lane_count && !junction_count)) return GRIDDY_OK;
+  if (c->tl.n_local == 0 || (!lane_count && !junction_count)) return GRIDDY_OK;
   // counted on the device: one atomic per living actor; the junction counters are the device's own
-  // incrementally maintained ones (route.scm:98-104), less the ghosts (file header)
-  std::vector<void*> tmp;
+  // incrementally maintained ones (route.scm:98-104), less the ghosts (file header).  The scratch arrays
+  // are indexed by global id like every per-item array; the outputs are compact (the held items in range order).
+  const size_t before = c->net_sparse.size();
   int32_t *d_lane = nullptr, *d_junc = nullptr;
-  int rc = GRIDDY_OK;
-  if (lane_count) rc = dev_alloc(c, tmp, &d_lane, n_items);
-  if (!rc && junction_count) rc = dev_alloc(c, tmp, &d_junc, n_items);
-  auto done = [&](int r) { free_pool(tmp); return r; };
-  if (rc) return done(rc);
+  auto done = [&](int r) {
+    while (c->net_sparse.size() > before) { sparse_free(c->net_sparse.back()); c->net_sparse.pop_back(); }
+    return r;
+  };
+  if (lane_count) { const int rc = sparse_alloc(c, sizeof(int32_t), (void**)&d_lane); if (rc) return done(rc); }
+  if (junction_count) { const int rc = sparse_alloc(c, sizeof(int32_t), (void**)&d_junc); if (rc) return done(rc); }
   cudaStream_t s = c->stream;
-  if (d_lane && cudaMemsetAsync(d_lane, 0, (size_t)n_items * sizeof(int32_t), s) != cudaSuccess) return done(fail(c, GRIDDY_ERR_CUDA, "memset failed"));
-  if (d_junc && cudaMemcpyAsync(d_junc, p.occ, (size_t)n_items * sizeof(int32_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
-    return done(fail(c, GRIDDY_ERR_CUDA, "copy of the junction counters failed"));
+  if (d_junc)
+    for (size_t k = 0; k < c->tl.beg.size(); ++k) {
+      const int64_t m = c->tl.end[k] - c->tl.beg[k];
+      if (m > 0 && cudaMemcpyAsync(d_junc + c->tl.beg[k], p.occ + c->tl.beg[k], (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        return done(fail(c, GRIDDY_ERR_CUDA, "copy of the junction counters failed"));
+    }
   if (ns > 0) {
     const unsigned blocks = (unsigned)((ns + 255) / 256);
     cudaMemsetAsync(c->d_ghost, 0, (size_t)ns, s);
@@ -1281,8 +1550,8 @@ int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_
     k_occupancy<<<blocks, 256, 0, s>>>(p, c->d_ghost, d_lane, d_junc);
     c->launches += 2;
   }
-  if (d_lane) cudaMemcpyAsync(lane_count, d_lane, (size_t)n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-  if (d_junc) cudaMemcpyAsync(junction_count, d_junc, (size_t)n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+  if (d_lane) { const int rc = sparse_download(c, lane_count, (const int32_t*)d_lane, s); if (rc) return done(rc); }
+  if (d_junc) { const int rc = sparse_download(c, junction_count, (const int32_t*)d_junc, s); if (rc) return done(rc); }
   const cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return done(fail(c, GRIDDY_ERR_CUDA, std::string("download_occupancy: ") + cudaGetErrorString(e)));
   return done(GRIDDY_OK);
@@ -1294,8 +1563,11 @@ int griddy_mg_plan(int64_t n_items, const uint8_t* kind, const int32_t* lane_in,
                    int32_t* lanes, int64_t* n_lanes, int32_t* junctions, int64_t* n_junctions) {
   if (n_items < 0 || !kind || !lane_in || !lane_out || !lane_junction || !owner || !n_lanes || !n_junctions)
     return GRIDDY_ERR_BAD_ARG;
+  Tiling tl;
+  tl.whole(n_items);
+  const NetView v{&tl, kind, lane_in, lane_out, lane_junction, owner};
   std::vector<int32_t> l, j;
-  mg_plan(n_items, kind, lane_in, lane_out, lane_junction, owner, owner_rank, reader_rank, l, j);
+  mg_plan(v, owner_rank, reader_rank, l, j);
   if (lanes) std::copy(l.begin(), l.end(), lanes);
   if (junctions) std::copy(j.begin(), j.end(), junctions);
   *n_lanes = (int64_t)l.size();
@@ -1303,24 +1575,53 @@ int griddy_mg_plan(int64_t n_items, const uint8_t* kind, const int32_t* lane_in,
   return GRIDDY_OK;
 }
 
+int griddy_mg_plan_tile(int64_t n_items_global, int32_t n_ranges, const int64_t* range_beg, const int64_t* range_end,
+                        const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out, const int32_t* lane_junction,
+                        const int32_t* owner, int32_t owner_rank, int32_t reader_rank, int32_t* lanes, int64_t* n_lanes,
+                        int32_t* junctions, int64_t* n_junctions, int64_t* n_feeders) {
+  if (n_items_global < 0 || n_ranges < 1 || !range_beg || !range_end || !kind || !lane_in || !lane_out || !lane_junction ||
+      !owner || !n_lanes || !n_junctions)
+    return GRIDDY_ERR_BAD_ARG;
+  Tiling tl;
+  tl.n_global = n_items_global;
+  for (int k = 0; k < n_ranges; ++k) {
+    if (range_end[k] < range_beg[k] || (k > 0 && range_beg[k] < range_end[k - 1]) || range_end[k] > n_items_global) return GRIDDY_ERR_BAD_ARG;
+    tl.beg.push_back(range_beg[k]);
+    tl.end.push_back(range_end[k]);
+    tl.off.push_back(tl.n_local);
+    tl.n_local += range_end[k] - range_beg[k];
+  }
+  const NetView v{&tl, kind, lane_in, lane_out, lane_junction, owner};
+  std::vector<int32_t> l, j;
+  mg_plan(v, owner_rank, reader_rank, l, j);
+  if (lanes) std::copy(l.begin(), l.end(), lanes);
+  if (junctions) std::copy(j.begin(), j.end(), junctions);
+  *n_lanes = (int64_t)l.size();
+  *n_junctions = (int64_t)j.size();
+  if (n_feeders) *n_feeders = mg_count_feeders(v, owner_rank, reader_rank);
+  return GRIDDY_OK;
+}
+
 int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* owner, const int32_t* lane_in,
-                        int32_t mig_cap, int64_t extra_slots) {
+                        int32_t mig_cap, int64_t extra_slots, int32_t max_agenda_items) {
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (!c->have_net) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure before upload_network");
-  if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || !owner || !lane_in || mig_cap < 1 || extra_slots < 0)
+  if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || !owner || !lane_in || mig_cap < 1 || extra_slots < 0 || max_agenda_items < 0)
     return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure: bad arguments");
   if (c->p.grid_n == 0) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure needs the grid routing table (griddy_set_routing_grid)");
   CUDA_TRY(c, cudaSetDevice(c->device));
-  const Params& q = c->p;
-  const int64_t n_items = q.n_items;
-  for (int64_t r = 0; r < n_items; ++r) {
+  const Tiling& tl = c->tl;
+  const int64_t n_local = tl.n_local;
+  for (int64_t r = 0; r < n_local; ++r) {
     if (owner[r] < 0 || owner[r] >= world) return fail(c, GRIDDY_ERR_BAD_ARG, "owner out of range");
-    const uint8_t k = c->h_kind[r];
     // a segment and its lanes share an owner, a junction and its lanes too: actors go on and off the
     // road, and junction occupancy is counted, without leaving the rank
-    if (k == GRIDDY_JUNCTION_LANE && owner[r] != owner[c->h_lane_junction[r]])
-      return fail(c, GRIDDY_ERR_BAD_ARG, "junction lane " + std::to_string(r) + " and its junction have different owners");
+    if (c->h_kind[r] == GRIDDY_JUNCTION_LANE) {
+      const int64_t lj = tl.local(c->h_lane_junction[r]);
+      if (lj >= 0 ? owner[r] != owner[lj] : owner[r] == rank)
+        return fail(c, GRIDDY_ERR_BAD_ARG, "junction lane (entry " + std::to_string(r) + ") and its junction have different owners, or the junction is not held");
+    }
   }
   free_pool(c->actor_allocs);
   c->have_actors = false;
@@ -1330,69 +1631,86 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
   m.rank = rank;
   m.world = world;
   m.mig_cap = mig_cap;
+  m.max_agenda_items = std::max(max_agenda_items, 1);
   m.extra_slots = extra_slots;
-  c->mg_owner_host.assign(owner, owner + n_items);
-  TRY(mg_alloc(c, &m.d_owner, (size_t)n_items));
-  CUDA_TRY(c, cudaMemcpy(m.d_owner, owner, (size_t)n_items * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
-  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_packed, cudaEventDisableTiming));
-  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_arrived, cudaEventDisableTiming));
-  {   // the small kernels and the exchanges must not queue behind the compute stream's blocks
-    int least = 0, greatest = 0;
-    CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    CUDA_TRY(c, cudaStreamCreateWithPriority(&m.comm_stream, cudaStreamNonBlocking, greatest));
+  c->mg_owner_host.assign(owner, owner + n_local);
+  {   // owner, by global id like every per-item device array (left in net_sparse: it lives as long as the network)
+    int32_t* d_owner = nullptr;
+    TRY(sparse_alloc(c, sizeof(int32_t), (void**)&d_owner));
+    TRY(sparse_upload(c, d_owner, owner));
+    m.d_owner = d_owner;
   }
+  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
+  const NetView v{&tl, c->h_kind.data(), lane_in, c->h_lane_out.data(), c->h_lane_junction.data(), owner};
   // what I export to / import from every other rank
   struct Lists { std::vector<int32_t> exp_l, exp_j, imp_l, imp_j; };
   std::vector<Lists> lists(world);
-  size_t halo_in = 0;
+  std::vector<int32_t> exp_all, imp_junc_all, imp_where_all;
+  size_t off = 0;   // index into halo_recv (values)
   for (int r = 0; r < world; ++r) {
     if (r == rank) continue;
     Lists& L = lists[r];
-    mg_plan(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), c->h_lane_junction.data(), owner, rank, r, L.exp_l, L.exp_j);
-    mg_plan(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), c->h_lane_junction.data(), owner, r, rank, L.imp_l, L.imp_j);
+    mg_plan(v, rank, r, L.exp_l, L.exp_j);
+    mg_plan(v, r, rank, L.imp_l, L.imp_j);
     if (L.exp_l.empty() && L.exp_j.empty() && L.imp_l.empty() && L.imp_j.empty()) continue;
-    halo_in += L.imp_l.size() + L.imp_j.size();
-  }
-  TRY(mg_alloc(c, &m.d_halo_recv, halo_in));
-  size_t halo_out = 0;
-  for (int r = 0; r < world; ++r)
-    if (r != rank) halo_out += lists[r].exp_l.size() + lists[r].exp_j.size();
-  TRY(mg_alloc(c, &m.d_halo_send, halo_out));
-  std::vector<int32_t> exp_all, imp_junc_all, imp_where_all;
-  size_t off = 0;
-  for (int r = 0; r < world; ++r) {
-    Lists& L = lists[r];
-    if (r == rank || (L.exp_l.empty() && L.exp_j.empty() && L.imp_l.empty() && L.imp_j.empty())) continue;
     Neighbor nb;
     nb.rank = r;
     nb.n_exp_lanes = (int)L.exp_l.size();
     nb.n_exp_junc = (int)L.exp_j.size();
     nb.n_imp_lanes = (int)L.imp_l.size();
     nb.n_imp_junc = (int)L.imp_j.size();
-    nb.d_halo_send = m.d_halo_send + exp_all.size();
+    nb.exp_first = (int)exp_all.size();
     exp_all.insert(exp_all.end(), L.exp_l.begin(), L.exp_l.end());
     for (int32_t j : L.exp_j) exp_all.push_back(~j);
-    nb.d_halo_recv = m.d_halo_recv + off;
+    nb.halo_off[0] = off;   // in values for now; bytes below
     for (size_t k = 0; k < L.imp_l.size(); ++k) m.import_marks.emplace_back(L.imp_l[k], (int32_t)(-2 - (int64_t)(off + k)));
     for (size_t k = 0; k < L.imp_j.size(); ++k) {
       imp_junc_all.push_back(L.imp_j[k]);
       imp_where_all.push_back((int32_t)(off + L.imp_l.size() + k));
     }
     off += L.imp_l.size() + L.imp_j.size();
-    nb.mig_out = (int)std::min<int64_t>(mig_cap, mg_count_feeders(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), owner, rank, r));
-    nb.mig_in = (int)std::min<int64_t>(mig_cap, mg_count_feeders(n_items, c->h_kind.data(), lane_in, c->h_lane_out.data(), owner, r, rank));
-    for (int par = 0; par < 2; ++par) {   // plain cudaMalloc: these are shared with the neighbour through cudaIpc
-      TRY(mg_alloc(c, &nb.d_mig_recv[par], nb.in_bytes()));
-      CUDA_TRY(c, cudaMemset(nb.d_mig_recv[par], 0, nb.in_bytes()));
-      c->p.mig_mine[r][par] = (int32_t*)nb.d_mig_recv[par];
-    }
-    c->p.mig_cap[r] = nb.mig_out;
-    c->p.mig_in[r] = nb.mig_in;
+    nb.mig_out = (int)std::min<int64_t>(mig_cap, mg_count_feeders(v, rank, r));
+    nb.mig_in = (int)std::min<int64_t>(mig_cap, mg_count_feeders(v, r, rank));
+    nb.item_out = (int64_t)nb.mig_out * m.max_agenda_items;
+    nb.item_in = (int64_t)nb.mig_in * m.max_agenda_items;
     m.nb.push_back(nb);
   }
-  TRY(mg_alloc(c, &c->p.mig_done, 1));
-  CUDA_TRY(c, cudaMemset(c->p.mig_done, 0, sizeof(int32_t)));
+  // my window: [halo values, parity 0][halo values, parity 1][per neighbour: halo flag x 2 (64 bytes each)]
+  //            [per neighbour and parity: MigHeader, records, items]
+  auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t halo_bytes = align(off * sizeof(double));
+  size_t w = 0;
+  m.halo_base[0] = w; w += halo_bytes;
+  m.halo_base[1] = w; w += halo_bytes;
+  for (Neighbor& nb : m.nb) {
+    const size_t first = nb.halo_off[0];   // value index
+    for (int q = 0; q < 2; ++q) nb.halo_off[q] = m.halo_base[q] + first * sizeof(double);
+    for (int q = 0; q < 2; ++q) { nb.hflag_off[q] = w; w += 64; }
+  }
+  for (Neighbor& nb : m.nb)
+    for (int q = 0; q < 2; ++q) { nb.mig_off[q] = w; w += align(nb.mig_bytes_in()); }
+  m.window_bytes = std::max<size_t>(w, 256);
+  TRY(mg_alloc(c, &m.window, m.window_bytes));   // plain cudaMalloc: shared with the neighbours through cudaIpc
+  CUDA_TRY(c, cudaMemset(m.window, 0, m.window_bytes));
+  Params& p = c->p;
+  for (int q = 0; q < 2; ++q) p.halo_recv[q] = (const double*)(m.window + m.halo_base[q]);
+  for (Neighbor& nb : m.nb) {
+    for (int q = 0; q < 2; ++q) {
+      p.hflag_mine[nb.rank][q] = (const int32_t*)(m.window + nb.hflag_off[q]);
+      p.mig_mine[nb.rank][q] = (int32_t*)(m.window + nb.mig_off[q]);
+    }
+    p.halo_first[nb.rank] = nb.exp_first;
+    p.halo_n[nb.rank] = nb.n_exp_lanes + nb.n_exp_junc;
+    p.mig_cap[nb.rank] = nb.mig_out;
+    p.mig_icap[nb.rank] = (int32_t)std::min<int64_t>(nb.item_out, INT32_MAX);
+    p.mig_in[nb.rank] = nb.mig_in;
+  }
+  TRY(mg_alloc(c, &p.mig_done, 1));
+  TRY(mg_alloc(c, &p.halo_done, 1));
+  TRY(mg_alloc(c, &p.mig_count, 2 * MAX_RANKS));
+  CUDA_TRY(c, cudaMemset(p.mig_done, 0, sizeof(int32_t)));
+  CUDA_TRY(c, cudaMemset(p.halo_done, 0, sizeof(int32_t)));
+  CUDA_TRY(c, cudaMemset(p.mig_count, 0, 2 * MAX_RANKS * sizeof(int32_t)));
   m.n_exp = (int)exp_all.size();
   m.n_imp_junc = (int)imp_junc_all.size();
   TRY(mg_alloc(c, &m.d_exp_items, exp_all.size()));
@@ -1403,9 +1721,9 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     CUDA_TRY(c, cudaMemcpy(m.d_imp_junc, imp_junc_all.data(), imp_junc_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(m.d_imp_where, imp_where_all.data(), imp_where_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
-  c->p.owner = m.d_owner;
-  c->p.my_rank = rank;
-  c->p.halo_recv = m.d_halo_recv;
+  p.owner = m.d_owner;
+  p.my_rank = rank;
+  m.connected = m.nb.empty();
   return GRIDDY_OK;
 }
 
@@ -1429,28 +1747,6 @@ int griddy_mg_set_global_ids(void* ctx, const int32_t* gid) {
   return GRIDDY_OK;
 }
 
-int griddy_mg_nccl_unique_id(uint8_t* out128) {
-  NcclApi* api = nccl_api();
-  if (!api || !out128) return GRIDDY_ERR_NCCL;
-  NcclId id;
-  if (api->GetUniqueId(&id) != 0) return GRIDDY_ERR_NCCL;
-  memcpy(out128, id.internal, 128);
-  return GRIDDY_OK;
-}
-
-int griddy_mg_connect_nccl(void* ctx, const uint8_t* id128) {
-  Ctx* c = (Ctx*)ctx;
-  if (!c) return GRIDDY_ERR_BAD_ARG;
-  if (!c->mg.on || !id128) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_connect_nccl before mg_configure");
-  NcclApi* api = nccl_api();
-  if (!api) return fail(c, GRIDDY_ERR_NCCL, "libnccl.so.2 could not be loaded");
-  CUDA_TRY(c, cudaSetDevice(c->device));
-  NcclId id;
-  memcpy(id.internal, id128, 128);
-  NCCL_TRY(c, api->CommInitRank(&c->mg.nccl_comm, c->mg.world, id, c->mg.rank));
-  return GRIDDY_OK;
-}
-
 int griddy_mg_neighbors(void* ctx, int32_t* ranks, int32_t* n) {
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
@@ -1461,41 +1757,79 @@ int griddy_mg_neighbors(void* ctx, int32_t* ranks, int32_t* n) {
   return GRIDDY_OK;
 }
 
-// One process per GPU: the receive buffers for `from_rank`'s emigrants are handed to that rank as
-// cudaIpc handles (2 x 64 bytes, one per tick parity), which it maps with griddy_mg_ipc_import.
-int griddy_mg_ipc_export(void* ctx, int32_t from_rank, uint8_t* handles128) {
+namespace {
+
+// Where `nb` writes in my window, as the 6 offsets that travel with the window's handle.
+void window_offsets(const Neighbor& nb, int64_t out[6]) {
+  for (int q = 0; q < 2; ++q) {
+    out[q] = (int64_t)nb.halo_off[q];
+    out[2 + q] = (int64_t)nb.hflag_off[q];
+    out[4 + q] = (int64_t)nb.mig_off[q];
+  }
+}
+
+// The neighbour's window is mapped at `base`: point the kernels at my places in it.
+void bind_peer(Ctx* c, Neighbor& nb, uint8_t* base, const int64_t off[6]) {
+  nb.peer_base = base;
+  for (int q = 0; q < 2; ++q) {
+    nb.peer_halo_off[q] = (size_t)off[q];
+    nb.peer_hflag_off[q] = (size_t)off[2 + q];
+    nb.peer_mig_off[q] = (size_t)off[4 + q];
+    c->p.halo_peer[nb.rank][q] = (double*)(base + off[q]);
+    c->p.hflag_peer[nb.rank][q] = (int32_t*)(base + off[2 + q]);
+    c->p.mig_peer[nb.rank][q] = base + off[4 + q];
+  }
+  nb.mapped = true;
+  bool all = true;
+  for (const Neighbor& o : c->mg.nb) all = all && o.mapped;
+  c->mg.connected = all;
+}
+
+}  // namespace
+
+// One process per GPU: my window is handed to every neighbour as a cudaIpc handle (64 bytes) followed by
+// the six byte offsets (int64) of the places that neighbour writes: halo values, halo flag and migrant area, by
+// tick parity.  The neighbour maps it with griddy_mg_ipc_import.
+int griddy_mg_ipc_export(void* ctx, int32_t from_rank, uint8_t* blob128) {
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
-  if (!c->mg.on || !handles128) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_ipc_export before mg_configure");
+  if (!c->mg.on || !blob128) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_ipc_export before mg_configure");
   CUDA_TRY(c, cudaSetDevice(c->device));
   for (Neighbor& nb : c->mg.nb)
     if (nb.rank == from_rank) {
-      for (int par = 0; par < 2; ++par) {
-        cudaIpcMemHandle_t h;
-        CUDA_TRY(c, cudaIpcGetMemHandle(&h, nb.d_mig_recv[par]));
-        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
-        memcpy(handles128 + 64 * par, &h, 64);
-      }
+      cudaIpcMemHandle_t h;
+      CUDA_TRY(c, cudaIpcGetMemHandle(&h, c->mg.window));
+      static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+      memset(blob128, 0, 128);
+      memcpy(blob128, &h, 64);
+      int64_t off[6];
+      window_offsets(nb, off);
+      memcpy(blob128 + 64, off, sizeof(off));
+      const int32_t plan[2] = {nb.n_imp_lanes + nb.n_imp_junc, nb.mig_in};   // what I expect of it: it must agree
+      memcpy(blob128 + 112, plan, sizeof(plan));
       return GRIDDY_OK;
     }
   return fail(c, GRIDDY_ERR_BAD_ARG, "rank " + std::to_string(from_rank) + " is not a neighbour");
 }
 
-int griddy_mg_ipc_import(void* ctx, int32_t to_rank, const uint8_t* handles128) {
+int griddy_mg_ipc_import(void* ctx, int32_t to_rank, const uint8_t* blob128) {
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
-  if (!c->mg.on || !handles128) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_ipc_import before mg_configure");
+  if (!c->mg.on || !blob128) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_ipc_import before mg_configure");
   CUDA_TRY(c, cudaSetDevice(c->device));
   for (Neighbor& nb : c->mg.nb)
     if (nb.rank == to_rank) {
-      for (int par = 0; par < 2; ++par) {
-        cudaIpcMemHandle_t h;
-        memcpy(&h, handles128 + 64 * par, 64);
-        void* ptr = nullptr;
-        CUDA_TRY(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-        nb.peer_mig[par] = (uint8_t*)ptr;
-        c->p.mig_peer[to_rank][par] = (uint8_t*)ptr;
-      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, blob128, 64);
+      int64_t off[6];
+      memcpy(off, blob128 + 64, sizeof(off));
+      int32_t plan[2];
+      memcpy(plan, blob128 + 112, sizeof(plan));
+      if (plan[0] != nb.n_exp_lanes + nb.n_exp_junc || plan[1] != nb.mig_out)
+        return fail(c, GRIDDY_ERR_BAD_STATE, "exchange plans of ranks " + std::to_string(c->mg.rank) + " and " + std::to_string(to_rank) + " disagree");
+      void* ptr = nullptr;
+      CUDA_TRY(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+      bind_peer(c, nb, (uint8_t*)ptr, off);
       return GRIDDY_OK;
     }
   return fail(c, GRIDDY_ERR_BAD_ARG, "rank " + std::to_string(to_rank) + " is not a neighbour");
@@ -1517,11 +1851,18 @@ int griddy_mg_connect_local(void** ctxs, int32_t n) {
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
           return fail(c, GRIDDY_ERR_CUDA, "no peer access between devices " + std::to_string(c->device) + " and " + std::to_string(d->device));
       }
-    // same process: the neighbours' receive buffers are directly addressable
-    for (Neighbor& nb : c->mg.nb)
-      for (Neighbor& back : cs[nb.rank]->mg.nb)
-        if (back.rank == c->mg.rank)
-          for (int par = 0; par < 2; ++par) c->p.mig_peer[nb.rank][par] = nb.peer_mig[par] = back.d_mig_recv[par];
+    // same process: the neighbours' windows are directly addressable
+    for (Neighbor& nb : c->mg.nb) {
+      Neighbor* back = nullptr;
+      for (Neighbor& b : cs[nb.rank]->mg.nb)
+        if (b.rank == c->mg.rank) back = &b;
+      if (!back) return fail(c, GRIDDY_ERR_BAD_STATE, "neighbour lists are not symmetric");
+      if (nb.n_exp_lanes + nb.n_exp_junc != back->n_imp_lanes + back->n_imp_junc || nb.mig_out != back->mig_in)
+        return fail(c, GRIDDY_ERR_BAD_STATE, "exchange plans of two neighbours disagree");
+      int64_t off[6];
+      window_offsets(*back, off);
+      bind_peer(c, nb, cs[nb.rank]->mg.window, off);
+    }
   }
   return GRIDDY_OK;
 }
@@ -1532,8 +1873,9 @@ int griddy_upload_geometry(void* ctx, const double* geom) {
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (!c->have_net || !geom) return fail(c, GRIDDY_ERR_BAD_ARG, "upload_geometry: no network or null array");
   CUDA_TRY(c, cudaSetDevice(c->device));
-  const double2* d = nullptr;
-  TRY(dev_upload(c, c->net_allocs, &d, (const double2*)geom, 4 * c->p.n_items));
+  double2* d = nullptr;   // 4 x double2 per item, by global id like every per-item array; geom is compact
+  TRY(sparse_alloc(c, 4 * sizeof(double2), (void**)&d));
+  TRY(sparse_upload(c, d, (const double2*)geom, 4));
   c->d_geom = d;
   return GRIDDY_OK;
 }

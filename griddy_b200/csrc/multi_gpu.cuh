@@ -9,20 +9,34 @@ namespace griddy {
 // while it turns from a segment lane onto a junction lane or back (never while it goes on or off the
 // road).  An actor lives on the rank that owns its container.  What a turning actor reads of the OLD
 // world on the other side — the target lane's rearmost positive pos-param (route.scm:118-121) and the
-// target junction's occupancy (route.scm:98-108) — is the halo, exchanged while k_advance runs; the actors
-// that crossed are exchanged as fixed-size records before k_link, which then inserts them by key
-// exactly as it inserts local movers (their old lane and old pos-param travel along, because
-// processing order decides equal-key winners).  Results are identical to a single-GPU run.
+// target junction's occupancy (route.scm:98-108) — is the halo; the actors that crossed are handed over
+// as records before k_link, which then inserts them by key exactly as it inserts local movers (their old
+// lane and old pos-param travel along, because processing order decides equal-key winners).  Results
+// are identical to a single-GPU run.
+//
+// Transport: every rank owns a WINDOW of device memory that its neighbours' kernels write into directly
+// (peer stores over NVLink 5 / NVSwitch; the window is shared through cudaIpc between processes).  Per
+// neighbour and tick parity it holds
+//     the halo values that neighbour exports to me, and a flag
+//     [MigHeader][MigRec x bound][AgendaItem x bound]: the actors that crossed from it to me this tick.
+// A sender writes its data, then raises the flag to tick + 1 with a system-scope release; the receiver's
+// next kernel spins on the flag with a system-scope acquire.  No message, no collective, no host in the loop.
+// A buffer of parity q is written at tick t and again at tick t + 2: in between, the receiver has read it
+// (tick t), then sent its own halo of tick t + 1 — which the sender waits for before its tick t + 1 goes
+// on — so the second write cannot overtake the first read.
 
-struct MigRec {
-  double pos_old, pos_new, delta, buf, arrive, land_pos, speed, speed_dt;
-  int32_t gid, st, container, mv_old, hop, tj, popped, n_items, land_tick, land_lane, dest_lane, dest_from_j,
-      dest_to_j, pad;
-  int32_t item_sleep[MIG_ITEMS], item_seg[MIG_ITEMS];
-  double item_pos[MIG_ITEMS];
-  uint8_t item_kind[MIG_ITEMS], item_side[MIG_ITEMS];
+struct __align__(16) MigHeader {
+  int32_t count;     // records written this tick (published by the sender's last packing block)
+  int32_t flag;      // tick + 1 once everything of that tick is in place
+  int32_t n_items;   // agenda items written this tick
+  int32_t pad;
 };
-constexpr size_t MIG_HEADER = 8;   // int32 count (reserved by remote atomics), int32 flag (tick + 1 once the sender is done)
+struct __align__(16) MigRec {
+  double pos_old, pos_new, delta, buf, arrive, land_pos, speed, speed_dt;
+  int32_t gid, st, container, mv_old, hop, tj, popped, n_items;   // n_items: agenda items NOT yet popped, at item_off
+  int32_t land_tick, land_lane, dest_lane, dest_from_j, dest_to_j, item_off, route_cur, pad;
+};
+static_assert(sizeof(MigHeader) == 16 && sizeof(MigRec) == 128, "window layout");
 
 __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* ptr) {
   int32_t v;
@@ -32,40 +46,68 @@ __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t* ptr) {
 __device__ __forceinline__ void st_release_sys(int32_t* ptr, int32_t v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
+// Spin until *flag >= want (thread 0 of a block), ~10 s at most: then the neighbour is gone.
+__device__ __forceinline__ void wait_flag(const Params& p, const int32_t* flag, int32_t want) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < want)
+    if (clock64() - t0 > (20LL << 30)) { atomicOr(&p.scal[SC_ERR], DEV_ERR_MIG_TIMEOUT); break; }
+}
 
 // Halo out: for every lane of mine that a neighbour's actors can enter, its smallest key in (0, ...]
 // (the walk route.scm:118-121 would do), +inf if there is none; for every such junction, its occupancy.
-// One launch for all neighbours: `items` and `out` are the neighbours' lists back to back (each
-// neighbour's part of `out` is what is sent to it); a junction is listed as ~id.
-__global__ void __launch_bounds__(128) k_halo_pack(Params p, int par, const int32_t* __restrict__ items, int n,
-                                                    double* __restrict__ out, int tick) {
+// One launch for all neighbours: `items` holds the neighbours' lists back to back (a junction is listed
+// as ~id); every value is stored straight into the reading rank's window, and the block that finishes
+// last raises the flag in every neighbour's window.
+__global__ void __launch_bounds__(128) k_halo_pack(Params p, const int32_t* __restrict__ items, int n, int tick) {
+  __shared__ bool s_last;
   grid_dependency_wait();
   TRACE(p, tick, TR_HALO_PACK);
+  const int par = tick & 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int32_t item = items[i];
-  if (item < 0) { out[i] = (double)p.occ[~item]; return; }
-  const double* __restrict__ pos = p.pos[par];
-  int32_t x = p.lane[item].tail;
-  while (x >= 0 && !(pos[x] > 0.0)) x = p.sa[x].ahead;
-  out[i] = x >= 0 ? pos[x] : __longlong_as_double(0x7ff0000000000000LL);
+  if (i < n) {
+    const int32_t item = items[i];
+    double v;
+    if (item < 0) {
+      v = (double)p.occ[~item];
+    } else {
+      const double* __restrict__ pos = p.pos[par];
+      int32_t x = p.lane[item].tail;
+      while (x >= 0 && !(pos[x] > 0.0)) x = p.sa[x].ahead;
+      v = x >= 0 ? pos[x] : __longlong_as_double(0x7ff0000000000000LL);
+    }
+    int r = 0;
+    while (r < MAX_RANKS - 1 && !(i >= p.halo_first[r] && i < p.halo_first[r] + p.halo_n[r])) ++r;
+    p.halo_peer[r][par][i - p.halo_first[r]] = v;
+  }
+  __threadfence_system();   // my values before my block's count
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(p.halo_done, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();   // every block's values before the flags
+  if (threadIdx.x < MAX_RANKS && p.hflag_peer[threadIdx.x][par]) st_release_sys(p.hflag_peer[threadIdx.x][par], tick + 1);
+  if (threadIdx.x == 0) *p.halo_done = 0;
 }
 
-// Halo in: occupancy of the neighbours' junctions (the lane values are read in place from halo_recv).
-// One launch for all neighbours: junctions[i] is a junction another rank owns, where[i] its place in
-// halo_recv.
+// Halo in: wait for every neighbour's flag of this tick, then take over the occupancy of the neighbours'
+// junctions (the lane values are read in place from halo_recv by turn_onto).  One launch for all
+// neighbours: junctions[i] is a junction another rank owns, where[i] its place in halo_recv.  k_slow, next
+// on the stream, may then read the halo.
 __global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __restrict__ junctions,
                                                       const int32_t* __restrict__ where, int n, int tick) {
   grid_dependency_wait();
   TRACE(p, tick, TR_HALO_UNPACK);
+  const int par = tick & 1;
+  if (threadIdx.x < MAX_RANKS && p.hflag_mine[threadIdx.x][par]) wait_flag(p, p.hflag_mine[threadIdx.x][par], tick + 1);
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p.occ[junctions[i]] = (int32_t)p.halo_recv[where[i]];
+  if (i < n) p.occ[junctions[i]] = (int32_t)__ldcg(&p.halo_recv[par][where[i]]);
 }
 
-// Emigrants -> one record each, written straight into the receive buffer of the rank that owns their
-// new lane (peer memory over NVLink: remote stores for the records, one remote atomic per block and
-// destination for the slots), so only the actors that actually crossed travel, not a bound-sized message.
-// The block that finishes last raises the flag in every neighbour's buffer: no message follows the records.
+// Emigrants -> one record each plus their remaining agenda items, written straight into the window of the
+// rank that owns their new lane, so only the actors that actually crossed travel, not a bound-sized message.
+// Places are handed out by atomics on this rank's own counters; the block that finishes last publishes the
+// counts and raises the flag in every neighbour's window: nothing follows the records.
 // Runs as the first EMIG_BLOCKS blocks of k_unlink (lanes.cuh): both need k_slow only, and what k_unlink
 // changes of an emigrant's slot — it clears ALIVE | MOVED | EMIG in st — is rebuilt here.
 constexpr int EMIG_BLOCKS = 64;
@@ -81,6 +123,7 @@ __device__ __forceinline__ void emig_pack_block(const Params& p, const int tick,
     __syncthreads();
     const int32_t i = chunk + threadIdx.x;
     int a = -1, to = -1, mine = 0;
+    int32_t first_item = 0;
     MigRec r;
     if (i < n) {
       a = p.emig[i];
@@ -88,7 +131,7 @@ __device__ __forceinline__ void emig_pack_block(const Params& p, const int tick,
       if (k.dead_mark == tick + 1) {
         a = -1;   // a ghost's move is void
       } else {
-        // the whole record is gathered before the slot is reserved: one round trip less on the way
+        // the whole record is gathered before a place is reserved: one round trip less on the way
         const ColdF f = p.coldf[a];
         const double2 db = p.db[a];
         const int32_t tj = p.tj[a];
@@ -111,40 +154,40 @@ __device__ __forceinline__ void emig_pack_block(const Params& p, const int tick,
         r.dest_lane = k.dest_lane;
         r.dest_from_j = k.dest_from_j;
         r.dest_to_j = k.dest_to_j;
+        r.route_cur = k.route_cur;
         r.pad = 0;
-        const int32_t beg = f.agenda_beg;
-        r.popped = k.agenda_cur - beg;
-        r.n_items = f.agenda_end - beg;
+        first_item = k.agenda_cur;
+        r.popped = k.agenda_cur - f.agenda_beg;
+        r.n_items = f.agenda_end - k.agenda_cur;
         r.land_tick = f.land_tick;
         r.land_lane = f.land_lane;
-        if (r.n_items > MIG_ITEMS) { dev_error(p, DEV_ERR_MIG_AGENDA); r.n_items = MIG_ITEMS; }
-#pragma unroll
-        for (int q = 0; q < MIG_ITEMS; ++q) {
-          const bool in = q < r.n_items;
-          r.item_kind[q] = in ? p.item_kind[beg + q] : 0;
-          r.item_side[q] = in ? p.item_side[beg + q] : 0;
-          r.item_sleep[q] = in ? p.item_sleep[beg + q] : 0;
-          r.item_seg[q] = in ? p.item_seg[beg + q] : -1;
-          r.item_pos[q] = in ? p.item_pos[beg + q] : 0.0;
-        }
+        r.item_off = atomicAdd(&p.mig_count[MAX_RANKS + to], r.n_items);
       }
     }
     __syncthreads();
     if (threadIdx.x < MAX_RANKS && s_count[threadIdx.x] > 0)
-      s_base[threadIdx.x] = atomicAdd_system((int32_t*)p.mig_peer[threadIdx.x][par], s_count[threadIdx.x]);
+      s_base[threadIdx.x] = atomicAdd(&p.mig_count[threadIdx.x], s_count[threadIdx.x]);
     __syncthreads();
     if (a < 0) continue;
     const int32_t at = s_base[to] + mine;
-    if (at >= p.mig_cap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
-    ((MigRec*)(p.mig_peer[to][par] + MIG_HEADER))[at] = r;
+    if (at >= p.mig_cap[to] || r.item_off + r.n_items > p.mig_icap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
+    uint8_t* area = p.mig_peer[to][par];
+    ((MigRec*)(area + sizeof(MigHeader)))[at] = r;
+    AgendaItem* items = (AgendaItem*)(area + sizeof(MigHeader) + (size_t)p.mig_cap[to] * sizeof(MigRec)) + r.item_off;
+    for (int32_t q = 0; q < r.n_items; ++q) items[q] = p.agenda[first_item + q];
   }
   __threadfence_system();   // my records before my block's count
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(p.mig_done, 1) == n_blocks - 1;
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();   // every block's records before the flags
-  if (threadIdx.x < MAX_RANKS && p.mig_peer[threadIdx.x][par]) st_release_sys((int32_t*)p.mig_peer[threadIdx.x][par] + 1, tick + 1);
+  __threadfence_system();   // every block's records before the headers
+  if (threadIdx.x < MAX_RANKS && p.mig_peer[threadIdx.x][par]) {
+    MigHeader* h = (MigHeader*)p.mig_peer[threadIdx.x][par];
+    h->count = min(atomicExch(&p.mig_count[threadIdx.x], 0), p.mig_cap[threadIdx.x]);
+    h->n_items = min(atomicExch(&p.mig_count[MAX_RANKS + threadIdx.x], 0), p.mig_icap[threadIdx.x]);
+    st_release_sys(&h->flag, tick + 1);
+  }
   if (threadIdx.x == 0) *p.mig_done = 0;
 #ifdef GRIDDY_TRACE
   if (p.trace && threadIdx.x == 0) {
@@ -161,13 +204,10 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
   grid_dependency_wait();
   const int par = tick & 1;
   TRACE(p, tick, TR_IMMIG_UNPACK);
-  const uint8_t* buf = (const uint8_t*)p.mig_mine[blockIdx.y][par];
-  if (!buf) return;
-  if (threadIdx.x == 0) {   // the sender's flag: all its records of this tick are in my memory
-    const long long t0 = clock64();
-    while (ld_acquire_sys((const int32_t*)buf + 1) < tick + 1)
-      if (clock64() - t0 > (20LL << 30)) { dev_error(p, DEV_ERR_MIG_TIMEOUT); break; }   // ~10 s: the neighbour is gone
-  }
+  const uint8_t* area = (const uint8_t*)p.mig_mine[blockIdx.y][par];
+  if (!area) return;
+  const MigHeader* h = (const MigHeader*)area;
+  if (threadIdx.x == 0) wait_flag(p, &h->flag, tick + 1);   // the sender's flag: all its records of this tick are in my memory
   __syncthreads();
 #ifdef GRIDDY_TRACE
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {   // the later of the neighbours' flags
@@ -176,25 +216,25 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
     atomicMax(&p.trace[(tick & 63) * TR_COUNT + TR_IMMIG_GO], t_);
   }
 #endif
-  const int32_t n = min(ld_acquire_sys((const int32_t*)buf), p.mig_in[blockIdx.y]);
-  const MigRec* recs = (const MigRec*)(buf + MIG_HEADER);
+  const int32_t n = min(ld_acquire_sys(&h->count), p.mig_in[blockIdx.y]);
+  const MigRec* recs = (const MigRec*)(area + sizeof(MigHeader));
+  const AgendaItem* payload = (const AgendaItem*)(area + sizeof(MigHeader) + (size_t)p.mig_in[blockIdx.y] * sizeof(MigRec));
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const MigRec r = recs[i];
     const int32_t a = atomicAdd(&p.scal[SC_NSLOTS], 1);
     const int32_t it = atomicAdd(&p.scal[SC_NITEMS], r.n_items);
-    if (a >= p.cap || it + r.n_items > p.icap) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
+    if (a >= p.cap || it + r.n_items > p.icap) {   // no room: give the places back, report, drop the actor
+      atomicSub(&p.scal[SC_NSLOTS], 1);
+      atomicSub(&p.scal[SC_NITEMS], r.n_items);
+      dev_error(p, DEV_ERR_MIG_OVERFLOW);
+      continue;
+    }
     p.coldf[a].speed = r.speed;
     p.coldf[a].speed_dt = r.speed_dt;
     p.cold[a].gid = r.gid;
-    p.coldf[a].agenda_beg = it;
+    p.coldf[a].agenda_beg = it - r.popped;   // only the items not yet popped travelled; the head is item `it`
     p.coldf[a].agenda_end = it + r.n_items;
-    for (int k = 0; k < r.n_items; ++k) {
-      p.item_kind[it + k] = r.item_kind[k];
-      p.item_side[it + k] = r.item_side[k];
-      p.item_sleep[it + k] = r.item_sleep[k];
-      p.item_seg[it + k] = r.item_seg[k];
-      p.item_pos[it + k] = r.item_pos[k];
-    }
+    for (int k = 0; k < r.n_items; ++k) p.agenda[it + k] = payload[r.item_off + k];
     p.sa[a] = SA{(uint32_t)r.st, -1};
     p.cold[a].behind = -1;
     p.pos[par][a] = r.pos_old;       // processing order among a lane's entrants looks at old lane and old key
@@ -210,8 +250,8 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
     p.cold[a].dest_from_j = r.dest_from_j;
     p.cold[a].dest_to_j = r.dest_to_j;
     p.tj[a] = tag_junction(p, r.tj);
-    p.cold[a].agenda_cur = it + r.popped;
-    p.cold[a].route_cur = 0;
+    p.cold[a].agenda_cur = it;
+    p.cold[a].route_cur = r.route_cur;
     p.coldf[a].land_tick = r.land_tick;
     p.coldf[a].land_lane = r.land_lane;
     p.cold[a].dead_mark = 0;

@@ -53,7 +53,7 @@ __device__ __forceinline__ void grid_dependency_wait() {
 // device scalars (Params::scal)
 constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_COUNT = 4;
 constexpr int MAX_RANKS = 8;     // one box
-constexpr int MIG_ITEMS = 4;     // agenda items a migrating actor can carry
+constexpr int MAX_RANGES = 64;   // id ranges of a tiled network (griddy_set_item_ranges)
 
 // st and ahead of a slot share an 8-byte word: every kernel that walks a lane needs both.
 struct __align__(8) SA {
@@ -110,6 +110,20 @@ struct __align__(16) LaneDyn {
 };
 static_assert(sizeof(Item) == 32 && sizeof(LaneDyn) == 32, "one sector per record");
 
+// One agenda item (actor.scm:25-26), one sector.  A travel-to item carries its destination resolved at
+// upload time — off-road->on-road of the destination (location.scm:49-57): the outer lane of (segment, side),
+// the pos-param on it, the junctions that lane leaves and reaches (grid routing) — so that begin-route$ reads
+// nothing of the destination's part of the network, which on a tiled world another rank holds.
+struct __align__(16) AgendaItem {
+  double dpos;            // travel-to: pos-param on the destination lane
+  int32_t sleep;          // sleep-for: the time
+  int32_t dlane;          // travel-to: destination lane, -1: the road has no lanes on that side
+  int32_t dfrom, dto;     // travel-to: junctions dlane leaves / reaches (-1 without a grid routing table)
+  uint32_t kind;          // GRIDDY_SLEEP_FOR / GRIDDY_TRAVEL_TO
+  int32_t pad;
+};
+static_assert(sizeof(AgendaItem) == 32, "one sector per agenda item");
+
 struct Params {
   // network, by registration index
   int64_t n_items;
@@ -128,12 +142,9 @@ struct Params {
   int32_t* tj;    // junction of the lane the route head turns onto, -1 if that is not a junction lane
   Cold* cold;
   ColdF* coldf;
-  // agenda items (immutable; actors that arrive from another rank append theirs)
+  // agenda items (immutable; actors that arrive from another rank append theirs, a reorder compacts the pool)
   int64_t n_actors;
-  uint8_t* item_kind;
-  int32_t *item_sleep, *item_seg;
-  uint8_t* item_side;
-  double* item_pos;
+  AgendaItem* agenda;
   int32_t icap;   // item capacity
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
@@ -144,20 +155,30 @@ struct Params {
   int4* slow;   // deferred actors: {slot (~slot: turn-onto), st, pos-param lo, hi} as k_advance read them
   int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, lanes left, deferred actors, lanes entered
   double dt, two_size;
-  // multi-GPU (owner == null on a single GPU): spatial partition, see "Multi-GPU" below
+  // multi-GPU (owner == null on a single GPU): spatial partition, see multi_gpu.cuh.  Every rank owns a
+  // WINDOW of device memory that its neighbours write into over NVLink (peer access; cudaIpc between
+  // processes): per neighbour and tick parity the halo values with a flag, and the migrants' records and
+  // agenda items with a header.  Nothing else crosses: no message, no collective.
   const int32_t* owner;      // rank that owns each item
   int32_t my_rank;
-  const double* halo_recv;   // rearmost positive pos-param of the remote lanes my actors can enter;
-                             // lane_tail[remote lane] = -2 - index into this array
+  const double* halo_recv[2];   // by parity: rearmost positive pos-param of the remote lanes my actors can enter
+                                // (and the neighbours' junction occupancies); lane.tail = -2 - index into it
+  double* halo_peer[MAX_RANKS][2];        // by neighbour and parity: where I write its halo, in ITS window
+  int32_t* hflag_peer[MAX_RANKS][2];      //   and the flag I raise there (tick + 1) once it is complete
+  const int32_t* hflag_mine[MAX_RANKS][2];   // the flags my neighbours raise in my window
+  int32_t halo_first[MAX_RANKS], halo_n[MAX_RANKS];   // my export list, by neighbour: entries [first, first + n)
+  int32_t* halo_done;        // blocks of k_halo_pack that have finished (the last one raises the flags)
   int32_t* emig;             // slots that emigrated this tick
   int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
-  // by destination rank and tick parity: that rank's receive buffer for my emigrants, in ITS memory
-  // (peer access over NVLink): [int32 count, int32 flag][MigRec x mig_cap].  emig_pack_block writes the records there
-  // directly and then raises the flag to tick + 1, which is what the receiver's k_immig_unpack waits for.
+  int32_t mig_icap[MAX_RANKS];    //   and agenda items per tick
+  // by destination rank and tick parity: that rank's receive area for my emigrants, in ITS window:
+  // [MigHeader][MigRec x mig_cap][AgendaItem x mig_icap].  emig_pack_block writes records and items there
+  // directly, then the header's counts, then raises its flag to tick + 1 — what the receiver's k_immig_unpack waits for.
   uint8_t* mig_peer[MAX_RANKS][2];
-  int32_t* mig_mine[MAX_RANKS][2];   // my own receive buffers, by source rank: [int32 count, pad][MigRec x mig_in[rank]]
+  int32_t* mig_mine[MAX_RANKS][2];   // my own receive areas, by source rank
   int32_t mig_in[MAX_RANKS];         // by source rank: records per tick at most
-  int32_t* mig_done;                 // packing blocks of k_unlink that have finished (the last one raises the flags)
+  int32_t* mig_count;                // [2 x MAX_RANKS] places handed out this tick, by destination: records, items
+  int32_t* mig_done;                 // packing blocks of k_unlink that have finished (the last one publishes)
   unsigned long long* trace;         // -DGRIDDY_TRACE builds: [64 ticks][16] %globaltimer stamps (griddy_debug_trace)
 };
 

@@ -23,6 +23,8 @@ struct Permute {
   Cold* dst_cold;
   const ColdF* src_coldf;
   ColdF* dst_coldf;
+  AgendaItem* agenda_dst;   // partitioned worlds: the pool the remaining agenda items are compacted into (else null)
+  int32_t* n_items_new;     //   and its fill count
 };
 
 // grid = n_pad / 256 exactly: every lane of every warp reaches the ballot
@@ -77,8 +79,17 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
   } else {
     cold.behind = -1;
   }
+  ColdF coldf = q.src_coldf[old];
+  if (q.agenda_dst) {   // only the items not yet popped are kept; agenda_beg stays "head minus items popped"
+    const int32_t rem = coldf.agenda_end - cold.agenda_cur, popped = cold.agenda_cur - coldf.agenda_beg;
+    const int32_t base = rem > 0 ? atomicAdd(q.n_items_new, rem) : 0;
+    for (int32_t k = 0; k < rem; ++k) q.agenda_dst[base + k] = p.agenda[cold.agenda_cur + k];
+    cold.agenda_cur = base;
+    coldf.agenda_beg = base - popped;
+    coldf.agenda_end = base + rem;
+  }
   q.dst_cold[s] = cold;
-  q.dst_coldf[s] = q.src_coldf[old];
+  q.dst_coldf[s] = coldf;
   q.dst_db[s] = q.src_db[old];
 #pragma unroll
   for (int k = 0; k < PERM8; ++k) {

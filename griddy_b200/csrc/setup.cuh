@@ -5,12 +5,14 @@ namespace griddy {
 
 // ------------------------------------------------------------------------------------------------
 // Set-up: the network is assembled on the device from the arrays that cross the ABI (staged through
-// a reusable device buffer), so that no host copy of the 32-byte records is ever made.
+// a reusable device buffer), so that no host copy of the 32-byte records is ever made.  Every kernel works
+// on one id range of the held items: `item` / `lane` point at the range's first record (global id g0), the
+// source arrays at its first compact entry.
 __global__ void __launch_bounds__(256) k_item_build(Item* __restrict__ item, int64_t n, const uint8_t* __restrict__ kind,
                                                      const double* __restrict__ len, const uint8_t* __restrict__ dir,
                                                      const int32_t* __restrict__ seg, const int32_t* __restrict__ out,
                                                      const int32_t* __restrict__ junction, const int32_t* __restrict__ of,
-                                                     const int32_t* __restrict__ ob) {
+                                                     const int32_t* __restrict__ ob, int64_t g0) {
   const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (r >= n) return;
   Item it;
@@ -21,7 +23,7 @@ __global__ void __launch_bounds__(256) k_item_build(Item* __restrict__ item, int
   it.link = it.kind == GRIDDY_SEGMENT_LANE ? seg[r] : it.kind == GRIDDY_JUNCTION_LANE ? out[r] : it.kind == GRIDDY_SEGMENT ? of[r] : -1;
   it.link2 = it.kind == GRIDDY_JUNCTION_LANE ? junction[r] : it.kind == GRIDDY_SEGMENT ? ob[r] : -1;
   it.from_j = it.to_j = -1;
-  it.loc_key = (uint32_t)r;   // default locality key: the registration index
+  it.loc_key = (uint32_t)(g0 + r);   // default locality key: the registration index
   item[r] = it;
 }
 

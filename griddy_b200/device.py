@@ -26,7 +26,7 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_download_occupancy", "griddy_last_step_ms", "griddy_tick", "griddy_kernel_launches",
            "griddy_set_locality_keys", "griddy_set_reorder_period", "griddy_slots_in_use",
            "griddy_debug_sort_pairs", "griddy_count_alive", "griddy_mg_configure", "griddy_mg_set_global_ids",
-           "griddy_mg_nccl_unique_id", "griddy_mg_connect_nccl", "griddy_mg_connect_local", "griddy_mg_step_local",
+           "griddy_set_item_ranges", "griddy_set_agenda_destinations", "griddy_mg_plan_tile", "griddy_mg_connect_local", "griddy_mg_step_local",
            "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
            "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
            "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace", "griddy_state_digest")
@@ -76,11 +76,13 @@ class Simulation:
 
     With `partition=(rank, world, owner, mig_cap, extra_slots)` the context holds one part of a
     spatially partitioned world (include/griddy_cuda.h, "Multi-GPU"): `actors` are then the actors on
-    this rank's items, `gids` their global ids."""
+    this rank's items, `gids` their global ids; `owner` has one entry per item of `net`.  `net` may be a
+    TILE (FlatNetwork.range_beg / range_end: the rank's own rows plus the ring next to them): its arrays are
+    compact and `actors` must carry their resolved destinations (dest_*)."""
 
     def __init__(self, net: FlatNetwork, actors: FlatActors, device: int = -1,
                  dt: float = 1.0 / 15.0, two_size: float = 10.0, reorder_period: int | None = None,
-                 partition=None, gids=None):
+                 partition=None, gids=None, max_agenda_items=None):
         L = lib()
         self.h = C.c_void_p()
         rc = L.griddy_create(C.byref(self.h), C.c_int(device))
@@ -89,6 +91,9 @@ class Simulation:
             raise GriddyCudaError(rc, "griddy_create failed (no CUDA device?)")
         self.net, self.actors = net, actors
         self._chk(L.griddy_set_constants(self.h, C.c_double(dt), C.c_double(two_size)))
+        if net.tiled:
+            self._chk(L.griddy_set_item_ranges(self.h, C.c_int64(net.n_global), C.c_int32(len(net.range_beg)),
+                                               _p(net.range_beg), _p(net.range_end)))
         self._chk(L.griddy_upload_network(self.h, C.c_int64(net.n_items), _p(net.kind), _p(net.lane_len),
                                           _p(net.lane_dir), _p(net.lane_segment), _p(net.lane_out),
                                           _p(net.lane_junction), _p(net.seg_outer_forw),
@@ -108,8 +113,11 @@ class Simulation:
         self.partition = partition
         if partition is not None:
             rank, world, owner, mig_cap, extra_slots = partition
-            self._chk(L.griddy_mg_configure(self.h, C.c_int32(rank), C.c_int32(world), _p(owner), _p(net.lane_in),
-                                            C.c_int32(mig_cap), C.c_int64(extra_slots)))
+            lens = actors.agenda_off[1:] - actors.agenda_off[:-1]
+            max_items = max(int(lens.max()) if len(lens) else 0, int(max_agenda_items or 0), 1)
+            self._owner = np.ascontiguousarray(owner, np.int32)
+            self._chk(L.griddy_mg_configure(self.h, C.c_int32(rank), C.c_int32(world), _p(self._owner), _p(net.lane_in),
+                                            C.c_int32(mig_cap), C.c_int64(extra_slots), C.c_int32(max_items)))
         self.upload_actors(actors)
         if partition is not None:
             self.gids = np.ascontiguousarray(gids, np.int32)
@@ -117,6 +125,9 @@ class Simulation:
 
     def upload_actors(self, a: FlatActors):
         self.actors = a
+        if a.dest_lane is not None:   # destinations resolved by the generator (needed on a tiled network)
+            self._chk(lib().griddy_set_agenda_destinations(self.h, C.c_int64(a.n_agenda_items), _p(a.dest_lane), _p(a.dest_dir),
+                                                           _p(a.dest_from_j), _p(a.dest_to_j)))
         self._chk(lib().griddy_upload_actors(self.h, C.c_int64(a.n), _p(a.loc_kind), _p(a.container),
                                              _p(a.pos), _p(a.side), _p(a.speed), _p(a.speed_dt),
                                              _p(a.agenda_off), _p(a.item_kind), _p(a.item_sleep),
@@ -219,6 +230,7 @@ class Simulation:
         return buf.array[: n.value]
 
     def occupancy(self):
+        """Actors per container and per junction, one entry per item of `net` (compact on a tile)."""
         lane_count = np.zeros(self.net.n_items, np.int32)
         junction_count = np.zeros(self.net.n_items, np.int32)
         self._chk(lib().griddy_download_occupancy(self.h, _p(lane_count), _p(junction_count)))
@@ -253,21 +265,13 @@ class PinnedFrame:
             self.ptr = None
 
 
-def connect_nccl(sim: "Simulation"):
-    """One process per GPU: share rank 0's NCCL id through torch.distributed, then join the communicator."""
-    import torch
+def connect_ipc(sim: "Simulation"):
+    """One process per GPU: every rank exports its window to each neighbour (cudaIpc handle + the offsets of that
+    neighbour's places in it), the blobs travel through torch.distributed (any backend), every rank maps its
+    neighbours' windows.  After the closing barrier the ranks call step() in lock-step; the data plane is peer
+    stores and flags between the kernels, with no message and no collective."""
     import torch.distributed as dist
     rank = sim.partition[0]
-    buf = np.zeros(128, np.uint8)
-    if rank == 0:
-        rc = lib().griddy_mg_nccl_unique_id(_p(buf))
-        if rc:
-            raise GriddyCudaError(rc, "ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
-    t = torch.from_numpy(buf).cuda() if dist.get_backend() == "nccl" else torch.from_numpy(buf)
-    dist.broadcast(t, src=0)
-    buf = t.cpu().numpy()
-    sim._chk(lib().griddy_mg_connect_nccl(sim.h, _p(np.ascontiguousarray(buf))))
-    # the buffers each neighbour writes its emigrants into: cudaIpc handles, rank -> rank
     nbs = np.zeros(8, np.int32)
     n = C.c_int32(0)
     sim._chk(lib().griddy_mg_neighbors(sim.h, _p(nbs), C.byref(n)))
@@ -279,10 +283,9 @@ def connect_nccl(sim: "Simulation"):
     everyone = [None] * dist.get_world_size()
     dist.all_gather_object(everyone, mine)
     for q in nbs[: n.value].tolist():
-        h = np.frombuffer(everyone[q][rank], np.uint8).copy()      # q's buffers for what comes from me
+        h = np.frombuffer(everyone[q][rank], np.uint8).copy()      # q's window, and my places in it
         sim._chk(lib().griddy_mg_ipc_import(sim.h, C.c_int32(q), _p(h)))
     dist.barrier()
-
 
 
 class PartitionedSimulation:
@@ -290,15 +293,23 @@ class PartitionedSimulation:
     executable form of the multi-GPU path for tests — on one GPU, or spread over the visible ones."""
 
     def __init__(self, net: FlatNetwork, actors: FlatActors, owner: np.ndarray, world: int, devices=None,
-                 mig_cap: int = 4096, extra_slots: int | None = None, reorder_period: int | None = None, **kw):
+                 mig_cap: int = 4096, extra_slots: int | None = None, reorder_period: int | None = None, tiles=None, **kw):
+        """tiles: per rank the (range_beg, range_end) id ranges it holds — every rank then uploads only that part of
+        `net` (FlatNetwork.tile_of) and resolves its actors' destinations on the host."""
         self.net, self.actors, self.world = net, actors, world
         owner = np.ascontiguousarray(owner, np.int32)
         extra = actors.n if extra_slots is None else extra_slots
+        lens = actors.agenda_off[1:] - actors.agenda_off[:-1]
+        kw.setdefault("max_agenda_items", int(lens.max()) if len(lens) else 1)
+        if tiles is not None and actors.dest_lane is None:
+            actors = with_destinations(net, actors)
         self.ranks = []
         for r in range(world):
             mine = np.flatnonzero(owner[actors.container] == r)
-            self.ranks.append(Simulation(net, subset_actors(actors, mine), device=devices[r] if devices else -1,
-                                         reorder_period=reorder_period, partition=(r, world, owner, mig_cap, extra),
+            part = net if tiles is None else net.tile_of(tiles[r][0], tiles[r][1], owner)
+            self.ranks.append(Simulation(part, subset_actors(actors, mine), device=devices[r] if devices else -1,
+                                         reorder_period=reorder_period,
+                                         partition=(r, world, owner if tiles is None else part.owner, mig_cap, extra),
                                          gids=mine, **kw))
         self._hs = (C.c_void_p * world)(*[s.h for s in self.ranks])
         rc = lib().griddy_mg_connect_local(self._hs, C.c_int32(world))
@@ -332,8 +343,26 @@ def subset_actors(a: FlatActors, idx: np.ndarray) -> FlatActors:
     items = np.repeat(beg - off[:-1], lens) + np.arange(off[-1]) if len(idx) else np.zeros(0, np.int64)
     if a.route_off is not None:
         raise ValueError("partitioned worlds use the grid routing table, not uploaded routes")
+    dest = {} if a.dest_lane is None else dict(dest_lane=a.dest_lane[items], dest_dir=a.dest_dir[items],
+                                               dest_from_j=a.dest_from_j[items], dest_to_j=a.dest_to_j[items])
     return FlatActors(a.loc_kind[idx], a.container[idx], a.pos[idx], a.side[idx], a.speed[idx], a.speed_dt[idx], off,
-                      a.item_kind[items], a.item_sleep[items], a.item_seg[items], a.item_side[items], a.item_pos[items])
+                      a.item_kind[items], a.item_sleep[items], a.item_seg[items], a.item_side[items], a.item_pos[items], **dest)
+
+
+def with_destinations(net: FlatNetwork, a: FlatActors) -> FlatActors:
+    """`a` with every travel-to destination resolved from the WHOLE network `net`, as begin-route$ would
+    (off-road->on-road, location.scm:49-57; get-outer-lane, location.scm:16-24): what griddy_set_agenda_destinations takes."""
+    travel = a.item_kind == 1
+    seg = np.where(travel, a.item_seg, 0)
+    lane = np.where(travel, np.where(a.item_side == 1, net.seg_outer_back[seg], net.seg_outer_forw[seg]), -1).astype(np.int32)
+    ok = lane >= 0
+    l0 = np.where(ok, lane, 0)
+    pick = lambda arr, fill: np.where(ok, arr[l0], fill) if arr is not None else np.full(len(lane), fill)
+    out = FlatActors(a.loc_kind, a.container, a.pos, a.side, a.speed, a.speed_dt, a.agenda_off, a.item_kind, a.item_sleep,
+                     a.item_seg, a.item_side, a.item_pos, a.route_off, a.route_lane, dest_lane=lane,
+                     dest_dir=pick(net.lane_dir, 0).astype(np.uint8), dest_from_j=pick(net.lane_from_j, -1).astype(np.int32),
+                     dest_to_j=pick(net.lane_to_j, -1).astype(np.int32))
+    return out
 
 
 def merge_local_states(parts, n_total: int) -> ActorState:

@@ -46,6 +46,12 @@ class FlatNetwork:
     seg_reg: Optional[np.ndarray] = None       # i32 segment ordinal -> registration id
     loc_key: Optional[np.ndarray] = None       # u32 locality key per item (griddy_set_locality_keys)
     geom: Optional[np.ndarray] = None          # f64 [n_items,8] drawing geometry (griddy_upload_geometry)
+    # a TILE of a larger network (griddy_set_item_ranges): every array above then has one entry per held item,
+    # the id ranges back to back; the ids inside the arrays stay global
+    n_global: Optional[int] = None             # items of the whole network
+    range_beg: Optional[np.ndarray] = None     # i64 ascending, disjoint id ranges held
+    range_end: Optional[np.ndarray] = None
+    owner: Optional[np.ndarray] = None         # i32 owner rank per held item (partitioned worlds)
 
     def __post_init__(self):
         self.kind = _arr(self.kind, np.uint8)
@@ -62,10 +68,43 @@ class FlatNetwork:
         if self.geom is not None:
             self.geom = _arr(self.geom, np.float64).reshape(-1, 8)
             assert self.geom.shape[0] == self.kind.shape[0], "geom needs 8 doubles per item"
+        if self.range_beg is not None:
+            self.range_beg = _arr(self.range_beg, np.int64)
+            self.range_end = _arr(self.range_end, np.int64)
+            assert int((self.range_end - self.range_beg).sum()) == self.kind.shape[0], "ranges do not match the arrays"
+        if self.owner is not None:
+            self.owner = _arr(self.owner, np.int32)
 
     @property
     def n_items(self) -> int:
         return int(self.kind.shape[0])
+
+    @property
+    def tiled(self) -> bool:
+        return self.range_beg is not None
+
+    def local(self, gid) -> np.ndarray:
+        """Compact index of global ids (-1 where the tile does not hold the item)."""
+        gid = np.asarray(gid, np.int64)
+        if not self.tiled:
+            return np.where((gid >= 0) & (gid < self.n_items), gid, -1)
+        k = np.searchsorted(self.range_end, gid, side="right")
+        k = np.minimum(k, len(self.range_beg) - 1)
+        inside = (gid >= self.range_beg[k]) & (gid < self.range_end[k])
+        off = np.concatenate([[0], np.cumsum(self.range_end - self.range_beg)])[:-1]
+        return np.where(inside, off[k] + gid - self.range_beg[k], -1)
+
+    def tile_of(self, range_beg, range_end, owner=None) -> "FlatNetwork":
+        """The tile of this (whole) network that holds the given id ranges: what a rank would have generated."""
+        rb, re = np.asarray(range_beg, np.int64), np.asarray(range_end, np.int64)
+        idx = np.concatenate([np.arange(b, e) for b, e in zip(rb, re)]) if len(rb) else np.zeros(0, np.int64)
+        pick = lambda a: None if a is None else a[idx]
+        return FlatNetwork(self.kind[idx], self.lane_len[idx], self.lane_dir[idx], self.lane_segment[idx], self.lane_out[idx],
+                           self.lane_junction[idx], self.seg_outer_forw[idx], self.seg_outer_back[idx],
+                           lane_in=pick(self.lane_in), grid_n=self.grid_n, lane_from_j=pick(self.lane_from_j),
+                           lane_to_j=pick(self.lane_to_j), turn4=pick(self.turn4), seg_reg=self.seg_reg,
+                           loc_key=pick(self.loc_key), geom=pick(self.geom), n_global=self.n_items, range_beg=rb,
+                           range_end=re, owner=None if owner is None else np.ascontiguousarray(owner[idx], np.int32))
 
 
 @dataclass
@@ -91,6 +130,11 @@ class FlatActors:
     item_pos: np.ndarray    # f64
     route_off: Optional[np.ndarray] = None   # i64 [n_agenda_items+1]
     route_lane: Optional[np.ndarray] = None  # i32
+    # optional: travel-to destinations resolved by the generator (griddy_set_agenda_destinations), per agenda item
+    dest_lane: Optional[np.ndarray] = None   # i32 get-outer-lane of (item_seg, item_side)
+    dest_dir: Optional[np.ndarray] = None    # u8  that lane's direction
+    dest_from_j: Optional[np.ndarray] = None # i32 junction it leaves (grid routing)
+    dest_to_j: Optional[np.ndarray] = None   # i32 junction it reaches
 
     def __post_init__(self):
         self.loc_kind = _arr(self.loc_kind, np.uint8)
@@ -108,6 +152,11 @@ class FlatActors:
         if self.route_off is not None:
             self.route_off = _arr(self.route_off, np.int64)
             self.route_lane = _arr(self.route_lane if self.route_lane is not None else [], np.int32)
+        if self.dest_lane is not None:
+            self.dest_lane = _arr(self.dest_lane, np.int32)
+            self.dest_dir = _arr(self.dest_dir, np.uint8)
+            self.dest_from_j = _arr(self.dest_from_j, np.int32)
+            self.dest_to_j = _arr(self.dest_to_j, np.int32)
 
     @property
     def n(self) -> int:

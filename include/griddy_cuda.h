@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GRIDDY_ABI_VERSION 4
+#define GRIDDY_ABI_VERSION 5
 
 enum {
   GRIDDY_OK = 0,
@@ -73,6 +73,20 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
                           const int32_t* lane_out, const int32_t* lane_junction,
                           const int32_t* seg_outer_forw, const int32_t* seg_outer_back);
 
+/* Optional, before griddy_upload_network: this context holds only PART of the network (one rank's tile of
+ * a partitioned world plus the ring of items next to it): the items whose registration index lies in one
+ * of the n_ranges half-open ranges [range_beg[k], range_end[k]) — ascending, disjoint, at most 64.  Every
+ * per-item array that crosses this ABI afterwards (griddy_upload_network, griddy_set_locality_keys,
+ * griddy_set_routing_grid, griddy_upload_geometry, griddy_mg_configure, griddy_download_occupancy) is then
+ * COMPACT: one entry per held item, the ranges back to back; n_items of griddy_upload_network is their
+ * total length.  The ids INSIDE the arrays (lane_segment, lane_out, turn4, containers, ...) stay global
+ * registration indices.  On the device the per-item arrays keep the global index space (virtual address
+ * space for every id, memory mapped behind the held ranges only), so the kernels are the same.
+ * A tiled context cannot resolve a travel-to destination that lies outside its tile: pass the destinations
+ * with griddy_set_agenda_destinations.  n_ranges = 0 returns to an untiled network. */
+int griddy_set_item_ranges(void* ctx, int64_t n_items_global, int32_t n_ranges, const int64_t* range_beg,
+                           const int64_t* range_end);
+
 /* Optional.  Actors are kept in device "slots" that are re-sorted every few ticks by (locality key
  * of their lane or segment, pos-param) so that neighbours on the road are neighbours in memory.
  * item_key[n_items] gives each item's place in that order (items that are close on the map should
@@ -107,6 +121,15 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
                          const int32_t* item_sleep, const int32_t* item_seg, const uint8_t* item_side,
                          const double* item_pos, const int64_t* route_off, const int32_t* route_lane);
 
+/* Optional, before griddy_upload_actors: the destination of every agenda item resolved by the caller, as
+ * begin-route$ would (simulate.scm:80-85 -> off-road->on-road, location.scm:49-57): dest_lane = get-outer-lane of
+ * (item_seg, item_side) (location.scm:16-24; -1: the road has no lanes there), dest_dir that lane's direction,
+ * dest_from_j / dest_to_j the junctions it leaves and reaches (grid routing table; may be NULL).  Entries of
+ * sleep-for items are ignored.  Without this call the library resolves them from the uploaded network, which
+ * needs every destination segment to be held by this context. */
+int griddy_set_agenda_destinations(void* ctx, int64_t n_agenda_items, const int32_t* dest_lane,
+                                   const uint8_t* dest_dir, const int32_t* dest_from_j, const int32_t* dest_to_j);
+
 /* Advance the world n_ticks ticks: the body of `update`, simulate.scm:144-151, n_ticks times. */
 int griddy_step(void* ctx, int64_t n_ticks);
 
@@ -120,8 +143,9 @@ int griddy_download_actors(void* ctx, uint8_t* alive, uint8_t* loc_kind, int32_t
                            uint8_t* route_status, int32_t* route_head, int32_t* order,
                            int64_t* n_order);
 
-/* Actors per container (n_items entries; lanes and segments) and per junction (sum over its
- * junction lanes — the quantity junction-full? tests, route.scm:98-104). */
+/* Actors per container (one entry per held item — n_items of griddy_upload_network; lanes and segments) and
+ * per junction (sum over its junction lanes — the quantity junction-full? tests, route.scm:98-104).
+ * Counted on the device. */
 int griddy_download_occupancy(void* ctx, int32_t* lane_count, int32_t* junction_count);
 
 /* ---- Drawing read-back: (get-pos actor) of every actor, computed on the device --------------------
@@ -162,43 +186,54 @@ void griddy_host_free(void* ptr);
  * while it turns from one lane onto another (route.scm:92-135).  Each tick the ranks exchange (1) the
  * halo: for every lane a neighbour's actors can enter, its rearmost positive pos-param
  * (route.scm:118-121), and for every such junction its occupancy (route.scm:98-104), both of the OLD
- * world; (2) the actors that crossed, as fixed-size records.  Results are identical to a single-GPU
- * run of the same world.  Requires the grid routing table; a migrating actor carries at most 4 agenda
- * items.
+ * world; (2) the actors that crossed, each as a 128-byte record plus its agenda items not yet popped
+ * (32 bytes each; any number).  Results are identical to a single-GPU run of the same world.  Requires
+ * the grid routing table.
  *
- * Order of calls on every rank: griddy_upload_network, griddy_set_routing_grid, griddy_mg_configure,
- * griddy_upload_actors (only the actors on this rank's items, in ascending global id),
- * griddy_mg_set_global_ids, then one of the two transports:
- *   griddy_mg_connect_nccl  one process per GPU (torchrun): rank 0 calls griddy_mg_nccl_unique_id and
- *                           broadcasts the 128 bytes; afterwards every rank calls griddy_step with the
- *                           same n_ticks, and the exchanges are grouped ncclSend/ncclRecv on the
- *                           context's stream (NVLink / NVSwitch inside a box);
- *   griddy_mg_connect_local all ranks are contexts of ONE process (tests; works on a single GPU too):
- *                           griddy_mg_step_local drives them tick by tick with device-to-device copies.
+ * Data plane: every rank owns a WINDOW of device memory that its neighbours' kernels write into directly
+ * (peer stores over NVLink / NVSwitch) and then flag; the reader's next kernel waits for the flag.  No
+ * message, no collective and no host work per tick — NCCL is not involved.  Needs peer access between the
+ * GPUs of the box.
+ *
+ * Order of calls on every rank: [griddy_set_item_ranges,] griddy_upload_network, griddy_set_routing_grid,
+ * griddy_mg_configure, [griddy_set_agenda_destinations,] griddy_upload_actors (only the actors on this
+ * rank's items, in ascending global id), griddy_mg_set_global_ids, then one of the two ways to connect:
+ *   one process per GPU (torchrun): every rank calls griddy_mg_ipc_export for each of its neighbours
+ *       (griddy_mg_neighbors), the 128-byte blobs are exchanged by any means (torch.distributed, MPI, a
+ *       file), every rank calls griddy_mg_ipc_import with what each neighbour exported FOR IT; after a
+ *       barrier every rank calls griddy_step with the same n_ticks;
+ *   griddy_mg_connect_local: all ranks are contexts of ONE process (tests; works on a single GPU too) and
+ *       griddy_mg_step_local drives them tick by tick, ordering the ranks' streams with events.
  * Read back with griddy_download_local. */
-int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* owner /* n_items */,
-                        const int32_t* lane_in /* n_items: junction lanes: their input segment lane */,
+int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* owner /* one per held item */,
+                        const int32_t* lane_in /* one per held item: junction lanes: their input segment lane */,
                         int32_t mig_cap /* ceiling on boundary crossings per neighbour per tick; the exchange is
                                             sized by min(mig_cap, lanes that lead across), which crossings cannot exceed */,
-                        int64_t extra_slots /* room for actors that arrive from other ranks */);
+                        int64_t extra_slots /* room for actors that arrive from other ranks */,
+                        int32_t max_agenda_items /* sizes the room for migrants' agenda items: records per tick x this */);
 int griddy_mg_set_global_ids(void* ctx, const int32_t* gid /* one per uploaded actor, ascending */);
-int griddy_mg_nccl_unique_id(uint8_t* out128);
-int griddy_mg_connect_nccl(void* ctx, const uint8_t* id128);
-/* NCCL transport only: the actors that cross are written by the sender's kernel straight into the
- * receiver's memory (peer access over NVLink), so every rank hands each neighbour the cudaIpc handles
- * of the buffers it receives in (2 x 64 bytes), after griddy_mg_configure and before the first step.  Nothing else follows the records: the sender raises a flag in the receiver's buffer. */
 int griddy_mg_neighbors(void* ctx, int32_t* ranks /* MAX 8, may be NULL */, int32_t* n);
-int griddy_mg_ipc_export(void* ctx, int32_t from_rank, uint8_t* handles128);
-int griddy_mg_ipc_import(void* ctx, int32_t to_rank, const uint8_t* handles128);
+/* blob128: the cudaIpc handle of my window (64 bytes), the byte offsets of the six places `from_rank` writes in it
+ * (int64: halo values, halo flag, migrant area; by tick parity) and the sizes I expect of it (2 x int32). */
+int griddy_mg_ipc_export(void* ctx, int32_t from_rank, uint8_t* blob128);
+int griddy_mg_ipc_import(void* ctx, int32_t to_rank, const uint8_t* blob128);
 int griddy_mg_connect_local(void** ctxs, int32_t n);
 int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks);
-/* Host-only helper (no GPU needed): the items of owner_rank that actors on reader_rank read before
- * crossing — lanes they can enter, junctions whose occupancy gates them — ascending.  Pass NULL
- * arrays to get the counts.  Both sides derive identical lists, so none is ever exchanged. */
+/* Host-only helper (no GPU needed; arrays over ALL items): the items of owner_rank that actors on
+ * reader_rank read before crossing — lanes they can enter, junctions whose occupancy gates them —
+ * ascending.  Pass NULL arrays to get the counts.  Both sides derive identical lists, so none is ever exchanged. */
 int griddy_mg_plan(int64_t n_items, const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out,
                    const int32_t* lane_junction, const int32_t* owner, int32_t owner_rank,
                    int32_t reader_rank, int32_t* lanes, int64_t* n_lanes, int32_t* junctions,
                    int64_t* n_junctions);
+/* The same from ONE rank's tile (compact arrays over the id ranges it holds, as for griddy_set_item_ranges): what
+ * griddy_mg_configure derives on a tiled network.  Owner and reader each see everything next to their own part, so
+ * both get the list the whole network gives.  *n_feeders (may be NULL): lanes of owner_rank with a successor on
+ * reader_rank — the most actors that can cross that way in one tick, which sizes the migrant area. */
+int griddy_mg_plan_tile(int64_t n_items_global, int32_t n_ranges, const int64_t* range_beg, const int64_t* range_end,
+                        const uint8_t* kind, const int32_t* lane_in, const int32_t* lane_out,
+                        const int32_t* lane_junction, const int32_t* owner, int32_t owner_rank, int32_t reader_rank,
+                        int32_t* lanes, int64_t* n_lanes, int32_t* junctions, int64_t* n_junctions, int64_t* n_feeders);
 /* Read back this rank's actors: arrays of `capacity` >= griddy_slots_in_use entries, indexed by slot;
  * gid = the actor's global id; alive = 0 for slots whose actor vanished or left for another rank;
  * order = slot numbers in get-actors order of this rank's containers (a container is owned by one
@@ -234,7 +269,7 @@ int griddy_debug_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int32_t k
 /* Diagnostics, builds with -DGRIDDY_TRACE only (BAD_STATE otherwise): %globaltimer stamps (ns) of the last 64
  * ticks, 16 per tick (row = tick mod 64): starts of k_advance, k_slow, k_unlink, k_link, k_halo_pack,
  * k_halo_unpack, the emigrant packing, the moment its flags are raised, start of k_immig_unpack, the moment the last
- * neighbour's flag was seen; the rest unused.  How the multi-GPU timeline in profiles/ was obtained. */
+ * neighbour's flag was seen; the rest unused.  How the multi-GPU timelines in profiles/ were obtained. */
 int griddy_debug_trace(void* ctx, uint64_t* stamps /* 64 x 16 */);
 
 #ifdef __cplusplus

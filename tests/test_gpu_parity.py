@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import examples
-from griddy_b200 import core, device
+from griddy_b200 import core, device, digest
 from griddy_b200.flat import FlatActors
 from helpers import compare, crowded_grid, grid_flat, simple_flat, triangle_flat, world_to_flat
 from oracle.oracle import Oracle
@@ -211,16 +211,22 @@ def test_default_locality_keys_without_grid():
         compare(sim, ref, f"tick {t + 1}")
 
 
-@pytest.mark.parametrize("world,n,n_actors,strips", [(2, 6, 2500, 1), (4, 8, 4000, 1), (3, 5, 600, 1), (3, 9, 3000, 2),
-                                                     (2, 8, 3000, 4)])
-def test_partitioned_world_matches_oracle(world, n, n_actors, strips):
-    """The multi-GPU path (spatial partition, halo + migrant exchange every tick) with all ranks as
-    contexts of this process: state, order and population identical to the oracle's single world."""
+@pytest.mark.parametrize("world,n,n_actors,strips,tiled", [(2, 6, 2500, 1, False), (4, 8, 4000, 1, False), (3, 5, 600, 1, False),
+                                                           (3, 9, 3000, 2, False), (2, 8, 3000, 4, False),
+                                                           (2, 8, 2500, 1, True), (4, 12, 6000, 1, True), (3, 12, 5000, 2, True)])
+def test_partitioned_world_matches_oracle(world, n, n_actors, strips, tiled):
+    """The multi-GPU path (spatial partition, halo + migrant hand-over every tick) with all ranks as
+    contexts of this process: state, order and population identical to the oracle's single world.
+    tiled: every rank uploads only its own rows of the network plus the ring next to them."""
     from griddy_b200 import synth
     net, actors = crowded_grid(n, n_actors, n_dest=max(4, n), seed=31 + world, agenda_len=4)
     owner = synth.grid_owner(net, world, strips)   # strips > 1: interleaved strips, every rank borders every other
     assert len(set(owner.tolist())) == world
-    sim = device.PartitionedSimulation(net, actors, owner, world, reorder_period=5)
+    tiles = [synth.tile_ranges(n, *synth.tile_rows(n, world, strips, r)) for r in range(world)] if tiled else None
+    if tiled:
+        held = [int((e - b).sum()) for b, e in tiles]
+        assert max(held) < net.n_items, "every rank holds the whole network: nothing is tiled"
+    sim = device.PartitionedSimulation(net, actors, owner, world, reorder_period=5, tiles=tiles)
     ref = Oracle(net, actors)
     moved = 0
     for t in range(400):
@@ -233,18 +239,55 @@ def test_partitioned_world_matches_oracle(world, n, n_actors, strips):
         moved += int((owner[ds.container[m]] != owner[actors.container[m]]).sum() > 0)
     assert moved > 0, "no actor ever crossed a partition boundary"
     assert ref.vanished > 0
+    assert digest.combine([r.digest() for r in sim.ranks]) == digest.commutative(os_)
+    if tiled:   # occupancy of a tile: compact, this rank's items only
+        ol, oj = ref.occupancy()
+        for r, s_ in enumerate(sim.ranks):
+            idx = np.concatenate([np.arange(b, e) for b, e in zip(*tiles[r])])
+            own = s_.net.owner == r
+            dl, dj = s_.occupancy()
+            assert np.array_equal(dl[own], ol[idx][own]) and np.array_equal(dj[own], oj[idx][own]), f"rank {r}: tile occupancy differs"
 
 
-def test_partitioned_world_over_nccl():
-    """The NCCL transport (one process per GPU, grouped ncclSend/ncclRecv each tick) against the oracle.
-    Needs two GPUs; the single-GPU suite covers the same kernels through the in-process transport."""
+def test_migrants_do_not_exhaust_slots_or_the_agenda_pool():
+    """Actors that cross ranks again and again take a fresh slot and fresh room for their agenda items at every
+    arrival; a reorder gives both back.  Far more cumulative arrivals than extra_slots (and long agendas, of which
+    only the items not yet popped travel) must therefore run without an overflow, and stay equal to the oracle."""
+    from griddy_b200 import synth
+    net, actors = crowded_grid(6, 1500, n_dest=6, seed=5, agenda_len=12, max_sleep=3)
+    owner = synth.grid_owner(net, 2, 3)   # six strips: an actor crosses often
+    sim = device.PartitionedSimulation(net, actors, owner, 2, reorder_period=8, extra_slots=700)
+    ref = Oracle(net, actors)
+    arrivals = 0
+    for k in range(40):
+        before = [s_.slots_in_use for s_ in sim.ranks]
+        sim.step(50); ref.step(50)
+        ds, os_ = sim.state(), ref.state()
+        assert not ds.diff(os_), f"tick {50 * (k + 1)}"
+        arrivals += sum(max(0, s_.slots_in_use - b) for s_, b in zip(sim.ranks, before))
+    assert ref.vanished < actors.n
+
+
+def run_ipc_check(world, *extra, gpus_needed=1, timeout=900):
     import subprocess
     import sys
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    if torch.cuda.device_count() < gpus_needed:
+        pytest.skip(f"needs {gpus_needed} GPUs (run with gpurun --gpus {gpus_needed})")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mg_nccl_check.py")],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "mg_nccl_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", str(29517 + world),
+                        os.path.join(root, "tests", "mg_ipc_check.py"), *extra],
+                       capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0 and "mg_ipc_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_partitioned_world_over_ipc_windows_sharing_one_gpu():
+    """The production transport — one process per rank, windows shared through cudaIpc, flags between kernels of
+    DIFFERENT processes — on whatever GPUs the box has: with one GPU the ranks share it (time-sliced)."""
+    run_ipc_check(2, "--grid", "8", "--actors", "4000", "--ticks", "100", "--every", "25", "--tiled")
+
+
+def test_partitioned_world_over_ipc_windows_two_gpus():
+    """Two ranks on two GPUs (NVLink peer stores), interleaved strips, tiled network, against the oracle."""
+    run_ipc_check(2, "--strips", "2", "--tiled", gpus_needed=2)
