@@ -10,22 +10,31 @@ run out and the actors are on the road, which is the expensive phase of the upda
 
   value     device-timed throughput, state resident in HBM (CUDA events around griddy_step)
   e2e       the same metric through the C ABI with host buffers, as the reference's game loop runs it:
-            every step is one `update` (griddy_step(1)) and one `draw` read-back — (get-pos actor) of every
-            actor (simulate.scm:155-160 -> draw.scm:74-88 -> spatial.scm:125-149) computed on the device
-            and copied into pinned host memory, 8 bytes per slot, the copy of frame t in flight while tick
-            t+1 runs (griddy_positions_begin / _end).  e2e_full_state: the round-1 definition, the whole
-            per-actor state (15 bytes per actor) fetched synchronously after every tick
-  roofline  k_advance against the measured HBM copy bandwidth, 80 algorithmic bytes per actor-update
-            (SURVEY 8(d)), timed with per-kernel CUDA events (griddy_profile_step)
+            every step is one `update` and one `draw` read-back — (get-pos actor) of every actor
+            (simulate.scm:155-160 -> draw.scm:74-88 -> spatial.scm:125-149) computed on the device and
+            copied into pinned host memory, 8 bytes per slot, the copy of frame t in flight while tick
+            t+1 runs (griddy_positions_begin / _end)
+  roofline  the whole tick against the measured HBM copy bandwidth, 80 algorithmic bytes per actor-update
+            (SURVEY 8(d)); per-kernel times from CUDA events (griddy_profile_step); the cost of a reorder of
+            the slots is measured separately and given amortised over its period
+  state_digest  partition-independent digest of the world right after the timed region (griddy_state_digest),
+            with the oracle's digest of the same world at the same tick where tests/golden/scale_digests.json has it
   cpu_baseline / --impl reference   the CPU oracle (C++ restatement of the reference; Guile is not in
-            this image) on one host core, on a bounded sample with the same actors per segment
+            this image) on one host core, on a bounded sample of the same workload: the same actors per
+            junction on a 256x256 grid
 
 Launch: python bench.py --gpus N --steps K --warmup W  (N>1 under torchrun, one rank per GPU).
+N > 1: ONE world partitioned into horizontal strips of junction rows; every rank generates, uploads and holds only
+its own rows of the network plus the ring next to them.  Default: weak scaling (N x --actors actors on a
+round(--grid * sqrt(N))^2 grid).  --same-world: the --grid / --actors world itself on N GPUs (strong scaling;
+BASELINE configs[3] "1 vs 2 B200").  --world-grid / --world-actors: any one world, e.g. configs[4]:
+--gpus 8 --world-grid 4096 --world-actors 100000000.
 """
 import argparse
 import json
 import math
 import os
+import resource
 import sys
 import threading
 import time
@@ -93,130 +102,144 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def build_world(grid, n_actors, agenda_len, seed_offset=0, geometry=False):
-    from griddy_b200 import synth
-    t0 = time.time()
-    net = synth.grid_network(grid, geometry=geometry)
-    actors = synth.grid_actors(net, n_actors, seed=synth.DEFAULT_SEED + seed_offset, agenda_len=agenda_len)
-    log(f"[bench] generated {grid}x{grid} grid ({net.n_items} items), {n_actors} actors in {time.time() - t0:.1f}s")
-    return net, actors
+# ---- CPU legs: the oracle (test infrastructure) as the reference's stand-in ---------------------------------
+def cpu_sample_shape(args):
+    """Bounded CPU sample of the workload: the same actors per junction on a --cpu-grid^2 grid."""
+    n = max(1, int(round(args.actors * (args.cpu_grid * args.cpu_grid) / (args.grid * args.grid))))
+    return args.cpu_grid, n
 
 
 def cpu_sample_world(args, seed_offset=0):
-    """Bounded CPU sample: a 64x64 grid with the same actors per segment and agenda shape."""
     from griddy_b200 import synth
-    sz_full, sz = synth.grid_sizes(args.grid), synth.grid_sizes(args.cpu_grid)
-    n = max(1, int(round(args.actors * sz["n_segments"] / sz_full["n_segments"])))
-    net, actors = build_world(args.cpu_grid, n, args.agenda_len, seed_offset=seed_offset)
+    grid, n = cpu_sample_shape(args)
+    t0 = time.time()
+    net = synth.grid_network(grid)
+    actors = synth.grid_actors(net, n, seed=synth.DEFAULT_SEED + seed_offset, agenda_len=args.agenda_len)
+    log(f"[bench] CPU sample: {grid}x{grid} grid ({net.n_items} items), {n} actors generated in {time.time() - t0:.1f}s")
     return net, actors, n
 
 
-def time_oracle(args, ticks, seed_offset=0):
+def time_oracle_world(net, actors, spinup, ticks):
     """Living-actor updates per second of the oracle (vanished actors are not advanced, core.scm:173-178)."""
     from oracle.oracle import Oracle
-    net, actors, n = cpu_sample_world(args, seed_offset)
     o = Oracle(net, actors)
-    o.step(args.spinup)
+    o.step(spinup)
     a0 = int(o.state().alive.sum())
     t0 = time.perf_counter()
     o.step(ticks)
     dt = time.perf_counter() - t0
     a1 = int(o.state().alive.sum())
-    return 0.5 * (a0 + a1) * ticks / dt, dt, n, a1
+    return 0.5 * (a0 + a1) * ticks / dt, dt, a1
 
 
-def time_oracle_all_cores(args, ticks):
-    """The same sample on every host core at once: independent replicas of the single-threaded loop (different
-    actors each), one process per core.  The reference cannot use more than one core for one world
-    (readme.md:23-26); this is what the box's CPUs deliver in total, for scale."""
-    import subprocess
-    cores = len(os.sched_getaffinity(0))
-    cmd = [sys.executable, os.path.abspath(__file__), "--grid", str(args.grid), "--actors", str(args.actors),
-           "--agenda-len", str(args.agenda_len), "--spinup", str(args.spinup), "--cpu-grid", str(args.cpu_grid),
-           "--cpu-ticks", str(ticks)]
-    procs = [subprocess.Popen(cmd + ["--oracle-worker", str(k + 1)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-             for k in range(cores)]
-    updates, slowest = 0.0, 0.0
-    for pr in procs:
-        out, _ = pr.communicate(timeout=600)
-        r = json.loads(out.strip().splitlines()[-1])
-        updates += r["updates"]
-        slowest = max(slowest, r["seconds"])
-    return updates / slowest, slowest, cores
+def cpu_size_table(args):
+    """The oracle at the sizes BASELINE.md names: the reference's two shipped single-actor examples and a 64x64 grid
+    (the cpu_baseline itself is 256x256 / 1M).  Single-threaded, like the reference (readme.md:23-26)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from griddy_b200 import synth
+    rows = []
+    try:
+        import helpers   # tests/helpers.py: the reference's examples/simple.scm and triangle.scm through the API mirror
+        for name, flat, ticks in (("C1 examples/simple.scm", helpers.simple_flat, 20000),
+                                  ("C2 examples/triangle.scm", helpers.triangle_flat, 20000)):
+            net, actors = flat()
+            v, dt, _ = time_oracle_world(net, actors, 0, ticks)
+            rows.append({"config": name, "items": net.n_items, "actors": actors.n, "ticks": ticks, "actor_updates_per_s": v,
+                         "ticks_per_s": ticks / dt})
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] C1/C2 CPU legs skipped: {e!r}")
+    n64 = max(1, int(round(args.actors * 64 * 64 / (args.grid * args.grid))))
+    net = synth.grid_network(64)
+    actors = synth.grid_actors(net, n64, agenda_len=args.agenda_len)
+    v, dt, _ = time_oracle_world(net, actors, args.spinup, 400)
+    rows.append({"config": "64x64 grid, same actors per junction", "items": net.n_items, "actors": n64, "ticks": 400,
+                 "actor_updates_per_s": v, "ticks_per_s": 400 / dt})
+    return rows
+
+
+def sample_text(args, n, extra=""):
+    grid, _ = cpu_sample_shape(args)
+    return (f"{grid}x{grid} grid, {n} actors — the {args.grid}x{args.grid}/{args.actors} workload's actors per junction — "
+            f"{args.agenda_len}-item agendas, after {args.spinup} spin-up ticks{extra}; C++ restatement of the reference "
+            f"(oracle/), not Guile, on 1 of {os.cpu_count()} host cores: the reference is single-threaded (readme.md:23-26)")
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path.  Guile + Chickadee are not installed (and cannot be:
-    no network), so this is the C++ oracle port, single-threaded like the reference (readme.md:23-26)."""
+    no network), so this is the C++ oracle port, single-threaded like the reference (readme.md:23-26).
+    A step is one tick of the bounded sample world; config says what was run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # size the per-step sample so the whole run stays within a couple of minutes
-    ticks_per_step = 10
-    for _ in range(args.warmup):
-        pass
+    import __graft_entry__ as entry
+    entry.build()
     from oracle.oracle import Oracle
     net, actors, n = cpu_sample_world(args)
+    grid, _ = cpu_sample_shape(args)
     o = Oracle(net, actors)
     o.step(args.spinup)
-    o.step(args.warmup * ticks_per_step)
-    steps = min(args.steps, 50)
+    o.step(args.warmup)
     a0 = int(o.state().alive.sum())
     t0 = time.perf_counter()
-    o.step(steps * ticks_per_step)
+    o.step(args.steps)
     dt = time.perf_counter() - t0
     a1 = int(o.state().alive.sum())
-    value = 0.5 * (a0 + a1) * steps * ticks_per_step / dt   # living actors only
-    sample = (f"{args.cpu_grid}x{args.cpu_grid} grid, {n} actors (same actors per segment as the "
-              f"{args.grid}x{args.grid}/{args.actors} workload), {ticks_per_step} ticks per step after "
-              f"{args.spinup} spin-up ticks; C++ restatement of the reference, not Guile")
+    value = 0.5 * (a0 + a1) * args.steps / dt   # living actors only
+    sample = sample_text(args, n, f", {args.steps} ticks timed")
+    cfg = {"workload": f"synthetic {grid}x{grid} procedural grid, {n} actors, {args.agenda_len}-item sleep-for/travel-to agendas, "
+                       f"grid routing table, {args.spinup} spin-up ticks — a bounded sample of the {args.grid}x{args.grid} / "
+                       f"{args.actors}-actor workload of the GPU arm (same actors per junction)",
+           "grid": grid, "actors": n, "agenda_len": args.agenda_len, "spinup_ticks": args.spinup,
+           "sample_of": {"grid": args.grid, "actors": args.actors}, "parallelism": "1 host thread"}
     print(json.dumps({
         "impl": "reference", "metric": "actor-updates/sec", "value": value, "unit": "actor-updates/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args),
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": "actor-updates/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "actor-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
+# ---- the world of the GPU arm ------------------------------------------------------------------------------
 def world_shape(args, world):
-    """Weak scaling: every GPU gets args.grid^2 junctions and args.actors actors of ONE world whose
-    junction grid is square, n = round(args.grid * sqrt(world)).  The static network is replicated
-    on every rank, so the tile is shrunk if the box's host memory could not hold `world` copies."""
-    per_gpu = args.grid
-    note = None
-    while world > 1:
-        n = int(round(per_gpu * math.sqrt(world)))
-        need = world * 30 * n * n * 170          # ~30 items per junction, ~100 host bytes per item + 64 of geometry
-        try:
-            avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
-        except Exception:  # noqa: BLE001
-            avail = None
-        if avail is None or need < 0.5 * avail or per_gpu <= 128:
-            break
-        per_gpu //= 2
-        note = f"tile shrunk to {per_gpu}^2 junctions per GPU: host memory ({avail >> 30} GiB) cannot hold {world} network replicas"
-    n = int(round(per_gpu * math.sqrt(world))) if world > 1 else args.grid
-    actors = args.actors * (per_gpu * per_gpu) // (args.grid * args.grid)
-    return n, actors * world, note
+    """(grid n, total actors, scaling) of the ONE world that `world` GPUs share."""
+    if args.world_grid:
+        return args.world_grid, args.world_actors or args.actors * world, "strong"
+    if args.same_world or world == 1:
+        return args.grid, args.actors, ("strong" if world > 1 else "weak")
+    return int(round(args.grid * math.sqrt(world))), args.actors * world, "weak"
 
 
-def workload_config(args, world=None):
-    world = world or args.gpus
-    n, total, note = world_shape(args, world)
+def workload_config(args, world):
+    n, total, _ = world_shape(args, world)
     cfg = {"workload": f"synthetic {n}x{n} procedural grid, {total} actors, "
                        f"{args.agenda_len}-item sleep-for/travel-to agendas, grid routing table, "
                        f"{args.spinup} spin-up ticks",
            "grid": n, "actors": total, "actors_per_gpu": total // world, "agenda_len": args.agenda_len,
            "spinup_ticks": args.spinup, "l2": "working set per tick >> 126 MB L2 (no flush needed)",
-           "parallelism": (f"{world} ranks, {world * args.strips_per_rank} horizontal strips of junction rows of one world dealt "
-                           f"to the ranks in turn; per tick the halo "
-                           f"(boundary lanes' rearmost pos-param, boundary junctions' occupancy) and the actors that "
-                           f"crossed are exchanged with grouped ncclSend/ncclRecv" if world > 1 else "1 gpu")}
-    if note:
-        cfg["note"] = note
+           "parallelism": (f"{world} ranks, {world * args.strips_per_rank} horizontal strips of junction rows of ONE world dealt to "
+                           f"the ranks in turn; every rank holds only its rows of the network and the ring next to them. "
+                           f"Data plane: peer memory — per tick the halo (boundary lanes' rearmost pos-param, boundary "
+                           f"junctions' occupancy) and the actors that crossed are written by the sender's kernels straight "
+                           f"into the neighbour's window over NVLink and flagged; no NCCL call, no message, no host work per "
+                           f"tick (torch.distributed/NCCL only carries the cudaIpc handles at set-up and this script's "
+                           f"barriers)" if world > 1 else "1 gpu")}
     return cfg
+
+
+def golden_digest(args, world, tick):
+    """The oracle's digest of this very world at this tick, if tests/golden/scale_digests.json holds it."""
+    path = os.path.join(ROOT, "tests", "golden", "scale_digests.json")
+    if not os.path.exists(path):
+        return None
+    n, total, _ = world_shape(args, world)
+    with open(path) as f:
+        for entry in json.load(f).values():
+            if (entry["grid"], entry["actors"], entry["agenda_len"]) == (n, total, args.agenda_len):
+                cp = entry["checkpoints"].get(str(tick))
+                return cp["commutative"] if cp else None
+    return None
 
 
 def main():
@@ -231,11 +254,13 @@ def main():
     ap.add_argument("--spinup", type=int, default=300)
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--profile-ticks", type=int, default=50)
-    ap.add_argument("--cpu-grid", type=int, default=64)
-    ap.add_argument("--cpu-ticks", type=int, default=1500)
+    ap.add_argument("--cpu-grid", type=int, default=256)
+    ap.add_argument("--cpu-ticks", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--oracle-worker", type=int, default=0, help=argparse.SUPPRESS)   # one replica of time_oracle_all_cores
     ap.add_argument("--reorder-period", type=int, default=384)
+    ap.add_argument("--same-world", action="store_true", help="multi-GPU: the --grid / --actors world itself on all GPUs (strong scaling)")
+    ap.add_argument("--world-grid", type=int, default=0, help="multi-GPU: junctions per side of the one world (overrides the scaling rule)")
+    ap.add_argument("--world-actors", type=int, default=0, help="multi-GPU: actors of the one world (with --world-grid)")
     ap.add_argument("--strips-per-rank", type=int, default=0,
                     help="multi-GPU: strips of junction rows per rank, dealt in turn (load balance); 0 = 2 beyond two GPUs")
     ap.add_argument("--mig-cap", type=int, default=1 << 24, help="multi-GPU: boundary crossings per neighbour per tick")
@@ -244,12 +269,6 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.strips_per_rank <= 0:   # edge strips drain towards the middle of the grid: give every rank some of both
         args.strips_per_rank = 2 if args.gpus > 2 else 1
-    os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout, which carries the one JSON line
-
-    if args.oracle_worker:
-        v, dt, _, _ = time_oracle(args, args.cpu_ticks, seed_offset=args.oracle_worker)
-        print(json.dumps({"updates": v * dt, "seconds": dt}), flush=True)
-        return
     if args.impl == "reference":
         run_reference(args)
         return
@@ -271,8 +290,11 @@ def main():
         log(f"[bench] rank {rank}: bound to the CPUs next to GPU {local_rank} ({len(os.sched_getaffinity(0))} of {os.cpu_count()})")
     except Exception as e:  # noqa: BLE001
         log(f"[bench] rank {rank}: CPU affinity left alone ({e!r})")
+    real_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        real_stdout = os.dup(1)      # NCCL's banner lines go to fd 1: keep it for the one JSON line, send the rest to stderr
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import __graft_entry__ as entry
@@ -280,24 +302,28 @@ def main():
         entry.build()
     if world > 1:
         dist.barrier()
-    from griddy_b200 import device
+    from griddy_b200 import device, digest, synth
 
-    from griddy_b200 import synth
-    n_grid, total_actors, _ = world_shape(args, world)
+    n_grid, total_actors, scaling = world_shape(args, world)
     t0 = time.time()
     if world == 1:
-        net, actors = build_world(args.grid, args.actors, args.agenda_len, geometry=True)
+        net = synth.grid_network(args.grid, geometry=True)
+        actors = synth.grid_actors(net, args.actors, agenda_len=args.agenda_len)
+        log(f"[bench] generated {args.grid}x{args.grid} grid ({net.n_items} items), {args.actors} actors in {time.time() - t0:.1f}s")
         sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period)
+        n_items_world, held = net.n_items, net.n_items
     else:
-        # ONE world, partitioned into horizontal strips; this rank generates and uploads its own actors
-        net = synth.grid_network(n_grid, geometry=True)
-        owner = synth.grid_owner(net, world, args.strips_per_rank)
-        ids = synth.actor_ids_of_rank(net, total_actors, owner, rank)
-        actors = synth.grid_actors(net, total_actors, agenda_len=args.agenda_len, ids=ids)
-        log(f"[bench] rank {rank}: {n_grid}x{n_grid} grid ({net.n_items} items), {actors.n} of {total_actors} actors "
-            f"generated in {time.time() - t0:.1f}s")
+        # ONE world, partitioned into horizontal strips; this rank generates, uploads and holds only its own rows
+        # of the network (plus the ring next to them) and its own actors
+        rb, re = synth.tile_rows(n_grid, world, args.strips_per_rank, rank)
+        net = synth.grid_tile(n_grid, rb, re, world, args.strips_per_rank, geometry=True)
+        actors, ids = synth.grid_actors_of_rank(n_grid, total_actors, world, args.strips_per_rank, rank, agenda_len=args.agenda_len)
+        n_items_world, held = net.n_global, net.n_items
+        log(f"[bench] rank {rank}: {n_grid}x{n_grid} grid, holding {net.n_items} of {net.n_global} items (rows "
+            f"{list(zip(rb.tolist(), re.tolist()))}), {actors.n} of {total_actors} actors, generated in {time.time() - t0:.1f}s")
         sim = device.Simulation(net, actors, device=local_rank, reorder_period=args.reorder_period,
-                                partition=(rank, world, owner, args.mig_cap, args.extra_slots), gids=ids)
+                                partition=(rank, world, net.owner, args.mig_cap, args.extra_slots), gids=ids,
+                                max_agenda_items=args.agenda_len)
         device.connect_ipc(sim)
     net.geom = None   # on the device now
     log(f"[bench] rank {rank}: uploaded in {time.time() - t0:.1f}s")
@@ -309,9 +335,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
     sim.step(args.warmup)
     alive0 = sim.count_alive()
     launches0 = sim.kernel_launches
+    reorders0 = sim.reorders
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -323,6 +357,13 @@ def main():
     barrier()
     dev_ms = sim.last_step_ms
     launches = sim.kernel_launches - launches0
+    reorders_timed = sim.reorders - reorders0
+    tick_after = sim.tick
+    # outside the timed region: the state the timed ticks produced, as a partition-independent digest
+    state_digest = digest.combine(gather(sim.digest()))
+    want = golden_digest(args, world, tick_after)
+    state_digest.update({"tick": tick_after, "oracle": want, "matches_oracle": (None if want is None else
+                         all(state_digest[k] == want[k] for k in ("sum", "xor", "alive")))})
     if os.environ.get("GRIDDY_DUMP_TRACE"):   # -DGRIDDY_TRACE builds: the last 64 ticks' kernel start stamps
         stamps = np.zeros((64, 16), np.uint64)
         rc = device.lib().griddy_debug_trace(sim.h, stamps.ctypes.data)
@@ -347,14 +388,19 @@ def main():
         alive_total = alive_mean
     value = alive_total * args.steps / (dev_ms * 1e-3)
 
-    # per-kernel device time (events around every launch; rank-local)
+    # per-kernel device time (events around every launch; rank-local), then one forced reorder, timed
     kms = sim.profile_step(args.profile_ticks)
     alive_prof = sim.count_alive()
     kpt = {k: v / args.profile_ticks for k, v in kms.items()}
+    reorder_events = kpt.pop("reorder")   # event overhead unless a reorder fell into the window
     tick_ms_prof = sum(kpt.values())
+    reorder_ms = sim.timed_reorder() if args.reorder_period > 0 else None
     peak, peak_src = measured_peaks()
     gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
-    whole_tick = gbs(alive_mean * ALGO_BYTES_PER_UPDATE, dev_ms / args.steps)
+    tick_ms = dev_ms / args.steps
+    whole_tick = gbs(alive_total / world * ALGO_BYTES_PER_UPDATE, tick_ms)   # per GPU
+    amortised = (gbs(alive_total / world * ALGO_BYTES_PER_UPDATE, tick_ms + reorder_ms / args.reorder_period)
+                 if reorder_ms is not None else whole_tick)
     adv = gbs(alive_prof * ADVANCE_BYTES_PER_ACTOR, kpt["k_advance"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -365,20 +411,19 @@ def main():
     # e2e: what the reference's game loop does per tick — `update`, then `draw` reads (get-pos actor) of
     # every actor.  Frame t is formatted on the device and copied into pinned host memory while tick t+1
     # runs; every frame is complete on the host inside the timed region.
-    import ctypes as C
-    L = device.lib()
     cap = actors.n if world == 1 else actors.n + args.extra_slots
     frames = [device.PinnedFrame(cap), device.PinnedFrame(cap)]
 
     def e2e_loop(steps):
         slots = 0
-        sim.step(1)
+        sim.step_async(1)
         sim.frame_begin(frames[0])
         for k in range(1, steps):
-            sim.step(1)
+            sim.step_async(1)
             sim.frame_begin(frames[k & 1])
             slots += len(sim.frame_end())        # frame k-1 is on the host
         last = sim.frame_end()
+        sim.step(0)                              # the device's error word, checked once per batch of frames
         return slots + len(last), last
 
     e2e_loop(3)
@@ -397,46 +442,8 @@ def main():
         e_dt = float(tmax[0].item())
     alive_e2e_total, d2h_total, living_in_frame = float(t[1].item()), float(t[2].item()), int(t[3].item())
     e2e_value = alive_e2e_total * args.e2e_steps / e_dt
-
-    # the round-1 definition, kept for continuity: the whole per-actor state `draw` could want (alive,
-    # location kind, container, road side, pos-param), fetched synchronously after every tick
-    n = cap
-    pin = lambda dt: torch.empty(n, dtype=dt, pin_memory=True).numpy()
-    bufs = [pin(torch.uint8), pin(torch.uint8), pin(torch.int32), pin(torch.uint8), pin(torch.float64)]
-    ptrs = [b.ctypes.data_as(C.c_void_p) for b in bufs] + [None] * 6
-    gid_buf = pin(torch.int32) if world > 1 else None
-    n_local = C.c_int64(0)
-
-    def full_state_step():
-        sim.step(1)
-        if world == 1:
-            rc = L.griddy_download_actors(sim.h, *ptrs)
-        else:
-            rc = L.griddy_download_local(sim.h, C.c_int64(n), C.byref(n_local), gid_buf.ctypes.data_as(C.c_void_p), *ptrs)
-        assert rc == 0, L.griddy_last_error(sim.h)
-
-    full_steps = max(1, min(args.e2e_steps, 5))
-    full_state_step()
-    barrier()
-    f0 = time.perf_counter()
-    for _ in range(full_steps):
-        full_state_step()
-    torch.cuda.synchronize()
-    f_dt = time.perf_counter() - f0
-    if world > 1:
-        full_bytes = int(n_local.value) * (sum(b.itemsize for b in bufs) + 4)
-        alive = int(bufs[0][: n_local.value].sum())
-        on_road = int((bufs[0][: n_local.value] & bufs[1][: n_local.value]).sum())
-        t = torch.tensor([float(alive), float(full_bytes)], device="cuda", dtype=torch.float64)
-        tm = torch.tensor([f_dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        full_value, full_bytes = float(t[0].item()) * full_steps / float(tm.item()), int(t[1].item())
-    else:
-        full_bytes = sum(b.nbytes for b in bufs)
-        alive = int(bufs[0].sum())
-        on_road = int((bufs[0] & bufs[1]).sum())
-        full_value = alive * full_steps / f_dt
+    rss = gather(round(resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6, 2))
+    held_all = gather(held)
 
     if rank != 0:
         if world > 1:
@@ -444,66 +451,69 @@ def main():
             dist.destroy_process_group()
         return
 
-    cpu = cpu_all = None
+    cpu = sizes = None
     if not args.no_cpu_baseline and world == 1:
-        v, dt, n_cpu, _ = time_oracle(args, args.cpu_ticks)
+        net_c, actors_c, n_cpu = cpu_sample_world(args)
+        v, dt, _ = time_oracle_world(net_c, actors_c, args.spinup, args.cpu_ticks)
         cpu = {"value": v, "unit": "actor-updates/s", "cores": 1, "kind": "port",
-               "sample": f"{args.cpu_grid}x{args.cpu_grid} grid, {n_cpu} actors (same actors per segment), "
-                         f"{args.cpu_ticks} ticks after {args.spinup} spin-up ticks, {dt:.1f}s; C++ restatement "
-                         f"of the reference on 1 of {os.cpu_count()} host cores (the reference is single-threaded; "
-                         f"Guile is not installed)"}
+               "sample": sample_text(args, n_cpu, f", {args.cpu_ticks} ticks timed in {dt:.1f}s")}
         try:
-            va, dta, cores = time_oracle_all_cores(args, max(args.cpu_ticks // 2, 1))
-            cpu_all = {"value": va, "unit": "actor-updates/s", "cores": cores, "kind": "port",
-                       "sample": f"{cores} independent replicas of the same sample (different actors each), one process "
-                                 f"per core, {max(args.cpu_ticks // 2, 1)} ticks after {args.spinup} spin-up ticks, "
-                                 f"{dta:.1f}s; the reference itself is single-threaded, so this is the box's total, not "
-                                 f"one world's speed"}
+            sizes = cpu_size_table(args)
+            sizes.append({"config": f"{args.cpu_grid}x{args.cpu_grid} grid, same actors per junction (the cpu_baseline)",
+                          "actors": n_cpu, "ticks": args.cpu_ticks, "actor_updates_per_s": v, "ticks_per_s": args.cpu_ticks / dt})
         except Exception as e:  # noqa: BLE001  (an extra, never worth losing the line for)
-            log(f"[bench] all-cores CPU leg failed: {e!r}")
+            log(f"[bench] CPU size table failed: {e!r}")
     out = {
         "metric": "actor-updates/sec", "value": value, "unit": "actor-updates/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tick_ms,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": "actor-updates/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": int(d2h_total), "steps": args.e2e_steps,
                 "living_actors_in_last_frame": living_in_frame,
-                "note": "per step: one `update` (griddy_step(1)) + one `draw` read-back: (get-pos actor) of every "
-                        "slot computed on the device (spatial.scm:125-149), float x,y, copied into pinned host memory "
-                        "with griddy_positions_begin/_end — the copy of frame t overlaps tick t+1, every frame is on "
-                        "the host inside the timed region; no per-step input exists: the world is uploaded once "
-                        "through the same ABI before the timed region"},
-        "e2e_full_state": {"value": full_value, "unit": "actor-updates/s", "d2h_bytes_per_step": full_bytes,
-                           "steps": full_steps,
-                           "note": "round-1 definition: griddy_step(1) + synchronous griddy_download_actors of alive, "
-                                   "location kind, container, side, pos-param (15 bytes per actor)"},
+                "note": "per step: one `update` (griddy_step_async(1): no host synchronisation per tick) + one `draw` "
+                        "read-back: (get-pos actor) of every slot computed on the device (spatial.scm:125-149), float x,y, "
+                        "copied into pinned host memory with griddy_positions_begin/_end — the copy of frame t overlaps tick "
+                        "t+1, every frame is on the host inside the timed region; no per-step input exists: the world is "
+                        "uploaded once through the same ABI before the timed region"},
         "gpu_launches": launches,
         "clocks": clocks,
+        "state_digest": state_digest,
         # The tick is four kernels of comparable duration, so the roofline is stated for the whole
         # tick: 80 algorithmic bytes per living actor over the device time of one tick
         # of the timed region.  k_advance, the kernel that streams the per-actor state, is given
         # beside it against its own 44 bytes per actor.
-        "roofline": {"bound": "hbm", "kernel": "whole tick (k_advance + k_slow + k_unlink + k_link + amortised reorder)",
+        "roofline": {"bound": "hbm", "kernel": "whole tick (k_advance + k_slow + k_unlink + k_link), per GPU",
                      "achieved": whole_tick, "peak": peak, "unit": "GB/s", "frac": whole_tick / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_actor_update": ALGO_BYTES_PER_UPDATE,
-                     "living_actors": alive_mean,
+                     "living_actors": alive_total,
+                     "with_amortised_reorder": {"achieved": amortised, "frac": amortised / peak, "reorder_ms": reorder_ms,
+                                                "reorder_period_ticks": args.reorder_period,
+                                                "reorders_in_timed_region": reorders_timed,
+                                                "note": "one reorder of the slots, forced and timed with CUDA events right after "
+                                                        "the profile ticks, spread over its period"},
                      "k_advance": {"algorithmic_bytes_per_actor": ADVANCE_BYTES_PER_ACTOR, "achieved": adv,
                                    "frac": adv / peak if adv else None, "ms": kpt["k_advance"]},
                      "kernel_ms_per_tick": kpt,
                      "kernel_share_of_tick": {k: v / tick_ms_prof for k, v in kpt.items()} if tick_ms_prof else None,
-                     "reorder_period_ticks": args.reorder_period},
+                     "profile_window": {"ticks": args.profile_ticks, "first_tick": tick_after,
+                                        "reorder_events_ms_per_tick": reorder_events}},
         "cpu_baseline": cpu,
-        "cpu_baseline_all_cores": cpu_all,
-        "world": {"alive_before": alive0, "alive_after": alive1, "alive_at_end": alive, "on_road": on_road,
-                  "actors_uploaded": total_actors, "wall_s_timed_region": wall,
+        "cpu_baseline_sizes": sizes,
+        "world": {"alive_before": alive0, "alive_after": alive1, "actors_uploaded": total_actors,
+                  "items_in_world": n_items_world, "items_held_per_rank": held_all, "host_rss_gb_per_rank": rss,
+                  "wall_s_timed_region": wall,
                   "note": "value counts living actors only" + ("; alive_* are rank 0's, per_rank has every rank's: strips "
                           "at the edge of the grid drain towards the middle, and the tick is as long as the fullest rank's"
                           if world > 1 else ""),
                   "per_rank": per_rank},
     }
-    print(json.dumps(out), flush=True)
+    line = json.dumps(out)
+    if real_stdout is not None:
+        os.write(real_stdout, (line + "\n").encode())
+    else:
+        print(line, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -169,12 +169,17 @@ struct Ctx {
   bool have_ranges = false;
   Params p{};
   bool have_net = false, have_actors = false;
-  int64_t tick = 0, launches = 0;
+  int64_t tick = 0, launches = 0, reorders = 0;
   double last_ms = 0.0;
+  int32_t* h_scal = nullptr;        // pinned mirror of Params::scal for griddy_step_async
+  cudaEvent_t ev_scal = nullptr;
+  bool scal_pending = false;
+  int64_t ticks_after_scal = 0;     // ticks enqueued since that copy was: arrivals they may bring are not in it
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // slots
   int32_t ns_host = 0;         // upper bound of the slots in use (refreshed after every step)
+  int32_t dead_host = 0;       // slots whose actor is gone, as of the last step's end
   int reorder_period = 384;
   int64_t last_reorder_tick = -1;
   int loc_key_bits = 1;
@@ -285,6 +290,8 @@ int reorder_slots(Ctx* c, int64_t tick) {
   const int n_pad = n_tiles * rsort::TILE;
   cudaStream_t s = c->stream;
   CUDA_TRY(c, cudaMemsetAsync(&p.scal[SC_NALIVE], 0, sizeof(int32_t), s));
+  CUDA_TRY(c, cudaMemsetAsync(&p.scal[SC_NDEAD], 0, sizeof(int32_t), s));
+  c->dead_host = 0;
   CUDA_TRY(c, cudaMemsetAsync(c->newslot, 0xFF, (size_t)c->ns_host * sizeof(int32_t), s));
   const int key_bits = c->loc_key_bits + 17;   // [off-road][locality key][pos16]
   k_make_keys<<<n_pad / 256, 256, 0, s>>>(p, par, key_bits, c->sort_keys, c->sort_vals, c->tailflag);
@@ -317,6 +324,7 @@ int reorder_slots(Ctx* c, int64_t tick) {
   std::swap(c->coldf_cur, c->coldf_alt);
   bind_slot_arrays(c, par);
   c->last_reorder_tick = tick;
+  ++c->reorders;
   CUDA_TRY(c, cudaGetLastError());
   return GRIDDY_OK;
 }
@@ -582,6 +590,8 @@ int griddy_create(void** ctx, int device) {
   c->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_scal, cudaEventDisableTiming) != cudaSuccess ||
+      cudaHostAlloc((void**)&c->h_scal, SC_COUNT * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
       rsort::prepare() != cudaSuccess) {
     delete c;
     return GRIDDY_ERR_CUDA;
@@ -603,6 +613,8 @@ void griddy_destroy(void* ctx) {
   free_sparse(c);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_scal) cudaEventDestroy(c->ev_scal);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
   for (int f = 0; f < 2; ++f) {
     if (c->ev_drawn[f]) cudaEventDestroy(c->ev_drawn[f]);
     if (c->ev_copied[f]) cudaEventDestroy(c->ev_copied[f]);
@@ -1046,7 +1058,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
 #endif
   CUDA_TRY(c, cudaMemset(p.counters, 0, 2 * CNT_STRIDE * sizeof(int32_t)));
   {
-    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n_agenda};
+    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n_agenda, 0, 0, 0, 0};
     CUDA_TRY(c, cudaMemcpy(p.scal, scal, sizeof(scal), cudaMemcpyHostToDevice));
   }
   // reorder scratch
@@ -1122,11 +1134,10 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
 
 namespace {
 
-// End of a step: device error bits and the slot count, in one copy.
-int finish_step(Ctx* c) {
-  int32_t scal[2] = {0, 0};
-  CUDA_TRY(c, cudaMemcpy(scal, c->p.scal, sizeof(scal), cudaMemcpyDeviceToHost));
-  c->ns_host = scal[SC_NSLOTS];
+// The device's scalars as last read: slot count, dead slots, error bits.
+int take_scalars(Ctx* c, const int32_t* scal) {
+  c->ns_host = std::min(scal[SC_NSLOTS], c->p.cap);
+  c->dead_host = scal[SC_NDEAD];
   const int32_t derr = scal[SC_ERR];
   if (!derr) return GRIDDY_OK;
   std::string m = "advance$:";
@@ -1136,10 +1147,17 @@ int finish_step(Ctx* c) {
   if (derr & DEV_ERR_NO_LANE) m += " road-has-no-lanes;";
   if (derr & DEV_ERR_NO_ROUTE) m += " routing table has no next hop;";
   if (derr & DEV_ERR_INTERNAL) m += " internal: a live actor pointed at a dropped slot;";
-  if (derr & DEV_ERR_MIG_OVERFLOW) m += " multi-GPU: more boundary crossings in one tick than mig_cap, or no slots left for arrivals;";
-  if (derr & DEV_ERR_MIG_AGENDA) m += " multi-GPU: a migrating actor's agenda has more than 4 items;";
-  if (derr & DEV_ERR_MIG_TIMEOUT) m += " multi-GPU: a neighbour never signalled that its migrants of a tick were written;";
+  if (derr & DEV_ERR_MIG_OVERFLOW) m += " multi-GPU: more boundary crossings (or migrating agenda items) in one tick than the window holds, or no slots / agenda room left for arrivals;";
+  if (derr & DEV_ERR_MIG_TIMEOUT) m += " multi-GPU: a neighbour never signalled that its halo or its migrants of a tick were written;";
   return fail(c, GRIDDY_ERR_BAD_STATE, m);
+}
+
+// End of a step: device error bits and the slot count, in one copy.
+int finish_step(Ctx* c) {
+  int32_t scal[SC_COUNT] = {};
+  CUDA_TRY(c, cudaMemcpy(scal, c->p.scal, sizeof(scal), cudaMemcpyDeviceToHost));
+  c->scal_pending = false;
+  return take_scalars(c, scal);
 }
 
 // One tick = four launches on the compute stream (plus a reorder every reorder_period ticks; on a
@@ -1147,7 +1165,10 @@ int finish_step(Ctx* c) {
 // ev (optional) receives 6 events bracketing reorder, k_advance, k_slow, k_unlink, k_link.
 int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   if (ev) cudaEventRecord(ev[0], c->stream);
-  if (c->reorder_period > 0 && tick % c->reorder_period == 0 && tick != c->last_reorder_tick)
+  // Reorder every reorder_period ticks, and — checked wherever a step begins, which is when the host knows
+  // the count — as soon as more than 1/16 of the slots hold actors that are gone: k_advance streams dead slots too.
+  if (c->reorder_period > 0 && tick != c->last_reorder_tick &&
+      (tick % c->reorder_period == 0 || ((int64_t)c->dead_host * 16 > c->ns_host && tick - c->last_reorder_tick >= 16)))
     TRY(reorder_slots(c, tick));
   if (ev) cudaEventRecord(ev[1], c->stream);
   return GRIDDY_OK;
@@ -1308,6 +1329,53 @@ int griddy_step(void* ctx, int64_t n_ticks) {
   CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->last_ms = ms;
   c->tick += n_ticks;
+  return finish_step(c);
+}
+
+int griddy_step_async(void* ctx, int64_t n_ticks) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, "step before upload_actors");
+  if (n_ticks < 0 || c->tick + n_ticks > INT32_MAX - 2) return fail(c, GRIDDY_ERR_BAD_ARG, "bad n_ticks");
+  if (c->mg.on && (!c->mg.connected || !c->mg.peers.empty()))
+    return fail(c, GRIDDY_ERR_BAD_ARG, "a partitioned world steps with griddy_mg_step_local, or once every neighbour's window is mapped");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  // the scalars an earlier call asked for, if they have landed: slot count and error bits without a wait
+  if (c->scal_pending && cudaEventQuery(c->ev_scal) == cudaSuccess) {
+    c->scal_pending = false;
+    TRY(take_scalars(c, c->h_scal));
+    // the copy is older than the ticks enqueued after it: every one of them may have brought arrivals
+    int64_t per_tick = 0;
+    for (const Neighbor& nb : c->mg.nb) per_tick += nb.mig_in;
+    c->ns_host = (int32_t)std::min<int64_t>(c->p.cap, (int64_t)c->ns_host + per_tick * c->ticks_after_scal);
+  }
+  if (c->ns_host > 0 || c->mg.on)
+    for (int64_t t = 0; t < n_ticks; ++t) TRY(launch_tick(c, c->tick + t, nullptr));
+  c->tick += n_ticks;
+  c->ticks_after_scal += n_ticks;
+  if (!c->scal_pending) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->p.scal, SC_COUNT * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev_scal, c->stream));
+    c->scal_pending = true;
+    c->ticks_after_scal = 0;
+  }
+  return GRIDDY_OK;
+}
+
+int griddy_reorder_now(void* ctx, double* ms) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_actors) return fail(c, GRIDDY_ERR_BAD_ARG, "reorder before upload_actors");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  TRY(finish_step(c));
+  CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+  TRY(reorder_slots(c, c->tick));
+  CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+  CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  float t = 0.f;
+  CUDA_TRY(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  if (ms) *ms = t;
   return finish_step(c);
 }
 
@@ -1890,7 +1958,7 @@ int launch_positions(Ctx* c, double2* xy64, float2* xy32, int32_t* gid) {
   const int par = (int)(c->tick & 1);
   CUDA_TRY(c, cudaMemsetAsync(c->d_ghost, 0, (size_t)ns, c->stream));
   k_flag_ghosts<<<blocks, 256, 0, c->stream>>>(c->p, par, c->d_ghost);
-  k_positions<<<blocks, 256, 0, c->stream>>>(c->p, par, c->d_geom, c->d_ghost, xy64, xy32, gid);
+  k_positions<<<blocks, 256, 0, c->stream>>>(c->p, par, c->d_geom, c->d_ghost, xy64, xy32, gid, (int)ns);
   c->launches += 2;
   CUDA_TRY(c, cudaGetLastError());
   return GRIDDY_OK;
@@ -2071,5 +2139,6 @@ double griddy_last_step_ms(void* ctx) { return ctx ? ((Ctx*)ctx)->last_ms : 0.0;
 int64_t griddy_tick(void* ctx) { return ctx ? ((Ctx*)ctx)->tick : 0; }
 int64_t griddy_kernel_launches(void* ctx) { return ctx ? ((Ctx*)ctx)->launches : 0; }
 int64_t griddy_slots_in_use(void* ctx) { return ctx ? ((Ctx*)ctx)->ns_host : 0; }
+int64_t griddy_reorders(void* ctx) { return ctx ? ((Ctx*)ctx)->reorders : 0; }
 
 }  // extern "C"

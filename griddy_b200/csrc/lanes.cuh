@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128, MG ? 12 : 1) k_unlink(Params p, int tick)
     if (ld.outbox < 0 && ld.ghosts < 0) continue;
     if (ld.outbox >= 0) p.lane[lane].outbox = -1;
     if (ld.ghosts >= 0) p.lane[lane].ghosts = -1;
-    int32_t tail = ld.tail, gone = 0;
+    int32_t tail = ld.tail, gone = 0, died = 0;
     // A ghost that also moved is on both lists; the second visit finds it UNLINKED.
     auto unlink = [&](int32_t z, int32_t b) {
       const int32_t f = p.sa[z].ahead;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128, MG ? 12 : 1) k_unlink(Params p, int tick)
       unlink(z, k.behind);
       ++gone;   // every mover leaves its old lane, whatever becomes of it
       const uint32_t sz = p.sa[z].st;
-      if (k.dead_mark == tick + 1 || (sz & ST_EMIG)) p.sa[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG);
+      if (k.dead_mark == tick + 1 || (sz & ST_EMIG)) { p.sa[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG); ++died; }
       else if (!(sz & ST_ONROAD)) p.sa[z].st = sz & ~ST_MOVED;   // went off the road: nothing to link
       z = k.outbox_next;
     }
@@ -103,11 +103,13 @@ __global__ void __launch_bounds__(128, MG ? 12 : 1) k_unlink(Params p, int tick)
       if (unlink(z, k.behind) && !(sz & ST_MOVED)) {   // (one that also moved was settled above)
         p.sa[z].st = sz & ~ST_ALIVE;
         ++gone;
+        ++died;
       }
       z = k.ghost_next;
     }
     if (tail != ld.tail) p.lane[lane].tail = tail;
     if (ld.junction >= 0 && gone) atomicSub(&p.occ[ld.junction], gone);
+    if (died) atomicAdd(&p.scal[SC_NDEAD], died);   // dead slots pile up until the next reorder drops them
   }
 }
 
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
       p.cold[z].behind = b;
       if (f >= 0) p.cold[f].behind = z;
     };
-    int32_t prev = -1, x = ld.tail, delta = 0;
+    int32_t prev = -1, x = ld.tail, delta = 0, died = 0;
     for (next_entrant(true); e >= 0; next_entrant(false)) {
       while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = p.sa[x].ahead; }
       if (x >= 0 && pos_new[x] == e_pos) {   // equal key: bbtree-set keeps the one processed later
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
         const int32_t lose = e_wins ? x : e;
         const uint32_t sl = p.sa[lose].st;
         p.sa[lose].st = sl & ~ST_ALIVE;        // (still marked moved if it is an entrant: see below)
+        ++died;
         if (!(sl & ST_MOVED) || lose == x) --delta;   // a resident, or an entrant that had been counted in
         if (!e_wins) continue;
         link(prev, e, p.sa[x].ahead);   // e takes x's place
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
       if (sy & ST_MOVED) p.sa[y].st = sy & ~(ST_MOVED | ST_IMMIG);
     }
     if (ld.junction >= 0 && delta) atomicAdd(&p.occ[ld.junction], delta);
+    if (died) atomicAdd(&p.scal[SC_NDEAD], died);
   }
 }
 

@@ -223,9 +223,13 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
     const MigRec r = recs[i];
     const int32_t a = atomicAdd(&p.scal[SC_NSLOTS], 1);
     const int32_t it = atomicAdd(&p.scal[SC_NITEMS], r.n_items);
-    if (a >= p.cap || it + r.n_items > p.icap) {   // no room: give the places back, report, drop the actor
+    if (a >= p.cap) {   // no slot left: give the place back (the count stays a valid loop bound), report, drop the actor
       atomicSub(&p.scal[SC_NSLOTS], 1);
-      atomicSub(&p.scal[SC_NITEMS], r.n_items);
+      dev_error(p, DEV_ERR_MIG_OVERFLOW);
+      continue;
+    }
+    if (it + r.n_items > p.icap) {   // no room for its agenda: the slot stays counted, but dead
+      p.sa[a] = SA{0u, -1};
       dev_error(p, DEV_ERR_MIG_OVERFLOW);
       continue;
     }

@@ -130,14 +130,15 @@ __device__ __forceinline__ double bezier_1d(double w0, double w1, double w2, dou
 
 __global__ void __launch_bounds__(256) k_positions(Params p, int par, const double2* __restrict__ geom,
                                                     const uint8_t* __restrict__ ghost, double2* __restrict__ xy64,
-                                                    float2* __restrict__ xy32, int32_t* __restrict__ gid) {
+                                                    float2* __restrict__ xy32, int32_t* __restrict__ gid, int n_bound) {
   const int a = blockIdx.x * 256 + threadIdx.x;
-  if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.sa[a].st;
+  if (a >= n_bound) return;   // the host's upper bound of the slots in use: what it will copy
+  const bool used = a < p.scal[SC_NSLOTS];
+  const uint32_t st = used ? p.sa[a].st : 0u;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   double x = nan, y = nan;
   int32_t id = -1;
-  if ((st & ST_ALIVE) && !ghost[a]) {
+  if (used && (st & ST_ALIVE) && !ghost[a]) {
     const int32_t c = p.cold[a].container;
     id = p.cold[a].gid;
     const double t = p.pos[par][a];

@@ -51,7 +51,7 @@ __device__ __forceinline__ void grid_dependency_wait() {
 #endif
 }
 // device scalars (Params::scal)
-constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_COUNT = 4;
+constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_NDEAD = 4, SC_COUNT = 8;   // NDEAD: slots whose actor is gone since the last reorder
 constexpr int MAX_RANKS = 8;     // one box
 constexpr int MAX_RANGES = 64;   // id ranges of a tiled network (griddy_set_item_ranges)
 

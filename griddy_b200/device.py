@@ -26,7 +26,8 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_download_occupancy", "griddy_last_step_ms", "griddy_tick", "griddy_kernel_launches",
            "griddy_set_locality_keys", "griddy_set_reorder_period", "griddy_slots_in_use",
            "griddy_debug_sort_pairs", "griddy_count_alive", "griddy_mg_configure", "griddy_mg_set_global_ids",
-           "griddy_set_item_ranges", "griddy_set_agenda_destinations", "griddy_mg_plan_tile", "griddy_mg_connect_local", "griddy_mg_step_local",
+           "griddy_set_item_ranges", "griddy_set_agenda_destinations", "griddy_mg_plan_tile", "griddy_step_async",
+           "griddy_reorder_now", "griddy_reorders", "griddy_mg_connect_local", "griddy_mg_step_local",
            "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
            "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
            "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace", "griddy_state_digest")
@@ -57,6 +58,8 @@ def lib():
         L.griddy_kernel_launches.argtypes = [C.c_void_p]
         L.griddy_slots_in_use.restype = C.c_int64
         L.griddy_slots_in_use.argtypes = [C.c_void_p]
+        L.griddy_reorders.restype = C.c_int64
+        L.griddy_reorders.argtypes = [C.c_void_p]
         L.griddy_destroy.restype = None
         L.griddy_destroy.argtypes = [C.c_void_p]
         L.griddy_host_alloc.restype = C.c_void_p
@@ -140,6 +143,20 @@ class Simulation:
 
     def step(self, n_ticks: int = 1):
         self._chk(lib().griddy_step(self.h, C.c_int64(n_ticks)))
+
+    def step_async(self, n_ticks: int = 1):
+        """Enqueue n_ticks ticks without waiting for the device (griddy_step_async)."""
+        self._chk(lib().griddy_step_async(self.h, C.c_int64(n_ticks)))
+
+    def timed_reorder(self) -> float:
+        """Reorder the slots now; device ms (griddy_reorder_now)."""
+        ms = C.c_double(0.0)
+        self._chk(lib().griddy_reorder_now(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def reorders(self) -> int:
+        return int(lib().griddy_reorders(self.h))
 
     def profile_step(self, n_ticks: int = 1) -> dict:
         """Per-kernel device ms summed over n_ticks (events around every launch)."""

@@ -94,8 +94,12 @@ int griddy_set_item_ranges(void* ctx, int64_t n_items_global, int32_t n_ranges, 
  * not depend on it.  Call after griddy_upload_network and before griddy_upload_actors. */
 int griddy_set_locality_keys(void* ctx, const uint32_t* item_key);
 
-/* Ticks between two reorders of the actor slots (default 384; 0 = never).  Performance only. */
+/* Ticks between two reorders of the actor slots (default 384; 0 = never).  Performance only.  With a period set,
+ * a step also begins with a reorder when more than 1/16 of the slots hold actors that are gone. */
 int griddy_set_reorder_period(void* ctx, int32_t ticks);
+/* Reorder the slots now (between steps); *ms (may be NULL) receives its device time (CUDA events). */
+int griddy_reorder_now(void* ctx, double* ms);
+int64_t griddy_reorders(void* ctx);          /* reorders run so far */
 
 /* Device-side routing table for procedural grids (examples/procedural-grid.scm): the first n*n
  * items are the junctions in row-major order; lane_from_j / lane_to_j give the junctions a segment
@@ -132,6 +136,11 @@ int griddy_set_agenda_destinations(void* ctx, int64_t n_agenda_items, const int3
 
 /* Advance the world n_ticks ticks: the body of `update`, simulate.scm:144-151, n_ticks times. */
 int griddy_step(void* ctx, int64_t n_ticks);
+/* The same without waiting for the device: the ticks are enqueued and the call returns.  For frame loops
+ * (`update` then `draw` per tick, with griddy_positions_begin / _end): nothing synchronises the host per tick.
+ * An error the device meets (GRIDDY_ERR_BAD_STATE) is reported by a later call — at the latest by the next
+ * blocking one, e.g. griddy_step(ctx, 0). */
+int griddy_step_async(void* ctx, int64_t n_ticks);
 
 /* Read the world back (caller-allocated arrays of n entries; any pointer may be NULL).
  *   alive        0 once an equal-key insert replaced the actor (core.scm:173-178)

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--every", type=int, default=25)
     ap.add_argument("--strips", type=int, default=1)
     ap.add_argument("--tiled", action="store_true")
+    ap.add_argument("--async-steps", action="store_true", help="tick by tick with griddy_step_async, one blocking call per checkpoint")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = local % torch.cuda.device_count()
@@ -56,7 +57,12 @@ def main():
         ref = Oracle(net, actors)
     crossed = 0
     for t in range(0, args.ticks, args.every):
-        sim.step(args.every)
+        if args.async_steps:   # a frame loop's way of stepping: nothing waits for the device between ticks
+            for _ in range(args.every):
+                sim.step_async(1)
+            sim.step(0)
+        else:
+            sim.step(args.every)
         parts, digs = [None] * world, [None] * world
         dist.all_gather_object(parts, sim.local_state())
         dist.all_gather_object(digs, sim.digest())

@@ -291,3 +291,4 @@ def test_partitioned_world_over_ipc_windows_sharing_one_gpu():
 def test_partitioned_world_over_ipc_windows_two_gpus():
     """Two ranks on two GPUs (NVLink peer stores), interleaved strips, tiled network, against the oracle."""
     run_ipc_check(2, "--strips", "2", "--tiled", gpus_needed=2)
+    run_ipc_check(2, "--strips", "3", "--tiled", "--async-steps", "--every", "100", gpus_needed=2)
