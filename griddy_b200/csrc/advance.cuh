@@ -7,14 +7,14 @@ __device__ __forceinline__ void dev_error(const Params& p, int bit) { atomicOr(&
 
 // location.scm:16-24 through the uploaded per-segment table
 __device__ __forceinline__ int32_t outer_lane(const Params& p, int32_t seg, uint32_t side) {
-  return side ? p.item[seg].link2 : p.item[seg].link;
+  return side ? p.lane[seg].link2 : p.lane[seg].link;
 }
 
 // Dimension-ordered next hop on procedural grids (include/griddy_cuda.h, griddy_set_routing_grid):
-// from segment lane `lane` towards the lane that leaves junction dest_from_j for junction dest_to_j.
-__device__ int32_t grid_next_hop(const Params& p, int32_t lane, int32_t lane_to_j, int32_t dest_from_j, int32_t dest_to_j) {
+// from the segment lane `it` towards the lane that leaves junction dest_from_j for junction dest_to_j.
+__device__ __forceinline__ int32_t grid_next_hop(const Params& p, const LaneRec& it, int32_t dest_from_j, int32_t dest_to_j) {
   const int n = p.grid_n;
-  const int32_t J = lane_to_j, E = dest_from_j;
+  const int32_t J = it.to_j, E = dest_from_j;
   int h;
   if (J == E) {
     const int32_t T = dest_to_j;
@@ -24,19 +24,19 @@ __device__ int32_t grid_next_hop(const Params& p, int32_t lane, int32_t lane_to_
   } else {
     h = E % n > J % n ? 2 : 3;
   }
-  return p.turn4[4 * (int64_t)lane + h];
+  return h == 0 ? it.turn[0] : h == 1 ? it.turn[1] : h == 2 ? it.turn[2] : it.turn[3];   // (no dynamic index: the record stays in registers)
 }
 
 // Head of the route after the actor has reached `lane` (route.scm:48-51 evaluated lazily); `it` is
 // lane's record, k holds the route's destination.
-__device__ int32_t route_head_on(const Params& p, int32_t lane, const Item& it, const Cold& k, int32_t item, int32_t* rc) {
+__device__ __forceinline__ int32_t route_head_on(const Params& p, int32_t lane, const LaneRec& it, const Cold& k, int32_t item, int32_t* rc) {
   if (p.route_off) {
     const int64_t c = *rc;
     return c < p.route_off[item + 1] ? p.route_lane[c] : HOP_ARRIVE;
   }
   if (lane == k.dest_lane) return HOP_ARRIVE;
-  if (it.kind == GRIDDY_JUNCTION_LANE) return it.link;
-  const int32_t hop = grid_next_hop(p, lane, it.to_j, k.dest_from_j, k.dest_to_j);
+  if (meta_kind(it.meta) == GRIDDY_JUNCTION_LANE) return it.link;
+  const int32_t hop = grid_next_hop(p, it, k.dest_from_j, k.dest_to_j);
   if (hop < 0) dev_error(p, DEV_ERR_NO_ROUTE);
   return hop;
 }
@@ -49,16 +49,18 @@ __device__ __forceinline__ int32_t tag_junction(const Params& p, int32_t j) {
   return (j >= 0 && p.owner && p.owner[j] != p.my_rank) ? (j | TJ_REMOTE) : j;
 }
 __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop) {
-  return tag_junction(p, (hop >= 0 && p.item[hop].kind == GRIDDY_JUNCTION_LANE) ? p.item[hop].link2 : -1);
+  if (hop < 0) return -1;
+  const LaneRec& h = p.lane[hop];
+  return tag_junction(p, meta_kind(h.meta) == GRIDDY_JUNCTION_LANE ? h.link2 : -1);
 }
 
 // The same for the head `nhop` of a route that has just reached lane `it`.  With the grid routing table a
-// segment lane's next hop is a junction lane of the junction the lane reaches (Item::to_j; checked by
+// segment lane's next hop is a junction lane of the junction the lane reaches (LaneRec::to_j; checked by
 // griddy_set_routing_grid) and a junction lane's next hop is a segment lane, so the hop's own record
 // is not needed.
-__device__ __forceinline__ int32_t junction_after(const Params& p, const Item& it, int32_t nhop) {
+__device__ __forceinline__ int32_t junction_after(const Params& p, const LaneRec& it, int32_t nhop) {
   if (p.route_off) return junction_of_hop(p, nhop);
-  return tag_junction(p, (nhop >= 0 && it.kind == GRIDDY_SEGMENT_LANE) ? it.to_j : -1);
+  return tag_junction(p, (nhop >= 0 && meta_kind(it.meta) == GRIDDY_SEGMENT_LANE) ? it.to_j : -1);
 }
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
@@ -72,6 +74,9 @@ __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_
 
 // Lanes whose list must be rebuilt this tick are collected per block in shared memory and flushed to
 // Params::touched with one global atomic per block (a same-address atomic per lane would serialise).
+// Whether a lane is on a list already is kept in its own record (LaneRec::meta): the first leaver / ghost
+// finder / entrant of the tick lists it, and the counts tell k_unlink / k_link whether the list has one
+// element — then they never read the chain through the cold records.
 struct TouchSink {
   int32_t *left, *n_left;         // shared: lanes that lost an actor or hold a ghost (k_unlink), SLOW_THREADS entries
   int32_t *entered, *n_entered;   // shared: lanes that gained an actor (k_link), SLOW_THREADS entries
@@ -83,42 +88,50 @@ struct TouchSink {
 #endif
 constexpr int SLOW_THREADS = 128;   // an actor leaves at most one lane (its own, ghost or not) and enters at most one
 
-__device__ __forceinline__ void mark_left(const Params& p, int32_t lane, int tick, const TouchSink& sink) {
-  if (atomicExch(&p.lane[lane].mark_out, tick + 1) != tick + 1) sink.left[atomicAdd(sink.n_left, 1)] = lane;
+__device__ __forceinline__ void mark_ghost_found(const Params& p, int32_t lane, const TouchSink& sink) {
+  if (!(atomicOr(&p.lane[lane].meta, META_GHOST) & META_LEFT)) sink.left[atomicAdd(sink.n_left, 1)] = lane;
 }
 
-__device__ __forceinline__ void enter_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
-  p.cold[a].inbox_next = atomicExch(&p.lane[lane].inbox, a);
-  if (atomicExch(&p.lane[lane].mark_in, tick + 1) != tick + 1) sink.entered[atomicAdd(sink.n_entered, 1)] = lane;
+// Returns the lane's previous inbox head (the caller stores it as the entrant's inbox_next).
+__device__ __forceinline__ int32_t enter_lane(const Params& p, int a, int32_t lane, const TouchSink& sink) {
+  const int32_t prev = atomicExch(&p.lane[lane].inbox, a);
+  const uint32_t old = atomicAdd(&p.lane[lane].meta, META_IN_ONE);
+  if (!(old & META_IN)) sink.entered[atomicAdd(sink.n_entered, 1)] = lane;
+  else if ((old & META_IN) == META_IN) dev_error(p, DEV_ERR_LANE_BURST);
+  return prev;
 }
 
-__device__ __forceinline__ void leave_lane(const Params& p, int a, int32_t lane, int tick, const TouchSink& sink) {
-  p.cold[a].outbox_next = atomicExch(&p.lane[lane].outbox, a);
-  mark_left(p, lane, tick, sink);
+// Returns the lane's previous outbox head (the caller stores it as the leaver's outbox_next).
+__device__ __forceinline__ int32_t leave_lane(const Params& p, int a, int32_t lane, const TouchSink& sink) {
+  const int32_t prev = atomicExch(&p.lane[lane].outbox, a);
+  const uint32_t old = atomicAdd(&p.lane[lane].meta, META_OUT_ONE);
+  if (!(old & META_LEFT)) sink.left[atomicAdd(sink.n_left, 1)] = lane;
+  else if ((old & META_OUT) == META_OUT) dev_error(p, DEV_ERR_LANE_BURST);
+  return prev;
 }
 
 // ------------------------------------------------------------------------------------------------
 // route-step/turn-onto$ (route.scm:92-135) for an actor that reaches the end of its lane and is not
 // held by a full junction: carry the rest of the tick over into the target lane, pop the route.
-// Reads one cold record of the actor and one record of the target lane; returns the new pos-param.
+// Touches six 64-byte lines: the actor's cold record, its hot record, its new pos-param, the target lane's
+// record, the old lane's record and the pos-param of the target lane's rearmost actor.  Returns the new pos-param.
 __device__ __forceinline__ double turn_onto(const Params& p, const int a, const int tick, const uint32_t st,
                                             const double cur, const double* __restrict__ pos_old, const TouchSink& sink) {
   Cold k = p.cold[a];
-  const ColdF f = p.coldf[a];
   const int32_t target = k.hop, lane = k.container;
-  const Item it = p.item[target];
-  const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), f.speed);
+  const LaneRec it = p.lane[target];
+  const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), k.speed);
   const double time_remaining = __dsub_rn(p.dt, time_spent);
   const double tinv = __ddiv_rn(1.0, it.len);
   const double tbuf = __ddiv_rn(p.two_size, it.len);
-  double tnext = __dmul_rn(__dmul_rn(f.speed, time_remaining), tinv);   // (+ 0 delta)
-  int32_t x = p.lane[target].tail;
+  double tnext = __dmul_rn(__dmul_rn(k.speed, time_remaining), tinv);   // (+ 0 delta)
+  int32_t x = it.tail;
   const bool remote = x <= -2;   // multi-GPU: another rank owns the target lane
   if (remote) {                  // its smallest key in (0, ...] came with the halo (+inf: none)
     const double tlead = __ldcg(&p.halo_recv[tick & 1][-2 - x]);
     if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
   } else {
-    while (x >= 0 && !(pos_old[x] > 0.0)) x = p.sa[x].ahead;   // smallest key in (0, ...]
+    while (x >= 0 && !(pos_old[x] > 0.0)) x = p.hot[x].ahead;   // smallest key in (0, ...]
     if (x >= 0) {
       const double tlead = pos_old[x];
       if (tlead <= __dadd_rn(tnext, tbuf)) tnext = __dsub_rn(tlead, tbuf);
@@ -126,16 +139,21 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
   }
   int32_t rc = p.route_off ? k.route_cur + 1 : 0;
   const int32_t nhop = route_head_on(p, target, it, k, k.agenda_cur, &rc);
-  p.cold[a].route_cur = rc;
-  p.cold[a].hop = nhop;
-  p.cold[a].container = target;
-  p.cold[a].mv_old = lane;
-  p.tj[a] = junction_after(p, it, nhop);
-  p.db[a] = make_double2(__dmul_rn(f.speed_dt, tinv), tbuf);
-  p.sa[a].st = st | ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u);
+  // (ahead / behind stay: k_unlink reads them.  atomicOr: a follower may be flagging this actor as a ghost right now)
+  atomicOr(&p.hot[a].st, ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u));
+  p.hot[a].tj = junction_after(p, it, nhop);
+  p.hot[a].delta = __dmul_rn(k.speed_dt, tinv);
+  p.hot[a].buf = tbuf;
+  k.hop = nhop;
+  k.container = target;
+  k.mv_old = lane;
   if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
-  else enter_lane(p, a, target, tick, sink);
-  leave_lane(p, a, lane, tick, sink);
+  else k.inbox_next = enter_lane(p, a, target, sink);
+  k.outbox_next = leave_lane(p, a, lane, sink);
+  int4* kc = (int4*)&p.cold[a];   // the first sector, in two stores
+  kc[0] = make_int4(k.container, k.hop, k.dest_lane, k.dest_from_j);
+  kc[1] = make_int4(k.dest_to_j, k.mv_old, k.inbox_next, k.outbox_next);
+  if (p.route_off) p.cold[a].route_cur = rc;
   return tnext;
 }
 
@@ -155,12 +173,12 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   if (ah >= 0 && lead == cur) {
     const int32_t lane = p.cold[a].container;
     do {
-      if (atomicExch(&p.cold[ah].dead_mark, tick + 1) != tick + 1)   // the first to notice hands it to k_unlink
+      if (!(atomicOr(&p.hot[ah].st, ST_GHOST) & ST_GHOST))   // the first to notice hands it to k_unlink
         p.cold[ah].ghost_next = atomicExch(&p.lane[lane].ghosts, ah);
-      ah = p.sa[ah].ahead;
+      ah = p.hot[ah].ahead;
       if (ah >= 0) lead = pos_old[ah];
     } while (ah >= 0 && lead == cur);
-    mark_left(p, lane, tick, sink);
+    mark_ghost_found(p, lane, sink);
   }
 
   if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {   // advance-on-route$  route.scm:137-141
@@ -171,34 +189,37 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
       const double target = p.coldf[a].arrive;
       if (!(next >= target)) return next;
       const bool back = target < cur;
-      p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_ARRIVE)) | (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u);
+      // (atomicAnd / atomicOr: a follower may be flagging this actor as a ghost right now)
+      atomicAnd(&p.hot[a].st, ~((3u << ST_RS_SHIFT) | ST_ARRIVE));
+      atomicOr(&p.hot[a].st, (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u));
       if (back) {   // jumped back past other residents: re-insert by key
         const int32_t lane = p.cold[a].container;
         p.cold[a].mv_old = lane;
-        leave_lane(p, a, lane, tick, sink);
-        enter_lane(p, a, lane, tick, sink);
+        p.cold[a].outbox_next = leave_lane(p, a, lane, sink);
+        p.cold[a].inbox_next = enter_lane(p, a, lane, sink);
       }
       return target;
     }
     // route-step/turn-onto$  route.scm:92-135
     if (!(next >= 1.0)) return next;
-    const int32_t tj = p.tj[a];   // junction-full?  route.scm:98-108 (k_advance has usually answered this)
+    const int32_t tj = p.hot[a].tj;   // junction-full?  route.scm:98-108 (k_advance has usually answered this)
     if (tj >= 0 && p.occ[tj & ~TJ_REMOTE] > 0) return cur;   // waiting
     return turn_onto(p, a, tick, st, cur, pos_old, sink);
   }
 
   if (rs == GRIDDY_ROUTE_NONE && head == HEAD_NONE) return cur;   // do-nothing$  simulate.scm:70-72
   if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {            // sleep$  simulate.scm:74-78
-    const int32_t t = p.aux[a];
+    const int32_t t = p.hot[a].tj;
     if (t == 0) {
       const int32_t ac = p.cold[a].agenda_cur + 1;
       int32_t aux;
       const uint32_t h = load_head(p, a, ac, &aux);
       p.cold[a].agenda_cur = ac;
-      p.aux[a] = aux;
-      p.sa[a].st = (st & ~(3u << ST_HEAD_SHIFT)) | (h << ST_HEAD_SHIFT);
+      p.hot[a].tj = aux;
+      atomicAnd(&p.hot[a].st, ~(3u << ST_HEAD_SHIFT));
+      atomicOr(&p.hot[a].st, h << ST_HEAD_SHIFT);
     } else {
-      p.aux[a] = t - 1;
+      p.hot[a].tj = t - 1;
     }
     return cur;
   }
@@ -216,69 +237,68 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     const AgendaItem ai = p.agenda[item];
     const int32_t dest_lane = ai.dlane;
     if (init_lane < 0 || dest_lane < 0) { dev_error(p, DEV_ERR_NO_LANE); return cur; }
-    const Item init_it = p.item[init_lane];
+    const LaneRec init_it = p.lane[init_lane];
     // off-road->on-road  location.scm:49-57
-    const double init_pos = init_it.dir ? __dsub_rn(1.0, cur) : cur;
+    const double init_pos = meta_dir(init_it.meta) ? __dsub_rn(1.0, cur) : cur;
     const double dest_pos = ai.dpos;
     int32_t rc = p.route_off ? (int32_t)p.route_off[item] : 0;
-    Cold k;
+    Cold k = p.cold[a];
     k.dest_lane = dest_lane;
     k.dest_from_j = ai.dfrom;
     k.dest_to_j = ai.dto;
     const int32_t hop = route_head_on(p, init_lane, init_it, k, item, &rc);
     const double len = init_it.len;
-    p.cold[a].route_cur = rc;
-    p.cold[a].dest_lane = dest_lane;
-    p.cold[a].dest_from_j = k.dest_from_j;
-    p.cold[a].dest_to_j = k.dest_to_j;
     p.coldf[a].arrive = dest_pos;
-    p.cold[a].hop = hop;
-    p.tj[a] = junction_after(p, init_it, hop);
-    p.db[a] = make_double2(__dmul_rn(p.coldf[a].speed_dt, __ddiv_rn(1.0, len)), __ddiv_rn(p.two_size, len));
-    p.cold[a].container = init_lane;
-    p.cold[a].mv_old = ~seg;
-    p.sa[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
-              ST_ONROAD | ST_MOVED | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);
-    enter_lane(p, a, init_lane, tick, sink);
+    p.hot[a].tj = junction_after(p, init_it, hop);
+    p.hot[a].delta = __dmul_rn(k.speed_dt, __ddiv_rn(1.0, len));
+    p.hot[a].buf = __ddiv_rn(p.two_size, len);
+    p.hot[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
+                  ST_ONROAD | ST_MOVED | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);   // (off road: nobody flags it)
+    k.hop = hop;
+    k.container = init_lane;
+    k.mv_old = ~seg;
+    k.route_cur = rc;
+    k.inbox_next = enter_lane(p, a, init_lane, sink);
+    p.cold[a] = k;
     return init_pos;
   }
 
   // end-route$  simulate.scm:87-91   (rs == GRIDDY_ROUTE_DONE)
   const int32_t lane = p.cold[a].container;
-  if (p.item[lane].kind != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); return cur; }
-  const int32_t seg = p.item[lane].link;
-  const uint32_t dir = p.item[lane].dir;
+  const LaneRec lr = p.lane[lane];
+  if (meta_kind(lr.meta) != GRIDDY_SEGMENT_LANE) { dev_error(p, DEV_ERR_END_ON_JLANE); return cur; }
+  const int32_t seg = lr.link;
+  const uint32_t dir = meta_dir(lr.meta);
   const int32_t ac = item + 1;
   int32_t aux;
   const uint32_t h = load_head(p, a, ac, &aux);
   p.cold[a].agenda_cur = ac;
-  p.aux[a] = aux;
+  p.hot[a].tj = aux;
   p.cold[a].container = seg;
   p.cold[a].mv_old = lane;
   // landing stamp: where this actor sits in the segment's consed list (core.scm:169-171)
   p.coldf[a].land_tick = tick + 1;
   p.coldf[a].land_lane = lane;
   p.coldf[a].land_pos = cur;
-  uint32_t ns = st & ~((3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE);
-  ns |= (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
-  p.sa[a].st = ns;
-  leave_lane(p, a, lane, tick, sink);
+  const uint32_t clear = (3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE;
+  const uint32_t set = (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
+  atomicAnd(&p.hot[a].st, ~clear);   // (a follower may be flagging this actor as a ghost right now)
+  atomicOr(&p.hot[a].st, set);
+  p.cold[a].outbox_next = leave_lane(p, a, lane, sink);
   return dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
 }
 
 // k_advance: the common cases of advance$ for every slot; everything else is deferred to k_slow.
 // ADV_UNROLL slots per thread, strided by the block so that every load is coalesced.  The loads of all
 // ADV_UNROLL actors are issued before the first use (one slot per thread leaves too few bytes in
-// flight to cover HBM latency): first st / ahead / pos, then the leaders' pos-params (a gather that
-// the slot order keeps inside the same or a neighbouring cache line) with delta / buf.
+// flight to cover HBM latency): first the hot record (two 16-byte loads of one sector) and the pos-param,
+// then the leaders' pos-params (a gather that the slot order keeps inside the same or a neighbouring line).
 // Handled here: an actor on its route that has no (arrive-at _) head and either stays on its lane
 // or waits at its end for a full junction (the junction-occupancy table is small enough to live in
 // L2); a sleeper whose time has not run out; an idle actor.  These touch only the hot
 // arrays.  Any other actor — a few percent — would drag its whole warp through chains of dependent
 // gathers, so its slot is appended to the slow list instead (block-aggregated: one global atomic per
 // block) and k_slow runs the full advance$ for it with one thread per listed actor.
-// Measured on B200 (profiles/r1_variants.md): 2 slots per thread = 40 registers = 6 blocks per SM beats
-// 3 slots (58 registers with the slow list's payload, 4 blocks) and 3 slots capped at 48 registers.
 #ifndef ADV_UNROLL
 #define ADV_UNROLL 2
 #endif
@@ -286,9 +306,6 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 #define ADV_THREADS_N 256
 #endif
 constexpr int ADV_THREADS = ADV_THREADS_N;
-#ifndef SLOW_PAYLOAD
-#define SLOW_PAYLOAD 1
-#endif
 #ifdef ADV_MIN_BLOCKS
 #define ADV_BOUNDS __launch_bounds__(ADV_THREADS, ADV_MIN_BLOCKS)
 #else
@@ -310,35 +327,29 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick) {
   __syncthreads();
   const double* __restrict__ pos_old = p.pos[par];
   double* __restrict__ pos_new = p.pos[par ^ 1];
+  const int4* __restrict__ hot4 = (const int4*)p.hot;
 
   uint32_t st[ADV_UNROLL];
-  int32_t ah[ADV_UNROLL], slp[ADV_UNROLL], tj[ADV_UNROLL];
+  int32_t ah[ADV_UNROLL], tj[ADV_UNROLL];
   double cur[ADV_UNROLL], dlt[ADV_UNROLL], buf[ADV_UNROLL], lead[ADV_UNROLL];
 #pragma unroll
   for (int k = 0; k < ADV_UNROLL; ++k) {
     const int a = base + k * ADV_THREADS;
     const bool in = a < n;
-    const SA sa = in ? p.sa[a] : SA{0u, -1};
-    st[k] = sa.st;
-    ah[k] = sa.ahead;
+    const int4 h0 = in ? hot4[2 * (size_t)a] : make_int4(0, -1, -1, -1);            // st, ahead, behind, tj
+    const int4 h1 = in ? hot4[2 * (size_t)a + 1] : make_int4(0, 0, 0, 0);           // delta, buf (same sector)
+    st[k] = (uint32_t)h0.x;
+    ah[k] = h0.y;
+    tj[k] = h0.w;
+    dlt[k] = __hiloint2double(h1.y, h1.x);
+    buf[k] = __hiloint2double(h1.w, h1.z);
     cur[k] = in ? pos_old[a] : 0.0;
   }
 #pragma unroll
   for (int k = 0; k < ADV_UNROLL; ++k) {
-    const int a = base + k * ADV_THREADS;
-    const bool alive = st[k] & ST_ALIVE;
-    const bool on_road = alive && (st[k] & ST_ONROAD);
+    const bool on_road = (st[k] & (ST_ALIVE | ST_ONROAD)) == (ST_ALIVE | ST_ONROAD);
     if (!on_road) ah[k] = -1;   // an off-road actor's ahead is stale
-    const int rs = (st[k] >> ST_RS_SHIFT) & 3, head = (st[k] >> ST_HEAD_SHIFT) & 3;
-    const bool on_route = on_road && rs == GRIDDY_ROUTE_SOME;
     lead[k] = ah[k] >= 0 ? pos_old[ah[k]] : 0.0;
-    const double2 db = on_route ? p.db[a] : make_double2(0.0, 0.0);
-    dlt[k] = db.x;
-    buf[k] = db.y;
-    // (loading tj only at the lane's end was measured slower: on a congested grid every queue head
-    // gets there every tick, so most sectors are fetched anyway, now behind a dependent load)
-    tj[k] = (on_route && !(st[k] & ST_ARRIVE)) ? p.tj[a] : -1;
-    slp[k] = (alive && rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) ? p.aux[a] : 0;
   }
 #pragma unroll
   for (int k = 0; k < ADV_UNROLL; ++k) {
@@ -359,18 +370,14 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick) {
         else if (tj[k] >= 0 && p.occ[tj[k]] > 0) np = cur[k];   // waiting for a full junction  route.scm:98-111
         else slow = turn = true;                                   // turns onto the next lane
       } else if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {   // sleep$, time left  simulate.scm:77
-        if (slp[k] == 0) slow = true;
-        else p.aux[a] = slp[k] - 1;
+        if (tj[k] == 0) slow = true;
+        else p.hot[a].tj = tj[k] - 1;
       } else if (!(rs == GRIDDY_ROUTE_NONE && head == HEAD_NONE)) {   // not do-nothing$ either
         slow = true;
       }
     }
     if (slow)   // ~slot: k_slow goes straight to turn_onto; st and pos-param ride along (two gathers less there)
-#if SLOW_PAYLOAD
       s_list[atomicAdd(&s_n, 1)] = make_int4(turn ? ~a : a, (int)st[k], __double2loint(cur[k]), __double2hiint(cur[k]));
-#else
-      s_list[atomicAdd(&s_n, 1)] = make_int4(turn ? ~a : a, 0, 0, 0);
-#endif
     else pos_new[a] = np;
   }
   __syncthreads();
@@ -403,22 +410,17 @@ __global__ void SLOW_BOUNDS k_slow(Params p, int tick) {
       const int4 ent = p.slow[i];
       const int32_t e = ent.x;
       const int a = e < 0 ? ~e : e;
-#if SLOW_PAYLOAD
       const uint32_t st = (uint32_t)ent.y;
       const double cur = __hiloint2double(ent.w, ent.z);
-#else
-      const uint32_t st = p.sa[a].st;
-      const double cur = pos_old[a];
-#endif
       if (e < 0) {
         pos_new[a] = turn_onto(p, a, tick, st, cur, pos_old, sink);
       } else {
-      const bool on_road = st & ST_ONROAD;
-      const bool on_route = on_road && ((st >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME;
-      const int32_t ah = on_road ? p.sa[a].ahead : -1;
-      const double lead = ah >= 0 ? pos_old[ah] : 0.0;
-      const double2 db = on_route ? p.db[a] : make_double2(0.0, 0.0);
-      pos_new[a] = advance_actor(p, a, tick, st, ah, cur, db.x, db.y, lead, pos_old, sink);
+        const bool on_road = st & ST_ONROAD;
+        const bool on_route = on_road && ((st >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME;
+        const Hot h = p.hot[a];
+        const int32_t ah = on_road ? h.ahead : -1;
+        const double lead = ah >= 0 ? pos_old[ah] : 0.0;
+        pos_new[a] = advance_actor(p, a, tick, st, ah, cur, on_route ? h.delta : 0.0, on_route ? h.buf : 0.0, lead, pos_old, sink);
       }
     }
     __syncthreads();

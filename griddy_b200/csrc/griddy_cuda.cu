@@ -183,9 +183,8 @@ struct Ctx {
   int reorder_period = 384;
   int64_t last_reorder_tick = -1;
   int loc_key_bits = 1;
-  uint32_t *alt4[PERM4] = {}, *cur4[PERM4] = {};   // double buffers of the permuted arrays
-  uint64_t *alt8[PERM8] = {}, *cur8[PERM8] = {};
-  double2 *db_cur = nullptr, *db_alt = nullptr;
+  Hot *hot_cur = nullptr, *hot_alt = nullptr;       // double buffers of the permuted arrays
+  double* pos_alt = nullptr;                        // (the two pos-param buffers of the tick and this one rotate)
   Cold *cold_cur = nullptr, *cold_alt = nullptr;
   ColdF *coldf_cur = nullptr, *coldf_alt = nullptr;
   uint64_t* sort_keys = nullptr;
@@ -268,18 +267,6 @@ int bits_for(uint32_t max_value) {   // bits that hold 0..max_value with all-one
   return b;
 }
 
-// Point Params at the current buffers of the permuted arrays.
-void bind_slot_arrays(Ctx* c, int par) {
-  Params& p = c->p;
-  p.sa = (SA*)c->cur8[P8_SA];
-  p.aux = (int32_t*)c->cur4[P4_AUX];
-  p.tj = (int32_t*)c->cur4[P4_TJ];
-  p.pos[par] = (double*)c->cur8[P8_POS];
-  p.db = c->db_cur;
-  p.cold = c->cold_cur;
-  p.coldf = c->coldf_cur;
-}
-
 // Enqueue a reorder of the slots on the context's stream.  Runs between ticks: no actor is marked
 // moved, every inbox is empty.  `tick` is the next tick to run (its parity names the valid pos buffer).
 int reorder_slots(Ctx* c, int64_t tick) {
@@ -297,12 +284,9 @@ int reorder_slots(Ctx* c, int64_t tick) {
   k_make_keys<<<n_pad / 256, 256, 0, s>>>(p, par, key_bits, c->sort_keys, c->sort_vals, c->tailflag);
   c->launches += 1 + rsort::sort_pairs(&c->sort_keys, &c->sort_vals, n_tiles, key_bits, &c->sort_scratch, s);
   k_inverse<<<n_pad / 256, 256, 0, s>>>(c->sort_vals, n_pad, c->newslot);
-  // the valid pos buffer is the one of parity `par`
-  c->cur8[P8_POS] = (uint64_t*)p.pos[par];
   Permute q;
-  for (int k = 0; k < PERM4; ++k) { q.src4[k] = c->cur4[k]; q.dst4[k] = c->alt4[k]; }
-  for (int k = 0; k < PERM8; ++k) { q.src8[k] = c->cur8[k]; q.dst8[k] = c->alt8[k]; }
-  q.src_db = c->db_cur; q.dst_db = c->db_alt;
+  q.src_hot = c->hot_cur; q.dst_hot = c->hot_alt;
+  q.src_pos = p.pos[par]; q.dst_pos = c->pos_alt;   // the valid pos buffer is the one of parity `par`
   q.src_cold = c->cold_cur; q.dst_cold = c->cold_alt;
   q.src_coldf = c->coldf_cur; q.dst_coldf = c->coldf_alt;
   // a partitioned world: the surviving actors' remaining agenda items move to the second pool, so that the
@@ -317,12 +301,13 @@ int reorder_slots(Ctx* c, int64_t tick) {
     CUDA_TRY(c, cudaMemcpyAsync(&p.scal[SC_NITEMS], c->d_nitems_new, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     std::swap(p.agenda, c->agenda_alt);
   }
-  for (int k = 0; k < PERM4; ++k) std::swap(c->cur4[k], c->alt4[k]);
-  for (int k = 0; k < PERM8; ++k) std::swap(c->cur8[k], c->alt8[k]);
-  std::swap(c->db_cur, c->db_alt);
+  std::swap(c->hot_cur, c->hot_alt);
   std::swap(c->cold_cur, c->cold_alt);
   std::swap(c->coldf_cur, c->coldf_alt);
-  bind_slot_arrays(c, par);
+  std::swap(p.pos[par], c->pos_alt);
+  p.hot = c->hot_cur;
+  p.cold = c->cold_cur;
+  p.coldf = c->coldf_cur;
   c->last_reorder_tick = tick;
   ++c->reorders;
   CUDA_TRY(c, cudaGetLastError());
@@ -714,11 +699,18 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   Params& p = c->p;
   p.n_items = tl.n_global;
   p.grid_n = 0;
-  p.turn4 = nullptr;
   c->d_geom = nullptr;
-  TRY(sparse_alloc(c, sizeof(Item), (void**)&p.item));
-  TRY(sparse_alloc(c, sizeof(LaneDyn), (void**)&p.lane));
+  TRY(sparse_alloc(c, sizeof(LaneRec), (void**)&p.lane));
   TRY(sparse_alloc(c, sizeof(int32_t), (void**)&p.occ));
+  {   // locality keys: the registration index until griddy_set_locality_keys
+    uint32_t* d_key = nullptr;
+    TRY(sparse_alloc(c, sizeof(uint32_t), (void**)&d_key));
+    std::vector<uint32_t> ident((size_t)n_items);
+    for (size_t k = 0; k < tl.beg.size(); ++k)
+      for (int64_t g = tl.beg[k]; g < tl.end[k]; ++g) ident[(size_t)(tl.off[k] + (g - tl.beg[k]))] = (uint32_t)g;
+    TRY(sparse_upload(c, d_key, ident.data()));
+    p.loc_key = d_key;
+  }
   if (n_items > 0) {   // stage the ABI arrays on the device, assemble the records there
     std::vector<void*> tmp;
     const uint8_t *d_kind, *d_dir;
@@ -736,8 +728,8 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
       for (size_t k = 0; k < tl.beg.size(); ++k) {
         const int64_t m = tl.end[k] - tl.beg[k], o = tl.off[k];
         if (m > 0)
-          k_item_build<<<(unsigned)((m + 255) / 256), 256>>>(p.item + tl.beg[k], m, d_kind + o, d_len + o, d_dir + o, d_seg + o,
-                                                              d_out + o, d_jun + o, d_of + o, d_ob + o, tl.beg[k]);
+          k_item_build<<<(unsigned)((m + 255) / 256), 256>>>(p.lane + tl.beg[k], m, d_kind + o, d_len + o, d_dir + o, d_seg + o,
+                                                              d_out + o, d_jun + o, d_of + o, d_ob + o);
       }
       if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_build failed");
     }
@@ -768,20 +760,7 @@ int griddy_set_locality_keys(void* ctx, const uint32_t* item_key) {
   uint32_t mx = 0;
   for (int64_t r = 0; r < tl.n_local; ++r) mx = std::max(mx, item_key[r]);
   if (mx == UINT32_MAX) return fail(c, GRIDDY_ERR_BAD_ARG, "locality keys must be below 2^32-1");
-  {
-    std::vector<void*> tmp;
-    const uint32_t* d_key;
-    int rc = dev_upload(c, tmp, &d_key, item_key, tl.n_local);
-    if (!rc) {
-      for (size_t k = 0; k < tl.beg.size(); ++k) {
-        const int64_t m = tl.end[k] - tl.beg[k];
-        if (m > 0) k_item_set_key<<<(unsigned)((m + 255) / 256), 256>>>(c->p.item + tl.beg[k], m, d_key + tl.off[k]);
-      }
-      if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_set_key failed");
-    }
-    free_pool(tmp);
-    if (rc) return rc;
-  }
+  TRY(sparse_upload(c, (uint32_t*)c->p.loc_key, item_key));
   c->loc_key_bits = bits_for(mx);
   return GRIDDY_OK;
 }
@@ -811,23 +790,19 @@ int griddy_set_routing_grid(void* ctx, int32_t n, const int32_t* lane_from_j, co
   Params& p = c->p;
   {
     std::vector<void*> tmp;
-    const int32_t *d_from, *d_to;
-    int rc = dev_upload(c, tmp, &d_from, lane_from_j, tl.n_local);
-    if (!rc) rc = dev_upload(c, tmp, &d_to, lane_to_j, tl.n_local);
+    const int32_t *d_to, *d_turn;
+    int rc = dev_upload(c, tmp, &d_to, lane_to_j, tl.n_local);
+    if (!rc) rc = dev_upload(c, tmp, &d_turn, turn4, 4 * tl.n_local);
     if (!rc) {
       for (size_t k = 0; k < tl.beg.size(); ++k) {
         const int64_t m = tl.end[k] - tl.beg[k];
-        if (m > 0) k_item_set_grid<<<(unsigned)((m + 255) / 256), 256>>>(p.item + tl.beg[k], m, d_from + tl.off[k], d_to + tl.off[k]);
+        if (m > 0) k_item_set_grid<<<(unsigned)((m + 255) / 256), 256>>>(p.lane + tl.beg[k], m, d_to + tl.off[k], d_turn + 4 * tl.off[k]);
       }
       if (cudaDeviceSynchronize() != cudaSuccess) rc = fail(c, GRIDDY_ERR_CUDA, "k_item_set_grid failed");
     }
     free_pool(tmp);
     if (rc) return rc;
   }
-  int32_t* d_turn4 = nullptr;
-  TRY(sparse_alloc(c, 4 * sizeof(int32_t), (void**)&d_turn4));
-  TRY(sparse_upload(c, d_turn4, turn4, 4));
-  p.turn4 = d_turn4;
   p.grid_n = n;
   c->h_from.assign(lane_from_j, lane_from_j + tl.n_local);
   c->h_to.assign(lane_to_j, lane_to_j + tl.n_local);
@@ -957,8 +932,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   auto& pool = c->actor_allocs;
 
   // Initial world: link! every actor in id order (core.scm:169-178).  Slot = id until the first reorder.
-  std::vector<SA> sa(n);
-  std::vector<int32_t> aux(n, 0);
+  std::vector<Hot> hot(n);
   std::vector<Cold> cold(n);
   std::vector<ColdF> coldf(n);
   std::vector<int32_t> occ((size_t)tl.n_local, 0);   // compact, like every host copy of a per-item array
@@ -966,28 +940,32 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   std::vector<int32_t> on_road;
   for (int64_t a = 0; a < n; ++a) {
     uint32_t s = ST_ALIVE;
+    Hot& h = hot[a];
+    memset(&h, 0, sizeof(h));
+    h.ahead = h.behind = -1;
+    h.tj = -1;
     Cold& k = cold[a];
     memset(&k, 0, sizeof(k));
     k.container = container[a];
     k.agenda_cur = (int32_t)agenda_off[a];
     k.gid = (int32_t)a;         // global id = upload index until griddy_mg_set_global_ids
-    k.behind = -1;
     k.hop = HOP_ARRIVE;
     k.dest_lane = k.dest_from_j = k.dest_to_j = -1;
+    k.inbox_next = k.outbox_next = k.ghost_next = -1;
+    k.speed = speed[a];
+    k.speed_dt = speed_dt[a];
     ColdF& f = coldf[a];
     memset(&f, 0, sizeof(f));
-    f.speed = speed[a];
-    f.speed_dt = speed_dt[a];
     f.agenda_beg = (int32_t)agenda_off[a];
     f.agenda_end = (int32_t)agenda_off[a + 1];
     f.land_lane = (int32_t)a;   // landing stamp of the initial placement: tick 0, link! order
     if (agenda_off[a] < agenda_off[a + 1]) {
-      if (item_kind[agenda_off[a]] == GRIDDY_SLEEP_FOR) { s |= HEAD_SLEEP << ST_HEAD_SHIFT; aux[a] = item_sleep[agenda_off[a]]; }
+      if (item_kind[agenda_off[a]] == GRIDDY_SLEEP_FOR) { s |= HEAD_SLEEP << ST_HEAD_SHIFT; h.tj = item_sleep[agenda_off[a]]; }
       else s |= HEAD_TRAVEL << ST_HEAD_SHIFT;
     }
     if (loc_kind[a]) { s |= ST_ONROAD; on_road.push_back((int32_t)a); }
     else if (side[a]) s |= ST_SIDE;
-    sa[a] = SA{s, -1};
+    h.st = s;
   }
   // lanes: ascending pos-param; an equal key replaces the earlier actor (bbtree-set)
   std::sort(on_road.begin(), on_road.end(), [&](int32_t x, int32_t y) {
@@ -995,13 +973,13 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     if (pos[x] != pos[y]) return pos[x] < pos[y];
     return x < y;
   });
-  int32_t prev = -1;
+  int32_t prev = -1, dead0 = 0;
   for (size_t k = 0; k < on_road.size(); ++k) {
     const int32_t a = on_road[k];
     const bool replaced = k + 1 < on_road.size() && container[on_road[k + 1]] == container[a] && pos[on_road[k + 1]] == pos[a];
-    if (replaced) { sa[a].st &= ~ST_ALIVE; continue; }
+    if (replaced) { hot[a].st &= ~ST_ALIVE; ++dead0; continue; }
     const int32_t lane = container[a];
-    if (prev >= 0 && container[prev] == lane) { sa[prev].ahead = a; cold[a].behind = prev; } else { tail_lane.push_back(lane); tail_slot.push_back(a); }
+    if (prev >= 0 && container[prev] == lane) { hot[prev].ahead = a; hot[a].behind = prev; } else { tail_lane.push_back(lane); tail_slot.push_back(a); }
     const int64_t ll = tl.local(lane);
     if (c->h_kind[ll] == GRIDDY_JUNCTION_LANE) {
       const int64_t lj = tl.local(c->h_lane_junction[ll]);
@@ -1011,39 +989,31 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     prev = a;
   }
 
-  // permuted arrays: two buffers each
-  for (int k = 0; k < PERM4; ++k) {
-    TRY(dev_alloc(c, pool, &c->cur4[k], cap));
-    TRY(dev_alloc(c, pool, &c->alt4[k], cap));
-    CUDA_TRY(c, cudaMemset(c->cur4[k], 0, (size_t)cap * sizeof(uint32_t)));
-  }
-  for (int k = 0; k < PERM8; ++k) {
-    TRY(dev_alloc(c, pool, &c->cur8[k], cap));
-    TRY(dev_alloc(c, pool, &c->alt8[k], cap));
-    CUDA_TRY(c, cudaMemset(c->cur8[k], 0, (size_t)cap * sizeof(uint64_t)));
-  }
-  TRY(dev_alloc(c, pool, &c->db_cur, cap));
-  TRY(dev_alloc(c, pool, &c->db_alt, cap));
-  CUDA_TRY(c, cudaMemset(c->db_cur, 0, (size_t)cap * sizeof(double2)));
+  // permuted arrays: two buffers each (the tick's two pos-param buffers and a third one rotate)
+  TRY(dev_alloc(c, pool, &c->hot_cur, cap));
+  TRY(dev_alloc(c, pool, &c->hot_alt, cap));
+  CUDA_TRY(c, cudaMemset(c->hot_cur, 0, (size_t)cap * sizeof(Hot)));
   TRY(dev_alloc(c, pool, &c->cold_cur, cap));
   TRY(dev_alloc(c, pool, &c->cold_alt, cap));
   TRY(dev_alloc(c, pool, &c->coldf_cur, cap));
   TRY(dev_alloc(c, pool, &c->coldf_alt, cap));
   CUDA_TRY(c, cudaMemset(c->cold_cur, 0, (size_t)cap * sizeof(Cold)));
   CUDA_TRY(c, cudaMemset(c->coldf_cur, 0, (size_t)cap * sizeof(ColdF)));
+  for (int q = 0; q < 2; ++q) {
+    TRY(dev_alloc(c, pool, &p.pos[q], cap));
+    CUDA_TRY(c, cudaMemset(p.pos[q], 0, (size_t)cap * sizeof(double)));
+  }
+  TRY(dev_alloc(c, pool, &c->pos_alt, cap));
   if (n) {
-    CUDA_TRY(c, cudaMemcpy(c->cur8[P8_SA], sa.data(), (size_t)n * sizeof(SA), cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(c->cur8[P8_POS], pos, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(c->cur4[P4_AUX], aux.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->hot_cur, hot.data(), (size_t)n * sizeof(Hot), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(p.pos[0], pos, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(p.pos[1], pos, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(c->cold_cur, cold.data(), (size_t)n * sizeof(Cold), cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(c->coldf_cur, coldf.data(), (size_t)n * sizeof(ColdF), cudaMemcpyHostToDevice));
   }
-  CUDA_TRY(c, cudaMemset(c->cur4[P4_TJ], 0xFF, (size_t)cap * sizeof(int32_t)));
-  double* pos1 = nullptr;
-  TRY(dev_alloc(c, pool, &pos1, cap));
-  if (n) CUDA_TRY(c, cudaMemcpy(pos1, pos, (size_t)n * 8, cudaMemcpyHostToDevice));
-  p.pos[1] = pos1;
-  bind_slot_arrays(c, 0);
+  p.hot = c->hot_cur;
+  p.cold = c->cold_cur;
+  p.coldf = c->coldf_cur;
 
   TRY(dev_alloc(c, pool, &p.touched, 2 * cap));
   TRY(dev_alloc(c, pool, &p.slow, cap));
@@ -1058,7 +1028,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
 #endif
   CUDA_TRY(c, cudaMemset(p.counters, 0, 2 * CNT_STRIDE * sizeof(int32_t)));
   {
-    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n_agenda, 0, 0, 0, 0};
+    int32_t scal[SC_COUNT] = {0, (int32_t)n, 0, (int32_t)n_agenda, dead0, 0, 0, 0};
     CUDA_TRY(c, cudaMemcpy(p.scal, scal, sizeof(scal), cudaMemcpyHostToDevice));
   }
   // reorder scratch
@@ -1101,7 +1071,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
         return fail(c, GRIDDY_ERR_BAD_ARG, "actor " + std::to_string(a) + " is not on this rank's part of the world");
   for (size_t k = 0; k < tl.beg.size(); ++k) {
     const int64_t m = tl.end[k] - tl.beg[k];
-    if (m > 0) k_lane_init<<<(unsigned)((m + 255) / 256), 256>>>(p.lane + tl.beg[k], p.item + tl.beg[k], m);
+    if (m > 0) k_lane_init<<<(unsigned)((m + 255) / 256), 256>>>(p.lane + tl.beg[k], m);
   }
   if (!tail_lane.empty()) {
     std::vector<void*> tmp;
@@ -1509,24 +1479,29 @@ int download_state(Ctx* c, bool by_slot, int32_t* gid, uint8_t* alive, uint8_t* 
   if (order || n_order) {
     // get-actors order (world.scm:24-30): containers by descending registration index, a lane's
     // actors by descending pos-param, a segment's in list order (landing stamps, see lanes.cuh).
-    std::vector<SA> sa(ns);
+    // What the comparison needs of every slot, packed on the device into 32 bytes (instead of pulling the hot and
+    // both cold records, 160 bytes a slot); the living actors' slots are then sorted here.
+    OrderRec* d_rec = nullptr;
+    std::vector<void*> tmp;
+    TRY(dev_alloc(c, tmp, &d_rec, ns));
+    k_pack_order<<<blocks, 256, 0, c->stream>>>(p, tick & 1, c->d_ghost, d_rec);
+    ++c->launches;
+    std::vector<OrderRec> rec(ns);
+    const cudaError_t e = cudaMemcpy(rec.data(), d_rec, (size_t)ns * sizeof(OrderRec), cudaMemcpyDeviceToHost);
+    free_pool(tmp);
+    CUDA_TRY(c, e);
     std::vector<uint32_t> st(ns);
     std::vector<uint8_t> ghost(ns);
     std::vector<int32_t> cont(ns), land_tick(ns), land_lane(ns), ident(ns);
     std::vector<double> ps(ns), land_pos(ns);
-    auto pull = [&](void* dst, const void* src, size_t bytes) { return bytes ? cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) : cudaSuccess; };
-    CUDA_TRY(c, pull(sa.data(), p.sa, ns * sizeof(SA)));
-    for (int32_t a = 0; a < ns; ++a) st[a] = sa[a].st;
-    CUDA_TRY(c, pull(ghost.data(), c->d_ghost, ns));
-    std::vector<Cold> cold(ns);
-    std::vector<ColdF> coldf(ns);
-    CUDA_TRY(c, pull(cold.data(), p.cold, ns * sizeof(Cold)));
-    CUDA_TRY(c, pull(coldf.data(), p.coldf, ns * sizeof(ColdF)));
     for (int32_t a = 0; a < ns; ++a) {
-      cont[a] = cold[a].container; ident[a] = cold[a].gid;
-      land_tick[a] = coldf[a].land_tick; land_lane[a] = coldf[a].land_lane; land_pos[a] = coldf[a].land_pos;
+      const OrderRec& r = rec[a];
+      st[a] = r.st & ~ORDER_GHOST; ghost[a] = (r.st & ORDER_GHOST) ? 1 : 0;
+      cont[a] = r.container; ident[a] = r.gid;
+      land_tick[a] = r.land_tick; land_lane[a] = r.land_lane;
+      // on the road the order is by pos-param, off the road by landing stamp: one slot serves both
+      ps[a] = r.key; land_pos[a] = r.key;
     }
-    CUDA_TRY(c, pull(ps.data(), p.pos[tick & 1], ns * sizeof(double)));
     std::vector<int32_t> ord;
     ord.reserve(ns);
     for (int32_t a = 0; a < ns; ++a)

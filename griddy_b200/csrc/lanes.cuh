@@ -23,7 +23,7 @@ __device__ __forceinline__ bool stamp_less(const Params& p, int a, int b, uint32
 // Is a before b in their segment's list at `tick`?  The list reverses every tick (core.scm:169-171
 // conses while get-actors walks head to tail), so a stamp's sign alternates with tick parity.
 __device__ bool offroad_before(const Params& p, int a, int b, int tick) {
-  const uint32_t sta = p.sa[a].st, stb = p.sa[b].st;
+  const uint32_t sta = p.hot[a].st, stb = p.hot[b].st;
   const bool nega = (((tick - p.coldf[a].land_tick) & 1) != 0) == ((sta & ST_CLASS_P) != 0);
   const bool negb = (((tick - p.coldf[b].land_tick) & 1) != 0) == ((stb & ST_CLASS_P) != 0);
   if (nega != negb) return nega;
@@ -33,7 +33,7 @@ __device__ bool offroad_before(const Params& p, int a, int b, int tick) {
 // Of two actors landing on the same (lane, pos-param) this tick: the one visited later, which is
 // the one bbtree-set keeps (core.scm:173-178).
 __device__ int later_processed(const Params& p, int x, int y, int32_t lane, const double* pos_old, int tick) {
-  const uint32_t sx = p.sa[x].st, sy = p.sa[y].st;
+  const uint32_t sx = p.hot[x].st, sy = p.hot[y].st;
   const int32_t mx = (sx & ST_MOVED) ? p.cold[x].mv_old : lane, my = (sy & ST_MOVED) ? p.cold[y].mv_old : lane;
   const int32_t cx = mx < 0 ? ~mx : mx, cy = my < 0 ? ~my : my;
   if (cx != cy) return cx < cy ? x : y;
@@ -51,6 +51,9 @@ __device__ int later_processed(const Params& p, int x, int y, int32_t lane, cons
 //   k_link    (after every lane has been unlinked, so a mover's pointers are free to overwrite)
 //             inserts the lane's entrants (its inbox, sorted) by walking up from the rear — entrants
 //             land near pos 0, so that is a step or two — and writes their final pointers.
+// The usual case — one leaver at the front, one entrant at the rear — touches the lane's record and the hot
+// records of the mover and of its neighbour, nothing else: LaneRec::meta says how many leavers / entrants were
+// pushed, so the chains through the cold records are followed only when there are several.
 // Residents keep their relative order (a follower is clamped behind its leader, route.scm:68-74).
 // Equal keys: an entrant that lands on a resident's or another entrant's key is resolved in k_link,
 // the later-processed one stays (core.scm:173-178); two residents that round to the same key are left
@@ -74,75 +77,78 @@ __global__ void __launch_bounds__(128, MG ? 12 : 1) k_unlink(Params p, int tick)
   const int32_t stride = ((int)gridDim.x - (MG ? EMIG_BLOCKS : 0)) * blockDim.x;
   for (int32_t i = first; i < n_touched; i += stride) {
     const int32_t lane = p.touched[i];
-    const LaneDyn ld = p.lane[lane];
-    if (ld.outbox < 0 && ld.ghosts < 0) continue;
-    if (ld.outbox >= 0) p.lane[lane].outbox = -1;
-    if (ld.ghosts >= 0) p.lane[lane].ghosts = -1;
-    int32_t tail = ld.tail, gone = 0, died = 0;
+    LaneRec* lr = &p.lane[lane];
+    const uint32_t meta = lr->meta;
+    const int4 heads = *(const int4*)&lr->tail;   // tail, inbox, outbox, ghosts
+    const int32_t outbox = heads.z, ghosts = heads.w;
+    const int n_out = (int)((meta & META_OUT) >> 4);
+    atomicAnd(&lr->meta, ~META_LEFT);
+    if (outbox >= 0) lr->outbox = -1;
+    if (ghosts >= 0) lr->ghosts = -1;
+    int32_t tail = heads.x, gone = 0, died = 0;
     // A ghost that also moved is on both lists; the second visit finds it UNLINKED.
-    auto unlink = [&](int32_t z, int32_t b) {
-      const int32_t f = p.sa[z].ahead;
+    auto unlink = [&](int32_t z, int32_t f, int32_t b) {
       if (f == UNLINKED) return false;
-      if (b >= 0) p.sa[b].ahead = f; else tail = f;
-      if (f >= 0) p.cold[f].behind = b;
-      p.sa[z].ahead = UNLINKED;
+      if (b >= 0) p.hot[b].ahead = f; else tail = f;
+      if (f >= 0) p.hot[f].behind = b;
+      p.hot[z].ahead = UNLINKED;
       return true;
     };
-    for (int32_t z = ld.outbox; z >= 0;) {
-      const Cold k = p.cold[z];
-      unlink(z, k.behind);
+    for (int32_t z = outbox, k = 0; z >= 0; ++k) {
+      const int4 h = *(const int4*)&p.hot[z];   // st, ahead, behind, tj
+      unlink(z, h.y, h.z);
       ++gone;   // every mover leaves its old lane, whatever becomes of it
-      const uint32_t sz = p.sa[z].st;
-      if (k.dead_mark == tick + 1 || (sz & ST_EMIG)) { p.sa[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG); ++died; }
-      else if (!(sz & ST_ONROAD)) p.sa[z].st = sz & ~ST_MOVED;   // went off the road: nothing to link
-      z = k.outbox_next;
+      const uint32_t sz = (uint32_t)h.x;
+      if (sz & (ST_GHOST | ST_EMIG)) { p.hot[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG); ++died; }
+      else if (!(sz & ST_ONROAD)) p.hot[z].st = sz & ~ST_MOVED;   // went off the road: nothing to link
+      z = k + 1 < n_out ? p.cold[z].outbox_next : -1;   // (the usual single leaver: its cold record is not read)
     }
-    for (int32_t z = ld.ghosts; z >= 0;) {
-      const Cold k = p.cold[z];
-      const uint32_t sz = p.sa[z].st;
-      if (unlink(z, k.behind) && !(sz & ST_MOVED)) {   // (one that also moved was settled above)
-        p.sa[z].st = sz & ~ST_ALIVE;
+    for (int32_t z = ghosts; z >= 0;) {
+      const int4 h = *(const int4*)&p.hot[z];
+      const uint32_t sz = (uint32_t)h.x;
+      if (unlink(z, h.y, h.z) && !(sz & ST_MOVED)) {   // (one that also moved was settled above)
+        p.hot[z].st = sz & ~ST_ALIVE;
         ++gone;
         ++died;
       }
-      z = k.ghost_next;
+      z = p.cold[z].ghost_next;
     }
-    if (tail != ld.tail) p.lane[lane].tail = tail;
-    if (ld.junction >= 0 && gone) atomicSub(&p.occ[ld.junction], gone);
+    if (tail != heads.x) lr->tail = tail;
+    if (gone && meta_kind(meta) == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[lr->link2], gone);
     if (died) atomicAdd(&p.scal[SC_NDEAD], died);   // dead slots pile up until the next reorder drops them
   }
 }
 
-// After this tick's immigrants are unpacked (k_link runs behind k_immig_unpack): empty my
-// receive buffers of this parity.  The sender writes them again two ticks from now, after it has
-// received the halo I send next tick.
-__device__ __forceinline__ void mig_reset(const Params& p, int par) {
-  if (blockIdx.x == 0 && threadIdx.x < MAX_RANKS && p.mig_mine[threadIdx.x][par]) *p.mig_mine[threadIdx.x][par] = 0;
-}
+// After this tick's immigrants are unpacked (k_link runs behind k_immig_unpack): nothing to reset — the
+// sender overwrites header and records two ticks from now, after it has received the halo I send next tick.
 
 __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
   grid_dependency_wait();
   TRACE(p, tick, TR_LINK);
   const int par = tick & 1;
   const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_ENTERED];
-  mig_reset(p, par);
   const double* __restrict__ pos_old = p.pos[par];
   const double* __restrict__ pos_new = p.pos[par ^ 1];
   const int32_t* __restrict__ entered = p.touched + p.cap;
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = entered[i];
-    const LaneDyn ld = p.lane[lane];
-    const int32_t inbox = ld.inbox;
+    LaneRec* lr = &p.lane[lane];
+    const uint32_t meta = lr->meta;
+    const int4 heads = *(const int4*)&lr->tail;   // tail, inbox, outbox, ghosts
+    const int32_t inbox = heads.y;
+    const bool single = (meta & META_IN) == META_IN_ONE;
+    atomicAnd(&lr->meta, ~META_IN);
     if (inbox < 0) continue;
-    p.lane[lane].inbox = -1;
+    lr->inbox = -1;
+    auto next_in = [&](int32_t y) { return single ? -1 : p.cold[y].inbox_next; };
     // entrants by ascending (pos-param, slot): selection over the inbox, which is short
     double e_pos = 0.0;
     int32_t e = -1;
     auto next_entrant = [&](bool first) {
       int32_t best = -1;
       double best_pos = 0.0;
-      for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
-        if (!(p.sa[y].st & ST_MOVED)) continue;   // a ghost's move is void: k_unlink settled it
+      for (int32_t y = inbox; y >= 0; y = next_in(y)) {
+        if (!(p.hot[y].st & ST_MOVED)) continue;   // a ghost's move is void: k_unlink settled it
         const double py = pos_new[y];
         if (!first && !(py > e_pos || (py == e_pos && y > e))) continue;
         if (best < 0 || py < best_pos || (py == best_pos && y < best)) { best = y; best_pos = py; }
@@ -150,36 +156,39 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
       e = best;
       e_pos = best_pos;
     };
+    int32_t tail = heads.x;
     auto link = [&](int32_t b, int32_t z, int32_t f) {   // b -> z -> f
-      if (b < 0) p.lane[lane].tail = z; else p.sa[b].ahead = z;
-      p.sa[z].ahead = f;
-      p.cold[z].behind = b;
-      if (f >= 0) p.cold[f].behind = z;
+      if (b < 0) tail = z; else p.hot[b].ahead = z;
+      p.hot[z].ahead = f;
+      p.hot[z].behind = b;
+      if (f >= 0) p.hot[f].behind = z;
     };
-    int32_t prev = -1, x = ld.tail, delta = 0, died = 0;
+    int32_t prev = -1, x = heads.x, delta = 0, died = 0;
     for (next_entrant(true); e >= 0; next_entrant(false)) {
-      while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = p.sa[x].ahead; }
+      while (x >= 0 && pos_new[x] < e_pos) { prev = x; x = p.hot[x].ahead; }
       if (x >= 0 && pos_new[x] == e_pos) {   // equal key: bbtree-set keeps the one processed later
         const bool e_wins = later_processed(p, e, x, lane, pos_old, tick) == e;
         const int32_t lose = e_wins ? x : e;
-        const uint32_t sl = p.sa[lose].st;
-        p.sa[lose].st = sl & ~ST_ALIVE;        // (still marked moved if it is an entrant: see below)
+        const uint32_t sl = p.hot[lose].st;
+        p.hot[lose].st = sl & ~ST_ALIVE;        // (still marked moved if it is an entrant: see below)
         ++died;
         if (!(sl & ST_MOVED) || lose == x) --delta;   // a resident, or an entrant that had been counted in
-        if (!e_wins) continue;
-        link(prev, e, p.sa[x].ahead);   // e takes x's place
+        if (!e_wins) { if (single) break; continue; }
+        link(prev, e, p.hot[x].ahead);   // e takes x's place
       } else {
         link(prev, e, x);
       }
       ++delta;
       x = e;   // the next entrant (same or higher key) meets e first
+      if (single) break;
     }
     // the entrants stayed marked as movers so that ties among them could look at where they came from
-    for (int32_t y = inbox; y >= 0; y = p.cold[y].inbox_next) {
-      const uint32_t sy = p.sa[y].st;
-      if (sy & ST_MOVED) p.sa[y].st = sy & ~(ST_MOVED | ST_IMMIG);
+    for (int32_t y = inbox; y >= 0; y = next_in(y)) {
+      const uint32_t sy = p.hot[y].st;
+      if (sy & ST_MOVED) p.hot[y].st = sy & ~(ST_MOVED | ST_IMMIG);
     }
-    if (ld.junction >= 0 && delta) atomicAdd(&p.occ[ld.junction], delta);
+    if (tail != heads.x) lr->tail = tail;
+    if (delta && meta_kind(meta) == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[lr->link2], delta);
     if (died) atomicAdd(&p.scal[SC_NDEAD], died);
   }
 }

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_halo_pack(Params p, const int32_t* __re
     } else {
       const double* __restrict__ pos = p.pos[par];
       int32_t x = p.lane[item].tail;
-      while (x >= 0 && !(pos[x] > 0.0)) x = p.sa[x].ahead;
+      while (x >= 0 && !(pos[x] > 0.0)) x = p.hot[x].ahead;
       v = x >= 0 ? pos[x] : __longlong_as_double(0x7ff0000000000000LL);
     }
     int r = 0;
@@ -127,30 +127,29 @@ __device__ __forceinline__ void emig_pack_block(const Params& p, const int tick,
     MigRec r;
     if (i < n) {
       a = p.emig[i];
-      const Cold k = p.cold[a];
-      if (k.dead_mark == tick + 1) {
+      const Hot h = p.hot[a];
+      if (h.st & ST_GHOST) {
         a = -1;   // a ghost's move is void
       } else {
         // the whole record is gathered before a place is reserved: one round trip less on the way
+        const Cold k = p.cold[a];
         const ColdF f = p.coldf[a];
-        const double2 db = p.db[a];
-        const int32_t tj = p.tj[a];
         to = p.owner[k.container];
         mine = atomicAdd(&s_count[to], 1);
         r.pos_old = p.pos[par][a];
         r.pos_new = p.pos[par ^ 1][a];
-        r.delta = db.x;
-        r.buf = db.y;
+        r.delta = h.delta;
+        r.buf = h.buf;
         r.arrive = f.arrive;
         r.land_pos = f.land_pos;
-        r.speed = f.speed;
-        r.speed_dt = f.speed_dt;
+        r.speed = k.speed;
+        r.speed_dt = k.speed_dt;
         r.gid = k.gid;
-        r.st = (int32_t)(((p.sa[a].st | ST_ALIVE | ST_MOVED) & ~ST_EMIG) | ST_IMMIG);
+        r.st = (int32_t)(((h.st | ST_ALIVE | ST_MOVED) & ~ST_EMIG) | ST_IMMIG);
         r.container = k.container;
         r.mv_old = k.mv_old;
         r.hop = k.hop;
-        r.tj = tj >= 0 ? (tj & ~TJ_REMOTE) : -1;
+        r.tj = h.tj >= 0 ? (h.tj & ~TJ_REMOTE) : -1;
         r.dest_lane = k.dest_lane;
         r.dest_from_j = k.dest_from_j;
         r.dest_to_j = k.dest_to_j;
@@ -229,40 +228,51 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
       continue;
     }
     if (it + r.n_items > p.icap) {   // no room for its agenda: the slot stays counted, but dead
-      p.sa[a] = SA{0u, -1};
+      p.hot[a].st = 0u;
       dev_error(p, DEV_ERR_MIG_OVERFLOW);
       continue;
     }
-    p.coldf[a].speed = r.speed;
-    p.coldf[a].speed_dt = r.speed_dt;
-    p.cold[a].gid = r.gid;
-    p.coldf[a].agenda_beg = it - r.popped;   // only the items not yet popped travelled; the head is item `it`
-    p.coldf[a].agenda_end = it + r.n_items;
-    for (int k = 0; k < r.n_items; ++k) p.agenda[it + k] = payload[r.item_off + k];
-    p.sa[a] = SA{(uint32_t)r.st, -1};
-    p.cold[a].behind = -1;
+    Cold k;
+    k.container = r.container;
+    k.hop = r.hop;
+    k.dest_lane = r.dest_lane;
+    k.dest_from_j = r.dest_from_j;
+    k.dest_to_j = r.dest_to_j;
+    k.mv_old = r.mv_old;
+    k.outbox_next = -1;
+    k.speed = r.speed;
+    k.speed_dt = r.speed_dt;
+    k.agenda_cur = it;
+    k.route_cur = r.route_cur;
+    k.ghost_next = -1;
+    k.gid = r.gid;
+    ColdF f;
+    f.arrive = r.arrive;
+    f.land_pos = r.land_pos;
+    f.agenda_beg = it - r.popped;   // only the items not yet popped travelled; the head is item `it`
+    f.agenda_end = it + r.n_items;
+    f.land_tick = r.land_tick;
+    f.land_lane = r.land_lane;
+    for (int q = 0; q < 8; ++q) f.pad[q] = 0;
+    for (int q = 0; q < r.n_items; ++q) p.agenda[it + q] = payload[r.item_off + q];
+    Hot h;
+    h.st = (uint32_t)r.st;
+    h.ahead = -1;
+    h.behind = -1;
+    h.tj = tag_junction(p, r.tj);
+    h.delta = r.delta;
+    h.buf = r.buf;
+    p.hot[a] = h;
     p.pos[par][a] = r.pos_old;       // processing order among a lane's entrants looks at old lane and old key
     p.pos[par ^ 1][a] = r.pos_new;
-    p.db[a] = make_double2(r.delta, r.buf);
-    p.coldf[a].arrive = r.arrive;
-    p.coldf[a].land_pos = r.land_pos;
-    p.cold[a].container = r.container;
-    p.cold[a].mv_old = r.mv_old;
-    p.aux[a] = 0;
-    p.cold[a].hop = r.hop;
-    p.cold[a].dest_lane = r.dest_lane;
-    p.cold[a].dest_from_j = r.dest_from_j;
-    p.cold[a].dest_to_j = r.dest_to_j;
-    p.tj[a] = tag_junction(p, r.tj);
-    p.cold[a].agenda_cur = it;
-    p.cold[a].route_cur = r.route_cur;
-    p.coldf[a].land_tick = r.land_tick;
-    p.coldf[a].land_lane = r.land_lane;
-    p.cold[a].dead_mark = 0;
+    p.coldf[a] = f;
     // onto the lane's inbox
-    p.cold[a].inbox_next = atomicExch(&p.lane[r.container].inbox, a);
-    if (atomicExch(&p.lane[r.container].mark_in, tick + 1) != tick + 1)
-      p.touched[p.cap + atomicAdd(&p.counters[CNT_STRIDE * par + CNT_ENTERED], 1)] = r.container;
+    LaneRec* lr = &p.lane[r.container];
+    k.inbox_next = atomicExch(&lr->inbox, a);
+    p.cold[a] = k;
+    const uint32_t old = atomicAdd(&lr->meta, META_IN_ONE);
+    if (!(old & META_IN)) p.touched[p.cap + atomicAdd(&p.counters[CNT_STRIDE * par + CNT_ENTERED], 1)] = r.container;
+    else if ((old & META_IN) == META_IN) dev_error(p, DEV_ERR_LANE_BURST);
   }
 }
 

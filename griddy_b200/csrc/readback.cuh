@@ -10,17 +10,17 @@ namespace griddy {
 __global__ void __launch_bounds__(256) k_flag_ghosts(Params p, int par, uint8_t* ghost) {
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.sa[a].st;
+  const uint32_t st = p.hot[a].st;
   if ((st & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD)) return;
   const double* pos = p.pos[par];
   const double cur = pos[a];
-  for (int32_t x = p.sa[a].ahead; x >= 0 && pos[x] == cur; x = p.sa[x].ahead) ghost[x] = 1;
+  for (int32_t x = p.hot[a].ahead; x >= 0 && pos[x] == cur; x = p.hot[x].ahead) ghost[x] = 1;
 }
 
 // Living actors of the world: alive and not a ghost.
 __global__ void __launch_bounds__(256) k_count_alive(Params p, const uint8_t* ghost, unsigned long long* out) {
   const int a = blockIdx.x * 256 + threadIdx.x;
-  const bool live = a < p.scal[SC_NSLOTS] && (p.sa[a].st & ST_ALIVE) && !ghost[a];
+  const bool live = a < p.scal[SC_NSLOTS] && (p.hot[a].st & ST_ALIVE) && !ghost[a];
   const uint32_t m = __ballot_sync(0xffffffffu, live);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
@@ -35,10 +35,10 @@ struct PackOut {
 __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uint8_t* ghost, PackOut o) {
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.sa[a].st;
+  const uint32_t st = p.hot[a].st;
   const int32_t id = o.by_slot ? a : p.cold[a].gid;
   const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
-  const int32_t aux = p.aux[a];
+  const int32_t aux = p.hot[a].tj;
   if (o.gid) o.gid[id] = p.cold[a].gid;
   if (o.alive) o.alive[id] = ((st & ST_ALIVE) && !ghost[a]) ? 1 : 0;
   if (o.loc_kind) o.loc_kind[id] = (st & ST_ONROAD) ? 1 : 0;
@@ -49,6 +49,31 @@ __global__ void __launch_bounds__(256) k_pack_state(Params p, int par, const uin
   if (o.sleep_left) o.sleep_left[id] = head == HEAD_SLEEP ? aux : 0;
   if (o.route_status) o.route_status[id] = (uint8_t)rs;
   if (o.route_head) o.route_head[id] = rs == GRIDDY_ROUTE_SOME ? p.cold[a].hop : -2;
+}
+
+// What the get-actors order (world.scm:24-30) of a slot depends on, for the read-back's sort: 32 bytes per slot.
+constexpr uint32_t ORDER_GHOST = 0x80000000u;
+struct __align__(16) OrderRec {
+  double key;        // on the road: pos-param; off the road: the landing stamp's pos-param
+  uint32_t st;       // ST_* | ORDER_GHOST
+  int32_t container, land_tick, land_lane, gid, pad;
+};
+static_assert(sizeof(OrderRec) == 32, "one sector per slot");
+
+__global__ void __launch_bounds__(256) k_pack_order(Params p, int par, const uint8_t* __restrict__ ghost, OrderRec* __restrict__ out) {
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= p.scal[SC_NSLOTS]) return;
+  const uint32_t st = p.hot[a].st;
+  const ColdF f = p.coldf[a];
+  OrderRec r;
+  r.key = (st & ST_ONROAD) ? p.pos[par][a] : f.land_pos;
+  r.st = st | (ghost[a] ? ORDER_GHOST : 0u);
+  r.container = p.cold[a].container;
+  r.land_tick = f.land_tick;
+  r.land_lane = f.land_lane;
+  r.gid = p.cold[a].gid;
+  r.pad = 0;
+  out[a] = r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -69,14 +94,14 @@ __global__ void __launch_bounds__(256) k_digest(Params p, int par, const uint8_t
   uint64_t h = 0;
   bool live = false;
   if (a < p.scal[SC_NSLOTS]) {
-    const uint32_t st = p.sa[a].st;
+    const uint32_t st = p.hot[a].st;
     if ((st & ST_ALIVE) && !ghost[a]) {
       live = true;
       const Cold k = p.cold[a];
       const int head = (st >> ST_HEAD_SHIFT) & 3, rs = (st >> ST_RS_SHIFT) & 3;
       const uint64_t on_road = (st & ST_ONROAD) ? 1 : 0, side = (!on_road && (st & ST_SIDE)) ? 1 : 0;
       const uint32_t popped = (uint32_t)(k.agenda_cur - p.coldf[a].agenda_beg);
-      const uint32_t sleep_left = head == HEAD_SLEEP ? (uint32_t)p.aux[a] : 0u;
+      const uint32_t sleep_left = head == HEAD_SLEEP ? (uint32_t)p.hot[a].tj : 0u;
       const uint32_t route_head = (uint32_t)(rs == GRIDDY_ROUTE_SOME ? k.hop : -2);
       h = mix64((uint64_t)(int64_t)k.gid + 1);
       h = mix64(h ^ ((uint64_t)(uint32_t)k.container | (on_road << 32) | (side << 33) | ((uint64_t)rs << 34)));
@@ -105,13 +130,13 @@ __global__ void __launch_bounds__(256) k_occupancy(Params p, const uint8_t* __re
                                                     int32_t* __restrict__ junction_count) {
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= p.scal[SC_NSLOTS]) return;
-  const uint32_t st = p.sa[a].st;
+  const uint32_t st = p.hot[a].st;
   if (!(st & ST_ALIVE)) return;
   const int32_t c = p.cold[a].container;
   if (!ghost[a]) {
     if (lane_count) atomicAdd(&lane_count[c], 1);
-  } else if (junction_count && p.item[c].kind == GRIDDY_JUNCTION_LANE) {
-    atomicSub(&junction_count[p.item[c].link2], 1);
+  } else if (junction_count && meta_kind(p.lane[c].meta) == GRIDDY_JUNCTION_LANE) {
+    atomicSub(&junction_count[p.lane[c].link2], 1);
   }
 }
 
@@ -134,7 +159,7 @@ __global__ void __launch_bounds__(256) k_positions(Params p, int par, const doub
   const int a = blockIdx.x * 256 + threadIdx.x;
   if (a >= n_bound) return;   // the host's upper bound of the slots in use: what it will copy
   const bool used = a < p.scal[SC_NSLOTS];
-  const uint32_t st = used ? p.sa[a].st : 0u;
+  const uint32_t st = used ? p.hot[a].st : 0u;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   double x = nan, y = nan;
   int32_t id = -1;
@@ -143,7 +168,7 @@ __global__ void __launch_bounds__(256) k_positions(Params p, int par, const doub
     id = p.cold[a].gid;
     const double t = p.pos[par][a];
     const double2* g = geom + 4 * (int64_t)c;
-    if (!(st & ST_ONROAD) || p.item[c].kind == GRIDDY_SEGMENT_LANE) {
+    if (!(st & ST_ONROAD) || meta_kind(p.lane[c].meta) == GRIDDY_SEGMENT_LANE) {
       const double2 o = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? g[2] : g[0];
       const double2 v = g[1];
       x = __dadd_rn(o.x, __dmul_rn(t, v.x));

@@ -14,10 +14,11 @@ constexpr int HOP_ARRIVE = -1;
 
 constexpr uint32_t ST_EMIG = 1024u;     // multi-GPU: moved onto a lane another rank owns (this slot dies in k_unlink)
 constexpr uint32_t ST_IMMIG = 2048u;    // multi-GPU: arrived from another rank this tick (cleared in k_link)
+constexpr uint32_t ST_GHOST = 4096u;    // found to be a ghost (its follower holds an equal key): k_unlink of this tick removes it
 
 constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
               DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32, DEV_ERR_MIG_OVERFLOW = 64,
-              DEV_ERR_MIG_AGENDA = 128, DEV_ERR_MIG_TIMEOUT = 256;
+              DEV_ERR_MIG_AGENDA = 128, DEV_ERR_MIG_TIMEOUT = 256, DEV_ERR_LANE_BURST = 512;
 
 // Params::counters[parity][...]
 constexpr int CNT_EMIG = 0, CNT_LEFT = 1, CNT_SLOW = 2, CNT_ENTERED = 3, CNT_STRIDE = 4;
@@ -55,60 +56,63 @@ constexpr int SC_ERR = 0, SC_NSLOTS = 1, SC_NALIVE = 2, SC_NITEMS = 3, SC_NDEAD 
 constexpr int MAX_RANKS = 8;     // one box
 constexpr int MAX_RANGES = 64;   // id ranges of a tiled network (griddy_set_item_ranges)
 
-// st and ahead of a slot share an 8-byte word: every kernel that walks a lane needs both.
-struct __align__(8) SA {
-  uint32_t st;
-  int32_t ahead;
+// The per-slot state every actor reads every tick, one 32-byte sector: k_advance streams it with two 16-byte
+// loads, and an actor that changes lane rewrites one sector instead of three.
+struct __align__(16) Hot {
+  uint32_t st;       // ST_* flags
+  int32_t ahead;     // slot of the next actor ahead on the lane (ascending pos-param), -1 at the front
+  int32_t behind;    // slot of the next actor behind, -1 at the rear
+  int32_t tj;        // on a route: junction of the lane the route head turns onto (-1: none; TJ_REMOTE tag);
+                     // asleep (no route): the remaining (sleep-for t) time
+  double delta, buf; // fl(speed*dt)*fl(1/len) and 10/len on the current lane (route.scm:62-66), cached at lane entry
 };
+static_assert(sizeof(Hot) == 32, "one sector per slot");
 
 // Everything about a slot that only matters when its actor does something rare (changes lane, wakes,
-// starts or ends a route), in one 64-byte record — one DRAM burst instead of a dozen sectors.
+// starts or ends a route), in one 64-byte line.  A lane change reads the whole line and writes the first sector;
+// k_unlink / k_link touch it only when a lane has several leavers / entrants in one tick, or on a tie.
 struct __align__(16) Cold {
-  // first sector: where the actor is and where it is going (read by a lane change, k_make_keys, read-back)
+  // first sector
   int32_t container;                  // lane (on road) or segment (off road)
-  int32_t agenda_cur, route_cur;      // agenda head (index into the item arrays), route head (explicit routes)
-  int32_t gid;                        // the actor's id (global id on a partitioned world)
   int32_t hop;                        // head of the route: lane of (turn-onto lane), or -1 for (arrive-at _)
   int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions
-  // second sector: everything k_unlink / k_link read and write — list surgery touches this sector only
-  int32_t behind;                     // slot of the next actor behind on the lane (-1 at the rear)
   int32_t mv_old;                     // where a mover came from: lane, or ~segment
-  int32_t inbox_next, outbox_next, ghost_next;
-  int32_t dead_mark;                  // tick+1 when the actor was found to be a ghost during `tick`
-  int32_t spare[2];
+  int32_t inbox_next, outbox_next;    // this tick's entrants / leavers of a lane, chained
+  // second sector
+  double speed, speed_dt;             // max-speed and fl(max-speed * dt)
+  int32_t agenda_cur, route_cur;      // agenda head (index into the item pool), route head (explicit routes)
+  int32_t ghost_next;                 // ghosts found on a lane this tick, chained
+  int32_t gid;                        // the actor's id (global id on a partitioned world)
 };
-// The rest of an actor's rarely read state, also one burst.
+// The rest of an actor's rarely read state.
 struct __align__(16) ColdF {
   double arrive;            // target of the (arrive-at _) that ends the current route
   double land_pos;          // landing stamp (with land_tick, land_lane), see "processing order"
-  double speed, speed_dt;   // max-speed and fl(max-speed * dt)
-  int32_t agenda_beg, agenda_end;     // the actor's agenda in the item arrays
+  int32_t agenda_beg, agenda_end;     // the actor's agenda in the item pool
   int32_t land_tick, land_lane;
-  int32_t pad[4];
+  int32_t pad[8];
 };
-static_assert(sizeof(Cold) == 64 && sizeof(ColdF) == 64, "cold records are one DRAM burst each");
+static_assert(sizeof(Cold) == 64 && sizeof(ColdF) == 64, "cold records are one 64-byte line each");
 
-// The static network, one 32-byte record per registered item: a lane change reads its target lane's
-// kind, length, successor and junctions from one sector.
-struct __align__(16) Item {
+// One registered item, one 64-byte line: the static record (first sector: what a lane change reads of its
+// target) and, for lanes, the list heads and the row of the grid routing table (second sector).
+struct __align__(16) LaneRec {
   double len;             // lanes: length (host-computed, spatial.scm:28-46)
   int32_t link;           // segment lane: its segment; junction lane: the lane it leads onto; segment: outer forw-side lane
   int32_t link2;          // junction lane: its junction; segment: outer back-side lane
-  int32_t from_j, to_j;   // grid routing: junction a segment lane leaves / reaches
-  uint32_t loc_key;       // locality key for the reorder (default: the registration index)
-  uint8_t kind, dir;
-  uint16_t pad;
+  int32_t to_j;           // grid routing: junction a segment lane reaches
+  uint32_t meta;          // kind (bits 0-2), direction (bit 3); this tick's work marks: leavers pushed (bits 4-14),
+                          // ghost found (bit 15), entrants pushed (bits 16-31) — reset by k_unlink / k_link
+  int32_t pad[2];
+  int32_t tail;           // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
+  int32_t inbox, outbox, ghosts;   // this tick's entrants, leavers and ghosts (chained through Cold)
+  int32_t turn[4];        // grid routing: junction lane leading onto the segment that leaves this lane's end with heading h
 };
-// Per-lane list heads: rearmost actor, and this tick's entrants, leavers and ghosts.
-struct __align__(16) LaneDyn {
-  int32_t tail;      // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
-  int32_t inbox, outbox, ghosts;
-  int32_t mark_out;  // tick+1 once the lane is on this tick's list of lanes that lost an actor (k_unlink's work)
-  int32_t junction;  // junction lanes: their junction (whose occupancy they count towards), else -1
-  int32_t mark_in;   // tick+1 once the lane is on this tick's list of lanes that gained an actor (k_link's work)
-  int32_t pad;
-};
-static_assert(sizeof(Item) == 32 && sizeof(LaneDyn) == 32, "one sector per record");
+static_assert(sizeof(LaneRec) == 64, "one line per item");
+constexpr uint32_t META_KIND = 7u, META_DIR = 8u, META_OUT_ONE = 1u << 4, META_OUT = 0x7ff0u, META_GHOST = 1u << 15,
+                   META_LEFT = META_OUT | META_GHOST, META_IN_ONE = 1u << 16, META_IN = 0xffff0000u;
+__host__ __device__ __forceinline__ int meta_kind(uint32_t m) { return (int)(m & META_KIND); }
+__host__ __device__ __forceinline__ uint32_t meta_dir(uint32_t m) { return (m >> 3) & 1u; }
 
 // One agenda item (actor.scm:25-26), one sector.  A travel-to item carries its destination resolved at
 // upload time — off-road->on-road of the destination (location.scm:49-57): the outer lane of (segment, side),
@@ -127,19 +131,15 @@ static_assert(sizeof(AgendaItem) == 32, "one sector per agenda item");
 struct Params {
   // network, by registration index
   int64_t n_items;
-  Item* item;
-  LaneDyn* lane;
-  int32_t* occ;       // actors on a junction's lanes (route.scm:98-104); compact, so that it lives in L2
-  int32_t grid_n;
-  const int32_t* turn4;
+  LaneRec* lane;
+  int32_t* occ;       // actors on a junction's lanes (route.scm:98-104); compact, so that the busy part lives in L2
+  const uint32_t* loc_key;   // locality key per item (the reorder's sort key)
+  int32_t grid_n;     // > 0: LaneRec::turn / to_j hold the grid routing table
   // slots
   int32_t cap;     // allocated slots
   int32_t* scal;   // SC_*: device error bits, slots in use, live actors counted by the reorder
-  SA* sa;          // {st, ahead}: one 8-byte load per actor
+  Hot* hot;
   double* pos[2];
-  double2* db;    // {delta, buf}: fl(speed*dt)*fl(1/len) and 10/len on the current lane (route.scm:62-66), one 16-byte load
-  int32_t* aux;   // sleeping: remaining time; travelling: head route step (lane, or -1 arrive-at)
-  int32_t* tj;    // junction of the lane the route head turns onto, -1 if that is not a junction lane
   Cold* cold;
   ColdF* coldf;
   // agenda items (immutable; actors that arrive from another rank append theirs, a reorder compacts the pool)

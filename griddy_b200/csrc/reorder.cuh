@@ -5,20 +5,13 @@ namespace griddy {
 
 // ------------------------------------------------------------------------------------------------
 // Reorder: sort the live slots by (locality key of the container, coarse pos-param), permute every
-// per-slot array, remap the slot-valued pointers (ahead, lane_tail) and drop the dead.
-
-// Arrays that travel with an actor.  ahead is remapped through the inverse permutation.
-constexpr int PERM4 = 2, PERM8 = 2;
-enum { P4_AUX, P4_TJ };
-enum { P8_SA, P8_POS };
+// per-slot array, remap the slot-valued pointers (ahead, behind, lane tails) and drop the dead.
 
 struct Permute {
-  const uint32_t* src4[PERM4];
-  uint32_t* dst4[PERM4];
-  const uint64_t* src8[PERM8];
-  uint64_t* dst8[PERM8];
-  const double2* src_db;
-  double2* dst_db;
+  const Hot* src_hot;
+  Hot* dst_hot;
+  const double* src_pos;
+  double* dst_pos;
   const Cold* src_cold;
   Cold* dst_cold;
   const ColdF* src_coldf;
@@ -35,7 +28,7 @@ __global__ void __launch_bounds__(256) k_make_keys(Params p, int par, int key_bi
   uint32_t val = 0xffffffffu;
   bool live = false;
   if (s < p.scal[SC_NSLOTS]) {
-    const uint32_t st = p.sa[s].st;
+    const uint32_t st = p.hot[s].st;
     if (st & ST_ALIVE) {
       live = true;
       const int32_t c = p.cold[s].container;
@@ -43,7 +36,7 @@ __global__ void __launch_bounds__(256) k_make_keys(Params p, int par, int key_bi
       // 16 bits of pos-param over [-0.5, 1.5): enough to keep a lane's actors in list order
       const double q = fmin(fmax((x + 0.5) * 32768.0, 0.0), 65535.0);
       // off-road actors after the on-road ones: warps are then all-travelling or all-parked
-      key = ((uint64_t)((st & ST_ONROAD) ? 0u : 1u) << (key_bits - 1)) | ((uint64_t)p.item[c].loc_key << 16) | (uint64_t)(uint32_t)q;
+      key = ((uint64_t)((st & ST_ONROAD) ? 0u : 1u) << (key_bits - 1)) | ((uint64_t)p.loc_key[c] << 16) | (uint64_t)(uint32_t)q;
       val = (uint32_t)s;
       tailflag[s] = ((st & ST_ONROAD) && p.lane[c].tail == s) ? 1 : 0;
     }
@@ -68,17 +61,23 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
   if (s >= p.scal[SC_NALIVE]) return;
   const uint32_t old = vals[s];
   // ahead / behind are meaningful on the road only; an off-road actor's values are stale
-  SA sa = ((const SA*)q.src8[P8_SA])[old];
-  const bool on_road = sa.st & ST_ONROAD;
-#pragma unroll
-  for (int k = 0; k < PERM4; ++k) q.dst4[k][s] = q.src4[k][old];
-  Cold cold = q.src_cold[old];
-  if (on_road && cold.behind >= 0) {
-    cold.behind = newslot[cold.behind];
-    if (cold.behind < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's follower must be live
+  Hot h = q.src_hot[old];
+  const bool on_road = h.st & ST_ONROAD;
+  if (on_road && h.ahead >= 0) {
+    h.ahead = newslot[h.ahead];
+    if (h.ahead < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's leader must be live
   } else {
-    cold.behind = -1;
+    h.ahead = -1;
   }
+  if (on_road && h.behind >= 0) {
+    h.behind = newslot[h.behind];
+    if (h.behind < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's follower must be live
+  } else {
+    h.behind = -1;
+  }
+  q.dst_hot[s] = h;
+  q.dst_pos[s] = q.src_pos[old];
+  Cold cold = q.src_cold[old];
   ColdF coldf = q.src_coldf[old];
   if (q.agenda_dst) {   // only the items not yet popped are kept; agenda_beg stays "head minus items popped"
     const int32_t rem = coldf.agenda_end - cold.agenda_cur, popped = cold.agenda_cur - coldf.agenda_beg;
@@ -90,21 +89,6 @@ __global__ void __launch_bounds__(256) k_permute(Params p, Permute q, const uint
   }
   q.dst_cold[s] = cold;
   q.dst_coldf[s] = coldf;
-  q.dst_db[s] = q.src_db[old];
-#pragma unroll
-  for (int k = 0; k < PERM8; ++k) {
-    if (k == P8_SA) {
-      if (on_road && sa.ahead >= 0) {
-        sa.ahead = newslot[sa.ahead];
-        if (sa.ahead < 0) dev_error(p, DEV_ERR_INTERNAL);   // a live actor's leader must be live
-      } else {
-        sa.ahead = -1;
-      }
-      ((SA*)q.dst8[k])[s] = sa;
-    } else {
-      q.dst8[k][s] = q.src8[k][old];
-    }
-  }
   if (tailflag[old]) p.lane[cold.container].tail = s;
 }
 

@@ -43,6 +43,9 @@ struct Actor {
   int32_t sleep_left = 0;   // the head's time when it is (sleep-for time)   simulate.scm:77
   int route_status = ROUTE_NONE;
   size_t route_cur = 0;     // head of the route list held in Oracle::route_lanes / route_arrive
+  // lazy grid routes (Oracle::lazy_routes): the list element at index route_cur — a lane, or -1 for the final
+  // (arrive-at _) — and the route's last lane; the list itself is never materialised
+  int32_t lazy_head = -1, lazy_dest = -1;
 };
 
 struct Oracle {
@@ -72,6 +75,11 @@ struct Oracle {
   // only its own list, so one shared copy behaves identically.
   std::vector<std::vector<int32_t>> route_lanes;
   std::vector<double> route_arrive;
+  // With the grid rule the list is a pure function of (lane reached so far, destination): element k + 1
+  // follows from element k.  lazy_routes keeps only the head (Actor::lazy_head) and derives the next element
+  // when the head is popped — the same sequence find_route unrolls eagerly (tests/test_oracle_properties.py
+  // checks the two modes against each other), without 5 kB of lane ids per actor on a 1024 x 1024 grid.
+  bool lazy_routes = true;
   // actors on the junction lanes of each junction in the current world (route.scm:98-104), folded
   // once per tick instead of once per query; the old world does not change during a tick.
   std::vector<int32_t> junction_count;
@@ -105,6 +113,16 @@ int32_t grid_next_hop(const Oracle& o, int32_t lane, int32_t dest) {
     h = ej > jj ? 2 : 3;
   }
   return o.turn4[4 * (int64_t)lane + h];
+}
+
+// Element k + 1 of the grid rule's route list given element k (`x`; init = the lane the route starts on, which
+// is not part of the list): after a junction lane comes the lane it leads onto, after the destination lane the
+// final (arrive-at _) (-1), after any other segment lane the junction lane the rule picks (-2: none).
+int32_t grid_route_next(const Oracle& o, int32_t x, int32_t dest_lane) {
+  if (o.kind[x] == K_JLANE) return o.lane_out[x];
+  if (x == dest_lane) return -1;
+  const int32_t jl = grid_next_hop(o, x, dest_lane);
+  return jl < 0 ? -2 : jl;
 }
 
 // route.scm:17-51 as a route provider: explicit lane lists when uploaded, else the grid rule
@@ -212,7 +230,11 @@ bool advance(Oracle& o, int32_t a) {
     if (init_lane < 0 || dest_lane < 0) { o.err = "road-has-no-lanes"; return false; }
     const double init_pos = flip_for(o, init_lane, old.pos);
     const double dest_pos = flip_for(o, dest_lane, o.item_pos[it]);
-    if (!find_route(o, it, init_lane, dest_lane, o.route_lanes[a])) { o.err = "no route"; return false; }
+    if (o.grid_n > 0 && o.lazy_routes) {
+      nw.lazy_dest = dest_lane;
+      nw.lazy_head = grid_route_next(o, init_lane, dest_lane);   // element 0
+      if (nw.lazy_head == -2) { o.err = "no route"; return false; }
+    } else if (!find_route(o, it, init_lane, dest_lane, o.route_lanes[a])) { o.err = "no route"; return false; }
     o.route_arrive[a] = dest_pos;
     nw.route_cur = 0;
     nw.route_status = ROUTE_SOME;
@@ -221,15 +243,19 @@ bool advance(Oracle& o, int32_t a) {
   }
 
   if (head_kind == ITEM_TRAVEL && old.route_status == ROUTE_SOME) {   // route.scm:137-141
+    const bool lazy = o.grid_n > 0 && o.lazy_routes;
     const std::vector<int32_t>& lanes = o.route_lanes[a];
-    const bool head_arrive = old.route_cur >= lanes.size();
-    const int32_t head_lane = head_arrive ? -1 : lanes[old.route_cur];
+    const bool head_arrive = lazy ? old.lazy_head == -1 : old.route_cur >= lanes.size();
+    const int32_t head_lane = head_arrive ? -1 : (lazy ? old.lazy_head : lanes[old.route_cur]);
     const int32_t lane_current = old.container;
     const double pos_current = old.pos;
     const double next_naive = pos_param_next(o, pos_current, o.speed_dt[a], lane_current);
     auto route_pop = [&]() {   // actor.scm:33-34
       nw.route_cur = old.route_cur + 1;
-      if (nw.route_cur > lanes.size()) nw.route_status = ROUTE_DONE;
+      if (lazy) {
+        if (old.lazy_head == -1) nw.route_status = ROUTE_DONE;
+        else nw.lazy_head = grid_route_next(o, old.lazy_head, old.lazy_dest);
+      } else if (nw.route_cur > lanes.size()) nw.route_status = ROUTE_DONE;
     };
     if (head_arrive) {     // route.scm:76-90 arrive-at
       const double target_pos = o.route_arrive[a];
@@ -253,6 +279,7 @@ bool advance(Oracle& o, int32_t a) {
       } else pos_next = next_naive;
       const int32_t lane_next = (done && !waiting) ? target : lane_current;
       if (done && !waiting) route_pop();
+      if (nw.lazy_head == -2) { o.err = "no route"; return false; }
       link_on_road(o, a, lane_next, pos_next);
     }
     return true;
@@ -407,6 +434,13 @@ int go_load_actors(void* h, int64_t n, const uint8_t* loc_kind, const int32_t* c
   return ERR_OK;
 }
 
+// Grid rule only: 1 (default) derives the route head on demand, 0 unrolls the whole list at begin-route$ as
+// find-route returns it.  Same results; call before go_load_actors.
+int go_set_lazy_routes(void* h, int lazy) {
+  ((Oracle*)h)->lazy_routes = lazy != 0;
+  return ERR_OK;
+}
+
 int go_step(void* h, int64_t n_ticks) {
   Oracle& o = *(Oracle*)h;
   for (int64_t t = 0; t < n_ticks; ++t)
@@ -429,8 +463,10 @@ int go_get_state(void* h, uint8_t* alive, uint8_t* loc_kind, int32_t* container,
     sleep_left[a] = A.sleep_left;
     route_status[a] = (uint8_t)A.route_status;
     route_head[a] = -2;
-    if (A.route_status == ROUTE_SOME)
-      route_head[a] = A.route_cur < o.route_lanes[a].size() ? o.route_lanes[a][A.route_cur] : -1;
+    if (A.route_status == ROUTE_SOME) {
+      if (o.grid_n > 0 && o.lazy_routes) route_head[a] = A.lazy_head;
+      else route_head[a] = A.route_cur < o.route_lanes[a].size() ? o.route_lanes[a][A.route_cur] : -1;
+    }
   }
   std::vector<int32_t> ord;
   get_actors(o, ord);

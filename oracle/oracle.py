@@ -48,7 +48,7 @@ def get_pos(net, geom, loc_kind, container, side, pos):
 class Oracle:
     """Same call shape as griddy_b200.device.Simulation, so parity tests feed both identically."""
 
-    def __init__(self, net, actors, dt: float = 1.0 / 15.0, two_size: float = 10.0):
+    def __init__(self, net, actors, dt: float = 1.0 / 15.0, two_size: float = 10.0, lazy_routes: bool = True):
         from griddy_b200.flat import ActorState  # data containers only, no product code path
         self._State = ActorState
         L = lib()
@@ -63,6 +63,7 @@ class Oracle:
                 raise ValueError("actors carry no routes and the network has no grid routing table")
             self._chk(L.go_set_routing_grid(self.h, C.c_int(net.grid_n), _p(net.lane_from_j),
                                             _p(net.lane_to_j), _p(net.turn4)))
+        self._chk(L.go_set_lazy_routes(self.h, C.c_int(1 if lazy_routes else 0)))
         a = actors
         self._chk(L.go_load_actors(self.h, C.c_int64(a.n), _p(a.loc_kind), _p(a.container), _p(a.pos),
                                    _p(a.side), _p(a.speed), _p(a.speed_dt), _p(a.agenda_off),

@@ -49,13 +49,13 @@ def main():
         entry_["checkpoints"][str(cp)] = {"sha": digest.sha_fields(st, lane_count, junction_count),
                                           "commutative": digest.commutative(st), "vanished": ref.vanished}
         print(f"[{name}] tick {cp}: {entry_['checkpoints'][str(cp)]['commutative']} after {time.time() - t0:.0f}s", flush=True)
-    data = {}
-    if os.path.exists(OUT):
-        with open(OUT) as f:
-            data = json.load(f)
-    data[name] = entry_
-    with open(OUT, "w") as f:
-        json.dump(data, f, indent=1, sort_keys=True)
+        data = {}   # written after every checkpoint: a long run that is cut short keeps what it has
+        if os.path.exists(OUT):
+            with open(OUT) as f:
+                data = json.load(f)
+        data[name] = entry_
+        with open(OUT, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
     print(f"[{name}] written to {OUT}")
 
 

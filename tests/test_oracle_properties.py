@@ -43,3 +43,18 @@ def test_sleep_for_n_lasts_n_plus_one_ticks():
         o.step(1)
         s = o.state()
         assert np.array_equal(s.agenda_cur >= 1, first < t)   # simulate.scm:74-78
+
+
+def test_lazy_grid_routes_equal_the_unrolled_route_lists():
+    """With the grid rule the oracle derives the route head on demand instead of unrolling the whole
+    (turn-onto lane) ... list at begin-route$ (87 GB at 1024 x 1024 / 16M actors): both modes give the same world,
+    tick by tick, state, order and occupancy."""
+    for n, n_actors, seed in ((5, 700, 3), (9, 3000, 12)):
+        net, actors = crowded_grid(n, n_actors, n_dest=max(4, n), seed=seed, agenda_len=4)
+        lazy, eager = Oracle(net, actors, lazy_routes=True), Oracle(net, actors, lazy_routes=False)
+        for t in range(250):
+            lazy.step(1); eager.step(1)
+            a, b = lazy.state(), eager.state()
+            assert not a.diff(b) and np.array_equal(a.pos, b.pos), f"{n}x{n} tick {t + 1}"
+            assert all(np.array_equal(x, y) for x, y in zip(lazy.occupancy(), eager.occupancy()))
+        assert lazy.vanished == eager.vanished > 0
