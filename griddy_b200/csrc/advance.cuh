@@ -247,6 +247,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     k.dest_from_j = ai.dfrom;
     k.dest_to_j = ai.dto;
     const int32_t hop = route_head_on(p, init_lane, init_it, k, item, &rc);
+    if (hop == -2) { dev_error(p, DEV_ERR_NO_ROUTE); return cur; }   // find-route found no path (a* throws 'no-path)
     const double len = init_it.len;
     p.coldf[a].arrive = dest_pos;
     p.hot[a].tj = junction_after(p, init_it, hop);

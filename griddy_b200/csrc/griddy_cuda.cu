@@ -83,6 +83,7 @@
 #include "setup.cuh"
 #include "reorder.cuh"
 #include "readback.cuh"
+#include "routes.cuh"
 
 using namespace griddy;
 
@@ -210,6 +211,14 @@ struct Ctx {
   std::vector<int32_t> dst_lane, dst_from, dst_to;
   std::vector<uint8_t> dst_dir;
   bool have_dst = false;
+  // find-route on the device (griddy_set_route_graph): the lane graph, kept on the device with the network
+  const int64_t* g_nbr_off = nullptr;
+  const int32_t* g_nbr = nullptr;
+  const double* g_cost = nullptr;
+  const double2* g_mid = nullptr;
+  int64_t g_edges = 0;
+  std::vector<int64_t> h_route_off;     // the routes the last upload_actors used (given or computed), for griddy_download_routes
+  std::vector<int32_t> h_route_lane;
   AgendaItem* agenda_alt = nullptr;   // second item pool: a reorder of a partitioned world compacts into it
   int32_t* d_nitems_new = nullptr;
   Multi mg;
@@ -746,6 +755,8 @@ int griddy_upload_network(void* ctx, int64_t n_items, const uint8_t* kind, const
   c->h_from.clear();
   c->h_to.clear();
   c->have_dst = false;
+  c->g_nbr_off = nullptr;
+  c->g_edges = 0;
   mg_reset(c);
   c->have_net = true;
   return GRIDDY_OK;
@@ -828,6 +839,130 @@ int griddy_set_agenda_destinations(void* ctx, int64_t n_agenda_items, const int3
   return GRIDDY_OK;
 }
 
+int griddy_set_route_graph(void* ctx, const int64_t* nbr_off, const int32_t* nbr, const double* cost_out, const double* midpoint_xy) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_net) return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph before upload_network");
+  if (c->tl.tiled()) return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph: a route search needs the whole network, this context holds a tile");
+  if (!nbr_off || !cost_out || !midpoint_xy) return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph: null array");
+  const int64_t n = c->p.n_items;
+  if (nbr_off[0] != 0) return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph: nbr_off must start at 0");
+  for (int64_t r = 0; r < n; ++r) {
+    if (nbr_off[r + 1] < nbr_off[r]) return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph: nbr_off not monotone");
+    const bool lane = c->h_kind[r] == GRIDDY_SEGMENT_LANE || c->h_kind[r] == GRIDDY_JUNCTION_LANE;
+    if (!lane && nbr_off[r + 1] != nbr_off[r]) return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph: only lanes have neighbours");
+    if (lane && !(cost_out[r] >= 0.0)) return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph: negative cost");
+  }
+  const int64_t e = nbr_off[n];
+  if (e > 0 && !nbr) return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph: null neighbour list");
+  for (int64_t k = 0; k < e; ++k) {
+    const int32_t v = nbr[k];
+    if (v < 0 || v >= n || (c->h_kind[v] != GRIDDY_SEGMENT_LANE && c->h_kind[v] != GRIDDY_JUNCTION_LANE))
+      return fail(c, GRIDDY_ERR_BAD_ARG, "set_route_graph: neighbour " + std::to_string(k) + " is not a lane");
+  }
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  TRY(dev_upload(c, c->net_allocs, &c->g_nbr_off, nbr_off, n + 1));
+  TRY(dev_upload(c, c->net_allocs, &c->g_nbr, nbr, e));
+  TRY(dev_upload(c, c->net_allocs, &c->g_cost, cost_out, n));
+  TRY(dev_upload(c, c->net_allocs, &c->g_mid, (const double2*)midpoint_xy, n));
+  c->g_edges = e;
+  return GRIDDY_OK;
+}
+
+namespace {
+
+// find-route for every travel-to item, on the device (routes.cuh): item k's route starts on the lane the actor is
+// beside when it gets there — its first location, then the destination of the travel-to before — and ends on the
+// item's destination lane.  Fills the CSR upload_actors would have been given.
+int find_routes_on_device(Ctx* c, int64_t n, const uint8_t* loc_kind, const int32_t* container, const uint8_t* side,
+                          const int64_t* agenda_off, const std::vector<AgendaItem>& agenda, std::vector<int64_t>& route_off,
+                          std::vector<int32_t>& route_lane) {
+  const int64_t n_agenda = (int64_t)agenda.size(), V = c->p.n_items;
+  std::vector<int32_t> start, goal;
+  std::vector<int64_t> item_of;
+  for (int64_t a = 0; a < n; ++a) {
+    int32_t cur = -1;
+    if (!loc_kind[a]) cur = side[a] ? c->h_ob[container[a]] : c->h_of[container[a]];   // off-road->on-road, location.scm:49-57
+    for (int64_t k = agenda_off[a]; k < agenda_off[a + 1]; ++k) {
+      if (agenda[(size_t)k].kind != GRIDDY_TRAVEL_TO) continue;
+      start.push_back(loc_kind[a] ? -1 : cur);   // (begin-route$ on an on-road actor has no applicable method)
+      goal.push_back(agenda[(size_t)k].dlane);
+      item_of.push_back(k);
+      cur = agenda[(size_t)k].dlane;
+    }
+  }
+  route_off.assign((size_t)n_agenda + 1, 0);
+  route_lane.clear();
+  const int64_t n_search = (int64_t)start.size();
+  std::vector<int32_t> len((size_t)n_search, 0);
+  std::vector<std::vector<int32_t>> paths((size_t)n_search);
+  if (n_search > 0) {
+    const int64_t heap_cap = 4 * c->g_edges + 16;
+    const size_t per = (size_t)V * (sizeof(double) + 2 * sizeof(int32_t)) + (size_t)heap_cap * sizeof(HeapEnt);
+    const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_search, (int64_t)((size_t)1 << 30) / (int64_t)std::max<size_t>(per, 1)));
+    std::vector<void*> tmp;
+    int32_t *d_start, *d_goal, *d_came, *d_path, *d_len;
+    double* d_best;
+    HeapEnt* d_heap;
+    int rc = dev_alloc(c, tmp, &d_start, batch);
+    if (!rc) rc = dev_alloc(c, tmp, &d_goal, batch);
+    if (!rc) rc = dev_alloc(c, tmp, &d_len, batch);
+    if (!rc) rc = dev_alloc(c, tmp, &d_best, batch * V);
+    if (!rc) rc = dev_alloc(c, tmp, &d_came, batch * V);
+    if (!rc) rc = dev_alloc(c, tmp, &d_path, batch * V);
+    if (!rc) rc = dev_alloc(c, tmp, &d_heap, batch * heap_cap);
+    std::vector<int32_t> h_path;
+    for (int64_t b0 = 0; !rc && b0 < n_search; b0 += batch) {
+      const int64_t m = std::min(batch, n_search - b0);
+      cudaMemcpyAsync(d_start, start.data() + b0, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+      cudaMemcpyAsync(d_goal, goal.data() + b0, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream);
+      k_find_routes<<<(unsigned)((m + 31) / 32), 32, 0, c->stream>>>((int)m, d_start, d_goal, V, c->g_nbr_off, c->g_nbr, c->g_cost, c->g_mid,
+                                                                      d_best, d_came, d_heap, heap_cap, d_path, d_len);
+      ++c->launches;
+      cudaMemcpyAsync(len.data() + b0, d_len, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(c, GRIDDY_ERR_CUDA, std::string("k_find_routes: ") + cudaGetErrorString(cudaGetLastError())); break; }
+      for (int64_t s = 0; s < m && !rc; ++s) {
+        const int32_t l = len[(size_t)(b0 + s)];
+        if (l == -2) rc = fail(c, GRIDDY_ERR_BAD_STATE, "find-route: the search's queue overflowed");
+        if (l > 0) {
+          paths[(size_t)(b0 + s)].resize((size_t)l);
+          if (cudaMemcpy(paths[(size_t)(b0 + s)].data(), d_path + s * V, (size_t)l * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail(c, GRIDDY_ERR_CUDA, "find-route: copying a route failed");
+        }
+      }
+    }
+    free_pool(tmp);
+    if (rc) return rc;
+  }
+  // CSR over ALL agenda items; a travel-to without a route ('no-path) gets the single step -2, which begin-route$ reports
+  std::vector<int64_t> cnt((size_t)n_agenda, 0);
+  for (int64_t s = 0; s < n_search; ++s) cnt[(size_t)item_of[(size_t)s]] = len[(size_t)s] < 0 ? 1 : len[(size_t)s];
+  for (int64_t k = 0; k < n_agenda; ++k) route_off[(size_t)k + 1] = route_off[(size_t)k] + cnt[(size_t)k];
+  route_lane.resize((size_t)route_off[(size_t)n_agenda]);
+  for (int64_t s = 0; s < n_search; ++s) {
+    const int64_t o = route_off[(size_t)item_of[(size_t)s]];
+    if (len[(size_t)s] < 0) route_lane[(size_t)o] = -2;
+    else std::copy(paths[(size_t)s].begin(), paths[(size_t)s].end(), route_lane.begin() + o);
+  }
+  return GRIDDY_OK;
+}
+
+}  // namespace
+
+int griddy_download_routes(void* ctx, int64_t* route_off, int32_t* route_lane, int64_t capacity, int64_t* n_steps) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->have_actors || !n_steps) return fail(c, GRIDDY_ERR_BAD_ARG, "download_routes: no actors or null n_steps");
+  if (c->h_route_off.empty()) return fail(c, GRIDDY_ERR_BAD_ARG, "download_routes: this world uses the grid routing table, it has no route lists");
+  *n_steps = (int64_t)c->h_route_lane.size();
+  if (route_off) std::copy(c->h_route_off.begin(), c->h_route_off.end(), route_off);
+  if (route_lane) {
+    if (capacity < *n_steps) return fail(c, GRIDDY_ERR_BAD_ARG, "download_routes: route_lane too small, need " + std::to_string(*n_steps));
+    std::copy(c->h_route_lane.begin(), c->h_route_lane.end(), route_lane);
+  }
+  return GRIDDY_OK;
+}
+
 int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const int32_t* container,
                          const double* pos, const uint8_t* side, const double* speed,
                          const double* speed_dt, const int64_t* agenda_off, const uint8_t* item_kind,
@@ -842,8 +977,8 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   if (n_agenda < 0 || n_agenda > INT32_MAX - 1) return fail(c, GRIDDY_ERR_BAD_ARG, "too many agenda items");
   if (n_agenda > 0 && (!item_kind || !item_sleep || !item_seg || !item_side || !item_pos))
     return fail(c, GRIDDY_ERR_BAD_ARG, "upload_actors: null agenda arrays");
-  if (!route_off && c->p.grid_n == 0)
-    return fail(c, GRIDDY_ERR_BAD_ARG, "no routes uploaded and no grid routing table set");
+  if (!route_off && c->p.grid_n == 0 && !c->g_nbr_off)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "no routes uploaded, no route graph (griddy_set_route_graph) and no grid routing table set");
   const Params& q = c->p;
   const Tiling& tl = c->tl;
   for (int64_t a = 0; a < n; ++a) {
@@ -902,11 +1037,26 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
       return fail(c, GRIDDY_ERR_BAD_ARG, "agenda item " + std::to_string(k) + ": unknown kind");
     }
   }
+  std::vector<int64_t> found_off;
+  std::vector<int32_t> found_lane;
+  if (!route_off && c->g_nbr_off && c->p.grid_n == 0) {   // find-route on the device
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    TRY(find_routes_on_device(c, n, loc_kind, container, side, agenda_off, agenda, found_off, found_lane));
+    route_off = found_off.data();
+    route_lane = found_lane.data();
+  }
+  c->h_route_off.clear();
+  c->h_route_lane.clear();
+  if (route_off) {
+    c->h_route_off.assign(route_off, route_off + n_agenda + 1);
+    c->h_route_lane.assign(route_lane, route_lane + route_off[n_agenda]);
+  }
   if (route_off) {
     if (route_off[n_agenda] > 0 && !route_lane) return fail(c, GRIDDY_ERR_BAD_ARG, "route_lane is null");
     if (route_off[n_agenda] > INT32_MAX - 1) return fail(c, GRIDDY_ERR_BAD_ARG, "too many route steps");
     for (int64_t k = 0; k < route_off[n_agenda]; ++k) {
       const int32_t l = route_lane[k];
+      if (l == -2) continue;   // 'no-path, reported when the actor gets there
       const uint8_t kd = (l >= 0 && l < q.n_items) ? c->kind_of(l) : (uint8_t)254;
       if (kd != 255 && kd != GRIDDY_SEGMENT_LANE && kd != GRIDDY_JUNCTION_LANE)
         return fail(c, GRIDDY_ERR_BAD_ARG, "route step " + std::to_string(k) + " is not a lane");

@@ -27,7 +27,7 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_set_locality_keys", "griddy_set_reorder_period", "griddy_slots_in_use",
            "griddy_debug_sort_pairs", "griddy_count_alive", "griddy_mg_configure", "griddy_mg_set_global_ids",
            "griddy_set_item_ranges", "griddy_set_agenda_destinations", "griddy_mg_plan_tile", "griddy_step_async",
-           "griddy_reorder_now", "griddy_reorders", "griddy_mg_connect_local", "griddy_mg_step_local",
+           "griddy_reorder_now", "griddy_reorders", "griddy_set_route_graph", "griddy_download_routes", "griddy_mg_connect_local", "griddy_mg_step_local",
            "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
            "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
            "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace", "griddy_state_digest")
@@ -108,9 +108,12 @@ class Simulation:
         self._frames = []
         if reorder_period is not None:
             self._chk(L.griddy_set_reorder_period(self.h, C.c_int32(reorder_period)))
-        if actors.route_off is None:
+        if actors.route_off is None and net.nbr_off is not None and not net.grid_n:
+            # find-route on the device: the lane graph of route.scm:19-40
+            self._chk(L.griddy_set_route_graph(self.h, _p(net.nbr_off), _p(net.nbr), _p(net.cost_out), _p(net.midpoint)))
+        elif actors.route_off is None:
             if not net.grid_n:
-                raise ValueError("actors carry no routes and the network has no grid routing table")
+                raise ValueError("actors carry no routes and the network has neither a route graph nor a grid routing table")
             self._chk(L.griddy_set_routing_grid(self.h, C.c_int32(net.grid_n), _p(net.lane_from_j),
                                                 _p(net.lane_to_j), _p(net.turn4)))
         self.partition = partition
@@ -245,6 +248,15 @@ class Simulation:
         self._chk(lib().griddy_positions_end(self.h, C.byref(n)))
         buf = self._frames.pop(0)
         return buf.array[: n.value]
+
+    def routes(self):
+        """(route_off, route_lane) the world was uploaded with: the caller's, or those find-route computed on the device."""
+        n = C.c_int64(0)
+        self._chk(lib().griddy_download_routes(self.h, None, None, C.c_int64(0), C.byref(n)))
+        off = np.zeros(self.actors.n_agenda_items + 1, np.int64)
+        lanes = np.zeros(max(int(n.value), 1), np.int32)
+        self._chk(lib().griddy_download_routes(self.h, _p(off), _p(lanes), C.c_int64(len(lanes)), C.byref(n)))
+        return off, lanes[: n.value]
 
     def occupancy(self):
         """Actors per container and per junction, one entry per item of `net` (compact on a tile)."""

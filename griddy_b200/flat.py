@@ -46,6 +46,12 @@ class FlatNetwork:
     seg_reg: Optional[np.ndarray] = None       # i32 segment ordinal -> registration id
     loc_key: Optional[np.ndarray] = None       # u32 locality key per item (griddy_set_locality_keys)
     geom: Optional[np.ndarray] = None          # f64 [n_items,8] drawing geometry (griddy_upload_geometry)
+    # the lane graph find-route searches (griddy_set_route_graph): neighbours per item in the reference's order (CSR),
+    # the cost of leaving a lane, every lane's midpoint
+    nbr_off: Optional[np.ndarray] = None       # i64 [n_items+1]
+    nbr: Optional[np.ndarray] = None           # i32
+    cost_out: Optional[np.ndarray] = None      # f64 [n_items]
+    midpoint: Optional[np.ndarray] = None      # f64 [n_items,2]
     # a TILE of a larger network (griddy_set_item_ranges): every array above then has one entry per held item,
     # the id ranges back to back; the ids inside the arrays stay global
     n_global: Optional[int] = None             # items of the whole network
@@ -68,6 +74,11 @@ class FlatNetwork:
         if self.geom is not None:
             self.geom = _arr(self.geom, np.float64).reshape(-1, 8)
             assert self.geom.shape[0] == self.kind.shape[0], "geom needs 8 doubles per item"
+        if self.nbr_off is not None:
+            self.nbr_off = _arr(self.nbr_off, np.int64)
+            self.nbr = _arr(self.nbr, np.int32)
+            self.cost_out = _arr(self.cost_out, np.float64)
+            self.midpoint = _arr(self.midpoint, np.float64).reshape(-1, 2)
         if self.range_beg is not None:
             self.range_beg = _arr(self.range_beg, np.int64)
             self.range_end = _arr(self.range_end, np.int64)

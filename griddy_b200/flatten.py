@@ -56,8 +56,23 @@ def flatten_network(world: core.World):
             for in_lane, jls in item.junction.lane_map["inputs"].items():
                 if item in jls:
                     lane_in[r] = idx[in_lane]
+    # the graph find-route searches (route.scm:19-40): neighbours in the reference's list order, cost of leaving a
+    # lane, midpoints — computed here with the API mirror's procedures, by the Guile glue with the reference's own
+    by_id = sorted(idx.items(), key=lambda kv: kv[1])
+    nbr_off, nbr = [0], []
+    cost_out, midpoint = np.zeros(n, np.float64), np.zeros((n, 2), np.float64)
+    for item, r in by_id:
+        if isinstance(item, core.RoadLaneSegment):
+            nbr.extend(idx[jl] for jl in core.get_junction_lanes(item))
+            cost_out[r] = float(core.get_length(item.segment))
+            midpoint[r] = core.get_midpoint(item)
+        elif isinstance(item, core.RoadLaneJunction):
+            nbr.append(idx[core.get_segment_lane(item)])
+            midpoint[r] = core.get_midpoint(item)
+        nbr_off.append(len(nbr))
     return FlatNetwork(kind, lane_len, lane_dir, lane_segment, lane_out, lane_junction, so_f, so_b,
-                       lane_in=lane_in), idx
+                       lane_in=lane_in, nbr_off=np.array(nbr_off, np.int64), nbr=np.array(nbr, np.int32),
+                       cost_out=cost_out, midpoint=midpoint), idx
 
 
 def flatten_geometry(world: core.World, idx: dict) -> np.ndarray:

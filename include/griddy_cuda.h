@@ -125,6 +125,26 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
                          const int32_t* item_sleep, const int32_t* item_seg, const uint8_t* item_side,
                          const double* item_pos, const int64_t* route_off, const int32_t* route_lane);
 
+/* Optional: find-route on the device (route.scm:17-51).  With the lane graph uploaded, griddy_upload_actors called
+ * with route_off = NULL (and no grid routing table) computes the route of every travel-to item itself: A* from the
+ * lane the route starts on — the actor's first location, then the destination of the travel-to before
+ * (off-road->on-road, location.scm:49-57) — to the item's destination lane.
+ *   nbr_off [n_items+1], nbr   the `neighbors` of route.scm:19-23 per lane, in the reference's list order: a segment
+ *                              lane's junction lanes (get-junction-lanes, core.scm:97-104), a junction lane's one
+ *                              output lane (get-segment-lane, core.scm:106-111); nothing for other items
+ *   cost_out [n_items]         `cost` of leaving a lane (route.scm:25-34): (get-length (ref lane 'segment)) for a
+ *                              segment lane, 0 for a junction lane
+ *   midpoint_xy [2 x n_items]  (get-midpoint lane), spatial.scm:68-73: `distance` is the l2 of two of them
+ * The search is the A* that tests/golden/minischeme.py substitutes for Chickadee's un-vendored `a*` (priority = cost
+ * so far + distance to the goal, ties by order of insertion), so the routes equal the fixtures' recorded ones.  A
+ * travel-to without a path ('no-path) makes the step that reaches it fail with GRIDDY_ERR_BAD_STATE.  Whole
+ * networks only (no griddy_set_item_ranges). */
+int griddy_set_route_graph(void* ctx, const int64_t* nbr_off, const int32_t* nbr, const double* cost_out,
+                           const double* midpoint_xy);
+/* The route lists the last griddy_upload_actors used — given by the caller or found on the device: route_off
+ * [agenda items + 1], route_lane (`capacity` entries must hold *n_steps); either array may be NULL. */
+int griddy_download_routes(void* ctx, int64_t* route_off, int32_t* route_lane, int64_t capacity, int64_t* n_steps);
+
 /* Optional, before griddy_upload_actors: the destination of every agenda item resolved by the caller, as
  * begin-route$ would (simulate.scm:80-85 -> off-road->on-road, location.scm:49-57): dest_lane = get-outer-lane of
  * (item_seg, item_side) (location.scm:16-24; -1: the road has no lanes there), dest_dir that lane's direction,

@@ -113,3 +113,35 @@ def test_guile_dump_checker(tmp_path):
     bad.write_text("\n".join(lines) + "\n")
     ko = subprocess.run([sys.executable, script, str(bad), fixture], capture_output=True, text=True)
     assert ko.returncode == 1 and "pos-param" in ko.stdout
+
+
+GRID_FIXTURES = {"grid-2x2-jam": 2, "grid-3x3-crowded": 3, "grid-5x5-80": 5}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(GRID_FIXTURES))
+def test_device_finds_the_routes_the_reference_recorded(name):
+    """find-route on the device (route.scm:17-51; griddy_set_route_graph): given only the lane graph — neighbours in
+    the reference's order, segment lengths, lane midpoints, all from the API mirror, whose geometry
+    tests/test_positions.py pins against the reference's — the device's A* returns, for every travel-to item, exactly
+    the (turn-onto lane) ... list the reference's own find-route returned when the fixture was recorded, and the run
+    that uses those routes reproduces the reference's, tick by tick."""
+    import dataclasses
+
+    import examples
+    from griddy_b200 import device, flatten
+    fx, fnet, factors = load(name)
+    net, _ = flatten.flatten_network(examples.grid_make_skeleton(GRID_FIXTURES[name]))
+    for f in ("kind", "lane_len", "lane_dir", "lane_segment", "lane_out", "lane_junction", "seg_outer_forw", "seg_outer_back"):
+        assert np.array_equal(getattr(net, f), getattr(fnet, f)), f"the API mirror builds another network than the fixture's: {f}"
+    bare = dataclasses.replace(factors, route_off=None, route_lane=None)
+    sim = device.Simulation(net, bare, dt=fx["dt"], two_size=fx["two_size"], reorder_period=16)
+    off, lanes = sim.routes()
+    assert np.array_equal(off, factors.route_off), "route lengths differ from the reference's find-route"
+    assert np.array_equal(lanes, factors.route_lane), "routes differ from the reference's find-route"
+    assert len(lanes) > 0
+    states = expected_states(fx)
+    check(sim, fx, factors, 0, next(states))
+    for tick, s in enumerate(states, start=1):
+        sim.step(1)
+        check(sim, fx, factors, tick, s)
