@@ -26,7 +26,7 @@
   #:use-module (griddy simulate route)
   #:use-module (chickadee math vector)
   #:use-module (chickadee math bezier)
-  #:export (cuda-open cuda-close cuda-upload-world! cuda-step! cuda-download-world!
+  #:export (cuda-open cuda-close cuda-upload-world! cuda-step! cuda-step-async! cuda-download-world!
             cuda-last-step-ms cuda-positions make-frame-buffer cuda-frame-begin! cuda-frame-end!))
 
 (define %lib (dynamic-link (or (getenv "GRIDDY_CUDA_LIB") "libgriddy_cuda")))
@@ -41,6 +41,8 @@
 (define %network  (c-fn "griddy_upload_network" int '* int64 '* '* '* '* '* '* '* '*))
 (define %actors   (c-fn "griddy_upload_actors" int '* int64 '* '* '* '* '* '* '* '* '* '* '* '* '* '*))
 (define %step     (c-fn "griddy_step" int '* int64))
+(define %step-async (c-fn "griddy_step_async" int '* int64))
+(define %route-graph (c-fn "griddy_set_route_graph" int '* '* '* '* '*))
 (define %download (c-fn "griddy_download_actors" int '* '* '* '* '* '* '* '* '* '* '* '*))
 (define %step-ms  (c-fn "griddy_last_step_ms" double '*))
 (define %geometry (c-fn "griddy_upload_geometry" int '* '*))
@@ -160,8 +162,40 @@
          (vec! r 4 (off-road-origin item 'back))))))
     (check ctx (%geometry ctx (ptr geom)))))
 
+;;; ---- the lane graph find-route searches, for find-route on the device ------------------------
+;;; (griddy_set_route_graph) neighbours, cost and midpoints exactly as route.scm:19-40 defines them, every number
+;;; from the reference's own procedures; the device then runs the A* itself when the actors are uploaded
+;;; without routes.
+(define (upload-route-graph! ctx world index)
+  (let* ((n (hash-table-size index))
+         (items (list->vector (reverse (get-static-items world))))   ; id -> item
+         (nbr-off (make-i64 (1+ n)))
+         (cost (make-f64 n)) (mid (make-f64 (* 2 n)))
+         (nbrs '()) (k 0))
+    (define (id x) (hash-table-ref index x))
+    (do ((r 0 (1+ r))) ((= r n))
+      (let ((item (vector-ref items r)))
+        (i64! nbr-off r k)
+        (cond
+         ((is-a? item <road-lane/segment>)
+          (for-each (lambda (jl) (set! nbrs (cons (id jl) nbrs)) (set! k (1+ k)))
+                    (get-junction-lanes item))                      ; route.scm:20-21, core.scm:97-104
+          (f64! cost r (get-length (ref item 'segment))))            ; route.scm:26-29
+         ((is-a? item <road-lane/junction>)
+          (set! nbrs (cons (id (get-segment-lane item)) nbrs))       ; route.scm:22-23, core.scm:106-111
+          (set! k (1+ k))))                                          ; cost 0, route.scm:31-34
+        (when (is-a? item <road-lane>)
+          (let ((m (get-midpoint item)))                             ; route.scm:37-40, spatial.scm:68-73
+            (f64! mid (* 2 r) (vec2-x m))
+            (f64! mid (1+ (* 2 r)) (vec2-y m))))))
+    (i64! nbr-off n k)
+    (let ((nbr (make-i32 (max 1 k) -1)))
+      (let fill ((l (reverse nbrs)) (i 0))
+        (unless (null? l) (i32! nbr i (car l)) (fill (cdr l) (1+ i))))
+      (check ctx (%route-graph ctx (ptr nbr-off) (ptr nbr) (ptr cost) (ptr mid))))))
+
 ;;; ---- flatten actors, agendas and routes -----------------------------------------------------
-(define (upload-actors! ctx world index)
+(define* (upload-actors! ctx world index #:key (routes 'host))
   ;; id order is the reverse of get-actors order (see header)
   (let* ((actors (reverse (get-actors world)))
          (n (length actors))
@@ -176,6 +210,10 @@
     (let loop ((l actors) (a 0))
       (unless (null? l)
         (let* ((actor (car l)) (loc (ref actor 'location)) (cur #f))
+          ;; an actor in the middle of a route cannot be uploaded: the device starts every actor with route 'none
+          ;; (actor.scm:19-21), which is what add-actors! leaves behind
+          (unless (eq? (ref actor 'route) 'none)
+            (throw 'griddy-cuda 1 "cuda-upload-world!: an actor is already on a route; upload the world add-actors! built"))
           (if (is-a? loc <location/on-road>)
               (begin (bytevector-u8-set! loc-kind a 1)
                      (i32! container a (id (ref loc 'road-lane))))
@@ -199,7 +237,7 @@
                   (f64! item-pos k (ref dest 'pos-param))
                   ;; the reference's own find-route (route.scm:17-51), evaluated at upload: the start
                   ;; of travel item k is where the previous travel ended (simulate.scm:87-91)
-                  (when cur
+                  (when (and cur (eq? routes 'host))
                     (let ((steps (find-route (off-road->on-road cur) (off-road->on-road dest))))
                       (for-each (lambda (step)
                                   (when (eq? (car step) 'turn-onto)
@@ -216,21 +254,31 @@
     (let ((route-lane (make-i32 (max 1 n-route) -1)))
       (let fill ((l (reverse route-lanes)) (i 0))
         (unless (null? l) (i32! route-lane i (car l)) (fill (cdr l) (1+ i))))
+      ;; routes 'device: no route lists cross the boundary, the device's find-route fills them in
       (check ctx (%actors ctx n (ptr loc-kind) (ptr container) (ptr pos) (ptr side) (ptr speed)
                           (ptr speed-dt) (ptr agenda-off) (ptr item-kind) (ptr item-sleep)
-                          (ptr item-seg) (ptr item-side) (ptr item-pos) (ptr route-off)
-                          (ptr route-lane))))
+                          (ptr item-seg) (ptr item-side) (ptr item-pos)
+                          (if (eq? routes 'host) (ptr route-off) %null-pointer)
+                          (if (eq? routes 'host) (ptr route-lane) %null-pointer))))
     actors))
 
-(define (cuda-upload-world! ctx world)
-  "Flatten WORLD and upload it.  Returns (index . actors): what cuda-download-world! needs."
+(define* (cuda-upload-world! ctx world #:key (routes 'host))
+  "Flatten WORLD and upload it.  Returns (index . actors): what cuda-download-world! needs.
+ROUTES: 'host — every travel-to's route comes from the reference's own find-route, evaluated here;
+'device — the lane graph is uploaded and the device's find-route (the same A*) computes them."
   (let ((index (registration-index world)))
     (upload-network! ctx world index)
     (upload-geometry! ctx world index)
-    (cons index (upload-actors! ctx world index))))
+    (when (eq? routes 'device) (upload-route-graph! ctx world index))
+    (cons index (upload-actors! ctx world index #:routes routes))))
 
 (define (cuda-step! ctx n-ticks)
   (check ctx (%step ctx n-ticks)))
+
+(define (cuda-step-async! ctx n-ticks)
+  "Enqueue N-TICKS ticks and return without waiting for the device (frame loops); a device-side error is thrown by a
+later call, at the latest by the next (cuda-step! ctx 0)."
+  (check ctx (%step-async ctx n-ticks)))
 
 ;;; ---- read the world back into a fresh skeleton ----------------------------------------------
 (define (cuda-download-world! ctx handle make-skeleton)

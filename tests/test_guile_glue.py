@@ -90,16 +90,30 @@ class FakeLibrary:
         n = int(n)
         off = self.arr(agenda_off, np.int64, n + 1)
         ni = int(off[n])
-        roff = self.arr(route_off, np.int64, ni + 1)
+        no_routes = route_off.obj is None     # routes 'device: find-route runs on the device
+        roff = np.zeros(ni + 1, np.int64) if no_routes else self.arr(route_off, np.int64, ni + 1)
         self.calls.append(("griddy_upload_actors", {
+            "no_routes": no_routes,
             "n": n, "loc_kind": self.arr(loc_kind, np.uint8, n), "container": self.arr(container, np.int32, n),
             "pos": self.arr(pos, np.float64, n), "side": self.arr(side, np.uint8, n),
             "speed": self.arr(speed, np.float64, n), "speed_dt": self.arr(speed_dt, np.float64, n),
             "agenda_off": off, "item_kind": self.arr(item_kind, np.uint8, ni),
             "item_sleep": self.arr(item_sleep, np.int32, ni), "item_seg": self.arr(item_seg, np.int32, ni),
             "item_side": self.arr(item_side, np.uint8, ni), "item_pos": self.arr(item_pos, np.float64, ni),
-            "route_off": roff, "route_lane": self.arr(route_lane, np.int32, int(roff[ni]))}))
+            "route_off": roff, "route_lane": np.zeros(0, np.int32) if no_routes else self.arr(route_lane, np.int32, int(roff[ni]))}))
         self.n_actors = n
+        return 0
+
+    def griddy_set_route_graph(self, ctx, nbr_off, nbr, cost_out, midpoint_xy):
+        n = self.n_items
+        off = self.arr(nbr_off, np.int64, n + 1)
+        self.calls.append(("griddy_set_route_graph", {
+            "nbr_off": off, "nbr": self.arr(nbr, np.int32, int(off[n])), "cost_out": self.arr(cost_out, np.float64, n),
+            "midpoint": self.arr(midpoint_xy, np.float64, 2 * n).reshape(-1, 2)}))
+        return 0
+
+    def griddy_step_async(self, ctx, n_ticks):
+        self.calls.append(("griddy_step_async", {"ctx": ctx.address, "n_ticks": int(n_ticks)}))
         return 0
 
     def griddy_step(self, ctx, n_ticks):
@@ -219,6 +233,30 @@ def test_glue_flattens_the_world_like_the_fixtures(name):
     want = np.asarray(lib.state["xy"], np.float64).reshape(-1, 2).astype(np.float32)
     assert circles == sorted((float(x), float(y)) for x, y in want)
     assert all(c[0] == "circle" and c[3] == 5 for c in canvas[1][1])        # *actor/size*, constants.scm:34
+
+
+def test_glue_uploads_the_lane_graph_for_find_route_on_the_device():
+    """(cuda-upload-world! ctx world #:routes 'device): no route lists cross the boundary; instead the glue uploads the
+    graph find-route searches — neighbours in the reference's order, costs, midpoints, all computed by the reference's
+    own get-junction-lanes / get-segment-lane / get-length / get-midpoint — which must equal what the API mirror
+    (griddy_b200/flatten.py) builds and tests/test_golden.py feeds to the device's A*."""
+    import examples
+    from griddy_b200 import flatten
+    example, subs, seed = SCENARIOS["grid-2x2-jam"]
+    subs = subs + (("(simulate make-skeleton add-actors! #:width 700 #:height 700 #:duration 800)",
+                    "(use-modules (griddy cuda))\n(define world (make-skeleton))\n(add-actors! world)\n"
+                    "(define ctx (cuda-open))\n(cuda-upload-world! ctx world #:routes 'device)\n(cuda-step-async! ctx 3)"),)
+    I, lib, ms = run_example("grid-2x2-device-routes", example, subs, seed)
+    fx, net, actors = load("grid-2x2-jam")
+    got = the_call(lib, "griddy_set_route_graph")
+    want, _ = flatten.flatten_network(examples.grid_make_skeleton(2))
+    for k in ("nbr_off", "nbr", "cost_out", "midpoint"):
+        assert np.array_equal(got[k], getattr(want, k)), k
+    up = the_call(lib, "griddy_upload_actors")
+    assert up["no_routes"] and np.array_equal(up["item_seg"], actors.item_seg) and np.array_equal(up["pos"], actors.pos)
+    order = [c[0] for c in lib.calls]
+    assert order.index("griddy_upload_network") < order.index("griddy_set_route_graph") < order.index("griddy_upload_actors")
+    assert the_call(lib, "griddy_step_async")["n_ticks"] == 3
 
 
 @pytest.mark.parametrize("name", ["simple", "grid-2x2-jam"])
