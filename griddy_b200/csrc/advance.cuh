@@ -115,6 +115,10 @@ __device__ __forceinline__ int32_t leave_lane(const Params& p, int a, int32_t la
 // held by a full junction: carry the rest of the tick over into the target lane, pop the route.
 // Touches six 64-byte lines: the actor's cold record, its hot record, its new pos-param, the target lane's
 // record, the old lane's record and the pos-param of the target lane's rearmost actor.  Returns the new pos-param.
+__device__ void emigrate(const Params& p, int a, int tick, uint32_t st, const Cold& k, int32_t tj, double pos_old,
+                         double pos_new, double delta, double buf);   // multi_gpu.cuh
+__device__ void emig_publish(const Params& p, int tick);
+
 __device__ __forceinline__ double turn_onto(const Params& p, const int a, const int tick, const uint32_t st,
                                             const double cur, const double* __restrict__ pos_old, const TouchSink& sink) {
   Cold k = p.cold[a];
@@ -140,15 +144,28 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
   int32_t rc = p.route_off ? k.route_cur + 1 : 0;
   const int32_t nhop = route_head_on(p, target, it, k, k.agenda_cur, &rc);
   // (ahead / behind stay: k_unlink reads them.  atomicOr: a follower may be flagging this actor as a ghost right now)
-  atomicOr(&p.hot[a].st, ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u) | (remote ? ST_EMIG : 0u));
-  p.hot[a].tj = junction_after(p, it, nhop);
-  p.hot[a].delta = __dmul_rn(k.speed_dt, tinv);
+  const uint32_t more = ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
+  atomicOr(&p.hot[a].st, more | (remote ? ST_EMIG : 0u));
+  const int32_t tjn = junction_after(p, it, nhop);
+  const double delta = __dmul_rn(k.speed_dt, tinv);
+  p.hot[a].tj = tjn;
+  p.hot[a].delta = delta;
   p.hot[a].buf = tbuf;
   k.hop = nhop;
   k.container = target;
   k.mv_old = lane;
-  if (remote) p.emig[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_EMIG], 1)] = a;   // a few thousand per tick
-  else k.inbox_next = enter_lane(p, a, target, sink);
+  if (remote) {
+    // The actor lives on another rank from now on: its record goes straight into that rank's window (k_unlink
+    // then gives the slot up).  Not if it is a ghost — its follower holds its key, so its move is void
+    // (file header): the follower's thread flags it, this one just keeps the record back.
+    const int32_t b = p.hot[a].behind;
+    if (!(b >= 0 && pos_old[b] == cur)) {
+      if (p.route_off) k.route_cur = rc;
+      emigrate(p, a, tick, st | more, k, tjn, cur, tnext, delta, tbuf);
+    }
+  } else {
+    k.inbox_next = enter_lane(p, a, target, sink);
+  }
   k.outbox_next = leave_lane(p, a, lane, sink);
   int4* kc = (int4*)&p.cold[a];   // the first sector, in two stores
   kc[0] = make_int4(k.container, k.hop, k.dest_lane, k.dest_from_j);
@@ -432,6 +449,7 @@ __global__ void SLOW_BOUNDS k_slow(Params p, int tick) {
     if (threadIdx.x < nl) p.touched[s_base_l + threadIdx.x] = s_left[threadIdx.x];
     if (threadIdx.x < ne) p.touched[p.cap + s_base_e + threadIdx.x] = s_entered[threadIdx.x];
   }
+  if (p.owner) emig_publish(p, tick);   // partitioned world: the block that finishes last raises the migrant flags
 }
 
 }  // namespace griddy

@@ -130,6 +130,8 @@ struct Multi {
   bool connected = false;             // every neighbour's window is mapped
   std::vector<Ctx*> peers;            // local transport: every rank is a context of this process
   cudaEvent_t ev_ready = nullptr;     //   "what I write into my neighbours' windows in this phase is enqueued"
+  cudaStream_t side_stream = nullptr; // one process per GPU: carries k_halo_pack beside k_advance
+  cudaEvent_t ev_fork = nullptr, ev_packed = nullptr;
 };
 
 // Which items this context holds (griddy_set_item_ranges).  Ids are global registration indices everywhere;
@@ -329,6 +331,9 @@ void mg_reset(Ctx* c) {
     if (nb.mapped && nb.peer_base && m.peers.empty()) cudaIpcCloseMemHandle(nb.peer_base);
   for (void* ptr : m.allocs) cudaFree(ptr);
   if (m.ev_ready) cudaEventDestroy(m.ev_ready);
+  if (m.ev_fork) cudaEventDestroy(m.ev_fork);
+  if (m.ev_packed) cudaEventDestroy(m.ev_packed);
+  if (m.side_stream) cudaStreamDestroy(m.side_stream);
   m = Multi();
   c->mg_owner_host.clear();
   Params& p = c->p;
@@ -1167,7 +1172,6 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
 
   TRY(dev_alloc(c, pool, &p.touched, 2 * cap));
   TRY(dev_alloc(c, pool, &p.slow, cap));
-  TRY(dev_alloc(c, pool, &p.emig, cap));
   TRY(dev_alloc(c, pool, &p.counters, 2 * CNT_STRIDE));
   TRY(dev_alloc(c, pool, &p.scal, SC_COUNT));
 #ifdef GRIDDY_TRACE
@@ -1317,10 +1321,7 @@ unsigned relink_blocks(const Ctx* c) {
 }
 
 int tick_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // local lists only: does not need the migrants
-  if (c->mg.on)   // its first blocks send this tick's emigrants
-    CUDA_TRY(c, launch_dependent(k_unlink<true>, relink_blocks(c) + EMIG_BLOCKS, 128u, c->stream, c->p, (int)tick));
-  else
-    CUDA_TRY(c, launch_dependent(k_unlink<false>, relink_blocks(c), 128u, c->stream, c->p, (int)tick));
+  CUDA_TRY(c, launch_dependent(k_unlink, relink_blocks(c), 128u, c->stream, c->p, (int)tick));
   if (ev) cudaEventRecord(ev[4], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -1334,13 +1335,16 @@ int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // on a partitioned wor
 }
 
 // ---- the small kernels of a partitioned world ----------------------------------------------------------
-// All of them run on the compute stream, in this order per tick:
-//   k_halo_pack      (before k_advance: the halo travels over NVLink while k_advance streams the actors; it
-//                     reads the OLD world only, which k_advance does not write)
+// Per tick, one process per GPU:
+//   k_halo_pack      on a second, high-priority stream beside k_advance: it reads the OLD world only (which
+//                    k_advance does not write) and stores into the neighbours' windows, so the halo travels over
+//                    NVLink while k_advance streams the actors, and the four tick kernels stay back to back
 //   k_advance
-//   k_halo_unpack    waits for the neighbours' halo flags; k_slow behind it may read the halo
-//   k_slow
-//   k_unlink         its first blocks write the emigrants into the neighbours' windows and raise the flags
+//   k_halo_unpack    waits for the neighbours' halo flags (and, through an event, for this rank's own pack:
+//                    k_slow changes what it reads); k_slow behind it may read the halo
+//   k_slow           a mover whose new lane another rank owns writes its record into that rank's window; the
+//                    block that finishes last raises the migrant flags
+//   k_unlink         local lists only — meanwhile the neighbours' flags arrive
 //   k_immig_unpack   waits for the neighbours' migrant flags
 //   k_link
 int mg_halo_pack(Ctx* c, int64_t tick, cudaStream_t s) {
@@ -1390,11 +1394,16 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
     TRY(tick_unlink(c, tick, ev));
     return tick_link(c, tick, ev);
   }
-  TRY(mg_halo_pack(c, tick, c->stream));
+  Multi& m = c->mg;
+  CUDA_TRY(c, cudaEventRecord(m.ev_fork, c->stream));          // (everything up to the previous tick's k_link)
+  CUDA_TRY(c, cudaStreamWaitEvent(m.side_stream, m.ev_fork, 0));
+  TRY(mg_halo_pack(c, tick, m.side_stream));
+  CUDA_TRY(c, cudaEventRecord(m.ev_packed, m.side_stream));
   TRY(tick_advance(c, tick, ev));                 // while the halo travels
+  CUDA_TRY(c, cudaStreamWaitEvent(c->stream, m.ev_packed, 0));
   TRY(mg_halo_unpack(c, tick, c->stream));        // waits for the neighbours' halo flags
-  TRY(tick_slow(c, tick, ev));
-  TRY(tick_unlink(c, tick, ev));                  // its first blocks send the emigrants
+  TRY(tick_slow(c, tick, ev));                    // movers that cross write themselves into the neighbours' windows
+  TRY(tick_unlink(c, tick, ev));
   TRY(mg_immig_unpack(c, tick, c->stream));       // waits for the neighbours' migrant flags
   return tick_link(c, tick, ev);
 }
@@ -1522,7 +1531,11 @@ int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks) {
     TRY(each(tick_advance, t, false));
     for (Ctx* c : cs) TRY(wait_for_neighbours(c));
     TRY(each(local_slow, t, false));
-    TRY(each(tick_unlink, t, true));                       // (its first blocks write the emigrants)
+    for (Ctx* c : cs) {                                    // (k_slow wrote the emigrants into the neighbours' windows)
+      CUDA_TRY(c, cudaSetDevice(c->device));
+      CUDA_TRY(c, cudaEventRecord(c->mg.ev_ready, c->stream));
+    }
+    TRY(each(tick_unlink, t, false));
     for (Ctx* c : cs) TRY(wait_for_neighbours(c));
     TRY(each(local_link, t, false));
   }
@@ -1834,6 +1847,13 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     m.d_owner = d_owner;
   }
   CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_packed, cudaEventDisableTiming));
+  {   // the halo kernel must not queue behind k_advance's blocks
+    int least = 0, greatest = 0;
+    CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CUDA_TRY(c, cudaStreamCreateWithPriority(&m.side_stream, cudaStreamNonBlocking, greatest));
+  }
   const NetView v{&tl, c->h_kind.data(), lane_in, c->h_lane_out.data(), c->h_lane_junction.data(), owner};
   // what I export to / import from every other rank
   struct Lists { std::vector<int32_t> exp_l, exp_j, imp_l, imp_j; };

@@ -61,21 +61,12 @@ __device__ int later_processed(const Params& p, int x, int y, int32_t lane, cons
 // Junction occupancy (route.scm:98-104) changes by whole lanes: one atomic per lane and kernel.
 constexpr int32_t UNLINKED = -3;
 
-// On a partitioned world (MG) the first EMIG_BLOCKS blocks pack this tick's emigrants instead
-// (multi_gpu.cuh, emig_pack_block).
-template <bool MG>
-__global__ void __launch_bounds__(128, MG ? 12 : 1) k_unlink(Params p, int tick) {   // (the packing blocks may spill; the rest keep their occupancy)
+__global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
   grid_dependency_wait();
   TRACE(p, tick, TR_UNLINK);
-  if (MG && blockIdx.x < EMIG_BLOCKS) {
-    emig_pack_block(p, tick, blockIdx.x, EMIG_BLOCKS);
-    return;
-  }
   const int par = tick & 1;
   const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_LEFT];
-  const int32_t first = ((int)blockIdx.x - (MG ? EMIG_BLOCKS : 0)) * blockDim.x + threadIdx.x;
-  const int32_t stride = ((int)gridDim.x - (MG ? EMIG_BLOCKS : 0)) * blockDim.x;
-  for (int32_t i = first; i < n_touched; i += stride) {
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = p.touched[i];
     LaneRec* lr = &p.lane[lane];
     const uint32_t meta = lr->meta;

@@ -104,80 +104,56 @@ __global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __
   if (i < n) p.occ[junctions[i]] = (int32_t)__ldcg(&p.halo_recv[par][where[i]]);
 }
 
-// Emigrants -> one record each plus their remaining agenda items, written straight into the window of the
-// rank that owns their new lane, so only the actors that actually crossed travel, not a bound-sized message.
-// Places are handed out by atomics on this rank's own counters; the block that finishes last publishes the
-// counts and raises the flag in every neighbour's window: nothing follows the records.
-// Runs as the first EMIG_BLOCKS blocks of k_unlink (lanes.cuh): both need k_slow only, and what k_unlink
-// changes of an emigrant's slot — it clears ALIVE | MOVED | EMIG in st — is rebuilt here.
-constexpr int EMIG_BLOCKS = 64;
-
-__device__ __forceinline__ void emig_pack_block(const Params& p, const int tick, const int block, const int n_blocks) {
-  __shared__ bool s_last;
-  __shared__ int32_t s_count[MAX_RANKS], s_base[MAX_RANKS];
-  TRACE(p, tick, TR_EMIG_PACK);
+// Emigrants -> one record each plus their remaining agenda items, written by the k_slow thread that moves the actor
+// straight into the window of the rank that owns its new lane (everything the record holds is in that thread's
+// registers), so only the actors that actually crossed travel, not a bound-sized message, and nothing packs them
+// in a separate pass.  Places are handed out by atomics on this rank's own counters.  The block of k_slow that
+// finishes last publishes the counts and raises the flag in every neighbour's window: nothing follows the records.
+__device__ void emigrate(const Params& p, int a, int tick, uint32_t st, const Cold& k, int32_t tj, double pos_old,
+                         double pos_new, double delta, double buf) {
   const int par = tick & 1;
-  const int32_t n = p.counters[CNT_STRIDE * par + CNT_EMIG];
-  for (int32_t chunk = block * blockDim.x; chunk < n; chunk += n_blocks * blockDim.x) {
-    if (threadIdx.x < MAX_RANKS) s_count[threadIdx.x] = 0;
-    __syncthreads();
-    const int32_t i = chunk + threadIdx.x;
-    int a = -1, to = -1, mine = 0;
-    int32_t first_item = 0;
-    MigRec r;
-    if (i < n) {
-      a = p.emig[i];
-      const Hot h = p.hot[a];
-      if (h.st & ST_GHOST) {
-        a = -1;   // a ghost's move is void
-      } else {
-        // the whole record is gathered before a place is reserved: one round trip less on the way
-        const Cold k = p.cold[a];
-        const ColdF f = p.coldf[a];
-        to = p.owner[k.container];
-        mine = atomicAdd(&s_count[to], 1);
-        r.pos_old = p.pos[par][a];
-        r.pos_new = p.pos[par ^ 1][a];
-        r.delta = h.delta;
-        r.buf = h.buf;
-        r.arrive = f.arrive;
-        r.land_pos = f.land_pos;
-        r.speed = k.speed;
-        r.speed_dt = k.speed_dt;
-        r.gid = k.gid;
-        r.st = (int32_t)(((h.st | ST_ALIVE | ST_MOVED) & ~ST_EMIG) | ST_IMMIG);
-        r.container = k.container;
-        r.mv_old = k.mv_old;
-        r.hop = k.hop;
-        r.tj = h.tj >= 0 ? (h.tj & ~TJ_REMOTE) : -1;
-        r.dest_lane = k.dest_lane;
-        r.dest_from_j = k.dest_from_j;
-        r.dest_to_j = k.dest_to_j;
-        r.route_cur = k.route_cur;
-        r.pad = 0;
-        first_item = k.agenda_cur;
-        r.popped = k.agenda_cur - f.agenda_beg;
-        r.n_items = f.agenda_end - k.agenda_cur;
-        r.land_tick = f.land_tick;
-        r.land_lane = f.land_lane;
-        r.item_off = atomicAdd(&p.mig_count[MAX_RANKS + to], r.n_items);
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x < MAX_RANKS && s_count[threadIdx.x] > 0)
-      s_base[threadIdx.x] = atomicAdd(&p.mig_count[threadIdx.x], s_count[threadIdx.x]);
-    __syncthreads();
-    if (a < 0) continue;
-    const int32_t at = s_base[to] + mine;
-    if (at >= p.mig_cap[to] || r.item_off + r.n_items > p.mig_icap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); continue; }
-    uint8_t* area = p.mig_peer[to][par];
-    ((MigRec*)(area + sizeof(MigHeader)))[at] = r;
-    AgendaItem* items = (AgendaItem*)(area + sizeof(MigHeader) + (size_t)p.mig_cap[to] * sizeof(MigRec)) + r.item_off;
-    for (int32_t q = 0; q < r.n_items; ++q) items[q] = p.agenda[first_item + q];
-  }
-  __threadfence_system();   // my records before my block's count
+  const ColdF f = p.coldf[a];
+  const int to = p.owner[k.container];
+  MigRec r;
+  r.n_items = f.agenda_end - k.agenda_cur;
+  const int32_t at = atomicAdd(&p.mig_count[to], 1);
+  r.item_off = atomicAdd(&p.mig_count[MAX_RANKS + to], r.n_items);
+  if (at >= p.mig_cap[to] || r.item_off + r.n_items > p.mig_icap[to]) { dev_error(p, DEV_ERR_MIG_OVERFLOW); return; }
+  r.pos_old = pos_old;
+  r.pos_new = pos_new;
+  r.delta = delta;
+  r.buf = buf;
+  r.arrive = f.arrive;
+  r.land_pos = f.land_pos;
+  r.speed = k.speed;
+  r.speed_dt = k.speed_dt;
+  r.gid = k.gid;
+  r.st = (int32_t)(((st | ST_ALIVE | ST_MOVED) & ~(ST_EMIG | ST_GHOST)) | ST_IMMIG);
+  r.container = k.container;
+  r.mv_old = k.mv_old;
+  r.hop = k.hop;
+  r.tj = tj >= 0 ? (tj & ~TJ_REMOTE) : -1;
+  r.popped = k.agenda_cur - f.agenda_beg;
+  r.land_tick = f.land_tick;
+  r.land_lane = f.land_lane;
+  r.dest_lane = k.dest_lane;
+  r.dest_from_j = k.dest_from_j;
+  r.dest_to_j = k.dest_to_j;
+  r.route_cur = k.route_cur;
+  r.pad = 0;
+  uint8_t* area = p.mig_peer[to][par];
+  ((MigRec*)(area + sizeof(MigHeader)))[at] = r;
+  AgendaItem* items = (AgendaItem*)(area + sizeof(MigHeader) + (size_t)p.mig_cap[to] * sizeof(MigRec)) + r.item_off;
+  for (int32_t q = 0; q < r.n_items; ++q) items[q] = p.agenda[k.agenda_cur + q];
+}
+
+// End of k_slow on a partitioned world, every block: my records before my block's count; the last block publishes.
+__device__ void emig_publish(const Params& p, int tick) {
+  __shared__ bool s_last;
+  const int par = tick & 1;
+  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(p.mig_done, 1) == n_blocks - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(p.mig_done, 1) == (int)gridDim.x - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();   // every block's records before the headers

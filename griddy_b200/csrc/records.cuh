@@ -168,7 +168,6 @@ struct Params {
   const int32_t* hflag_mine[MAX_RANKS][2];   // the flags my neighbours raise in my window
   int32_t halo_first[MAX_RANKS], halo_n[MAX_RANKS];   // my export list, by neighbour: entries [first, first + n)
   int32_t* halo_done;        // blocks of k_halo_pack that have finished (the last one raises the flags)
-  int32_t* emig;             // slots that emigrated this tick
   int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
   int32_t mig_icap[MAX_RANKS];    //   and agenda items per tick
   // by destination rank and tick parity: that rank's receive area for my emigrants, in ITS window:
@@ -178,7 +177,7 @@ struct Params {
   int32_t* mig_mine[MAX_RANKS][2];   // my own receive areas, by source rank
   int32_t mig_in[MAX_RANKS];         // by source rank: records per tick at most
   int32_t* mig_count;                // [2 x MAX_RANKS] places handed out this tick, by destination: records, items
-  int32_t* mig_done;                 // packing blocks of k_unlink that have finished (the last one publishes)
+  int32_t* mig_done;                 // blocks of k_slow that have finished (the last one publishes the counts and raises the flags)
   unsigned long long* trace;         // -DGRIDDY_TRACE builds: [64 ticks][16] %globaltimer stamps (griddy_debug_trace)
 };
 
