@@ -118,6 +118,7 @@ __device__ __forceinline__ int32_t leave_lane(const Params& p, int a, int32_t la
 __device__ void emigrate(const Params& p, int a, int tick, uint32_t st, const Cold& k, int32_t tj, double pos_old,
                          double pos_new, double delta, double buf);   // multi_gpu.cuh
 __device__ void emig_publish(const Params& p, int tick);
+__device__ __forceinline__ void halo_pack_block(const Params& p, int tick, int n_blocks);
 
 __device__ __forceinline__ double turn_onto(const Params& p, const int a, const int tick, const uint32_t st,
                                             const double cur, const double* __restrict__ pos_old, const TouchSink& sink) {
@@ -330,7 +331,8 @@ constexpr int ADV_THREADS = ADV_THREADS_N;
 #define ADV_BOUNDS __launch_bounds__(ADV_THREADS)
 #endif
 
-__global__ void ADV_BOUNDS k_advance(Params p, int tick) {
+// On a partitioned world the first halo_blocks blocks send the halo instead (multi_gpu.cuh, halo_pack_block).
+__global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks) {
   __shared__ int4 s_list[ADV_THREADS * ADV_UNROLL];
   __shared__ int32_t s_n, s_base;
   grid_dependency_wait();
@@ -338,8 +340,12 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick) {
   const int par = tick & 1;
   int32_t* counters = p.counters + CNT_STRIDE * par;
   if (blockIdx.x == 0 && threadIdx.x < CNT_STRIDE) p.counters[CNT_STRIDE * (par ^ 1) + threadIdx.x] = 0;
+  if ((int)blockIdx.x < halo_blocks) {
+    halo_pack_block(p, tick, halo_blocks);
+    return;
+  }
   const int n = p.scal[SC_NSLOTS];
-  const int base = blockIdx.x * (ADV_THREADS * ADV_UNROLL) + threadIdx.x;
+  const int base = ((int)blockIdx.x - halo_blocks) * (ADV_THREADS * ADV_UNROLL) + threadIdx.x;
   if (base - (int)threadIdx.x >= n) return;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();

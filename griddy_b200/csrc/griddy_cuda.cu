@@ -130,8 +130,6 @@ struct Multi {
   bool connected = false;             // every neighbour's window is mapped
   std::vector<Ctx*> peers;            // local transport: every rank is a context of this process
   cudaEvent_t ev_ready = nullptr;     //   "what I write into my neighbours' windows in this phase is enqueued"
-  cudaStream_t side_stream = nullptr; // one process per GPU: carries k_halo_pack beside k_advance
-  cudaEvent_t ev_fork = nullptr, ev_packed = nullptr;
 };
 
 // Which items this context holds (griddy_set_item_ranges).  Ids are global registration indices everywhere;
@@ -331,9 +329,6 @@ void mg_reset(Ctx* c) {
     if (nb.mapped && nb.peer_base && m.peers.empty()) cudaIpcCloseMemHandle(nb.peer_base);
   for (void* ptr : m.allocs) cudaFree(ptr);
   if (m.ev_ready) cudaEventDestroy(m.ev_ready);
-  if (m.ev_fork) cudaEventDestroy(m.ev_fork);
-  if (m.ev_packed) cudaEventDestroy(m.ev_packed);
-  if (m.side_stream) cudaStreamDestroy(m.side_stream);
   m = Multi();
   c->mg_owner_host.clear();
   Params& p = c->p;
@@ -352,6 +347,8 @@ void mg_reset(Ctx* c) {
     p.mig_cap[r] = p.mig_icap[r] = p.mig_in[r] = 0;
   }
   p.halo_done = p.mig_done = p.mig_count = nullptr;
+  p.halo_items = nullptr;
+  p.halo_total = 0;
 }
 
 // What a rank (or the host-only helper griddy_mg_plan) sees of the network: compact arrays over the held
@@ -1301,7 +1298,10 @@ int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
 int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   const unsigned per_block = ADV_THREADS * ADV_UNROLL;
   const unsigned adv_blocks = (unsigned)((c->ns_host + per_block - 1) / per_block);
-  if (adv_blocks) CUDA_TRY(c, launch_dependent(k_advance, adv_blocks, ADV_THREADS, c->stream, c->p, (int)tick));
+  // a partitioned world: its first blocks send the halo (at least one: it raises the flags)
+  const unsigned halo_blocks = c->mg.nb.empty() ? 0u : (unsigned)std::max(1, (c->mg.n_exp + ADV_THREADS - 1) / ADV_THREADS);
+  if (adv_blocks + halo_blocks)
+    CUDA_TRY(c, launch_dependent(k_advance, adv_blocks + halo_blocks, ADV_THREADS, c->stream, c->p, (int)tick, (int)halo_blocks));
   if (ev) cudaEventRecord(ev[2], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -1335,26 +1335,15 @@ int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // on a partitioned wor
 }
 
 // ---- the small kernels of a partitioned world ----------------------------------------------------------
-// Per tick, one process per GPU:
-//   k_halo_pack      on a second, high-priority stream beside k_advance: it reads the OLD world only (which
-//                    k_advance does not write) and stores into the neighbours' windows, so the halo travels over
-//                    NVLink while k_advance streams the actors, and the four tick kernels stay back to back
-//   k_advance
-//   k_halo_unpack    waits for the neighbours' halo flags (and, through an event, for this rank's own pack:
-//                    k_slow changes what it reads); k_slow behind it may read the halo
+// Per tick, all on the compute stream:
+//   k_advance        its first blocks send the halo: they read the OLD world only, like the rest of the kernel, and
+//                    store into the neighbours' windows, so the halo travels over NVLink while the actors stream
+//   k_halo_unpack    waits for the neighbours' halo flags; k_slow behind it may read the halo
 //   k_slow           a mover whose new lane another rank owns writes its record into that rank's window; the
 //                    block that finishes last raises the migrant flags
 //   k_unlink         local lists only — meanwhile the neighbours' flags arrive
 //   k_immig_unpack   waits for the neighbours' migrant flags
 //   k_link
-int mg_halo_pack(Ctx* c, int64_t tick, cudaStream_t s) {
-  if (c->mg.nb.empty()) return GRIDDY_OK;
-  const unsigned blocks = (unsigned)std::max(1, (c->mg.n_exp + 127) / 128);   // at least one: it raises the flags
-  CUDA_TRY(c, launch_dependent(k_halo_pack, blocks, 128u, s, c->p, (const int32_t*)c->mg.d_exp_items, c->mg.n_exp, (int)tick));
-  ++c->launches;
-  return GRIDDY_OK;
-}
-
 int mg_halo_unpack(Ctx* c, int64_t tick, cudaStream_t s) {
   if (c->mg.nb.empty()) return GRIDDY_OK;
   const unsigned blocks = (unsigned)std::max(1, (c->mg.n_imp_junc + 127) / 128);   // at least one: it waits for the flags
@@ -1394,13 +1383,7 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
     TRY(tick_unlink(c, tick, ev));
     return tick_link(c, tick, ev);
   }
-  Multi& m = c->mg;
-  CUDA_TRY(c, cudaEventRecord(m.ev_fork, c->stream));          // (everything up to the previous tick's k_link)
-  CUDA_TRY(c, cudaStreamWaitEvent(m.side_stream, m.ev_fork, 0));
-  TRY(mg_halo_pack(c, tick, m.side_stream));
-  CUDA_TRY(c, cudaEventRecord(m.ev_packed, m.side_stream));
-  TRY(tick_advance(c, tick, ev));                 // while the halo travels
-  CUDA_TRY(c, cudaStreamWaitEvent(c->stream, m.ev_packed, 0));
+  TRY(tick_advance(c, tick, ev));                 // its first blocks send the halo, which travels while the rest run
   TRY(mg_halo_unpack(c, tick, c->stream));        // waits for the neighbours' halo flags
   TRY(tick_slow(c, tick, ev));                    // movers that cross write themselves into the neighbours' windows
   TRY(tick_unlink(c, tick, ev));
@@ -1415,7 +1398,7 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
 // where a spinning kernel could otherwise keep the writer from running.
 int local_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   TRY(tick_begin(c, tick, ev));
-  return mg_halo_pack(c, tick, c->stream);
+  return tick_advance(c, tick, ev);   // (its first blocks write the halo into the neighbours' windows)
 }
 
 int local_slow(Ctx* c, int64_t tick, cudaEvent_t* ev) {
@@ -1527,8 +1510,7 @@ int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks) {
     return GRIDDY_OK;
   };
   for (int64_t t = 0; t < n_ticks; ++t) {
-    TRY(each(local_begin, t, true));                       // (k_halo_pack writes the neighbours' windows)
-    TRY(each(tick_advance, t, false));
+    TRY(each(local_begin, t, true));                       // (k_advance's first blocks write the neighbours' windows)
     for (Ctx* c : cs) TRY(wait_for_neighbours(c));
     TRY(each(local_slow, t, false));
     for (Ctx* c : cs) {                                    // (k_slow wrote the emigrants into the neighbours' windows)
@@ -1847,13 +1829,6 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     m.d_owner = d_owner;
   }
   CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_ready, cudaEventDisableTiming));
-  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming));
-  CUDA_TRY(c, cudaEventCreateWithFlags(&m.ev_packed, cudaEventDisableTiming));
-  {   // the halo kernel must not queue behind k_advance's blocks
-    int least = 0, greatest = 0;
-    CUDA_TRY(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    CUDA_TRY(c, cudaStreamCreateWithPriority(&m.side_stream, cudaStreamNonBlocking, greatest));
-  }
   const NetView v{&tl, c->h_kind.data(), lane_in, c->h_lane_out.data(), c->h_lane_junction.data(), owner};
   // what I export to / import from every other rank
   struct Lists { std::vector<int32_t> exp_l, exp_j, imp_l, imp_j; };
@@ -1935,6 +1910,8 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     CUDA_TRY(c, cudaMemcpy(m.d_imp_where, imp_where_all.data(), imp_where_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
   p.owner = m.d_owner;
+  p.halo_items = m.d_exp_items;
+  p.halo_total = m.n_exp;
   p.my_rank = rank;
   m.connected = m.nb.empty();
   return GRIDDY_OK;

@@ -55,17 +55,18 @@ __device__ __forceinline__ void wait_flag(const Params& p, const int32_t* flag, 
 
 // Halo out: for every lane of mine that a neighbour's actors can enter, its smallest key in (0, ...]
 // (the walk route.scm:118-121 would do), +inf if there is none; for every such junction, its occupancy.
-// One launch for all neighbours: `items` holds the neighbours' lists back to back (a junction is listed
-// as ~id); every value is stored straight into the reading rank's window, and the block that finishes
-// last raises the flag in every neighbour's window.
-__global__ void __launch_bounds__(128) k_halo_pack(Params p, const int32_t* __restrict__ items, int n, int tick) {
+// Runs as the first blocks of k_advance (advance.cuh): both read the OLD world only, so the halo leaves at the very
+// start of the tick and travels over NVLink while the other blocks stream the actors — no extra launch, no second
+// stream.  Params::halo_items holds the neighbours' lists back to back (a junction is listed as ~id); every value is
+// stored straight into the reading rank's window, and the block that finishes last raises the flag in every
+// neighbour's window.
+__device__ __forceinline__ void halo_pack_block(const Params& p, const int tick, const int n_blocks) {
   __shared__ bool s_last;
-  grid_dependency_wait();
   TRACE(p, tick, TR_HALO_PACK);
   const int par = tick & 1;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const int32_t item = items[i];
+  const int n = p.halo_total;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += n_blocks * blockDim.x) {
+    const int32_t item = p.halo_items[i];
     double v;
     if (item < 0) {
       v = (double)p.occ[~item];
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(128) k_halo_pack(Params p, const int32_t* __re
   }
   __threadfence_system();   // my values before my block's count
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(p.halo_done, 1) == (int)gridDim.x - 1;
+  if (threadIdx.x == 0) s_last = atomicAdd(p.halo_done, 1) == n_blocks - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();   // every block's values before the flags

@@ -167,7 +167,9 @@ struct Params {
   int32_t* hflag_peer[MAX_RANKS][2];      //   and the flag I raise there (tick + 1) once it is complete
   const int32_t* hflag_mine[MAX_RANKS][2];   // the flags my neighbours raise in my window
   int32_t halo_first[MAX_RANKS], halo_n[MAX_RANKS];   // my export list, by neighbour: entries [first, first + n)
-  int32_t* halo_done;        // blocks of k_halo_pack that have finished (the last one raises the flags)
+  const int32_t* halo_items; // my export list: my lane, or ~(my junction), the neighbours' parts back to back
+  int32_t halo_total;        //   its length
+  int32_t* halo_done;        // halo blocks of k_advance that have finished (the last one raises the flags)
   int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
   int32_t mig_icap[MAX_RANKS];    //   and agenda items per tick
   // by destination rank and tick parity: that rank's receive area for my emigrants, in ITS window:
