@@ -318,11 +318,13 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 // arrays.  Any other actor — a few percent — would drag its whole warp through chains of dependent
 // gathers, so its slot is appended to the slow list instead (block-aggregated: one global atomic per
 // block) and k_slow runs the full advance$ for it with one thread per listed actor.
+// Measured on B200 (profiles/r2/variants.md): 2 slots per thread x 128 threads (40 registers) beats 256 and 512
+// threads (the block's two barriers wait for fewer warps) and 1 or 4 slots per thread.
 #ifndef ADV_UNROLL
 #define ADV_UNROLL 2
 #endif
 #ifndef ADV_THREADS_N
-#define ADV_THREADS_N 256
+#define ADV_THREADS_N 128
 #endif
 constexpr int ADV_THREADS = ADV_THREADS_N;
 #ifdef ADV_MIN_BLOCKS
@@ -334,6 +336,7 @@ constexpr int ADV_THREADS = ADV_THREADS_N;
 // On a partitioned world the first halo_blocks blocks send the halo instead (multi_gpu.cuh, halo_pack_block).
 __global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks) {
   __shared__ int4 s_list[ADV_THREADS * ADV_UNROLL];
+  __shared__ double s_pos[ADV_THREADS * ADV_UNROLL];
   __shared__ int32_t s_n, s_base;
   grid_dependency_wait();
   TRACE(p, tick, TR_ADVANCE);
@@ -347,14 +350,13 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks) {
   const int n = p.scal[SC_NSLOTS];
   const int base = ((int)blockIdx.x - halo_blocks) * (ADV_THREADS * ADV_UNROLL) + threadIdx.x;
   if (base - (int)threadIdx.x >= n) return;
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
+  if (threadIdx.x == 0) s_n = 0;   // (the barrier after the first round of loads orders this before any append)
   const double* __restrict__ pos_old = p.pos[par];
   double* __restrict__ pos_new = p.pos[par ^ 1];
   const int4* __restrict__ hot4 = (const int4*)p.hot;
 
   uint32_t st[ADV_UNROLL];
-  int32_t ah[ADV_UNROLL], tj[ADV_UNROLL];
+  int32_t ah[ADV_UNROLL], tj[ADV_UNROLL], occ[ADV_UNROLL];
   double cur[ADV_UNROLL], dlt[ADV_UNROLL], buf[ADV_UNROLL], lead[ADV_UNROLL];
 #pragma unroll
   for (int k = 0; k < ADV_UNROLL; ++k) {
@@ -368,12 +370,22 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks) {
     dlt[k] = __hiloint2double(h1.y, h1.x);
     buf[k] = __hiloint2double(h1.w, h1.z);
     cur[k] = in ? pos_old[a] : 0.0;
+    s_pos[k * ADV_THREADS + threadIdx.x] = cur[k];   // the block's pos-params: most leaders are among them
   }
+  __syncthreads();
+  // second round of loads, all independent of each other: the leader's pos-param — from shared memory when the
+  // leader is one of this block's slots (after a reorder nearly always), else a gather — and, for an actor that can
+  // reach its lane's end this tick, the occupancy of the junction ahead (clamping behind a leader only shortens the step)
+  const int tile0 = base - (int)threadIdx.x;
 #pragma unroll
   for (int k = 0; k < ADV_UNROLL; ++k) {
     const bool on_road = (st[k] & (ST_ALIVE | ST_ONROAD)) == (ST_ALIVE | ST_ONROAD);
     if (!on_road) ah[k] = -1;   // an off-road actor's ahead is stale
-    lead[k] = ah[k] >= 0 ? pos_old[ah[k]] : 0.0;
+    const unsigned rel = (unsigned)(ah[k] - tile0);
+    lead[k] = ah[k] < 0 ? 0.0 : (rel < (unsigned)(ADV_THREADS * ADV_UNROLL) ? s_pos[rel] : pos_old[ah[k]]);
+    const bool may_turn = on_road && ((st[k] >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME && !(st[k] & ST_ARRIVE) &&
+                          tj[k] >= 0 && tj[k] < TJ_REMOTE && __dadd_rn(cur[k], dlt[k]) >= 1.0;
+    occ[k] = may_turn ? p.occ[tj[k]] : 0;
   }
 #pragma unroll
   for (int k = 0; k < ADV_UNROLL; ++k) {
@@ -391,7 +403,7 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks) {
         if (st[k] & ST_ARRIVE) slow = true;
         else if (!(next >= 1.0)) np = next;
         else if (tj[k] >= TJ_REMOTE) slow = true;                  // the junction's occupancy is still on its way (halo)
-        else if (tj[k] >= 0 && p.occ[tj[k]] > 0) np = cur[k];   // waiting for a full junction  route.scm:98-111
+        else if (tj[k] >= 0 && occ[k] > 0) np = cur[k];         // waiting for a full junction  route.scm:98-111
         else slow = turn = true;                                   // turns onto the next lane
       } else if (rs == GRIDDY_ROUTE_NONE && head == HEAD_SLEEP) {   // sleep$, time left  simulate.scm:77
         if (tj[k] == 0) slow = true;

@@ -595,6 +595,7 @@ int griddy_create(void** ctx, int device) {
   c->p.dt = 1.0 / 15.0;
   c->p.two_size = 10.0;
   if (const char* e = getenv("GRIDDY_REORDER_PERIOD")) c->reorder_period = atoi(e);
+  if (const char* e = getenv("GRIDDY_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));   // experiments: 32 / 64 / 128
   *ctx = c;
   return GRIDDY_OK;
 }
