@@ -9,38 +9,34 @@
 // on a lane replaces the earlier actor (core.scm:173-178), and a segment's off-road list is consed
 // (core.scm:169-171).  Both are reproduced from local data, without a global sort (see below).
 //
-// Data layout (HBM, structure of arrays).  Actors live in SLOTS; a slot's number is not the actor's
-// id.  Every REORDER_PERIOD ticks the live actors are radix-sorted by (locality key of their lane or
-// segment, coarse pos-param) and all per-slot arrays are permuted (radix_sort.cuh, k_make_keys,
-// k_permute): the actors of a lane then sit next to each other in ascending pos-param, neighbouring
-// lanes sit in neighbouring cache lines, and dead actors are dropped.  Between reorders slots are
-// stable; order within a lane is carried exactly by the `ahead` pointers, so the sort only has to be
+// Data layout (HBM; records.cuh).  Actors live in SLOTS; a slot's number is not the actor's id.  Every
+// reorder_period ticks — and whenever a step begins with more than 1/16 of the slots dead — the live actors are
+// radix-sorted by (locality key of their lane or segment, coarse pos-param) and all per-slot arrays are permuted
+// (radix_sort.cuh, reorder.cuh): the actors of a lane then sit next to each other in ascending pos-param,
+// neighbouring lanes sit in neighbouring cache lines, and dead actors are dropped.  Between reorders slots are
+// stable; order within a lane is carried exactly by the ahead / behind pointers, so the sort only has to be
 // good for locality, never for correctness.
-//   hot, read by every on-road actor every tick
-//     st         u32  alive | on_road | side | route status | agenda head kind | moved | stamp class
-//                     | route head is (arrive-at _)
-//     ahead      i32  slot of the next actor ahead on the same lane (ascending pos-param), -1 at the front
-//     pos[2]     f64  pos-param, ping-pong by tick parity: followers read the old buffer
-//     delta,buf  f64  per-tick advance and tailgate buffer on the current lane, cached at lane entry
-//                     (route.scm:62-66: fl(speed*dt)*fl(1/len) and 10/len)
-//   cold, touched only when an actor sleeps, changes lane, or starts / ends a route
-//     aux        i32  sleeping: remaining time; travelling: head route step (lane, or -1 arrive-at)
-//     container  i32  lane (on road) or segment (off road);  arrive f64  target of (arrive-at _)
-//     agenda_cur, route_cur, id (the actor's id), land_* (landing stamp, see below)
-//   by actor id, immutable:  speed, speed_dt, agenda CSR, explicit routes
-//   by item:  lane_tail i32 rearmost actor of a lane;  occ i32 actors on a junction's lanes
+//   Hot      32 B per slot, read by every actor every tick: st (alive | on_road | side | route status | agenda head kind
+//            | moved | stamp class | route head is (arrive-at _) | ghost), ahead / behind (neighbours on the lane), tj
+//            (junction gating the route head; asleep: remaining sleep time), delta / buf (per-tick advance and tailgate
+//            buffer on the current lane, route.scm:62-66, cached at lane entry)
+//   pos[2]   f64 pos-param, ping-pong by tick parity: followers read the old buffer
+//   Cold     64 B per slot, touched only when an actor changes lane, wakes, or starts / ends a route: container, route
+//            head, cached destination, list-surgery links, speed, cursors, actor id;  ColdF: arrive target, landing stamp
+//   LaneRec  64 B per registered item: length, links, this tick's marks and counts, list heads, routing-table row
+//   occ      i32 per junction: actors on its lanes
 // Per-lane order changes only where an actor entered or left a lane this tick; nothing is O(lanes)
 // per tick (lanes outnumber actors 1.5:1 to 4:1 on the grids).
 //
-// Kernels per tick
-//   k_advance  one thread per slot: agenda dispatch + motion, all handlers fused.  Coalesced SoA
-//              reads; the leader's pos-param is a gather that the slot order keeps inside the same
-//              or a neighbouring cache line.  Actors that change lane or road-side are appended to
-//              the movers list and pushed on their target lane's inbox (warp-aggregated atomics);
-//              their lanes are marked touched.
-//   k_unlink   one thread per touched lane.  Lanes are doubly linked lists: leavers and ghosts are
+// Kernels per tick (advance.cuh, lanes.cuh; multi_gpu.cuh for a partitioned world)
+//   k_advance  one thread per two slots: agenda dispatch + motion for the common cases (on the lane, waiting for a
+//              full junction, asleep, idle).  Coalesced reads of Hot and pos; the leader's pos-param comes from the
+//              block's shared-memory tile or a gather that the slot order keeps close.  Everything else is deferred.
+//   k_slow     one thread per deferred actor: lane changes with carry-over, arrive-at, begin / end of a route, waking,
+//              ghost detection.  Movers are pushed on their target lane's inbox and their old lane's outbox.
+//   k_unlink   one thread per lane an actor left.  Lanes are doubly linked lists: leavers and ghosts are
 //              taken out in O(1) each; actors that are done for the tick are settled.
-//   k_link     one thread per touched lane: entrants are inserted by a short walk up from the rear; an
+//   k_link     one thread per lane an actor entered: entrants are inserted by a short walk up from the rear; an
 //              entrant that lands on an occupied key is resolved exactly as bbtree-set would.
 //
 // Processing order without a global sort.  "a is processed before b" (world.scm:24-30) is decided
@@ -54,7 +50,7 @@
 // lane is walked in descending pos-param.  Such ties are always list-adjacent.  They are resolved one
 // tick late at no cost: an
 // actor whose list follower holds an equal key is a GHOST (it is not part of the world any more).
-// Every on-road actor reads its leader's key each tick, sees the tie, marks the ghost dead and has
+// Every on-road actor reads its leader's key each tick, sees the tie, flags the ghost (ST_GHOST) and has
 // the lane relinked; whatever the ghost itself did this tick is discarded by k_unlink.
 // Nothing else can observe a ghost: queries reach the follower first and see the same key, and the
 // junction it may stand on is occupied by the follower as well.  Downloads apply the same rule.
