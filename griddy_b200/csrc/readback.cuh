@@ -153,6 +153,25 @@ __device__ __forceinline__ double bezier_1d(double w0, double w1, double w2, dou
   return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w0, a), __dmul_rn(w1, b)), __dmul_rn(w2, c)), __dmul_rn(w3, d));
 }
 
+// (get-pos actor) of the living actor in slot a: st its flags, t its pos-param.
+__device__ __forceinline__ double2 get_pos_xy(const Params& p, const double2* __restrict__ geom, int a, uint32_t st, double t) {
+  const int32_t c = p.cold[a].container;
+  const double2* g = geom + 4 * (int64_t)c;
+  if (!(st & ST_ONROAD) || meta_kind(p.lane[c].meta) == GRIDDY_SEGMENT_LANE) {
+    const double2 o = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? g[2] : g[0];
+    const double2 v = g[1];
+    return make_double2(__dadd_rn(o.x, __dmul_rn(t, v.x)), __dadd_rn(o.y, __dmul_rn(t, v.y)));
+  }
+  // chickadee bezier-curve-point-at (not vendored; the form tests/golden/minischeme.py assumes)
+  const double2 p0 = g[0], p1 = g[1], p2 = g[2], p3 = g[3];
+  const double u = __dsub_rn(1.0, t);
+  const double w0 = __dmul_rn(__dmul_rn(u, u), u);
+  const double w1 = __dmul_rn(__dmul_rn(__dmul_rn(3.0, u), u), t);
+  const double w2 = __dmul_rn(__dmul_rn(__dmul_rn(3.0, u), t), t);
+  const double w3 = __dmul_rn(__dmul_rn(t, t), t);
+  return make_double2(bezier_1d(w0, w1, w2, w3, p0.x, p1.x, p2.x, p3.x), bezier_1d(w0, w1, w2, w3, p0.y, p1.y, p2.y, p3.y));
+}
+
 __global__ void __launch_bounds__(256) k_positions(Params p, int par, const double2* __restrict__ geom,
                                                     const uint8_t* __restrict__ ghost, double2* __restrict__ xy64,
                                                     float2* __restrict__ xy32, int32_t* __restrict__ gid, int n_bound) {
@@ -161,32 +180,150 @@ __global__ void __launch_bounds__(256) k_positions(Params p, int par, const doub
   const bool used = a < p.scal[SC_NSLOTS];
   const uint32_t st = used ? p.hot[a].st : 0u;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  double x = nan, y = nan;
+  double2 xy = make_double2(nan, nan);
   int32_t id = -1;
   if (used && (st & ST_ALIVE) && !ghost[a]) {
-    const int32_t c = p.cold[a].container;
     id = p.cold[a].gid;
-    const double t = p.pos[par][a];
-    const double2* g = geom + 4 * (int64_t)c;
-    if (!(st & ST_ONROAD) || meta_kind(p.lane[c].meta) == GRIDDY_SEGMENT_LANE) {
-      const double2 o = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? g[2] : g[0];
-      const double2 v = g[1];
-      x = __dadd_rn(o.x, __dmul_rn(t, v.x));
-      y = __dadd_rn(o.y, __dmul_rn(t, v.y));
-    } else {   // chickadee bezier-curve-point-at (not vendored; the form tests/golden/minischeme.py assumes)
-      const double2 p0 = g[0], p1 = g[1], p2 = g[2], p3 = g[3];
-      const double u = __dsub_rn(1.0, t);
-      const double w0 = __dmul_rn(__dmul_rn(u, u), u);
-      const double w1 = __dmul_rn(__dmul_rn(__dmul_rn(3.0, u), u), t);
-      const double w2 = __dmul_rn(__dmul_rn(__dmul_rn(3.0, u), t), t);
-      const double w3 = __dmul_rn(__dmul_rn(t, t), t);
-      x = bezier_1d(w0, w1, w2, w3, p0.x, p1.x, p2.x, p3.x);
-      y = bezier_1d(w0, w1, w2, w3, p0.y, p1.y, p2.y, p3.y);
+    xy = get_pos_xy(p, geom, a, st, p.pos[par][a]);
+  }
+  if (xy64) xy64[a] = xy;
+  if (xy32) xy32[a] = make_float2((float)xy.x, (float)xy.y);
+  if (gid) gid[a] = id;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frames for a `draw` loop (griddy_positions_begin / griddy_delta_begin): one kernel per frame, behind the tick.
+// A block takes FRAME_TILE consecutive slots, FRAME_UNROLL per thread, strided so that every load is coalesced.
+// The ghost rule is applied from the leader's side — a living on-road actor whose list follower (Hot::behind)
+// holds an equal key is not part of the world — which needs no pass over the followers and no flag array.
+//
+// FULL frame: float x, y of every slot below n_bound, NaN where the slot holds no living actor.
+// DELTA frame: only the slots whose drawn position differs from the last frame sent.  A position is a function of
+// (container, road side, pos-param): the pos-param is compared with the one last sent (pos_drawn, DRAWN_NONE: the
+// slot showed nothing), a change of container or side is flagged by k_slow in Hot::st (ST_REDRAW, cleared here).
+// So an actor that stands still — waiting in a queue, asleep, idle — costs 16 bytes of HBM reads beyond its hot
+// record and nothing on PCIe.  Output: one mask bit per slot (word j of a block covers its slots 32 j .. 32 j + 31),
+// the changed slots' values packed in slot order per block, blocks in the order they reserved their room
+// (blk_off[block] = first value of the block), and the total count — the last block to finish writes it where the
+// host reads it (mapped pinned memory) and resets the device counters for the next frame.
+// key != 0: the slot numbering changed (a reorder) or this is the first frame: every living slot is sent, every
+// other slot below n_bound is reset to "shows nothing"; the host starts from an all-NaN frame.
+constexpr int FRAME_THREADS = 256, FRAME_UNROLL = 4, FRAME_TILE = FRAME_THREADS * FRAME_UNROLL;
+constexpr unsigned long long DRAWN_NONE = ~0ull;   // a NaN no pos-param ever is (all ones: set with cudaMemset 0xFF)
+
+struct FrameOut {
+  float2* xy32;                 // FULL: by slot
+  unsigned long long* drawn;    // DELTA: by slot, bits of the pos-param last sent, or DRAWN_NONE
+  uint32_t* mask;               //        FRAME_TILE / 32 words per block
+  uint32_t* blk_off;            //        one per block
+  float2* vals;                 //        packed values
+  unsigned int* counter;        //        [0] values handed out, [1] blocks finished
+  unsigned int* host_count;     //        mapped pinned memory: the frame's total
+};
+
+template <bool DELTA>
+__global__ void __launch_bounds__(FRAME_THREADS) k_frame(Params p, int par, const double2* __restrict__ geom, FrameOut o,
+                                                          int n_bound, int key) {
+  __shared__ uint32_t s_cnt[FRAME_TILE / 32];
+  __shared__ uint32_t s_base;
+  __shared__ bool s_last;
+  const int n_used = min(p.scal[SC_NSLOTS], n_bound);
+  const double* __restrict__ pos = p.pos[par];
+  const int4* __restrict__ hot4 = (const int4*)p.hot;
+  const int tile0 = blockIdx.x * FRAME_TILE;
+  const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t st[FRAME_UNROLL];
+  int32_t bh[FRAME_UNROLL];
+  double t[FRAME_UNROLL];
+  unsigned long long drawn[FRAME_UNROLL];
+#pragma unroll
+  for (int k = 0; k < FRAME_UNROLL; ++k) {
+    const int a = tile0 + k * FRAME_THREADS + threadIdx.x;
+    const bool used = a < n_used;
+    const int4 h0 = used ? hot4[2 * (size_t)a] : make_int4(0, -1, -1, -1);   // st, ahead, behind, tj
+    st[k] = (uint32_t)h0.x;
+    bh[k] = h0.z;
+    t[k] = used ? pos[a] : 0.0;
+    drawn[k] = (DELTA && a < n_bound) ? o.drawn[a] : DRAWN_NONE;
+  }
+  bool vis[FRAME_UNROLL], chg[FRAME_UNROLL];
+#pragma unroll
+  for (int k = 0; k < FRAME_UNROLL; ++k) {
+    const int a = tile0 + k * FRAME_THREADS + threadIdx.x;
+    const bool on_road = (st[k] & (ST_ALIVE | ST_ONROAD)) == (ST_ALIVE | ST_ONROAD);
+    const int32_t b = on_road ? bh[k] : -1;
+    const bool ghost = b >= 0 && pos[b] == t[k];   // (the follower is next in slot order: the same or a neighbouring line)
+    vis[k] = (st[k] & ST_ALIVE) && !ghost;
+    if (DELTA) {
+      const unsigned long long now = (unsigned long long)__double_as_longlong(t[k]);
+      chg[k] = key ? vis[k] : (vis[k] ? (now != drawn[k] || (st[k] & ST_REDRAW)) : drawn[k] != DRAWN_NONE);
+      if (st[k] & ST_REDRAW) p.hot[a].st = st[k] & ~ST_REDRAW;   // (between ticks: nobody else touches the word)
+      if (a < n_bound && (key || chg[k])) o.drawn[a] = vis[k] ? now : DRAWN_NONE;
+    } else {
+      chg[k] = a < n_bound;
     }
   }
-  if (xy64) xy64[a] = make_double2(x, y);
-  if (xy32) xy32[a] = make_float2((float)x, (float)y);
-  if (gid) gid[a] = id;
+  const float nanf_ = __int_as_float(0x7fc00000);
+  float2 xy[FRAME_UNROLL];
+#pragma unroll
+  for (int k = 0; k < FRAME_UNROLL; ++k) {
+    const int a = tile0 + k * FRAME_THREADS + threadIdx.x;
+    xy[k] = make_float2(nanf_, nanf_);
+    if (vis[k] && chg[k]) {
+      const double2 v = get_pos_xy(p, geom, a, st[k], t[k]);
+      xy[k] = make_float2((float)v.x, (float)v.y);
+    }
+    if (!DELTA && chg[k]) o.xy32[a] = xy[k];
+  }
+  if constexpr (DELTA) {
+  // pack: rank of a changed slot = the block's room + changed slots before it in the block (slot order)
+  uint32_t ballot[FRAME_UNROLL];
+#pragma unroll
+  for (int k = 0; k < FRAME_UNROLL; ++k) {
+    ballot[k] = __ballot_sync(0xffffffffu, chg[k]);
+    if (lane_id == 0) {
+      const int word = k * (FRAME_THREADS / 32) + warp;
+      s_cnt[word] = __popc(ballot[k]);
+      o.mask[(size_t)blockIdx.x * (FRAME_TILE / 32) + word] = ballot[k];
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of the 32 word counts
+    const uint32_t c = s_cnt[lane_id];
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane_id >= d) incl += up;
+    }
+    s_cnt[lane_id] = incl - c;
+    if (lane_id == 31) {
+      const uint32_t base = incl ? atomicAdd(&o.counter[0], incl) : 0u;
+      s_base = base;
+      o.blk_off[blockIdx.x] = base;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < FRAME_UNROLL; ++k)
+    if (chg[k]) {
+      const int word = k * (FRAME_THREADS / 32) + warp;
+      o.vals[s_base + s_cnt[word] + __popc(ballot[k] & ((1u << lane_id) - 1u))] = xy[k];
+    }
+  // the last block to finish publishes the total and leaves the counters at zero for the next frame
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&o.counter[1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    *o.host_count = atomicExch(&o.counter[0], 0u);
+    o.counter[1] = 0u;
+    __threadfence_system();
+  }
+  }   // DELTA
 }
 
 }  // namespace griddy

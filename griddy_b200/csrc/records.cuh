@@ -15,6 +15,7 @@ constexpr int HOP_ARRIVE = -1;
 constexpr uint32_t ST_EMIG = 1024u;     // multi-GPU: moved onto a lane another rank owns (this slot dies in k_unlink)
 constexpr uint32_t ST_IMMIG = 2048u;    // multi-GPU: arrived from another rank this tick (cleared in k_link)
 constexpr uint32_t ST_GHOST = 4096u;    // found to be a ghost (its follower holds an equal key): k_unlink of this tick removes it
+constexpr uint32_t ST_REDRAW = 8192u;   // container or road side changed since the last delta frame (readback.cuh, k_frame clears it)
 
 constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_JLANE = 4,
               DEV_ERR_NO_LANE = 8, DEV_ERR_NO_ROUTE = 16, DEV_ERR_INTERNAL = 32, DEV_ERR_MIG_OVERFLOW = 64,

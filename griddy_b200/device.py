@@ -30,7 +30,8 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_reorder_now", "griddy_reorders", "griddy_set_route_graph", "griddy_download_routes", "griddy_mg_connect_local", "griddy_mg_step_local",
            "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
            "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
-           "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace", "griddy_state_digest")
+           "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace", "griddy_state_digest",
+           "griddy_delta_frame_bytes", "griddy_delta_begin", "griddy_delta_end", "griddy_delta_apply")
 
 
 class GriddyCudaError(RuntimeError):
@@ -66,6 +67,8 @@ def lib():
         L.griddy_host_alloc.argtypes = [C.c_int64]
         L.griddy_host_free.restype = None
         L.griddy_host_free.argtypes = [C.c_void_p]
+        L.griddy_delta_frame_bytes.restype = C.c_int64
+        L.griddy_delta_frame_bytes.argtypes = [C.c_int64]
         _LIB = L
     return _LIB
 
@@ -249,6 +252,19 @@ class Simulation:
         buf = self._frames.pop(0)
         return buf.array[: n.value]
 
+    def delta_begin(self, buf: "DeltaFrame"):
+        """Start the read-back of a delta frame: the slots whose drawn position changed since the frame before."""
+        self._chk(lib().griddy_delta_begin(self.h, C.c_void_p(buf.ptr), C.c_int64(buf.capacity)))
+        self._frames.append(buf)
+
+    def delta_end(self) -> "DeltaFrame":
+        """Wait for the oldest delta frame begun; returns its buffer (n_slots, n_changed, key, apply())."""
+        ns, nc = C.c_int64(0), C.c_int64(0)
+        self._chk(lib().griddy_delta_end(self.h, C.byref(ns), C.byref(nc)))
+        buf = self._frames.pop(0)
+        buf.n_slots, buf.n_changed = int(ns.value), int(nc.value)
+        return buf
+
     def routes(self):
         """(route_off, route_lane) the world was uploaded with: the caller's, or those find-route computed on the device."""
         n = C.c_int64(0)
@@ -290,6 +306,71 @@ class PinnedFrame:
     def free(self):
         if self.ptr:
             self.array = None
+            lib().griddy_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def decode_delta(raw: np.ndarray):
+    """(slots, xy) of a delta frame held in the uint8 array `raw`: the changed slots, ascending, and their values."""
+    T = DeltaFrame.TILE
+    h = raw[:64].view(np.int64)
+    nb_cap = (int(h[6]) + T - 1) // T
+    blocks = int(h[5])
+    mask_off, off_off = 64, 64 + nb_cap * 128
+    xy_off = (off_off + nb_cap * 4 + 63) // 64 * 64
+    mask = raw[mask_off: mask_off + blocks * 128]
+    first = raw[off_off: off_off + blocks * 4].view(np.uint32).astype(np.int64)
+    vals = raw[xy_off: xy_off + 8 * int(h[2])].view(np.float32).reshape(-1, 2)
+    bits = np.unpackbits(mask, bitorder="little")
+    slots = np.flatnonzero(bits)
+    per_block = bits.reshape(blocks, T).sum(axis=1).astype(np.int64)
+    start = np.cumsum(per_block) - per_block           # changed slots before each block, in slot order
+    blk = slots // T
+    # value index of the k-th changed slot overall = first[its block] + its rank inside the block
+    return slots, vals[first[blk] + (np.arange(len(slots), dtype=np.int64) - start[blk])]
+
+
+class DeltaFrame:
+    """Page-locked host memory for one delta frame over `capacity` slots (include/griddy_cuda.h, "Delta frames")."""
+    TILE = 1024
+
+    def __init__(self, capacity: int):
+        self.capacity = int(capacity)
+        self.bytes = int(lib().griddy_delta_frame_bytes(C.c_int64(self.capacity)))
+        self.ptr = lib().griddy_host_alloc(C.c_int64(self.bytes))
+        if not self.ptr:
+            raise GriddyCudaError(5, "griddy_host_alloc failed")
+        self.raw = np.ctypeslib.as_array((C.c_uint8 * self.bytes).from_address(self.ptr))
+        self.n_slots = self.n_changed = 0
+
+    @property
+    def header(self) -> np.ndarray:
+        return self.raw[:64].view(np.int64)
+
+    @property
+    def key(self) -> bool:
+        return bool(self.header[4])
+
+    @property
+    def bytes_copied(self) -> int:
+        """What griddy_delta_end moved over PCIe for this frame: mask, block table and the changed values."""
+        blocks = (self.n_slots + self.TILE - 1) // self.TILE
+        return blocks * (self.TILE // 32) * 4 + blocks * 4 + 8 * self.n_changed
+
+    def apply(self, xy32: np.ndarray):
+        """Patch the persistent [capacity, 2] float32 array with this frame (griddy_delta_apply)."""
+        assert xy32.dtype == np.float32 and xy32.flags.c_contiguous
+        rc = lib().griddy_delta_apply(C.c_void_p(self.ptr), _p(xy32), C.c_int64(xy32.shape[0]))
+        if rc:
+            raise GriddyCudaError(rc, "griddy_delta_apply: malformed frame or array too small")
+
+    def decode(self):
+        """(slots, xy) of this frame in numpy — an independent restatement of the layout, for tests."""
+        return decode_delta(self.raw)
+
+    def free(self):
+        if self.ptr:
+            self.raw = None
             lib().griddy_host_free(C.c_void_p(self.ptr))
             self.ptr = None
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GRIDDY_ABI_VERSION 5
+#define GRIDDY_ABI_VERSION 6
 
 enum {
   GRIDDY_OK = 0,
@@ -205,6 +205,30 @@ int griddy_download_positions(void* ctx, int64_t capacity, int64_t* n, double* x
  * begun and returns its entry count.  At most two frames are in flight. */
 int griddy_positions_begin(void* ctx, float* xy32, int64_t capacity);
 int griddy_positions_end(void* ctx, int64_t* n);
+/* Delta frames: the same pipeline, but a frame carries only the slots whose drawn position differs from the frame
+ * before — most of a traffic jam, every sleeper and every idle actor stand still — so that a `draw` loop moves a
+ * fraction of the bytes over PCIe.  The caller keeps one persistent array of float x, y per slot (what it draws from,
+ * e.g. a vertex buffer) and patches it with every frame, in order (griddy_delta_apply, or its own loop).
+ *
+ * A frame buffer of griddy_delta_frame_bytes(capacity) bytes (page-locked, griddy_host_alloc) holds, for T = 1024:
+ *   bytes 0-63   int64 x 8: magic, n_slots (slots this frame covers), n_changed, tick, key, blocks = ceil(n_slots / T),
+ *                capacity, 0
+ *   then         uint32 mask[32 * ceil(capacity / T)]: bit l of word j of block b is set when slot b*T + 32*j + l changed
+ *   then         uint32 first[ceil(capacity / T)]: index of block b's first value
+ *   then         (64-byte aligned) float x, y per changed slot: a block's changed slots in ascending slot order, the
+ *                blocks in no particular order (`first` says where each begins).  NaN, NaN: the slot holds no living actor
+ *                any more.
+ * key = 1 (the first frame, and the first after every reorder of the slots — griddy_reorders counts them): slot
+ * numbers mean something new; the frame holds every living actor and the persistent array starts over from all-NaN.
+ * _begin formats the frame on the device behind the ticks run so far and returns at once; _end waits for it, copies
+ * exactly its n_changed values, mask and table into `frame` and returns.  At most two frames are in flight; the caller
+ * runs griddy_step_async for the next ticks in between.  Full frames (griddy_positions_begin, griddy_download_positions)
+ * may be taken in between: they do not change what the delta stream considers sent. */
+int64_t griddy_delta_frame_bytes(int64_t capacity);
+int griddy_delta_begin(void* ctx, void* frame, int64_t capacity);
+int griddy_delta_end(void* ctx, int64_t* n_slots, int64_t* n_changed);
+/* Host only (no context, no GPU): patch xy32 (2 x capacity floats, capacity >= the frame's n_slots) with a frame. */
+int griddy_delta_apply(const void* frame, float* xy32, int64_t capacity);
 void* griddy_host_alloc(int64_t bytes);   /* page-locked host memory; NULL on failure */
 void griddy_host_free(void* ptr);
 

@@ -113,7 +113,7 @@ def test_c_abi_exports_every_declared_symbol():
     L = ctypes.CDLL(device.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.griddy_abi_version() == 5
+    assert L.griddy_abi_version() == 6
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -172,3 +172,176 @@ def test_api_mirror_geometry_matches_the_reference(name, make):
     assert np.array_equal(mirror.kind, net.kind)
     assert np.array_equal(mirror.lane_len, net.lane_len)
     assert np.array_equal(flatten.flatten_geometry(world, idx), np.asarray(fx["network"]["geom"]).reshape(-1, 8))
+
+
+# ---- delta frames (griddy_delta_begin / _end / _apply) -------------------------------------------------------------
+def synthetic_delta_frame(capacity, n_slots, changed_slots, values, key, first_of_block=None):
+    """A frame laid out by hand as include/griddy_cuda.h documents it (T = 1024), in plain host memory."""
+    T = 1024
+    nb_cap, blocks = (capacity + T - 1) // T, (n_slots + T - 1) // T
+    mask_off, off_off = 64, 64 + nb_cap * 128
+    xy_off = (off_off + nb_cap * 4 + 63) // 64 * 64
+    raw = np.zeros(xy_off + nb_cap * T * 8, np.uint8)
+    hdr = raw[:64].view(np.int64)
+    hdr[:] = [0x3156444459524747, n_slots, len(changed_slots), 7, int(key), blocks, capacity, 0]
+    bits = np.zeros(nb_cap * T, np.uint8)
+    bits[changed_slots] = 1
+    raw[mask_off:mask_off + nb_cap * 128] = np.packbits(bits, bitorder="little")
+    per_block = bits.reshape(nb_cap, T).sum(axis=1).astype(np.int64)
+    order = list(range(blocks)) if first_of_block is None else first_of_block   # the order the blocks reserved room in
+    first = np.zeros(nb_cap, np.uint32)
+    at = 0
+    for b in order:
+        first[b] = at
+        at += int(per_block[b])
+    raw[off_off:off_off + nb_cap * 4] = first.view(np.uint8)
+    vals = raw[xy_off:].view(np.float32).reshape(-1, 2)
+    rank_in_block = np.arange(len(changed_slots)) - np.concatenate([[0], np.cumsum(per_block)])[np.asarray(changed_slots) // T]
+    vals[first.astype(np.int64)[np.asarray(changed_slots) // T] + rank_in_block] = values
+    return raw
+
+
+def test_delta_apply_follows_the_documented_layout():
+    import ctypes as C
+    from griddy_b200 import device
+    L = device.lib()
+    rng = np.random.default_rng(3)
+    cap, n_slots = 5000, 4100
+    assert L.griddy_delta_frame_bytes(C.c_int64(cap)) == 64 + 5 * 128 + 64 + 5 * 1024 * 8   # header, mask, table (padded), values
+    slots = np.sort(rng.choice(n_slots, 900, replace=False))
+    vals = rng.standard_normal((900, 2)).astype(np.float32)
+    vals[::7] = np.nan                                   # slots that lost their actor
+    xy = rng.standard_normal((cap, 2)).astype(np.float32)
+    want = xy.copy()
+    want[slots] = vals
+    frame = synthetic_delta_frame(cap, n_slots, slots, vals, key=False, first_of_block=[3, 0, 4, 2, 1])
+    assert L.griddy_delta_apply(frame.ctypes.data_as(C.c_void_p), xy.ctypes.data_as(C.c_void_p), C.c_int64(cap)) == 0
+    assert np.array_equal(xy, want, equal_nan=True)
+    got_slots, got_vals = device.decode_delta(frame)     # the numpy restatement the GPU tests check apply against
+    assert np.array_equal(got_slots, slots) and np.array_equal(got_vals, vals, equal_nan=True)
+    # a key frame starts from all-NaN
+    frame = synthetic_delta_frame(cap, n_slots, slots, vals, key=True)
+    want = np.full((cap, 2), np.nan, np.float32)
+    want[slots] = vals
+    assert L.griddy_delta_apply(frame.ctypes.data_as(C.c_void_p), xy.ctypes.data_as(C.c_void_p), C.c_int64(cap)) == 0
+    assert np.array_equal(xy, want, equal_nan=True)
+    # malformed: wrong magic, an array smaller than the frame, a count that disagrees with the mask
+    bad = frame.copy(); bad[0] ^= 1
+    assert L.griddy_delta_apply(bad.ctypes.data_as(C.c_void_p), xy.ctypes.data_as(C.c_void_p), C.c_int64(cap)) == 1
+    assert L.griddy_delta_apply(frame.ctypes.data_as(C.c_void_p), xy.ctypes.data_as(C.c_void_p), C.c_int64(n_slots - 1)) == 1
+    bad = frame.copy(); bad[:64].view(np.int64)[2] += 1
+    assert L.griddy_delta_apply(bad.ctypes.data_as(C.c_void_p), xy.ctypes.data_as(C.c_void_p), C.c_int64(cap)) == 4
+
+
+def check_delta_stream(sim, bufs, full, strides, label=""):
+    """Steps `sim` by the given strides with two delta frames in flight; after every frame the patched array must
+    equal griddy_download_positions of the same tick, bit for bit.  Returns per-frame (key, n_changed, living)."""
+    want, log = [], []
+
+    def begin(k):
+        sim.delta_begin(bufs[k & 1])
+        want.append(sim.positions(f32=True)[0].copy())
+
+    def end(k):
+        fr = sim.delta_end()
+        slots, vals = fr.decode()                    # the layout, restated in numpy
+        assert len(slots) == fr.n_changed and fr.n_slots == len(want[k])
+        before = full.copy()
+        fr.apply(full)
+        ref = np.full_like(full, np.nan) if fr.key else before
+        ref[slots] = vals
+        assert np.array_equal(full, ref, equal_nan=True), f"{label}frame {k}: apply and decode disagree"
+        assert np.array_equal(full[: fr.n_slots], want[k], equal_nan=True), f"{label}frame {k} (key={fr.key})"
+        assert np.isnan(full[fr.n_slots:]).all()
+        if not fr.key:   # a delta frame holds nothing that did not change
+            same = np.all((before[slots] == vals) | (np.isnan(before[slots]) & np.isnan(vals)), axis=1)
+            assert not same.any(), f"{label}frame {k}: {int(same.sum())} unchanged slots were sent"
+        log.append((fr.key, fr.n_changed, int((~np.isnan(want[k][:, 0])).sum())))
+
+    begin(0)
+    for k, stride in enumerate(strides, start=1):
+        sim.step_async(stride)
+        begin(k)
+        end(k - 1)
+    end(len(strides))
+    sim.step(0)
+    return log
+
+
+@pytest.mark.gpu
+def test_delta_frames_rebuild_every_full_frame():
+    from griddy_b200 import device
+    net, actors = crowded_grid(8, 6000, agenda_len=4, seed=11, max_sleep=10)
+    net.geom = synth.grid_geometry(8)
+    sim = device.Simulation(net, actors, reorder_period=16)
+    bufs = [device.DeltaFrame(actors.n), device.DeltaFrame(actors.n)]
+    full = np.full((actors.n, 2), np.nan, np.float32)
+    sim.step(30)
+    reorders0 = sim.reorders
+    log = check_delta_stream(sim, bufs, full, [1, 1, 1, 2, 1, 3, 1, 1, 5, 1, 1, 1, 7, 1, 1, 1, 1, 2, 1, 1] * 4)
+    keys = [k for k, _, _ in log]
+    assert keys[0] and 2 <= sum(keys) - 1 <= sim.reorders - reorders0, "reorders must show up as key frames"
+    deltas = [(c, n) for k, c, n in log if not k]
+    assert sum(c for c, _ in deltas) < 0.8 * sum(n for _, n in deltas), "delta frames should be sparser than full frames"
+    assert sim.count_alive() < actors.n, "the workload must lose actors to equal keys (slots that turn NaN)"
+    # contract: two frames in flight at most, _end needs a _begin
+    with pytest.raises(device.GriddyCudaError) as e:
+        sim.delta_end()
+    assert e.value.code == 4
+    sim.delta_begin(bufs[0]); sim.delta_begin(bufs[1])
+    with pytest.raises(device.GriddyCudaError) as e:
+        sim.delta_begin(bufs[0])
+    assert e.value.code == 4
+    sim.delta_end(); sim.delta_end()
+    for b in bufs:
+        b.free()
+
+
+@pytest.mark.gpu
+def test_delta_frames_of_a_standing_world_are_empty():
+    """Idle actors and sleepers cost nothing on PCIe: after the key frame, frames of a world in which nobody moves
+    carry no values at all."""
+    from griddy_b200 import device
+    net, actors = crowded_grid(4, 300, agenda_len=0)
+    net.geom = synth.grid_geometry(4)
+    sim = device.Simulation(net, actors)
+    bufs = [device.DeltaFrame(actors.n), device.DeltaFrame(actors.n)]
+    full = np.full((actors.n, 2), np.nan, np.float32)
+    log = check_delta_stream(sim, bufs, full, [1, 1, 4, 1])
+    assert log[0][0] and log[0][1] == log[0][2] == sim.count_alive()
+    assert all(not k and c == 0 for k, c, _ in log[1:])
+    for b in bufs:
+        b.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_delta_frames_on_a_partitioned_world(world):
+    """Every rank streams its own slots: actors that leave for another rank turn NaN, arrivals appear in fresh slots."""
+    from griddy_b200 import device
+    net, actors = crowded_grid(9, 4000, agenda_len=4, seed=21, max_sleep=8)
+    net.geom = synth.grid_geometry(9)
+    owner = synth.grid_owner(net, world, 2)
+    ps = device.PartitionedSimulation(net, actors, owner, world, reorder_period=24)
+    cap = 2 * actors.n
+    bufs = [[device.DeltaFrame(cap), device.DeltaFrame(cap)] for _ in range(world)]
+    full = [np.full((cap, 2), np.nan, np.float32) for _ in range(world)]
+    ps.step(20)
+    arrivals = 0
+    covered = [0] * world
+    for k in range(40):
+        for r, sim in enumerate(ps.ranks):
+            sim.delta_begin(bufs[r][k & 1])
+        want = [sim.positions(f32=True)[0].copy() for sim in ps.ranks]
+        ps.step(1 if k % 5 else 3)
+        for r, sim in enumerate(ps.ranks):
+            fr = sim.delta_end()
+            fr.apply(full[r])
+            assert np.array_equal(full[r][: fr.n_slots], want[r], equal_nan=True), f"rank {r} frame {k} (key={fr.key})"
+            assert np.isnan(full[r][fr.n_slots:]).all()
+            arrivals += int(not fr.key and fr.n_slots > covered[r])
+            covered[r] = fr.n_slots
+    assert arrivals > 0, "actors must have crossed between the ranks (fresh slots between two reorders)"
+    for bb in bufs:
+        for b in bb:
+            b.free()
