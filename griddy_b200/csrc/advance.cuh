@@ -172,6 +172,9 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
   kc[0] = make_int4(k.container, k.hop, k.dest_lane, k.dest_from_j);
   kc[1] = make_int4(k.dest_to_j, k.mv_old, k.inbox_next, k.outbox_next);
   if (p.route_off) p.cold[a].route_cur = rc;
+  l2_keep(&p.hot[a], 1);
+  l2_keep(&p.lane[lane], 2);
+  if (!remote) l2_keep(&p.lane[target], 4);
   return tnext;
 }
 
@@ -450,6 +453,7 @@ __global__ void SLOW_BOUNDS k_slow(Params p, int tick) {
       const double cur = __hiloint2double(ent.w, ent.z);
       if (e < 0) {
         pos_new[a] = turn_onto(p, a, tick, st, cur, pos_old, sink);
+        l2_keep(&pos_new[a], 8);
       } else {
         const bool on_road = st & ST_ONROAD;
         const bool on_route = on_road && ((st >> ST_RS_SHIFT) & 3) == GRIDDY_ROUTE_SOME;

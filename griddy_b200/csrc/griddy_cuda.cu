@@ -207,7 +207,9 @@ struct Ctx {
   uint32_t *d_dmask[2] = {nullptr, nullptr}, *d_doff[2] = {nullptr, nullptr};
   unsigned int* d_dcnt = nullptr;            // [2 frames][2]
   unsigned int* h_dcnt = nullptr;            // [2 frames], page-locked and mapped
-  cudaEvent_t ev_delta[2] = {nullptr, nullptr};
+  cudaEvent_t ev_delta[2] = {nullptr, nullptr}, ev_dcopied[2] = {nullptr, nullptr};
+  uint64_t deltas_flushed = 0;               // frames whose copies have been enqueued
+  int64_t delta_n[2] = {0, 0};
   uint8_t* delta_dst[2] = {nullptr, nullptr};
   int64_t delta_ns[2] = {0, 0}, delta_cap[2] = {0, 0}, delta_tick[2] = {0, 0};
   int delta_key[2] = {0, 0};
@@ -626,6 +628,7 @@ void griddy_destroy(void* ctx) {
     if (c->ev_drawn[f]) cudaEventDestroy(c->ev_drawn[f]);
     if (c->ev_copied[f]) cudaEventDestroy(c->ev_copied[f]);
     if (c->ev_delta[f]) cudaEventDestroy(c->ev_delta[f]);
+    if (c->ev_dcopied[f]) cudaEventDestroy(c->ev_dcopied[f]);
   }
   if (c->h_dcnt) cudaFreeHost(c->h_dcnt);
   if (c->draw_stream) cudaStreamDestroy(c->draw_stream);
@@ -1085,7 +1088,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   c->d_xy_sync = nullptr;
   c->frames_begun = c->frames_ended = 0;
   c->d_drawn = nullptr;
-  c->deltas_begun = c->deltas_ended = 0;
+  c->deltas_begun = c->deltas_ended = c->deltas_flushed = 0;
   c->delta_reorders_seen = -1;
   c->delta_cover = 0;
   Params& p = c->p;
@@ -1439,6 +1442,10 @@ int wait_for_neighbours(Ctx* src) {   // every neighbour's stream waits for what
 
 }  // namespace
 
+namespace {
+int delta_flush(Ctx* c, bool wait);   // drawing read-back, below
+}
+
 int griddy_step(void* ctx, int64_t n_ticks) {
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
@@ -1469,6 +1476,7 @@ int griddy_step_async(void* ctx, int64_t n_ticks) {
   if (c->mg.on && (!c->mg.connected || !c->mg.peers.empty()))
     return fail(c, GRIDDY_ERR_BAD_ARG, "a partitioned world steps with griddy_mg_step_local, or once every neighbour's window is mapped");
   CUDA_TRY(c, cudaSetDevice(c->device));
+  TRY(delta_flush(c, false));   // a delta frame that is formatted by now starts its way to the host before the next ticks are enqueued
   // the scalars an earlier call asked for, if they have landed: slot count and error bits without a wait
   if (c->scal_pending && cudaEventQuery(c->ev_scal) == cudaSuccess) {
     c->scal_pending = false;
@@ -2217,7 +2225,11 @@ int griddy_delta_begin(void* ctx, void* frame, int64_t capacity) {
     }
   }
   if (!c->ev_delta[0])
-    for (int f = 0; f < 2; ++f) CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_delta[f], cudaEventDisableTiming));
+    for (int f = 0; f < 2; ++f) {
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_delta[f], cudaEventDisableTiming));
+      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_dcopied[f], cudaEventDisableTiming));
+    }
+  TRY(delta_flush(c, false));
   if (!c->h_dcnt) CUDA_TRY(c, cudaHostAlloc((void**)&c->h_dcnt, 2 * sizeof(unsigned int), cudaHostAllocMapped));
   if (!c->d_drawn) {
     const DeltaLayout dl(cap);
@@ -2269,35 +2281,56 @@ int griddy_delta_begin(void* ctx, void* frame, int64_t capacity) {
   return GRIDDY_OK;
 }
 
+namespace {
+
+// Start the copies of every frame whose kernel has finished (wait: of every frame begun, waiting for its kernel): the
+// size of a frame is known only then.  Called from griddy_step_async and griddy_delta_begin too, so that in a frame
+// loop the copy of frame t is on its way before the host enqueues tick t+2 — the copy engine never waits for the host.
+int delta_flush(Ctx* c, bool wait) {
+  while (c->deltas_flushed < c->deltas_begun) {
+    const int f = (int)(c->deltas_flushed & 1);
+    if (wait) CUDA_TRY(c, cudaEventSynchronize(c->ev_delta[f]));
+    else if (cudaEventQuery(c->ev_delta[f]) != cudaSuccess) { cudaGetLastError(); return GRIDDY_OK; }
+    const int64_t n = c->delta_ns[f] > 0 ? (int64_t)*(volatile unsigned int*)&c->h_dcnt[f] : 0;
+    const DeltaLayout dl(c->delta_cap[f]);
+    uint8_t* dst = c->delta_dst[f];
+    const int64_t blocks = (c->delta_ns[f] + FRAME_TILE - 1) / FRAME_TILE;
+    if (n > 0) CUDA_TRY(c, cudaMemcpyAsync(dst + dl.xy_off, c->d_dvals[f], (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->draw_stream));
+    if (blocks > 0) {
+      CUDA_TRY(c, cudaMemcpyAsync(dst + dl.mask_off, c->d_dmask[f], (size_t)blocks * (FRAME_TILE / 32) * 4, cudaMemcpyDeviceToHost, c->draw_stream));
+      CUDA_TRY(c, cudaMemcpyAsync(dst + dl.off_off, c->d_doff[f], (size_t)blocks * 4, cudaMemcpyDeviceToHost, c->draw_stream));
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev_dcopied[f], c->draw_stream));
+    int64_t* hdr = (int64_t*)dst;   // (the header is the host's own knowledge: written here, not copied)
+    hdr[0] = DELTA_MAGIC;
+    hdr[1] = c->delta_ns[f];
+    hdr[2] = n;
+    hdr[3] = c->delta_tick[f];
+    hdr[4] = c->delta_key[f];
+    hdr[5] = blocks;
+    hdr[6] = c->delta_cap[f];
+    hdr[7] = 0;
+    c->delta_n[f] = n;
+    ++c->deltas_flushed;
+  }
+  return GRIDDY_OK;
+}
+
+}  // namespace
+
 int griddy_delta_end(void* ctx, int64_t* n_slots, int64_t* n_changed) {
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (c->deltas_begun == c->deltas_ended) return fail(c, GRIDDY_ERR_BAD_STATE, "delta_end without delta_begin");
   const int f = (int)(c->deltas_ended & 1);
   CUDA_TRY(c, cudaSetDevice(c->device));
-  CUDA_TRY(c, cudaEventSynchronize(c->ev_delta[f]));   // the frame is formatted: its size is known
-  const int64_t n = c->delta_ns[f] > 0 ? (int64_t)*(volatile unsigned int*)&c->h_dcnt[f] : 0;
-  const DeltaLayout dl(c->delta_cap[f]);
-  uint8_t* dst = c->delta_dst[f];
-  // (the copies run on their own stream while the compute stream goes on with the next ticks; nothing here waits for those)
-  const int64_t blocks = (c->delta_ns[f] + FRAME_TILE - 1) / FRAME_TILE;
-  if (blocks > 0) {
-    CUDA_TRY(c, cudaMemcpyAsync(dst + dl.mask_off, c->d_dmask[f], (size_t)blocks * (FRAME_TILE / 32) * 4, cudaMemcpyDeviceToHost, c->draw_stream));
-    CUDA_TRY(c, cudaMemcpyAsync(dst + dl.off_off, c->d_doff[f], (size_t)blocks * 4, cudaMemcpyDeviceToHost, c->draw_stream));
+  if (c->deltas_flushed == c->deltas_ended) {   // its copies are not on their way yet: wait for the frame to be formatted
+    CUDA_TRY(c, cudaEventSynchronize(c->ev_delta[f]));
+    TRY(delta_flush(c, false));
   }
-  if (n > 0) CUDA_TRY(c, cudaMemcpyAsync(dst + dl.xy_off, c->d_dvals[f], (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->draw_stream));
-  int64_t* hdr = (int64_t*)dst;
-  hdr[0] = DELTA_MAGIC;
-  hdr[1] = c->delta_ns[f];
-  hdr[2] = n;
-  hdr[3] = c->delta_tick[f];
-  hdr[4] = c->delta_key[f];
-  hdr[5] = (c->delta_ns[f] + FRAME_TILE - 1) / FRAME_TILE;
-  hdr[6] = c->delta_cap[f];
-  hdr[7] = 0;
-  CUDA_TRY(c, cudaStreamSynchronize(c->draw_stream));
+  CUDA_TRY(c, cudaEventSynchronize(c->ev_dcopied[f]));
   if (n_slots) *n_slots = c->delta_ns[f];
-  if (n_changed) *n_changed = n;
+  if (n_changed) *n_changed = c->delta_n[f];
   ++c->deltas_ended;
   return GRIDDY_OK;
 }

@@ -47,6 +47,18 @@ enum { TR_ADVANCE, TR_SLOW, TR_UNLINK, TR_LINK, TR_HALO_PACK, TR_HALO_UNPACK, TR
 #define TRACE(p, tick, slot) do { } while (0)
 #endif
 
+// L2 residency of the lines a lane change touches in all three mover kernels: k_slow raises the eviction priority
+// of the mover's hot record (bit 0 of GRIDDY_L2_KEEP), its old lane's record (bit 1), its new lane's record (bit 2)
+// and its new pos-param (bit 3), so that k_unlink / k_link find them in L2 although 300 MB of other traffic passes in
+// between.  Measured in profiles/r2/variants.md; more lines than these, or giving the priority back at the last use
+// (applypriority), made the tick slower.
+#ifndef GRIDDY_L2_KEEP
+#define GRIDDY_L2_KEEP 5
+#endif
+__device__ __forceinline__ void l2_keep(const void* ptr, int bit) {
+  if (GRIDDY_L2_KEEP & bit) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ptr));
+}
+
 __device__ __forceinline__ void grid_dependency_wait() {
 #if GRIDDY_PDL
   asm volatile("griddepcontrol.wait;" ::: "memory");

