@@ -72,25 +72,43 @@ __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_
   return HEAD_TRAVEL;
 }
 
-// Lanes whose list must be rebuilt this tick are collected per block in shared memory and flushed to
-// Params::touched with one global atomic per block (a same-address atomic per lane would serialise).
-// Whether a lane is on a list already is kept in its own record (LaneRec::meta): the first leaver / ghost
-// finder / entrant of the tick lists it, and the counts tell k_unlink / k_link whether the list has one
-// element — then they never read the chain through the cold records.
+// Work lists of the order maintenance, collected per block in shared memory and flushed with one global atomic per
+// block (a same-address atomic per entry would serialise):
+//   leavers  one record per actor that leaves its lane's list this tick — it changed lane, went off the road, jumped
+//            back on its lane, or was found to be a ghost: {slot, the lane it leaves, that lane's junction if it is a
+//            junction lane (else -1), 0}.  k_unlink takes them out, one thread per record.
+//   entered  lanes that gained an actor: whether a lane is listed already is kept in its own record (LaneRec::meta
+//            counts the entrants), so k_link has one thread per lane and never reads the chain through the cold
+//            records when there is one entrant.
 struct TouchSink {
-  int32_t *left, *n_left;         // shared: lanes that lost an actor or hold a ghost (k_unlink), SLOW_THREADS entries
-  int32_t *entered, *n_entered;   // shared: lanes that gained an actor (k_link), SLOW_THREADS entries
+  int4* left;                     // shared: leaver records, LEAVER_STAGE entries; beyond that they go straight to the global list
+  int32_t* n_left;
+  int32_t *entered, *n_entered;   // shared: lanes that gained an actor, SLOW_THREADS entries
 };
 #ifdef SLOW_MIN_BLOCKS
 #define SLOW_BOUNDS __launch_bounds__(SLOW_THREADS, SLOW_MIN_BLOCKS)
 #else
 #define SLOW_BOUNDS __launch_bounds__(SLOW_THREADS)
 #endif
-constexpr int SLOW_THREADS = 128;   // an actor leaves at most one lane (its own, ghost or not) and enters at most one
+constexpr int SLOW_THREADS = 128;   // an actor enters at most one lane
+constexpr int LEAVER_STAGE = 2 * SLOW_THREADS;   // an actor leaves at most one lane; a follower may find a chain of ghosts
 
-__device__ __forceinline__ void mark_ghost_found(const Params& p, int32_t lane, const TouchSink& sink) {
-  if (!(atomicOr(&p.lane[lane].meta, META_GHOST) & META_LEFT)) sink.left[atomicAdd(sink.n_left, 1)] = lane;
+__device__ __forceinline__ void push_leaver(const Params& p, int tick, int32_t z, int32_t lane, int32_t junction, const TouchSink& sink) {
+  const int4 rec = make_int4(z, lane, junction, 0);
+  const int32_t at = atomicAdd(sink.n_left, 1);
+  if (at < LEAVER_STAGE) sink.left[at] = rec;
+  else p.leavers[atomicAdd(&p.counters[CNT_STRIDE * (tick & 1) + CNT_LEFT], 1)] = rec;
 }
+
+// The junction whose occupancy counts the actors of `lane` (route.scm:98-104), or -1 if it is not a junction lane.
+__device__ __forceinline__ int32_t junction_of_lane(const Params& p, int32_t lane) {
+  const LaneRec& r = p.lane[lane];
+  return meta_kind(r.meta) == GRIDDY_JUNCTION_LANE ? r.link2 : -1;
+}
+// An actor that stands on a junction lane has no gated route head (a junction lane leads onto a segment lane), so its
+// Hot::tj is free to remember the junction it occupies: -2 - junction.  A lane change then needs nothing of the lane
+// it leaves — not even its record.
+__device__ __forceinline__ int32_t occupied_junction(int32_t tj) { return tj <= -2 ? -2 - tj : -1; }
 
 // Returns the lane's previous inbox head (the caller stores it as the entrant's inbox_next).
 __device__ __forceinline__ int32_t enter_lane(const Params& p, int a, int32_t lane, const TouchSink& sink) {
@@ -101,20 +119,11 @@ __device__ __forceinline__ int32_t enter_lane(const Params& p, int a, int32_t la
   return prev;
 }
 
-// Returns the lane's previous outbox head (the caller stores it as the leaver's outbox_next).
-__device__ __forceinline__ int32_t leave_lane(const Params& p, int a, int32_t lane, const TouchSink& sink) {
-  const int32_t prev = atomicExch(&p.lane[lane].outbox, a);
-  const uint32_t old = atomicAdd(&p.lane[lane].meta, META_OUT_ONE);
-  if (!(old & META_LEFT)) sink.left[atomicAdd(sink.n_left, 1)] = lane;
-  else if ((old & META_OUT) == META_OUT) dev_error(p, DEV_ERR_LANE_BURST);
-  return prev;
-}
-
 // ------------------------------------------------------------------------------------------------
 // route-step/turn-onto$ (route.scm:92-135) for an actor that reaches the end of its lane and is not
 // held by a full junction: carry the rest of the tick over into the target lane, pop the route.
-// Touches six 64-byte lines: the actor's cold record, its hot record, its new pos-param, the target lane's
-// record, the old lane's record and the pos-param of the target lane's rearmost actor.  Returns the new pos-param.
+// Touches five 64-byte lines: the actor's cold record, its hot record, its new pos-param, the target lane's
+// record and the pos-param of the target lane's rearmost actor.  Returns the new pos-param.
 __device__ void emigrate(const Params& p, int a, int tick, uint32_t st, const Cold& k, int32_t tj, double pos_old,
                          double pos_new, double delta, double buf);   // multi_gpu.cuh
 __device__ void emig_publish(const Params& p, int tick);
@@ -123,6 +132,7 @@ __device__ __forceinline__ void halo_pack_block(const Params& p, int tick, int n
 __device__ __forceinline__ double turn_onto(const Params& p, const int a, const int tick, const uint32_t st,
                                             const double cur, const double* __restrict__ pos_old, const TouchSink& sink) {
   Cold k = p.cold[a];
+  const int32_t tj_old = p.hot[a].tj;
   const int32_t target = k.hop, lane = k.container;
   const LaneRec it = p.lane[target];
   const double time_spent = __ddiv_rn(__dsub_rn(1.0, cur), k.speed);
@@ -146,8 +156,9 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
   const int32_t nhop = route_head_on(p, target, it, k, k.agenda_cur, &rc);
   // (ahead / behind stay: k_unlink reads them.  atomicOr: a follower may be flagging this actor as a ghost right now)
   const uint32_t more = ST_MOVED | ST_REDRAW | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
-  atomicOr(&p.hot[a].st, more | (remote ? ST_EMIG : 0u));
-  const int32_t tjn = junction_after(p, it, nhop);
+  const uint32_t st_before = atomicOr(&p.hot[a].st, more | (remote ? ST_EMIG : 0u));
+  int32_t tjn = junction_after(p, it, nhop);
+  if (meta_kind(it.meta) == GRIDDY_JUNCTION_LANE) tjn = -2 - it.link2;   // (no gated head on a junction lane: see occupied_junction)
   const double delta = __dmul_rn(k.speed_dt, tinv);
   p.hot[a].tj = tjn;
   p.hot[a].delta = delta;
@@ -167,13 +178,13 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
   } else {
     k.inbox_next = enter_lane(p, a, target, sink);
   }
-  k.outbox_next = leave_lane(p, a, lane, sink);
+  // (a follower that found this actor to be a ghost before the atomicOr above has listed it already)
+  if (!(st_before & ST_GHOST)) push_leaver(p, tick, a, lane, occupied_junction(tj_old), sink);
   int4* kc = (int4*)&p.cold[a];   // the first sector, in two stores
   kc[0] = make_int4(k.container, k.hop, k.dest_lane, k.dest_from_j);
   kc[1] = make_int4(k.dest_to_j, k.mv_old, k.inbox_next, k.outbox_next);
   if (p.route_off) p.cold[a].route_cur = rc;
   l2_keep(&p.hot[a], 1);
-  l2_keep(&p.lane[lane], 2);
   if (!remote) l2_keep(&p.lane[target], 4);
   return tnext;
 }
@@ -193,13 +204,13 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   // ghosts: leaders that this actor replaced with an equal key at the end of the previous tick
   if (ah >= 0 && lead == cur) {
     const int32_t lane = p.cold[a].container;
+    const int32_t junction = junction_of_lane(p, lane);
     do {
-      if (!(atomicOr(&p.hot[ah].st, ST_GHOST) & ST_GHOST))   // the first to notice hands it to k_unlink
-        p.cold[ah].ghost_next = atomicExch(&p.lane[lane].ghosts, ah);
+      // the first to notice hands it to k_unlink — unless the ghost changed lane itself this tick and is listed already
+      if (!(atomicOr(&p.hot[ah].st, ST_GHOST) & (ST_GHOST | ST_MOVED))) push_leaver(p, tick, ah, lane, junction, sink);
       ah = p.hot[ah].ahead;
       if (ah >= 0) lead = pos_old[ah];
     } while (ah >= 0 && lead == cur);
-    mark_ghost_found(p, lane, sink);
   }
 
   if (rs == GRIDDY_ROUTE_SOME && head == HEAD_TRAVEL) {   // advance-on-route$  route.scm:137-141
@@ -212,11 +223,11 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
       const bool back = target < cur;
       // (atomicAnd / atomicOr: a follower may be flagging this actor as a ghost right now)
       atomicAnd(&p.hot[a].st, ~((3u << ST_RS_SHIFT) | ST_ARRIVE));
-      atomicOr(&p.hot[a].st, (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u));
-      if (back) {   // jumped back past other residents: re-insert by key
+      const uint32_t st_before = atomicOr(&p.hot[a].st, (GRIDDY_ROUTE_DONE << ST_RS_SHIFT) | (back ? ST_MOVED : 0u));
+      if (back) {   // jumped back past other residents: re-insert by key (the lane's occupancy does not change)
         const int32_t lane = p.cold[a].container;
         p.cold[a].mv_old = lane;
-        p.cold[a].outbox_next = leave_lane(p, a, lane, sink);
+        if (!(st_before & ST_GHOST)) push_leaver(p, tick, a, lane, -1, sink);
         p.cold[a].inbox_next = enter_lane(p, a, lane, sink);
       }
       return target;
@@ -305,8 +316,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
   const uint32_t clear = (3u << ST_RS_SHIFT) | (3u << ST_HEAD_SHIFT) | ST_ONROAD | ST_SIDE | ST_CLASS_P | ST_ARRIVE;
   const uint32_t set = (h << ST_HEAD_SHIFT) | (dir ? ST_SIDE : 0u) | (lane > seg ? ST_CLASS_P : 0u) | ST_MOVED | ST_REDRAW;
   atomicAnd(&p.hot[a].st, ~clear);   // (a follower may be flagging this actor as a ghost right now)
-  atomicOr(&p.hot[a].st, set);
-  p.cold[a].outbox_next = leave_lane(p, a, lane, sink);
+  if (!(atomicOr(&p.hot[a].st, set) & ST_GHOST)) push_leaver(p, tick, a, lane, -1, sink);   // (a segment lane: no junction)
   return dir ? __dsub_rn(1.0, cur) : cur;   // on-road->off-road  location.scm:41-47
 }
 
@@ -430,7 +440,8 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks) {
 // k_slow: the full advance$ for the actors k_advance deferred, one thread per actor, so that the
 // chains of dependent gathers of 32 such actors overlap instead of stalling 31 idle lanes.
 __global__ void SLOW_BOUNDS k_slow(Params p, int tick) {
-  __shared__ int32_t s_left[SLOW_THREADS], s_entered[SLOW_THREADS];
+  __shared__ int4 s_left[LEAVER_STAGE];
+  __shared__ int32_t s_entered[SLOW_THREADS];
   __shared__ int32_t s_nl, s_ne, s_base_l, s_base_e;
   grid_dependency_wait();
   TRACE(p, tick, TR_SLOW);
@@ -464,12 +475,12 @@ __global__ void SLOW_BOUNDS k_slow(Params p, int tick) {
       }
     }
     __syncthreads();
-    const int nl = s_nl, ne = s_ne;
+    const int nl = min(s_nl, LEAVER_STAGE), ne = s_ne;
     if (threadIdx.x == 0 && nl) s_base_l = atomicAdd(&counters[CNT_LEFT], nl);
     if (threadIdx.x == 1 && ne) s_base_e = atomicAdd(&counters[CNT_ENTERED], ne);
     __syncthreads();
-    if (threadIdx.x < nl) p.touched[s_base_l + threadIdx.x] = s_left[threadIdx.x];
-    if (threadIdx.x < ne) p.touched[p.cap + s_base_e + threadIdx.x] = s_entered[threadIdx.x];
+    for (int k = threadIdx.x; k < nl; k += SLOW_THREADS) p.leavers[s_base_l + k] = s_left[k];
+    if (threadIdx.x < ne) p.touched[s_base_e + threadIdx.x] = s_entered[threadIdx.x];
   }
   if (p.owner) emig_publish(p, tick);   // partitioned world: the block that finishes last raises the migrant flags
 }

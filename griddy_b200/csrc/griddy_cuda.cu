@@ -1187,7 +1187,8 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   p.cold = c->cold_cur;
   p.coldf = c->coldf_cur;
 
-  TRY(dev_alloc(c, pool, &p.touched, 2 * cap));
+  TRY(dev_alloc(c, pool, &p.touched, cap));
+  TRY(dev_alloc(c, pool, &p.leavers, cap));
   TRY(dev_alloc(c, pool, &p.slow, cap));
   TRY(dev_alloc(c, pool, &p.counters, 2 * CNT_STRIDE));
   TRY(dev_alloc(c, pool, &p.scal, SC_COUNT));

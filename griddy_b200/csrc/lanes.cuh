@@ -42,71 +42,60 @@ __device__ int later_processed(const Params& p, int x, int y, int32_t lane, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_unlink: one thread per lane that an actor left this tick; k_link: one per lane that an actor entered.  Lanes are doubly
-// linked lists in ascending pos-param, so nothing walks a whole lane.
-//   k_unlink  takes the lane's leavers (its outbox) and the ghosts found on it this tick out of the
-//             list in O(1) each, and settles the actors that are done for this tick: a ghost's move is
-//             void, an emigrant lives on another rank from now on, an actor that left the road has no
-//             lane to enter.
-//   k_link    (after every lane has been unlinked, so a mover's pointers are free to overwrite)
-//             inserts the lane's entrants (its inbox, sorted) by walking up from the rear — entrants
-//             land near pos 0, so that is a step or two — and writes their final pointers.
-// The usual case — one leaver at the front, one entrant at the rear — touches the lane's record and the hot
-// records of the mover and of its neighbour, nothing else: LaneRec::meta says how many leavers / entrants were
-// pushed, so the chains through the cold records are followed only when there are several.
+// k_unlink: one thread per actor that leaves its lane's list this tick; k_link: one per lane that an actor entered.
+// Lanes are doubly linked lists in ascending pos-param, so nothing walks a whole lane.
+//   k_unlink  takes every leaver (k_slow's records: actors that changed lane, went off the road or jumped back, and
+//             ghosts) out of its list and settles the actors that are done for this tick: a ghost's move is void, an
+//             emigrant lives on another rank from now on, an actor that left the road has no lane to enter.  No
+//             per-lane state is involved: the leavers of a lane form RUNS of list neighbours (nearly always of one),
+//             a leaver's own pointers stay as they were, and the foremost leaver of a run — the one whose leader
+//             stays — walks back over the run and joins the two residents around it.  Two runs never write the
+//             same word: they are separated by a resident, of which one run writes `ahead` and the other `behind`.
+//   k_link    (after every leaver is out, so a mover's pointers are free to overwrite) inserts the lane's entrants
+//             (its inbox, sorted) by walking up from the rear — entrants land near pos 0, so that is a step or
+//             two — and writes their final pointers.
+// The usual lane change — the front actor leaves, lands at the rear of the next lane — touches the hot records of the
+// mover and of its two new / old neighbours and the new lane's record; LaneRec::meta says how many entrants were
+// pushed, so the chain through the cold records is followed only when there are several.
 // Residents keep their relative order (a follower is clamped behind its leader, route.scm:68-74).
 // Equal keys: an entrant that lands on a resident's or another entrant's key is resolved in k_link,
 // the later-processed one stays (core.scm:173-178); two residents that round to the same key are left
 // linked and resolved next tick through the ghost rule (file header) — on every lane, touched or not.
-// Junction occupancy (route.scm:98-104) changes by whole lanes: one atomic per lane and kernel.
-constexpr int32_t UNLINKED = -3;
+// Junction occupancy (route.scm:98-104): one atomic per leaver of a junction lane, one per lane that gained actors.
+
+// Is the actor with these flags leaving its lane's list this tick (or gone already)?  Every linked actor is alive and on
+// the road; k_slow marks movers and ghosts, and what k_unlink itself clears (below) leaves one of the other marks.
+__device__ __forceinline__ bool is_leaver(uint32_t st) {
+  return (st & (ST_MOVED | ST_GHOST)) || (st & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD);
+}
 
 __global__ void __launch_bounds__(128) k_unlink(Params p, int tick) {
   grid_dependency_wait();
   TRACE(p, tick, TR_UNLINK);
   const int par = tick & 1;
-  const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_LEFT];
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
-    const int32_t lane = p.touched[i];
-    LaneRec* lr = &p.lane[lane];
-    const uint32_t meta = lr->meta;
-    const int4 heads = *(const int4*)&lr->tail;   // tail, inbox, outbox, ghosts
-    const int32_t outbox = heads.z, ghosts = heads.w;
-    const int n_out = (int)((meta & META_OUT) >> 4);
-    atomicAnd(&lr->meta, ~META_LEFT);
-    if (outbox >= 0) lr->outbox = -1;
-    if (ghosts >= 0) lr->ghosts = -1;
-    int32_t tail = heads.x, gone = 0, died = 0;
-    // A ghost that also moved is on both lists; the second visit finds it UNLINKED.
-    auto unlink = [&](int32_t z, int32_t f, int32_t b) {
-      if (f == UNLINKED) return false;
-      if (b >= 0) p.hot[b].ahead = f; else tail = f;
-      if (f >= 0) p.hot[f].behind = b;
-      p.hot[z].ahead = UNLINKED;
-      return true;
-    };
-    for (int32_t z = outbox, k = 0; z >= 0; ++k) {
-      const int4 h = *(const int4*)&p.hot[z];   // st, ahead, behind, tj
-      unlink(z, h.y, h.z);
-      ++gone;   // every mover leaves its old lane, whatever becomes of it
-      const uint32_t sz = (uint32_t)h.x;
-      if (sz & (ST_GHOST | ST_EMIG)) { p.hot[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG); ++died; }
-      else if (!(sz & ST_ONROAD)) p.hot[z].st = sz & ~ST_MOVED;   // went off the road: nothing to link
-      z = k + 1 < n_out ? p.cold[z].outbox_next : -1;   // (the usual single leaver: its cold record is not read)
-    }
-    for (int32_t z = ghosts; z >= 0;) {
-      const int4 h = *(const int4*)&p.hot[z];
-      const uint32_t sz = (uint32_t)h.x;
-      if (unlink(z, h.y, h.z) && !(sz & ST_MOVED)) {   // (one that also moved was settled above)
-        p.hot[z].st = sz & ~ST_ALIVE;
-        ++gone;
-        ++died;
+  const int32_t n_leavers = p.counters[CNT_STRIDE * par + CNT_LEFT];
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_leavers; i += gridDim.x * blockDim.x) {
+    const int4 rec = p.leavers[i];            // slot, lane, junction
+    const int32_t z = rec.x;
+    const int4 h = *(const int4*)&p.hot[z];   // st, ahead, behind, tj: the pointers are the old world's
+    const uint32_t sz = (uint32_t)h.x;
+    const int32_t f = h.y;
+    if (!(f >= 0 && is_leaver(p.hot[f].st))) {   // the foremost of its run
+      int32_t b = h.z;
+      while (b >= 0) {
+        const int4 hb = *(const int4*)&p.hot[b];
+        if (!is_leaver((uint32_t)hb.x)) break;
+        b = hb.z;
       }
-      z = p.cold[z].ghost_next;
+      if (b >= 0) p.hot[b].ahead = f; else p.lane[rec.y].tail = f;
+      if (f >= 0) p.hot[f].behind = b;
     }
-    if (tail != heads.x) lr->tail = tail;
-    if (gone && meta_kind(meta) == GRIDDY_JUNCTION_LANE) atomicSub(&p.occ[lr->link2], gone);
-    if (died) atomicAdd(&p.scal[SC_NDEAD], died);   // dead slots pile up until the next reorder drops them
+    // every mover leaves its old lane, whatever becomes of it
+    bool died = false;
+    if (sz & (ST_GHOST | ST_EMIG)) { p.hot[z].st = sz & ~(ST_MOVED | ST_ALIVE | ST_EMIG); died = true; }
+    else if (!(sz & ST_ONROAD)) p.hot[z].st = sz & ~ST_MOVED;   // went off the road: nothing to link
+    if (rec.z >= 0) atomicSub(&p.occ[rec.z], 1);
+    if (died) atomicAdd(&p.scal[SC_NDEAD], 1);   // dead slots pile up until the next reorder drops them
   }
 }
 
@@ -120,7 +109,7 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
   const int32_t n_touched = p.counters[CNT_STRIDE * par + CNT_ENTERED];
   const double* __restrict__ pos_old = p.pos[par];
   const double* __restrict__ pos_new = p.pos[par ^ 1];
-  const int32_t* __restrict__ entered = p.touched + p.cap;
+  const int32_t* __restrict__ entered = p.touched;
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = entered[i];
     LaneRec* lr = &p.lane[lane];

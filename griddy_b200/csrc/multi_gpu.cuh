@@ -133,7 +133,7 @@ __device__ void emigrate(const Params& p, int a, int tick, uint32_t st, const Co
   r.container = k.container;
   r.mv_old = k.mv_old;
   r.hop = k.hop;
-  r.tj = tj >= 0 ? (tj & ~TJ_REMOTE) : -1;
+  r.tj = tj >= 0 ? (tj & ~TJ_REMOTE) : tj;   // (negative: none, or the junction of the junction lane it now stands on)
   r.popped = k.agenda_cur - f.agenda_beg;
   r.land_tick = f.land_tick;
   r.land_lane = f.land_lane;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
     k.inbox_next = atomicExch(&lr->inbox, a);
     p.cold[a] = k;
     const uint32_t old = atomicAdd(&lr->meta, META_IN_ONE);
-    if (!(old & META_IN)) p.touched[p.cap + atomicAdd(&p.counters[CNT_STRIDE * par + CNT_ENTERED], 1)] = r.container;
+    if (!(old & META_IN)) p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_ENTERED], 1)] = r.container;
     else if ((old & META_IN) == META_IN) dev_error(p, DEV_ERR_LANE_BURST);
   }
 }

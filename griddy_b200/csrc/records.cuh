@@ -22,7 +22,7 @@ constexpr int DEV_ERR_BEGIN_ON_ROAD = 1, DEV_ERR_NO_CLAUSE = 2, DEV_ERR_END_ON_J
               DEV_ERR_MIG_AGENDA = 128, DEV_ERR_MIG_TIMEOUT = 256, DEV_ERR_LANE_BURST = 512;
 
 // Params::counters[parity][...]
-constexpr int CNT_EMIG = 0, CNT_LEFT = 1, CNT_SLOW = 2, CNT_ENTERED = 3, CNT_STRIDE = 4;
+constexpr int CNT_EMIG = 0, CNT_LEFT = 1 /* leaver records */, CNT_SLOW = 2, CNT_ENTERED = 3 /* lanes */, CNT_STRIDE = 4;
 
 // Programmatic dependent launch (sm_90+): the four kernels of a tick are launched with
 // programmaticStreamSerializationAllowed, so the blocks of the next one become resident while the last
@@ -75,8 +75,8 @@ struct __align__(16) Hot {
   uint32_t st;       // ST_* flags
   int32_t ahead;     // slot of the next actor ahead on the lane (ascending pos-param), -1 at the front
   int32_t behind;    // slot of the next actor behind, -1 at the rear
-  int32_t tj;        // on a route: junction of the lane the route head turns onto (-1: none; TJ_REMOTE tag);
-                     // asleep (no route): the remaining (sleep-for t) time
+  int32_t tj;        // on a route: junction of the lane the route head turns onto (-1: none; TJ_REMOTE tag), or, on a
+                     // junction lane, -2 - the junction it occupies; asleep (no route): the remaining (sleep-for t) time
   double delta, buf; // fl(speed*dt)*fl(1/len) and 10/len on the current lane (route.scm:62-66), cached at lane entry
 };
 static_assert(sizeof(Hot) == 32, "one sector per slot");
@@ -90,11 +90,11 @@ struct __align__(16) Cold {
   int32_t hop;                        // head of the route: lane of (turn-onto lane), or -1 for (arrive-at _)
   int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions
   int32_t mv_old;                     // where a mover came from: lane, or ~segment
-  int32_t inbox_next, outbox_next;    // this tick's entrants / leavers of a lane, chained
+  int32_t inbox_next, outbox_next;    // this tick's entrants of a lane, chained (outbox_next: unused)
   // second sector
   double speed, speed_dt;             // max-speed and fl(max-speed * dt)
   int32_t agenda_cur, route_cur;      // agenda head (index into the item pool), route head (explicit routes)
-  int32_t ghost_next;                 // ghosts found on a lane this tick, chained
+  int32_t ghost_next;                 // (unused)
   int32_t gid;                        // the actor's id (global id on a partitioned world)
 };
 // The rest of an actor's rarely read state.
@@ -114,11 +114,10 @@ struct __align__(16) LaneRec {
   int32_t link;           // segment lane: its segment; junction lane: the lane it leads onto; segment: outer forw-side lane
   int32_t link2;          // junction lane: its junction; segment: outer back-side lane
   int32_t to_j;           // grid routing: junction a segment lane reaches
-  uint32_t meta;          // kind (bits 0-2), direction (bit 3); this tick's work marks: leavers pushed (bits 4-14),
-                          // ghost found (bit 15), entrants pushed (bits 16-31) — reset by k_unlink / k_link
+  uint32_t meta;          // kind (bits 0-2), direction (bit 3); entrants pushed this tick (bits 16-31, reset by k_link)
   int32_t pad[2];
   int32_t tail;           // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
-  int32_t inbox, outbox, ghosts;   // this tick's entrants, leavers and ghosts (chained through Cold)
+  int32_t inbox, outbox, ghosts;   // this tick's entrants (chained through Cold); outbox, ghosts: unused
   int32_t turn[4];        // grid routing: junction lane leading onto the segment that leaves this lane's end with heading h
 };
 static_assert(sizeof(LaneRec) == 64, "one line per item");
@@ -162,9 +161,8 @@ struct Params {
   const int64_t* route_off;   // null: grid routing table
   const int32_t* route_lane;
   // per-tick scratch, by slot
-  // lanes an actor left (or a ghost was found on) / entered this tick: [0, cap) and [cap, 2 cap).  Two
-  // lists, so that k_unlink and k_link each fetch only the lane records they have work on.
-  int32_t* touched;
+  int32_t* touched;   // lanes an actor entered this tick (k_link's work list)
+  int4* leavers;      // actors that leave their lane's list this tick: {slot, lane, junction or -1, 0} (k_unlink's work list)
   int4* slow;   // deferred actors: {slot (~slot: turn-onto), st, pos-param lo, hi} as k_advance read them
   int32_t* counters;   // [2 parities][CNT_STRIDE]: emigrants, lanes left, deferred actors, lanes entered
   double dt, two_size;
