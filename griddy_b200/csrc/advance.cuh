@@ -110,8 +110,9 @@ __device__ __forceinline__ int32_t junction_of_lane(const Params& p, int32_t lan
 // it leaves — not even its record.
 __device__ __forceinline__ int32_t occupied_junction(int32_t tj) { return tj <= -2 ? -2 - tj : -1; }
 
-// Returns the lane's previous inbox head (the caller stores it as the entrant's inbox_next).
-__device__ __forceinline__ int32_t enter_lane(const Params& p, int a, int32_t lane, const TouchSink& sink) {
+// Returns the lane's previous inbox head (the caller stores it as the entrant's inbox_next).  `pos`: where it lands.
+__device__ __forceinline__ int32_t enter_lane(const Params& p, int a, int32_t lane, double pos, const TouchSink& sink) {
+  p.lane[lane].e_pos = pos;   // (several entrants overwrite each other: k_link then takes every one's own)
   const int32_t prev = atomicExch(&p.lane[lane].inbox, a);
   const uint32_t old = atomicAdd(&p.lane[lane].meta, META_IN_ONE);
   if (!(old & META_IN)) sink.entered[atomicAdd(sink.n_entered, 1)] = lane;
@@ -176,7 +177,7 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
       emigrate(p, a, tick, st | more, k, tjn, cur, tnext, delta, tbuf);
     }
   } else {
-    k.inbox_next = enter_lane(p, a, target, sink);
+    k.inbox_next = enter_lane(p, a, target, tnext, sink);
   }
   // (a follower that found this actor to be a ghost before the atomicOr above has listed it already)
   if (!(st_before & ST_GHOST)) push_leaver(p, tick, a, lane, occupied_junction(tj_old), sink);
@@ -228,7 +229,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
         const int32_t lane = p.cold[a].container;
         p.cold[a].mv_old = lane;
         if (!(st_before & ST_GHOST)) push_leaver(p, tick, a, lane, -1, sink);
-        p.cold[a].inbox_next = enter_lane(p, a, lane, sink);
+        p.cold[a].inbox_next = enter_lane(p, a, lane, target, sink);
       }
       return target;
     }
@@ -291,7 +292,7 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     k.container = init_lane;
     k.mv_old = ~seg;
     k.route_cur = rc;
-    k.inbox_next = enter_lane(p, a, init_lane, sink);
+    k.inbox_next = enter_lane(p, a, init_lane, init_pos, sink);
     p.cold[a] = k;
     return init_pos;
   }

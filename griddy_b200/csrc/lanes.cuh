@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = entered[i];
     LaneRec* lr = &p.lane[lane];
-    const uint32_t meta = lr->meta;
+    const int4 first = *(const int4*)&lr->to_j;   // to_j, meta, e_pos
+    const uint32_t meta = (uint32_t)first.y;
+    const double lone_pos = __hiloint2double(first.w, first.z);
     const int4 heads = *(const int4*)&lr->tail;   // tail, inbox, outbox, ghosts
     const int32_t inbox = heads.y;
     const bool single = (meta & META_IN) == META_IN_ONE;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
       double best_pos = 0.0;
       for (int32_t y = inbox; y >= 0; y = next_in(y)) {
         if (!(p.hot[y].st & ST_MOVED)) continue;   // a ghost's move is void: k_unlink settled it
-        const double py = pos_new[y];
+        const double py = single ? lone_pos : pos_new[y];   // (one entrant: its key came with the lane's record)
         if (!first && !(py > e_pos || (py == e_pos && y > e))) continue;
         if (best < 0 || py < best_pos || (py == best_pos && y < best)) { best = y; best_pos = py; }
       }

@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
     p.coldf[a] = f;
     // onto the lane's inbox
     LaneRec* lr = &p.lane[r.container];
+    lr->e_pos = r.pos_new;
     k.inbox_next = atomicExch(&lr->inbox, a);
     p.cold[a] = k;
     const uint32_t old = atomicAdd(&lr->meta, META_IN_ONE);

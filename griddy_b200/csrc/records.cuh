@@ -115,7 +115,7 @@ struct __align__(16) LaneRec {
   int32_t link2;          // junction lane: its junction; segment: outer back-side lane
   int32_t to_j;           // grid routing: junction a segment lane reaches
   uint32_t meta;          // kind (bits 0-2), direction (bit 3); entrants pushed this tick (bits 16-31, reset by k_link)
-  int32_t pad[2];
+  double e_pos;           // the new pos-param of this tick's entrant (k_link reads it instead of the entrant's own when there is one)
   int32_t tail;           // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
   int32_t inbox, outbox, ghosts;   // this tick's entrants (chained through Cold); outbox, ghosts: unused
   int32_t turn[4];        // grid routing: junction lane leading onto the segment that leaves this lane's end with heading h

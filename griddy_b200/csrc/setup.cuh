@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) k_item_build(LaneRec* __restrict__ lane, 
   it.link2 = k == GRIDDY_JUNCTION_LANE ? junction[r] : k == GRIDDY_SEGMENT ? ob[r] : -1;
   it.to_j = -1;
   it.meta = (uint32_t)(k & 7) | (dir[r] ? META_DIR : 0u);
-  it.pad[0] = it.pad[1] = 0;
+  it.e_pos = 0.0;
   it.tail = it.inbox = it.outbox = it.ghosts = -1;
   it.turn[0] = it.turn[1] = it.turn[2] = it.turn[3] = -1;
   lane[r] = it;
