@@ -415,6 +415,9 @@ def main():
     frames = [device.PinnedFrame(cap), device.PinnedFrame(cap)]
     dframes = [device.DeltaFrame(cap), device.DeltaFrame(cap)]
 
+    copy_ms = []
+    fmt_ms = []   # device time of the delta frames' format kernel (events around it; runs beside the previous frame's copy)
+
     def e2e_full_loop(steps):
         """Full frames: float x, y of every slot, every tick (griddy_positions_begin / _end)."""
         slots = 0
@@ -431,6 +434,8 @@ def main():
     def e2e_delta_loop(steps):
         """Delta frames: per tick the slots whose drawn position changed (griddy_delta_begin / _end)."""
         copied = changed = keys = 0
+        fmt_ms.clear()
+        copy_ms.clear()
         sim.step_async(1)
         sim.delta_begin(dframes[0])
         for k in range(1, steps + 1):
@@ -441,6 +446,9 @@ def main():
             copied += fr.bytes_copied
             changed += fr.n_changed
             keys += int(fr.key)
+            if not fr.key:
+                fmt_ms.append(sim.last_frame_ms)
+                copy_ms.append(sim.last_copy_ms)
         sim.step(0)
         return copied, changed, keys
 
@@ -494,6 +502,8 @@ def main():
                 "d2h_bytes_per_step": e2e_delta["d2h"], "steps": args.e2e_steps, "ms_per_step": e2e_delta["ms_per_step"],
                 "living_actors": e2e_delta["alive"], "positions_changed_per_step": e2e_delta["changed"],
                 "key_frames_in_timed_region": e2e_delta["keys"],
+                "frame_kernel_ms": (sorted(fmt_ms)[len(fmt_ms) // 2] if fmt_ms else None),
+                "frame_copy_ms": (sorted(copy_ms)[len(copy_ms) // 2] if copy_ms else None),
                 "note": "per step: one `update` (griddy_step_async(1): no host synchronisation per tick) + one `draw` "
                         "read-back as a DELTA frame (griddy_delta_begin/_end): (get-pos actor) (spatial.scm:125-149) is "
                         "evaluated on the device for every actor whose drawn position differs from the frame before, and "

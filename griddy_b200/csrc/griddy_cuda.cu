@@ -209,6 +209,9 @@ struct Ctx {
   unsigned int* h_dcnt = nullptr;            // [2 frames], page-locked and mapped
   cudaEvent_t ev_delta[2] = {nullptr, nullptr}, ev_dcopied[2] = {nullptr, nullptr};
   uint64_t deltas_flushed = 0;               // frames whose copies have been enqueued
+  cudaEvent_t ev_fmt0[2] = {nullptr, nullptr};   // with ev_delta: device time of the frame kernel (griddy_last_frame_ms)
+  cudaEvent_t ev_copy0[2] = {nullptr, nullptr};  // with ev_dcopied: time of the frame's copies on their stream
+  double last_frame_ms = 0.0, last_copy_ms = 0.0;
   int64_t delta_n[2] = {0, 0};
   uint8_t* delta_dst[2] = {nullptr, nullptr};
   int64_t delta_ns[2] = {0, 0}, delta_cap[2] = {0, 0}, delta_tick[2] = {0, 0};
@@ -599,7 +602,7 @@ int griddy_create(void** ctx, int device) {
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&c->stream) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_scal, cudaEventDisableTiming) != cudaSuccess ||
-      cudaHostAlloc((void**)&c->h_scal, SC_COUNT * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc((void**)&c->h_scal, SC_COUNT * sizeof(int32_t), cudaHostAllocMapped) != cudaSuccess ||
       rsort::prepare() != cudaSuccess) {
     delete c;
     return GRIDDY_ERR_CUDA;
@@ -628,6 +631,8 @@ void griddy_destroy(void* ctx) {
     if (c->ev_drawn[f]) cudaEventDestroy(c->ev_drawn[f]);
     if (c->ev_copied[f]) cudaEventDestroy(c->ev_copied[f]);
     if (c->ev_delta[f]) cudaEventDestroy(c->ev_delta[f]);
+    if (c->ev_fmt0[f]) cudaEventDestroy(c->ev_fmt0[f]);
+    if (c->ev_copy0[f]) cudaEventDestroy(c->ev_copy0[f]);
     if (c->ev_dcopied[f]) cudaEventDestroy(c->ev_dcopied[f]);
   }
   if (c->h_dcnt) cudaFreeHost(c->h_dcnt);
@@ -1492,7 +1497,12 @@ int griddy_step_async(void* ctx, int64_t n_ticks) {
   c->tick += n_ticks;
   c->ticks_after_scal += n_ticks;
   if (!c->scal_pending) {
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->p.scal, SC_COUNT * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    // (a kernel's stores into the mapped mirror, not a copy: a device-to-host copy here would queue up behind the
+    // frame that the copy engine is carrying for griddy_positions_begin / griddy_delta_begin and stall this stream)
+    int32_t* mirror = nullptr;
+    CUDA_TRY(c, cudaHostGetDevicePointer((void**)&mirror, c->h_scal, 0));
+    k_mirror_scalars<<<1, 32, 0, c->stream>>>(c->p.scal, mirror);
+    ++c->launches;
     CUDA_TRY(c, cudaEventRecord(c->ev_scal, c->stream));
     c->scal_pending = true;
     c->ticks_after_scal = 0;
@@ -2092,6 +2102,11 @@ int griddy_upload_geometry(void* ctx, const double* geom) {
   double2* d = nullptr;   // 4 x double2 per item, by global id like every per-item array; geom is compact
   TRY(sparse_alloc(c, 4 * sizeof(double2), (void**)&d));
   TRY(sparse_upload(c, d, (const double2*)geom, 4));
+  for (size_t k = 0; k < c->tl.beg.size(); ++k) {   // mark the straight lanes (readback.cuh, k_geom_mark)
+    const int64_t m = c->tl.end[k] - c->tl.beg[k];
+    if (m > 0) k_geom_mark<<<(unsigned)((m + 255) / 256), 256>>>(c->p.lane + c->tl.beg[k], d + 4 * c->tl.beg[k], m);
+  }
+  CUDA_TRY(c, cudaDeviceSynchronize());
   c->d_geom = d;
   return GRIDDY_OK;
 }
@@ -2227,8 +2242,10 @@ int griddy_delta_begin(void* ctx, void* frame, int64_t capacity) {
   }
   if (!c->ev_delta[0])
     for (int f = 0; f < 2; ++f) {
-      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_delta[f], cudaEventDisableTiming));
-      CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_dcopied[f], cudaEventDisableTiming));
+      CUDA_TRY(c, cudaEventCreate(&c->ev_delta[f]));
+      CUDA_TRY(c, cudaEventCreate(&c->ev_fmt0[f]));
+      CUDA_TRY(c, cudaEventCreate(&c->ev_copy0[f]));
+      CUDA_TRY(c, cudaEventCreate(&c->ev_dcopied[f]));
     }
   TRY(delta_flush(c, false));
   if (!c->h_dcnt) CUDA_TRY(c, cudaHostAlloc((void**)&c->h_dcnt, 2 * sizeof(unsigned int), cudaHostAllocMapped));
@@ -2255,6 +2272,7 @@ int griddy_delta_begin(void* ctx, void* frame, int64_t capacity) {
     CUDA_TRY(c, cudaMemsetAsync(c->d_drawn + ns, 0xFF, (size_t)(c->delta_cover - ns) * sizeof(unsigned long long), c->stream));
   const int f = (int)(c->deltas_begun & 1);   // its previous user has been waited for by griddy_delta_end
   c->h_dcnt[f] = 0;
+  CUDA_TRY(c, cudaEventRecord(c->ev_fmt0[f], c->stream));
   if (ns > 0) {
     FrameOut o{};
     o.drawn = c->d_drawn;
@@ -2296,6 +2314,7 @@ int delta_flush(Ctx* c, bool wait) {
     const DeltaLayout dl(c->delta_cap[f]);
     uint8_t* dst = c->delta_dst[f];
     const int64_t blocks = (c->delta_ns[f] + FRAME_TILE - 1) / FRAME_TILE;
+    CUDA_TRY(c, cudaEventRecord(c->ev_copy0[f], c->draw_stream));
     if (n > 0) CUDA_TRY(c, cudaMemcpyAsync(dst + dl.xy_off, c->d_dvals[f], (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->draw_stream));
     if (blocks > 0) {
       CUDA_TRY(c, cudaMemcpyAsync(dst + dl.mask_off, c->d_dmask[f], (size_t)blocks * (FRAME_TILE / 32) * 4, cudaMemcpyDeviceToHost, c->draw_stream));
@@ -2312,6 +2331,8 @@ int delta_flush(Ctx* c, bool wait) {
     hdr[6] = c->delta_cap[f];
     hdr[7] = 0;
     c->delta_n[f] = n;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_fmt0[f], c->ev_delta[f]) == cudaSuccess) c->last_frame_ms = ms;
     ++c->deltas_flushed;
   }
   return GRIDDY_OK;
@@ -2330,6 +2351,8 @@ int griddy_delta_end(void* ctx, int64_t* n_slots, int64_t* n_changed) {
     TRY(delta_flush(c, false));
   }
   CUDA_TRY(c, cudaEventSynchronize(c->ev_dcopied[f]));
+  float copy_ms = 0.f;
+  if (cudaEventElapsedTime(&copy_ms, c->ev_copy0[f], c->ev_dcopied[f]) == cudaSuccess) c->last_copy_ms = copy_ms;
   if (n_slots) *n_slots = c->delta_ns[f];
   if (n_changed) *n_changed = c->delta_n[f];
   ++c->deltas_ended;
@@ -2470,6 +2493,8 @@ int griddy_debug_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int32_t k
 }
 
 double griddy_last_step_ms(void* ctx) { return ctx ? ((Ctx*)ctx)->last_ms : 0.0; }
+double griddy_last_frame_ms(void* ctx) { return ctx ? ((Ctx*)ctx)->last_frame_ms : 0.0; }
+double griddy_last_copy_ms(void* ctx) { return ctx ? ((Ctx*)ctx)->last_copy_ms : 0.0; }
 int64_t griddy_tick(void* ctx) { return ctx ? ((Ctx*)ctx)->tick : 0; }
 int64_t griddy_kernel_launches(void* ctx) { return ctx ? ((Ctx*)ctx)->launches : 0; }
 int64_t griddy_slots_in_use(void* ctx) { return ctx ? ((Ctx*)ctx)->ns_host : 0; }

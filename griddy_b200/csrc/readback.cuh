@@ -6,6 +6,12 @@ namespace griddy {
 // ------------------------------------------------------------------------------------------------
 // Read-back: format the world on the device (by actor id), then one copy per output array.
 
+// The device's scalars (error bits, slots in use, dead slots) into the host's mapped mirror, for griddy_step_async.
+__global__ void k_mirror_scalars(const int32_t* __restrict__ scal, int32_t* __restrict__ host) {
+  if (threadIdx.x < SC_COUNT) host[threadIdx.x] = scal[threadIdx.x];
+  __threadfence_system();
+}
+
 // Ghost rule for downloads: flag every leader that shares its follower's key.
 __global__ void __launch_bounds__(256) k_flag_ghosts(Params p, int par, uint8_t* ghost) {
   const int a = blockIdx.x * 256 + threadIdx.x;
@@ -153,17 +159,25 @@ __device__ __forceinline__ double bezier_1d(double w0, double w1, double w2, dou
   return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w0, a), __dmul_rn(w1, b)), __dmul_rn(w2, c)), __dmul_rn(w3, d));
 }
 
+// A segment lane's geometry record uses two of its four vec2; the device copy carries NaN in the third, so that the
+// frame kernels tell a straight lane from a junction lane's curve without fetching the lane's record.
+__global__ void __launch_bounds__(256) k_geom_mark(const LaneRec* __restrict__ lane, double2* __restrict__ geom, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n && meta_kind(lane[i].meta) == GRIDDY_SEGMENT_LANE) geom[4 * i + 2].x = __longlong_as_double(0x7ff8000000000000LL);
+}
+
 // (get-pos actor) of the living actor in slot a: st its flags, t its pos-param.
 __device__ __forceinline__ double2 get_pos_xy(const Params& p, const double2* __restrict__ geom, int a, uint32_t st, double t) {
   const int32_t c = p.cold[a].container;
   const double2* g = geom + 4 * (int64_t)c;
-  if (!(st & ST_ONROAD) || meta_kind(p.lane[c].meta) == GRIDDY_SEGMENT_LANE) {
-    const double2 o = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? g[2] : g[0];
-    const double2 v = g[1];
+  const double2 g0 = g[0], g1 = g[1], g2 = g[2];
+  if (!(st & ST_ONROAD) || g2.x != g2.x) {
+    const double2 o = (!(st & ST_ONROAD) && (st & ST_SIDE)) ? g2 : g0;
+    const double2 v = g1;
     return make_double2(__dadd_rn(o.x, __dmul_rn(t, v.x)), __dadd_rn(o.y, __dmul_rn(t, v.y)));
   }
   // chickadee bezier-curve-point-at (not vendored; the form tests/golden/minischeme.py assumes)
-  const double2 p0 = g[0], p1 = g[1], p2 = g[2], p3 = g[3];
+  const double2 p0 = g0, p1 = g1, p2 = g2, p3 = g[3];
   const double u = __dsub_rn(1.0, t);
   const double w0 = __dmul_rn(__dmul_rn(u, u), u);
   const double w1 = __dmul_rn(__dmul_rn(__dmul_rn(3.0, u), u), t);

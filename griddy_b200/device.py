@@ -31,7 +31,8 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_mg_plan", "griddy_download_local", "griddy_mg_neighbors", "griddy_mg_ipc_export",
            "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
            "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace", "griddy_state_digest",
-           "griddy_delta_frame_bytes", "griddy_delta_begin", "griddy_delta_end", "griddy_delta_apply")
+           "griddy_delta_frame_bytes", "griddy_delta_begin", "griddy_delta_end", "griddy_delta_apply", "griddy_last_frame_ms",
+           "griddy_last_copy_ms")
 
 
 class GriddyCudaError(RuntimeError):
@@ -53,6 +54,10 @@ def lib():
         L.griddy_last_error.argtypes = [C.c_void_p]
         L.griddy_last_step_ms.restype = C.c_double
         L.griddy_last_step_ms.argtypes = [C.c_void_p]
+        L.griddy_last_frame_ms.restype = C.c_double
+        L.griddy_last_frame_ms.argtypes = [C.c_void_p]
+        L.griddy_last_copy_ms.restype = C.c_double
+        L.griddy_last_copy_ms.argtypes = [C.c_void_p]
         L.griddy_tick.restype = C.c_int64
         L.griddy_tick.argtypes = [C.c_void_p]
         L.griddy_kernel_launches.restype = C.c_int64
@@ -173,6 +178,14 @@ class Simulation:
     @property
     def last_step_ms(self) -> float:
         return float(lib().griddy_last_step_ms(self.h))
+
+    @property
+    def last_frame_ms(self) -> float:
+        return float(lib().griddy_last_frame_ms(self.h))
+
+    @property
+    def last_copy_ms(self) -> float:
+        return float(lib().griddy_last_copy_ms(self.h))
 
     @property
     def tick(self) -> int:

@@ -303,6 +303,8 @@ int griddy_download_local(void* ctx, int64_t capacity, int64_t* n_local, int32_t
 int griddy_profile_step(void* ctx, int64_t n_ticks, double* kernel_ms);
 
 double griddy_last_step_ms(void* ctx);       /* device time of the last griddy_step (CUDA events) */
+double griddy_last_frame_ms(void* ctx);      /* device time of the frame kernel of the delta frame whose copy started last */
+double griddy_last_copy_ms(void* ctx);       /* time the copies of the delta frame ended last took on their stream */
 int64_t griddy_tick(void* ctx);              /* ticks since upload */
 int64_t griddy_kernel_launches(void* ctx);   /* kernels launched by this context so far */
 /* Actors in the world right now (an actor replaced by an equal-key insert is gone, core.scm:173-178). */
