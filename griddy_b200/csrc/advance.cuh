@@ -77,9 +77,9 @@ __device__ __forceinline__ uint32_t load_head(const Params& p, int32_t a, int32_
 //   leavers  one record per actor that leaves its lane's list this tick — it changed lane, went off the road, jumped
 //            back on its lane, or was found to be a ghost: {slot, the lane it leaves, that lane's junction if it is a
 //            junction lane (else -1), 0}.  k_unlink takes them out, one thread per record.
-//   entered  lanes that gained an actor: whether a lane is listed already is kept in its own record (LaneRec::meta
-//            counts the entrants), so k_link has one thread per lane and never reads the chain through the cold
-//            records when there is one entrant.
+//   entered  lanes that gained an actor: the first entrant — the one that finds the lane's inbox empty — lists the
+//            lane, any other marks it (LaneRec::meta, META_MULTI), so k_link has one thread per lane and never
+//            reads the chain through the cold records when there is one entrant.
 struct TouchSink {
   int4* left;                     // shared: leaver records, LEAVER_STAGE entries; beyond that they go straight to the global list
   int32_t* n_left;
@@ -114,9 +114,8 @@ __device__ __forceinline__ int32_t occupied_junction(int32_t tj) { return tj <= 
 __device__ __forceinline__ int32_t enter_lane(const Params& p, int a, int32_t lane, double pos, const TouchSink& sink) {
   p.lane[lane].e_pos = pos;   // (several entrants overwrite each other: k_link then takes every one's own)
   const int32_t prev = atomicExch(&p.lane[lane].inbox, a);
-  const uint32_t old = atomicAdd(&p.lane[lane].meta, META_IN_ONE);
-  if (!(old & META_IN)) sink.entered[atomicAdd(sink.n_entered, 1)] = lane;
-  else if ((old & META_IN) == META_IN) dev_error(p, DEV_ERR_LANE_BURST);
+  if (prev < 0) sink.entered[atomicAdd(sink.n_entered, 1)] = lane;   // the first entrant lists the lane
+  else atomicOr(&p.lane[lane].meta, META_MULTI);                     // any other says that the inbox is a chain
   return prev;
 }
 

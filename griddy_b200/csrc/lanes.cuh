@@ -113,15 +113,32 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_touched; i += gridDim.x * blockDim.x) {
     const int32_t lane = entered[i];
     LaneRec* lr = &p.lane[lane];
+    const int4 links = *(const int4*)&lr->len;    // len, link, link2
     const int4 first = *(const int4*)&lr->to_j;   // to_j, meta, e_pos
     const uint32_t meta = (uint32_t)first.y;
     const double lone_pos = __hiloint2double(first.w, first.z);
     const int4 heads = *(const int4*)&lr->tail;   // tail, inbox, outbox, ghosts
     const int32_t inbox = heads.y;
-    const bool single = (meta & META_IN) == META_IN_ONE;
-    atomicAnd(&lr->meta, ~META_IN);
+    const bool single = !(meta & META_MULTI);
     if (inbox < 0) continue;
     lr->inbox = -1;
+    if (single) {
+      // One entrant, no tie — nearly every lane: its key came with the lane's record, its hot record is written once.
+      const int4 he = *(const int4*)&p.hot[inbox];   // st, ahead, behind, tj
+      if (!((uint32_t)he.x & ST_MOVED)) continue;    // a ghost's move is void: k_unlink settled it
+      int32_t prev = -1, x = heads.x;
+      double px = 0.0;
+      while (x >= 0 && (px = pos_new[x]) < lone_pos) { prev = x; x = p.hot[x].ahead; }
+      if (!(x >= 0 && px == lone_pos)) {
+        if (prev < 0) lr->tail = inbox; else p.hot[prev].ahead = inbox;
+        *(int4*)&p.hot[inbox] = make_int4((int)((uint32_t)he.x & ~(ST_MOVED | ST_IMMIG)), x, prev, he.w);
+        if (x >= 0) p.hot[x].behind = inbox;
+        if (meta_kind(meta) == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[links.w], 1);
+        continue;
+      }
+    } else {
+      atomicAnd(&lr->meta, ~META_MULTI);
+    }
     auto next_in = [&](int32_t y) { return single ? -1 : p.cold[y].inbox_next; };
     // entrants by ascending (pos-param, slot): selection over the inbox, which is short
     double e_pos = 0.0;
@@ -170,7 +187,7 @@ __global__ void __launch_bounds__(128) k_link(Params p, int tick) {
       if (sy & ST_MOVED) p.hot[y].st = sy & ~(ST_MOVED | ST_IMMIG);
     }
     if (tail != heads.x) lr->tail = tail;
-    if (delta && meta_kind(meta) == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[lr->link2], delta);
+    if (delta && meta_kind(meta) == GRIDDY_JUNCTION_LANE) atomicAdd(&p.occ[links.w], delta);
     if (died) atomicAdd(&p.scal[SC_NDEAD], died);
   }
 }

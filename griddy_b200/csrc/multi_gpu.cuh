@@ -248,9 +248,8 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
     lr->e_pos = r.pos_new;
     k.inbox_next = atomicExch(&lr->inbox, a);
     p.cold[a] = k;
-    const uint32_t old = atomicAdd(&lr->meta, META_IN_ONE);
-    if (!(old & META_IN)) p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_ENTERED], 1)] = r.container;
-    else if ((old & META_IN) == META_IN) dev_error(p, DEV_ERR_LANE_BURST);
+    if (k.inbox_next < 0) p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_ENTERED], 1)] = r.container;
+    else atomicOr(&lr->meta, META_MULTI);
   }
 }
 

@@ -114,15 +114,14 @@ struct __align__(16) LaneRec {
   int32_t link;           // segment lane: its segment; junction lane: the lane it leads onto; segment: outer forw-side lane
   int32_t link2;          // junction lane: its junction; segment: outer back-side lane
   int32_t to_j;           // grid routing: junction a segment lane reaches
-  uint32_t meta;          // kind (bits 0-2), direction (bit 3); entrants pushed this tick (bits 16-31, reset by k_link)
+  uint32_t meta;          // kind (bits 0-2), direction (bit 3); bit 16: several entrants were pushed this tick (reset by k_link)
   double e_pos;           // the new pos-param of this tick's entrant (k_link reads it instead of the entrant's own when there is one)
   int32_t tail;           // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
   int32_t inbox, outbox, ghosts;   // this tick's entrants (chained through Cold); outbox, ghosts: unused
   int32_t turn[4];        // grid routing: junction lane leading onto the segment that leaves this lane's end with heading h
 };
 static_assert(sizeof(LaneRec) == 64, "one line per item");
-constexpr uint32_t META_KIND = 7u, META_DIR = 8u, META_OUT_ONE = 1u << 4, META_OUT = 0x7ff0u, META_GHOST = 1u << 15,
-                   META_LEFT = META_OUT | META_GHOST, META_IN_ONE = 1u << 16, META_IN = 0xffff0000u;
+constexpr uint32_t META_KIND = 7u, META_DIR = 8u, META_MULTI = 1u << 16;
 __host__ __device__ __forceinline__ int meta_kind(uint32_t m) { return (int)(m & META_KIND); }
 __host__ __device__ __forceinline__ uint32_t meta_dir(uint32_t m) { return (m >> 3) & 1u; }
 
