@@ -60,7 +60,8 @@ __device__ __forceinline__ int32_t junction_of_hop(const Params& p, int32_t hop)
 // is not needed.
 __device__ __forceinline__ int32_t junction_after(const Params& p, const LaneRec& it, int32_t nhop) {
   if (p.route_off) return junction_of_hop(p, nhop);
-  return tag_junction(p, (nhop >= 0 && meta_kind(it.meta) == GRIDDY_SEGMENT_LANE) ? it.to_j : -1);
+  if (!(nhop >= 0 && meta_kind(it.meta) == GRIDDY_SEGMENT_LANE) || it.to_j < 0) return -1;
+  return (p.owner && (it.meta & META_TOJ_REMOTE)) ? (it.to_j | TJ_REMOTE) : it.to_j;   // (marked by griddy_mg_configure)
 }
 
 // New agenda head after a pop (actor.scm:28-31): its kind bits, and the sleep counter in *aux.
@@ -128,6 +129,7 @@ __device__ void emigrate(const Params& p, int a, int tick, uint32_t st, const Co
                          double pos_new, double delta, double buf);   // multi_gpu.cuh
 __device__ void emig_publish(const Params& p, int tick);
 __device__ __forceinline__ void halo_pack_block(const Params& p, int tick, int n_blocks);
+__device__ __forceinline__ void halo_unpack_block(const Params& p, int tick, int blk, int n_blocks);
 
 __device__ __forceinline__ double turn_onto(const Params& p, const int a, const int tick, const uint32_t st,
                                             const double cur, const double* __restrict__ pos_old, const TouchSink& sink) {
@@ -346,8 +348,9 @@ constexpr int ADV_THREADS = ADV_THREADS_N;
 #define ADV_BOUNDS __launch_bounds__(ADV_THREADS)
 #endif
 
-// On a partitioned world the first halo_blocks blocks send the halo instead (multi_gpu.cuh, halo_pack_block).
-__global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks) {
+// On a partitioned world the first halo_blocks blocks send the halo instead (multi_gpu.cuh, halo_pack_block) and, with
+// one process per GPU, the last unpack_blocks blocks take the neighbours' halo in (halo_unpack_block).
+__global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks, int unpack_blocks) {
   __shared__ int4 s_list[ADV_THREADS * ADV_UNROLL];
   __shared__ double s_pos[ADV_THREADS * ADV_UNROLL];
   __shared__ int32_t s_n, s_base;
@@ -358,6 +361,10 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks) {
   if (blockIdx.x == 0 && threadIdx.x < CNT_STRIDE) p.counters[CNT_STRIDE * (par ^ 1) + threadIdx.x] = 0;
   if ((int)blockIdx.x < halo_blocks) {
     halo_pack_block(p, tick, halo_blocks);
+    return;
+  }
+  if ((int)blockIdx.x >= (int)gridDim.x - unpack_blocks) {
+    halo_unpack_block(p, tick, (int)blockIdx.x - ((int)gridDim.x - unpack_blocks), unpack_blocks);
     return;
   }
   const int n = p.scal[SC_NSLOTS];

@@ -804,6 +804,7 @@ int griddy_set_routing_grid(void* ctx, int32_t n, const int32_t* lane_from_j, co
   Ctx* c = (Ctx*)ctx;
   if (!c) return GRIDDY_ERR_BAD_ARG;
   if (!c->have_net) return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid before upload_network");
+  if (c->mg.on) return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid after griddy_mg_configure (the partition marks the lanes that reach another rank's junction)");
   const Tiling& tl = c->tl;
   if (n < 1 || (int64_t)n * n > tl.n_global || !lane_from_j || !lane_to_j || !turn4)
     return fail(c, GRIDDY_ERR_BAD_ARG, "set_routing_grid: bad arguments");
@@ -1321,13 +1322,17 @@ int tick_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   return GRIDDY_OK;
 }
 
-int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+// fused (a partitioned world, one process per GPU): the halo and the immigrants are taken in by the last blocks of
+// k_advance and k_unlink; otherwise (all ranks on one GPU, ordered by events) by kernels of their own.
+int tick_advance(Ctx* c, int64_t tick, cudaEvent_t* ev, bool fused = false) {
   const unsigned per_block = ADV_THREADS * ADV_UNROLL;
   const unsigned adv_blocks = (unsigned)((c->ns_host + per_block - 1) / per_block);
   // a partitioned world: its first blocks send the halo (at least one: it raises the flags)
   const unsigned halo_blocks = c->mg.nb.empty() ? 0u : (unsigned)std::max(1, (c->mg.n_exp + ADV_THREADS - 1) / ADV_THREADS);
-  if (adv_blocks + halo_blocks)
-    CUDA_TRY(c, launch_dependent(k_advance, adv_blocks + halo_blocks, ADV_THREADS, c->stream, c->p, (int)tick, (int)halo_blocks));
+  const unsigned unpack_blocks = (fused && !c->mg.nb.empty()) ? (unsigned)std::max(1, (c->mg.n_imp_junc + ADV_THREADS - 1) / ADV_THREADS) : 0u;
+  if (adv_blocks + halo_blocks + unpack_blocks)
+    CUDA_TRY(c, launch_dependent(k_advance, adv_blocks + halo_blocks + unpack_blocks, ADV_THREADS, c->stream, c->p, (int)tick,
+                                 (int)halo_blocks, (int)unpack_blocks));
   if (ev) cudaEventRecord(ev[2], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -1346,8 +1351,19 @@ unsigned relink_blocks(const Ctx* c) {
   return std::min<unsigned>(std::max((unsigned)((c->ns_host / 8 + 127) / 128), 1u), 148u * 64u);
 }
 
-int tick_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // local lists only: does not need the migrants
-  CUDA_TRY(c, launch_dependent(k_unlink, relink_blocks(c), 128u, c->stream, c->p, (int)tick));
+int tick_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev, bool fused = false) {   // local lists only: does not need the migrants
+  unsigned immig_blocks = 0;
+  if (fused && !c->mg.nb.empty()) {
+    int most = 1;
+    for (Neighbor& nb : c->mg.nb) {
+      most = std::max(most, nb.mig_in);
+      // upper bound of the slots in use: the neighbour may have filled its buffer
+      c->ns_host = (int32_t)std::min<int64_t>(c->p.cap, (int64_t)c->ns_host + nb.mig_in);
+    }
+    immig_blocks = (unsigned)std::max(1, most / 512);
+  }
+  CUDA_TRY(c, launch_dependent(k_unlink, relink_blocks(c) + immig_blocks * (unsigned)c->mg.world, 128u, c->stream, c->p, (int)tick,
+                               (int)immig_blocks, (int)c->mg.world));
   if (ev) cudaEventRecord(ev[4], c->stream);
   ++c->launches;
   return GRIDDY_OK;
@@ -1373,8 +1389,7 @@ int tick_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {   // on a partitioned wor
 int mg_halo_unpack(Ctx* c, int64_t tick, cudaStream_t s) {
   if (c->mg.nb.empty()) return GRIDDY_OK;
   const unsigned blocks = (unsigned)std::max(1, (c->mg.n_imp_junc + 127) / 128);   // at least one: it waits for the flags
-  CUDA_TRY(c, launch_dependent(k_halo_unpack, blocks, 128u, s, c->p, (const int32_t*)c->mg.d_imp_junc,
-                               (const int32_t*)c->mg.d_imp_where, c->mg.n_imp_junc, (int)tick));
+  CUDA_TRY(c, launch_dependent(k_halo_unpack, blocks, 128u, s, c->p, (int)tick));
   ++c->launches;
   return GRIDDY_OK;
 }
@@ -1409,11 +1424,9 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
     TRY(tick_unlink(c, tick, ev));
     return tick_link(c, tick, ev);
   }
-  TRY(tick_advance(c, tick, ev));                 // its first blocks send the halo, which travels while the rest run
-  TRY(mg_halo_unpack(c, tick, c->stream));        // waits for the neighbours' halo flags
+  TRY(tick_advance(c, tick, ev, true));           // its first blocks send the halo, which travels while the rest run; its last take the neighbours' in
   TRY(tick_slow(c, tick, ev));                    // movers that cross write themselves into the neighbours' windows
-  TRY(tick_unlink(c, tick, ev));
-  TRY(mg_immig_unpack(c, tick, c->stream));       // waits for the neighbours' migrant flags
+  TRY(tick_unlink(c, tick, ev, true));            // its last blocks wait for the neighbours' migrant flags and unpack the arrivals
   return tick_link(c, tick, ev);
 }
 
@@ -1436,6 +1449,8 @@ int local_link(Ctx* c, int64_t tick, cudaEvent_t* ev) {
   TRY(mg_immig_unpack(c, tick, c->stream));
   return tick_link(c, tick, ev);
 }
+
+int local_unlink(Ctx* c, int64_t tick, cudaEvent_t* ev) { return tick_unlink(c, tick, ev); }
 
 int wait_for_neighbours(Ctx* src) {   // every neighbour's stream waits for what src has enqueued so far
   for (Neighbor& nb : src->mg.nb) {
@@ -1553,7 +1568,7 @@ int griddy_mg_step_local(void** ctxs, int32_t n, int64_t n_ticks) {
       CUDA_TRY(c, cudaSetDevice(c->device));
       CUDA_TRY(c, cudaEventRecord(c->mg.ev_ready, c->stream));
     }
-    TRY(each(tick_unlink, t, false));
+    TRY(each(local_unlink, t, false));
     for (Ctx* c : cs) TRY(wait_for_neighbours(c));
     TRY(each(local_link, t, false));
   }
@@ -1945,7 +1960,30 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
     CUDA_TRY(c, cudaMemcpy(m.d_imp_junc, imp_junc_all.data(), imp_junc_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(m.d_imp_where, imp_where_all.data(), imp_where_all.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
+  {   // segment lanes that reach a junction of another rank (META_TOJ_REMOTE)
+    for (size_t k = 0; k < c->tl.beg.size(); ++k) {
+      const int64_t n_k = c->tl.end[k] - c->tl.beg[k];
+      if (n_k > 0) k_lane_clear_remote<<<(unsigned)((n_k + 255) / 256), 256>>>(p.lane + c->tl.beg[k], n_k);
+    }
+    std::vector<int32_t> marks;
+    for (size_t k = 0; k < c->tl.beg.size() && !c->h_to.empty(); ++k)
+      for (int64_t g = c->tl.beg[k]; g < c->tl.end[k]; ++g) {
+        const int64_t l = c->tl.off[k] + (g - c->tl.beg[k]);
+        if (c->h_kind[(size_t)l] == GRIDDY_SEGMENT_LANE && c->h_to[(size_t)l] >= 0 && c->owner_of(c->h_to[(size_t)l]) != rank)
+          marks.push_back((int32_t)g);
+      }
+    if (!marks.empty()) {
+      int32_t* d_marks = nullptr;
+      TRY(mg_alloc(c, &d_marks, marks.size()));
+      CUDA_TRY(c, cudaMemcpy(d_marks, marks.data(), marks.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      k_lane_mark_remote<<<(unsigned)((marks.size() + 255) / 256), 256>>>(p.lane, d_marks, (int64_t)marks.size());
+      CUDA_TRY(c, cudaDeviceSynchronize());
+    }
+  }
   p.owner = m.d_owner;
+  p.imp_junc = m.d_imp_junc;
+  p.imp_where = m.d_imp_where;
+  p.n_imp_junc = m.n_imp_junc;
   p.halo_items = m.d_exp_items;
   p.halo_total = m.n_exp;
   p.my_rank = rank;

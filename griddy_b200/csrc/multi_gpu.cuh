@@ -91,18 +91,23 @@ __device__ __forceinline__ void halo_pack_block(const Params& p, const int tick,
 }
 
 // Halo in: wait for every neighbour's flag of this tick, then take over the occupancy of the neighbours'
-// junctions (the lane values are read in place from halo_recv by turn_onto).  One launch for all
-// neighbours: junctions[i] is a junction another rank owns, where[i] its place in halo_recv.  k_slow, next
-// on the stream, may then read the halo.
-__global__ void __launch_bounds__(128) k_halo_unpack(Params p, const int32_t* __restrict__ junctions,
-                                                      const int32_t* __restrict__ where, int n, int tick) {
-  grid_dependency_wait();
-  TRACE(p, tick, TR_HALO_UNPACK);
+// junctions (the lane values are read in place from halo_recv by turn_onto): Params::imp_junc[i] is a junction another
+// rank owns, imp_where[i] its place in halo_recv.  k_slow, next on the stream, may then read the halo.  Nothing else
+// reads those entries of the occupancy table (k_advance leaves an actor gated by a remote junction to k_slow), so with
+// one process per GPU this runs as the LAST blocks of k_advance — the neighbours' halo left with the first blocks of
+// theirs — and costs no launch; with all ranks on one stream-ordered GPU (tests) it is the kernel k_halo_unpack.
+__device__ __forceinline__ void halo_unpack_block(const Params& p, const int tick, const int blk, const int n_blocks) {
   const int par = tick & 1;
   if (threadIdx.x < MAX_RANKS && p.hflag_mine[threadIdx.x][par]) wait_flag(p, p.hflag_mine[threadIdx.x][par], tick + 1);
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p.occ[junctions[i]] = (int32_t)__ldcg(&p.halo_recv[par][where[i]]);
+  for (int i = blk * blockDim.x + threadIdx.x; i < p.n_imp_junc; i += n_blocks * blockDim.x)
+    p.occ[p.imp_junc[i]] = (int32_t)__ldcg(&p.halo_recv[par][p.imp_where[i]]);
+}
+
+__global__ void __launch_bounds__(128) k_halo_unpack(Params p, int tick) {
+  grid_dependency_wait();
+  TRACE(p, tick, TR_HALO_UNPACK);
+  halo_unpack_block(p, tick, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // Emigrants -> one record each plus their remaining agenda items, written by the k_slow thread that moves the actor
@@ -146,14 +151,14 @@ __device__ void emigrate(const Params& p, int a, int tick, uint32_t st, const Co
   ((MigRec*)(area + sizeof(MigHeader)))[at] = r;
   AgendaItem* items = (AgendaItem*)(area + sizeof(MigHeader) + (size_t)p.mig_cap[to] * sizeof(MigRec)) + r.item_off;
   for (int32_t q = 0; q < r.n_items; ++q) items[q] = p.agenda[k.agenda_cur + q];
+  __threadfence_system();   // my record before my block's count (emig_publish): only the threads that wrote one pay for it
 }
 
 // End of k_slow on a partitioned world, every block: my records before my block's count; the last block publishes.
 __device__ void emig_publish(const Params& p, int tick) {
   __shared__ bool s_last;
   const int par = tick & 1;
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();   // (every thread that wrote a record has fenced it, see emigrate)
   if (threadIdx.x == 0) s_last = atomicAdd(p.mig_done, 1) == (int)gridDim.x - 1;
   __syncthreads();
   if (!s_last) return;
@@ -174,28 +179,28 @@ __device__ void emig_publish(const Params& p, int tick) {
 #endif
 }
 
-// Immigrants: a fresh slot each, then onto their lane's inbox like any local mover.  One launch for all
-// neighbours: blockIdx.y is the rank the records came from.
-__global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
-  grid_dependency_wait();
+// Immigrants: a fresh slot each, then onto their lane's inbox like any local mover; `src` is the rank the records came
+// from, `blk` of `n_blocks` this block's share of them.  Nothing here meets what k_unlink touches (fresh slots are in no
+// list; inbox heads and list tails are different words), so with one process per GPU these run as the last blocks of
+// k_unlink and the wait for the neighbours' flags hides behind it; with all ranks on one GPU it is the kernel k_immig_unpack.
+__device__ __forceinline__ void immig_unpack_block(const Params& p, const int tick, const int src, const int blk, const int n_blocks) {
   const int par = tick & 1;
-  TRACE(p, tick, TR_IMMIG_UNPACK);
-  const uint8_t* area = (const uint8_t*)p.mig_mine[blockIdx.y][par];
+  const uint8_t* area = (const uint8_t*)p.mig_mine[src][par];
   if (!area) return;
   const MigHeader* h = (const MigHeader*)area;
   if (threadIdx.x == 0) wait_flag(p, &h->flag, tick + 1);   // the sender's flag: all its records of this tick are in my memory
   __syncthreads();
 #ifdef GRIDDY_TRACE
-  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {   // the later of the neighbours' flags
+  if (p.trace && blk == 0 && threadIdx.x == 0) {   // the later of the neighbours' flags
     unsigned long long t_;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
     atomicMax(&p.trace[(tick & 63) * TR_COUNT + TR_IMMIG_GO], t_);
   }
 #endif
-  const int32_t n = min(ld_acquire_sys(&h->count), p.mig_in[blockIdx.y]);
+  const int32_t n = min(ld_acquire_sys(&h->count), p.mig_in[src]);
   const MigRec* recs = (const MigRec*)(area + sizeof(MigHeader));
-  const AgendaItem* payload = (const AgendaItem*)(area + sizeof(MigHeader) + (size_t)p.mig_in[blockIdx.y] * sizeof(MigRec));
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const AgendaItem* payload = (const AgendaItem*)(area + sizeof(MigHeader) + (size_t)p.mig_in[src] * sizeof(MigRec));
+  for (int32_t i = blk * blockDim.x + threadIdx.x; i < n; i += n_blocks * blockDim.x) {
     const MigRec r = recs[i];
     const int32_t a = atomicAdd(&p.scal[SC_NSLOTS], 1);
     const int32_t it = atomicAdd(&p.scal[SC_NITEMS], r.n_items);
@@ -251,6 +256,12 @@ __global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {
     if (k.inbox_next < 0) p.touched[atomicAdd(&p.counters[CNT_STRIDE * par + CNT_ENTERED], 1)] = r.container;
     else atomicOr(&lr->meta, META_MULTI);
   }
+}
+
+__global__ void __launch_bounds__(128) k_immig_unpack(Params p, int tick) {   // blockIdx.y: the rank they came from
+  grid_dependency_wait();
+  TRACE(p, tick, TR_IMMIG_UNPACK);
+  immig_unpack_block(p, tick, (int)blockIdx.y, (int)blockIdx.x, (int)gridDim.x);
 }
 
 }  // namespace griddy

@@ -114,14 +114,15 @@ struct __align__(16) LaneRec {
   int32_t link;           // segment lane: its segment; junction lane: the lane it leads onto; segment: outer forw-side lane
   int32_t link2;          // junction lane: its junction; segment: outer back-side lane
   int32_t to_j;           // grid routing: junction a segment lane reaches
-  uint32_t meta;          // kind (bits 0-2), direction (bit 3); bit 16: several entrants were pushed this tick (reset by k_link)
+  uint32_t meta;          // kind (bits 0-2), direction (bit 3); bit 16: several entrants were pushed this tick (reset by k_link); bit 17: META_TOJ_REMOTE
   double e_pos;           // the new pos-param of this tick's entrant (k_link reads it instead of the entrant's own when there is one)
   int32_t tail;           // rearmost actor; on a partitioned world -2 - k marks a lane another rank owns
   int32_t inbox, outbox, ghosts;   // this tick's entrants (chained through Cold); outbox, ghosts: unused
   int32_t turn[4];        // grid routing: junction lane leading onto the segment that leaves this lane's end with heading h
 };
 static_assert(sizeof(LaneRec) == 64, "one line per item");
-constexpr uint32_t META_KIND = 7u, META_DIR = 8u, META_MULTI = 1u << 16;
+constexpr uint32_t META_KIND = 7u, META_DIR = 8u, META_MULTI = 1u << 16,
+                   META_TOJ_REMOTE = 1u << 17;   // partitioned world, segment lanes: another rank owns the junction the lane reaches
 __host__ __device__ __forceinline__ int meta_kind(uint32_t m) { return (int)(m & META_KIND); }
 __host__ __device__ __forceinline__ uint32_t meta_dir(uint32_t m) { return (m >> 3) & 1u; }
 
@@ -180,6 +181,9 @@ struct Params {
   const int32_t* halo_items; // my export list: my lane, or ~(my junction), the neighbours' parts back to back
   int32_t halo_total;        //   its length
   int32_t* halo_done;        // halo blocks of k_advance that have finished (the last one raises the flags)
+  const int32_t* imp_junc;   // the neighbours' junctions whose occupancy gates my actors, and where in halo_recv each arrives
+  const int32_t* imp_where;
+  int32_t n_imp_junc;
   int32_t mig_cap[MAX_RANKS];     // by destination rank: records per tick
   int32_t mig_icap[MAX_RANKS];    //   and agenda items per tick
   // by destination rank and tick parity: that rank's receive area for my emigrants, in ITS window:

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_item_set_grid(LaneRec* __restrict__ lan
 __global__ void __launch_bounds__(256) k_lane_init(LaneRec* __restrict__ lane, int64_t n) {
   const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (r >= n) return;
-  lane[r].meta &= META_KIND | META_DIR;
+  lane[r].meta &= META_KIND | META_DIR | META_TOJ_REMOTE;   // (the partition's mark belongs to the network)
   *(int4*)&lane[r].tail = make_int4(-1, -1, -1, -1);
 }
 
@@ -48,6 +48,17 @@ __global__ void __launch_bounds__(256) k_lane_set_tail(LaneRec* __restrict__ lan
                                                         const int32_t* __restrict__ tail, int64_t m) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i < m) lane[which[i]].tail = tail[i];
+}
+
+// Partitioned world: mark the lanes (ids in `which`) that reach a junction another rank owns, so that a lane change
+// knows it from the target lane's record instead of a gather into the owner table.
+__global__ void __launch_bounds__(256) k_lane_clear_remote(LaneRec* __restrict__ lane, int64_t m) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < m) lane[i].meta &= ~META_TOJ_REMOTE;
+}
+__global__ void __launch_bounds__(256) k_lane_mark_remote(LaneRec* __restrict__ lane, const int32_t* __restrict__ which, int64_t m) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < m) lane[which[i]].meta |= META_TOJ_REMOTE;
 }
 
 }  // namespace griddy
