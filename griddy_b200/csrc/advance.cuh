@@ -29,10 +29,10 @@ __device__ __forceinline__ int32_t grid_next_hop(const Params& p, const LaneRec&
 
 // Head of the route after the actor has reached `lane` (route.scm:48-51 evaluated lazily); `it` is
 // lane's record, k holds the route's destination.
-__device__ __forceinline__ int32_t route_head_on(const Params& p, int32_t lane, const LaneRec& it, const Cold& k, int32_t item, int32_t* rc) {
-  if (p.route_off) {
-    const int64_t c = *rc;
-    return c < p.route_off[item + 1] ? p.route_lane[c] : HOP_ARRIVE;
+__device__ __forceinline__ int32_t route_head_on(const Params& p, int32_t lane, const LaneRec& it, const Cold& k, int32_t* rc) {
+  if (p.route_off) {   // (k.dest_from_j: where the route ends in route_lane)
+    const int32_t c = *rc;
+    return c < k.dest_from_j ? p.route_lane[c] : HOP_ARRIVE;
   }
   if (lane == k.dest_lane) return HOP_ARRIVE;
   if (meta_kind(it.meta) == GRIDDY_JUNCTION_LANE) return it.link;
@@ -155,7 +155,7 @@ __device__ __forceinline__ double turn_onto(const Params& p, const int a, const 
     }
   }
   int32_t rc = p.route_off ? k.route_cur + 1 : 0;
-  const int32_t nhop = route_head_on(p, target, it, k, k.agenda_cur, &rc);
+  const int32_t nhop = route_head_on(p, target, it, k, &rc);
   // (ahead / behind stay: k_unlink reads them.  atomicOr: a follower may be flagging this actor as a ghost right now)
   const uint32_t more = ST_MOVED | ST_REDRAW | (nhop == HOP_ARRIVE ? ST_ARRIVE : 0u);
   const uint32_t st_before = atomicOr(&p.hot[a].st, more | (remote ? ST_EMIG : 0u));
@@ -275,12 +275,12 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
     // off-road->on-road  location.scm:49-57
     const double init_pos = meta_dir(init_it.meta) ? __dsub_rn(1.0, cur) : cur;
     const double dest_pos = ai.dpos;
-    int32_t rc = p.route_off ? (int32_t)p.route_off[item] : 0;
+    int32_t rc = p.route_off ? (int32_t)p.route_off[ai.rid] : 0;
     Cold k = p.cold[a];
     k.dest_lane = dest_lane;
-    k.dest_from_j = ai.dfrom;
+    k.dest_from_j = p.route_off ? (int32_t)p.route_off[ai.rid + 1] : ai.dfrom;
     k.dest_to_j = ai.dto;
-    const int32_t hop = route_head_on(p, init_lane, init_it, k, item, &rc);
+    const int32_t hop = route_head_on(p, init_lane, init_it, k, &rc);
     if (hop == -2) { dev_error(p, DEV_ERR_NO_ROUTE); return cur; }   // find-route found no path (a* throws 'no-path)
     const double len = init_it.len;
     p.coldf[a].arrive = dest_pos;

@@ -234,6 +234,11 @@ struct Ctx {
   int64_t g_edges = 0;
   std::vector<int64_t> h_route_off;     // the routes the last upload_actors used (given or computed), for griddy_download_routes
   std::vector<int32_t> h_route_lane;
+  // explicit routes on a partitioned world (griddy_mg_set_routes): the whole world's table, and the route of every
+  // agenda item of the next upload
+  std::vector<int64_t> mg_route_off;
+  std::vector<int32_t> mg_route_lane, mg_item_route;
+  bool have_mg_routes = false;
   AgendaItem* agenda_alt = nullptr;   // second item pool: a reorder of a partitioned world compacts into it
   int32_t* d_nitems_new = nullptr;
   Multi mg;
@@ -346,6 +351,10 @@ void mg_reset(Ctx* c) {
   if (m.ev_ready) cudaEventDestroy(m.ev_ready);
   m = Multi();
   c->mg_owner_host.clear();
+  c->have_mg_routes = false;
+  c->mg_route_off.clear();
+  c->mg_route_lane.clear();
+  c->mg_item_route.clear();
   Params& p = c->p;
   p.owner = nullptr;
   p.halo_recv[0] = p.halo_recv[1] = nullptr;
@@ -1001,7 +1010,11 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   if (n_agenda < 0 || n_agenda > INT32_MAX - 1) return fail(c, GRIDDY_ERR_BAD_ARG, "too many agenda items");
   if (n_agenda > 0 && (!item_kind || !item_sleep || !item_seg || !item_side || !item_pos))
     return fail(c, GRIDDY_ERR_BAD_ARG, "upload_actors: null agenda arrays");
-  if (!route_off && c->p.grid_n == 0 && !c->g_nbr_off)
+  const bool table_routes = c->mg.on && c->have_mg_routes && !route_off;   // routes by index into the replicated table
+  if (table_routes && (int64_t)c->mg_item_route.size() != n_agenda)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "griddy_mg_set_routes was given " + std::to_string(c->mg_item_route.size()) +
+                                           " items, the agendas hold " + std::to_string(n_agenda));
+  if (!route_off && !table_routes && c->p.grid_n == 0 && !c->g_nbr_off)
     return fail(c, GRIDDY_ERR_BAD_ARG, "no routes uploaded, no route graph (griddy_set_route_graph) and no grid routing table set");
   const Params& q = c->p;
   const Tiling& tl = c->tl;
@@ -1027,6 +1040,7 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     memset(&ai, 0, sizeof(ai));
     ai.dlane = ai.dfrom = ai.dto = -1;
     ai.kind = item_kind[k];
+    ai.rid = (int32_t)k;   // one GPU: the routes are uploaded per item
     if (item_kind[k] == GRIDDY_SLEEP_FOR) {
       ai.sleep = item_sleep[k];
     } else if (item_kind[k] == GRIDDY_TRAVEL_TO) {
@@ -1075,10 +1089,22 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     c->h_route_off.assign(route_off, route_off + n_agenda + 1);
     c->h_route_lane.assign(route_lane, route_lane + route_off[n_agenda]);
   }
+  int64_t n_routes = n_agenda;   // entries of the route table the device gets
+  if (table_routes) {
+    route_off = c->mg_route_off.data();
+    route_lane = c->mg_route_lane.data();
+    n_routes = (int64_t)c->mg_route_off.size() - 1;
+    for (int64_t k = 0; k < n_agenda; ++k) {
+      if (item_kind[k] != GRIDDY_TRAVEL_TO) continue;
+      const int32_t rid = c->mg_item_route[(size_t)k];
+      if (rid < 0 || rid >= n_routes) return fail(c, GRIDDY_ERR_BAD_ARG, "agenda item " + std::to_string(k) + ": route index out of range");
+      agenda[(size_t)k].rid = rid;
+    }
+  }
   if (route_off) {
-    if (route_off[n_agenda] > 0 && !route_lane) return fail(c, GRIDDY_ERR_BAD_ARG, "route_lane is null");
-    if (route_off[n_agenda] > INT32_MAX - 1) return fail(c, GRIDDY_ERR_BAD_ARG, "too many route steps");
-    for (int64_t k = 0; k < route_off[n_agenda]; ++k) {
+    if (route_off[n_routes] > 0 && !route_lane) return fail(c, GRIDDY_ERR_BAD_ARG, "route_lane is null");
+    if (route_off[n_routes] > INT32_MAX - 1) return fail(c, GRIDDY_ERR_BAD_ARG, "too many route steps");
+    for (int64_t k = 0; k < route_off[n_routes]; ++k) {
       const int32_t l = route_lane[k];
       if (l == -2) continue;   // 'no-path, reported when the actor gets there
       const uint8_t kd = (l >= 0 && l < q.n_items) ? c->kind_of(l) : (uint8_t)254;
@@ -1100,7 +1126,9 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
   Params& p = c->p;
   p.n_actors = n;
   const int64_t extra = c->mg.on ? c->mg.extra_slots : 0;   // room for actors arriving from other ranks
-  if (c->mg.on && route_off) return fail(c, GRIDDY_ERR_BAD_ARG, "multi-GPU worlds need the grid routing table, not uploaded routes");
+  if (c->mg.on && route_off && !table_routes)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "a partitioned world takes explicit routes through griddy_mg_set_routes (every rank holds the whole table), not per item");
+  if (table_routes && tl.tiled()) return fail(c, GRIDDY_ERR_BAD_ARG, "explicit routes on a partitioned world need the whole network on every rank (no griddy_set_item_ranges)");
   const int64_t extra_items = extra * std::max(c->mg.max_agenda_items, 1);
   if (n + extra > INT32_MAX - 2 * rsort::TILE || n_agenda + extra_items > INT32_MAX - 1)
     return fail(c, GRIDDY_ERR_BAD_ARG, "too many slots");
@@ -1235,8 +1263,8 @@ int griddy_upload_actors(void* ctx, int64_t n, const uint8_t* loc_kind, const in
     TRY(dev_alloc(c, pool, &c->d_nitems_new, 1));
   }
   if (route_off) {
-    TRY(dev_upload(c, pool, &p.route_off, route_off, n_agenda + 1));
-    TRY(dev_upload(c, pool, &p.route_lane, route_lane, route_off[n_agenda]));
+    TRY(dev_upload(c, pool, &p.route_off, route_off, n_routes + 1));
+    TRY(dev_upload(c, pool, &p.route_lane, route_lane, route_off[n_routes]));
   } else {
     p.route_off = nullptr;
     p.route_lane = nullptr;
@@ -1848,7 +1876,6 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
   if (!c->have_net) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure before upload_network");
   if (world < 1 || world > MAX_RANKS || rank < 0 || rank >= world || !owner || !lane_in || mig_cap < 1 || extra_slots < 0 || max_agenda_items < 0)
     return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure: bad arguments");
-  if (c->p.grid_n == 0) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_configure needs the grid routing table (griddy_set_routing_grid)");
   CUDA_TRY(c, cudaSetDevice(c->device));
   const Tiling& tl = c->tl;
   const int64_t n_local = tl.n_local;
@@ -1988,6 +2015,23 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
   p.halo_total = m.n_exp;
   p.my_rank = rank;
   m.connected = m.nb.empty();
+  return GRIDDY_OK;
+}
+
+int griddy_mg_set_routes(void* ctx, int64_t n_routes, const int64_t* route_off, const int32_t* route_lane, int64_t n_items,
+                         const int32_t* item_route) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return GRIDDY_ERR_BAD_ARG;
+  if (!c->mg.on) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_set_routes before mg_configure");
+  if (n_routes < 0 || n_items < 0 || !route_off || (n_items > 0 && !item_route) || route_off[0] != 0)
+    return fail(c, GRIDDY_ERR_BAD_ARG, "mg_set_routes: bad arguments");
+  for (int64_t k = 0; k < n_routes; ++k)
+    if (route_off[k + 1] < route_off[k]) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_set_routes: route_off not monotone");
+  if (route_off[n_routes] > 0 && !route_lane) return fail(c, GRIDDY_ERR_BAD_ARG, "mg_set_routes: route_lane is null");
+  c->mg_route_off.assign(route_off, route_off + n_routes + 1);
+  c->mg_route_lane.assign(route_lane, route_lane + route_off[n_routes]);
+  c->mg_item_route.assign(item_route, item_route + n_items);
+  c->have_mg_routes = true;
   return GRIDDY_OK;
 }
 

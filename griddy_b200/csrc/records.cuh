@@ -88,7 +88,8 @@ struct __align__(16) Cold {
   // first sector
   int32_t container;                  // lane (on road) or segment (off road)
   int32_t hop;                        // head of the route: lane of (turn-onto lane), or -1 for (arrive-at _)
-  int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions
+  int32_t dest_lane, dest_from_j, dest_to_j;   // grid routing: the route's last lane and its junctions;
+                                      // explicit routes: dest_from_j = end of the current route in Params::route_lane
   int32_t mv_old;                     // where a mover came from: lane, or ~segment
   int32_t inbox_next, outbox_next;    // this tick's entrants of a lane, chained (outbox_next: unused)
   // second sector
@@ -136,7 +137,8 @@ struct __align__(16) AgendaItem {
   int32_t dlane;          // travel-to: destination lane, -1: the road has no lanes on that side
   int32_t dfrom, dto;     // travel-to: junctions dlane leaves / reaches (-1 without a grid routing table)
   uint32_t kind;          // GRIDDY_SLEEP_FOR / GRIDDY_TRAVEL_TO
-  int32_t pad;
+  int32_t rid;            // travel-to with explicit routes: its route in Params::route_off (the item's own index on one GPU; an
+                          // index into the table every rank holds on a partitioned world — it travels with the item)
 };
 static_assert(sizeof(AgendaItem) == 32, "one sector per agenda item");
 
@@ -158,7 +160,7 @@ struct Params {
   int64_t n_actors;
   AgendaItem* agenda;
   int32_t icap;   // item capacity
-  const int64_t* route_off;   // null: grid routing table
+  const int64_t* route_off;   // explicit routes, by AgendaItem::rid (null: grid routing table)
   const int32_t* route_lane;
   // per-tick scratch, by slot
   int32_t* touched;   // lanes an actor entered this tick (k_link's work list)

@@ -32,7 +32,7 @@ SYMBOLS = ("griddy_abi_version", "griddy_create", "griddy_destroy", "griddy_last
            "griddy_mg_ipc_import", "griddy_upload_geometry", "griddy_download_positions", "griddy_positions_begin",
            "griddy_positions_end", "griddy_host_alloc", "griddy_host_free", "griddy_debug_trace", "griddy_state_digest",
            "griddy_delta_frame_bytes", "griddy_delta_begin", "griddy_delta_end", "griddy_delta_apply", "griddy_last_frame_ms",
-           "griddy_last_copy_ms")
+           "griddy_last_copy_ms", "griddy_mg_set_routes")
 
 
 class GriddyCudaError(RuntimeError):
@@ -116,7 +116,9 @@ class Simulation:
         self._frames = []
         if reorder_period is not None:
             self._chk(L.griddy_set_reorder_period(self.h, C.c_int32(reorder_period)))
-        if actors.route_off is None and net.nbr_off is not None and not net.grid_n:
+        if actors.route_table_off is not None:
+            pass   # a partitioned world with explicit routes: the table goes in after griddy_mg_configure
+        elif actors.route_off is None and net.nbr_off is not None and not net.grid_n:
             # find-route on the device: the lane graph of route.scm:19-40
             self._chk(L.griddy_set_route_graph(self.h, _p(net.nbr_off), _p(net.nbr), _p(net.cost_out), _p(net.midpoint)))
         elif actors.route_off is None:
@@ -139,6 +141,9 @@ class Simulation:
 
     def upload_actors(self, a: FlatActors):
         self.actors = a
+        if a.route_table_off is not None:
+            self._chk(lib().griddy_mg_set_routes(self.h, C.c_int64(len(a.route_table_off) - 1), _p(a.route_table_off),
+                                                 _p(a.route_table_lane), C.c_int64(len(a.item_route)), _p(a.item_route)))
         if a.dest_lane is not None:   # destinations resolved by the generator (needed on a tiled network)
             self._chk(lib().griddy_set_agenda_destinations(self.h, C.c_int64(a.n_agenda_items), _p(a.dest_lane), _p(a.dest_dir),
                                                            _p(a.dest_from_j), _p(a.dest_to_j)))
@@ -464,12 +469,14 @@ def subset_actors(a: FlatActors, idx: np.ndarray) -> FlatActors:
     off = np.zeros(len(idx) + 1, np.int64)
     np.cumsum(lens, out=off[1:])
     items = np.repeat(beg - off[:-1], lens) + np.arange(off[-1]) if len(idx) else np.zeros(0, np.int64)
-    if a.route_off is not None:
-        raise ValueError("partitioned worlds use the grid routing table, not uploaded routes")
+    routes = {}
+    if a.route_off is not None:   # explicit routes: every rank gets the whole table, its items name their routes in it
+        routes = dict(route_table_off=a.route_off, route_table_lane=a.route_lane, item_route=items.astype(np.int32))
     dest = {} if a.dest_lane is None else dict(dest_lane=a.dest_lane[items], dest_dir=a.dest_dir[items],
                                                dest_from_j=a.dest_from_j[items], dest_to_j=a.dest_to_j[items])
     return FlatActors(a.loc_kind[idx], a.container[idx], a.pos[idx], a.side[idx], a.speed[idx], a.speed_dt[idx], off,
-                      a.item_kind[items], a.item_sleep[items], a.item_seg[items], a.item_side[items], a.item_pos[items], **dest)
+                      a.item_kind[items], a.item_sleep[items], a.item_seg[items], a.item_side[items], a.item_pos[items], **dest,
+                      **routes)
 
 
 def with_destinations(net: FlatNetwork, a: FlatActors) -> FlatActors:

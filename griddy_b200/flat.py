@@ -146,6 +146,11 @@ class FlatActors:
     dest_dir: Optional[np.ndarray] = None    # u8  that lane's direction
     dest_from_j: Optional[np.ndarray] = None # i32 junction it leaves (grid routing)
     dest_to_j: Optional[np.ndarray] = None   # i32 junction it reaches
+    # optional, one rank's actors of a partitioned world with explicit routes (griddy_mg_set_routes): the WHOLE world's
+    # route table and, per agenda item of these actors, its route in it
+    route_table_off: Optional[np.ndarray] = None    # i64 [n_routes+1]
+    route_table_lane: Optional[np.ndarray] = None   # i32
+    item_route: Optional[np.ndarray] = None         # i32 [n_agenda_items]
 
     def __post_init__(self):
         self.loc_kind = _arr(self.loc_kind, np.uint8)
@@ -163,6 +168,10 @@ class FlatActors:
         if self.route_off is not None:
             self.route_off = _arr(self.route_off, np.int64)
             self.route_lane = _arr(self.route_lane if self.route_lane is not None else [], np.int32)
+        if self.route_table_off is not None:
+            self.route_table_off = _arr(self.route_table_off, np.int64)
+            self.route_table_lane = _arr(self.route_table_lane if self.route_table_lane is not None else [], np.int32)
+            self.item_route = _arr(self.item_route, np.int32)
         if self.dest_lane is not None:
             self.dest_lane = _arr(self.dest_lane, np.int32)
             self.dest_dir = _arr(self.dest_dir, np.uint8)

@@ -240,8 +240,8 @@ void griddy_host_free(void* ptr);
  * halo: for every lane a neighbour's actors can enter, its rearmost positive pos-param
  * (route.scm:118-121), and for every such junction its occupancy (route.scm:98-104), both of the OLD
  * world; (2) the actors that crossed, each as a 128-byte record plus its agenda items not yet popped
- * (32 bytes each; any number).  Results are identical to a single-GPU run of the same world.  Requires
- * the grid routing table.
+ * (32 bytes each; any number).  Results are identical to a single-GPU run of the same world.  Routes come
+ * from the grid routing table or from griddy_mg_set_routes.
  *
  * Data plane: every rank owns a WINDOW of device memory that its neighbours' kernels write into directly
  * (peer stores over NVLink / NVSwitch) and then flag; the reader's next kernel waits for the flag.  No
@@ -265,6 +265,14 @@ int griddy_mg_configure(void* ctx, int32_t rank, int32_t world, const int32_t* o
                         int64_t extra_slots /* room for actors that arrive from other ranks */,
                         int32_t max_agenda_items /* sizes the room for migrants' agenda items: records per tick x this */);
 int griddy_mg_set_global_ids(void* ctx, const int32_t* gid /* one per uploaded actor, ascending */);
+/* Explicit routes on a partitioned world (instead of the grid routing table): the routes of EVERY travel-to item of the
+ * whole world — route_off [n_routes + 1] / route_lane as for griddy_upload_actors — are given to every rank, and
+ * item_route [n_items] names, for each agenda item of the actors this rank uploads next, its route in that table
+ * (ignored for sleep-for items).  An actor that crosses to another rank takes its items' route indices along, so
+ * nothing of a route ever travels.  Call after griddy_mg_configure and before griddy_upload_actors, which is then
+ * given route_off = NULL.  Whole networks only (no griddy_set_item_ranges). */
+int griddy_mg_set_routes(void* ctx, int64_t n_routes, const int64_t* route_off, const int32_t* route_lane, int64_t n_items,
+                         const int32_t* item_route);
 int griddy_mg_neighbors(void* ctx, int32_t* ranks /* MAX 8, may be NULL */, int32_t* n);
 /* blob128: the cudaIpc handle of my window (64 bytes), the byte offsets of the six places `from_rank` writes in it
  * (int64: halo values, halo flag, migrant area; by tick parity) and the sizes I expect of it (2 x int32). */

@@ -87,6 +87,42 @@ def test_explicit_routes_from_host_a_star():
     run_pair(net, actors, 1200, every=10)
 
 
+@pytest.mark.parametrize("world,strips", [(2, 1), (3, 2)])
+def test_partitioned_world_with_explicit_routes(world, strips):
+    """Routes from the host's A* on a partitioned world: every rank holds the whole route table (griddy_mg_set_routes),
+    an actor that crosses takes its items' route indices and its place in the current route along."""
+    import random
+    from griddy_b200 import synth
+    rng = random.Random(11)
+    n = 6
+
+    def add_actors(w):
+        segs = core.get_static_items(w, core.RoadSegment)
+        loc = lambda: core.LocationOffRoad(rng.choice(segs), rng.choice(["forw", "back"]), 0.25 + 0.5 * rng.random())
+        for _ in range(400):
+            a = core.Actor(max_speed=30 + rng.randrange(30))
+            core.link(a, loc())
+            core.agenda_push(a, ("sleep-for", rng.randrange(12)))
+            for _ in range(3):
+                core.agenda_push(a, ("travel-to", loc()))
+    net, actors = world_to_flat(lambda: examples.grid_make_skeleton(n), add_actors)
+    assert actors.route_off is not None and len(actors.route_lane) > 0
+    owner = synth.grid_owner(synth.grid_network(n), world, strips)   # (the generator's ids are the API mirror's: test_host.py)
+    sim = device.PartitionedSimulation(net, actors, owner, world, reorder_period=7)
+    ref = Oracle(net, actors)
+    crossed = 0
+    for t in range(700):
+        sim.step(1); ref.step(1)
+        ds, os_ = sim.state(), ref.state()
+        bad = ds.diff(os_)
+        assert not bad, f"world {world} tick {t + 1}: partitioned device with explicit routes differs from oracle in {bad}"
+        m = ds.alive.astype(bool)
+        assert np.array_equal(ds.pos[m], os_.pos[m]), f"tick {t + 1}: pos not bit-identical"
+        crossed += int((owner[ds.container[m]] != owner[actors.container[m]]).sum() > 0)
+    assert crossed > 0, "no actor ever crossed a partition boundary"
+    assert digest.combine([r.digest() for r in sim.ranks]) == digest.commutative(os_)
+
+
 def test_empty_world_and_empty_agendas():
     net, actors = grid_flat(3, 0)
     sim = device.Simulation(net, actors)
