@@ -27,7 +27,8 @@
   #:use-module (chickadee math vector)
   #:use-module (chickadee math bezier)
   #:export (cuda-open cuda-close cuda-upload-world! cuda-step! cuda-step-async! cuda-download-world!
-            cuda-last-step-ms cuda-positions make-frame-buffer cuda-frame-begin! cuda-frame-end!))
+            cuda-last-step-ms cuda-positions make-frame-buffer cuda-frame-begin! cuda-frame-end!
+            make-delta-buffer cuda-delta-begin! cuda-delta-end! cuda-delta-apply!))
 
 (define %lib (dynamic-link (or (getenv "GRIDDY_CUDA_LIB") "libgriddy_cuda")))
 
@@ -49,6 +50,10 @@
 (define %positions (c-fn "griddy_download_positions" int '* int64 '* '* '* '*))
 (define %frame-begin (c-fn "griddy_positions_begin" int '* '* int64))
 (define %frame-end (c-fn "griddy_positions_end" int '* '*))
+(define %delta-bytes (c-fn "griddy_delta_frame_bytes" int64 int64))
+(define %delta-begin (c-fn "griddy_delta_begin" int '* '* int64))
+(define %delta-end (c-fn "griddy_delta_end" int '* '* '*))
+(define %delta-apply (c-fn "griddy_delta_apply" int '* '* int64))
 (define %host-alloc (c-fn "griddy_host_alloc" '* int64))
 (define %slots    (c-fn "griddy_slots_in_use" int64 '*))
 
@@ -332,3 +337,25 @@ caller may run cuda-step! meanwhile; at most two frames are in flight."
   (let ((n (make-i64 1)))
     (check ctx (%frame-end ctx (ptr n)))
     (bytevector-s64-native-ref n 0)))
+
+;;; Delta frames (include/griddy_cuda.h, "Delta frames"): a frame holds only the actors whose drawn position
+;;; changed since the frame before; the painter keeps one bytevector of float pairs per slot and patches it.
+(define (make-delta-buffer capacity)
+  "Page-locked host memory for one delta frame over CAPACITY slots, as a bytevector."
+  (let ((bytes (%delta-bytes capacity)))
+    (pointer->bytevector (%host-alloc bytes) bytes)))
+
+(define (cuda-delta-begin! ctx buffer capacity)
+  "Start formatting and reading back the delta frame of the current tick into BUFFER; returns at once."
+  (check ctx (%delta-begin ctx (ptr buffer) capacity)))
+
+(define (cuda-delta-end! ctx)
+  "Wait for the oldest delta frame begun; returns (values slots-covered positions-changed)."
+  (let ((n (make-i64 1)) (changed (make-i64 1)))
+    (check ctx (%delta-end ctx (ptr n) (ptr changed)))
+    (values (bytevector-s64-native-ref n 0) (bytevector-s64-native-ref changed 0))))
+
+(define (cuda-delta-apply! buffer xy)
+  "Patch XY, the painter's bytevector of float pairs (one per slot, NaN: nothing to draw), with the frame in BUFFER."
+  (let ((rc (%delta-apply (ptr buffer) (ptr xy) (quotient (bytevector-length xy) 8))))
+    (unless (zero? rc) (throw 'griddy-cuda rc "griddy_delta_apply: malformed frame or array too small"))))
