@@ -338,6 +338,9 @@ __device__ __forceinline__ double advance_actor(const Params& p, const int a, co
 #ifndef ADV_UNROLL
 #define ADV_UNROLL 2
 #endif
+#ifndef ADV_LD256   // the hot record as one 256-bit load (1), with L2 evict-first priority (2)
+#define ADV_LD256 0
+#endif
 #ifndef ADV_THREADS_N
 #define ADV_THREADS_N 128
 #endif
@@ -382,8 +385,16 @@ __global__ void ADV_BOUNDS k_advance(Params p, int tick, int halo_blocks, int un
   for (int k = 0; k < ADV_UNROLL; ++k) {
     const int a = base + k * ADV_THREADS;
     const bool in = a < n;
-    const int4 h0 = in ? hot4[2 * (size_t)a] : make_int4(0, -1, -1, -1);            // st, ahead, behind, tj
-    const int4 h1 = in ? hot4[2 * (size_t)a + 1] : make_int4(0, 0, 0, 0);           // delta, buf (same sector)
+    int4 h0 = make_int4(0, -1, -1, -1), h1 = make_int4(0, 0, 0, 0);   // st, ahead, behind, tj; delta, buf (one sector)
+#if ADV_LD256 == 0
+    if (in) { h0 = hot4[2 * (size_t)a]; h1 = hot4[2 * (size_t)a + 1]; }
+#elif ADV_LD256 == 1
+    if (in) asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(h0.x), "=r"(h0.y), "=r"(h0.z), "=r"(h0.w),
+                         "=r"(h1.x), "=r"(h1.y), "=r"(h1.z), "=r"(h1.w) : "l"(hot4 + 2 * (size_t)a));
+#else
+    if (in) asm volatile("ld.global.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(h0.x), "=r"(h0.y), "=r"(h0.z), "=r"(h0.w),
+                         "=r"(h1.x), "=r"(h1.y), "=r"(h1.z), "=r"(h1.w) : "l"(hot4 + 2 * (size_t)a));
+#endif
     st[k] = (uint32_t)h0.x;
     ah[k] = h0.y;
     tj[k] = h0.w;
@@ -489,7 +500,7 @@ __global__ void SLOW_BOUNDS k_slow(Params p, int tick) {
     for (int k = threadIdx.x; k < nl; k += SLOW_THREADS) p.leavers[s_base_l + k] = s_left[k];
     if (threadIdx.x < ne) p.touched[s_base_e + threadIdx.x] = s_entered[threadIdx.x];
   }
-  if (p.owner) emig_publish(p, tick);   // partitioned world: the block that finishes last raises the migrant flags
+  if (p.owner && !p.publish_late) emig_publish(p, tick);   // partitioned world: the block that finishes last raises the migrant flags
 }
 
 }  // namespace griddy

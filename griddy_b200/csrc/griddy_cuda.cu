@@ -1452,6 +1452,7 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
     TRY(tick_unlink(c, tick, ev));
     return tick_link(c, tick, ev);
   }
+  c->p.publish_late = 1;                          // (the first block of k_unlink raises the migrant flags)
   TRY(tick_advance(c, tick, ev, true));           // its first blocks send the halo, which travels while the rest run; its last take the neighbours' in
   TRY(tick_slow(c, tick, ev));                    // movers that cross write themselves into the neighbours' windows
   TRY(tick_unlink(c, tick, ev, true));            // its last blocks wait for the neighbours' migrant flags and unpack the arrivals
@@ -1464,6 +1465,7 @@ int launch_tick(Ctx* c, int64_t tick, cudaEvent_t* ev) {
 // kernel), so that the flags are always up when a waiting kernel starts — several ranks may share one GPU,
 // where a spinning kernel could otherwise keep the writer from running.
 int local_begin(Ctx* c, int64_t tick, cudaEvent_t* ev) {
+  c->p.publish_late = 0;
   TRY(tick_begin(c, tick, ev));
   return tick_advance(c, tick, ev);   // (its first blocks write the halo into the neighbours' windows)
 }

@@ -69,20 +69,23 @@ __device__ __forceinline__ bool is_leaver(uint32_t st) {
   return (st & (ST_MOVED | ST_GHOST)) || (st & (ST_ALIVE | ST_ONROAD)) != (ST_ALIVE | ST_ONROAD);
 }
 
-// immig_blocks > 0 (a partitioned world, one process per GPU): the last immig_blocks x immig_ranks blocks unpack the
+// immig_blocks > 0 (a partitioned world, one process per GPU): the first immig_blocks x immig_ranks blocks unpack the
 // actors that arrived from the other ranks instead (multi_gpu.cuh, immig_unpack_block).
 __global__ void __launch_bounds__(128) k_unlink(Params p, int tick, int immig_blocks, int immig_ranks) {
   grid_dependency_wait();
   TRACE(p, tick, TR_UNLINK);
   const int par = tick & 1;
-  const int n_blocks = (int)gridDim.x - immig_blocks * immig_ranks;   // blocks that unlink
-  if ((int)blockIdx.x >= n_blocks) {
-    const int k = (int)blockIdx.x - n_blocks;
-    immig_unpack_block(p, tick, k / immig_blocks, k % immig_blocks, immig_blocks);
+  // The FIRST immig_blocks x immig_ranks blocks: block 0 raises my migrant flags (k_slow is complete), then each waits
+  // for its neighbour's — whose block 0 has done the same before it waits for anyone — and unpacks beside the unlinking.
+  const int n_immig = immig_blocks * immig_ranks;
+  if (p.publish_late && blockIdx.x == 0) emig_publish_late(p, tick);
+  if ((int)blockIdx.x < n_immig) {
+    immig_unpack_block(p, tick, (int)blockIdx.x / immig_blocks, (int)blockIdx.x % immig_blocks, immig_blocks);
     return;
   }
+  const int n_blocks = (int)gridDim.x - n_immig;   // blocks that unlink
   const int32_t n_leavers = p.counters[CNT_STRIDE * par + CNT_LEFT];
-  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_leavers; i += n_blocks * blockDim.x) {
+  for (int32_t i = ((int)blockIdx.x - n_immig) * blockDim.x + threadIdx.x; i < n_leavers; i += n_blocks * blockDim.x) {
     const int4 rec = p.leavers[i];            // slot, lane, junction
     const int32_t z = rec.x;
     const int4 h = *(const int4*)&p.hot[z];   // st, ahead, behind, tj: the pointers are the old world's

@@ -151,7 +151,7 @@ __device__ void emigrate(const Params& p, int a, int tick, uint32_t st, const Co
   ((MigRec*)(area + sizeof(MigHeader)))[at] = r;
   AgendaItem* items = (AgendaItem*)(area + sizeof(MigHeader) + (size_t)p.mig_cap[to] * sizeof(MigRec)) + r.item_off;
   for (int32_t q = 0; q < r.n_items; ++q) items[q] = p.agenda[k.agenda_cur + q];
-  __threadfence_system();   // my record before my block's count (emig_publish): only the threads that wrote one pay for it
+  if (!p.publish_late) __threadfence_system();   // my record before my block's count (emig_publish): only the threads that wrote one pay for it
 }
 
 // End of k_slow on a partitioned world, every block: my records before my block's count; the last block publishes.
@@ -170,6 +170,27 @@ __device__ void emig_publish(const Params& p, int tick) {
     st_release_sys(&h->flag, tick + 1);
   }
   if (threadIdx.x == 0) *p.mig_done = 0;
+#ifdef GRIDDY_TRACE
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    p.trace[(tick & 63) * TR_COUNT + TR_EMIG_FLAG] = t_;
+  }
+#endif
+}
+
+// The same from the kernel after k_slow (its first block, all ranks as processes of their own): k_slow is complete, so
+// the counts are final and nothing in k_slow has to count blocks or fence — one system fence here orders every record
+// written by the kernel before, then the headers, then the flags.
+__device__ __forceinline__ void emig_publish_late(const Params& p, int tick) {
+  const int par = tick & 1;
+  if (threadIdx.x < MAX_RANKS && p.mig_peer[threadIdx.x][par]) {
+    __threadfence_system();
+    MigHeader* h = (MigHeader*)p.mig_peer[threadIdx.x][par];
+    h->count = min(atomicExch(&p.mig_count[threadIdx.x], 0), p.mig_cap[threadIdx.x]);
+    h->n_items = min(atomicExch(&p.mig_count[MAX_RANKS + threadIdx.x], 0), p.mig_icap[threadIdx.x]);
+    st_release_sys(&h->flag, tick + 1);
+  }
 #ifdef GRIDDY_TRACE
   if (p.trace && threadIdx.x == 0) {
     unsigned long long t_;

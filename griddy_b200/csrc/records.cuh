@@ -196,6 +196,7 @@ struct Params {
   int32_t mig_in[MAX_RANKS];         // by source rank: records per tick at most
   int32_t* mig_count;                // [2 x MAX_RANKS] places handed out this tick, by destination: records, items
   int32_t* mig_done;                 // blocks of k_slow that have finished (the last one publishes the counts and raises the flags)
+  int32_t publish_late;              // one process per GPU: the first block of k_unlink publishes instead (no count, no fence in k_slow)
   unsigned long long* trace;         // -DGRIDDY_TRACE builds: [64 ticks][16] %globaltimer stamps (griddy_debug_trace)
 };
 
