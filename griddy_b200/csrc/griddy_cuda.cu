@@ -23,7 +23,8 @@
 //   pos[2]   f64 pos-param, ping-pong by tick parity: followers read the old buffer
 //   Cold     64 B per slot, touched only when an actor changes lane, wakes, or starts / ends a route: container, route
 //            head, cached destination, list-surgery links, speed, cursors, actor id;  ColdF: arrive target, landing stamp
-//   LaneRec  64 B per registered item: length, links, this tick's marks and counts, list heads, routing-table row
+//   LaneRec  64 B per registered item: length, links, marks, this tick's entrant (inbox head, its key), rearmost actor,
+//            routing-table row
 //   occ      i32 per junction: actors on its lanes
 // Per-lane order changes only where an actor entered or left a lane this tick; nothing is O(lanes)
 // per tick (lanes outnumber actors 1.5:1 to 4:1 on the grids).
@@ -33,11 +34,13 @@
 //              full junction, asleep, idle).  Coalesced reads of Hot and pos; the leader's pos-param comes from the
 //              block's shared-memory tile or a gather that the slot order keeps close.  Everything else is deferred.
 //   k_slow     one thread per deferred actor: lane changes with carry-over, arrive-at, begin / end of a route, waking,
-//              ghost detection.  Movers are pushed on their target lane's inbox and their old lane's outbox.
-//   k_unlink   one thread per lane an actor left.  Lanes are doubly linked lists: leavers and ghosts are
-//              taken out in O(1) each; actors that are done for the tick are settled.
-//   k_link     one thread per lane an actor entered: entrants are inserted by a short walk up from the rear; an
-//              entrant that lands on an occupied key is resolved exactly as bbtree-set would.
+//              ghost detection.  Movers are pushed on their target lane's inbox (one atomic exchange); every actor that
+//              leaves a lane's list is put on the leaver list.  The lane an actor leaves is not touched.
+//   k_unlink   one thread per leaver.  Lanes are doubly linked lists: the foremost leaver of a run of list neighbours
+//              joins the residents around the run; actors that are done for the tick are settled.
+//   k_link     one thread per lane an actor entered: a lone entrant's key comes with the lane's record and it is linked
+//              behind the lane's rearmost actor with one write of its hot record; several entrants are inserted by a
+//              short walk up from the rear; an entrant that lands on an occupied key is resolved exactly as bbtree-set would.
 //
 // Processing order without a global sort.  "a is processed before b" (world.scm:24-30) is decided
 // from their OLD locations: different containers -> higher registration index first; same lane ->
@@ -50,8 +53,8 @@
 // lane is walked in descending pos-param.  Such ties are always list-adjacent.  They are resolved one
 // tick late at no cost: an
 // actor whose list follower holds an equal key is a GHOST (it is not part of the world any more).
-// Every on-road actor reads its leader's key each tick, sees the tie, flags the ghost (ST_GHOST) and has
-// the lane relinked; whatever the ghost itself did this tick is discarded by k_unlink.
+// Every on-road actor reads its leader's key each tick, sees the tie, flags the ghost (ST_GHOST) and lists it as
+// a leaver; whatever the ghost itself did this tick is discarded by k_unlink.
 // Nothing else can observe a ghost: queries reach the follower first and see the same key, and the
 // junction it may stand on is occupied by the follower as well.  Downloads apply the same rule.
 //
