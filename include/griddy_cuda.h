@@ -332,7 +332,8 @@ int griddy_debug_sort_pairs(uint64_t* keys, uint32_t* vals, int64_t n, int32_t k
 /* Diagnostics, builds with -DGRIDDY_TRACE only (BAD_STATE otherwise): %globaltimer stamps (ns) of the last 64
  * ticks, 16 per tick (row = tick mod 64): starts of k_advance, k_slow, k_unlink, k_link, k_halo_pack,
  * k_halo_unpack, the emigrant packing, the moment its flags are raised, start of k_immig_unpack, the moment the last
- * neighbour's flag was seen; the rest unused.  How the multi-GPU timelines in profiles/ were obtained. */
+ * neighbour's flag was seen; the rest unused (with one process per GPU the halo and the immigrants are taken in by blocks
+ * of k_advance / k_unlink, so the two unpack stamps stay 0).  How the multi-GPU timelines in profiles/ were obtained. */
 int griddy_debug_trace(void* ctx, uint64_t* stamps /* 64 x 16 */);
 
 #ifdef __cplusplus
