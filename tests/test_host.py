@@ -147,3 +147,32 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
                         "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_subset_of_a_routed_world_names_its_routes_in_the_whole_table():
+    """A rank's share of a partitioned world with explicit routes (griddy_mg_set_routes): the whole route table travels
+    to every rank, and each of the rank's agenda items names its own route in it."""
+    import random
+    rng = random.Random(3)
+
+    def add_actors(world):
+        segs = core.get_static_items(world, core.RoadSegment)
+        loc = lambda: core.LocationOffRoad(rng.choice(segs), rng.choice(["forw", "back"]), 0.3 + 0.4 * rng.random())
+        for _ in range(25):
+            a = core.Actor(max_speed=35)
+            core.link(a, loc())
+            core.agenda_push(a, ("sleep-for", 2))
+            core.agenda_push(a, ("travel-to", loc()))
+            core.agenda_push(a, ("travel-to", loc()))
+    net, actors = world_to_flat(lambda: examples.grid_make_skeleton(3), add_actors)
+    mine = np.arange(1, actors.n, 3)
+    part = device.subset_actors(actors, mine)
+    assert part.route_off is None and part.route_table_off is actors.route_off and part.route_table_lane is actors.route_lane
+    assert len(part.item_route) == part.n_agenda_items == int((actors.agenda_off[mine + 1] - actors.agenda_off[mine]).sum())
+    k = 0
+    for a in mine:
+        for item in range(actors.agenda_off[a], actors.agenda_off[a + 1]):
+            assert part.item_route[k] == item and part.item_kind[k] == actors.item_kind[item]
+            lo, hi = actors.route_off[item], actors.route_off[item + 1]
+            assert (hi > lo) == (actors.item_kind[item] == 1 and hi > lo)        # only travel-to items have steps
+            k += 1
